@@ -1,0 +1,147 @@
+/*
+ * b2ndt.h -- C ABI of the B200-native NDT scan-matching / voxel-filter engine (libb2ndt.so).
+ *
+ * This is the drop-in boundary under the reference's plug-in classes.  Each entry point names the
+ * reference interface it replaces (paths relative to /root/reference/lidar_localization/):
+ *
+ *   b2ndt_create / b2ndt_destroy    NDTRegistration ctor + SetRegistrationParam
+ *                                   (src/models/registration/ndt_registration.cpp:12-44)
+ *   b2ndt_set_target                NDTRegistration::SetInputTarget -> pcl::NDT::setInputTarget
+ *                                   (ndt_registration.cpp:46-51; include/.../registration_interface.hpp:18)
+ *   b2ndt_align                     NDTRegistration::ScanMatch -> setInputSource + align + getFinalTransformation
+ *                                   (ndt_registration.cpp:53-61; registration_interface.hpp:19-22)
+ *   b2ndt_fitness                   NDTRegistration::GetFitnessScore -> pcl::Registration::getFitnessScore
+ *                                   (ndt_registration.cpp:63-66; registration_interface.hpp:23)
+ *   b2ndt_align_batch[_device]      the same ScanMatch for many independent (source, guess) pairs against
+ *                                   one target (BASELINE.json configs 4/5; the callers loop ScanMatch per
+ *                                   frame: src/matching/matching.cpp:245-246, front_end.cpp:224-231)
+ *   b2vf_create / b2vf_destroy      VoxelFilter ctor + SetFilterParam (src/models/cloud_filter/voxel_filter.cpp:12-34)
+ *   b2vf_filter                     VoxelFilter::Filter -> pcl::VoxelGrid::filter
+ *                                   (voxel_filter.cpp:36-41; include/.../cloud_filter_interface.hpp:17)
+ *
+ * Conventions: plain pointers and sizes only; return 0 on success, negative b2_status on error
+ * (b2_last_error() gives the message for the calling thread); no C++ exceptions cross the ABI.
+ * A handle is bound to one CUDA device and one stream and is not thread-safe.  There is no CPU
+ * fallback: every entry point fails with B2_ERR_CUDA when no sm_100 device is usable.
+ *
+ * Host clouds are described by (pointer, count, byte stride, byte offset of intensity) so that
+ * pcl::PointXYZI memory (stride 32, xyz at +0, intensity at +16; cloud_data.hpp:35) is consumed in
+ * place.  Device clouds are packed float4 {x,y,z,intensity}.  Poses are column-major float[16]
+ * (Eigen::Matrix4f memory).
+ */
+#ifndef B2NDT_H_
+#define B2NDT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    B2_OK = 0,
+    B2_ERR_INVALID = -1,   /* bad argument */
+    B2_ERR_CUDA = -2,      /* CUDA runtime error / no usable device */
+    B2_ERR_STATE = -3,     /* call order (e.g. align before set_target) */
+    B2_ERR_CAPACITY = -4   /* output buffer too small */
+} b2_status;
+
+const char *b2_last_error(void);
+/* number of kernels launched by this library in the calling process (all handles) */
+uint64_t b2_kernel_launch_count(void);
+int b2_device_count(void);
+
+/* ------------------------------------------------------------------ registration ---------- */
+typedef struct b2ndt b2ndt;
+
+typedef struct {
+    float  res;            /* setResolution           (front_end.yaml:18-22 -> 1.0)  */
+    double step_size;      /* setStepSize             (0.1)                          */
+    double trans_eps;      /* setTransformationEpsilon(0.01)                         */
+    double outlier_ratio;  /* PCL default 0.55                                       */
+    int    max_iter;       /* setMaximumIterations    (30)                           */
+    int    min_pts;        /* min_points_per_voxel_   (PCL default 6)                */
+    double eig_mult;       /* min_covar_eigvalue_mult_(PCL default 0.01)             */
+    int    pcl17_compat;   /* 1 (default): More-Thuente interval guard as in PCL 1.7 (loop never runs
+                              when step_size > trans_eps/2); 0: full line search enabled */
+} b2ndt_params;
+
+typedef struct {
+    int32_t iterations;        /* nr_iterations_ */
+    int32_t converged;
+    double  score;
+    double  trans_probability; /* getTransformationProbability() = score / N */
+    double  p[6];              /* final (x,y,z,roll,pitch,yaw) */
+    int32_t passes;            /* derivative passes executed */
+    int32_t mt_trials;
+    int64_t pairs;             /* (point, voxel) pairs visited over all passes */
+} b2ndt_result;
+
+typedef struct {
+    int32_t ok;                /* 0: empty target or PCL's int32 voxel-index guard tripped */
+    int32_t min_b[3], div_b[3];
+    uint32_t n_points;         /* finite target points */
+    uint32_t n_leaves;         /* occupied voxels */
+    uint32_t n_tree;           /* voxels with >= min_pts points (searchable) */
+    float   inv_leaf;
+} b2ndt_target_info;
+
+void b2ndt_params_default(b2ndt_params *p);
+int  b2ndt_create(const b2ndt_params *p, int device, b2ndt **out);
+void b2ndt_destroy(b2ndt *h);
+/* run on an existing CUDA stream (cudaStream_t) instead of the handle's own; NULL restores it */
+int  b2ndt_set_stream(b2ndt *h, void *cuda_stream);
+int  b2ndt_synchronize(b2ndt *h);
+/* thread-block cluster width per match: 1..16 (single match default 8, batch default 1) */
+int  b2ndt_set_cluster(b2ndt *h, int single_match_ctas, int batch_ctas);
+
+int  b2ndt_set_target(b2ndt *h, const void *pts, size_t n, size_t stride, size_t ioff);
+int  b2ndt_set_target_device(b2ndt *h, const void *d_pts_f4, size_t n);
+int  b2ndt_target_info_get(b2ndt *h, b2ndt_target_info *info);
+/* copy the leaf table to host (ascending voxel index; arrays sized n_leaves, any may be NULL):
+ * idx, n_raw, centroid (4 floats), mean (3 doubles), icov (9 doubles, row-major; zeros when n<min_pts) */
+int  b2ndt_target_leaves(b2ndt *h, int32_t *idx, int32_t *n_raw, float *centroid4, double *mean3, double *icov9);
+
+int  b2ndt_align(b2ndt *h, const void *src, size_t n, size_t stride, size_t ioff, const float guess[16],
+                 float pose_out[16], b2ndt_result *res);
+/* B independent matches against the current target.  Sources are concatenated; offsets has B+1
+ * entries (points).  offsets == NULL: one shared source of n_total points x B guesses. */
+int  b2ndt_align_batch(b2ndt *h, const void *src, size_t n_total, size_t stride, size_t ioff,
+                       const uint32_t *offsets, size_t B, const float *guesses /*B*16*/,
+                       float *poses_out /*B*16*/, b2ndt_result *res /*B, may be NULL*/);
+/* device-resident variant: packed float4 sources, device offsets (B+1, or NULL), device guesses;
+ * results written to device buffers; asynchronous on the handle's stream. */
+int  b2ndt_align_batch_device(b2ndt *h, const void *d_src_f4, size_t n_total, const uint32_t *d_offsets,
+                              size_t B, const float *d_guesses, float *d_poses_out, b2ndt_result *d_res);
+/* one derivative pass at a 6-vector pose (parity gate): H is column-major 6x6 */
+int  b2ndt_derivatives(b2ndt *h, const void *src, size_t n, size_t stride, size_t ioff, const double p[6],
+                       double *score, double grad[6], double H[36], int64_t *pairs);
+/* getFitnessScore of the last b2ndt_align (source + final pose are retained on the device) */
+int  b2ndt_fitness(b2ndt *h, double max_range, double *out);
+/* explicit variant: any source / pose against the current target points */
+int  b2ndt_fitness_ex(b2ndt *h, const void *src, size_t n, size_t stride, size_t ioff, const float pose[16],
+                      double max_range, double *out);
+
+/* ------------------------------------------------------------------ voxel filter ---------- */
+typedef struct b2vf b2vf;
+
+int  b2vf_create(float lx, float ly, float lz, int device, b2vf **out);
+void b2vf_destroy(b2vf *h);
+int  b2vf_set_stream(b2vf *h, void *cuda_stream);
+/* out: capacity out_capacity points with byte stride out_stride / intensity at out_ioff (padding bytes
+ * of a 32-byte PointXYZI are written as data[3]=1.0f, rest 0).  in == out is allowed (viewer.cpp:207,
+ * matching.cpp:158).  *m receives the number of output points.  out_idx / out_cnt (capacity
+ * out_capacity, may be NULL) receive the voxel index and the point count of every output point. */
+int  b2vf_filter(b2vf *h, const void *in, size_t n, size_t stride, size_t ioff,
+                 void *out, size_t out_capacity, size_t out_stride, size_t out_ioff, size_t *m,
+                 int32_t *out_idx, int32_t *out_cnt);
+/* B clouds in one launch (concatenated, offsets B+1): device float4 in, device float4 out (capacity
+ * n_total), d_out_offsets (B+1) receives the output ranges (compacted, same order). Asynchronous. */
+int  b2vf_filter_batch_device(b2vf *h, const void *d_in_f4, size_t n_total, const uint32_t *h_offsets,
+                              size_t B, void *d_out_f4, uint32_t *d_out_offsets);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

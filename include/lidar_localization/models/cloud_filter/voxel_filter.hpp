@@ -1,0 +1,32 @@
+// voxel_filter.hpp -- B200 drop-in for the reference's VoxelFilter
+// (lidar_localization/include/lidar_localization/models/cloud_filter/voxel_filter.hpp:13-25,
+//  src/models/cloud_filter/voxel_filter.cpp:12-41).  The pcl::VoxelGrid member is replaced by a b2vf
+// handle.  Filter(in, out) may be called with in == out (matching.cpp:158, loop_closing.cpp:293,305,
+// viewer.cpp:207) and with an empty pre-allocated out (front_end.cpp:106-107).
+#ifndef LIDAR_LOCALIZATION_MODELS_CLOUD_FILTER_VOXEL_FILTER_HPP_
+#define LIDAR_LOCALIZATION_MODELS_CLOUD_FILTER_VOXEL_FILTER_HPP_
+
+#include "b2ndt.h"
+#include "lidar_localization/models/cloud_filter/cloud_filter_interface.hpp"
+
+namespace lidar_localization {
+class VoxelFilter : public CloudFilterInterface {
+  public:
+#ifdef B2_WITH_YAML
+    VoxelFilter(const YAML::Node& node);
+#endif
+    VoxelFilter(float leaf_size_x, float leaf_size_y, float leaf_size_z);
+    ~VoxelFilter() override;
+    VoxelFilter(const VoxelFilter&) = delete;
+    VoxelFilter& operator=(const VoxelFilter&) = delete;
+
+    bool Filter(const CloudData::CLOUD_PTR& input_cloud_ptr, CloudData::CLOUD_PTR& filtered_cloud_ptr) override;
+
+  private:
+    bool SetFilterParam(float leaf_size_x, float leaf_size_y, float leaf_size_z);
+
+  private:
+    b2vf* vf_ = nullptr;
+};
+}  // namespace lidar_localization
+#endif

@@ -1,0 +1,147 @@
+// b2_common.cuh -- shared host/device helpers for libb2ndt.so (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+#include <string>
+
+#include "b2ndt.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libb2ndt is written for sm_100a (B200) only"
+#endif
+
+namespace b2 {
+
+// ------------------------------------------------------------------ error plumbing ----------
+void set_error(const char *fmt, ...);
+extern std::atomic<uint64_t> g_launches;
+inline void count_launch(uint64_t n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+#define B2_CUDA(expr)                                                                         \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess) {                                                              \
+            b2::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return B2_ERR_CUDA;                                                               \
+        }                                                                                     \
+    } while (0)
+
+#define B2_LAUNCH_CHECK()                                                                     \
+    do {                                                                                      \
+        b2::count_launch();                                                                   \
+        cudaError_t _e = cudaGetLastError();                                                  \
+        if (_e != cudaSuccess) {                                                              \
+            b2::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return B2_ERR_CUDA;                                                               \
+        }                                                                                     \
+    } while (0)
+
+// growable device / pinned buffers (never shrink; reused across calls)
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { set_error("cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e)); p = nullptr; return B2_ERR_CUDA; }
+        cap = want;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+struct PinBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e != cudaSuccess) { set_error("cudaMallocHost(%zu) failed: %s", want, cudaGetErrorString(e)); p = nullptr; return B2_ERR_CUDA; }
+        cap = want;
+        return 0;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+// ------------------------------------------------------------------ voxel layout ------------
+// pcl::VoxelGrid / VoxelGridCovariance index layout, one per cloud.
+struct VoxLayout {
+    int32_t ok;          // 0: no finite point or int32 guard tripped
+    int32_t nbits;       // bits needed to sort keys in [0, ncells]  (ncells = invalid-point key)
+    float   inv[3];
+    float   min_p[3], max_p[3];
+    int32_t min_b[3], div_b[3], mul[3];
+    uint32_t ncells;     // div_x*div_y*div_z
+    uint32_t n_finite;
+};
+
+// float <-> order-preserving uint for atomic min/max
+__host__ __device__ inline uint32_t f2ord(float f) {
+#ifdef __CUDA_ARCH__
+    uint32_t u = __float_as_uint(f);
+#else
+    uint32_t u; memcpy(&u, &f, 4);
+#endif
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ inline float ord2f(uint32_t u) {
+    u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(u);
+#else
+    float f; memcpy(&f, &u, 4); return f;
+#endif
+}
+
+#ifdef __CUDACC__
+__device__ __forceinline__ bool finite3(float x, float y, float z) {
+    return isfinite(x) && isfinite(y) && isfinite(z);
+}
+// PCL: ijk = (int)(floor(x * inv) - (float)min_b)  -- float multiply, no FMA contraction
+__device__ __forceinline__ int32_t vox_index(const VoxLayout &L, float x, float y, float z) {
+    int i0 = (int)(floorf(__fmul_rn(x, L.inv[0])) - (float)L.min_b[0]);
+    int i1 = (int)(floorf(__fmul_rn(y, L.inv[1])) - (float)L.min_b[1]);
+    int i2 = (int)(floorf(__fmul_rn(z, L.inv[2])) - (float)L.min_b[2]);
+    return i0 * L.mul[0] + i1 * L.mul[1] + i2 * L.mul[2];
+}
+// pcl::transformPointCloud, float, evaluated left to right without contraction
+__device__ __forceinline__ void transform_f32(const float *T /*col-major 4x4*/, float x, float y, float z,
+                                              float &ox, float &oy, float &oz) {
+    ox = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T[0], x), __fmul_rn(T[4], y)), __fmul_rn(T[8], z)), T[12]);
+    oy = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T[1], x), __fmul_rn(T[5], y)), __fmul_rn(T[9], z)), T[13]);
+    oz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T[2], x), __fmul_rn(T[6], y)), __fmul_rn(T[10], z)), T[14]);
+}
+#endif
+
+// ------------------------------------------------------------------ sort plan ----------------
+// A "tile" is a run of at most TILE consecutive elements of ONE cloud (segment) of a concatenated
+// batch; kernels are launched one CTA per tile.
+constexpr int SORT_TILE = 4096;      // 256 threads x 16 keys
+constexpr int SORT_THREADS = 256;
+constexpr int RADIX_BITS = 8;
+constexpr int RADIX = 1 << RADIX_BITS;
+
+struct TileDesc {
+    uint32_t seg;        // cloud index
+    uint32_t begin;      // first element (global index into the concatenated arrays)
+    uint32_t count;      // elements in this tile
+    uint32_t tile_in_seg;
+};
+struct SegDesc {
+    uint32_t begin, count;      // element range
+    uint32_t tile_begin, ntiles;
+};
+
+}  // namespace b2

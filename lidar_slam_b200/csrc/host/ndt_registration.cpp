@@ -1,0 +1,121 @@
+// ndt_registration.cpp -- NDTRegistration over the b2ndt C ABI (see ndt_registration.hpp).
+#include "lidar_localization/models/registration/ndt_registration.hpp"
+
+#include <cstdlib>
+#include <cstring>
+#include <iostream>
+
+namespace lidar_localization {
+namespace {
+int g_default_device = -1;
+int DefaultDevice() {
+    if (g_default_device >= 0) return g_default_device;
+    const char* e = std::getenv("B2NDT_DEVICE");
+    return e ? std::atoi(e) : 0;
+}
+constexpr std::size_t kStride = sizeof(CloudData::POINT);          // 32
+constexpr std::size_t kIntensityOffset = 16;                       // data_c[0]
+}  // namespace
+
+void NDTRegistration::SetDefaultDevice(int device) { g_default_device = device; }
+
+#ifdef B2_WITH_YAML
+NDTRegistration::NDTRegistration(const YAML::Node& node) {
+    SetRegistrationParam(node["res"].as<float>(), node["step_size"].as<float>(), node["trans_eps"].as<float>(),
+                         node["max_iter"].as<int>());
+}
+#endif
+
+NDTRegistration::NDTRegistration(float res, float step_size, float trans_eps, int max_iter) {
+    SetRegistrationParam(res, step_size, trans_eps, max_iter);
+}
+
+NDTRegistration::~NDTRegistration() { b2ndt_destroy(ndt_); }
+
+bool NDTRegistration::SetRegistrationParam(float res, float step_size, float trans_eps, int max_iter) {
+    b2ndt_params p;
+    b2ndt_params_default(&p);
+    p.res = res;
+    p.step_size = step_size;   // float -> double exactly as pcl::NDT::setStepSize(double) receives it
+    p.trans_eps = trans_eps;
+    p.max_iter = max_iter;
+    if (b2ndt_create(&p, DefaultDevice(), &ndt_) != B2_OK) {
+        std::cerr << "[NDTRegistration] " << b2_last_error() << std::endl;
+        ndt_ = nullptr;
+    }
+    std::cout << "NDT params: res: " << res << ", step_size: " << step_size << ", trans_eps: " << trans_eps
+              << ", max_iter: " << max_iter << std::endl;
+    return true;
+}
+
+bool NDTRegistration::SetInputTarget(const CloudData::CLOUD_PTR& input_target) {
+    if (ndt_ && b2ndt_set_target(ndt_, input_target->points.data(), input_target->points.size(), kStride, kIntensityOffset) != B2_OK)
+        std::cerr << "[NDTRegistration::SetInputTarget] " << b2_last_error() << std::endl;
+    return true;
+}
+
+bool NDTRegistration::ScanMatch(const CloudData::CLOUD_PTR& input_source, const Eigen::Matrix4f& predict_pose,
+                                CloudData::CLOUD_PTR& result_cloud_ptr, Eigen::Matrix4f& result_pose) {
+    const std::size_t n = input_source->points.size();
+    float pose[16];
+    std::memcpy(pose, predict_pose.data(), sizeof(pose));
+    if (!ndt_ || b2ndt_align(ndt_, input_source->points.data(), n, kStride, kIntensityOffset, predict_pose.data(), pose, &last_) != B2_OK) {
+        std::cerr << "[NDTRegistration::ScanMatch] " << b2_last_error() << std::endl;
+        return true;   // the reference wrapper never reports failure either (ndt_registration.cpp:60)
+    }
+    std::memcpy(result_pose.data(), pose, sizeof(pose));
+    // align(output): the source transformed by the final pose, float arithmetic of pcl::transformPointCloud
+    if (result_cloud_ptr) {
+        CloudData::CLOUD& out = *result_cloud_ptr;
+        const bool alias = (result_cloud_ptr.get() == input_source.get());
+        if (!alias) {
+            out.points.resize(n);
+            out.width = input_source->width; out.height = input_source->height; out.is_dense = input_source->is_dense;
+        }
+        for (std::size_t i = 0; i < n; ++i) {
+            const CloudData::POINT& s = input_source->points[i];
+            const float x = s.x, y = s.y, z = s.z;
+            CloudData::POINT o = s;
+            o.x = ((pose[0] * x + pose[4] * y) + pose[8] * z) + pose[12];
+            o.y = ((pose[1] * x + pose[5] * y) + pose[9] * z) + pose[13];
+            o.z = ((pose[2] * x + pose[6] * y) + pose[10] * z) + pose[14];
+            o.data[3] = 1.0f;
+            out.points[i] = o;
+        }
+    }
+    return true;
+}
+
+float NDTRegistration::GetFitnessScore() {
+    double v = 0.0;
+    if (!ndt_ || b2ndt_fitness(ndt_, 1.7976931348623157e308, &v) != B2_OK) {
+        std::cerr << "[NDTRegistration::GetFitnessScore] " << b2_last_error() << std::endl;
+        return 3.402823466e+38f;
+    }
+    return static_cast<float>(v);
+}
+
+bool NDTRegistration::ScanMatchBatch(const std::vector<CloudData::CLOUD_PTR>& sources,
+                                     const std::vector<Eigen::Matrix4f>& predict_poses,
+                                     std::vector<Eigen::Matrix4f>& result_poses, std::vector<b2ndt_result>* details) {
+    const std::size_t B = sources.size();
+    result_poses.assign(B, Eigen::Matrix4f::Identity());
+    if (!ndt_ || predict_poses.size() != B || B == 0) return B == 0;
+    std::vector<uint32_t> off(B + 1, 0);
+    for (std::size_t b = 0; b < B; ++b) off[b + 1] = off[b] + (uint32_t)sources[b]->points.size();
+    std::vector<CloudData::POINT> all(off[B]);
+    for (std::size_t b = 0; b < B; ++b)
+        if (!sources[b]->points.empty())
+            std::memcpy(&all[off[b]], sources[b]->points.data(), sources[b]->points.size() * kStride);
+    std::vector<float> g(B * 16), out(B * 16);
+    for (std::size_t b = 0; b < B; ++b) std::memcpy(&g[b * 16], predict_poses[b].data(), 64);
+    if (details) details->resize(B);
+    if (b2ndt_align_batch(ndt_, all.data(), all.size(), kStride, kIntensityOffset, off.data(), B, g.data(), out.data(),
+                          details ? details->data() : nullptr) != B2_OK) {
+        std::cerr << "[NDTRegistration::ScanMatchBatch] " << b2_last_error() << std::endl;
+        return false;
+    }
+    for (std::size_t b = 0; b < B; ++b) std::memcpy(result_poses[b].data(), &out[b * 16], 64);
+    return true;
+}
+}  // namespace lidar_localization

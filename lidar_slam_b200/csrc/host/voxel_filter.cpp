@@ -1,0 +1,57 @@
+// voxel_filter.cpp -- VoxelFilter over the b2vf C ABI (see voxel_filter.hpp).
+#include "lidar_localization/models/cloud_filter/voxel_filter.hpp"
+
+#include <cstdlib>
+#include <iostream>
+#include <vector>
+
+namespace lidar_localization {
+namespace {
+int DefaultDevice() {
+    const char* e = std::getenv("B2NDT_DEVICE");
+    return e ? std::atoi(e) : 0;
+}
+constexpr std::size_t kStride = sizeof(CloudData::POINT);
+constexpr std::size_t kIntensityOffset = 16;
+}  // namespace
+
+#ifdef B2_WITH_YAML
+VoxelFilter::VoxelFilter(const YAML::Node& node) {
+    SetFilterParam(node["leaf_size"][0].as<float>(), node["leaf_size"][1].as<float>(), node["leaf_size"][2].as<float>());
+}
+#endif
+
+VoxelFilter::VoxelFilter(float leaf_size_x, float leaf_size_y, float leaf_size_z) {
+    SetFilterParam(leaf_size_x, leaf_size_y, leaf_size_z);
+}
+
+VoxelFilter::~VoxelFilter() { b2vf_destroy(vf_); }
+
+bool VoxelFilter::SetFilterParam(float leaf_size_x, float leaf_size_y, float leaf_size_z) {
+    if (b2vf_create(leaf_size_x, leaf_size_y, leaf_size_z, DefaultDevice(), &vf_) != B2_OK) {
+        std::cerr << "[VoxelFilter] " << b2_last_error() << std::endl;
+        vf_ = nullptr;
+    }
+    std::cout << "Voxel Filter params: " << leaf_size_x << ", " << leaf_size_y << ", " << leaf_size_z << std::endl;
+    return true;
+}
+
+bool VoxelFilter::Filter(const CloudData::CLOUD_PTR& input_cloud_ptr, CloudData::CLOUD_PTR& filtered_cloud_ptr) {
+    const std::size_t n = input_cloud_ptr->points.size();
+    // pcl::Filter::filter computes into a temporary when output aliases the input; same here
+    std::vector<CloudData::POINT> tmp(n);
+    std::size_t m = 0;
+    if (!vf_ || b2vf_filter(vf_, input_cloud_ptr->points.data(), n, kStride, kIntensityOffset, tmp.data(), n, kStride,
+                            kIntensityOffset, &m, nullptr, nullptr) != B2_OK) {
+        std::cerr << "[VoxelFilter::Filter] " << b2_last_error() << std::endl;
+        return true;
+    }
+    tmp.resize(m);
+    CloudData::CLOUD& out = *filtered_cloud_ptr;
+    out.points.assign(tmp.begin(), tmp.end());
+    out.width = static_cast<uint32_t>(m);
+    out.height = 1;
+    out.is_dense = true;
+    return true;
+}
+}  // namespace lidar_localization

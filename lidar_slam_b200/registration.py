@@ -1,0 +1,244 @@
+"""Python mirror of the reference's plug-in interface for the registration hot path.
+
+Same class / method names, argument meaning and error behaviour as
+  lidar_localization/include/lidar_localization/models/registration/registration_interface.hpp:14-24
+  lidar_localization/src/models/registration/ndt_registration.cpp:12-66
+  lidar_localization/include/lidar_localization/models/cloud_filter/cloud_filter_interface.hpp:13-18
+  lidar_localization/src/models/cloud_filter/voxel_filter.cpp:12-41
+so the parity tests read like the reference's call sites.  All work is done by libb2ndt.so through
+the C ABI of include/b2ndt.h; nothing here computes on the CPU except the final float transform of the
+source cloud that fills `result_cloud` (pcl::Registration::align's output), and there is no fallback.
+
+Clouds are numpy float32 arrays: (n, 8) in pcl::PointXYZI memory layout
+{x, y, z, 1, intensity, 0, 0, 0} (cloud_data.hpp:35) or (n, 4) packed {x, y, z, intensity}.
+Poses are 4x4 float32 (row/column indexed like Eigen::Matrix4f).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+
+DBL_MAX = float(np.finfo(np.float64).max)
+
+
+def to_xyzi8(cloud4):
+    """(n,4) packed -> (n,8) pcl::PointXYZI layout."""
+    c = np.asarray(cloud4, np.float32)
+    out = np.zeros((c.shape[0], 8), np.float32)
+    out[:, :3] = c[:, :3]
+    out[:, 3] = 1.0
+    out[:, 4] = c[:, 3]
+    return out
+
+
+def transform_cloud(cloud, T):
+    """pcl::transformPointCloud float semantics: x' = ((m00 x + m01 y) + m02 z) + m03."""
+    c = np.array(cloud, dtype=np.float32, copy=True)
+    T = np.asarray(T, np.float32).reshape(4, 4)
+    x, y, z = c[:, 0].copy(), c[:, 1].copy(), c[:, 2].copy()
+    for r in range(3):
+        c[:, r] = ((T[r, 0] * x + T[r, 1] * y) + T[r, 2] * z) + T[r, 3]
+    return c
+
+
+class RegistrationInterface:
+    def SetInputTarget(self, input_target):
+        raise NotImplementedError
+
+    def ScanMatch(self, input_source, predict_pose):
+        raise NotImplementedError
+
+    def GetFitnessScore(self):
+        raise NotImplementedError
+
+
+class CloudFilterInterface:
+    def Filter(self, input_cloud):
+        raise NotImplementedError
+
+
+class NDTRegistration(RegistrationInterface):
+    """NDTRegistration(res, step_size, trans_eps, max_iter) or NDTRegistration(node) with a dict holding
+    the YAML keys res / step_size / trans_eps / max_iter (ndt_registration.cpp:12-27)."""
+
+    def __init__(self, res, step_size=None, trans_eps=None, max_iter=None, device=0, pcl17_compat=True,
+                 outlier_ratio=0.55, min_pts=6, eig_mult=0.01):
+        if isinstance(res, dict):
+            node = res
+            res, step_size, trans_eps, max_iter = (float(node["res"]), float(node["step_size"]),
+                                                   float(node["trans_eps"]), int(node["max_iter"]))
+        L = capi.lib()
+        p = capi.Params()
+        L.b2ndt_params_default(C.byref(p))
+        # the reference passes float values into setStepSize(double) / setTransformationEpsilon(double)
+        p.res = float(np.float32(res))
+        p.step_size = float(np.float32(step_size))
+        p.trans_eps = float(np.float32(trans_eps))
+        p.max_iter = int(max_iter)
+        p.outlier_ratio = outlier_ratio
+        p.min_pts = min_pts
+        p.eig_mult = eig_mult
+        p.pcl17_compat = 1 if pcl17_compat else 0
+        self.params = p
+        self._h = C.c_void_p()
+        capi.check(L.b2ndt_create(C.byref(p), int(device), C.byref(self._h)))
+        self.device = device
+        self.last_result = None
+        self._keep = None
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            capi.lib().b2ndt_destroy(h)
+            self._h = None
+
+    # ---- reference surface -------------------------------------------------------------------
+    def SetInputTarget(self, input_target):
+        a, ptr, n, stride, ioff = capi.cloud_args(input_target)
+        capi.check(capi.lib().b2ndt_set_target(self._h, ptr, n, stride, ioff))
+        return True
+
+    def ScanMatch(self, input_source, predict_pose, want_cloud=True):
+        """-> (True, result_cloud, result_pose).  result_cloud = source transformed by the final pose."""
+        a, ptr, n, stride, ioff = capi.cloud_args(input_source)
+        g = capi.pose_to_colmajor(predict_pose)
+        out = np.zeros(16, np.float32)
+        res = capi.Result()
+        capi.check(capi.lib().b2ndt_align(self._h, ptr, n, stride, ioff, capi._fp(g), capi._fp(out), C.byref(res)))
+        pose = capi.colmajor_to_pose(out)
+        self.last_result = dict(iterations=res.iterations, converged=bool(res.converged), score=res.score,
+                                trans_probability=res.trans_probability, p=np.array(res.p[:]), passes=res.passes,
+                                mt_trials=res.mt_trials, pairs=res.pairs)
+        cloud = transform_cloud(a, pose) if want_cloud else None
+        return True, cloud, pose
+
+    def GetFitnessScore(self, max_range=DBL_MAX):
+        v = C.c_double()
+        capi.check(capi.lib().b2ndt_fitness(self._h, max_range, C.byref(v)))
+        return float(np.float32(v.value)) if max_range == DBL_MAX else v.value
+
+    # ---- extensions over the same C ABI --------------------------------------------------------
+    def GetFitnessScoreFor(self, source, pose, max_range=DBL_MAX):
+        a, ptr, n, stride, ioff = capi.cloud_args(source)
+        v = C.c_double()
+        P = capi.pose_to_colmajor(pose)
+        capi.check(capi.lib().b2ndt_fitness_ex(self._h, ptr, n, stride, ioff, capi._fp(P), max_range, C.byref(v)))
+        return v.value
+
+    def ScanMatchBatch(self, sources, predict_poses):
+        """Many independent ScanMatch calls in one launch.  sources: list of clouds (same layout) or one
+        cloud shared by all guesses (relocalisation hypotheses).  -> (poses (B,4,4), results recarray)."""
+        poses = np.asarray(predict_poses, np.float32).reshape(-1, 4, 4)
+        B = poses.shape[0]
+        g = np.ascontiguousarray(poses.transpose(0, 2, 1).reshape(B, 16))
+        out = np.zeros((B, 16), np.float32)
+        res = np.zeros(B, capi.RESULT_DTYPE)
+        L = capi.lib()
+        if isinstance(sources, (list, tuple)):
+            assert len(sources) == B
+            cat = np.ascontiguousarray(np.concatenate([np.asarray(s, np.float32) for s in sources], axis=0))
+            off = np.zeros(B + 1, np.uint32)
+            off[1:] = np.cumsum([len(s) for s in sources])
+            a, ptr, n, stride, ioff = capi.cloud_args(cat)
+            capi.check(L.b2ndt_align_batch(self._h, ptr, n, stride, ioff, off.ctypes.data_as(C.POINTER(C.c_uint32)), B,
+                                           capi._fp(g), capi._fp(out), res.ctypes.data))
+        else:
+            a, ptr, n, stride, ioff = capi.cloud_args(sources)
+            capi.check(L.b2ndt_align_batch(self._h, ptr, n, stride, ioff, None, B, capi._fp(g), capi._fp(out),
+                                           res.ctypes.data))
+        return out.reshape(B, 4, 4).transpose(0, 2, 1).copy(), res
+
+    def Derivatives(self, source, pose6):
+        """One computeDerivatives pass at a 6-vector pose -> (score, grad(6), H(6,6), pairs)."""
+        a, ptr, n, stride, ioff = capi.cloud_args(source)
+        p = np.ascontiguousarray(pose6, np.float64)
+        score = C.c_double()
+        g = np.zeros(6)
+        H = np.zeros(36)
+        pairs = C.c_int64()
+        capi.check(capi.lib().b2ndt_derivatives(self._h, ptr, n, stride, ioff, capi._dp(p), C.byref(score), capi._dp(g),
+                                                capi._dp(H), C.byref(pairs)))
+        return score.value, g, H.reshape(6, 6, order="F").copy(), pairs.value
+
+    def TargetInfo(self):
+        info = capi.TargetInfo()
+        capi.check(capi.lib().b2ndt_target_info_get(self._h, C.byref(info)))
+        return dict(ok=bool(info.ok), min_b=list(info.min_b), div_b=list(info.div_b), n_points=info.n_points,
+                    n_leaves=info.n_leaves, n_tree=info.n_tree)
+
+    def TargetLeaves(self):
+        V = self.TargetInfo()["n_leaves"]
+        idx = np.zeros(V, np.int32)
+        n = np.zeros(V, np.int32)
+        cen = np.zeros((V, 4), np.float32)
+        mean = np.zeros((V, 3))
+        icov = np.zeros((V, 9))
+        if V:
+            capi.check(capi.lib().b2ndt_target_leaves(self._h, idx.ctypes.data_as(C.POINTER(C.c_int32)),
+                                                      n.ctypes.data_as(C.POINTER(C.c_int32)), capi._fp(cen),
+                                                      capi._dp(mean), capi._dp(icov)))
+        return dict(idx=idx, n=n, centroid=cen, mean=mean, icov=icov)
+
+    def SetCluster(self, single_match_ctas, batch_ctas=1):
+        capi.check(capi.lib().b2ndt_set_cluster(self._h, single_match_ctas, batch_ctas))
+
+    def SetStream(self, cuda_stream_ptr):
+        capi.check(capi.lib().b2ndt_set_stream(self._h, C.c_void_p(cuda_stream_ptr) if cuda_stream_ptr else None))
+
+    def Synchronize(self):
+        capi.check(capi.lib().b2ndt_synchronize(self._h))
+
+    # device-resident entry points (torch tensors' data_ptr()); asynchronous on the handle's stream
+    def SetInputTargetDevice(self, d_ptr, n):
+        capi.check(capi.lib().b2ndt_set_target_device(self._h, C.c_void_p(d_ptr), n))
+        return True
+
+    def ScanMatchBatchDevice(self, d_src, n_total, d_offsets, B, d_guesses, d_poses_out, d_results=None):
+        capi.check(capi.lib().b2ndt_align_batch_device(self._h, C.c_void_p(d_src), n_total,
+                                                       C.c_void_p(d_offsets) if d_offsets else None, B,
+                                                       C.c_void_p(d_guesses), C.c_void_p(d_poses_out),
+                                                       C.c_void_p(d_results) if d_results else None))
+
+
+class VoxelFilter(CloudFilterInterface):
+    """VoxelFilter(lx, ly, lz) or VoxelFilter(node) with node["leaf_size"] = [lx, ly, lz]
+    (voxel_filter.cpp:12-23)."""
+
+    def __init__(self, leaf_size_x, leaf_size_y=None, leaf_size_z=None, device=0):
+        if isinstance(leaf_size_x, dict):
+            leaf_size_x, leaf_size_y, leaf_size_z = [float(v) for v in leaf_size_x["leaf_size"]]
+        self._h = C.c_void_p()
+        capi.check(capi.lib().b2vf_create(float(leaf_size_x), float(leaf_size_y), float(leaf_size_z), int(device),
+                                          C.byref(self._h)))
+        self.leaf = (float(leaf_size_x), float(leaf_size_y), float(leaf_size_z))
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            capi.lib().b2vf_destroy(h)
+            self._h = None
+
+    def Filter(self, input_cloud, with_info=False):
+        """-> (True, filtered_cloud) in the layout of the input; with_info adds (voxel idx, counts)."""
+        a, ptr, n, stride, ioff = capi.cloud_args(input_cloud)
+        out = np.zeros_like(a)
+        m = C.c_size_t(0)
+        idx = np.zeros(max(n, 1), np.int32)
+        cnt = np.zeros(max(n, 1), np.int32)
+        capi.check(capi.lib().b2vf_filter(self._h, ptr, n, stride, ioff, out.ctypes.data, n, stride, ioff, C.byref(m),
+                                          idx.ctypes.data_as(C.POINTER(C.c_int32)),
+                                          cnt.ctypes.data_as(C.POINTER(C.c_int32))))
+        M = m.value
+        if with_info:
+            return True, out[:M].copy(), idx[:M].copy(), cnt[:M].copy()
+        return True, out[:M].copy()
+
+    def SetStream(self, cuda_stream_ptr):
+        capi.check(capi.lib().b2vf_set_stream(self._h, C.c_void_p(cuda_stream_ptr) if cuda_stream_ptr else None))
+
+    def FilterBatchDevice(self, d_in, n_total, h_offsets, d_out, d_out_offsets):
+        off = np.ascontiguousarray(h_offsets, np.uint32)
+        capi.check(capi.lib().b2vf_filter_batch_device(self._h, C.c_void_p(d_in), n_total,
+                                                       off.ctypes.data_as(C.POINTER(C.c_uint32)), len(off) - 1,
+                                                       C.c_void_p(d_out), C.c_void_p(d_out_offsets)))

@@ -1,0 +1,304 @@
+"""ctypes binding of the CPU oracle (oracle/libndt_oracle.so).  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg import this
+module.  The product package (lidar_slam_b200) never does.
+
+Clouds are numpy float32 arrays of shape (n, 4) = packed {x, y, z, intensity} (stride 16) or
+(n, 8) = pcl::PointXYZI memory layout (stride 32, intensity in column 4; cloud_data.hpp:35).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+_REF = None
+
+
+def build(ref=True):
+    """Compile the C restatement (always) and, where /root/reference exists, oracle/_ref."""
+    subprocess.check_call(["make", "-s", "-C", _HERE, "all"])
+    if ref and os.path.isdir("/root/reference/lidar_localization/third_party/eigen3"):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "ref"])
+
+
+class Cloud(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("n", C.c_size_t), ("stride", C.c_size_t), ("ioff", C.c_size_t)]
+
+
+class VoxLayout(C.Structure):
+    _fields_ = [("ok", C.c_int), ("inv", C.c_float * 3), ("min_p", C.c_float * 3), ("max_p", C.c_float * 3),
+                ("min_b", C.c_int32 * 3), ("max_b", C.c_int32 * 3), ("div_b", C.c_int32 * 3),
+                ("divb_mul", C.c_int32 * 3), ("n_finite", C.c_size_t)]
+
+
+class Leaf(C.Structure):
+    _fields_ = [("idx", C.c_int32), ("n_raw", C.c_int32), ("nr_points", C.c_int32), ("in_tree", C.c_int32),
+                ("centroid", C.c_float * 4), ("mean", C.c_double * 3), ("cov", C.c_double * 9),
+                ("icov", C.c_double * 9), ("evals", C.c_double * 3)]
+
+
+LEAF_DTYPE = np.dtype([("idx", "<i4"), ("n_raw", "<i4"), ("nr_points", "<i4"), ("in_tree", "<i4"),
+                       ("centroid", "<f4", (4,)), ("mean", "<f8", (3,)), ("cov", "<f8", (9,)),
+                       ("icov", "<f8", (9,)), ("evals", "<f8", (3,))], align=True)
+
+
+class Params(C.Structure):
+    _fields_ = [("res", C.c_float), ("step_size", C.c_double), ("trans_eps", C.c_double),
+                ("outlier_ratio", C.c_double), ("max_iter", C.c_int), ("min_pts", C.c_int),
+                ("eig_mult", C.c_double), ("pcl17_compat", C.c_int)]
+
+
+class Result(C.Structure):
+    _fields_ = [("iterations", C.c_int), ("converged", C.c_int), ("score", C.c_double),
+                ("trans_probability", C.c_double), ("p", C.c_double * 6), ("passes", C.c_int),
+                ("pairs", C.c_longlong), ("mt_trials", C.c_int)]
+
+
+def lib():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = os.path.join(_HERE, "libndt_oracle.so")
+    if not os.path.exists(path):
+        build(ref=False)
+    L = C.CDLL(path)
+    dp = C.POINTER(C.c_double)
+    fp = C.POINTER(C.c_float)
+    ip = C.POINTER(C.c_int32)
+    L.orc_vox_layout_compute.argtypes = [Cloud, C.c_float, C.c_float, C.c_float, C.POINTER(VoxLayout)]
+    L.orc_vox_layout_compute.restype = C.c_int
+    L.orc_vox_index.argtypes = [C.POINTER(VoxLayout), C.c_float, C.c_float, C.c_float]
+    L.orc_vox_index.restype = C.c_int32
+    L.orc_voxel_filter.argtypes = [Cloud, C.c_float, C.c_float, C.c_float, fp, ip, ip, C.POINTER(C.c_int)]
+    L.orc_voxel_filter.restype = C.c_size_t
+    L.orc_grid_build.argtypes = [Cloud, C.c_float, C.c_int, C.c_double]
+    L.orc_grid_build.restype = C.c_void_p
+    L.orc_grid_free.argtypes = [C.c_void_p]
+    L.orc_grid_num_leaves.argtypes = [C.c_void_p]
+    L.orc_grid_num_leaves.restype = C.c_size_t
+    L.orc_grid_leaves.argtypes = [C.c_void_p]
+    L.orc_grid_leaves.restype = C.POINTER(Leaf)
+    L.orc_grid_layout.argtypes = [C.c_void_p]
+    L.orc_grid_layout.restype = C.POINTER(VoxLayout)
+    L.orc_grid_radius_search.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_double, ip, fp, C.c_int]
+    L.orc_grid_radius_search.restype = C.c_int
+    L.orc_euler_angles_012_f32.argtypes = [fp, fp]
+    L.orc_pose_to_matrix_f32.argtypes = [dp, fp]
+    L.orc_jacobi_svd_solve6.argtypes = [dp, dp, dp, dp]
+    L.orc_jacobi_svd_solve6.restype = C.c_int
+    L.orc_eig3_sym.argtypes = [dp, dp, dp]
+    L.orc_inverse3.argtypes = [dp, dp]
+    L.orc_gauss_constants.argtypes = [C.c_double, C.c_float, dp, dp]
+    L.orc_transform_point_f32.argtypes = [fp, C.c_float, C.c_float, C.c_float, fp]
+    L.orc_params_default.argtypes = [C.POINTER(Params)]
+    L.orc_ndt_derivatives.argtypes = [C.c_void_p, C.POINTER(Params), Cloud, fp, dp, C.c_int, dp, dp,
+                                      C.POINTER(C.c_longlong)]
+    L.orc_ndt_derivatives.restype = C.c_double
+    L.orc_ndt_align.argtypes = [C.c_void_p, C.POINTER(Params), Cloud, fp, fp, fp, C.POINTER(Result), dp, C.c_int]
+    L.orc_ndt_align.restype = C.c_int
+    L.orc_fitness_score.argtypes = [Cloud, Cloud, fp, C.c_double]
+    L.orc_fitness_score.restype = C.c_double
+    _LIB = L
+    return L
+
+
+def ref_lib():
+    """oracle/_ref/libeigen_ref.so (real vendored Eigen) or None when not built."""
+    global _REF
+    if _REF is not None:
+        return _REF
+    path = os.path.join(_HERE, "_ref", "libeigen_ref.so")
+    if not os.path.exists(path):
+        return None
+    R = C.CDLL(path)
+    dp = C.POINTER(C.c_double)
+    fp = C.POINTER(C.c_float)
+    R.ref_svd_solve6.argtypes = [dp, dp, dp, dp]
+    R.ref_svd_solve6.restype = C.c_int
+    R.ref_euler012.argtypes = [fp, fp]
+    R.ref_pose_matrix.argtypes = [dp, fp]
+    R.ref_leaf_finish.argtypes = [dp, dp, C.c_int, C.c_double, dp, dp, dp, dp]
+    R.ref_leaf_finish.restype = C.c_int
+    R.ref_inverse3.argtypes = [dp, dp]
+    R.ref_transform_point.argtypes = [fp, fp, fp]
+    _REF = R
+    return R
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _fp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+def as_cloud(a):
+    """numpy (n,4) packed or (n,8) PCL-layout float32 -> (Cloud struct, keepalive array)."""
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    if a.ndim != 2 or a.shape[1] not in (4, 8):
+        raise ValueError("cloud must be (n,4) or (n,8) float32")
+    ioff = 12 if a.shape[1] == 4 else 16
+    return Cloud(a.ctypes.data, a.shape[0], a.shape[1] * 4, ioff), a
+
+
+def params(res=1.0, step_size=0.1, trans_eps=0.01, max_iter=30, outlier_ratio=0.55, min_pts=6,
+           eig_mult=0.01, pcl17_compat=1):
+    return Params(res, step_size, trans_eps, outlier_ratio, max_iter, min_pts, eig_mult, pcl17_compat)
+
+
+def vox_layout(cloud, lx, ly, lz):
+    c, keep = as_cloud(cloud)
+    L = VoxLayout()
+    lib().orc_vox_layout_compute(c, lx, ly, lz, C.byref(L))
+    return L
+
+
+def voxel_indices(cloud, lx, ly, lz):
+    """Per-point PCL voxel index (int32; -1 for non-finite points) + layout."""
+    c, a = as_cloud(cloud)
+    L = VoxLayout()
+    ok = lib().orc_vox_layout_compute(c, lx, ly, lz, C.byref(L))
+    out = np.full(a.shape[0], -1, np.int32)
+    if ok:
+        f = lib().orc_vox_index
+        for i in range(a.shape[0]):
+            if np.all(np.isfinite(a[i, :3])):
+                out[i] = f(C.byref(L), a[i, 0], a[i, 1], a[i, 2])
+    return out, L
+
+
+def voxel_filter(cloud, lx, ly, lz):
+    """-> (out (M,4) float32, idx (M,) int32, counts (M,) int32, overflow flag)."""
+    c, a = as_cloud(cloud)
+    n = a.shape[0]
+    out = np.zeros((max(n, 1), 4), np.float32)
+    idx = np.zeros(max(n, 1), np.int32)
+    cnt = np.zeros(max(n, 1), np.int32)
+    ov = C.c_int(0)
+    m = lib().orc_voxel_filter(c, lx, ly, lz, _fp(out), _ip(idx), _ip(cnt), C.byref(ov))
+    return out[:m].copy(), idx[:m].copy(), cnt[:m].copy(), bool(ov.value)
+
+
+class Grid:
+    """NDT target cells (pcl::VoxelGridCovariance restatement)."""
+
+    def __init__(self, target, res=1.0, min_pts=6, eig_mult=0.01):
+        c, self._keep = as_cloud(target)
+        self.h = lib().orc_grid_build(c, res, min_pts, eig_mult)
+        self.res = res
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_grid_free(self.h)
+            self.h = None
+
+    @property
+    def layout(self):
+        return lib().orc_grid_layout(self.h).contents
+
+    def leaves(self):
+        n = lib().orc_grid_num_leaves(self.h)
+        if n == 0:
+            return np.zeros(0, LEAF_DTYPE)
+        assert C.sizeof(Leaf) == LEAF_DTYPE.itemsize, (C.sizeof(Leaf), LEAF_DTYPE.itemsize)
+        ptr = lib().orc_grid_leaves(self.h)
+        buf = (C.c_char * (n * C.sizeof(Leaf))).from_address(C.addressof(ptr.contents))
+        return np.frombuffer(buf, dtype=LEAF_DTYPE, count=n).copy()
+
+    def radius_search(self, q, radius=None, cap=64):
+        slots = np.zeros(cap, np.int32)
+        d2 = np.zeros(cap, np.float32)
+        k = lib().orc_grid_radius_search(self.h, float(q[0]), float(q[1]), float(q[2]),
+                                         float(self.res if radius is None else radius), _ip(slots), _fp(d2), cap)
+        return slots[:k].copy(), d2[:k].copy()
+
+
+def transform_points(T, xyz):
+    """pcl::transformPointCloud float semantics, vectorised (numpy float32 ops round like C)."""
+    T = np.asarray(T, np.float32).reshape(4, 4, order="F")
+    x = xyz[:, 0].astype(np.float32)
+    y = xyz[:, 1].astype(np.float32)
+    z = xyz[:, 2].astype(np.float32)
+    out = np.empty((xyz.shape[0], 3), np.float32)
+    for r in range(3):
+        out[:, r] = ((T[r, 0] * x + T[r, 1] * y) + T[r, 2] * z) + T[r, 3]
+    return out
+
+
+def pose_to_matrix(p):
+    p = np.ascontiguousarray(p, np.float64)
+    T = np.zeros(16, np.float32)
+    lib().orc_pose_to_matrix_f32(_dp(p), _fp(T))
+    return T.reshape(4, 4, order="F").copy()
+
+
+def euler_angles(T):
+    Tc = np.ascontiguousarray(np.asarray(T, np.float32).reshape(4, 4).flatten(order="F"))
+    out = np.zeros(3, np.float32)
+    lib().orc_euler_angles_012_f32(_fp(Tc), _fp(out))
+    return out
+
+
+def svd_solve6(H, b):
+    Hc = np.ascontiguousarray(np.asarray(H, np.float64).reshape(6, 6).flatten(order="F"))
+    bc = np.ascontiguousarray(b, np.float64)
+    x = np.zeros(6)
+    sv = np.zeros(6)
+    rank = lib().orc_jacobi_svd_solve6(_dp(Hc), _dp(bc), _dp(x), _dp(sv))
+    return x, sv, rank
+
+
+def gauss_constants(outlier_ratio=0.55, res=1.0):
+    d1 = C.c_double()
+    d2 = C.c_double()
+    lib().orc_gauss_constants(outlier_ratio, res, C.byref(d1), C.byref(d2))
+    return d1.value, d2.value
+
+
+def derivatives(grid, prm, src, pose6, trans_xyz=None, compute_hessian=True):
+    """computeDerivatives at 6-vector pose; trans_xyz defaults to T(pose)*src in float."""
+    c, a = as_cloud(src)
+    p = np.ascontiguousarray(pose6, np.float64)
+    if trans_xyz is None:
+        trans_xyz = transform_points(pose_to_matrix(p), a[:, :3])
+    t = np.ascontiguousarray(trans_xyz, np.float32)
+    g = np.zeros(6)
+    H = np.zeros(36)
+    pairs = C.c_longlong(0)
+    s = lib().orc_ndt_derivatives(grid.h, C.byref(prm), c, _fp(t), _dp(p), int(compute_hessian), _dp(g), _dp(H),
+                                  C.byref(pairs))
+    return s, g, H.reshape(6, 6, order="F").copy(), pairs.value
+
+
+def align(grid, prm, src, guess, want_cloud=False, trace_cap=0):
+    c, a = as_cloud(src)
+    G = np.ascontiguousarray(np.asarray(guess, np.float32).reshape(4, 4).flatten(order="F"))
+    pose = np.zeros(16, np.float32)
+    res = Result()
+    out = np.zeros((a.shape[0], 3), np.float32) if want_cloud else None
+    trace = np.zeros((max(trace_cap, 1), 8)) if trace_cap else None
+    lib().orc_ndt_align(grid.h, C.byref(prm), c, _fp(G), _fp(pose), _fp(out) if want_cloud else None,
+                        C.byref(res), _dp(trace) if trace_cap else None, trace_cap)
+    r = dict(pose=pose.reshape(4, 4, order="F").copy(), iterations=res.iterations, converged=bool(res.converged),
+             score=res.score, trans_probability=res.trans_probability, p=np.array(res.p[:]), passes=res.passes,
+             pairs=res.pairs, mt_trials=res.mt_trials)
+    if want_cloud:
+        r["cloud"] = out
+    if trace_cap:
+        r["trace"] = trace[:min(res.iterations, trace_cap)].copy()
+    return r
+
+
+def fitness_score(target, src, pose, max_range=np.finfo(np.float64).max):
+    ct, kt = as_cloud(target)
+    cs, ks = as_cloud(src)
+    P = np.ascontiguousarray(np.asarray(pose, np.float32).reshape(4, 4).flatten(order="F"))
+    return lib().orc_fitness_score(ct, cs, _fp(P), max_range)
