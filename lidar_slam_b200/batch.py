@@ -1,0 +1,46 @@
+"""Sharding of independent scan matches over the GPUs of one box (BASELINE.json configs 4/5).
+
+One process per GPU (torchrun); the target map is replicated, the batch of (source, guess) pairs is
+split into contiguous blocks, and there is NO collective on the match path (north_star): the only
+communication is the final gather of (pose, score, iterations) per match, done here with
+torch.distributed (NCCL on GPUs, gloo in the CPU tests).
+"""
+import numpy as np
+
+
+def shard_range(n_items, rank, world):
+    """Contiguous block [lo, hi) of n_items owned by `rank` (sizes differ by at most one)."""
+    base, rem = divmod(int(n_items), int(world))
+    lo = rank * base + min(rank, rem)
+    hi = lo + base + (1 if rank < rem else 0)
+    return lo, hi
+
+
+def shard_sizes(n_items, world):
+    return [shard_range(n_items, r, world)[1] - shard_range(n_items, r, world)[0] for r in range(world)]
+
+
+def gather_rows(local_rows, n_items, dist=None, device=None):
+    """All ranks contribute their (n_local, k) float64 rows; rank 0 gets the (n_items, k) table in batch
+    order (other ranks get None).  Uses all_gather on padded blocks so it works with NCCL and gloo."""
+    import torch
+    local_rows = np.ascontiguousarray(local_rows, np.float64)
+    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+        return local_rows
+    world, rank = dist.get_world_size(), dist.get_rank()
+    k = local_rows.shape[1]
+    sizes = shard_sizes(n_items, world)
+    pad = max(sizes)
+    buf = torch.zeros((pad, k), dtype=torch.float64, device=device)
+    if local_rows.shape[0]:
+        buf[:local_rows.shape[0]] = torch.from_numpy(local_rows).to(buf.device)
+    out = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(out, buf)
+    if rank != 0:
+        return None
+    return np.concatenate([out[r][:sizes[r]].cpu().numpy() for r in range(world)], axis=0)
+
+
+def best_hypothesis(rows, score_col=0):
+    """config 5: index of the best-scoring hypothesis (highest NDT score)."""
+    return int(np.argmax(rows[:, score_col]))

@@ -41,19 +41,19 @@ def oracle():
 @pytest.fixture(scope="session")
 def scene():
     from lidar_slam_b200 import synth
-    return synth.Scene(leg=80.0)
+    return synth.Scene(leg=100.0)
 
 
 @pytest.fixture(scope="session")
 def small_map(scene):
-    return scene.make_map(150_000, 2.0)
+    return scene.make_map(300_000, 2.0)
 
 
 @pytest.fixture(scope="session")
 def scans(scene):
     """a few raw HDL-64 scans with their true poses"""
     out = []
-    for k, s in enumerate((12.0, 33.5, 61.0, 90.0)):
+    for k, s in enumerate((41.3, 63.5, 88.0, 127.0)):
         p = scene.path_pose(s)
         out.append((p, scene.scan(100 + k, p)))
     return out

@@ -1,0 +1,60 @@
+// test_dropin.cpp -- exercises the C++ drop-in classes exactly the way the reference's call sites do
+// (front_end.cpp:106-107,221-231; matching.cpp:155-158,245-246; loop_closing.cpp:253).
+// Usage: test_dropin <target.bin> <scan.bin> <guess16.bin>   (float32 x,y,z,intensity records)
+// Prints: M <filtered count> / POSE <16 floats col-major> / FIT <fitness> / ITER <iterations>
+#include <cstdio>
+#include <fstream>
+#include <memory>
+#include <vector>
+
+#include "lidar_localization/models/cloud_filter/voxel_filter.hpp"
+#include "lidar_localization/models/registration/ndt_registration.hpp"
+
+using namespace lidar_localization;
+
+static CloudData::CLOUD_PTR load(const char* path) {
+    std::ifstream f(path, std::ios::binary);
+    std::vector<float> v((std::istreambuf_iterator<char>(f)), {});
+    f.clear(); f.seekg(0, std::ios::end);
+    size_t bytes = (size_t)f.tellg(); f.seekg(0);
+    v.resize(bytes / 4);
+    f.read((char*)v.data(), bytes);
+    CloudData::CLOUD_PTR c(new CloudData::CLOUD());
+    for (size_t i = 0; i + 3 < v.size(); i += 4) {
+        CloudData::POINT p;
+        p.x = v[i]; p.y = v[i + 1]; p.z = v[i + 2]; p.intensity = v[i + 3];
+        c->push_back(p);
+    }
+    return c;
+}
+
+int main(int argc, char** argv) {
+    if (argc < 4) { std::fprintf(stderr, "usage\n"); return 2; }
+    CloudData::CLOUD_PTR target = load(argv[1]), scan = load(argv[2]);
+    Eigen::Matrix4f guess = Eigen::Matrix4f::Identity();
+    { std::ifstream f(argv[3], std::ios::binary); f.read((char*)guess.data(), 64); }
+
+    std::shared_ptr<CloudFilterInterface> frame_filter = std::make_shared<VoxelFilter>(1.3f, 1.3f, 1.3f);
+    std::shared_ptr<RegistrationInterface> registration = std::make_shared<NDTRegistration>(1.0f, 0.1f, 0.01f, 30);
+
+    CloudData::CLOUD_PTR filtered(new CloudData::CLOUD());
+    frame_filter->Filter(scan, filtered);                 // out pre-allocated empty (front_end.cpp:106)
+    CloudData::CLOUD_PTR inplace = load(argv[2]);
+    frame_filter->Filter(inplace, inplace);               // in == out (matching.cpp:158)
+    if (inplace->points.size() != filtered->points.size()) { std::fprintf(stderr, "in-place mismatch\n"); return 1; }
+    for (size_t i = 0; i < filtered->points.size(); ++i)
+        if (inplace->points[i].x != filtered->points[i].x || inplace->points[i].intensity != filtered->points[i].intensity) return 1;
+
+    registration->SetInputTarget(target);
+    CloudData::CLOUD_PTR result(new CloudData::CLOUD());
+    Eigen::Matrix4f pose = Eigen::Matrix4f::Identity();
+    registration->ScanMatch(filtered, guess, result, pose);
+    float fit = registration->GetFitnessScore();
+    std::printf("M %zu\nPOSE", filtered->points.size());
+    for (int i = 0; i < 16; ++i) std::printf(" %.9g", pose.data()[i]);
+    std::printf("\nFIT %.9g\nITER %d\n", fit, static_cast<NDTRegistration*>(registration.get())->LastResult().iterations);
+    // result cloud = source under the final pose
+    if (result->points.size() != filtered->points.size()) return 1;
+    std::printf("R0 %.9g %.9g %.9g %.9g\n", result->points[0].x, result->points[0].y, result->points[0].z, result->points[0].intensity);
+    return 0;
+}

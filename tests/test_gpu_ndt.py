@@ -1,0 +1,258 @@
+"""-m gpu: NDT target grid, derivative pass, align, fitness through the C ABI vs the oracle.
+Tolerances (north_star): voxel assignment + counts bit-exact; pose <= 1e-3 m / 1e-4 rad; fitness <= 1e-4
+relative.  Tighter internal gates: per-pass score / gradient / Hessian <= 1e-9 relative at the same
+pose, identical iteration counts."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from lidar_slam_b200 import build, synth
+from lidar_slam_b200.registration import NDTRegistration, VoxelFilter, to_xyzi8
+from tests.conftest import f32
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "ndt_small.npz")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _pose_close(p_gpu, T_gpu, ref):
+    assert np.max(np.abs(T_gpu[:3, 3] - ref["pose"][:3, 3])) <= 1e-3
+    assert np.max(np.abs(p_gpu[3:] - ref["p"][3:])) <= 1e-4
+    assert np.max(np.abs(T_gpu[:3, :3] - ref["pose"][:3, :3])) <= 1e-4
+
+
+@pytest.fixture(scope="module")
+def setup(oracle, small_map, scans):
+    reg = NDTRegistration(1.0, 0.1, 0.01, 30)
+    reg.SetInputTarget(small_map)
+    grid = oracle.Grid(small_map, 1.0)
+    prm = oracle.params(step_size=f32(0.1), trans_eps=f32(0.01))
+    srcs = [oracle.voxel_filter(s, 1.3, 1.3, 1.3)[0] for _, s in scans]
+    return reg, grid, prm, srcs
+
+
+def test_target_grid_bit_exact(oracle, setup, small_map):
+    reg, grid, prm, _ = setup
+    lv = grid.leaves()
+    L = reg.TargetLeaves()
+    info = reg.TargetInfo()
+    lay = grid.layout
+    assert info["ok"] and info["min_b"] == list(lay.min_b) and info["div_b"] == list(lay.div_b)
+    assert info["n_leaves"] == len(lv) and info["n_tree"] == int((lv["n_raw"] >= 6).sum()) and info["n_points"] == len(small_map)
+    assert np.array_equal(L["idx"], lv["idx"]) and np.array_equal(L["n"], lv["n_raw"])
+    assert np.array_equal(L["centroid"], lv["centroid"])
+    assert np.array_equal(L["mean"], lv["mean"])
+    tree = lv["n_raw"] >= 6
+    assert np.allclose(L["icov"][tree], lv["icov"][tree], rtol=1e-12, atol=0)
+    assert np.mean(np.all(L["icov"][tree] == lv["icov"][tree], axis=1)) > 0.999
+
+
+def test_golden_fixture(oracle):
+    G = np.load(GOLD)
+    reg = NDTRegistration(1.0, 0.1, 0.01, 30)
+    reg.SetInputTarget(G["target"])
+    L = reg.TargetLeaves()
+    assert np.array_equal(L["idx"], G["leaf_idx"]) and np.array_equal(L["n"], G["leaf_n"])
+    assert np.array_equal(L["centroid"], G["leaf_centroid"]) and np.array_equal(L["mean"], G["leaf_mean"])
+    assert np.allclose(L["icov"], G["leaf_icov"], rtol=1e-12, atol=0)
+    for k, q in enumerate(G["deriv_pose"]):
+        s, g, H, pairs = reg.Derivatives(G["src"], q)
+        assert pairs == G["deriv_pairs"][k]
+        assert abs(s - G["deriv_score"][k]) <= 1e-9 * abs(s)
+        assert np.allclose(g, G["deriv_grad"][k], rtol=0, atol=1e-9 * np.abs(g).max())
+        assert np.allclose(H, G["deriv_hess"][k], rtol=0, atol=1e-9 * np.abs(H).max())
+    for compat in (1, 0):
+        r2 = NDTRegistration(1.0, 0.1, 0.01, 30, pcl17_compat=bool(compat))
+        r2.SetInputTarget(G["target"])
+        tag = "c%d_" % compat
+        for k, guess in enumerate(G["guesses"]):
+            ok, cloud, pose = r2.ScanMatch(G["src"], guess)
+            lr = r2.last_result
+            assert lr["iterations"] == G[tag + "iterations"][k] and lr["converged"] == G[tag + "converged"][k]
+            assert lr["passes"] == G[tag + "passes"][k]
+            assert np.max(np.abs(pose[:3, 3] - G[tag + "pose"][k][:3, 3])) <= 1e-3
+            assert np.max(np.abs(lr["p"][3:] - G[tag + "p"][k][3:])) <= 1e-4
+            assert abs(lr["score"] - G[tag + "score"][k]) <= 1e-6 * max(1.0, abs(G[tag + "score"][k]))
+            if compat:
+                fit = r2.GetFitnessScore()
+                assert abs(fit - G["fitness"][k]) <= 1e-4 * G["fitness"][k]
+
+
+def test_derivative_pass_matches_oracle(oracle, setup, scans):
+    reg, grid, prm, srcs = setup
+    rng = np.random.default_rng(3)
+    for (truth, _), src in zip(scans, srcs):
+        for C_ in (1, 4, 16):
+            reg.SetCluster(C_, 1)
+            q = synth.perturb_pose(truth, rng)
+            s0, g0, H0, p0 = oracle.derivatives(grid, prm, src, q)
+            s1, g1, H1, p1 = reg.Derivatives(src, q)
+            assert p0 == p1, "neighbour sets differ"
+            assert abs(s0 - s1) <= 1e-9 * abs(s0)
+            assert np.max(np.abs(g0 - g1)) <= 1e-9 * np.abs(g0).max()
+            assert np.max(np.abs(H0 - H1)) <= 1e-9 * np.abs(H0).max()
+    reg.SetCluster(8, 1)
+
+
+def test_align_matches_oracle(oracle, setup, scans, small_map):
+    reg, grid, prm, srcs = setup
+    rng = np.random.default_rng(4)
+    for (truth, _), src in zip(scans, srcs):
+        for trial in range(3):
+            guess = synth.pose6_to_matrix(synth.perturb_pose(truth, rng)).astype(np.float32)
+            ref = oracle.align(grid, prm, src, guess, want_cloud=True)
+            ok, cloud, pose = reg.ScanMatch(src, guess)
+            lr = reg.last_result
+            assert ok and lr["iterations"] == ref["iterations"] and lr["converged"] == ref["converged"]
+            assert lr["passes"] == ref["passes"] and lr["pairs"] == ref["pairs"]
+            _pose_close(lr["p"], pose, ref)
+            assert abs(lr["score"] - ref["score"]) <= 1e-6 * abs(ref["score"])
+            assert abs(lr["trans_probability"] - ref["trans_probability"]) <= 1e-6 * abs(ref["trans_probability"])
+            assert np.max(np.abs(cloud[:, :3] - ref["cloud"])) <= 2e-3
+            fit = reg.GetFitnessScore()
+            ofit = oracle.fitness_score(small_map, src, ref["pose"])
+            assert abs(fit - ofit) <= 1e-4 * ofit
+    # identity guess (the `guess != Identity` branch) and PointXYZI layout
+    src = srcs[0]
+    ident = np.eye(4, dtype=np.float32)
+    ref = oracle.align(grid, prm, src, ident)
+    ok, cloud, pose = reg.ScanMatch(to_xyzi8(src), ident)
+    assert reg.last_result["iterations"] == ref["iterations"]
+    _pose_close(reg.last_result["p"], pose, ref)
+
+
+def test_cluster_widths_agree(oracle, setup, scans):
+    reg, grid, prm, srcs = setup
+    truth, _ = scans[1]
+    guess = synth.pose6_to_matrix(truth + np.array([0.3, -0.2, 0.1, 0.01, 0.01, -0.02])).astype(np.float32)
+    res = []
+    for C_ in (1, 2, 4, 8, 16):
+        reg.SetCluster(C_, 1)
+        ok, _, pose = reg.ScanMatch(srcs[1], guess, want_cloud=False)
+        res.append((pose, reg.last_result["iterations"]))
+    reg.SetCluster(8, 1)
+    for pose, it in res[1:]:
+        assert it == res[0][1] and np.max(np.abs(pose - res[0][0])) <= 1e-6
+    # run-to-run reproducibility (fixed-order reductions)
+    ok, _, p1 = reg.ScanMatch(srcs[1], guess, want_cloud=False)
+    ok, _, p2 = reg.ScanMatch(srcs[1], guess, want_cloud=False)
+    assert np.array_equal(p1, p2)
+
+
+def test_more_thuente_enabled_matches_oracle(oracle, small_map, scans):
+    reg = NDTRegistration(1.0, 0.1, 0.01, 30, pcl17_compat=False)
+    reg.SetInputTarget(small_map)
+    grid = oracle.Grid(small_map, 1.0)
+    prm = oracle.params(step_size=f32(0.1), trans_eps=f32(0.01), pcl17_compat=0)
+    rng = np.random.default_rng(5)
+    trials = 0
+    for truth, scan in scans[:3]:
+        src = oracle.voxel_filter(scan, 1.3, 1.3, 1.3)[0]
+        for _ in range(2):
+            guess = synth.pose6_to_matrix(synth.perturb_pose(truth, rng)).astype(np.float32)
+            ref = oracle.align(grid, prm, src, guess)
+            ok, _, pose = reg.ScanMatch(src, guess, want_cloud=False)
+            lr = reg.last_result
+            assert lr["iterations"] == ref["iterations"] and lr["mt_trials"] == ref["mt_trials"] and lr["passes"] == ref["passes"]
+            _pose_close(lr["p"], pose, ref)
+            trials += ref["mt_trials"]
+    assert trials > 0, "the line search never ran"
+
+
+def test_batch_equals_single_matches(oracle, setup, scans):
+    reg, grid, prm, srcs = setup
+    rng = np.random.default_rng(6)
+    B = 48
+    sources, guesses = [], []
+    for b in range(B):
+        k = b % len(srcs)
+        sources.append(srcs[k][: len(srcs[k]) - (b % 7)])     # ragged lengths
+        guesses.append(synth.pose6_to_matrix(synth.perturb_pose(scans[k][0], rng)).astype(np.float32))
+    poses, res = reg.ScanMatchBatch(sources, guesses)
+    for b in (0, 5, 17, 47):
+        ok, _, p1 = reg.ScanMatch(sources[b], guesses[b], want_cloud=False)
+        assert np.max(np.abs(p1 - poses[b])) <= 1e-6 and reg.last_result["iterations"] == res[b]["iterations"]
+        ref = oracle.align(grid, prm, sources[b], guesses[b])
+        assert res[b]["iterations"] == ref["iterations"]
+        _pose_close(res[b]["p"], poses[b], ref)
+    # cluster of 2 CTAs per match in batch mode gives the same answers
+    reg.SetCluster(8, 2)
+    poses2, res2 = reg.ScanMatchBatch(sources, guesses)
+    reg.SetCluster(8, 1)
+    assert np.max(np.abs(poses2 - poses)) <= 1e-6 and np.array_equal(res2["iterations"], res["iterations"])
+    # relocalisation hypotheses: one source x B guesses (config 5)
+    hyp = [synth.pose6_to_matrix(synth.perturb_pose(scans[0][0], rng, 1.0, 3.0)).astype(np.float32) for _ in range(32)]
+    ph, rh = reg.ScanMatchBatch(srcs[0], hyp)
+    pl, rl = reg.ScanMatchBatch([srcs[0]] * 32, hyp)
+    assert np.array_equal(ph, pl) and np.array_equal(rh["iterations"], rl["iterations"])
+    # empty batch member
+    sources[3] = np.zeros((0, 4), np.float32)
+    poses3, res3 = reg.ScanMatchBatch(sources, guesses)
+    assert res3[3]["iterations"] == 0 and np.max(np.abs(poses3[4] - poses[4])) <= 1e-6
+
+
+def test_degenerate_inputs(oracle, small_map):
+    reg = NDTRegistration(1.0, 0.1, 0.01, 30)
+    from lidar_slam_b200 import capi
+    with pytest.raises(capi.B2Error) as e:
+        reg.ScanMatch(np.zeros((4, 4), np.float32), np.eye(4, dtype=np.float32))
+    assert e.value.code == capi.B2_ERR_STATE
+    reg.SetInputTarget(small_map)
+    with pytest.raises(capi.B2Error):
+        reg.GetFitnessScore()                       # no ScanMatch yet
+    far = np.array([[1e4, 1e4, 50, 0], [1e4 + 1, 1e4, 50, 0]], np.float32)
+    ok, cloud, pose = reg.ScanMatch(far, np.eye(4, dtype=np.float32))
+    assert reg.last_result["converged"] and reg.last_result["iterations"] == 0 and np.array_equal(pose, np.eye(4, dtype=np.float32))
+    # far-away queries exercise the fitness brute-force fallback
+    fit = reg.GetFitnessScore()
+    ofit = oracle.fitness_score(small_map, far, np.eye(4, dtype=np.float32))
+    assert abs(fit - ofit) <= 1e-4 * ofit
+    # empty target: PCL leaves no cells
+    reg.SetInputTarget(np.zeros((0, 4), np.float32))
+    ok, cloud, pose = reg.ScanMatch(far, np.eye(4, dtype=np.float32))
+    assert reg.last_result["iterations"] == 0
+    # target with NaNs and fewer than 6 points per voxel anywhere
+    t = np.array([[0, 0, 0, 1], [np.nan, 1, 1, 1], [5, 5, 5, 1]], np.float32)
+    reg.SetInputTarget(t)
+    info = reg.TargetInfo()
+    assert info["n_points"] == 2 and info["n_leaves"] == 2 and info["n_tree"] == 0
+
+
+def test_fitness_matches_oracle(oracle, setup, small_map, scans):
+    reg, grid, prm, srcs = setup
+    for (truth, scan), src in zip(scans[:2], srcs[:2]):
+        T = synth.pose6_to_matrix(truth + np.array([0.05, 0.02, 0, 0, 0, 0.002])).astype(np.float32)
+        got = reg.GetFitnessScoreFor(src, T)
+        want = oracle.fitness_score(small_map, src, T)
+        assert abs(got - want) <= 1e-9 * want
+        got = reg.GetFitnessScoreFor(scan[::5], T, max_range=0.5)
+        want = oracle.fitness_score(small_map, scan[::5], T, max_range=0.5)
+        assert abs(got - want) <= 1e-9 * want
+
+
+def test_cpp_dropin_classes(oracle, small_map, scans, tmp_path):
+    """C++ NDTRegistration / VoxelFilter (reference interface) driven like front_end.cpp / matching.cpp."""
+    build.build_host()
+    src = os.path.join(ROOT, "tests", "cpp", "test_dropin.cpp")
+    exe = str(tmp_path / "test_dropin")
+    subprocess.check_call(["g++", "-O2", "-std=c++14", "-I", os.path.join(ROOT, "include"), "-o", exe, src,
+                           "-L", build.LIBDIR, "-lb2host", "-lb2ndt", "-Wl,-rpath," + build.LIBDIR])
+    truth, scan = scans[0]
+    guess = synth.pose6_to_matrix(truth + np.array([0.2, 0.1, -0.1, 0.01, -0.01, 0.015])).astype(np.float32)
+    small_map.tofile(str(tmp_path / "t.bin")); scan.tofile(str(tmp_path / "s.bin"))
+    np.ascontiguousarray(guess.flatten(order="F")).tofile(str(tmp_path / "g.bin"))
+    out = subprocess.run([exe, str(tmp_path / "t.bin"), str(tmp_path / "s.bin"), str(tmp_path / "g.bin")],
+                         stdout=subprocess.PIPE, text=True, check=True).stdout
+    kv = {l.split()[0]: l.split()[1:] for l in out.splitlines() if l and l.split()[0] in ("M", "POSE", "FIT", "ITER", "R0")}
+    filt = oracle.voxel_filter(scan, 1.3, 1.3, 1.3)[0]
+    grid = oracle.Grid(small_map, 1.0)
+    ref = oracle.align(grid, oracle.params(step_size=f32(0.1), trans_eps=f32(0.01)), filt, guess, want_cloud=True)
+    assert int(kv["M"][0]) == len(filt) and int(kv["ITER"][0]) == ref["iterations"]
+    pose = np.array([float(v) for v in kv["POSE"]], np.float32).reshape(4, 4, order="F")
+    assert np.max(np.abs(pose[:3, 3] - ref["pose"][:3, 3])) <= 1e-3 and np.max(np.abs(pose[:3, :3] - ref["pose"][:3, :3])) <= 1e-4
+    ofit = oracle.fitness_score(small_map, filt, ref["pose"])
+    assert abs(float(kv["FIT"][0]) - ofit) <= 1e-4 * ofit
+    r0 = np.array([float(v) for v in kv["R0"]])
+    assert np.max(np.abs(r0[:3] - ref["cloud"][0])) <= 2e-3 and r0[3] == filt[0, 3]

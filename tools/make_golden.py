@@ -1,0 +1,134 @@
+"""Generate the committed fixtures under tests/golden/ (run in the build container, where
+/root/reference exists).
+
+  eigen_numerics.npz  outputs of the REAL Eigen 3.2.92 vendored by the reference
+                      (/root/reference/lidar_localization/third_party/eigen3, via oracle/_ref/libeigen_ref.so)
+                      for the expressions PCL's NDT uses: JacobiSVD<6x6>.solve, Translation*AngleAxis^3,
+                      Transform::rotation().eulerAngles(0,1,2), and the per-leaf covariance finish with
+                      SelfAdjointEigenSolver.  These pin the plain-C oracle AND the product's device math.
+  ndt_small.npz       a small scan-to-map case with the oracle's own outputs (regression pin of the
+                      restatement; the reference itself ships no golden vectors).
+"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import oracle as O  # noqa: E402
+from lidar_slam_b200 import synth  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def fp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def eigen_numerics():
+    O.build(ref=True)
+    R = O.ref_lib()
+    assert R is not None, "oracle/_ref/libeigen_ref.so missing (needs /root/reference)"
+    rng = np.random.default_rng(20261018)
+    n = 240
+    H = np.zeros((n, 36)); b = np.zeros((n, 6)); x = np.zeros((n, 6)); sv = np.zeros((n, 6)); rank = np.zeros(n, np.int32)
+    for t in range(n):
+        A = rng.standard_normal((6, 6))
+        kind = t % 6
+        if kind == 0: M = -(A @ A.T) * 10 ** rng.uniform(-2, 4)          # negative definite (typical NDT Hessian)
+        elif kind == 1: M = A + A.T                                      # symmetric indefinite
+        elif kind == 2: Bm = rng.standard_normal((6, 4)); M = Bm @ Bm.T   # rank 4
+        elif kind == 3: M = A                                            # general
+        elif kind == 4: Bm = rng.standard_normal((6, 1)); M = Bm @ Bm.T   # rank 1
+        else: M = np.diag(10.0 ** rng.uniform(-8, 8, 6)) @ (A + A.T) @ np.diag(10.0 ** rng.uniform(-3, 3, 6)); M = M + M.T
+        if t == n - 1: M = np.zeros((6, 6))
+        H[t] = M.flatten(order="F"); b[t] = rng.standard_normal(6)
+        rank[t] = R.ref_svd_solve6(dp(H[t]), dp(b[t]), dp(x[t]), dp(sv[t]))
+    m = 400
+    P = np.zeros((m, 6)); T = np.zeros((m, 16), np.float32); E = np.zeros((m, 3), np.float32)
+    for t in range(m):
+        scale = [1.0, 0.05, 1e-3, 1e-5][t % 4]
+        P[t] = np.concatenate([rng.uniform(-800, 800, 3), rng.uniform(-3.1, 3.1, 3) * scale])
+        if t == 0: P[t] = 0
+        R.ref_pose_matrix(dp(P[t]), fp(T[t]))
+        R.ref_euler012(fp(T[t]), fp(E[t]))
+    k = 300
+    pts_list = []; meta = np.zeros((k, 2), np.int32)
+    mean = np.zeros((k, 3)); cov = np.zeros((k, 9)); icov = np.zeros((k, 9)); ev = np.zeros((k, 3)); ret = np.zeros(k, np.int32)
+    for t in range(k):
+        npts = int(rng.integers(6, 120))
+        c = rng.uniform(100, 1500, 3)
+        kind = t % 4
+        sig = np.array([0.3, 0.3, 0.3 if kind == 0 else (0.01 if kind == 1 else 1e-4)])
+        q = rng.standard_normal((npts, 3)) * sig
+        if kind == 2: q[:, 1] *= 1e-3
+        if kind == 3: q[:] = q[0]                                         # all points identical
+        Q, _ = np.linalg.qr(rng.standard_normal((3, 3)))
+        q = (q @ Q.T + c).astype(np.float32)
+        s = np.zeros(3); acc = np.eye(3)
+        for v in q.astype(np.float64):
+            s += v; acc += np.outer(v, v)
+        accf = np.ascontiguousarray(acc.flatten())
+        ret[t] = R.ref_leaf_finish(dp(s), dp(accf), npts, 0.01, dp(mean[t]), dp(cov[t]), dp(icov[t]), dp(ev[t]))
+        meta[t] = (len(pts_list) and sum(len(p) for p in pts_list), npts)
+        pts_list.append(q)
+    pts = np.concatenate(pts_list, 0)
+    np.savez_compressed(os.path.join(OUT, "eigen_numerics.npz"), svd_H=H, svd_b=b, svd_x=x, svd_sv=sv, svd_rank=rank,
+                        pose_p=P, pose_T=T, pose_euler=E, leaf_pts=pts, leaf_meta=meta, leaf_mean=mean, leaf_cov=cov,
+                        leaf_icov=icov, leaf_evals=ev, leaf_ret=ret)
+    print("eigen_numerics.npz:", n, m, k)
+
+
+def ndt_small():
+    scene = synth.Scene(leg=40.0)
+    target = scene.make_map(24000, 2.0)
+    truth = scene.path_pose(17.0)
+    scan = scene.scan(5, truth)
+    filt, idx, cnt, _ = O.voxel_filter(scan, 1.3, 1.3, 1.3)
+    src = filt[::2].copy()
+    raw = scan[::16].copy()
+    r_filt, r_idx, r_cnt, _ = O.voxel_filter(raw, 1.3, 1.3, 1.3)
+    grid = O.Grid(target, 1.0)
+    lv = grid.leaves()
+    f32 = lambda v: float(np.float32(v))
+    out = dict(target=target, src=src, raw=raw, raw_filt=r_filt, raw_idx=r_idx, raw_cnt=r_cnt,
+               leaf_idx=lv["idx"], leaf_n=lv["n_raw"], leaf_centroid=lv["centroid"], leaf_mean=lv["mean"], leaf_icov=lv["icov"],
+               truth=truth)
+    rng = np.random.default_rng(7)
+    guesses = [synth.pose6_to_matrix(synth.perturb_pose(truth, rng)).astype(np.float32) for _ in range(6)]
+    guesses.append(np.eye(4, dtype=np.float32))
+    out["guesses"] = np.stack(guesses)
+    for compat in (1, 0):
+        prm = O.params(step_size=f32(0.1), trans_eps=f32(0.01), pcl17_compat=compat)
+        poses, ps, its, conv, sc, tp, passes = [], [], [], [], [], [], []
+        for G in guesses:
+            r = O.align(grid, prm, src, G)
+            poses.append(r["pose"]); ps.append(r["p"]); its.append(r["iterations"]); conv.append(r["converged"])
+            sc.append(r["score"]); tp.append(r["trans_probability"]); passes.append(r["passes"])
+        tag = "c%d_" % compat
+        out[tag + "pose"] = np.stack(poses); out[tag + "p"] = np.stack(ps); out[tag + "iterations"] = np.array(its)
+        out[tag + "converged"] = np.array(conv); out[tag + "score"] = np.array(sc); out[tag + "trans_probability"] = np.array(tp)
+        out[tag + "passes"] = np.array(passes)
+    prm = O.params(step_size=f32(0.1), trans_eps=f32(0.01))
+    dposes = np.stack([synth.perturb_pose(truth, rng) for _ in range(4)])
+    ds, dg, dH, dpairs = [], [], [], []
+    for q in dposes:
+        s, g, H, pairs = O.derivatives(grid, prm, src, q)
+        ds.append(s); dg.append(g); dH.append(H); dpairs.append(pairs)
+    out.update(deriv_pose=dposes, deriv_score=np.array(ds), deriv_grad=np.stack(dg), deriv_hess=np.stack(dH), deriv_pairs=np.array(dpairs))
+    out["fitness"] = np.array([O.fitness_score(target, src, out["c1_pose"][i]) for i in range(len(guesses))])
+    np.savez_compressed(os.path.join(OUT, "ndt_small.npz"), **out)
+    print("ndt_small.npz: target", target.shape, "src", src.shape, "raw", raw.shape, "leaves", len(lv),
+          "iterations", out["c1_iterations"], out["c0_iterations"])
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    eigen_numerics()
+    ndt_small()
