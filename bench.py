@@ -204,8 +204,11 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    stream = torch.cuda.current_stream()
+    # a dedicated (non-default) stream: the library launches on it and the CUDA events are recorded on it
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     sptr = stream.cuda_stream
+    assert sptr != 0
 
     # ---------------- setup (untimed): map, frames, VoxelFilter on the GPU, device-resident batch -------------
     vf = VoxelFilter(FRAME_LEAF, FRAME_LEAF, FRAME_LEAF, device=local_rank)
