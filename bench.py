@@ -182,6 +182,8 @@ def main():
     ap.add_argument("--map-points", type=int, default=1_000_000)
     ap.add_argument("--cpu-sample", type=int, default=48, help="frames of the CPU baseline sample (rank 0, N=1)")
     ap.add_argument("--batch-cluster", type=int, default=1, help="CTAs per match in batch mode")
+    ap.add_argument("--profile-range", action="store_true",
+                    help="bracket the timed device-resident steps with cudaProfilerStart/Stop (ncu --profile-from-start off)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -273,6 +275,8 @@ def main():
     launches0 = capi.launches()
     evs = []
     barrier()
+    if args.profile_range:
+        torch.cuda.profiler.start()
     wall0 = time.perf_counter()
     for _ in range(args.steps):
         flush.fill_(0.0)                      # L2 flush between timed steps (outside the event pair)
@@ -283,6 +287,8 @@ def main():
         evs.append((e0, e1))
     barrier()
     wall_s = time.perf_counter() - wall0
+    if args.profile_range:
+        torch.cuda.profiler.stop()
     gpu_launches = capi.launches() - launches0
     clocks = sampler.stop()
     step_ms = [a.elapsed_time(b) for a, b in evs]

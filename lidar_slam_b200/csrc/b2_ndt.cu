@@ -32,6 +32,7 @@ int check_device(int device);
 struct TargetDev {
     VoxLayout L;              // host copy of the layout
     uint32_t N = 0, V = 0, n_tree = 0;
+    float max_disp = 0.f;     // max distance of a searchable leaf's float centroid outside its own cell
     DevBuf pts_in;            // float4[N] as given (host path)
     DevBuf pts_sorted;        // float4[N]
     DevBuf leaf_idx, leaf_n, leaf_start, centroid4, gauss, sums, icov9, cell2leaf, counters;
@@ -84,8 +85,11 @@ __global__ void __launch_bounds__(256) leaf_stats_kernel(const float4 *__restric
 
 // One thread per voxel: mean, single-pass covariance, eigen inflation, inverse (leaf_finish), the
 // 80-byte gather record, and the dense-grid entry.
-__global__ void __launch_bounds__(128) leaf_finish_kernel(uint32_t V, int min_pts, double eig_mult,
+struct LayoutArg { int32_t min_b[3], div_b[3]; float inv[3]; };
+
+__global__ void __launch_bounds__(128) leaf_finish_kernel(uint32_t V, int min_pts, double eig_mult, LayoutArg LA,
                                                           const int32_t *__restrict__ leaf_idx, const int32_t *__restrict__ leaf_n,
+                                                          const float4 *__restrict__ centroid4,
                                                           const double *__restrict__ sums, double *__restrict__ gauss,
                                                           double *__restrict__ icov9, int32_t *__restrict__ cell2leaf,
                                                           uint32_t *__restrict__ counters) {
@@ -107,13 +111,40 @@ __global__ void __launch_bounds__(128) leaf_finish_kernel(uint32_t V, int min_pt
     for (int a = 0; a < 9; ++a) ic[a] = icov[a];
     const bool tree = n >= min_pts;
     cell2leaf[leaf_idx[j]] = tree ? (int32_t)(j + 1) : -(int32_t)(j + 1);
-    if (tree) atomicAdd(&counters[0], 1u);
+    if (tree) {
+        atomicAdd(&counters[0], 1u);
+        // how far the float centroid (PCL's kd-tree point) lies outside its own cell: bounds the search
+        // window margin of the match kernel.  Cell k of an axis spans [k/inv, (k+1)/inv).
+        const int idx = leaf_idx[j];
+        const int iz = idx / (LA.div_b[0] * LA.div_b[1]);
+        const int iy = (idx - iz * LA.div_b[0] * LA.div_b[1]) / LA.div_b[0];
+        const int ix = idx - iz * LA.div_b[0] * LA.div_b[1] - iy * LA.div_b[0];
+        const float4 c = centroid4[j];
+        const double cc[3] = {(double)c.x, (double)c.y, (double)c.z};
+        const int ii[3] = {ix, iy, iz};
+        double disp = 0.0;
+        for (int a = 0; a < 3; ++a) {
+            const double lo = (double)(ii[a] + LA.min_b[a]) / (double)LA.inv[a];
+            const double hi = (double)(ii[a] + LA.min_b[a] + 1) / (double)LA.inv[a];
+            disp = fmax(disp, fmax(lo - cc[a], cc[a] - hi));
+        }
+        if (disp > 0.0) atomicMax(&counters[1], __float_as_uint(__double2float_ru(disp)));   // positive floats order as uints
+    }
 }
 
 // ------------------------------------------------------------------ the NDT match kernel ------
+// One thread-block cluster (1..16 CTAs x 256 threads) per match; the whole Newton / More-Thuente loop
+// runs inside the kernel.  Each pass is WARP-LOCAL and two-phase:
+//   phase 1 (search, latency bound): lane = source point.  Float transform, the 3x3x3 window of the dense
+//     cell grid fetched with 27 independent loads, float centroid tests, hits appended to the warp's pair
+//     queue in shared memory at positions given by ballots (deterministic order, no atomics);
+//   phase 2 (compute, FP64 bound): lane = (point, voxel) pair taken from the queue in chunks of 32, so
+//     every lane is busy: 80-byte record gather, exp, score / gradient / Hessian terms of
+//     updateDerivatives (NDTM:485-520) accumulated in 29 FP64 registers.
+// Warps of co-resident CTAs are in different phases at any time, so gather latency hides under FP64 issue.
 constexpr int NDT_THREADS = 256;
 constexpr int NDT_WARPS = NDT_THREADS / 32;
-constexpr int NBR_CAP = 12;      // per-thread neighbour list in shared memory
+constexpr int QCAP = 1024;       // pair queue entries per warp: 31 left-overs + 32 lanes x (27 + slack)
 
 struct GridView {
     const int32_t *cell2leaf;
@@ -122,6 +153,7 @@ struct GridView {
     int32_t min_b[3], div_b[3], mul[3];
     float res, r2;      // search radius = resolution ; r2 = (float)(res*res)
     float inv_leaf;     // 1/res (only used to find candidate cells)
+    float margin;       // >= how far a float centroid can lie outside its own cell (measured at build time)
     int32_t ok;
 };
 
@@ -142,62 +174,106 @@ struct NdtSmem {
     double warp_part[NDT_WARPS][ACC_N];
     double cta_part[2][ACC_N];     // double-buffered per-CTA partial, read by cluster peers over DSMEM
     double total[ACC_N];
-    int32_t nbr[NBR_CAP][NDT_THREADS];
     int go;
+    int pad_;
+    uint2 queue[NDT_WARPS][QCAP];  // (source point index, leaf index)
 };
+
+__device__ __forceinline__ double dot3v(const double *h, double x, double y, double z) { return x * h[0] + y * h[1] + z * h[2]; }
+__device__ __forceinline__ double dot2v(const double *h, double x, double y) { return x * h[0] + y * h[1]; }
 
 // Hessian accumulators: upper triangle, row-major packed, k(i,j) for i<=j:
 //   row0: 0..5   row1: 6..10   row2: 11..14   row3: 15,16,17   row4: 18,19   row5: 20      (+7 in acc[])
 //
-// Per (point, voxel) pair: everything that depends on the voxel.  Accumulates the score, the rank-1
-// Hessian term -d2 w (J^T q)(J^T q)^T, and the per-point sums Q = sum w q, M = sum w Sigma^-1 that
-// are contracted with the point Jacobian / second derivatives once after the voxel loop
-// (updateDerivatives NDTM:485-520 regrouped; same terms, ~30% fewer FP64 operations).
-__device__ __forceinline__ void ndt_pair(const double *__restrict__ g, double xt, double yt, double zt, double d1, double d2,
-                                         const double *J, bool hess, double &score, double *Hacc, double *Q, double *M) {
+// One (point, voxel) pair: computePointDerivatives (NDTM:448-482) + updateDerivatives (NDTM:485-520).
+// J = [I | c3 c4 c5] with c3 = (0,J0,J1), c4 = (J2,J3,J4), c5 = (J5,J6,J7); structural zeros of the angle
+// tables (j_ang_f/g/h and h_ang_c/e/f have no z component) are exploited.
+__device__ __forceinline__ void ndt_pair(const float4 pt, const float *__restrict__ T, const AngTab &ang,
+                                         const double *__restrict__ g, double d1, double d2, bool hess, double *acc) {
+    float tx, ty, tz;
+    transform_f32(T, pt.x, pt.y, pt.z, tx, ty, tz);
     const double2 *g2 = reinterpret_cast<const double2 *>(g);      // 80-byte record, five 16-byte loads
     const double2 a0 = __ldg(g2 + 0), a1 = __ldg(g2 + 1), a2 = __ldg(g2 + 2), a3 = __ldg(g2 + 3), a4 = __ldg(g2 + 4);
-    const double x = xt - a0.x, y = yt - a0.y, z = zt - a1.x;
+    acc[28] += 1.0;
+    const double xq = (double)tx - a0.x, yq = (double)ty - a0.y, zq = (double)tz - a1.x;
     const double ixx = a1.y, ixy = a2.x, ixz = a2.y, iyy = a3.x, iyz = a3.y, izz = a4.x;
-    const double q0 = ixx * x + ixy * y + ixz * z;
-    const double q1 = ixy * x + iyy * y + iyz * z;
-    const double q2 = ixz * x + iyz * y + izz * z;
-    const double m = x * q0 + y * q1 + z * q2;
+    const double q0 = ixx * xq + ixy * yq + ixz * zq;
+    const double q1 = ixy * xq + iyy * yq + iyz * zq;
+    const double q2 = ixz * xq + iyz * yq + izz * zq;
+    const double m = xq * q0 + yq * q1 + zq * q2;
     double e = exp(-d2 * m / 2);
     const double sinc = -d1 * e;
     e = d2 * e;
     if (e > 1 || e < 0 || e != e) return;      // NDTM:499-501
     const double w = e * d1;
-    score += sinc;
-    Q[0] += w * q0; Q[1] += w * q1; Q[2] += w * q2;
-    if (hess) {
-        M[0] += w * ixx; M[1] += w * ixy; M[2] += w * ixz; M[3] += w * iyy; M[4] += w * iyz; M[5] += w * izz;
-        // a = J^T q  with J = [I | c3 c4 c5], c3 = (0,J0,J1), c4 = (J2,J3,J4), c5 = (J5,J6,J7)
-        double a[6];
-        a[0] = q0; a[1] = q1; a[2] = q2;
-        a[3] = q1 * J[0] + q2 * J[1];
-        a[4] = q0 * J[2] + q1 * J[3] + q2 * J[4];
-        a[5] = q0 * J[5] + q1 * J[6] + q2 * J[7];
+    acc[0] += sinc;
+    const double x = (double)pt.x, y = (double)pt.y, z = (double)pt.z;
+    double J[8];
+    J[0] = dot3v(ang.j[0], x, y, z); J[1] = dot3v(ang.j[1], x, y, z);
+    J[2] = dot3v(ang.j[2], x, y, z); J[3] = dot3v(ang.j[3], x, y, z); J[4] = dot3v(ang.j[4], x, y, z);
+    J[5] = dot2v(ang.j[5], x, y);    J[6] = dot2v(ang.j[6], x, y);    J[7] = dot2v(ang.j[7], x, y);
+    // a = J^T q ; gradient += w a
+    double a[6];
+    a[0] = q0; a[1] = q1; a[2] = q2;
+    a[3] = q1 * J[0] + q2 * J[1];
+    a[4] = q0 * J[2] + q1 * J[3] + q2 * J[4];
+    a[5] = q0 * J[5] + q1 * J[6] + q2 * J[7];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) acc[1 + i] += w * a[i];
+    if (!hess) return;
+    double *Hh = &acc[7];
+    {   // -d2 w (J^T q)(J^T q)^T
         const double wd = -d2 * w;
         int k = 0;
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
             const double t = wd * a[i];
 #pragma unroll
-            for (int j = i; j < 6; ++j) Hacc[k++] += t * a[j];
+            for (int j = i; j < 6; ++j) Hh[k++] += t * a[j];
         }
+    }
+    {   // w q . H_E(i,j): a=(0,x.a2,x.a3) b=(0,x.b2,x.b3) c=(0,x.c2,x.c3) d=(x.d1,x.d2,x.d3) e=(...) f=(...)
+        const double wq0 = w * q0, wq1 = w * q1, wq2 = w * q2;
+        Hh[15] += wq1 * dot3v(ang.h[0], x, y, z) + wq2 * dot3v(ang.h[1], x, y, z);
+        Hh[16] += wq1 * dot3v(ang.h[2], x, y, z) + wq2 * dot3v(ang.h[3], x, y, z);
+        Hh[17] += wq1 * dot2v(ang.h[4], x, y) + wq2 * dot2v(ang.h[5], x, y);
+        Hh[18] += wq0 * dot3v(ang.h[6], x, y, z) + wq1 * dot3v(ang.h[7], x, y, z) + wq2 * dot3v(ang.h[8], x, y, z);
+        Hh[19] += wq0 * dot2v(ang.h[9], x, y) + wq1 * dot2v(ang.h[10], x, y) + wq2 * dot2v(ang.h[11], x, y);
+        Hh[20] += wq0 * dot2v(ang.h[12], x, y) + wq1 * dot2v(ang.h[13], x, y) + wq2 * dot2v(ang.h[14], x, y);
+    }
+    {   // w J^T Sigma^-1 J
+        const double wxx = w * ixx, wxy = w * ixy, wxz = w * ixz, wyy = w * iyy, wyz = w * iyz, wzz = w * izz;
+        double m3[3], m4[3], m5[3];
+        m3[0] = wxy * J[0] + wxz * J[1];
+        m3[1] = wyy * J[0] + wyz * J[1];
+        m3[2] = wyz * J[0] + wzz * J[1];
+        m4[0] = wxx * J[2] + wxy * J[3] + wxz * J[4];
+        m4[1] = wxy * J[2] + wyy * J[3] + wyz * J[4];
+        m4[2] = wxz * J[2] + wyz * J[3] + wzz * J[4];
+        m5[0] = wxx * J[5] + wxy * J[6] + wxz * J[7];
+        m5[1] = wxy * J[5] + wyy * J[6] + wyz * J[7];
+        m5[2] = wxz * J[5] + wyz * J[6] + wzz * J[7];
+        Hh[0] += wxx; Hh[1] += wxy; Hh[2] += wxz; Hh[3] += m3[0]; Hh[4] += m4[0]; Hh[5] += m5[0];
+        Hh[6] += wyy; Hh[7] += wyz; Hh[8] += m3[1]; Hh[9] += m4[1]; Hh[10] += m5[1];
+        Hh[11] += wzz; Hh[12] += m3[2]; Hh[13] += m4[2]; Hh[14] += m5[2];
+        Hh[15] += J[0] * m3[1] + J[1] * m3[2];
+        Hh[16] += J[0] * m4[1] + J[1] * m4[2];
+        Hh[17] += J[0] * m5[1] + J[1] * m5[2];
+        Hh[18] += J[2] * m4[0] + J[3] * m4[1] + J[4] * m4[2];
+        Hh[19] += J[2] * m5[0] + J[3] * m5[1] + J[4] * m5[2];
+        Hh[20] += J[5] * m5[0] + J[6] * m5[1] + J[7] * m5[2];
     }
 }
 
-__device__ __forceinline__ double dot3v(const double *h, double x, double y, double z) { return x * h[0] + y * h[1] + z * h[2]; }
-
-__global__ void __launch_bounds__(NDT_THREADS) ndt_match_kernel(GridView G, NdtConst K, MatchArgs A) {
-    __shared__ NdtSmem S;
+__global__ void __launch_bounds__(NDT_THREADS, 2) ndt_match_kernel(GridView G, NdtConst K, MatchArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    NdtSmem &S = *reinterpret_cast<NdtSmem *>(smem_raw);
     cg::cluster_group cluster = cg::this_cluster();
     const unsigned C = cluster.num_blocks();
     const unsigned crank = cluster.block_rank();
     const unsigned match = blockIdx.x / C;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t lt = (1u << lane) - 1u;
 
     uint32_t first = 0, last = A.n_shared;
     if (A.offsets) { first = A.offsets[match]; last = A.offsets[match + 1]; }
@@ -216,107 +292,124 @@ __global__ void __launch_bounds__(NDT_THREADS) ndt_match_kernel(GridView G, NdtC
     }
     __syncthreads();
 
+    uint2 *queue = S.queue[warp];
     int parity = 0;
     while (true) {
-        // ---------------- one derivative pass over this CTA's share of the source points ----------
         const bool hess = S.ctl.hess != 0;
         double acc[ACC_N];
 #pragma unroll
         for (int i = 0; i < ACC_N; ++i) acc[i] = 0.0;
         const float *T = S.ctl.T;
         const AngTab &ang = S.ctl.ang;
-        for (uint32_t i = first + crank * NDT_THREADS + tid; i < last; i += C * NDT_THREADS) {
-            const float4 pt = __ldg(&A.src[i]);
-            float tx, ty, tz;
-            transform_f32(T, pt.x, pt.y, pt.z, tx, ty, tz);
-            if (!G.ok || !finite3(tx, ty, tz)) continue;
-            // candidate cells: every cell that can hold a centroid within the radius (with a margin for
-            // float centroids that round onto a cell face)
-            int lo[3], hi[3];
-            const float q[3] = {tx, ty, tz};
-            bool empty = false;
+        uint32_t qn = 0;       // warp-uniform: entries in the queue
+        // -------- this warp's share of the source points, 32 at a time --------
+        for (uint32_t base = first + (crank * NDT_WARPS + warp) * 32u; base < last; base += C * NDT_WARPS * 32u) {
+            const uint32_t i = base + lane;
+            int ex0 = -1, ex1 = -1, ex2 = -1;         // window extents - 1 ; -1 = no window
+            size_t wbase = 0;
+            float tx = 0.f, ty = 0.f, tz = 0.f;
+            bool slow = false;
+            float4 pt = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < last && G.ok) {
+                pt = __ldg(&A.src[i]);
+                transform_f32(T, pt.x, pt.y, pt.z, tx, ty, tz);
+                if (finite3(tx, ty, tz)) {
+                    // every cell that can hold a centroid within the radius (centroids may sit up to
+                    // G.margin outside their own cell; the slack also covers the rounding of this arithmetic)
+                    const float q[3] = {tx, ty, tz};
+                    int lo[3], ex[3];
+                    bool empty = false;
 #pragma unroll
-            for (int a = 0; a < 3; ++a) {
-                const float mg = 1e-3f * G.res + 1e-6f * fabsf(q[a]);
-                int l = (int)floorf((q[a] - G.res - mg) * G.inv_leaf) - G.min_b[a];
-                int h = (int)floorf((q[a] + G.res + mg) * G.inv_leaf) - G.min_b[a];
-                l = max(l, 0); h = min(h, G.div_b[a] - 1);
-                lo[a] = l; hi[a] = h;
-                empty = empty || (h < l);
-            }
-            if (empty) continue;
-            const double x = (double)pt.x, y = (double)pt.y, z = (double)pt.z;
-            const double xt = (double)tx, yt = (double)ty, zt = (double)tz;
-            // first-order terms of computePointDerivatives (NDTM:453-460)
-            double J[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) J[k] = dot3v(ang.j[k], x, y, z);
-            double Q[3] = {0, 0, 0}, M[6] = {0, 0, 0, 0, 0, 0};
-            int cnt = 0, npair = 0;
-            for (int kz = lo[2]; kz <= hi[2]; ++kz)
-                for (int ky = lo[1]; ky <= hi[1]; ++ky) {
-                    const int32_t *row = G.cell2leaf + (size_t)ky * G.mul[1] + (size_t)kz * G.mul[2];
-                    for (int kx = lo[0]; kx <= hi[0]; ++kx) {
-                        const int32_t v = __ldg(row + kx);
-                        if (v <= 0) continue;
-                        const float4 c = __ldg(&G.centroid4[v - 1]);
-                        // flann::L2_Simple<float>: (dx*dx + dy*dy) + dz*dz, accepted when < (float)(r*r)
-                        const float dx = __fsub_rn(tx, c.x), dy = __fsub_rn(ty, c.y), dz = __fsub_rn(tz, c.z);
-                        const float d2f = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-                        if (d2f < G.r2) {
-                            ++npair;
-                            if (cnt < NBR_CAP) S.nbr[cnt++][tid] = v - 1;
-                            else ndt_pair(G.gauss + (size_t)(v - 1) * 10, xt, yt, zt, K.d1, K.d2, J, hess, acc[0], &acc[7], Q, M);
+                    for (int a = 0; a < 3; ++a) {
+                        const float mg = G.margin + 1e-6f * fabsf(q[a]);
+                        int l = (int)floorf((q[a] - G.res - mg) * G.inv_leaf) - G.min_b[a];
+                        int h = (int)floorf((q[a] + G.res + mg) * G.inv_leaf) - G.min_b[a];
+                        l = max(l, 0); h = min(h, G.div_b[a] - 1);
+                        lo[a] = l; ex[a] = h - l;
+                        empty = empty || (h < l);
+                    }
+                    if (!empty) {
+                        slow = (ex[0] > 2) || (ex[1] > 2) || (ex[2] > 2);
+                        if (!slow) { ex0 = ex[0]; ex1 = ex[1]; ex2 = ex[2]; }
+                        wbase = (size_t)lo[0] + (size_t)lo[1] * G.mul[1] + (size_t)lo[2] * G.mul[2];
+                        if (slow) {
+                            // window wider than 3 cells (query within `margin` of a cell face): rare, handled
+                            // by this lane alone without the queue
+                            for (int kz = 0; kz <= ex[2]; ++kz)
+                                for (int ky = 0; ky <= ex[1]; ++ky)
+                                    for (int kx = 0; kx <= ex[0]; ++kx) {
+                                        const int32_t v = __ldg(G.cell2leaf + wbase + kx + (size_t)ky * G.mul[1] + (size_t)kz * G.mul[2]);
+                                        if (v <= 0) continue;
+                                        const float4 c = __ldg(&G.centroid4[v - 1]);
+                                        const float dx = __fsub_rn(tx, c.x), dy = __fsub_rn(ty, c.y), dz = __fsub_rn(tz, c.z);
+                                        const float d2f = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+                                        if (d2f < G.r2) ndt_pair(pt, T, ang, G.gauss + (size_t)(v - 1) * 10, K.d1, K.d2, hess, acc);
+                                    }
                         }
                     }
                 }
-            for (int k = 0; k < cnt; ++k)
-                ndt_pair(G.gauss + (size_t)S.nbr[k][tid] * 10, xt, yt, zt, K.d1, K.d2, J, hess, acc[0], &acc[7], Q, M);
-            if (npair == 0) continue;
-            acc[28] += (double)npair;
-            // gradient g = J^T Q
-            acc[1] += Q[0]; acc[2] += Q[1]; acc[3] += Q[2];
-            acc[4] += Q[1] * J[0] + Q[2] * J[1];
-            acc[5] += Q[0] * J[2] + Q[1] * J[3] + Q[2] * J[4];
-            acc[6] += Q[0] * J[5] + Q[1] * J[6] + Q[2] * J[7];
-            if (hess) {
-                double *Hh = &acc[7];
-                // Q . H_E(i,j): second-order terms of computePointDerivatives (NDTM:465-480)
-                Hh[15] += Q[1] * dot3v(ang.h[0], x, y, z) + Q[2] * dot3v(ang.h[1], x, y, z);        // a = (0, x.a2, x.a3)
-                Hh[16] += Q[1] * dot3v(ang.h[2], x, y, z) + Q[2] * dot3v(ang.h[3], x, y, z);        // b
-                Hh[17] += Q[1] * dot3v(ang.h[4], x, y, z) + Q[2] * dot3v(ang.h[5], x, y, z);        // c
-                Hh[18] += Q[0] * dot3v(ang.h[6], x, y, z) + Q[1] * dot3v(ang.h[7], x, y, z) + Q[2] * dot3v(ang.h[8], x, y, z);     // d
-                Hh[19] += Q[0] * dot3v(ang.h[9], x, y, z) + Q[1] * dot3v(ang.h[10], x, y, z) + Q[2] * dot3v(ang.h[11], x, y, z);   // e
-                Hh[20] += Q[0] * dot3v(ang.h[12], x, y, z) + Q[1] * dot3v(ang.h[13], x, y, z) + Q[2] * dot3v(ang.h[14], x, y, z);  // f
-                // J^T M J, M = (xx,xy,xz,yy,yz,zz)
-                double m3[3], m4[3], m5[3];
-                m3[0] = M[1] * J[0] + M[2] * J[1];
-                m3[1] = M[3] * J[0] + M[4] * J[1];
-                m3[2] = M[4] * J[0] + M[5] * J[1];
-                m4[0] = M[0] * J[2] + M[1] * J[3] + M[2] * J[4];
-                m4[1] = M[1] * J[2] + M[3] * J[3] + M[4] * J[4];
-                m4[2] = M[2] * J[2] + M[4] * J[3] + M[5] * J[4];
-                m5[0] = M[0] * J[5] + M[1] * J[6] + M[2] * J[7];
-                m5[1] = M[1] * J[5] + M[3] * J[6] + M[4] * J[7];
-                m5[2] = M[2] * J[5] + M[4] * J[6] + M[5] * J[7];
-                Hh[0] += M[0]; Hh[1] += M[1]; Hh[2] += M[2]; Hh[3] += m3[0]; Hh[4] += m4[0]; Hh[5] += m5[0];
-                Hh[6] += M[3]; Hh[7] += M[4]; Hh[8] += m3[1]; Hh[9] += m4[1]; Hh[10] += m5[1];
-                Hh[11] += M[5]; Hh[12] += m3[2]; Hh[13] += m4[2]; Hh[14] += m5[2];
-                Hh[15] += J[0] * m3[1] + J[1] * m3[2];
-                Hh[16] += J[0] * m4[1] + J[1] * m4[2];
-                Hh[17] += J[0] * m5[1] + J[1] * m5[2];
-                Hh[18] += J[2] * m4[0] + J[3] * m4[1] + J[4] * m4[2];
-                Hh[19] += J[2] * m5[0] + J[3] * m5[1] + J[4] * m5[2];
-                Hh[20] += J[5] * m5[0] + J[6] * m5[1] + J[7] * m5[2];
+            }
+            // ---- phase 1: the 3x3x3 window, 27 independent loads ----
+            const int32_t *wp = G.cell2leaf + wbase;
+            int32_t v[27];
+#pragma unroll
+            for (int dz = 0; dz < 3; ++dz)
+#pragma unroll
+                for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                    for (int dx = 0; dx < 3; ++dx) {
+                        const bool in = (dx <= ex0) && (dy <= ex1) && (dz <= ex2);
+                        v[dz * 9 + dy * 3 + dx] = in ? __ldg(wp + dx + (size_t)dy * G.mul[1] + (size_t)dz * G.mul[2]) : 0;
+                    }
+#pragma unroll
+            for (int r = 0; r < 9; ++r) {          // one x-row of the window at a time: 3 centroid loads in flight
+                float4 c[3];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    c[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (v[r * 3 + k] > 0) c[k] = __ldg(&G.centroid4[v[r * 3 + k] - 1]);
+                }
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    // flann::L2_Simple<float>: (dx*dx + dy*dy) + dz*dz, accepted when < (float)(r*r)
+                    const float dx = __fsub_rn(tx, c[k].x), dy = __fsub_rn(ty, c[k].y), dzz = __fsub_rn(tz, c[k].z);
+                    const float d2f = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dzz, dzz));
+                    const bool hit = (v[r * 3 + k] > 0) && (d2f < G.r2);
+                    const uint32_t b = __ballot_sync(0xffffffffu, hit);
+                    if (hit) queue[qn + __popc(b & lt)] = make_uint2(i, (uint32_t)(v[r * 3 + k] - 1));
+                    qn += __popc(b);
+                }
+            }
+            __syncwarp();
+            // ---- phase 2: full chunks of 32 pairs ----
+            uint32_t qh = 0;
+            while (qn - qh >= 32u) {
+                const uint2 e = queue[qh + lane];
+                ndt_pair(__ldg(&A.src[e.x]), T, ang, G.gauss + (size_t)e.y * 10, K.d1, K.d2, hess, acc);
+                qh += 32u;
+            }
+            if (qh) {      // move the left-over (< 32 entries) to the front
+                const uint32_t rem = qn - qh;
+                uint2 e = make_uint2(0u, 0u);
+                if ((uint32_t)lane < rem) e = queue[qh + lane];
+                __syncwarp();
+                if ((uint32_t)lane < rem) queue[lane] = e;
+                qn = rem;
+                __syncwarp();
             }
         }
+        if ((uint32_t)lane < qn) {     // tail: partial chunk
+            const uint2 e = queue[lane];
+            ndt_pair(__ldg(&A.src[e.x]), T, ang, G.gauss + (size_t)e.y * 10, K.d1, K.d2, hess, acc);
+        }
+        __syncwarp();
         // ---------------- deterministic reduction: warp butterfly -> CTA -> cluster (fixed order) -----
 #pragma unroll
         for (int i = 0; i < ACC_N; ++i) {
-            double v = acc[i];
+            double vsum = acc[i];
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == 0) S.warp_part[warp][i] = v;
+            for (int o = 16; o > 0; o >>= 1) vsum += __shfl_xor_sync(0xffffffffu, vsum, o);
+            if (lane == 0) S.warp_part[warp][i] = vsum;
         }
         __syncthreads();
         if (tid < ACC_N) {
@@ -471,7 +564,7 @@ struct b2ndt {
     float last_pose[16];
     bool have_last = false;
     int cl_single = 8, cl_batch = 1;
-    bool nonportable_set = false;
+    bool attrs_set = false;
 };
 
 static void gauss_constants(double outlier_ratio, float resolution, double *d1, double *d2) {
@@ -551,7 +644,7 @@ extern "C" int b2ndt_set_cluster(b2ndt *h, int single_match_ctas, int batch_ctas
 
 static int build_target(b2ndt *h, const float4 *d_pts, size_t n) {
     TargetDev &t = h->tgt;
-    t.valid = false; t.N = (uint32_t)n; t.V = 0; t.n_tree = 0;
+    t.valid = false; t.N = (uint32_t)n; t.V = 0; t.n_tree = 0; t.max_disp = 0.f;
     h->have_last = false;
     memset(&t.L, 0, sizeof(t.L));
     int rc;
@@ -589,14 +682,18 @@ static int build_target(b2ndt *h, const float4 *d_pts, size_t n) {
                                                     t.leaf_n.as<int32_t>(), t.leaf_start.as<uint32_t>(), t.centroid4.as<float4>(),
                                                     t.sums.as<double>());
         B2_LAUNCH_CHECK();
-        leaf_finish_kernel<<<(V + 127) / 128, 128, 0, h->st>>>(V, h->prm.min_pts, h->prm.eig_mult, t.leaf_idx.as<int32_t>(),
-                                                              t.leaf_n.as<int32_t>(), t.sums.as<double>(), t.gauss.as<double>(),
-                                                              t.icov9.as<double>(), t.cell2leaf.as<int32_t>(), t.counters.as<uint32_t>());
+        LayoutArg LA;
+        for (int a = 0; a < 3; ++a) { LA.min_b[a] = t.L.min_b[a]; LA.div_b[a] = t.L.div_b[a]; LA.inv[a] = t.L.inv[a]; }
+        leaf_finish_kernel<<<(V + 127) / 128, 128, 0, h->st>>>(V, h->prm.min_pts, h->prm.eig_mult, LA, t.leaf_idx.as<int32_t>(),
+                                                              t.leaf_n.as<int32_t>(), t.centroid4.as<float4>(), t.sums.as<double>(),
+                                                              t.gauss.as<double>(), t.icov9.as<double>(), t.cell2leaf.as<int32_t>(),
+                                                              t.counters.as<uint32_t>());
         B2_LAUNCH_CHECK();
     }
-    B2_CUDA(cudaMemcpyAsync(misc, t.counters.p, 4, cudaMemcpyDeviceToHost, h->st));
+    B2_CUDA(cudaMemcpyAsync(misc, t.counters.p, 8, cudaMemcpyDeviceToHost, h->st));
     B2_CUDA(cudaStreamSynchronize(h->st));
     t.n_tree = misc[0];
+    memcpy(&t.max_disp, &misc[1], 4);
     return 0;
 }
 
@@ -670,22 +767,24 @@ static GridView make_grid_view(const b2ndt *h) {
     G.res = h->prm.res;
     G.r2 = (float)((double)h->prm.res * (double)h->prm.res);
     G.inv_leaf = 1.0f / h->prm.res;
+    G.margin = t.max_disp * 1.0001f + 1e-5f * h->prm.res;
     G.ok = (t.L.ok && t.V > 0) ? 1 : 0;
     return G;
 }
 
 static int launch_match(b2ndt *h, const MatchArgs &A, size_t B, int C) {
     if (B == 0) return 0;
-    if (C > 8 && !h->nonportable_set) {
+    if (!h->attrs_set) {
+        B2_CUDA(cudaFuncSetAttribute(ndt_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NdtSmem)));
         B2_CUDA(cudaFuncSetAttribute(ndt_match_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-        h->nonportable_set = true;
+        h->attrs_set = true;
     }
     GridView G = make_grid_view(h);
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)(B * (size_t)C));
     cfg.blockDim = dim3(NDT_THREADS);
-    cfg.dynamicSmemBytes = 0;
+    cfg.dynamicSmemBytes = sizeof(NdtSmem);
     cfg.stream = h->st;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;

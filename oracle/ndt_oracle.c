@@ -714,7 +714,7 @@ int orc_grid_radius_search(const orc_grid *g, float qx, float qy, float qz, doub
     int lo[3], hi[3];
     for (int a = 0; a < 3; ++a) {
         double leaf = (double)g->res;
-        double m = 1e-3 * leaf;
+        double m = 0.25 * leaf; /* a float centroid can lie slightly outside its own cell */
         double l = floor(((double)q[a] - radius - m) / leaf) - (double)g->L.min_b[a];
         double h = floor(((double)q[a] + radius + m) / leaf) - (double)g->L.min_b[a];
         if (l < 0) l = 0;
