@@ -94,7 +94,7 @@ def build_hostcheck(force=False):
     src = os.path.join(CSRC, "hostcheck", "b2_hostcheck.cpp")
     if force or _newer(out, [src, os.path.join(CSRC, "b2_ndt_math.cuh")]):
         subprocess.check_call(["g++", "-O2", "-std=c++14", "-fPIC", "-shared", "-ffp-contract=off", "-Wall",
-                               "-Wno-unused-function", "-o", out, src])
+                               "-Wno-unused-function", "-Wno-unknown-pragmas", "-o", out, src])
     return out
 
 

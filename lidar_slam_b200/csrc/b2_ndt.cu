@@ -12,7 +12,8 @@
 //   leaf_idx    int32[V]       voxel linear index, ascending;  leaf_n int32[V];  leaf_start uint32[V]
 //   centroid4   float4[V]      float centroid (the kd-tree search point of PCL), intensity mean in .w
 //   gauss       double[10][V]  80-byte records {mean[3], icov xx,xy,xz,yy,yz,zz, pad}
-//   cell2leaf   int32[ncells]  dense grid: +(leaf+1) searchable (n >= min_pts), -(leaf+1) sparse, 0 empty
+//   cells       float4[ncells] dense grid record {centroid x,y,z, code}: code = +(leaf+1) searchable (n >= min_pts),
+//                              -(leaf+1) sparse, 0 empty
 // The path is a gather + reduction (no dense contraction): no tensor cores by design.
 #include <cooperative_groups.h>
 
@@ -35,7 +36,7 @@ struct TargetDev {
     float max_disp = 0.f;     // max distance of a searchable leaf's float centroid outside its own cell
     DevBuf pts_in;            // float4[N] as given (host path)
     DevBuf pts_sorted;        // float4[N]
-    DevBuf leaf_idx, leaf_n, leaf_start, centroid4, gauss, sums, icov9, cell2leaf, counters;
+    DevBuf leaf_idx, leaf_n, leaf_start, centroid4, gauss, sums, icov9, cells, counters;
     bool valid = false;
 };
 
@@ -91,7 +92,7 @@ __global__ void __launch_bounds__(128) leaf_finish_kernel(uint32_t V, int min_pt
                                                           const int32_t *__restrict__ leaf_idx, const int32_t *__restrict__ leaf_n,
                                                           const float4 *__restrict__ centroid4,
                                                           const double *__restrict__ sums, double *__restrict__ gauss,
-                                                          double *__restrict__ icov9, int32_t *__restrict__ cell2leaf,
+                                                          double *__restrict__ icov9, float4 *__restrict__ cells,
                                                           uint32_t *__restrict__ counters) {
     uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= V) return;
@@ -110,7 +111,11 @@ __global__ void __launch_bounds__(128) leaf_finish_kernel(uint32_t V, int min_pt
     double *ic = icov9 + (size_t)j * 9;
     for (int a = 0; a < 9; ++a) ic[a] = icov[a];
     const bool tree = n >= min_pts;
-    cell2leaf[leaf_idx[j]] = tree ? (int32_t)(j + 1) : -(int32_t)(j + 1);
+    {
+        // dense-grid record: the float centroid travels with the voxel code so the search needs one load
+        const float4 c = centroid4[j];
+        cells[leaf_idx[j]] = make_float4(c.x, c.y, c.z, __int_as_float(tree ? (int32_t)(j + 1) : -(int32_t)(j + 1)));
+    }
     if (tree) {
         atomicAdd(&counters[0], 1u);
         // how far the float centroid (PCL's kd-tree point) lies outside its own cell: bounds the search
@@ -135,8 +140,9 @@ __global__ void __launch_bounds__(128) leaf_finish_kernel(uint32_t V, int min_pt
 // ------------------------------------------------------------------ the NDT match kernel ------
 // One thread-block cluster (1..16 CTAs x 256 threads) per match; the whole Newton / More-Thuente loop
 // runs inside the kernel.  Each pass is WARP-LOCAL and two-phase:
-//   phase 1 (search, latency bound): lane = source point.  Float transform, the 3x3x3 window of the dense
-//     cell grid fetched with 27 independent loads, float centroid tests, hits appended to the warp's pair
+//   phase 1 (search, latency bound): lane = source point.  Float transform, then one z-plane of the
+//     3x3x3 window of the dense cell grid per step: nine independent 16-byte loads bring the voxel code
+//     AND its float centroid (no second dependent load), float L2 tests, hits appended to the warp's pair
 //     queue in shared memory at positions given by ballots (deterministic order, no atomics);
 //   phase 2 (compute, FP64 bound): lane = (point, voxel) pair taken from the queue in chunks of 32, so
 //     every lane is busy: 80-byte record gather, exp, score / gradient / Hessian terms of
@@ -144,11 +150,10 @@ __global__ void __launch_bounds__(128) leaf_finish_kernel(uint32_t V, int min_pt
 // Warps of co-resident CTAs are in different phases at any time, so gather latency hides under FP64 issue.
 constexpr int NDT_THREADS = 256;
 constexpr int NDT_WARPS = NDT_THREADS / 32;
-constexpr int QCAP = 1024;       // pair queue entries per warp: 31 left-overs + 32 lanes x (27 + slack)
+constexpr int QCAP = 576;        // pair queue entries per warp: < 32 left-overs + 32 lanes x 16 cells of a plane
 
 struct GridView {
-    const int32_t *cell2leaf;
-    const float4 *centroid4;
+    const float4 *cells;         // dense grid record {cx, cy, cz, int code}: code > 0 searchable leaf+1, < 0 sparse, 0 empty
     const double *gauss;
     int32_t min_b[3], div_b[3], mul[3];
     float res, r2;      // search radius = resolution ; r2 = (float)(res*res)
@@ -174,9 +179,11 @@ struct NdtSmem {
     double warp_part[NDT_WARPS][ACC_N];
     double cta_part[2][ACC_N];     // double-buffered per-CTA partial, read by cluster peers over DSMEM
     double total[ACC_N];
+    double trig_d[6];              // snapped double sin x3, cos x3 of the requested pose
+    float  trig_f[6];              // float sin x3, cos x3
     int go;
     int pad_;
-    uint2 queue[NDT_WARPS][QCAP];  // (source point index, leaf index)
+    float4 queue[NDT_WARPS][QCAP]; // {source x, y, z, leaf index bits}
 };
 
 __device__ __forceinline__ double dot3v(const double *h, double x, double y, double z) { return x * h[0] + y * h[1] + z * h[2]; }
@@ -188,10 +195,11 @@ __device__ __forceinline__ double dot2v(const double *h, double x, double y) { r
 // One (point, voxel) pair: computePointDerivatives (NDTM:448-482) + updateDerivatives (NDTM:485-520).
 // J = [I | c3 c4 c5] with c3 = (0,J0,J1), c4 = (J2,J3,J4), c5 = (J5,J6,J7); structural zeros of the angle
 // tables (j_ang_f/g/h and h_ang_c/e/f have no z component) are exploited.
-__device__ __forceinline__ void ndt_pair(const float4 pt, const float *__restrict__ T, const AngTab &ang,
-                                         const double *__restrict__ g, double d1, double d2, bool hess, double *acc) {
+__device__ __forceinline__ void ndt_pair(const float px, const float py, const float pz, const float *__restrict__ T,
+                                         const AngTab &ang, const double *__restrict__ g, double d1, double d2, bool hess,
+                                         double *acc) {
     float tx, ty, tz;
-    transform_f32(T, pt.x, pt.y, pt.z, tx, ty, tz);
+    transform_f32(T, px, py, pz, tx, ty, tz);
     const double2 *g2 = reinterpret_cast<const double2 *>(g);      // 80-byte record, five 16-byte loads
     const double2 a0 = __ldg(g2 + 0), a1 = __ldg(g2 + 1), a2 = __ldg(g2 + 2), a3 = __ldg(g2 + 3), a4 = __ldg(g2 + 4);
     acc[28] += 1.0;
@@ -207,7 +215,7 @@ __device__ __forceinline__ void ndt_pair(const float4 pt, const float *__restric
     if (e > 1 || e < 0 || e != e) return;      // NDTM:499-501
     const double w = e * d1;
     acc[0] += sinc;
-    const double x = (double)pt.x, y = (double)pt.y, z = (double)pt.z;
+    const double x = (double)px, y = (double)py, z = (double)pz;
     double J[8];
     J[0] = dot3v(ang.j[0], x, y, z); J[1] = dot3v(ang.j[1], x, y, z);
     J[2] = dot3v(ang.j[2], x, y, z); J[3] = dot3v(ang.j[3], x, y, z); J[4] = dot3v(ang.j[4], x, y, z);
@@ -265,6 +273,24 @@ __device__ __forceinline__ void ndt_pair(const float4 pt, const float *__restric
     }
 }
 
+// warp 0 completes a pass request: the twelve sin/cos evaluations run on twelve lanes
+__device__ __forceinline__ void finish_request_warp0(NdtSmem &S, int lane) {
+    __syncwarp();
+    if (S.ctl.need_trig) {
+        if (lane < 12) {
+            const int k = lane % 3;
+            const double a = S.ctl.x_req[3 + k];
+            if (lane < 3) S.trig_f[k] = sin_f32((float)a);
+            else if (lane < 6) S.trig_f[3 + k] = cos_f32((float)a);
+            else if (lane < 9) S.trig_d[k] = ang_sin(a);
+            else S.trig_d[3 + k] = ang_cos(a);
+        }
+        __syncwarp();
+        if (lane == 0) ctl_finish_request(S.ctl, &S.trig_f[0], &S.trig_f[3], &S.trig_d[0], &S.trig_d[3]);
+    }
+    __syncwarp();
+}
+
 __global__ void __launch_bounds__(NDT_THREADS, 2) ndt_match_kernel(GridView G, NdtConst K, MatchArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     NdtSmem &S = *reinterpret_cast<NdtSmem *>(smem_raw);
@@ -279,20 +305,24 @@ __global__ void __launch_bounds__(NDT_THREADS, 2) ndt_match_kernel(GridView G, N
     if (A.offsets) { first = A.offsets[match]; last = A.offsets[match + 1]; }
     const uint32_t npts = last - first;
 
-    if (tid == 0) {
-        if (A.deriv_only) {
-            const double *p = A.poses6 + (size_t)match * 6;
-            for (int i = 0; i < 6; ++i) S.ctl.p[i] = S.ctl.x_t[i] = p[i];
-            ctl_request(S.ctl, p, 1, ST_INIT);
-            S.ctl.passes = 0; S.ctl.pairs = 0;
-        } else {
-            ctl_start(S.ctl, K, A.guesses + (size_t)match * 16, (double)npts);
+    if (warp == 0) {
+        if (lane == 0) {
+            if (A.deriv_only) {
+                const double *p = A.poses6 + (size_t)match * 6;
+                for (int i = 0; i < 6; ++i) S.ctl.p[i] = S.ctl.x_t[i] = p[i];
+                ctl_request(S.ctl, p, 1, ST_INIT);
+                S.ctl.passes = 0; S.ctl.pairs = 0;
+            } else {
+                ctl_start(S.ctl, K, A.guesses + (size_t)match * 16, (double)npts);
+            }
+            S.go = 1;
         }
-        S.go = 1;
+        finish_request_warp0(S, lane);
     }
     __syncthreads();
 
-    uint2 *queue = S.queue[warp];
+    float4 *queue = S.queue[warp];
+    const uint32_t stride = C * NDT_WARPS * 32u;
     int parity = 0;
     while (true) {
         const bool hess = S.ctl.hess != 0;
@@ -301,108 +331,117 @@ __global__ void __launch_bounds__(NDT_THREADS, 2) ndt_match_kernel(GridView G, N
         for (int i = 0; i < ACC_N; ++i) acc[i] = 0.0;
         const float *T = S.ctl.T;
         const AngTab &ang = S.ctl.ang;
-        uint32_t qn = 0;       // warp-uniform: entries in the queue
-        // -------- this warp's share of the source points, 32 at a time --------
-        for (uint32_t base = first + (crank * NDT_WARPS + warp) * 32u; base < last; base += C * NDT_WARPS * 32u) {
-            const uint32_t i = base + lane;
-            int ex0 = -1, ex1 = -1, ex2 = -1;         // window extents - 1 ; -1 = no window
-            size_t wbase = 0;
-            float tx = 0.f, ty = 0.f, tz = 0.f;
-            bool slow = false;
-            float4 pt = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (i < last && G.ok) {
-                pt = __ldg(&A.src[i]);
-                transform_f32(T, pt.x, pt.y, pt.z, tx, ty, tz);
-                if (finite3(tx, ty, tz)) {
-                    // every cell that can hold a centroid within the radius (centroids may sit up to
-                    // G.margin outside their own cell; the slack also covers the rounding of this arithmetic)
-                    const float q[3] = {tx, ty, tz};
-                    int lo[3], ex[3];
-                    bool empty = false;
+        // warp-uniform state of the search / compute pipeline
+        uint32_t qn = 0;
+        uint32_t base = first + (crank * NDT_WARPS + warp) * 32u;
+        int plane = 0, nplanes = 0;
+        bool have_round = false, wide = false;
+        // per-lane state of the current round (32 source points)
+        float px = 0.f, py = 0.f, pz = 0.f, tx = 0.f, ty = 0.f, tz = 0.f;
+        int ex0 = -1, ex1 = -1, ex2 = -1;
+        size_t wbase = 0;
+        while (true) {
+            if (!have_round && base < last) {
+                // ---- new round: transform 32 points, window of candidate cells per lane ----
+                const uint32_t i = base + lane;
+                ex0 = ex1 = ex2 = -1;
+                wbase = 0;
+                if (i < last && G.ok) {
+                    const float4 pt = __ldg(&A.src[i]);
+                    px = pt.x; py = pt.y; pz = pt.z;
+                    transform_f32(T, px, py, pz, tx, ty, tz);
+                    if (finite3(tx, ty, tz)) {
+                        // every cell that can hold a centroid within the radius (centroids may sit up to
+                        // G.margin outside their own cell; the slack also covers the rounding of this arithmetic)
+                        const float q[3] = {tx, ty, tz};
+                        int lo[3], ex[3];
+                        bool empty = false;
 #pragma unroll
-                    for (int a = 0; a < 3; ++a) {
-                        const float mg = G.margin + 1e-6f * fabsf(q[a]);
-                        int l = (int)floorf((q[a] - G.res - mg) * G.inv_leaf) - G.min_b[a];
-                        int h = (int)floorf((q[a] + G.res + mg) * G.inv_leaf) - G.min_b[a];
-                        l = max(l, 0); h = min(h, G.div_b[a] - 1);
-                        lo[a] = l; ex[a] = h - l;
-                        empty = empty || (h < l);
-                    }
-                    if (!empty) {
-                        slow = (ex[0] > 2) || (ex[1] > 2) || (ex[2] > 2);
-                        if (!slow) { ex0 = ex[0]; ex1 = ex[1]; ex2 = ex[2]; }
-                        wbase = (size_t)lo[0] + (size_t)lo[1] * G.mul[1] + (size_t)lo[2] * G.mul[2];
-                        if (slow) {
-                            // window wider than 3 cells (query within `margin` of a cell face): rare, handled
-                            // by this lane alone without the queue
-                            for (int kz = 0; kz <= ex[2]; ++kz)
-                                for (int ky = 0; ky <= ex[1]; ++ky)
-                                    for (int kx = 0; kx <= ex[0]; ++kx) {
-                                        const int32_t v = __ldg(G.cell2leaf + wbase + kx + (size_t)ky * G.mul[1] + (size_t)kz * G.mul[2]);
-                                        if (v <= 0) continue;
-                                        const float4 c = __ldg(&G.centroid4[v - 1]);
-                                        const float dx = __fsub_rn(tx, c.x), dy = __fsub_rn(ty, c.y), dz = __fsub_rn(tz, c.z);
-                                        const float d2f = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-                                        if (d2f < G.r2) ndt_pair(pt, T, ang, G.gauss + (size_t)(v - 1) * 10, K.d1, K.d2, hess, acc);
-                                    }
+                        for (int a = 0; a < 3; ++a) {
+                            const float mg = G.margin + 1e-6f * fabsf(q[a]);
+                            int l = (int)floorf((q[a] - G.res - mg) * G.inv_leaf) - G.min_b[a];
+                            int h = (int)floorf((q[a] + G.res + mg) * G.inv_leaf) - G.min_b[a];
+                            l = max(l, 0); h = min(h, G.div_b[a] - 1);
+                            lo[a] = l; ex[a] = min(h - l, 3);      // the window never exceeds 4 cells (margin << cell)
+                            empty = empty || (h < l);
+                        }
+                        if (!empty) {
+                            ex0 = ex[0]; ex1 = ex[1]; ex2 = ex[2];
+                            wbase = (size_t)lo[0] + (size_t)lo[1] * G.mul[1] + (size_t)lo[2] * G.mul[2];
                         }
                     }
                 }
+                nplanes = __reduce_max_sync(0xffffffffu, ex2 + 1);
+                wide = __any_sync(0xffffffffu, (ex0 > 2) || (ex1 > 2));
+                plane = 0;
+                have_round = true;
             }
-            // ---- phase 1: the 3x3x3 window, 27 independent loads ----
-            const int32_t *wp = G.cell2leaf + wbase;
-            int32_t v[27];
+            if (have_round) {
+                if (plane < nplanes) {
+                    // ---- phase 1: one z-plane of the window ----
+                    const bool act = plane <= ex2;
+                    const float4 *wp = G.cells + wbase + (size_t)plane * G.mul[2];
+                    if (!wide) {
+                        float4 c[9];
 #pragma unroll
-            for (int dz = 0; dz < 3; ++dz)
+                        for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
-                for (int dy = 0; dy < 3; ++dy)
+                            for (int dx = 0; dx < 3; ++dx) {
+                                c[dy * 3 + dx] = make_float4(0.f, 0.f, 0.f, 0.f);
+                                if (act && dx <= ex0 && dy <= ex1) c[dy * 3 + dx] = __ldg(wp + dx + (size_t)dy * G.mul[1]);
+                            }
 #pragma unroll
-                    for (int dx = 0; dx < 3; ++dx) {
-                        const bool in = (dx <= ex0) && (dy <= ex1) && (dz <= ex2);
-                        v[dz * 9 + dy * 3 + dx] = in ? __ldg(wp + dx + (size_t)dy * G.mul[1] + (size_t)dz * G.mul[2]) : 0;
+                        for (int k = 0; k < 9; ++k) {
+                            // flann::L2_Simple<float>: (dx*dx + dy*dy) + dz*dz, accepted when < (float)(r*r)
+                            const float dx = __fsub_rn(tx, c[k].x), dy = __fsub_rn(ty, c[k].y), dz = __fsub_rn(tz, c[k].z);
+                            const float d2f = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+                            const int code = __float_as_int(c[k].w);
+                            const bool hit = (code > 0) && (d2f < G.r2);
+                            const uint32_t b = __ballot_sync(0xffffffffu, hit);
+                            if (hit) queue[qn + __popc(b & lt)] = make_float4(px, py, pz, __int_as_float(code - 1));
+                            qn += __popc(b);
+                        }
+                    } else {
+                        // some lane's window is 4 cells wide (query within `margin` of a cell face): rare
+                        for (int dy = 0; dy < 4; ++dy)
+                            for (int dx = 0; dx < 4; ++dx) {
+                                float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+                                if (act && dx <= ex0 && dy <= ex1) c = __ldg(wp + dx + (size_t)dy * G.mul[1]);
+                                const float ddx = __fsub_rn(tx, c.x), ddy = __fsub_rn(ty, c.y), ddz = __fsub_rn(tz, c.z);
+                                const float d2f = __fadd_rn(__fadd_rn(__fmul_rn(ddx, ddx), __fmul_rn(ddy, ddy)), __fmul_rn(ddz, ddz));
+                                const int code = __float_as_int(c.w);
+                                const bool hit = (code > 0) && (d2f < G.r2);
+                                const uint32_t b = __ballot_sync(0xffffffffu, hit);
+                                if (hit) queue[qn + __popc(b & lt)] = make_float4(px, py, pz, __int_as_float(code - 1));
+                                qn += __popc(b);
+                            }
                     }
-#pragma unroll
-            for (int r = 0; r < 9; ++r) {          // one x-row of the window at a time: 3 centroid loads in flight
-                float4 c[3];
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    c[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (v[r * 3 + k] > 0) c[k] = __ldg(&G.centroid4[v[r * 3 + k] - 1]);
                 }
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    // flann::L2_Simple<float>: (dx*dx + dy*dy) + dz*dz, accepted when < (float)(r*r)
-                    const float dx = __fsub_rn(tx, c[k].x), dy = __fsub_rn(ty, c[k].y), dzz = __fsub_rn(tz, c[k].z);
-                    const float d2f = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dzz, dzz));
-                    const bool hit = (v[r * 3 + k] > 0) && (d2f < G.r2);
-                    const uint32_t b = __ballot_sync(0xffffffffu, hit);
-                    if (hit) queue[qn + __popc(b & lt)] = make_uint2(i, (uint32_t)(v[r * 3 + k] - 1));
-                    qn += __popc(b);
-                }
+                ++plane;
+                if (plane >= nplanes) { have_round = false; base += stride; }
             }
+            const bool flush = !have_round && base >= last;
             __syncwarp();
-            // ---- phase 2: full chunks of 32 pairs ----
+            // ---- phase 2: chunks of 32 pairs (single call site of the pair arithmetic) ----
             uint32_t qh = 0;
-            while (qn - qh >= 32u) {
-                const uint2 e = queue[qh + lane];
-                ndt_pair(__ldg(&A.src[e.x]), T, ang, G.gauss + (size_t)e.y * 10, K.d1, K.d2, hess, acc);
+            while (qh + 32u <= qn || (flush && qh < qn)) {
+                if (qh + lane < qn) {
+                    const float4 e = queue[qh + lane];
+                    ndt_pair(e.x, e.y, e.z, T, ang, G.gauss + (size_t)__float_as_int(e.w) * 10, K.d1, K.d2, hess, acc);
+                }
                 qh += 32u;
             }
             if (qh) {      // move the left-over (< 32 entries) to the front
-                const uint32_t rem = qn - qh;
-                uint2 e = make_uint2(0u, 0u);
+                const uint32_t rem = qn > qh ? qn - qh : 0u;
+                float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
                 if ((uint32_t)lane < rem) e = queue[qh + lane];
                 __syncwarp();
                 if ((uint32_t)lane < rem) queue[lane] = e;
                 qn = rem;
                 __syncwarp();
             }
+            if (flush) break;
         }
-        if ((uint32_t)lane < qn) {     // tail: partial chunk
-            const uint2 e = queue[lane];
-            ndt_pair(__ldg(&A.src[e.x]), T, ang, G.gauss + (size_t)e.y * 10, K.d1, K.d2, hess, acc);
-        }
-        __syncwarp();
         // ---------------- deterministic reduction: warp butterfly -> CTA -> cluster (fixed order) -----
 #pragma unroll
         for (int i = 0; i < ACC_N; ++i) {
@@ -430,8 +469,13 @@ __global__ void __launch_bounds__(NDT_THREADS, 2) ndt_match_kernel(GridView G, N
             if (tid < ACC_N) S.total[tid] = S.cta_part[parity][tid];
         }
         __syncthreads();
-        // ---------------- controller: Newton step + More-Thuente state machine (thread 0) -------------
-        if (tid == 0) S.go = A.deriv_only ? 0 : ctl_step(S.ctl, K, S.total);
+        // ---------------- controller: Newton step + More-Thuente state machine (warp 0) ----------------
+        if (warp == 0) {
+            int go = 0;
+            if (lane == 0) { go = A.deriv_only ? 0 : ctl_step(S.ctl, K, S.total); S.go = go; }
+            go = __shfl_sync(0xffffffffu, go, 0);
+            if (go) finish_request_warp0(S, lane);
+        }
         __syncthreads();
         if (!S.go) break;
         parity ^= 1;
@@ -459,7 +503,7 @@ __global__ void __launch_bounds__(NDT_THREADS, 2) ndt_match_kernel(GridView G, N
 // pcl::Registration::getFitnessScore: per transformed source point the exact nearest target POINT
 // (float squared L2), found by expanding Chebyshev rings over the voxel buckets of the target.
 struct FitView {
-    const int32_t *cell2leaf;
+    const float4 *cells;
     const uint32_t *leaf_start;
     const int32_t *leaf_n;
     const float4 *pts_sorted;
@@ -474,7 +518,7 @@ constexpr int FIT_THREADS = 128;
 constexpr int FIT_RMAX = 8;
 
 __device__ __forceinline__ void fit_cell(const FitView &F, int kx, int ky, int kz, float qx, float qy, float qz, float &best) {
-    const int32_t v = __ldg(F.cell2leaf + (size_t)kx + (size_t)ky * F.mul[1] + (size_t)kz * F.mul[2]);
+    const int32_t v = __float_as_int(__ldg(F.cells + (size_t)kx + (size_t)ky * F.mul[1] + (size_t)kz * F.mul[2]).w);
     if (v == 0) return;
     const int j = (v > 0 ? v : -v) - 1;
     const uint32_t s = __ldg(&F.leaf_start[j]);
@@ -612,7 +656,7 @@ extern "C" void b2ndt_destroy(b2ndt *h) {
     h->pipe.release();
     TargetDev &t = h->tgt;
     t.pts_in.release(); t.pts_sorted.release(); t.leaf_idx.release(); t.leaf_n.release(); t.leaf_start.release();
-    t.centroid4.release(); t.gauss.release(); t.sums.release(); t.icov9.release(); t.cell2leaf.release(); t.counters.release();
+    t.centroid4.release(); t.gauss.release(); t.sums.release(); t.icov9.release(); t.cells.release(); t.counters.release();
     h->d_src.release(); h->d_guess.release(); h->d_pose.release(); h->d_res.release(); h->d_off.release();
     h->d_p6.release(); h->d_acc.release(); h->d_fit_sum.release(); h->d_fit_cnt.release();
     h->h_stage.release(); h->h_small.release(); h->h_res.release();
@@ -670,9 +714,9 @@ static int build_target(b2ndt *h, const float4 *d_pts, size_t n) {
     if ((rc = t.gauss.reserve((size_t)(V + 1) * 80))) return rc;
     if ((rc = t.sums.reserve((size_t)(V + 1) * 72))) return rc;
     if ((rc = t.icov9.reserve((size_t)(V + 1) * 72))) return rc;
-    if ((rc = t.cell2leaf.reserve((size_t)t.L.ncells * 4 + 16))) return rc;
+    if ((rc = t.cells.reserve((size_t)t.L.ncells * 16 + 16))) return rc;
     if ((rc = t.counters.reserve(64))) return rc;
-    B2_CUDA(cudaMemsetAsync(t.cell2leaf.p, 0, (size_t)t.L.ncells * 4, h->st));
+    B2_CUDA(cudaMemsetAsync(t.cells.p, 0, (size_t)t.L.ncells * 16, h->st));
     B2_CUDA(cudaMemsetAsync(t.counters.p, 0, 64, h->st));
     if (V) {
         unsigned blocks = (V + 7) / 8;
@@ -686,7 +730,7 @@ static int build_target(b2ndt *h, const float4 *d_pts, size_t n) {
         for (int a = 0; a < 3; ++a) { LA.min_b[a] = t.L.min_b[a]; LA.div_b[a] = t.L.div_b[a]; LA.inv[a] = t.L.inv[a]; }
         leaf_finish_kernel<<<(V + 127) / 128, 128, 0, h->st>>>(V, h->prm.min_pts, h->prm.eig_mult, LA, t.leaf_idx.as<int32_t>(),
                                                               t.leaf_n.as<int32_t>(), t.centroid4.as<float4>(), t.sums.as<double>(),
-                                                              t.gauss.as<double>(), t.icov9.as<double>(), t.cell2leaf.as<int32_t>(),
+                                                              t.gauss.as<double>(), t.icov9.as<double>(), t.cells.as<float4>(),
                                                               t.counters.as<uint32_t>());
         B2_LAUNCH_CHECK();
     }
@@ -760,8 +804,7 @@ static GridView make_grid_view(const b2ndt *h) {
     GridView G;
     memset(&G, 0, sizeof(G));
     const TargetDev &t = h->tgt;
-    G.cell2leaf = t.cell2leaf.as<int32_t>();
-    G.centroid4 = t.centroid4.as<float4>();
+    G.cells = t.cells.as<float4>();
     G.gauss = t.gauss.as<double>();
     for (int a = 0; a < 3; ++a) { G.min_b[a] = t.L.min_b[a]; G.div_b[a] = t.L.div_b[a]; G.mul[a] = t.L.mul[a]; }
     G.res = h->prm.res;
@@ -930,7 +973,7 @@ static int fitness_device(b2ndt *h, const float4 *d_src, size_t n, const float p
     if (n == 0 || !t.L.ok || t.V == 0) { *out = DBL_MAX; return 0; }
     FitView F;
     memset(&F, 0, sizeof(F));
-    F.cell2leaf = t.cell2leaf.as<int32_t>(); F.leaf_start = t.leaf_start.as<uint32_t>(); F.leaf_n = t.leaf_n.as<int32_t>();
+    F.cells = t.cells.as<float4>(); F.leaf_start = t.leaf_start.as<uint32_t>(); F.leaf_n = t.leaf_n.as<int32_t>();
     F.pts_sorted = t.pts_sorted.as<float4>(); F.N = t.L.n_finite;
     for (int a = 0; a < 3; ++a) { F.min_b[a] = t.L.min_b[a]; F.div_b[a] = t.L.div_b[a]; F.mul[a] = t.L.mul[a]; }
     F.res = h->prm.res; F.inv_leaf = 1.0f / h->prm.res; F.ok = 1;

@@ -18,9 +18,11 @@
 #ifdef __CUDACC__
 #define B2_HD __host__ __device__ __forceinline__
 #define B2_HD_NOINLINE __host__ __device__
+#define B2_SVD_ATTR __host__ __device__ __noinline__
 #else
 #define B2_HD inline
 #define B2_HD_NOINLINE
+#define B2_SVD_ATTR inline
 #endif
 
 namespace b2 {
@@ -60,8 +62,7 @@ B2_HD float atan2_f32(float y, float x) { return (float)atan2((double)y, (double
 // ------------------------------------------------------------------ pose <-> matrix ----------
 // (Translation(p0,p1,p2) * AngleAxis(p3,X) * AngleAxis(p4,Y) * AngleAxis(p5,Z)).matrix() in float
 // (NDTM:370-373, 691-694); T column-major.
-B2_HD void rot_axis_f32(int axis, float ang, float R[9]) {
-    float s = sin_f32(ang), c = cos_f32(ang);
+B2_HD void rot_axis_sc_f32(int axis, float s, float c, float R[9]) {
     float one_c = fsub(1.0f, c);
     float e[3] = {0.f, 0.f, 0.f};
     e[axis] = 1.0f;
@@ -79,17 +80,23 @@ B2_HD void mat3_mul_f32(const float A[9], const float Bm[9], float C[9]) {
             C[i * 3 + j] = fadd(fadd(fmul(A[i * 3 + 0], Bm[0 * 3 + j]), fmul(A[i * 3 + 1], Bm[1 * 3 + j])),
                                 fmul(A[i * 3 + 2], Bm[2 * 3 + j]));
 }
-B2_HD_NOINLINE inline void pose_to_matrix_f32(const double p[6], float T[16]) {
+// fs[k] / fc[k] = sin_f32 / cos_f32 of (float)p[3+k]
+B2_HD_NOINLINE inline void pose_to_matrix_sc_f32(const double p[6], const float fs[3], const float fc[3], float T[16]) {
     float Rx[9], Ry[9], Rz[9], Rxy[9], R[9];
-    rot_axis_f32(0, (float)p[3], Rx);
-    rot_axis_f32(1, (float)p[4], Ry);
-    rot_axis_f32(2, (float)p[5], Rz);
+    rot_axis_sc_f32(0, fs[0], fc[0], Rx);
+    rot_axis_sc_f32(1, fs[1], fc[1], Ry);
+    rot_axis_sc_f32(2, fs[2], fc[2], Rz);
     mat3_mul_f32(Rx, Ry, Rxy);
     mat3_mul_f32(Rxy, Rz, R);
     for (int r = 0; r < 3; ++r)
         for (int c = 0; c < 3; ++c) T[c * 4 + r] = R[r * 3 + c];
     T[3] = T[7] = T[11] = 0.0f;
     T[12] = (float)p[0]; T[13] = (float)p[1]; T[14] = (float)p[2]; T[15] = 1.0f;
+}
+B2_HD_NOINLINE inline void pose_to_matrix_f32(const double p[6], float T[16]) {
+    float fs[3], fc[3];
+    for (int k = 0; k < 3; ++k) { fs[k] = sin_f32((float)p[3 + k]); fc[k] = cos_f32((float)p[3 + k]); }
+    pose_to_matrix_sc_f32(p, fs, fc, T);
 }
 
 // Transform<float,3,Affine>::rotation() = U V^T of JacobiSVD<Matrix3f>(linear) (Eigen Transform.h
@@ -210,11 +217,14 @@ struct AngTab {
     double j[8][3];
     double h[15][3];
 };
+// snapped trig of NDTM:527-549: |angle| < 10e-5 -> (cos, sin) = (1, 0)
+B2_HD double ang_sin(double a) { return (fabs(a) < 10e-5) ? 0.0 : sin(a); }
+B2_HD double ang_cos(double a) { return (fabs(a) < 10e-5) ? 1.0 : cos(a); }
+B2_HD_NOINLINE inline void angle_derivatives_sc(double sx, double cx, double sy, double cy, double sz, double cz, AngTab &A);
 B2_HD_NOINLINE inline void angle_derivatives(const double p[6], AngTab &A) {
-    double cx, cy, cz, sx, sy, sz;
-    if (fabs(p[3]) < 10e-5) { cx = 1.0; sx = 0.0; } else { cx = cos(p[3]); sx = sin(p[3]); }
-    if (fabs(p[4]) < 10e-5) { cy = 1.0; sy = 0.0; } else { cy = cos(p[4]); sy = sin(p[4]); }
-    if (fabs(p[5]) < 10e-5) { cz = 1.0; sz = 0.0; } else { cz = cos(p[5]); sz = sin(p[5]); }
+    angle_derivatives_sc(ang_sin(p[3]), ang_cos(p[3]), ang_sin(p[4]), ang_cos(p[4]), ang_sin(p[5]), ang_cos(p[5]), A);
+}
+B2_HD_NOINLINE inline void angle_derivatives_sc(double sx, double cx, double sy, double cy, double sz, double cz, AngTab &A) {
     double (*j)[3] = A.j;
     double (*h)[3] = A.h;
     j[0][0] = -sx * sz + cx * sy * cz; j[0][1] = -sx * cz - cx * sy * sz; j[0][2] = -cx * cy;
@@ -363,7 +373,7 @@ B2_HD void rot_plane_d(double *x, int incx, double *y, int incy, int n, double c
         y[i * incy] = -s * xi + c * yi;
     }
 }
-B2_HD_NOINLINE inline int svd_solve6(const double Hin[36], const double b[6], double x[6]) {
+B2_SVD_ATTR int svd_solve6(const double Hin[36], const double b[6], double x[6]) {
     enum { N = 6 };
     double W[36], U[36], V[36], sv[6];
 #define M_(A, r, c) (A)[(c) * N + (r)]
@@ -454,28 +464,52 @@ B2_HD_NOINLINE inline int svd_solve6(const double Hin[36], const double b[6], do
 // rank-truncation semantics of Eigen's solve() are kept for (near-)singular Hessians.
 B2_HD_NOINLINE inline double lu_solve6(const double Hin[36], const double b[6], double x[6]) {
     enum { N = 6 };
+    // fully unrolled with static indices so the augmented matrix lives in registers (no local memory):
+    // partial pivoting is done by compare-and-swap sweeps that leave the largest |entry| in row k.
     double A[N][N + 1];
-    for (int r = 0; r < N; ++r) { for (int c = 0; c < N; ++c) A[r][c] = Hin[c * N + r]; A[r][N] = b[r]; }
+#pragma unroll
+    for (int r = 0; r < N; ++r) {
+#pragma unroll
+        for (int c = 0; c < N; ++c) A[r][c] = Hin[c * N + r];
+        A[r][N] = b[r];
+    }
     double pmin = DBL_MAX, pmax = 0.0;
+    bool singular = false;
+#pragma unroll
     for (int k = 0; k < N; ++k) {
-        int piv = k;
-        double best = fabs(A[k][k]);
-        for (int r = k + 1; r < N; ++r) { double v = fabs(A[r][k]); if (v > best) { best = v; piv = r; } }
-        if (!(best > 0.0)) return 0.0;   // singular (or NaN)
-        if (piv != k) for (int c = k; c <= N; ++c) { double t = A[k][c]; A[k][c] = A[piv][c]; A[piv][c] = t; }
-        if (best < pmin) pmin = best;
-        if (best > pmax) pmax = best;
-        double inv = 1.0 / A[k][k];
+#pragma unroll
         for (int r = k + 1; r < N; ++r) {
-            double f = A[r][k] * inv;
+            const bool sw = fabs(A[r][k]) > fabs(A[k][k]);
+#pragma unroll
+            for (int c = k; c <= N; ++c) {
+                const double u = A[k][c], v = A[r][c];
+                A[k][c] = sw ? v : u;
+                A[r][c] = sw ? u : v;
+            }
+        }
+        const double best = fabs(A[k][k]);
+        if (!(best > 0.0)) singular = true;   // zero or NaN pivot
+        pmin = fmin(pmin, best);
+        pmax = fmax(pmax, best);
+        const double inv = 1.0 / A[k][k];
+#pragma unroll
+        for (int r = k + 1; r < N; ++r) {
+            const double f = A[r][k] * inv;
+#pragma unroll
             for (int c = k + 1; c <= N; ++c) A[r][c] -= f * A[k][c];
         }
     }
+    double xs[N];
+#pragma unroll
     for (int r = N - 1; r >= 0; --r) {
         double s = A[r][N];
-        for (int c = r + 1; c < N; ++c) s -= A[r][c] * x[c];
-        x[r] = s / A[r][r];
+#pragma unroll
+        for (int c = r + 1; c < N; ++c) s -= A[r][c] * xs[c];
+        xs[r] = s / A[r][r];
     }
+#pragma unroll
+    for (int r = 0; r < N; ++r) x[r] = xs[r];
+    if (singular) return 0.0;
     return pmin / pmax;
 }
 
@@ -556,6 +590,8 @@ struct Ctl {
     AngTab ang;
     int    hess;
     int    state;
+    int    need_trig;   // 0: request complete; 1: T and angle tables must be built from x_req; 2: tables only
+    double x_req[6];    // pose the pending request refers to
     // optimiser state
     double p[6], x_t[6], dir[6];
     double score, g[6], H[36];
@@ -582,12 +618,36 @@ B2_HD void ctl_unpack_acc(Ctl &c, const double *acc, bool take_score_grad, bool 
     c.passes++;
 }
 
+// A request is completed in two steps so that the twelve sin/cos evaluations can be spread over the
+// lanes of a warp on the GPU: ctl_request records the pose, ctl_finish_request builds the float pose
+// matrix (NDTM:691-694) and the angle tables (NDTM:523-645) from the trig values.
 B2_HD void ctl_request(Ctl &c, const double x[6], int hess, int state) {
-    pose_to_matrix_f32(x, c.T);
-    for (int i = 0; i < 16; ++i) c.finalT[i] = c.T[i];
-    angle_derivatives(x, c.ang);
+    for (int i = 0; i < 6; ++i) c.x_req[i] = x[i];
+    c.need_trig = 1;
     c.hess = hess;
     c.state = state;
+}
+// fs/fc: float sin/cos of (float)x_req[3+k] (pose matrix);  ds/dc: snapped double sin/cos of x_req[3+k]
+B2_HD void ctl_trig_serial(const Ctl &c, float fs[3], float fc[3], double ds[3], double dc[3]) {
+    for (int k = 0; k < 3; ++k) {
+        fs[k] = sin_f32((float)c.x_req[3 + k]); fc[k] = cos_f32((float)c.x_req[3 + k]);
+        ds[k] = ang_sin(c.x_req[3 + k]); dc[k] = ang_cos(c.x_req[3 + k]);
+    }
+}
+B2_HD_NOINLINE inline void ctl_finish_request(Ctl &c, const float fs[3], const float fc[3], const double ds[3], const double dc[3]) {
+    if (c.need_trig == 1) {
+        pose_to_matrix_sc_f32(c.x_req, fs, fc, c.T);
+        for (int i = 0; i < 16; ++i) c.finalT[i] = c.T[i];
+    }
+    angle_derivatives_sc(ds[0], dc[0], ds[1], dc[1], ds[2], dc[2], c.ang);
+    c.need_trig = 0;
+}
+B2_HD void ctl_finish_request_serial(Ctl &c) {
+    if (!c.need_trig) return;
+    float fs[3], fc[3];
+    double ds[3], dc[3];
+    ctl_trig_serial(c, fs, fc, ds, dc);
+    ctl_finish_request(c, fs, fc, ds, dc);
 }
 
 // start: guess (column-major float 4x4).  Sets up the initial pass (NDTM:323-346).
@@ -601,7 +661,8 @@ B2_HD_NOINLINE inline void ctl_start(Ctl &c, const NdtConst &k, const float gues
     euler_from_matrix_f32(c.finalT, ang);
     c.p[0] = (double)c.finalT[12]; c.p[1] = (double)c.finalT[13]; c.p[2] = (double)c.finalT[14];
     c.p[3] = (double)ang[0]; c.p[4] = (double)ang[1]; c.p[5] = (double)ang[2];
-    angle_derivatives(c.p, c.ang);
+    for (int i = 0; i < 6; ++i) c.x_req[i] = c.p[i];
+    c.need_trig = 2;          // T is the guess itself; only the angle tables are needed
     c.hess = 1;
     c.state = ST_INIT;
     c.nr_iter = 0; c.converged = 0; c.passes = 0; c.mt_trials = 0; c.pairs = 0;
@@ -675,6 +736,7 @@ B2_HD_NOINLINE inline int ctl_step(Ctl &c, const NdtConst &k, const double *acc)
             // same pose, Hessian only
             c.hess = 1;
             c.state = ST_MT_HESS;
+            c.need_trig = 0;
             return 1;
         }
         finish_iter = true;

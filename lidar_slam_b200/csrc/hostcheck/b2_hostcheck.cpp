@@ -35,14 +35,21 @@ void *hc_ctl_new(double d1, double d2, double step_size, double trans_eps, int m
     return h;
 }
 void hc_ctl_free(void *h) { delete (hc_ctl *)h; }
-void hc_ctl_start(void *h, const float *guess, double npoints) { ctl_start(((hc_ctl *)h)->c, ((hc_ctl *)h)->k, guess, npoints); }
-int hc_ctl_step(void *h, const double *acc29) { return ctl_step(((hc_ctl *)h)->c, ((hc_ctl *)h)->k, acc29); }
+void hc_ctl_start(void *h, const float *guess, double npoints) {
+    ctl_start(((hc_ctl *)h)->c, ((hc_ctl *)h)->k, guess, npoints);
+    ctl_finish_request_serial(((hc_ctl *)h)->c);
+}
+int hc_ctl_step(void *h, const double *acc29) {
+    int go = ctl_step(((hc_ctl *)h)->c, ((hc_ctl *)h)->k, acc29);
+    if (go) ctl_finish_request_serial(((hc_ctl *)h)->c);
+    return go;
+}
 // request of the next pass
 void hc_ctl_request(void *h, float *T16, double *x6, int *hess) {
     Ctl &c = ((hc_ctl *)h)->c;
     std::memcpy(T16, c.T, 64);
     // pose the angle tables were built for: p before the first Newton step, x_t afterwards
-    for (int i = 0; i < 6; ++i) x6[i] = (c.state == ST_INIT) ? c.p[i] : c.x_t[i];
+    for (int i = 0; i < 6; ++i) x6[i] = c.x_req[i];
     *hess = c.hess;
 }
 void hc_ctl_result(void *h, float *finalT, double *p6, double *score, double *tp, int *iters, int *conv, int *passes, int *mt) {
