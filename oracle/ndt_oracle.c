@@ -556,7 +556,7 @@ void orc_gauss_constants(double outlier_ratio, float resolution, double *d1, dou
 
 void orc_params_default(orc_params *p) {
     p->res = 1.0f; p->step_size = 0.1; p->trans_eps = 0.01; p->outlier_ratio = 0.55;
-    p->max_iter = 30; p->min_pts = 6; p->eig_mult = 0.01; p->pcl17_compat = 1;
+    p->max_iter = 30; p->min_pts = 6; p->eig_mult = 0.01; p->pcl17_compat = 1; p->intree_compat = 0;
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -619,6 +619,7 @@ orc_grid *orc_grid_build(orc_cloud tgt, float res, int min_pts, double eig_mult)
         int n = (int)(e - s);
         lf->n_raw = n;
         lf->nr_points = n;
+        lf->weight = 1.0;
         /* first pass of applyFilter: per point, in input order (std::map leaf accumulates as the
          * cloud is walked): mean_ += p (double), cov_ += p p^T (double, cov_ starts at Identity),
          * centroid += (x,y,z,intensity) (float) */
@@ -692,6 +693,49 @@ orc_grid *orc_grid_build(orc_cloud tgt, float res, int min_pts, double eig_mult)
     return g;
 }
 
+static int cmp_leaf_idx(const void *a, const void *b) {
+    const orc_leaf *x = (const orc_leaf *)a, *y = (const orc_leaf *)b;
+    return x->idx < y->idx ? -1 : (x->idx > y->idx);
+}
+
+orc_grid *orc_grid_from_leaves(size_t n, const int32_t *ijk, const double *mean3, const double *icov9,
+                               const double *weight, float res) {
+    orc_grid *g = (orc_grid *)calloc(1, sizeof(orc_grid));
+    g->res = res;
+    g->min_pts = 1;
+    g->hcap = 16;
+    while (g->hcap < 2 * n + 16) g->hcap <<= 1;
+    g->hkey = (int32_t *)malloc(g->hcap * sizeof(int32_t));
+    g->hval = (int32_t *)malloc(g->hcap * sizeof(int32_t));
+    memset(g->hkey, 0xff, g->hcap * sizeof(int32_t));
+    g->n_leaves = n;
+    g->leaves = (orc_leaf *)calloc(n ? n : 1, sizeof(orc_leaf));
+    if (n == 0) return g;
+    int32_t mn[3] = {INT32_MAX, INT32_MAX, INT32_MAX}, mx[3] = {INT32_MIN, INT32_MIN, INT32_MIN};
+    for (size_t i = 0; i < n; ++i)
+        for (int a = 0; a < 3; ++a) { if (ijk[3 * i + a] < mn[a]) mn[a] = ijk[3 * i + a]; if (ijk[3 * i + a] > mx[a]) mx[a] = ijk[3 * i + a]; }
+    g->L.ok = 1;
+    g->L.n_finite = n;
+    for (int a = 0; a < 3; ++a) { g->L.inv[a] = 1.0f / res; g->L.min_b[a] = mn[a]; g->L.max_b[a] = mx[a]; g->L.div_b[a] = mx[a] - mn[a] + 1; }
+    g->L.divb_mul[0] = 1; g->L.divb_mul[1] = g->L.div_b[0]; g->L.divb_mul[2] = g->L.div_b[0] * g->L.div_b[1];
+    for (size_t i = 0; i < n; ++i) {
+        orc_leaf *lf = &g->leaves[i];
+        lf->idx = (ijk[3 * i] - mn[0]) + (ijk[3 * i + 1] - mn[1]) * g->L.divb_mul[1] + (ijk[3 * i + 2] - mn[2]) * g->L.divb_mul[2];
+        lf->n_raw = lf->nr_points = 6; lf->in_tree = 1;
+        for (int a = 0; a < 3; ++a) { lf->mean[a] = mean3[3 * i + a]; lf->centroid[a] = (float)mean3[3 * i + a]; }
+        memcpy(lf->icov, &icov9[9 * i], 9 * sizeof(double));
+        lf->weight = weight ? weight[i] : 1.0;
+    }
+    qsort(g->leaves, n, sizeof(orc_leaf), cmp_leaf_idx);
+    for (size_t i = 0; i < n; ++i) {
+        size_t h = hash_u32((uint32_t)g->leaves[i].idx) & (g->hcap - 1);
+        while (g->hkey[h] != -1) h = (h + 1) & (g->hcap - 1);
+        g->hkey[h] = g->leaves[i].idx;
+        g->hval[h] = (int32_t)i;
+    }
+    return g;
+}
+
 void orc_grid_free(orc_grid *g) {
     if (!g) return;
     free(g->leaves); free(g->hkey); free(g->hval); free(g);
@@ -743,6 +787,35 @@ int orc_grid_radius_search(const orc_grid *g, float qx, float qy, float qz, doub
                     d2out[pos] = d2; slots[pos] = s;
                     ++cnt;
                 }
+            }
+    return cnt < cap ? cnt : cap;
+}
+
+/* The in-tree copy's VoxelGrid::radiusSearch (NDTM/VoxelGrid.cpp:432-480): scan the index cube
+ * floor((t +- radius)/leaf) (float arithmetic) clamped to the occupied range, accept when the DOUBLE
+ * distance to the double centroid is < radius; visiting order x, y, z.  Only used with intree_compat. */
+static int grid_radius_search_intree(const orc_grid *g, float tx, float ty, float tz, float radius, int32_t *slots, int cap) {
+    if (!g->L.ok || g->n_leaves == 0) return 0;
+    const float t[3] = {tx, ty, tz};
+    int lo[3], hi[3];
+    for (int a = 0; a < 3; ++a) {
+        int mx = (int)floor((t[a] + radius) / g->res);
+        int mn = (int)floor((t[a] - radius) / g->res);
+        if (mx > g->L.max_b[a]) mx = g->L.max_b[a];
+        if (mn < g->L.min_b[a]) mn = g->L.min_b[a];
+        lo[a] = mn; hi[a] = mx;
+    }
+    int cnt = 0;
+    for (int i = lo[0]; i <= hi[0]; ++i)
+        for (int j = lo[1]; j <= hi[1]; ++j)
+            for (int k = lo[2]; k <= hi[2]; ++k) {
+                int32_t idx = (i - g->L.min_b[0]) + (j - g->L.min_b[1]) * g->L.divb_mul[1] + (k - g->L.min_b[2]) * g->L.divb_mul[2];
+                int32_t s = grid_lookup(g, idx);
+                if (s < 0 || !g->leaves[s].in_tree) continue;
+                const orc_leaf *lf = &g->leaves[s];
+                double cx = lf->mean[0] - (double)tx, cy = lf->mean[1] - (double)ty, cz = lf->mean[2] - (double)tz;
+                double distance = sqrt(cx * cx + cy * cy + cz * cz);
+                if (distance < radius) { if (cnt < cap) slots[cnt] = s; ++cnt; }
             }
     return cnt < cap ? cnt : cap;
 }
@@ -817,7 +890,9 @@ double orc_ndt_derivatives(const orc_grid *g, const orc_params *prm, orc_cloud s
     float d2s[64];
     for (size_t idx = 0; idx < src.n; ++idx) {
         const float *xt = &trans_xyz[3 * idx];
-        int nn = orc_grid_radius_search(g, xt[0], xt[1], xt[2], (double)prm->res, slots, d2s, 64);
+        int nn = (prm->intree_compat & 2)
+                     ? grid_radius_search_intree(g, xt[0], xt[1], xt[2], prm->res, slots, 64)
+                     : orc_grid_radius_search(g, xt[0], xt[1], xt[2], (double)prm->res, slots, d2s, 64);
         for (int k = 0; k < nn; ++k) {
             const orc_leaf *lf = &g->leaves[slots[k]];
             const float *xo = pt_xyz(src, idx);
@@ -867,7 +942,7 @@ double orc_ndt_derivatives(const orc_grid *g, const orc_params *prm, orc_cloud s
                     }
                 }
             }
-            score += score_inc;
+            score += (prm->intree_compat & 1) ? lf->weight * score_inc : score_inc;
         }
     }
     if (pairs_out) *pairs_out = pairs;
@@ -1002,10 +1077,12 @@ static double step_length_mt(align_ctx *c, const double x[6], double step_dir[6]
         *score = derivs(c, x_t, 0, grad, H);
         c->res->mt_trials++;
         /* PCL: phi_t = -score; d_phi_t = -(g . dir)   (in-tree copy accumulates, :726-727; A.4) */
-        phi_t = -(*score);
-        d_phi_t = 0.0;
-        for (int i = 0; i < 6; ++i) d_phi_t += grad[i] * step_dir[i];
-        d_phi_t = -d_phi_t;
+        {
+            double gd = 0.0;
+            for (int i = 0; i < 6; ++i) gd += grad[i] * step_dir[i];
+            if (c->prm->intree_compat & 4) { phi_t -= *score; d_phi_t -= gd; }
+            else { phi_t = -(*score); d_phi_t = -gd; }
+        }
         psi_t = psi_mt(a_t, phi_t, phi_0, d_phi_0, mu);
         d_psi_t = dpsi_mt(d_phi_t, d_phi_0, mu);
         if (open_interval && (psi_t <= 0 && d_psi_t >= 0)) {

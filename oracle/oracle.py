@@ -37,18 +37,18 @@ class VoxLayout(C.Structure):
 class Leaf(C.Structure):
     _fields_ = [("idx", C.c_int32), ("n_raw", C.c_int32), ("nr_points", C.c_int32), ("in_tree", C.c_int32),
                 ("centroid", C.c_float * 4), ("mean", C.c_double * 3), ("cov", C.c_double * 9),
-                ("icov", C.c_double * 9), ("evals", C.c_double * 3)]
+                ("icov", C.c_double * 9), ("evals", C.c_double * 3), ("weight", C.c_double)]
 
 
 LEAF_DTYPE = np.dtype([("idx", "<i4"), ("n_raw", "<i4"), ("nr_points", "<i4"), ("in_tree", "<i4"),
                        ("centroid", "<f4", (4,)), ("mean", "<f8", (3,)), ("cov", "<f8", (9,)),
-                       ("icov", "<f8", (9,)), ("evals", "<f8", (3,))], align=True)
+                       ("icov", "<f8", (9,)), ("evals", "<f8", (3,)), ("weight", "<f8")], align=True)
 
 
 class Params(C.Structure):
     _fields_ = [("res", C.c_float), ("step_size", C.c_double), ("trans_eps", C.c_double),
                 ("outlier_ratio", C.c_double), ("max_iter", C.c_int), ("min_pts", C.c_int),
-                ("eig_mult", C.c_double), ("pcl17_compat", C.c_int)]
+                ("eig_mult", C.c_double), ("pcl17_compat", C.c_int), ("intree_compat", C.c_int)]
 
 
 class Result(C.Structure):
@@ -76,6 +76,8 @@ def lib():
     L.orc_voxel_filter.restype = C.c_size_t
     L.orc_grid_build.argtypes = [Cloud, C.c_float, C.c_int, C.c_double]
     L.orc_grid_build.restype = C.c_void_p
+    L.orc_grid_from_leaves.argtypes = [C.c_size_t, ip, dp, dp, dp, C.c_float]
+    L.orc_grid_from_leaves.restype = C.c_void_p
     L.orc_grid_free.argtypes = [C.c_void_p]
     L.orc_grid_num_leaves.argtypes = [C.c_void_p]
     L.orc_grid_num_leaves.restype = C.c_size_t
@@ -128,6 +130,38 @@ def ref_lib():
     return R
 
 
+_REFNDT = None
+
+
+def refndt_lib():
+    """oracle/_ref/libndt_manual_ref.so: the reference's own in-tree NDT compiled against stub headers."""
+    global _REFNDT
+    if _REFNDT is not None:
+        return _REFNDT
+    path = os.path.join(_HERE, "_ref", "libndt_manual_ref.so")
+    if not os.path.exists(path):
+        return None
+    R = C.CDLL(path)
+    dp, fp, ip = C.POINTER(C.c_double), C.POINTER(C.c_float), C.POINTER(C.c_int)
+    R.refndt_new.argtypes = [C.c_float, C.c_double, C.c_double, C.c_int, C.c_double]
+    R.refndt_new.restype = C.c_void_p
+    R.refndt_free.argtypes = [C.c_void_p]
+    R.refndt_set_target.argtypes = [C.c_void_p, fp, C.c_size_t]
+    R.refndt_grid_info.argtypes = [C.c_void_p, ip]
+    R.refndt_voxel.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, dp, dp, dp]
+    R.refndt_voxel.restype = C.c_int
+    R.refndt_radius_search.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, ip, C.c_int]
+    R.refndt_radius_search.restype = C.c_int
+    R.refndt_voxel_coords.argtypes = [C.c_void_p, C.c_int, ip]
+    R.refndt_set_source.argtypes = [C.c_void_p, fp, C.c_size_t]
+    R.refndt_derivatives.argtypes = [C.c_void_p, fp, dp, C.c_int, dp, dp]
+    R.refndt_derivatives.restype = C.c_double
+    R.refndt_angle_tables.argtypes = [C.c_void_p, dp, dp, dp]
+    R.refndt_align.argtypes = [C.c_void_p, fp, fp, ip, ip, dp, fp]
+    _REFNDT = R
+    return R
+
+
 def _dp(a):
     return a.ctypes.data_as(C.POINTER(C.c_double))
 
@@ -150,8 +184,8 @@ def as_cloud(a):
 
 
 def params(res=1.0, step_size=0.1, trans_eps=0.01, max_iter=30, outlier_ratio=0.55, min_pts=6,
-           eig_mult=0.01, pcl17_compat=1):
-    return Params(res, step_size, trans_eps, outlier_ratio, max_iter, min_pts, eig_mult, pcl17_compat)
+           eig_mult=0.01, pcl17_compat=1, intree_compat=0):
+    return Params(res, step_size, trans_eps, outlier_ratio, max_iter, min_pts, eig_mult, pcl17_compat, intree_compat)
 
 
 def vox_layout(cloud, lx, ly, lz):
@@ -191,9 +225,23 @@ class Grid:
     """NDT target cells (pcl::VoxelGridCovariance restatement)."""
 
     def __init__(self, target, res=1.0, min_pts=6, eig_mult=0.01):
+        if target is None:
+            self.h = None
+            self.res = res
+            return
         c, self._keep = as_cloud(target)
         self.h = lib().orc_grid_build(c, res, min_pts, eig_mult)
         self.res = res
+
+    @classmethod
+    def from_leaves(cls, ijk, mean, icov, weight=None, res=1.0):
+        """grid from externally supplied per-voxel statistics (absolute cell coordinates)."""
+        g = cls(None, res)
+        ijk = np.ascontiguousarray(ijk, np.int32); mean = np.ascontiguousarray(mean, np.float64)
+        icov = np.ascontiguousarray(icov, np.float64).reshape(-1, 9)
+        w = None if weight is None else np.ascontiguousarray(weight, np.float64)
+        g.h = lib().orc_grid_from_leaves(len(ijk), _ip(ijk), _dp(mean), _dp(icov), _dp(w) if w is not None else None, res)
+        return g
 
     def __del__(self):
         if getattr(self, "h", None):

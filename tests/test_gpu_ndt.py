@@ -80,6 +80,37 @@ def test_golden_fixture(oracle):
                 assert abs(fit - G["fitness"][k]) <= 1e-4 * G["fitness"][k]
 
 
+def test_gpu_matches_reference_intree_outputs():
+    """GPU vs outputs of the reference's OWN in-tree NDT code (tests/golden/intree_ndt.npz): per-voxel
+    mean bit-identical, inverse covariance to round-off, and the gradient / Hessian of computeDerivatives
+    (which the in-tree copy does not weight) to 1e-9."""
+    ref = np.load(os.path.join(os.path.dirname(__file__), "golden", "intree_ndt.npz"))
+    G = np.load(GOLD)
+    reg = NDTRegistration(1.0, 0.1, 0.01, 30)
+    reg.SetInputTarget(G["target"])
+    L = reg.TargetLeaves(); info = reg.TargetInfo()
+    tree = L["n"] >= 6
+    mb = np.array(info["min_b"]); dv = np.array(info["div_b"])
+    idx = L["idx"][tree].astype(np.int64)
+    iz = idx // (dv[0] * dv[1]); iy = (idx - iz * dv[0] * dv[1]) // dv[0]; ix = idx - iz * dv[0] * dv[1] - iy * dv[0]
+    ijk = np.stack([ix + mb[0], iy + mb[1], iz + mb[2]], 1)
+    key = lambda a: a[:, 0].astype(np.int64) * 1_000_000_007 + a[:, 1].astype(np.int64) * 1_000_003 + a[:, 2]
+    o = np.argsort(key(ijk)); r = np.argsort(key(ref["vox_ijk"]))
+    assert np.array_equal(ijk[o], ref["vox_ijk"][r]) and np.array_equal(L["n"][tree][o], ref["vox_n"][r])
+    assert np.array_equal(L["mean"][tree][o], ref["vox_mean"][r])
+    a, b = L["icov"][tree][o], ref["vox_icov"][r]
+    assert np.max(np.abs(a - b).max(1) / np.abs(b).max(1)) < 1e-12
+    for k, q in enumerate(ref["deriv_pose"]):
+        s, g, H, pairs = reg.Derivatives(G["src"], q)
+        assert np.max(np.abs(g - ref["deriv_grad"][k])) <= 1e-9 * np.abs(ref["deriv_grad"][k]).max()
+        assert np.max(np.abs(H - ref["deriv_hess"][k])) <= 1e-9 * np.abs(ref["deriv_hess"][k]).max()
+    for k, guess in enumerate(ref["guesses"]):
+        ok, cloud, pose = reg.ScanMatch(G["src"], guess)
+        assert reg.last_result["iterations"] == ref["align_iterations"][k]
+        assert np.max(np.abs(pose[:3, 3] - ref["align_pose"][k][:3, 3])) <= 1e-3
+        assert np.max(np.abs(pose[:3, :3] - ref["align_pose"][k][:3, :3])) <= 1e-4
+
+
 def test_derivative_pass_matches_oracle(oracle, setup, scans):
     reg, grid, prm, srcs = setup
     rng = np.random.default_rng(3)

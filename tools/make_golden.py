@@ -8,6 +8,9 @@
                       SelfAdjointEigenSolver.  These pin the plain-C oracle AND the product's device math.
   ndt_small.npz       a small scan-to-map case with the oracle's own outputs (regression pin of the
                       restatement; the reference itself ships no golden vectors).
+  intree_ndt.npz      outputs of the reference's OWN in-tree NDT source (compiled where it lies against
+                      oracle/ref_stubs) on that case: voxel statistics, angle tables, computeDerivatives,
+                      align.  True reference outputs; pin the oracle's NDT core and grid build.
 """
 import ctypes as C
 import os
@@ -128,7 +131,59 @@ def ndt_small():
           "iterations", out["c1_iterations"], out["c0_iterations"])
 
 
+def intree_ndt():
+    """Outputs of the reference's OWN in-tree NDT (ndt_registration_manual/*.cpp compiled where it lies
+    against oracle/ref_stubs, oracle/_ref/libndt_manual_ref.so) on the ndt_small case: per-voxel mean /
+    inverse covariance / static value, computeAngleDerivatives tables, computeDerivatives at fixed poses,
+    and align() results.  These are true reference outputs (not oracle outputs)."""
+    O.build(ref=True)
+    R = O.refndt_lib()
+    assert R is not None, "oracle/_ref/libndt_manual_ref.so missing (needs /root/reference)"
+    ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int))
+    G = np.load(os.path.join(OUT, "ndt_small.npz"))
+    target = np.ascontiguousarray(G["target"]); src = np.ascontiguousarray(G["src"])
+    f32 = lambda v: float(np.float32(v))
+    h = R.refndt_new(1.0, f32(0.1), f32(0.01), 30, 0.55)
+    R.refndt_set_target(h, fp(target), len(target))
+    info = np.zeros(12, np.int32); R.refndt_grid_info(h, ip(info))
+    # enumerate the reference's searchable voxels (points_per_voxel >= 6) over its occupied index range
+    ijk, cen, icov, sv, npv = [], [], [], [], []
+    for ix in range(info[6], info[9] + 1):
+        for iy in range(info[7], info[10] + 1):
+            for iz in range(info[8], info[11] + 1):
+                c = np.zeros(3); ic = np.zeros(9); s = C.c_double()
+                n = R.refndt_voxel(h, ix, iy, iz, dp(c), dp(ic), C.byref(s))
+                if n >= 6:
+                    ijk.append((ix, iy, iz)); cen.append(c); icov.append(ic); sv.append(s.value); npv.append(n)
+    out = dict(grid_info=info, vox_ijk=np.array(ijk, np.int32), vox_mean=np.array(cen), vox_icov=np.array(icov),
+               vox_static=np.array(sv), vox_n=np.array(npv, np.int32))
+    R.refndt_set_source(h, fp(src), len(src))
+    poses = G["deriv_pose"]
+    ds, dg, dH, tabs_j, tabs_h, trans = [], [], [], [], [], []
+    for q in poses:
+        q = np.ascontiguousarray(q)
+        tr = np.ascontiguousarray(O.transform_points(O.pose_to_matrix(q), src[:, :3]))
+        g6 = np.zeros(6); H = np.zeros(36)
+        ds.append(R.refndt_derivatives(h, fp(tr), dp(q), 1, dp(g6), dp(H))); dg.append(g6); dH.append(H.reshape(6, 6, order="F")); trans.append(tr)
+        j = np.zeros(24); hh = np.zeros(45)
+        R.refndt_angle_tables(h, dp(q), dp(j), dp(hh)); tabs_j.append(j); tabs_h.append(hh)
+    out.update(deriv_pose=poses, deriv_trans=np.stack(trans), deriv_score=np.array(ds), deriv_grad=np.stack(dg), deriv_hess=np.stack(dH),
+               ang_j=np.stack(tabs_j), ang_h=np.stack(tabs_h))
+    al_pose, al_it, al_conv, al_tp, al_cloud = [], [], [], [], []
+    for guess in G["guesses"]:
+        Gc = np.ascontiguousarray(guess.flatten(order="F")); pose = np.zeros(16, np.float32)
+        it = C.c_int(); cv = C.c_int(); tp = C.c_double(); tc = np.zeros((len(src), 3), np.float32)
+        R.refndt_align(h, fp(Gc), fp(pose), C.byref(it), C.byref(cv), C.byref(tp), fp(tc))
+        al_pose.append(pose.reshape(4, 4, order="F")); al_it.append(it.value); al_conv.append(cv.value); al_tp.append(tp.value); al_cloud.append(tc[::16])
+    out.update(guesses=G["guesses"], align_pose=np.stack(al_pose), align_iterations=np.array(al_it), align_converged=np.array(al_conv),
+               align_trans_probability=np.array(al_tp), align_cloud_every16=np.stack(al_cloud))
+    R.refndt_free(h)
+    np.savez_compressed(os.path.join(OUT, "intree_ndt.npz"), **out)
+    print("intree_ndt.npz: voxels", len(ijk), "iterations", al_it)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     eigen_numerics()
     ndt_small()
+    intree_ndt()
