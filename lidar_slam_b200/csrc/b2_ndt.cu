@@ -60,6 +60,7 @@ __global__ void __launch_bounds__(256) leaf_stats_kernel(const float4 *__restric
             float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
             if (c + l < e) { p = __ldg(&pts[vals[c + l]]); pts_sorted[c + l] = p; }
             const int m = (e - c < 32u) ? (int)(e - c) : 32;
+#pragma unroll 4
             for (int k = 0; k < m; ++k) {
                 float x = __shfl_sync(0xffffffffu, p.x, k), y = __shfl_sync(0xffffffffu, p.y, k);
                 float z = __shfl_sync(0xffffffffu, p.z, k), w = __shfl_sync(0xffffffffu, p.w, k);

@@ -10,6 +10,8 @@
 #include <float.h>
 #include <stdarg.h>
 
+#include <cmath>
+
 #include <thread>
 
 namespace b2 {
@@ -26,6 +28,38 @@ void set_error(const char *fmt, ...) {
     t_err = buf;
 }
 const char *last_error() { return t_err.c_str(); }
+
+// Upper bound on the voxel-key width from a host-side bounding box (PCL layout arithmetic, one extra
+// cell per axis of slack); lets the sort run only the radix passes it needs without a device round trip.
+int key_bits_from_bbox(const float mn[3], const float mx[3], float lx, float ly, float lz) {
+    const float leaf[3] = {lx, ly, lz};
+    double cells = 1.0;
+    for (int a = 0; a < 3; ++a) {
+        if (!(mx[a] >= mn[a])) return 0;
+        const float inv = 1.0f / leaf[a];
+        double d = floor((double)mx[a] * inv) - floor((double)mn[a] * inv) + 2.0;
+        cells *= d;
+    }
+    if (!(cells < 2147483000.0)) return 32;
+    uint32_t c = (uint32_t)cells;
+    int bits = 0;
+    while (c) { ++bits; c >>= 1; }
+    return bits < 1 ? 1 : bits;
+}
+
+void pack_cloud_f4_bbox(const void *src, size_t n, size_t stride, size_t ioff, float *dst, float mn[3], float mx[3]) {
+    const char *s = (const char *)src;
+    for (int a = 0; a < 3; ++a) { mn[a] = FLT_MAX; mx[a] = -FLT_MAX; }
+    for (size_t i = 0; i < n; ++i) {
+        const float *p = (const float *)(s + i * stride);
+        const float x = p[0], y = p[1], z = p[2];
+        dst[4 * i + 0] = x; dst[4 * i + 1] = y; dst[4 * i + 2] = z; dst[4 * i + 3] = *(const float *)(s + i * stride + ioff);
+        if (std::isfinite(x) && std::isfinite(y) && std::isfinite(z)) {
+            mn[0] = x < mn[0] ? x : mn[0]; mn[1] = y < mn[1] ? y : mn[1]; mn[2] = z < mn[2] ? z : mn[2];
+            mx[0] = x > mx[0] ? x : mx[0]; mx[1] = y > mx[1] ? y : mx[1]; mx[2] = z > mx[2] ? z : mx[2];
+        }
+    }
+}
 
 void pack_cloud_f4(const void *src, size_t n, size_t stride, size_t ioff, float *dst) {
     auto work = [=](size_t a, size_t b) {
@@ -508,11 +542,23 @@ __global__ void __launch_bounds__(256) vf_centroid_kernel(const float4 *__restri
             float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
             if (c + l < e) p = __ldg(&pts[vals[c + l]]);
             const int m = (e - c < 32u) ? (int)(e - c) : 32;
-            for (int k = 0; k < m; ++k) {
-                ax = __fadd_rn(ax, __shfl_sync(0xffffffffu, p.x, k));
-                ay = __fadd_rn(ay, __shfl_sync(0xffffffffu, p.y, k));
-                az = __fadd_rn(az, __shfl_sync(0xffffffffu, p.z, k));
-                ai = __fadd_rn(ai, __shfl_sync(0xffffffffu, p.w, k));
+            if (m == 32) {
+                // full chunk: all 128 shuffles are independent of the four add chains, so the fold costs
+                // ~one FADD latency per member (crowded voxels hold thousands of points)
+#pragma unroll
+                for (int k = 0; k < 32; ++k) {
+                    ax = __fadd_rn(ax, __shfl_sync(0xffffffffu, p.x, k));
+                    ay = __fadd_rn(ay, __shfl_sync(0xffffffffu, p.y, k));
+                    az = __fadd_rn(az, __shfl_sync(0xffffffffu, p.z, k));
+                    ai = __fadd_rn(ai, __shfl_sync(0xffffffffu, p.w, k));
+                }
+            } else {
+                for (int k = 0; k < m; ++k) {
+                    ax = __fadd_rn(ax, __shfl_sync(0xffffffffu, p.x, k));
+                    ay = __fadd_rn(ay, __shfl_sync(0xffffffffu, p.y, k));
+                    az = __fadd_rn(az, __shfl_sync(0xffffffffu, p.z, k));
+                    ai = __fadd_rn(ai, __shfl_sync(0xffffffffu, p.w, k));
+                }
             }
         }
         if (l == 0) {
@@ -633,11 +679,18 @@ extern "C" int b2vf_filter(b2vf *h, const void *in, size_t n, size_t stride, siz
     if ((rc = h->h_misc.reserve(256))) return rc;
     // host pass: repack to float4 and (for free) bound the key width so the sort runs only the radix
     // passes it needs
-    pack_cloud_f4(in, n, stride, ioff, h->h_in.as<float>());
+    int nbits_hint = 0;
+    if (n <= 2000000) {
+        float mn[3], mx[3];
+        pack_cloud_f4_bbox(in, n, stride, ioff, h->h_in.as<float>(), mn, mx);
+        nbits_hint = key_bits_from_bbox(mn, mx, h->leaf[0], h->leaf[1], h->leaf[2]);
+    } else {
+        pack_cloud_f4(in, n, stride, ioff, h->h_in.as<float>());
+    }
     B2_CUDA(cudaMemcpyAsync(h->d_in.p, h->h_in.p, n * 16, cudaMemcpyHostToDevice, h->st));
     uint32_t off[2] = {0u, (uint32_t)n};
     if ((rc = h->pipe.plan(off, 1, h->st))) return rc;
-    if ((rc = h->pipe.run(h->d_in.as<float4>(), h->leaf[0], h->leaf[1], h->leaf[2], 0, h->st))) return rc;
+    if ((rc = h->pipe.run(h->d_in.as<float4>(), h->leaf[0], h->leaf[1], h->leaf[2], nbits_hint, h->st))) return rc;
     if ((rc = vf_launch_centroids(h, h->d_in.as<float4>(), h->d_out.as<float4>(), h->d_idx.as<int32_t>(),
                                   h->d_cnt.as<int32_t>(), n))) return rc;
     uint32_t *misc = h->h_misc.as<uint32_t>();

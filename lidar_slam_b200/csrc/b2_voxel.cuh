@@ -51,5 +51,7 @@ struct VoxPipeline {
 
 // host cloud (ptr, n, stride, ioff) -> pinned packed float4 staging; returns bbox-free copy
 void pack_cloud_f4(const void *src, size_t n, size_t stride, size_t ioff, float *dst_f4);
+void pack_cloud_f4_bbox(const void *src, size_t n, size_t stride, size_t ioff, float *dst_f4, float mn[3], float mx[3]);
+int key_bits_from_bbox(const float mn[3], const float mx[3], float lx, float ly, float lz);
 
 }  // namespace b2
