@@ -139,19 +139,38 @@ __global__ void __launch_bounds__(128) leaf_finish_kernel(uint32_t V, int min_pt
 }
 
 // ------------------------------------------------------------------ the NDT match kernel ------
-// One thread-block cluster (1..16 CTAs x 256 threads) per match; the whole Newton / More-Thuente loop
-// runs inside the kernel.  Each pass is WARP-LOCAL and two-phase:
-//   phase 1 (search, latency bound): lane = source point.  Float transform, then one z-plane of the
+// One thread-block cluster (1..16 CTAs) per match; the whole Newton / More-Thuente loop runs inside the
+// kernel.  Every CTA is WARP-SPECIALISED (producer / consumer, registers re-balanced with setmaxnreg):
+//   search warps  (NDT_NSW, 56 registers): lane = source point.  Float transform, then one z-plane of the
 //     3x3x3 window of the dense cell grid per step: nine independent 16-byte loads bring the voxel code
-//     AND its float centroid (no second dependent load), float L2 tests, hits appended to the warp's pair
-//     queue in shared memory at positions given by ballots (deterministic order, no atomics);
-//   phase 2 (compute, FP64 bound): lane = (point, voxel) pair taken from the queue in chunks of 32, so
-//     every lane is busy: 80-byte record gather, exp, score / gradient / Hessian terms of
-//     updateDerivatives (NDTM:485-520) accumulated in 29 FP64 registers.
-// Warps of co-resident CTAs are in different phases at any time, so gather latency hides under FP64 issue.
-constexpr int NDT_THREADS = 256;
-constexpr int NDT_WARPS = NDT_THREADS / 32;
-constexpr int QCAP = 576;        // pair queue entries per warp: < 32 left-overs + 32 lanes x 16 cells of a plane
+//     AND its float centroid (no second dependent load), float L2 tests, hits appended to the warp's ring
+//     buffer in shared memory at positions given by ballots (deterministic order, no atomics);
+//   compute warps (NDT_NCW, 128 registers): lane = (point, voxel) pair.  Each compute warp drains the
+//     rings of its search warps in a fixed round-robin, 32 pairs at a time, so every lane is busy:
+//     80-byte record gather, exp, score / gradient / Hessian terms of updateDerivatives (NDTM:485-520)
+//     accumulated in 29 FP64 registers.
+// The latency-bound gather and the FP64-bound arithmetic thus run concurrently on different warps, and
+// the cheap search warps raise the number of resident warps per SM.
+#ifndef NDT_NCW
+#define NDT_NCW 4
+#endif
+#ifndef NDT_NSW
+#define NDT_NSW 8
+#endif
+#ifndef NDT_MIN_CTAS
+#define NDT_MIN_CTAS 2
+#endif
+#ifndef NDT_REG_COMPUTE
+#define NDT_REG_COMPUTE 128
+#endif
+#ifndef NDT_REG_SEARCH
+#define NDT_REG_SEARCH 56
+#endif
+constexpr int NDT_WARPS = NDT_NCW + NDT_NSW;
+constexpr int NDT_THREADS = NDT_WARPS * 32;
+constexpr int NDT_PPC = NDT_NSW / NDT_NCW;     // producers (search warps) per compute warp
+constexpr uint32_t RING = 1024;                // ring entries per search warp (power of two, > 512 + 32)
+static_assert(NDT_NCW % 4 == 0 && NDT_NSW % 4 == 0 && NDT_NSW % NDT_NCW == 0, "warp-group multiples");
 
 struct GridView {
     const float4 *cells;         // dense grid record {cx, cy, cz, int code}: code > 0 searchable leaf+1, < 0 sparse, 0 empty
@@ -177,15 +196,23 @@ struct MatchArgs {
 
 struct NdtSmem {
     Ctl ctl;
-    double warp_part[NDT_WARPS][ACC_N];
+    double warp_part[NDT_NCW][ACC_N];
     double cta_part[2][ACC_N];     // double-buffered per-CTA partial, read by cluster peers over DSMEM
     double total[ACC_N];
     double trig_d[6];              // snapped double sin x3, cos x3 of the requested pose
     float  trig_f[6];              // float sin x3, cos x3
     int go;
     int pad_;
-    float4 queue[NDT_WARPS][QCAP]; // {source x, y, z, leaf index bits}
+    // producer -> consumer rings (monotonic counters, never reset)
+    uint32_t tail[NDT_NSW];        // entries produced by search warp s
+    uint32_t head[NDT_NSW];        // entries consumed from search warp s
+    uint32_t finished[NDT_NSW];    // last pass id search warp s has completed
+    uint2 ring[NDT_NSW][RING];     // (source point index, leaf index)
 };
+
+__device__ __forceinline__ void cta_barrier() { asm volatile("bar.sync 0, %0;" ::"n"(NDT_THREADS) : "memory"); }
+__device__ __forceinline__ uint32_t ld_vol(const uint32_t *p) { return *reinterpret_cast<const volatile uint32_t *>(p); }
+__device__ __forceinline__ void st_vol(uint32_t *p, uint32_t v) { *reinterpret_cast<volatile uint32_t *>(p) = v; }
 
 __device__ __forceinline__ double dot3v(const double *h, double x, double y, double z) { return x * h[0] + y * h[1] + z * h[2]; }
 __device__ __forceinline__ double dot2v(const double *h, double x, double y) { return x * h[0] + y * h[1]; }
@@ -292,7 +319,7 @@ __device__ __forceinline__ void finish_request_warp0(NdtSmem &S, int lane) {
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(NDT_THREADS, 2) ndt_match_kernel(GridView G, NdtConst K, MatchArgs A) {
+__global__ void __launch_bounds__(NDT_THREADS, NDT_MIN_CTAS) ndt_match_kernel(GridView G, NdtConst K, MatchArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     NdtSmem &S = *reinterpret_cast<NdtSmem *>(smem_raw);
     cg::cluster_group cluster = cg::this_cluster();
@@ -300,12 +327,14 @@ __global__ void __launch_bounds__(NDT_THREADS, 2) ndt_match_kernel(GridView G, N
     const unsigned crank = cluster.block_rank();
     const unsigned match = blockIdx.x / C;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool is_compute = warp < NDT_NCW;
     const uint32_t lt = (1u << lane) - 1u;
 
     uint32_t first = 0, last = A.n_shared;
     if (A.offsets) { first = A.offsets[match]; last = A.offsets[match + 1]; }
     const uint32_t npts = last - first;
 
+    if (tid < NDT_NSW) { S.tail[tid] = 0u; S.head[tid] = 0u; S.finished[tid] = 0u; }
     if (warp == 0) {
         if (lane == 0) {
             if (A.deriv_only) {
@@ -322,35 +351,27 @@ __global__ void __launch_bounds__(NDT_THREADS, 2) ndt_match_kernel(GridView G, N
     }
     __syncthreads();
 
-    float4 *queue = S.queue[warp];
-    const uint32_t stride = C * NDT_WARPS * 32u;
-    int parity = 0;
-    while (true) {
-        const bool hess = S.ctl.hess != 0;
-        double acc[ACC_N];
-#pragma unroll
-        for (int i = 0; i < ACC_N; ++i) acc[i] = 0.0;
-        const float *T = S.ctl.T;
-        const AngTab &ang = S.ctl.ang;
-        // warp-uniform state of the search / compute pipeline
-        uint32_t qn = 0;
-        uint32_t base = first + (crank * NDT_WARPS + warp) * 32u;
-        int plane = 0, nplanes = 0;
-        bool have_round = false, wide = false;
-        // per-lane state of the current round (32 source points)
-        float px = 0.f, py = 0.f, pz = 0.f, tx = 0.f, ty = 0.f, tz = 0.f;
-        int ex0 = -1, ex1 = -1, ex2 = -1;
-        size_t wbase = 0;
+    const uint32_t stride = C * NDT_NSW * 32u;
+    // The two roles never share code after this point (ptxas sizes each branch for its own register
+    // budget); they meet at CTA-wide barriers issued from both branches.
+    if (!is_compute) {
+        // =========================== search warps (producers) ===========================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(NDT_REG_SEARCH));
+        const int sw = warp - NDT_NCW;
+        uint2 *ring = S.ring[sw];
+        uint32_t pass_id = 0;
+        uint32_t my_tail = 0;                       // entries produced so far (warp-uniform)
         while (true) {
-            if (!have_round && base < last) {
-                // ---- new round: transform 32 points, window of candidate cells per lane ----
+            ++pass_id;
+            const float *T = S.ctl.T;
+            for (uint32_t base = first + (crank * NDT_NSW + sw) * 32u; base < last; base += stride) {
                 const uint32_t i = base + lane;
-                ex0 = ex1 = ex2 = -1;
-                wbase = 0;
+                int ex0 = -1, ex1 = -1, ex2 = -1;
+                size_t wbase = 0;
+                float tx = 0.f, ty = 0.f, tz = 0.f;
                 if (i < last && G.ok) {
                     const float4 pt = __ldg(&A.src[i]);
-                    px = pt.x; py = pt.y; pz = pt.z;
-                    transform_f32(T, px, py, pz, tx, ty, tz);
+                    transform_f32(T, pt.x, pt.y, pt.z, tx, ty, tz);
                     if (finite3(tx, ty, tz)) {
                         // every cell that can hold a centroid within the radius (centroids may sit up to
                         // G.margin outside their own cell; the slack also covers the rounding of this arithmetic)
@@ -372,16 +393,18 @@ __global__ void __launch_bounds__(NDT_THREADS, 2) ndt_match_kernel(GridView G, N
                         }
                     }
                 }
-                nplanes = __reduce_max_sync(0xffffffffu, ex2 + 1);
-                wide = __any_sync(0xffffffffu, (ex0 > 2) || (ex1 > 2));
-                plane = 0;
-                have_round = true;
-            }
-            if (have_round) {
-                if (plane < nplanes) {
-                    // ---- phase 1: one z-plane of the window ----
+                const int nplanes = __reduce_max_sync(0xffffffffu, ex2 + 1);
+                const bool wide = __any_sync(0xffffffffu, (ex0 > 2) || (ex1 > 2));
+                for (int plane = 0; plane < nplanes; ++plane) {
+                    // a plane appends at most 32 x 16 entries: wait until the consumer has made room
+                    if (lane == 0) {
+                        uint32_t hd = ld_vol(&S.head[sw]);
+                        while (my_tail - hd > RING - 512u) { __nanosleep(64); hd = ld_vol(&S.head[sw]); }
+                    }
+                    __syncwarp();
                     const bool act = plane <= ex2;
                     const float4 *wp = G.cells + wbase + (size_t)plane * G.mul[2];
+                    uint32_t qn = my_tail;
                     if (!wide) {
                         float4 c[9];
 #pragma unroll
@@ -399,7 +422,7 @@ __global__ void __launch_bounds__(NDT_THREADS, 2) ndt_match_kernel(GridView G, N
                             const int code = __float_as_int(c[k].w);
                             const bool hit = (code > 0) && (d2f < G.r2);
                             const uint32_t b = __ballot_sync(0xffffffffu, hit);
-                            if (hit) queue[qn + __popc(b & lt)] = make_float4(px, py, pz, __int_as_float(code - 1));
+                            if (hit) ring[(qn + __popc(b & lt)) & (RING - 1u)] = make_uint2(i, (uint32_t)(code - 1));
                             qn += __popc(b);
                         }
                     } else {
@@ -413,49 +436,98 @@ __global__ void __launch_bounds__(NDT_THREADS, 2) ndt_match_kernel(GridView G, N
                                 const int code = __float_as_int(c.w);
                                 const bool hit = (code > 0) && (d2f < G.r2);
                                 const uint32_t b = __ballot_sync(0xffffffffu, hit);
-                                if (hit) queue[qn + __popc(b & lt)] = make_float4(px, py, pz, __int_as_float(code - 1));
+                                if (hit) ring[(qn + __popc(b & lt)) & (RING - 1u)] = make_uint2(i, (uint32_t)(code - 1));
                                 qn += __popc(b);
                             }
                     }
+                    __syncwarp();
+                    if (qn != my_tail) {
+                        my_tail = qn;
+                        if (lane == 0) { __threadfence_block(); st_vol(&S.tail[sw], my_tail); }
+                    }
                 }
-                ++plane;
-                if (plane >= nplanes) { have_round = false; base += stride; }
             }
-            const bool flush = !have_round && base >= last;
+            // publish the end of this warp's stream for this pass
             __syncwarp();
-            // ---- phase 2: chunks of 32 pairs (single call site of the pair arithmetic) ----
-            uint32_t qh = 0;
-            while (qh + 32u <= qn || (flush && qh < qn)) {
-                if (qh + lane < qn) {
-                    const float4 e = queue[qh + lane];
-                    ndt_pair(e.x, e.y, e.z, T, ang, G.gauss + (size_t)__float_as_int(e.w) * 10, K.d1, K.d2, hess, acc);
+            if (lane == 0) { __threadfence_block(); st_vol(&S.tail[sw], my_tail); __threadfence_block(); st_vol(&S.finished[sw], pass_id); }
+            cta_barrier();                          // (1) all pairs of the pass consumed, partials written
+            if (C > 1) cluster.sync();
+            cta_barrier();                          // (2) totals ready
+            cta_barrier();                          // (3) controller done
+            if (!ld_vol(reinterpret_cast<const uint32_t *>(&S.go))) break;
+        }
+        if (C > 1) cluster.sync();
+    } else {
+    // =========================== compute warps (consumers) ===========================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(NDT_REG_COMPUTE));
+    int parity = 0;
+    uint32_t pass_id = 0;
+    uint32_t cpos[NDT_PPC];                         // entries consumed per producer
+#pragma unroll
+    for (int k = 0; k < NDT_PPC; ++k) cpos[k] = 0;
+    while (true) {
+        ++pass_id;
+        {
+            const float *T = S.ctl.T;
+            const bool hess = S.ctl.hess != 0;
+            const AngTab &ang = S.ctl.ang;
+            double acc[ACC_N];
+#pragma unroll
+            for (int i = 0; i < ACC_N; ++i) acc[i] = 0.0;
+            uint32_t done_mask = 0;                         // bit k: producer k exhausted for this pass
+            int turn = 0;
+            while (done_mask != (1u << NDT_PPC) - 1u) {
+                // fixed round-robin over this warp's producers (deterministic accumulation order)
+                const int k = turn;
+                turn = (turn + 1 == NDT_PPC) ? 0 : turn + 1;
+                if (done_mask & (1u << k)) continue;
+                const int sw = warp + k * NDT_NCW;
+                uint32_t pos = 0;
+#pragma unroll
+                for (int kk = 0; kk < NDT_PPC; ++kk) if (kk == k) pos = cpos[kk];
+                // wait for a full chunk of 32 pairs, or for the producer to finish the pass
+                uint32_t n = 0;
+                if (lane == 0) {
+                    while (true) {
+                        const uint32_t fin = ld_vol(&S.finished[sw]);
+                        __threadfence_block();
+                        const uint32_t avail = ld_vol(&S.tail[sw]) - pos;
+                        if (avail >= 32u) { n = 32u; break; }
+                        if (fin == pass_id) { n = avail | 0x80000000u; break; }     // final (possibly empty) chunk
+                        __nanosleep(32);
+                    }
                 }
-                qh += 32u;
-            }
-            if (qh) {      // move the left-over (< 32 entries) to the front
-                const uint32_t rem = qn > qh ? qn - qh : 0u;
-                float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
-                if ((uint32_t)lane < rem) e = queue[qh + lane];
-                __syncwarp();
-                if ((uint32_t)lane < rem) queue[lane] = e;
-                qn = rem;
-                __syncwarp();
-            }
-            if (flush) break;
-        }
-        // ---------------- deterministic reduction: warp butterfly -> CTA -> cluster (fixed order) -----
+                n = __shfl_sync(0xffffffffu, n, 0);
+                const bool final_chunk = (n & 0x80000000u) != 0;
+                n &= 0x7fffffffu;
+                __threadfence_block();
+                if ((uint32_t)lane < n) {
+                    const uint2 e = S.ring[sw][(pos + lane) & (RING - 1u)];
+                    const float4 sp = __ldg(&A.src[e.x]);
+                    ndt_pair(sp.x, sp.y, sp.z, T, ang, G.gauss + (size_t)e.y * 10, K.d1, K.d2, hess, acc);
+                }
+                pos += n;
 #pragma unroll
-        for (int i = 0; i < ACC_N; ++i) {
-            double vsum = acc[i];
+                for (int kk = 0; kk < NDT_PPC; ++kk) if (kk == k) cpos[kk] = pos;
+                __syncwarp();
+                if (lane == 0 && n) st_vol(&S.head[sw], pos);
+                if (final_chunk) done_mask |= (1u << k);
+            }
+            // warp butterfly (fixed order) -> one partial per compute warp
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) vsum += __shfl_xor_sync(0xffffffffu, vsum, o);
-            if (lane == 0) S.warp_part[warp][i] = vsum;
+            for (int i = 0; i < ACC_N; ++i) {
+                double vsum = acc[i];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) vsum += __shfl_xor_sync(0xffffffffu, vsum, o);
+                if (lane == 0) S.warp_part[warp][i] = vsum;
+            }
         }
-        __syncthreads();
+        cta_barrier();                              // (1)
+        // ---------------- deterministic reduction: CTA -> cluster (fixed order) ----------------
         if (tid < ACC_N) {
             double s = 0.0;
 #pragma unroll
-            for (int w = 0; w < NDT_WARPS; ++w) s += S.warp_part[w][tid];
+            for (int w = 0; w < NDT_NCW; ++w) s += S.warp_part[w][tid];
             S.cta_part[parity][tid] = s;
         }
         if (C > 1) {
@@ -466,10 +538,9 @@ __global__ void __launch_bounds__(NDT_THREADS, 2) ndt_match_kernel(GridView G, N
                 S.total[tid] = tot;
             }
         } else {
-            __syncthreads();
             if (tid < ACC_N) S.total[tid] = S.cta_part[parity][tid];
         }
-        __syncthreads();
+        cta_barrier();                              // (2)
         // ---------------- controller: Newton step + More-Thuente state machine (warp 0) ----------------
         if (warp == 0) {
             int go = 0;
@@ -477,7 +548,7 @@ __global__ void __launch_bounds__(NDT_THREADS, 2) ndt_match_kernel(GridView G, N
             go = __shfl_sync(0xffffffffu, go, 0);
             if (go) finish_request_warp0(S, lane);
         }
-        __syncthreads();
+        cta_barrier();                              // (3)
         if (!S.go) break;
         parity ^= 1;
     }
@@ -498,6 +569,7 @@ __global__ void __launch_bounds__(NDT_THREADS, 2) ndt_match_kernel(GridView G, N
             }
         }
     }
+    }   // compute branch
 }
 
 // ------------------------------------------------------------------ fitness score -------------
@@ -904,7 +976,7 @@ extern "C" int b2ndt_align(b2ndt *h, const void *src, size_t n, size_t stride, s
     B2_CUDA(cudaSetDevice(h->device));
     // spread a single match over a cluster only when there is enough work per CTA
     int C = h->cl_single;
-    while (C > 1 && (size_t)C * NDT_THREADS > n) C >>= 1;
+    while (C > 1 && (size_t)C * NDT_NSW * 32 > n) C >>= 1;
     rc = align_host(h, src, n, stride, ioff, nullptr, 1, guess, pose_out, res, C < 1 ? 1 : C);
     if (rc) return rc;
     h->last_n = n;
@@ -953,7 +1025,7 @@ extern "C" int b2ndt_derivatives(b2ndt *h, const void *src, size_t n, size_t str
     A.src = h->d_src.as<float4>(); A.n_shared = (uint32_t)n; A.poses6 = h->d_p6.as<double>();
     A.acc_out = h->d_acc.as<double>(); A.deriv_only = 1;
     int C = h->cl_single;
-    while (C > 1 && (size_t)C * NDT_THREADS > n) C >>= 1;
+    while (C > 1 && (size_t)C * NDT_NSW * 32 > n) C >>= 1;
     if ((rc = launch_match(h, A, 1, C < 1 ? 1 : C))) return rc;
     double *acc = h->h_res.as<double>();
     B2_CUDA(cudaMemcpyAsync(acc, h->d_acc.p, ACC_N * 8, cudaMemcpyDeviceToHost, h->st));

@@ -54,9 +54,42 @@ B2_HD double ddiv(double a, double b) { return a / b; }
 B2_HD double dsqrt(double a) { return sqrt(a); }
 #endif
 
+// ---- double sin / cos shared by host and device.
+// Same source and same operations (explicit fma) on both sides, so the host-compiled test shim computes
+// exactly what the GPU computes.  Also a toolchain necessity: CUDA 12.9's ptxas crashes on the libdevice
+// sin/cos slow-path call inside a setmaxnreg region of the warp-specialised match kernel.
+// Cody-Waite reduction by pi/2 with a three-part constant, then the fdlibm minimax kernels on
+// [-pi/4, pi/4] (error < 1 ulp for |x| < ~1e5, far beyond any pose angle).
+B2_HD void b2_sincos(double x, double &sn, double &cs) {
+    const double n = rint(x * 6.36619772367581382433e-01);
+    double r = fma(n, -1.57079632679489655800e+00, x);
+    r = fma(n, -6.12323399573676603587e-17, r);
+    r = fma(n, -8.47842766036889956997e-32, r);
+    const double z = r * r;
+    // __kernel_sin
+    double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+    ps = fma(z, ps, 2.75573137070700676789e-06);
+    ps = fma(z, ps, -1.98412698298579493134e-04);
+    ps = fma(z, ps, 8.33333333332248946124e-03);
+    ps = fma(z, ps, -1.66666666666666324348e-01);
+    const double s = fma(z * r, ps, r);
+    // __kernel_cos
+    double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+    pc = fma(z, pc, -2.75573143513906633035e-07);
+    pc = fma(z, pc, 2.48015872894767294178e-05);
+    pc = fma(z, pc, -1.38888888888741095749e-03);
+    pc = fma(z, pc, 4.16666666666666019037e-02);
+    const double c = 1.0 - fma(0.5, z, -(z * z * pc));
+    const long long q = (long long)n & 3LL;
+    sn = (q == 0) ? s : (q == 1) ? c : (q == 2) ? -s : -c;
+    cs = (q == 0) ? c : (q == 1) ? -s : (q == 2) ? -c : s;
+}
+B2_HD double b2_sin(double x) { double s, c; b2_sincos(x, s, c); return s; }
+B2_HD double b2_cos(double x) { double s, c; b2_sincos(x, s, c); return c; }
+
 // float trig evaluated through double and rounded once: reproducible on host and device
-B2_HD float sin_f32(float x) { return (float)sin((double)x); }
-B2_HD float cos_f32(float x) { return (float)cos((double)x); }
+B2_HD float sin_f32(float x) { return (float)b2_sin((double)x); }
+B2_HD float cos_f32(float x) { return (float)b2_cos((double)x); }
 B2_HD float atan2_f32(float y, float x) { return (float)atan2((double)y, (double)x); }
 
 // ------------------------------------------------------------------ pose <-> matrix ----------
@@ -218,8 +251,8 @@ struct AngTab {
     double h[15][3];
 };
 // snapped trig of NDTM:527-549: |angle| < 10e-5 -> (cos, sin) = (1, 0)
-B2_HD double ang_sin(double a) { return (fabs(a) < 10e-5) ? 0.0 : sin(a); }
-B2_HD double ang_cos(double a) { return (fabs(a) < 10e-5) ? 1.0 : cos(a); }
+B2_HD double ang_sin(double a) { return (fabs(a) < 10e-5) ? 0.0 : b2_sin(a); }
+B2_HD double ang_cos(double a) { return (fabs(a) < 10e-5) ? 1.0 : b2_cos(a); }
 B2_HD_NOINLINE inline void angle_derivatives_sc(double sx, double cx, double sy, double cy, double sz, double cz, AngTab &A);
 B2_HD_NOINLINE inline void angle_derivatives(const double p[6], AngTab &A) {
     angle_derivatives_sc(ang_sin(p[3]), ang_cos(p[3]), ang_sin(p[4]), ang_cos(p[4]), ang_sin(p[5]), ang_cos(p[5]), A);

@@ -10,6 +10,7 @@
 using namespace b2;
 
 extern "C" {
+void hc_sincos(double x, double *s, double *c) { b2_sincos(x, *s, *c); }
 void hc_pose_to_matrix(const double *p, float *T) { pose_to_matrix_f32(p, T); }
 void hc_euler(const float *T, float *out) { euler_from_matrix_f32(T, out); }
 void hc_newton_solve6(const double *H, const double *b, double *x, int force_svd) { newton_solve6(H, b, x, force_svd); }
