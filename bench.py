@@ -357,6 +357,15 @@ def main():
         alg_bytes = float(np.sum(passes * (16.0 * npts + 80.0 * rho * npts + 224.0)) + 64.0 * B)
         launch_s = (dev_ms / args.steps) * 1e-3
         achieved = alg_bytes / launch_s / 1e9
+        # DRAM traffic of one launch from the committed ncu --set full capture (same command, same frames)
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+                tj = json.load(f)
+            if tj.get("frames_per_launch") == B:
+                traffic = float(tj["dram_bytes_read"] + tj["dram_bytes_write"])
+        except Exception:
+            pass
         flops = float(np.sum(passes * 60.0 * npts) + 450.0 * res["pairs"].sum())
 
         # CPU baseline: the oracle, single thread, bounded sample of the same frames
@@ -394,10 +403,10 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(tot[1].item()),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "kernel": "ndt_match_kernel", "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                          "v_touched_per_source_point": rho, "fp64_gflops_est": flops / launch_s / 1e9,
-                         "note": "L2-resident gather+reduce; latency/FP64-bound, see DESIGN.md"},
+                         "note": "working set is L2-resident (DRAM traffic << algorithmic bytes): bound by L1/LSU wavefronts + load latency, see profiles/README.md"},
             "cpu_baseline": ({"value": cpu_value, "unit": UNIT, "cores": 1, "kind": "port",
                               "sample": "%d of the %d frames, oracle align, 1 thread" % (len(sample), B)} if cpu_value else None),
             "parity": parity,

@@ -56,7 +56,8 @@ def build_cuda(force=False, verbose=False):
     deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     deps.append(os.path.join(ROOT, "include", "b2ndt.h"))
     if force or _newer(out, deps):
-        cmd = [_nvcc()] + NVCC_FLAGS + ["-I", os.path.join(ROOT, "include"), "-I", CSRC, "-shared", "-o", out] + srcs
+        extra = os.environ.get("B2_NVCC_EXTRA", "").split()
+        cmd = [_nvcc()] + NVCC_FLAGS + extra + ["-I", os.path.join(ROOT, "include"), "-I", CSRC, "-shared", "-o", out] + srcs
         cmd += ["-lcudart"]
         r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         log = os.path.join(LIBDIR, "nvcc_ptxas.log")
