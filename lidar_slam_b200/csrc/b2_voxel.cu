@@ -70,7 +70,7 @@ void pack_cloud_f4(const void *src, size_t n, size_t stride, size_t ioff, float 
             dst[4 * i + 0] = p[0]; dst[4 * i + 1] = p[1]; dst[4 * i + 2] = p[2]; dst[4 * i + 3] = inten;
         }
     };
-    if (stride == 16 && ioff == 12) { memcpy(dst, src, n * 16); return; }
+    if (stride == 16 && ioff == 12 && n <= 400000) { memcpy(dst, src, n * 16); return; }
     unsigned hw = std::thread::hardware_concurrency();
     size_t nt = n > 400000 ? (hw > 8 ? 8 : (hw ? hw : 1)) : 1;
     if (nt <= 1) { work(0, n); return; }

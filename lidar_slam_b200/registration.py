@@ -89,8 +89,11 @@ class NDTRegistration(RegistrationInterface):
 
     def __del__(self):
         h = getattr(self, "_h", None)
-        if h:
-            capi.lib().b2ndt_destroy(h)
+        if h and capi is not None and getattr(capi, "_LIB", None) is not None:
+            try:
+                capi._LIB.b2ndt_destroy(h)
+            except Exception:
+                pass
             self._h = None
 
     # ---- reference surface -------------------------------------------------------------------
@@ -215,8 +218,11 @@ class VoxelFilter(CloudFilterInterface):
 
     def __del__(self):
         h = getattr(self, "_h", None)
-        if h:
-            capi.lib().b2vf_destroy(h)
+        if h and capi is not None and getattr(capi, "_LIB", None) is not None:
+            try:
+                capi._LIB.b2vf_destroy(h)
+            except Exception:
+                pass
             self._h = None
 
     def Filter(self, input_cloud, with_info=False):
