@@ -53,7 +53,8 @@ def measured_peaks():
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,"
+         "utilization.gpu")
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
@@ -79,15 +80,18 @@ class ClockSampler:
             self.p.kill()
         self.f.flush()
         self.f.seek(0)
-        sm, mx, reasons = [], [], set()
+        sm, mx, reasons, load = [], [], set(), []
         for line in self.f.read().splitlines():
             c = [x.strip() for x in line.split(",")]
-            if len(c) < 9:
+            if len(c) < 10:
                 continue
             try:
-                sm.append(float(c[1])); mx.append(float(c[2]))
+                s_, m_, u_ = float(c[1]), float(c[2]), float(c[9])
             except ValueError:
                 continue
+            sm.append(s_); mx.append(m_)
+            if u_ >= 50.0:
+                load.append(s_)
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
@@ -96,7 +100,9 @@ class ClockSampler:
         except OSError:
             pass
         if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(np.max(mx)), reasons=sorted(reasons), samples=len(sm))
+            under = load if load else sm
+            out.update(sm_mhz=float(np.median(under)), sm_max_mhz=float(np.max(mx)), reasons=sorted(reasons), samples=len(sm),
+                       samples_under_load=len(load))
         return out
 
 
