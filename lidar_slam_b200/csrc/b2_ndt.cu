@@ -760,7 +760,7 @@ extern "C" int b2ndt_set_cluster(b2ndt *h, int single_match_ctas, int batch_ctas
     return 0;
 }
 
-static int build_target(b2ndt *h, const float4 *d_pts, size_t n) {
+static int build_target(b2ndt *h, const float4 *d_pts, size_t n, int nbits_hint) {
     TargetDev &t = h->tgt;
     t.valid = false; t.N = (uint32_t)n; t.V = 0; t.n_tree = 0; t.max_disp = 0.f;
     h->have_last = false;
@@ -769,7 +769,7 @@ static int build_target(b2ndt *h, const float4 *d_pts, size_t n) {
     uint32_t off[2] = {0u, (uint32_t)n};
     if ((rc = h->pipe.plan(off, 1, h->st))) return rc;
     const float res = h->prm.res;
-    if ((rc = h->pipe.run(d_pts, res, res, res, 0, h->st))) return rc;
+    if ((rc = h->pipe.run(d_pts, res, res, res, nbits_hint, h->st))) return rc;
     if ((rc = h->h_small.reserve(4096))) return rc;
     uint32_t *misc = h->h_small.as<uint32_t>();
     B2_CUDA(cudaMemcpyAsync(misc, h->pipe.scalars(), 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->st));
@@ -829,11 +829,14 @@ extern "C" int b2ndt_set_target(b2ndt *h, const void *pts, size_t n, size_t stri
     B2_CUDA(cudaSetDevice(h->device));
     if ((rc = h->h_stage.reserve(n * 16 + 16))) return rc;
     if ((rc = h->tgt.pts_in.reserve(n * 16 + 16))) return rc;
+    int nbits_hint = 0;
     if (n) {
-        pack_cloud_f4(pts, n, stride, ioff, h->h_stage.as<float>());
+        float mn[3], mx[3];
+        pack_cloud_f4_bbox(pts, n, stride, ioff, h->h_stage.as<float>(), mn, mx);
+        nbits_hint = key_bits_from_bbox(mn, mx, h->prm.res, h->prm.res, h->prm.res);
         B2_CUDA(cudaMemcpyAsync(h->tgt.pts_in.p, h->h_stage.p, n * 16, cudaMemcpyHostToDevice, h->st));
     }
-    return build_target(h, h->tgt.pts_in.as<float4>(), n);
+    return build_target(h, h->tgt.pts_in.as<float4>(), n, nbits_hint);
 }
 
 extern "C" int b2ndt_set_target_device(b2ndt *h, const void *d_pts_f4, size_t n) {
@@ -841,7 +844,7 @@ extern "C" int b2ndt_set_target_device(b2ndt *h, const void *d_pts_f4, size_t n)
     if (n && !d_pts_f4) { set_error("b2ndt_set_target_device: NULL cloud"); return B2_ERR_INVALID; }
     if (n >= 0xFFFFFFF0ull) { set_error("b2ndt_set_target_device: cloud too large"); return B2_ERR_INVALID; }
     B2_CUDA(cudaSetDevice(h->device));
-    return build_target(h, (const float4 *)d_pts_f4, n);
+    return build_target(h, (const float4 *)d_pts_f4, n, 0);
 }
 
 extern "C" int b2ndt_target_info_get(b2ndt *h, b2ndt_target_info *info) {

@@ -48,17 +48,38 @@ int key_bits_from_bbox(const float mn[3], const float mx[3], float lx, float ly,
 }
 
 void pack_cloud_f4_bbox(const void *src, size_t n, size_t stride, size_t ioff, float *dst, float mn[3], float mx[3]) {
-    const char *s = (const char *)src;
-    for (int a = 0; a < 3; ++a) { mn[a] = FLT_MAX; mx[a] = -FLT_MAX; }
-    for (size_t i = 0; i < n; ++i) {
-        const float *p = (const float *)(s + i * stride);
-        const float x = p[0], y = p[1], z = p[2];
-        dst[4 * i + 0] = x; dst[4 * i + 1] = y; dst[4 * i + 2] = z; dst[4 * i + 3] = *(const float *)(s + i * stride + ioff);
-        if (std::isfinite(x) && std::isfinite(y) && std::isfinite(z)) {
-            mn[0] = x < mn[0] ? x : mn[0]; mn[1] = y < mn[1] ? y : mn[1]; mn[2] = z < mn[2] ? z : mn[2];
-            mx[0] = x > mx[0] ? x : mx[0]; mx[1] = y > mx[1] ? y : mx[1]; mx[2] = z > mx[2] ? z : mx[2];
+    struct BB { float mn[3], mx[3]; };
+    auto work = [=](size_t a, size_t b, BB *bb) {
+        const char *s = (const char *)src;
+        float lmn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, lmx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+        for (size_t i = a; i < b; ++i) {
+            const float *p = (const float *)(s + i * stride);
+            const float x = p[0], y = p[1], z = p[2];
+            dst[4 * i + 0] = x; dst[4 * i + 1] = y; dst[4 * i + 2] = z; dst[4 * i + 3] = *(const float *)(s + i * stride + ioff);
+            if (std::isfinite(x) && std::isfinite(y) && std::isfinite(z)) {
+                lmn[0] = x < lmn[0] ? x : lmn[0]; lmn[1] = y < lmn[1] ? y : lmn[1]; lmn[2] = z < lmn[2] ? z : lmn[2];
+                lmx[0] = x > lmx[0] ? x : lmx[0]; lmx[1] = y > lmx[1] ? y : lmx[1]; lmx[2] = z > lmx[2] ? z : lmx[2];
+            }
         }
+        for (int k = 0; k < 3; ++k) { bb->mn[k] = lmn[k]; bb->mx[k] = lmx[k]; }
+    };
+    unsigned hw = std::thread::hardware_concurrency();
+    size_t nt = n > 400000 ? (hw > 8 ? 8 : (hw ? hw : 1)) : 1;
+    std::vector<BB> bbs(nt);
+    if (nt <= 1) work(0, n, &bbs[0]);
+    else {
+        std::vector<std::thread> th;
+        size_t chunk = (n + nt - 1) / nt;
+        for (size_t t = 0; t < nt; ++t) {
+            size_t a = t * chunk, b = a + chunk < n ? a + chunk : n;
+            if (a >= b) { for (int k = 0; k < 3; ++k) { bbs[t].mn[k] = FLT_MAX; bbs[t].mx[k] = -FLT_MAX; } continue; }
+            th.emplace_back(work, a, b, &bbs[t]);
+        }
+        for (auto &t : th) t.join();
     }
+    for (int k = 0; k < 3; ++k) { mn[k] = FLT_MAX; mx[k] = -FLT_MAX; }
+    for (size_t t = 0; t < nt; ++t)
+        for (int k = 0; k < 3; ++k) { mn[k] = bbs[t].mn[k] < mn[k] ? bbs[t].mn[k] : mn[k]; mx[k] = bbs[t].mx[k] > mx[k] ? bbs[t].mx[k] : mx[k]; }
 }
 
 void pack_cloud_f4(const void *src, size_t n, size_t stride, size_t ioff, float *dst) {
@@ -216,46 +237,33 @@ __global__ void __launch_bounds__(SORT_THREADS) radix_hist_kernel(const uint32_t
     tilehist[(size_t)sg.tile_begin * RADIX + (size_t)threadIdx.x * sg.ntiles + t.tile_in_seg] = h[threadIdx.x];
 }
 
-// ---- radix pass: per cloud, exclusive scan of every bin row over tiles + scan of the bin totals
+// ---- radix pass: exclusive scan of every (cloud, bin) row over the cloud's tiles.  One warp per row,
+// eight rows per CTA, 32 CTAs per cloud (a single CTA per cloud took 330 us per pass on a 5 M-point map).
+// The row totals go to binbase[cloud][bin]; the scatter kernel turns them into bin offsets itself.
 __global__ void __launch_bounds__(SORT_THREADS) radix_scan_kernel(const SegDesc *__restrict__ segs,
                                                                   uint32_t *__restrict__ tilehist,
                                                                   uint32_t *__restrict__ binbase, int shift,
                                                                   const uint32_t *__restrict__ scalars) {
     if ((uint32_t)shift >= scalars[0]) return;
-    const SegDesc sg = segs[blockIdx.x];
-    __shared__ uint32_t tot[RADIX];
-    __shared__ uint32_t wsum[SORT_THREADS / 32];
+    constexpr int ROWS_PER_CTA = SORT_THREADS / 32;
+    const uint32_t seg = blockIdx.x / (RADIX / ROWS_PER_CTA);
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-    uint32_t *base = tilehist + (size_t)sg.tile_begin * RADIX;
-    for (int bin = w; bin < RADIX; bin += SORT_THREADS / 32) {
-        uint32_t *row = base + (size_t)bin * sg.ntiles;
-        uint32_t running = 0;
-        for (uint32_t t0 = 0; t0 < sg.ntiles; t0 += 32) {
-            uint32_t v = (t0 + l < sg.ntiles) ? row[t0 + l] : 0u;
-            uint32_t inc = v;
+    const int bin = (blockIdx.x % (RADIX / ROWS_PER_CTA)) * ROWS_PER_CTA + w;
+    const SegDesc sg = segs[seg];
+    uint32_t *row = tilehist + (size_t)sg.tile_begin * RADIX + (size_t)bin * sg.ntiles;
+    uint32_t running = 0;
+    for (uint32_t t0 = 0; t0 < sg.ntiles; t0 += 32) {
+        uint32_t v = (t0 + l < sg.ntiles) ? row[t0 + l] : 0u;
+        uint32_t inc = v;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                uint32_t n = __shfl_up_sync(0xffffffffu, inc, o);
-                if (l >= o) inc += n;
-            }
-            if (t0 + l < sg.ntiles) row[t0 + l] = running + inc - v;
-            running += __shfl_sync(0xffffffffu, inc, 31);
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t n = __shfl_up_sync(0xffffffffu, inc, o);
+            if (l >= o) inc += n;
         }
-        if (l == 0) tot[bin] = running;
+        if (t0 + l < sg.ntiles) row[t0 + l] = running + inc - v;
+        running += __shfl_sync(0xffffffffu, inc, 31);
     }
-    __syncthreads();
-    // exclusive scan of the 256 bin totals
-    uint32_t v = tot[threadIdx.x], inc = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        uint32_t n = __shfl_up_sync(0xffffffffu, inc, o);
-        if (l >= o) inc += n;
-    }
-    if (l == 31) wsum[w] = inc;
-    __syncthreads();
-    uint32_t add = 0;
-    for (int i = 0; i < w; ++i) add += wsum[i];
-    binbase[(size_t)blockIdx.x * RADIX + threadIdx.x] = add + inc - v;
+    if (l == 0) binbase[(size_t)seg * RADIX + bin] = running;      // row total
 }
 
 // ---- radix pass: stable scatter.  Warp w owns elements [512w, 512w+512) of the tile in 16 rounds of
@@ -278,6 +286,7 @@ __global__ void __launch_bounds__(SORT_THREADS) radix_scatter_kernel(
     constexpr int ROUNDS = SORT_TILE / SORT_THREADS;
     __shared__ uint32_t wcnt[NW][RADIX];
     __shared__ uint32_t gbase[RADIX];
+    __shared__ uint32_t wtot[NW];
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
     for (int i = threadIdx.x; i < NW * RADIX; i += SORT_THREADS) (&wcnt[0][0])[i] = 0;
     __syncthreads();
@@ -307,7 +316,19 @@ __global__ void __launch_bounds__(SORT_THREADS) radix_scatter_kernel(
         uint32_t d = threadIdx.x, run = 0;
 #pragma unroll
         for (int i = 0; i < NW; ++i) { uint32_t c = wcnt[i][d]; wcnt[i][d] = run; run += c; }
-        gbase[d] = sg.begin + binbase[(size_t)t.seg * RADIX + d] +
+        // exclusive scan of the cloud's 256 bin totals (block scan)
+        const uint32_t v = binbase[(size_t)t.seg * RADIX + d];
+        uint32_t inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t n = __shfl_up_sync(0xffffffffu, inc, o);
+            if (l >= o) inc += n;
+        }
+        if (l == 31) wtot[w] = inc;
+        __syncthreads();
+        uint32_t add = 0;
+        for (int i = 0; i < w; ++i) add += wtot[i];
+        gbase[d] = sg.begin + (add + inc - v) +
                    tilehist[(size_t)sg.tile_begin * RADIX + (size_t)d * sg.ntiles + t.tile_in_seg];
     }
     __syncthreads();
@@ -488,7 +509,7 @@ int VoxPipeline::run(const float4 *d_pts, float lx, float ly, float lz, int nbit
             uint32_t *ko = d_keys[final_buf ^ 1].as<uint32_t>(), *vo = d_vals[final_buf ^ 1].as<uint32_t>();
             radix_hist_kernel<<<nt, SORT_THREADS, 0, st>>>(ki, tiles, segs, d_tilehist.as<uint32_t>(), shift, sc);
             B2_LAUNCH_CHECK();
-            radix_scan_kernel<<<nB, SORT_THREADS, 0, st>>>(segs, d_tilehist.as<uint32_t>(), d_binbase.as<uint32_t>(), shift, sc);
+            radix_scan_kernel<<<nB * (RADIX / (SORT_THREADS / 32)), SORT_THREADS, 0, st>>>(segs, d_tilehist.as<uint32_t>(), d_binbase.as<uint32_t>(), shift, sc);
             B2_LAUNCH_CHECK();
             radix_scatter_kernel<<<nt, SORT_THREADS, 0, st>>>(ki, vi, ko, vo, tiles, segs, d_tilehist.as<uint32_t>(),
                                                              d_binbase.as<uint32_t>(), shift, sc);
@@ -680,14 +701,17 @@ extern "C" int b2vf_filter(b2vf *h, const void *in, size_t n, size_t stride, siz
     // host pass: repack to float4 and (for free) bound the key width so the sort runs only the radix
     // passes it needs
     int nbits_hint = 0;
-    if (n <= 2000000) {
+    const void *h2d_from = h->h_in.p;
+    if (stride == 16 && ioff == 12 && n > 1000000) {
+        // large packed cloud: DMA straight from the caller's memory (full PCIe rate when it is pinned, the
+        // driver's staging otherwise); the key width is then decided on the device
+        h2d_from = in;
+    } else {
         float mn[3], mx[3];
         pack_cloud_f4_bbox(in, n, stride, ioff, h->h_in.as<float>(), mn, mx);
         nbits_hint = key_bits_from_bbox(mn, mx, h->leaf[0], h->leaf[1], h->leaf[2]);
-    } else {
-        pack_cloud_f4(in, n, stride, ioff, h->h_in.as<float>());
     }
-    B2_CUDA(cudaMemcpyAsync(h->d_in.p, h->h_in.p, n * 16, cudaMemcpyHostToDevice, h->st));
+    B2_CUDA(cudaMemcpyAsync(h->d_in.p, h2d_from, n * 16, cudaMemcpyHostToDevice, h->st));
     uint32_t off[2] = {0u, (uint32_t)n};
     if ((rc = h->pipe.plan(off, 1, h->st))) return rc;
     if ((rc = h->pipe.run(h->d_in.as<float4>(), h->leaf[0], h->leaf[1], h->leaf[2], nbits_hint, h->st))) return rc;
@@ -712,6 +736,7 @@ extern "C" int b2vf_filter(b2vf *h, const void *in, size_t n, size_t stride, siz
         if (L.n_finite == 0) { *m = 0; return 0; }
         // PCL: "Leaf size is too small for the input dataset" -> output = *input
         if (out_capacity < n) { set_error("b2vf_filter: output capacity %zu < %zu", out_capacity, n); return B2_ERR_CAPACITY; }
+        if (h2d_from == in) pack_cloud_f4(in, n, stride, ioff, h->h_in.as<float>());
         const float *src = h->h_in.as<float>();
         for (size_t j = 0; j < n; ++j) {
             put(j, src + 4 * j);
