@@ -55,12 +55,19 @@ def build_cuda(force=False, verbose=False):
     srcs = cuda_sources()
     deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     deps.append(os.path.join(ROOT, "include", "b2ndt.h"))
-    if force or _newer(out, deps):
-        extra = os.environ.get("B2_NVCC_EXTRA", "").split()
-        cmd = [_nvcc()] + NVCC_FLAGS + extra + ["-I", os.path.join(ROOT, "include"), "-I", CSRC, "-shared", "-o", out] + srcs
-        cmd += ["-lcudart"]
+    extra = os.environ.get("B2_NVCC_EXTRA", "").split()
+    cmd = [_nvcc()] + NVCC_FLAGS + extra + ["-I", os.path.join(ROOT, "include"), "-I", CSRC, "-shared", "-o", out] + srcs
+    cmd += ["-lcudart"]
+    log = os.path.join(LIBDIR, "nvcc_ptxas.log")
+    # the library is rebuilt when a source is newer OR when it was built with a different command line
+    # (e.g. an experiment's -D flags): the first line of the log is the stamp
+    try:
+        with open(log) as f:
+            same_cmd = f.readline().rstrip("\n") == " ".join(cmd)
+    except OSError:
+        same_cmd = False
+    if force or not same_cmd or _newer(out, deps):
         r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-        log = os.path.join(LIBDIR, "nvcc_ptxas.log")
         with open(log, "w") as f:
             f.write(" ".join(cmd) + "\n" + r.stdout)
         if verbose or r.returncode != 0:
