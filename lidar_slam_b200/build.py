@@ -48,17 +48,19 @@ def cuda_sources():
     return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
 
 
-def build_cuda(force=False, verbose=False):
-    """nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo ... -> libb2ndt.so (cross-compiles without a GPU)."""
+def build_cuda(force=False, verbose=False, variant=None, variant_flags=()):
+    """nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo ... -> libb2ndt.so (cross-compiles without a GPU).
+    `variant` builds a tuning variant libb2ndt_<variant>.so with extra -D flags (selected at run time with
+    the environment variable B2NDT_LIB; used by tools/ for kernel-shape sweeps only)."""
     os.makedirs(LIBDIR, exist_ok=True)
-    out = os.path.join(LIBDIR, "libb2ndt.so")
+    out = os.path.join(LIBDIR, "libb2ndt%s.so" % ("_" + variant if variant else ""))
     srcs = cuda_sources()
     deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     deps.append(os.path.join(ROOT, "include", "b2ndt.h"))
-    extra = os.environ.get("B2_NVCC_EXTRA", "").split()
+    extra = os.environ.get("B2_NVCC_EXTRA", "").split() + list(variant_flags)
     cmd = [_nvcc()] + NVCC_FLAGS + extra + ["-I", os.path.join(ROOT, "include"), "-I", CSRC, "-shared", "-o", out] + srcs
     cmd += ["-lcudart"]
-    log = os.path.join(LIBDIR, "nvcc_ptxas.log")
+    log = os.path.join(LIBDIR, "nvcc_ptxas%s.log" % ("_" + variant if variant else ""))
     # the library is rebuilt when a source is newer OR when it was built with a different command line
     # (e.g. an experiment's -D flags): the first line of the log is the stamp
     try:

@@ -54,7 +54,8 @@ class TargetInfo(C.Structure):
 
 
 def lib_path():
-    return os.path.join(_build.LIBDIR, "libb2ndt.so")
+    # B2NDT_LIB selects a tuning variant built by build.build_cuda(variant=...) (kernel-shape sweeps)
+    return os.environ.get("B2NDT_LIB") or os.path.join(_build.LIBDIR, "libb2ndt.so")
 
 
 def lib():

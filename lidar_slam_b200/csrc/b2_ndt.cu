@@ -14,6 +14,10 @@
 //   gauss       double[10][V]  80-byte records {mean[3], icov xx,xy,xz,yy,yz,zz, pad}
 //   cells       float4[ncells] dense grid record {centroid x,y,z, code}: code = +(leaf+1) searchable (n >= min_pts),
 //                              -(leaf+1) sparse, 0 empty
+//   nbr_head    uint2[ncells]  {first entry, count} of the cell's neighbour list
+//   nbr_list    float4[..]     per cell, the searchable leaves of its 3x3x3 window {centroid x,y,z, leaf} in
+//                              fixed (z,y,x) order, lists laid out in cell order (a radius query reads ONE
+//                              header and one contiguous run instead of 27 scattered cells)
 // The path is a gather + reduction (no dense contraction): no tensor cores by design.
 #include <cooperative_groups.h>
 
@@ -38,6 +42,7 @@ struct TargetDev {
     DevBuf pts_in;            // float4[N] as given (host path)
     DevBuf pts_sorted;        // float4[N]
     DevBuf leaf_idx, leaf_n, leaf_start, centroid4, gauss, sums, icov9, cells, counters;
+    DevBuf nbr_head, nbr_list, nbr_tiles;
     bool valid = false;
 };
 
@@ -95,7 +100,7 @@ __global__ void __launch_bounds__(128) leaf_finish_kernel(uint32_t V, int min_pt
                                                           const float4 *__restrict__ centroid4,
                                                           const double *__restrict__ sums, double *__restrict__ gauss,
                                                           double *__restrict__ icov9, float4 *__restrict__ cells,
-                                                          uint32_t *__restrict__ counters) {
+                                                          uint2 *__restrict__ nbr_head, uint32_t *__restrict__ counters) {
     uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= V) return;
     const double *s = sums + (size_t)j * 9;
@@ -126,6 +131,14 @@ __global__ void __launch_bounds__(128) leaf_finish_kernel(uint32_t V, int min_pt
         const int iz = idx / (LA.div_b[0] * LA.div_b[1]);
         const int iy = (idx - iz * LA.div_b[0] * LA.div_b[1]) / LA.div_b[0];
         const int ix = idx - iz * LA.div_b[0] * LA.div_b[1] - iy * LA.div_b[0];
+        // this leaf appears in the neighbour list of every in-grid cell of its 3x3x3 window
+        for (int dz = -1; dz <= 1; ++dz)
+            for (int dy = -1; dy <= 1; ++dy)
+                for (int dx = -1; dx <= 1; ++dx) {
+                    const int kx = ix + dx, ky = iy + dy, kz = iz + dz;
+                    if (kx < 0 || ky < 0 || kz < 0 || kx >= LA.div_b[0] || ky >= LA.div_b[1] || kz >= LA.div_b[2]) continue;
+                    atomicAdd(&nbr_head[(size_t)kx + (size_t)ky * LA.div_b[0] + (size_t)kz * LA.div_b[0] * LA.div_b[1]].y, 1u);
+                }
         const float4 c = centroid4[j];
         const double cc[3] = {(double)c.x, (double)c.y, (double)c.z};
         const int ii[3] = {ix, iy, iz};
@@ -136,6 +149,102 @@ __global__ void __launch_bounds__(128) leaf_finish_kernel(uint32_t V, int min_pt
             disp = fmax(disp, fmax(lo - cc[a], cc[a] - hi));
         }
         if (disp > 0.0) atomicMax(&counters[1], __float_as_uint(__double2float_ru(disp)));   // positive floats order as uints
+    }
+}
+
+// ------------------------------------------------------------------ neighbour lists ----------
+// nbr_head[c].y holds the number of searchable leaves in the 3x3x3 window of cell c (counted by
+// leaf_finish_kernel).  Three steps lay the lists out in cell order: per-tile sums, a scan of the tile
+// sums, and a fill pass that scans inside each tile, writes the list offsets and gathers the entries
+// in fixed (z, y, x) window order -- the layout and the order are deterministic.
+constexpr int NBR_TPB = 256;
+constexpr int NBR_ROUNDS = 8;
+constexpr uint32_t NBR_TILE = NBR_TPB * NBR_ROUNDS;
+
+__device__ __forceinline__ uint32_t block_excl_scan_256(uint32_t v, uint32_t *warp_tot /*smem[9]*/, uint32_t &block_total) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+    if (lane == 31) warp_tot[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+        uint32_t t = (lane < 8) ? warp_tot[lane] : 0u;
+        uint32_t ti = t;
+#pragma unroll
+        for (int d = 1; d < 8; d <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, ti, d); if (lane >= d) ti += u; }
+        if (lane < 8) warp_tot[lane] = ti - t;
+        if (lane == 7) warp_tot[8] = ti;
+    }
+    __syncthreads();
+    const uint32_t r = warp_tot[w] + incl - v;
+    block_total = warp_tot[8];
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(NBR_TPB) nbr_tile_sum_kernel(const uint2 *__restrict__ head, uint32_t ncells,
+                                                               uint32_t *__restrict__ tile_sum) {
+    __shared__ uint32_t wsum[8];
+    uint32_t s = 0;
+#pragma unroll
+    for (int r = 0; r < NBR_ROUNDS; ++r) {
+        const size_t c = (size_t)blockIdx.x * NBR_TILE + (size_t)r * NBR_TPB + threadIdx.x;
+        if (c < ncells) s += __ldg(&head[c]).y;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int w = 0; w < 8; ++w) t += wsum[w];
+        tile_sum[blockIdx.x] = t;
+    }
+}
+
+// single CTA: exclusive scan of the tile sums in place
+__global__ void __launch_bounds__(NBR_TPB) nbr_tile_scan_kernel(uint32_t *__restrict__ tile_sum, uint32_t ntiles) {
+    __shared__ uint32_t wt[9];
+    uint32_t base = 0;
+    for (uint32_t t0 = 0; t0 < ntiles; t0 += NBR_TPB) {
+        const uint32_t t = t0 + threadIdx.x;
+        const uint32_t v = (t < ntiles) ? tile_sum[t] : 0u;
+        uint32_t tot;
+        const uint32_t ex = block_excl_scan_256(v, wt, tot);
+        if (t < ntiles) tile_sum[t] = base + ex;
+        base += tot;
+    }
+}
+
+__global__ void __launch_bounds__(NBR_TPB) nbr_fill_kernel(uint2 *__restrict__ head, const float4 *__restrict__ cells,
+                                                           uint32_t ncells, const uint32_t *__restrict__ tile_base, LayoutArg LA,
+                                                           float4 *__restrict__ list) {
+    __shared__ uint32_t wt[9];
+    uint32_t base = tile_base[blockIdx.x];
+    const int dx_n = LA.div_b[0], dy_n = LA.div_b[1], dz_n = LA.div_b[2];
+    for (int r = 0; r < NBR_ROUNDS; ++r) {
+        const size_t c = (size_t)blockIdx.x * NBR_TILE + (size_t)r * NBR_TPB + threadIdx.x;
+        const uint32_t cnt = (c < ncells) ? head[c].y : 0u;
+        uint32_t tot;
+        const uint32_t off = base + block_excl_scan_256(cnt, wt, tot);
+        base += tot;
+        if (cnt) {
+            head[c].x = off;
+            const int iz = (int)(c / ((size_t)dx_n * dy_n));
+            const int rem = (int)(c - (size_t)iz * dx_n * dy_n);
+            const int iy = rem / dx_n, ix = rem - iy * dx_n;
+            uint32_t k = 0;
+            for (int dz = -1; dz <= 1; ++dz)
+                for (int dy = -1; dy <= 1; ++dy)
+                    for (int dx = -1; dx <= 1; ++dx) {
+                        const int kx = ix + dx, ky = iy + dy, kz = iz + dz;
+                        if (kx < 0 || ky < 0 || kz < 0 || kx >= dx_n || ky >= dy_n || kz >= dz_n) continue;
+                        const float4 e = __ldg(&cells[(size_t)kx + (size_t)ky * dx_n + (size_t)kz * dx_n * dy_n]);
+                        const int code = __float_as_int(e.w);
+                        if (code > 0) { list[off + k] = make_float4(e.x, e.y, e.z, __int_as_float(code - 1)); ++k; }
+                    }
+        }
     }
 }
 
@@ -167,14 +276,20 @@ __global__ void __launch_bounds__(128) leaf_finish_kernel(uint32_t V, int min_pt
 #ifndef NDT_REG_SEARCH
 #define NDT_REG_SEARCH 56
 #endif
+#ifndef NDT_PF
+#define NDT_PF 0       // compute warps prefetch the next chunk's voxel records into L1
+#endif
+constexpr int NACC = 35;                       // per-lane accumulators of a derivative pass (layout at ndt_pair)
 constexpr int NDT_WARPS = NDT_NCW + NDT_NSW;
 constexpr int NDT_THREADS = NDT_WARPS * 32;
 constexpr int NDT_PPC = NDT_NSW / NDT_NCW;     // producers (search warps) per compute warp
-constexpr uint32_t RING = 1024;                // ring entries per search warp (power of two, > 512 + 32)
+constexpr uint32_t RING = 512;                 // ring entries per search warp (power of two, >= 128 + 32)
 static_assert(NDT_NCW % 4 == 0 && NDT_NSW % 4 == 0 && NDT_NSW % NDT_NCW == 0, "warp-group multiples");
 
 struct GridView {
     const float4 *cells;         // dense grid record {cx, cy, cz, int code}: code > 0 searchable leaf+1, < 0 sparse, 0 empty
+    const uint2 *nbr_head;       // per cell {first entry, count} of its neighbour list
+    const float4 *nbr_list;      // {cx, cy, cz, leaf} of the searchable leaves of the cell's 3x3x3 window
     const double *gauss;
     int32_t min_b[3], div_b[3], mul[3];
     float res, r2;      // search radius = resolution ; r2 = (float)(res*res)
@@ -193,13 +308,25 @@ struct MatchArgs {
     b2ndt_result *results;       // B
     double *acc_out;             // B*ACC_N (deriv-only mode)
     int deriv_only;
+    unsigned long long *timing;  // NDT_TIMING builds only: per-phase SM-cycle totals (tools/ sweeps)
 };
+
+#ifdef NDT_TIMING
+#define TM_NOW() clock64()
+#define TM_ADD(slot, t0) do { if (lane == 0) tm[slot] += (unsigned long long)(clock64() - (t0)); } while (0)
+#define TM_EV(k) do { if (lane == 0 && blockIdx.x == 0 && pass_id <= 4 && A.timing) A.timing[32 + (pass_id - 1) * 16 + (k)] = (unsigned long long)clock64(); } while (0)
+#else
+#define TM_NOW() 0ll
+#define TM_ADD(slot, t0) do { (void)(t0); } while (0)
+#define TM_EV(k) do { } while (0)
+#endif
 
 struct NdtSmem {
     Ctl ctl;
-    double warp_part[NDT_NCW][ACC_N];
-    double cta_part[2][ACC_N];     // double-buffered per-CTA partial, read by cluster peers over DSMEM
-    double total[ACC_N];
+    double warp_part[NDT_NCW][NACC];
+    double cta_part[2][NACC];      // double-buffered per-CTA partial, read by cluster peers over DSMEM
+    double raw_total[NACC];        // reduced pair sums (NACC layout)
+    double total[ACC_N];           // contracted with the angle tables: what the controller consumes
     double trig_d[6];              // snapped double sin x3, cos x3 of the requested pose
     float  trig_f[6];              // float sin x3, cos x3
     int go;
@@ -208,22 +335,43 @@ struct NdtSmem {
     uint32_t tail[NDT_NSW];        // entries produced by search warp s
     uint32_t head[NDT_NSW];        // entries consumed from search warp s
     uint32_t finished[NDT_NSW];    // last pass id search warp s has completed
-    uint2 ring[NDT_NSW][RING];     // (source point index, leaf index)
+    float4 ring[NDT_NSW][RING];    // (source point x, y, z, leaf index): consumers never touch the source cloud
+    float4 stage[NDT_NSW][128];    // per search warp, double-buffered: [lane] source point, [32 + lane] transformed point
 };
 
 __device__ __forceinline__ void cta_barrier() { asm volatile("bar.sync 0, %0;" ::"n"(NDT_THREADS) : "memory"); }
 __device__ __forceinline__ uint32_t ld_vol(const uint32_t *p) { return *reinterpret_cast<const volatile uint32_t *>(p); }
 __device__ __forceinline__ void st_vol(uint32_t *p, uint32_t v) { *reinterpret_cast<volatile uint32_t *>(p) = v; }
+#ifndef NDT_FENCE
+#define NDT_FENCE 1
+#endif
+// producer side: make the ring entries written by the warp (ordered by the preceding __syncwarp) visible
+// before the new tail
+__device__ __forceinline__ void publish_tail(uint32_t *p, uint32_t v) {
+#if NDT_FENCE == 1
+    __threadfence_block();
+    st_vol(p, v);
+#elif NDT_FENCE == 2
+    asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+#else
+    st_vol(p, v);
+#endif
+}
 
 __device__ __forceinline__ double dot3v(const double *h, double x, double y, double z) { return x * h[0] + y * h[1] + z * h[2]; }
 __device__ __forceinline__ double dot2v(const double *h, double x, double y) { return x * h[0] + y * h[1]; }
 
-// Hessian accumulators: upper triangle, row-major packed, k(i,j) for i<=j:
-//   row0: 0..5   row1: 6..10   row2: 11..14   row3: 15,16,17   row4: 18,19   row5: 20      (+7 in acc[])
-//
-// One (point, voxel) pair: computePointDerivatives (NDTM:448-482) + updateDerivatives (NDTM:485-520).
-// J = [I | c3 c4 c5] with c3 = (0,J0,J1), c4 = (J2,J3,J4), c5 = (J5,J6,J7); structural zeros of the angle
-// tables (j_ang_f/g/h and h_ang_c/e/f have no z component) are exploited.
+// Per-lane accumulators of a derivative pass (NACC doubles).  With M = w (Sigma^-1 - d2 q q^T), q = Sigma^-1 x',
+// w = d1 d2 exp(-d2 x'^T q / 2) and J = [I | C(x)] (computePointDerivatives, NDTM:448-482), the sums of
+// updateDerivatives (NDTM:485-520) are
+//   gradient = sum w J^T q,   Hessian = sum J^T M J + [second-derivative term  w q . H_E(x)]
+// and both C(x) and H_E(x) are LINEAR in the source point x, so the gradient's rotational part and the whole
+// second-derivative term are contractions of P = sum w q x^T with the angle tables.  A pair therefore only
+// accumulates
+//   [0] score  [1..3] Q = sum w q  [4..12] P (3x3, row r = q component)  [13..18] H00 = sum M (xx,xy,xz,yy,yz,zz)
+//   [19..27] H01 = sum M C (3x3)  [28..33] H11c = sum C^T M C (33,34,35,44,45,55)  [34] pair count
+// (~150 FP64 operations per pair instead of ~250, and no angle-table reads for the second-derivative term);
+// acc_finish() contracts P with the tables once per pass and emits the ACC_N-vector the controller consumes.
 __device__ __forceinline__ void ndt_pair(const float px, const float py, const float pz, const float *__restrict__ T,
                                          const AngTab &ang, const double *__restrict__ g, double d1, double d2, bool hess,
                                          double *acc) {
@@ -231,7 +379,7 @@ __device__ __forceinline__ void ndt_pair(const float px, const float py, const f
     transform_f32(T, px, py, pz, tx, ty, tz);
     const double2 *g2 = reinterpret_cast<const double2 *>(g);      // 80-byte record, five 16-byte loads
     const double2 a0 = __ldg(g2 + 0), a1 = __ldg(g2 + 1), a2 = __ldg(g2 + 2), a3 = __ldg(g2 + 3), a4 = __ldg(g2 + 4);
-    acc[28] += 1.0;
+    acc[34] += 1.0;
     const double xq = (double)tx - a0.x, yq = (double)ty - a0.y, zq = (double)tz - a1.x;
     const double ixx = a1.y, ixy = a2.x, ixz = a2.y, iyy = a3.x, iyz = a3.y, izz = a4.x;
     const double q0 = ixx * xq + ixy * yq + ixz * zq;
@@ -245,61 +393,68 @@ __device__ __forceinline__ void ndt_pair(const float px, const float py, const f
     const double w = e * d1;
     acc[0] += sinc;
     const double x = (double)px, y = (double)py, z = (double)pz;
-    double J[8];
-    J[0] = dot3v(ang.j[0], x, y, z); J[1] = dot3v(ang.j[1], x, y, z);
-    J[2] = dot3v(ang.j[2], x, y, z); J[3] = dot3v(ang.j[3], x, y, z); J[4] = dot3v(ang.j[4], x, y, z);
-    J[5] = dot2v(ang.j[5], x, y);    J[6] = dot2v(ang.j[6], x, y);    J[7] = dot2v(ang.j[7], x, y);
-    // a = J^T q ; gradient += w a
-    double a[6];
-    a[0] = q0; a[1] = q1; a[2] = q2;
-    a[3] = q1 * J[0] + q2 * J[1];
-    a[4] = q0 * J[2] + q1 * J[3] + q2 * J[4];
-    a[5] = q0 * J[5] + q1 * J[6] + q2 * J[7];
-#pragma unroll
-    for (int i = 0; i < 6; ++i) acc[1 + i] += w * a[i];
+    const double wq0 = w * q0, wq1 = w * q1, wq2 = w * q2;
+    acc[1] += wq0; acc[2] += wq1; acc[3] += wq2;
+    acc[4] += wq0 * x; acc[5] += wq0 * y; acc[6] += wq0 * z;
+    acc[7] += wq1 * x; acc[8] += wq1 * y; acc[9] += wq1 * z;
+    acc[10] += wq2 * x; acc[11] += wq2 * y; acc[12] += wq2 * z;
     if (!hess) return;
-    double *Hh = &acc[7];
-    {   // -d2 w (J^T q)(J^T q)^T
-        const double wd = -d2 * w;
-        int k = 0;
+    // M = w Sigma^-1 - d2 (w q) q^T
+    const double t0 = -d2 * wq0, t1 = -d2 * wq1, t2 = -d2 * wq2;
+    const double mxx = t0 * q0 + w * ixx, mxy = t0 * q1 + w * ixy, mxz = t0 * q2 + w * ixz;
+    const double myy = t1 * q1 + w * iyy, myz = t1 * q2 + w * iyz, mzz = t2 * q2 + w * izz;
+    acc[13] += mxx; acc[14] += mxy; acc[15] += mxz; acc[16] += myy; acc[17] += myz; acc[18] += mzz;
+    // C = [c3 c4 c5], c3 = (0,J0,J1), c4 = (J2,J3,J4), c5 = (J5,J6,J7)  (j_ang_f/g/h have no z component)
+    const double J0 = dot3v(ang.j[0], x, y, z), J1 = dot3v(ang.j[1], x, y, z);
+    const double J2 = dot3v(ang.j[2], x, y, z), J3 = dot3v(ang.j[3], x, y, z), J4 = dot3v(ang.j[4], x, y, z);
+    const double J5 = dot2v(ang.j[5], x, y), J6 = dot2v(ang.j[6], x, y), J7 = dot2v(ang.j[7], x, y);
+    // M C
+    const double m30 = mxy * J0 + mxz * J1, m31 = myy * J0 + myz * J1, m32 = myz * J0 + mzz * J1;
+    const double m40 = mxx * J2 + mxy * J3 + mxz * J4, m41 = mxy * J2 + myy * J3 + myz * J4, m42 = mxz * J2 + myz * J3 + mzz * J4;
+    const double m50 = mxx * J5 + mxy * J6 + mxz * J7, m51 = mxy * J5 + myy * J6 + myz * J7, m52 = mxz * J5 + myz * J6 + mzz * J7;
+    acc[19] += m30; acc[20] += m40; acc[21] += m50;
+    acc[22] += m31; acc[23] += m41; acc[24] += m51;
+    acc[25] += m32; acc[26] += m42; acc[27] += m52;
+    // C^T M C
+    acc[28] += J0 * m31 + J1 * m32;
+    acc[29] += J0 * m41 + J1 * m42;
+    acc[30] += J0 * m51 + J1 * m52;
+    acc[31] += J2 * m40 + J3 * m41 + J4 * m42;
+    acc[32] += J2 * m50 + J3 * m51 + J4 * m52;
+    acc[33] += J5 * m50 + J6 * m51 + J7 * m52;
+}
+
+// Contract the reduced NACC sums with the angle tables of the finished pass -> ACC_N layout of the controller:
+// [0] score, [1..6] gradient, [7..27] Hessian upper triangle row-major, [28] pairs.  Lane o (< ACC_N) of one
+// warp computes output o = t[base] + sum_k P[row_k] . table[vec_k]; AngTab is 23 consecutive 3-vectors
+// (j_ang_a..h then h_ang_a2..f3).
+__constant__ signed char ACCF_BASE[ACC_N] = {0, 1, 2, 3, -1, -1, -1,
+                                             13, 14, 15, 19, 20, 21, 16, 17, 22, 23, 24, 18, 25, 26, 27, 28, 29, 30, 31, 32, 33, 34};
+__constant__ signed char ACCF_ROW[ACC_N][3] = {
+    {-1, -1, -1}, {-1, -1, -1}, {-1, -1, -1}, {-1, -1, -1}, {1, 2, -1}, {0, 1, 2}, {0, 1, 2},
+    {-1, -1, -1}, {-1, -1, -1}, {-1, -1, -1}, {-1, -1, -1}, {-1, -1, -1}, {-1, -1, -1}, {-1, -1, -1}, {-1, -1, -1},
+    {-1, -1, -1}, {-1, -1, -1}, {-1, -1, -1}, {-1, -1, -1}, {-1, -1, -1}, {-1, -1, -1}, {-1, -1, -1},
+    {1, 2, -1}, {1, 2, -1}, {1, 2, -1}, {0, 1, 2}, {0, 1, 2}, {0, 1, 2}, {-1, -1, -1}};
+__constant__ signed char ACCF_VEC[ACC_N][3] = {
+    {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 1, 0}, {2, 3, 4}, {5, 6, 7},
+    {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0},
+    {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0},
+    {8, 9, 0}, {10, 11, 0}, {12, 13, 0}, {14, 15, 16}, {17, 18, 19}, {20, 21, 22}, {0, 0, 0}};
+
+__device__ __forceinline__ double acc_finish(const double *t /*NACC*/, const AngTab &ang, int o) {
+    const double *tab = &ang.j[0][0];
+    const int base = ACCF_BASE[o];
+    double v = (base >= 0) ? t[base] : 0.0;
 #pragma unroll
-        for (int i = 0; i < 6; ++i) {
-            const double t = wd * a[i];
-#pragma unroll
-            for (int j = i; j < 6; ++j) Hh[k++] += t * a[j];
+    for (int k = 0; k < 3; ++k) {
+        const int r = ACCF_ROW[o][k];
+        if (r >= 0) {
+            const double *P = t + 4 + 3 * r;
+            const double *h = tab + 3 * ACCF_VEC[o][k];
+            v += P[0] * h[0] + P[1] * h[1] + P[2] * h[2];
         }
     }
-    {   // w q . H_E(i,j): a=(0,x.a2,x.a3) b=(0,x.b2,x.b3) c=(0,x.c2,x.c3) d=(x.d1,x.d2,x.d3) e=(...) f=(...)
-        const double wq0 = w * q0, wq1 = w * q1, wq2 = w * q2;
-        Hh[15] += wq1 * dot3v(ang.h[0], x, y, z) + wq2 * dot3v(ang.h[1], x, y, z);
-        Hh[16] += wq1 * dot3v(ang.h[2], x, y, z) + wq2 * dot3v(ang.h[3], x, y, z);
-        Hh[17] += wq1 * dot2v(ang.h[4], x, y) + wq2 * dot2v(ang.h[5], x, y);
-        Hh[18] += wq0 * dot3v(ang.h[6], x, y, z) + wq1 * dot3v(ang.h[7], x, y, z) + wq2 * dot3v(ang.h[8], x, y, z);
-        Hh[19] += wq0 * dot2v(ang.h[9], x, y) + wq1 * dot2v(ang.h[10], x, y) + wq2 * dot2v(ang.h[11], x, y);
-        Hh[20] += wq0 * dot2v(ang.h[12], x, y) + wq1 * dot2v(ang.h[13], x, y) + wq2 * dot2v(ang.h[14], x, y);
-    }
-    {   // w J^T Sigma^-1 J
-        const double wxx = w * ixx, wxy = w * ixy, wxz = w * ixz, wyy = w * iyy, wyz = w * iyz, wzz = w * izz;
-        double m3[3], m4[3], m5[3];
-        m3[0] = wxy * J[0] + wxz * J[1];
-        m3[1] = wyy * J[0] + wyz * J[1];
-        m3[2] = wyz * J[0] + wzz * J[1];
-        m4[0] = wxx * J[2] + wxy * J[3] + wxz * J[4];
-        m4[1] = wxy * J[2] + wyy * J[3] + wyz * J[4];
-        m4[2] = wxz * J[2] + wyz * J[3] + wzz * J[4];
-        m5[0] = wxx * J[5] + wxy * J[6] + wxz * J[7];
-        m5[1] = wxy * J[5] + wyy * J[6] + wyz * J[7];
-        m5[2] = wxz * J[5] + wyz * J[6] + wzz * J[7];
-        Hh[0] += wxx; Hh[1] += wxy; Hh[2] += wxz; Hh[3] += m3[0]; Hh[4] += m4[0]; Hh[5] += m5[0];
-        Hh[6] += wyy; Hh[7] += wyz; Hh[8] += m3[1]; Hh[9] += m4[1]; Hh[10] += m5[1];
-        Hh[11] += wzz; Hh[12] += m3[2]; Hh[13] += m4[2]; Hh[14] += m5[2];
-        Hh[15] += J[0] * m3[1] + J[1] * m3[2];
-        Hh[16] += J[0] * m4[1] + J[1] * m4[2];
-        Hh[17] += J[0] * m5[1] + J[1] * m5[2];
-        Hh[18] += J[2] * m4[0] + J[3] * m4[1] + J[4] * m4[2];
-        Hh[19] += J[2] * m5[0] + J[3] * m5[1] + J[4] * m5[2];
-        Hh[20] += J[5] * m5[0] + J[6] * m5[1] + J[7] * m5[2];
-    }
+    return v;
 }
 
 // warp 0 completes a pass request: the twelve sin/cos evaluations run on twelve lanes
@@ -359,24 +514,141 @@ __global__ void __launch_bounds__(NDT_THREADS, NDT_MIN_CTAS) ndt_match_kernel(Gr
         // =========================== search warps (producers) ===========================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(NDT_REG_SEARCH));
         const int sw = warp - NDT_NCW;
-        uint2 *ring = S.ring[sw];
+        float4 *ring = S.ring[sw];
         uint32_t pass_id = 0;
         uint32_t my_tail = 0;                       // entries produced so far (warp-uniform)
+        uint32_t hd_seen = 0;                       // last consumer position read (warp-uniform)
+#ifdef NDT_TIMING
+        unsigned long long tm[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        const long long t_life = clock64();
+#endif
+        // wait until the ring has room for `need` more entries
+        auto ring_room = [&](uint32_t need) {
+            if (my_tail - hd_seen > RING - need) {
+                const long long tw = TM_NOW();
+                uint32_t hd = 0;
+                if (lane == 0) {
+                    hd = ld_vol(&S.head[sw]);
+                    while (my_tail - hd > RING - need) { __nanosleep(64); hd = ld_vol(&S.head[sw]); }
+                }
+                hd_seen = __shfl_sync(0xffffffffu, hd, 0);
+                TM_ADD(1, tw);
+            }
+        };
+        // Software pipeline over rounds of 32 points: while round r is searched, the neighbour-list header
+        // of round r+1 and the source points of round r+2 are in flight.
+        //   prepare(b, pt, buf): transform the points of the round starting at b, park (point, transformed
+        //   point) in stage buffer `buf`, and issue the header load -> (off, cnt); cnt = IRREGULAR marks a
+        //   lane that needs the dense-window fallback (4-cell window or centre cell outside the grid).
+        constexpr uint32_t IRREGULAR = 0xffffffffu;
+        const uint32_t b0 = first + (crank * NDT_NSW + sw) * 32u;
+        auto load_pt = [&](uint32_t b) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (b < last && b + lane < last) v = __ldg(&A.src[b + lane]);
+            return v;
+        };
         while (true) {
             ++pass_id;
             const float *T = S.ctl.T;
-            for (uint32_t base = first + (crank * NDT_NSW + sw) * 32u; base < last; base += stride) {
-                const uint32_t i = base + lane;
-                int ex0 = -1, ex1 = -1, ex2 = -1;
-                size_t wbase = 0;
+            const long long t_pass = TM_NOW();
+            if (sw == 0) TM_EV(0);
+            auto prepare = [&](uint32_t b, const float4 pt, int buf, uint32_t &off, uint32_t &cnt) {
+                off = 0u; cnt = 0u;
                 float tx = 0.f, ty = 0.f, tz = 0.f;
-                if (i < last && G.ok) {
-                    const float4 pt = __ldg(&A.src[i]);
+                if (b < last && b + lane < last && G.ok) {
                     transform_f32(T, pt.x, pt.y, pt.z, tx, ty, tz);
                     if (finite3(tx, ty, tz)) {
                         // every cell that can hold a centroid within the radius (centroids may sit up to
                         // G.margin outside their own cell; the slack also covers the rounding of this arithmetic)
                         const float q[3] = {tx, ty, tz};
+                        int lo[3];
+                        bool regular = true;
+#pragma unroll
+                        for (int a = 0; a < 3; ++a) {
+                            const float mg = G.margin + 1e-6f * fabsf(q[a]);
+                            lo[a] = (int)floorf((q[a] - G.res - mg) * G.inv_leaf) - G.min_b[a];
+                            const int hi = (int)floorf((q[a] + G.res + mg) * G.inv_leaf) - G.min_b[a];
+                            // regular: the window is exactly the 3 cells around an in-grid centre cell
+                            regular = regular && (hi - lo[a] == 2) && (lo[a] + 1 >= 0) && (lo[a] + 1 < G.div_b[a]);
+                        }
+                        if (regular) {
+                            const uint2 hd = __ldg(&G.nbr_head[(size_t)(lo[0] + 1) + (size_t)(lo[1] + 1) * G.mul[1] +
+                                                                (size_t)(lo[2] + 1) * G.mul[2]]);
+                            off = hd.x; cnt = hd.y;
+                        } else {
+                            cnt = IRREGULAR;
+                        }
+                    }
+                }
+                S.stage[sw][buf * 64 + lane] = pt;
+                S.stage[sw][buf * 64 + 32 + lane] = make_float4(tx, ty, tz, 0.f);
+            };
+            int buf = 0;
+            uint32_t off, cnt, off_n = 0, cnt_n = 0;
+            prepare(b0, load_pt(b0), 0, off, cnt);
+            float4 pt_nn = load_pt(b0 + stride);              // points of the round after
+            for (uint32_t base = b0; base < last; base += stride, buf ^= 1) {
+                // kick off the next two rounds, then search this one
+                __syncwarp();
+                prepare(base + stride, pt_nn, buf ^ 1, off_n, cnt_n);
+                pt_nn = load_pt(base + 2u * stride);
+                const float4 *stage = &S.stage[sw][buf * 64];
+                const bool irregular = (cnt == IRREGULAR);
+                if (irregular) cnt = 0u;
+                // ---- regular lanes: the warp walks the concatenation of its 32 neighbour lists, 32 entries
+                // at a time (coalesced runs of 16-byte entries); the owner of entry e is found by a binary
+                // search over the inclusive scan of the list lengths
+                uint32_t incl = cnt;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+                const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+                const uint32_t excl = incl - cnt;
+                auto fetch = [&](uint32_t e, int &o) {
+                    o = 0;
+#pragma unroll
+                    for (int sft = 16; sft > 0; sft >>= 1) {
+                        const uint32_t v = __shfl_sync(0xffffffffu, incl, (o + sft - 1) & 31);
+                        if (v <= e) o += sft;
+                    }
+                    o &= 31;
+                    const uint32_t o_excl = __shfl_sync(0xffffffffu, excl, o);
+                    const uint32_t o_off = __shfl_sync(0xffffffffu, off, o);
+                    float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (e < total) c = __ldg(&G.nbr_list[o_off + (e - o_excl)]);
+                    return c;
+                };
+                int o_nx = 0;
+                float4 c_nx = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (total) c_nx = fetch(lane, o_nx);
+                for (uint32_t e0 = 0; e0 < total; e0 += 32u) {
+                    const float4 c = c_nx;
+                    const int o = o_nx;
+                    if (e0 + 32u < total) c_nx = fetch(e0 + 32u + lane, o_nx);      // next batch in flight
+                    ring_room(32u);
+                    const float4 q = stage[32 + o];
+                    // flann::L2_Simple<float>: (dx*dx + dy*dy) + dz*dz, accepted when < (float)(r*r)
+                    const float dx = __fsub_rn(q.x, c.x), dy = __fsub_rn(q.y, c.y), dz = __fsub_rn(q.z, c.z);
+                    const float d2f = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+                    const bool hit = (e0 + lane < total) && (d2f < G.r2);
+                    const uint32_t b = __ballot_sync(0xffffffffu, hit);
+                    if (hit) {
+                        const float4 sp = stage[o];
+                        ring[(my_tail + __popc(b & lt)) & (RING - 1u)] = make_float4(sp.x, sp.y, sp.z, c.w);
+                    }
+                    if (b) {
+                        my_tail += __popc(b);
+                        __syncwarp();
+                        if (lane == 0) publish_tail(&S.tail[sw], my_tail);
+                    }
+                }
+                // ---- irregular lanes: dense window walk over the cell grid, one row of <= 4 cells at a time
+                if (__any_sync(0xffffffffu, irregular)) {
+                    int ex0 = -1, ex1 = -1, ex2 = -1;
+                    size_t wbase = 0;
+                    const float4 pt = stage[lane];
+                    const float4 tq = stage[32 + lane];
+                    if (irregular) {
+                        const float q[3] = {tq.x, tq.y, tq.z};
                         int lo[3], ex[3];
                         bool empty = false;
 #pragma unroll
@@ -393,76 +665,66 @@ __global__ void __launch_bounds__(NDT_THREADS, NDT_MIN_CTAS) ndt_match_kernel(Gr
                             wbase = (size_t)lo[0] + (size_t)lo[1] * G.mul[1] + (size_t)lo[2] * G.mul[2];
                         }
                     }
-                }
-                const int nplanes = __reduce_max_sync(0xffffffffu, ex2 + 1);
-                const bool wide = __any_sync(0xffffffffu, (ex0 > 2) || (ex1 > 2));
-                for (int plane = 0; plane < nplanes; ++plane) {
-                    // a plane appends at most 32 x 16 entries: wait until the consumer has made room
-                    if (lane == 0) {
-                        uint32_t hd = ld_vol(&S.head[sw]);
-                        while (my_tail - hd > RING - 512u) { __nanosleep(64); hd = ld_vol(&S.head[sw]); }
-                    }
-                    __syncwarp();
-                    const bool act = plane <= ex2;
-                    const float4 *wp = G.cells + wbase + (size_t)plane * G.mul[2];
-                    uint32_t qn = my_tail;
-                    if (!wide) {
-                        float4 c[9];
-#pragma unroll
-                        for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-                            for (int dx = 0; dx < 3; ++dx) {
-                                c[dy * 3 + dx] = make_float4(0.f, 0.f, 0.f, 0.f);
-                                if (act && dx <= ex0 && dy <= ex1) c[dy * 3 + dx] = __ldg(wp + dx + (size_t)dy * G.mul[1]);
-                            }
-#pragma unroll
-                        for (int k = 0; k < 9; ++k) {
-                            // flann::L2_Simple<float>: (dx*dx + dy*dy) + dz*dz, accepted when < (float)(r*r)
-                            const float dx = __fsub_rn(tx, c[k].x), dy = __fsub_rn(ty, c[k].y), dz = __fsub_rn(tz, c[k].z);
-                            const float d2f = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-                            const int code = __float_as_int(c[k].w);
-                            const bool hit = (code > 0) && (d2f < G.r2);
-                            const uint32_t b = __ballot_sync(0xffffffffu, hit);
-                            if (hit) ring[(qn + __popc(b & lt)) & (RING - 1u)] = make_uint2(i, (uint32_t)(code - 1));
-                            qn += __popc(b);
-                        }
-                    } else {
-                        // some lane's window is 4 cells wide (query within `margin` of a cell face): rare
-                        for (int dy = 0; dy < 4; ++dy)
-                            for (int dx = 0; dx < 4; ++dx) {
+                    const int nplanes = __reduce_max_sync(0xffffffffu, ex2 + 1);
+                    for (int plane = 0; plane < nplanes; ++plane) {
+                        const int nrows = __reduce_max_sync(0xffffffffu, (plane <= ex2) ? ex1 + 1 : 0);
+                        for (int row = 0; row < nrows; ++row) {
+                            ring_room(128u);
+                            const bool act = (plane <= ex2) && (row <= ex1);
+                            const float4 *wp = G.cells + wbase + (size_t)plane * G.mul[2] + (size_t)row * G.mul[1];
+                            uint32_t qn = my_tail;
+                            for (int dxi = 0; dxi < 4; ++dxi) {
                                 float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
-                                if (act && dx <= ex0 && dy <= ex1) c = __ldg(wp + dx + (size_t)dy * G.mul[1]);
-                                const float ddx = __fsub_rn(tx, c.x), ddy = __fsub_rn(ty, c.y), ddz = __fsub_rn(tz, c.z);
+                                if (act && dxi <= ex0) c = __ldg(wp + dxi);
+                                const float ddx = __fsub_rn(tq.x, c.x), ddy = __fsub_rn(tq.y, c.y), ddz = __fsub_rn(tq.z, c.z);
                                 const float d2f = __fadd_rn(__fadd_rn(__fmul_rn(ddx, ddx), __fmul_rn(ddy, ddy)), __fmul_rn(ddz, ddz));
                                 const int code = __float_as_int(c.w);
                                 const bool hit = (code > 0) && (d2f < G.r2);
                                 const uint32_t b = __ballot_sync(0xffffffffu, hit);
-                                if (hit) ring[(qn + __popc(b & lt)) & (RING - 1u)] = make_uint2(i, (uint32_t)(code - 1));
+                                if (hit) ring[(qn + __popc(b & lt)) & (RING - 1u)] = make_float4(pt.x, pt.y, pt.z, __int_as_float(code - 1));
                                 qn += __popc(b);
                             }
-                    }
-                    __syncwarp();
-                    if (qn != my_tail) {
-                        my_tail = qn;
-                        if (lane == 0) { __threadfence_block(); st_vol(&S.tail[sw], my_tail); }
+                            __syncwarp();
+                            if (qn != my_tail) {
+                                my_tail = qn;
+                                if (lane == 0) publish_tail(&S.tail[sw], my_tail);
+                            }
+                        }
                     }
                 }
+                off = off_n; cnt = cnt_n;
             }
             // publish the end of this warp's stream for this pass
             __syncwarp();
             if (lane == 0) { __threadfence_block(); st_vol(&S.tail[sw], my_tail); __threadfence_block(); st_vol(&S.finished[sw], pass_id); }
+            TM_ADD(0, t_pass);
+            if (sw == 0) TM_EV(1);
             cta_barrier();                          // (1) all pairs of the pass consumed, partials written
+            TM_ADD(2, t_pass);
+            if (sw == 0) TM_EV(2);
             if (C > 1) cluster.sync();
             cta_barrier();                          // (2) totals ready
+            if (sw == 0) TM_EV(3);
             cta_barrier();                          // (3) controller done
+            if (sw == 0) TM_EV(4);
+            TM_ADD(3, t_pass);
             if (!ld_vol(reinterpret_cast<const uint32_t *>(&S.go))) break;
         }
         if (C > 1) cluster.sync();
+#ifdef NDT_TIMING
+        if (sw == 0 && lane == 0 && A.timing) {
+            tm[4] = (unsigned long long)(clock64() - t_life);
+            for (int k = 0; k < 5; ++k) atomicAdd(&A.timing[k], tm[k]);
+        }
+#endif
     } else {
     // =========================== compute warps (consumers) ===========================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(NDT_REG_COMPUTE));
     int parity = 0;
     uint32_t pass_id = 0;
+#ifdef NDT_TIMING
+    unsigned long long tm[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
     uint32_t cpos[NDT_PPC];                         // entries consumed per producer
 #pragma unroll
     for (int k = 0; k < NDT_PPC; ++k) cpos[k] = 0;
@@ -472,9 +734,10 @@ __global__ void __launch_bounds__(NDT_THREADS, NDT_MIN_CTAS) ndt_match_kernel(Gr
             const float *T = S.ctl.T;
             const bool hess = S.ctl.hess != 0;
             const AngTab &ang = S.ctl.ang;
-            double acc[ACC_N];
+            double acc[NACC];
 #pragma unroll
-            for (int i = 0; i < ACC_N; ++i) acc[i] = 0.0;
+            for (int i = 0; i < NACC; ++i) acc[i] = 0.0;
+            if (warp == 0) TM_EV(8);
             uint32_t done_mask = 0;                         // bit k: producer k exhausted for this pass
             int turn = 0;
             while (done_mask != (1u << NDT_PPC) - 1u) {
@@ -488,24 +751,39 @@ __global__ void __launch_bounds__(NDT_THREADS, NDT_MIN_CTAS) ndt_match_kernel(Gr
                 for (int kk = 0; kk < NDT_PPC; ++kk) if (kk == k) pos = cpos[kk];
                 // wait for a full chunk of 32 pairs, or for the producer to finish the pass
                 uint32_t n = 0;
+                uint32_t avail_all = 0;
+                const long long tw = TM_NOW();
                 if (lane == 0) {
                     while (true) {
                         const uint32_t fin = ld_vol(&S.finished[sw]);
                         __threadfence_block();
                         const uint32_t avail = ld_vol(&S.tail[sw]) - pos;
+                        avail_all = avail;
                         if (avail >= 32u) { n = 32u; break; }
                         if (fin == pass_id) { n = avail | 0x80000000u; break; }     // final (possibly empty) chunk
                         __nanosleep(32);
                     }
                 }
                 n = __shfl_sync(0xffffffffu, n, 0);
+                TM_ADD(0, tw);
+                const long long tb = TM_NOW();
                 const bool final_chunk = (n & 0x80000000u) != 0;
                 n &= 0x7fffffffu;
                 __threadfence_block();
+#if NDT_PF
+                {   // pull the records of this ring's NEXT chunk towards L1 while this chunk is computed
+                    avail_all = __shfl_sync(0xffffffffu, avail_all, 0);
+                    if (avail_all > 32u + (uint32_t)lane) {
+                        const float lw = S.ring[sw][(pos + 32u + lane) & (RING - 1u)].w;
+                        const char *gp = reinterpret_cast<const char *>(G.gauss + (size_t)__float_as_uint(lw) * 10);
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(gp));
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(gp + 72));
+                    }
+                }
+#endif
                 if ((uint32_t)lane < n) {
-                    const uint2 e = S.ring[sw][(pos + lane) & (RING - 1u)];
-                    const float4 sp = __ldg(&A.src[e.x]);
-                    ndt_pair(sp.x, sp.y, sp.z, T, ang, G.gauss + (size_t)e.y * 10, K.d1, K.d2, hess, acc);
+                    const float4 e = S.ring[sw][(pos + lane) & (RING - 1u)];
+                    ndt_pair(e.x, e.y, e.z, T, ang, G.gauss + (size_t)__float_as_uint(e.w) * 10, K.d1, K.d2, hess, acc);
                 }
                 pos += n;
 #pragma unroll
@@ -513,19 +791,29 @@ __global__ void __launch_bounds__(NDT_THREADS, NDT_MIN_CTAS) ndt_match_kernel(Gr
                 __syncwarp();
                 if (lane == 0 && n) st_vol(&S.head[sw], pos);
                 if (final_chunk) done_mask |= (1u << k);
+                TM_ADD(1, tb);
+#ifdef NDT_TIMING
+                if (lane == 0) { tm[5] += 1; tm[6] += n; }
+#endif
             }
+            if (warp == 0) TM_EV(9);
             // warp butterfly (fixed order) -> one partial per compute warp
 #pragma unroll
-            for (int i = 0; i < ACC_N; ++i) {
+            for (int i = 0; i < NACC; ++i) {
                 double vsum = acc[i];
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) vsum += __shfl_xor_sync(0xffffffffu, vsum, o);
                 if (lane == 0) S.warp_part[warp][i] = vsum;
             }
         }
+        const long long t_b1 = TM_NOW();
+        if (warp == 0) TM_EV(10);
         cta_barrier();                              // (1)
+        if (warp == 0) TM_EV(11);
+        TM_ADD(2, t_b1);
+        const long long t_red = TM_NOW();
         // ---------------- deterministic reduction: CTA -> cluster (fixed order) ----------------
-        if (tid < ACC_N) {
+        if (tid < NACC) {
             double s = 0.0;
 #pragma unroll
             for (int w = 0; w < NDT_NCW; ++w) s += S.warp_part[w][tid];
@@ -533,26 +821,39 @@ __global__ void __launch_bounds__(NDT_THREADS, NDT_MIN_CTAS) ndt_match_kernel(Gr
         }
         if (C > 1) {
             cluster.sync();
-            if (tid < ACC_N) {
+            if (tid < NACC) {
                 double tot = 0.0;
                 for (unsigned r = 0; r < C; ++r) tot += *cluster.map_shared_rank(&S.cta_part[parity][tid], r);
-                S.total[tid] = tot;
+                S.raw_total[tid] = tot;
             }
         } else {
-            if (tid < ACC_N) S.total[tid] = S.cta_part[parity][tid];
+            if (tid < NACC) S.raw_total[tid] = S.cta_part[parity][tid];
         }
         cta_barrier();                              // (2)
+        if (warp == 0) TM_EV(12);
+        TM_ADD(3, t_red);
+        const long long t_ctl = TM_NOW();
         // ---------------- controller: Newton step + More-Thuente state machine (warp 0) ----------------
         if (warp == 0) {
+            if (lane < ACC_N) S.total[lane] = acc_finish(S.raw_total, S.ctl.ang, lane);
+            __syncwarp();
             int go = 0;
             if (lane == 0) { go = A.deriv_only ? 0 : ctl_step(S.ctl, K, S.total); S.go = go; }
             go = __shfl_sync(0xffffffffu, go, 0);
             if (go) finish_request_warp0(S, lane);
         }
         cta_barrier();                              // (3)
+        if (warp == 0) TM_EV(13);
+        TM_ADD(4, t_ctl);
         if (!S.go) break;
         parity ^= 1;
     }
+#ifdef NDT_TIMING
+    if (warp == 0 && lane == 0 && A.timing) {
+        for (int k = 0; k < 7; ++k) atomicAdd(&A.timing[8 + k], tm[k]);
+        atomicAdd(&A.timing[15], 1ull);
+    }
+#endif
     if (C > 1) cluster.sync();    // peers may still be reading this CTA's partials
     if (tid == 0 && crank == 0) {
         if (A.deriv_only) {
@@ -731,6 +1032,7 @@ extern "C" void b2ndt_destroy(b2ndt *h) {
     TargetDev &t = h->tgt;
     t.pts_in.release(); t.pts_sorted.release(); t.leaf_idx.release(); t.leaf_n.release(); t.leaf_start.release();
     t.centroid4.release(); t.gauss.release(); t.sums.release(); t.icov9.release(); t.cells.release(); t.counters.release();
+    t.nbr_head.release(); t.nbr_list.release(); t.nbr_tiles.release();
     h->d_src.release(); h->d_guess.release(); h->d_pose.release(); h->d_res.release(); h->d_off.release();
     h->d_p6.release(); h->d_acc.release(); h->d_fit_sum.release(); h->d_fit_cnt.release();
     h->h_stage.release(); h->h_small.release(); h->h_res.release();
@@ -790,8 +1092,12 @@ static int build_target(b2ndt *h, const float4 *d_pts, size_t n, int nbits_hint)
     if ((rc = t.icov9.reserve((size_t)(V + 1) * 72))) return rc;
     if ((rc = t.cells.reserve((size_t)t.L.ncells * 16 + 16))) return rc;
     if ((rc = t.counters.reserve(64))) return rc;
+    if ((rc = t.nbr_head.reserve((size_t)t.L.ncells * 8 + 16))) return rc;
+    B2_CUDA(cudaMemsetAsync(t.nbr_head.p, 0, (size_t)t.L.ncells * 8, h->st));
     B2_CUDA(cudaMemsetAsync(t.cells.p, 0, (size_t)t.L.ncells * 16, h->st));
     B2_CUDA(cudaMemsetAsync(t.counters.p, 0, 64, h->st));
+    LayoutArg LA;
+    for (int a = 0; a < 3; ++a) { LA.min_b[a] = t.L.min_b[a]; LA.div_b[a] = t.L.div_b[a]; LA.inv[a] = t.L.inv[a]; }
     if (V) {
         unsigned blocks = (V + 7) / 8;
         if (blocks > 148 * 32) blocks = 148 * 32;
@@ -800,18 +1106,29 @@ static int build_target(b2ndt *h, const float4 *d_pts, size_t n, int nbits_hint)
                                                     t.leaf_n.as<int32_t>(), t.leaf_start.as<uint32_t>(), t.centroid4.as<float4>(),
                                                     t.sums.as<double>());
         B2_LAUNCH_CHECK();
-        LayoutArg LA;
-        for (int a = 0; a < 3; ++a) { LA.min_b[a] = t.L.min_b[a]; LA.div_b[a] = t.L.div_b[a]; LA.inv[a] = t.L.inv[a]; }
         leaf_finish_kernel<<<(V + 127) / 128, 128, 0, h->st>>>(V, h->prm.min_pts, h->prm.eig_mult, LA, t.leaf_idx.as<int32_t>(),
                                                               t.leaf_n.as<int32_t>(), t.centroid4.as<float4>(), t.sums.as<double>(),
                                                               t.gauss.as<double>(), t.icov9.as<double>(), t.cells.as<float4>(),
-                                                              t.counters.as<uint32_t>());
+                                                              t.nbr_head.as<uint2>(), t.counters.as<uint32_t>());
         B2_LAUNCH_CHECK();
     }
     B2_CUDA(cudaMemcpyAsync(misc, t.counters.p, 8, cudaMemcpyDeviceToHost, h->st));
     B2_CUDA(cudaStreamSynchronize(h->st));
     t.n_tree = misc[0];
     memcpy(&t.max_disp, &misc[1], 4);
+    // neighbour lists (27 entries per searchable leaf at most), laid out in cell order
+    if ((rc = t.nbr_list.reserve(((size_t)t.n_tree * 27 + 1) * sizeof(float4)))) return rc;
+    if (t.n_tree) {
+        const uint32_t ntiles = (uint32_t)(((size_t)t.L.ncells + NBR_TILE - 1) / NBR_TILE);
+        if ((rc = t.nbr_tiles.reserve((size_t)ntiles * 4 + 16))) return rc;
+        nbr_tile_sum_kernel<<<ntiles, NBR_TPB, 0, h->st>>>(t.nbr_head.as<uint2>(), t.L.ncells, t.nbr_tiles.as<uint32_t>());
+        B2_LAUNCH_CHECK();
+        nbr_tile_scan_kernel<<<1, NBR_TPB, 0, h->st>>>(t.nbr_tiles.as<uint32_t>(), ntiles);
+        B2_LAUNCH_CHECK();
+        nbr_fill_kernel<<<ntiles, NBR_TPB, 0, h->st>>>(t.nbr_head.as<uint2>(), t.cells.as<float4>(), t.L.ncells,
+                                                       t.nbr_tiles.as<uint32_t>(), LA, t.nbr_list.as<float4>());
+        B2_LAUNCH_CHECK();
+    }
     return 0;
 }
 
@@ -883,6 +1200,8 @@ static GridView make_grid_view(const b2ndt *h) {
     const TargetDev &t = h->tgt;
     G.cells = t.cells.as<float4>();
     G.gauss = t.gauss.as<double>();
+    G.nbr_head = t.nbr_head.as<uint2>();
+    G.nbr_list = t.nbr_list.as<float4>();
     for (int a = 0; a < 3; ++a) { G.min_b[a] = t.L.min_b[a]; G.div_b[a] = t.L.div_b[a]; G.mul[a] = t.L.mul[a]; }
     G.res = h->prm.res;
     G.r2 = (float)((double)h->prm.res * (double)h->prm.res);
@@ -912,9 +1231,34 @@ static int launch_match(b2ndt *h, const MatchArgs &A, size_t B, int C) {
     cfg.attrs = at; cfg.numAttrs = 1;
     NdtConst K = h->K;
     MatchArgs Ac = A;
+#ifdef NDT_TIMING
+    static unsigned long long *d_tm = nullptr;
+    if (!d_tm) cudaMalloc(&d_tm, 96 * 8);
+    cudaMemsetAsync(d_tm, 0, 96 * 8, h->st);
+    Ac.timing = d_tm;
+#endif
     cudaError_t e = cudaLaunchKernelEx(&cfg, ndt_match_kernel, G, K, Ac);
     b2::count_launch();
     if (e != cudaSuccess) { set_error("ndt_match_kernel launch failed: %s", cudaGetErrorString(e)); return B2_ERR_CUDA; }
+#ifdef NDT_TIMING
+    {
+        unsigned long long t[96];
+        cudaStreamSynchronize(h->st);
+        cudaMemcpy(t, d_tm, sizeof(t), cudaMemcpyDeviceToHost);
+        const double n = (double)t[15] > 0 ? (double)t[15] : 1.0;
+        fprintf(stderr, "[ndt timing] ctas %.0f | search0: pass %.0f ring-wait %.0f to-bar1 %.0f to-bar3 %.0f life %.0f | compute0: wait %.0f busy %.0f bar1 %.0f reduce %.0f ctl %.0f chunks %.0f pairs %.0f (cycles per CTA)\n",
+                n, t[0] / n, t[1] / n, t[2] / n, t[3] / n, t[4] / n, t[8] / n, t[9] / n, t[10] / n, t[11] / n, t[12] / n, t[13] / n, t[14] / n);
+        // event trace of CTA 0, first 4 passes, relative to the search warp's first pass start
+        const unsigned long long t0 = t[32];
+        for (int ps = 0; ps < 4; ++ps) {
+            const unsigned long long *e = t + 32 + ps * 16;
+            if (!e[0]) break;
+            fprintf(stderr, "[ndt trace] pass %d search: start %lld finish %lld b1 %lld b2 %lld b3 %lld | compute: start %lld drained %lld bfly %lld b1 %lld b2 %lld b3 %lld\n",
+                    ps + 1, (long long)(e[0] - t0), (long long)(e[1] - t0), (long long)(e[2] - t0), (long long)(e[3] - t0), (long long)(e[4] - t0),
+                    (long long)(e[8] - t0), (long long)(e[9] - t0), (long long)(e[10] - t0), (long long)(e[11] - t0), (long long)(e[12] - t0), (long long)(e[13] - t0));
+        }
+    }
+#endif
     return 0;
 }
 
