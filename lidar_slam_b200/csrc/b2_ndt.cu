@@ -93,7 +93,26 @@ __global__ void __launch_bounds__(256) leaf_stats_kernel(const float4 *__restric
 
 // One thread per voxel: mean, single-pass covariance, eigen inflation, inverse (leaf_finish), the
 // 80-byte gather record, and the dense-grid entry.
-struct LayoutArg { int32_t min_b[3], div_b[3]; float inv[3]; };
+struct LayoutArg { int32_t min_b[3], div_b[3]; float inv[3]; float res; };
+
+// Can the leaf with float centroid (cx,cy,cz) be within the search radius of ANY query that falls into
+// cell (kx,ky,kz)?  Distance from the centroid to the cell's box, against the radius plus a generous slack
+// (covers the float rounding of the query's cell assignment and of the distance test).  Prunes ~1/4 of
+// the 3x3x3 window (corner and edge cells); used identically by the count and the fill pass.
+__device__ __forceinline__ bool nbr_keep(float cx, float cy, float cz, int kx, int ky, int kz, const LayoutArg &LA) {
+    const double c[3] = {(double)cx, (double)cy, (double)cz};
+    const int k[3] = {kx, ky, kz};
+    double d2 = 0.0;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const double lo = (double)(k[a] + LA.min_b[a]) / (double)LA.inv[a];
+        const double hi = (double)(k[a] + LA.min_b[a] + 1) / (double)LA.inv[a];
+        const double d = fmax(fmax(lo - c[a], c[a] - hi), 0.0);
+        d2 += d * d;
+    }
+    const double lim = (double)LA.res * 1.002 + 1e-5 * (fabs(c[0]) + fabs(c[1]) + fabs(c[2]));
+    return d2 < lim * lim;
+}
 
 __global__ void __launch_bounds__(128) leaf_finish_kernel(uint32_t V, int min_pts, double eig_mult, LayoutArg LA,
                                                           const int32_t *__restrict__ leaf_idx, const int32_t *__restrict__ leaf_n,
@@ -131,12 +150,14 @@ __global__ void __launch_bounds__(128) leaf_finish_kernel(uint32_t V, int min_pt
         const int iz = idx / (LA.div_b[0] * LA.div_b[1]);
         const int iy = (idx - iz * LA.div_b[0] * LA.div_b[1]) / LA.div_b[0];
         const int ix = idx - iz * LA.div_b[0] * LA.div_b[1] - iy * LA.div_b[0];
-        // this leaf appears in the neighbour list of every in-grid cell of its 3x3x3 window
+        // this leaf appears in the neighbour list of every in-grid cell of its 3x3x3 window it can be reached from
+        const float4 c0 = centroid4[j];
         for (int dz = -1; dz <= 1; ++dz)
             for (int dy = -1; dy <= 1; ++dy)
                 for (int dx = -1; dx <= 1; ++dx) {
                     const int kx = ix + dx, ky = iy + dy, kz = iz + dz;
                     if (kx < 0 || ky < 0 || kz < 0 || kx >= LA.div_b[0] || ky >= LA.div_b[1] || kz >= LA.div_b[2]) continue;
+                    if (!nbr_keep(c0.x, c0.y, c0.z, kx, ky, kz, LA)) continue;
                     atomicAdd(&nbr_head[(size_t)kx + (size_t)ky * LA.div_b[0] + (size_t)kz * LA.div_b[0] * LA.div_b[1]].y, 1u);
                 }
         const float4 c = centroid4[j];
@@ -242,7 +263,10 @@ __global__ void __launch_bounds__(NBR_TPB) nbr_fill_kernel(uint2 *__restrict__ h
                         if (kx < 0 || ky < 0 || kz < 0 || kx >= dx_n || ky >= dy_n || kz >= dz_n) continue;
                         const float4 e = __ldg(&cells[(size_t)kx + (size_t)ky * dx_n + (size_t)kz * dx_n * dy_n]);
                         const int code = __float_as_int(e.w);
-                        if (code > 0) { list[off + k] = make_float4(e.x, e.y, e.z, __int_as_float(code - 1)); ++k; }
+                        if (code > 0 && nbr_keep(e.x, e.y, e.z, ix, iy, iz, LA)) {
+                            list[off + k] = make_float4(e.x, e.y, e.z, __int_as_float(code - 1));
+                            ++k;
+                        }
                     }
         }
     }
@@ -275,6 +299,9 @@ __global__ void __launch_bounds__(NBR_TPB) nbr_fill_kernel(uint2 *__restrict__ h
 #endif
 #ifndef NDT_REG_SEARCH
 #define NDT_REG_SEARCH 56
+#endif
+#ifndef NDT_LPF
+#define NDT_LPF 1      // search warps pull the neighbour-list lines of the next round into L1
 #endif
 #ifndef NDT_PF
 #define NDT_PF 0       // compute warps prefetch the next chunk's voxel records into L1
@@ -336,7 +363,7 @@ struct NdtSmem {
     uint32_t head[NDT_NSW];        // entries consumed from search warp s
     uint32_t finished[NDT_NSW];    // last pass id search warp s has completed
     float4 ring[NDT_NSW][RING];    // (source point x, y, z, leaf index): consumers never touch the source cloud
-    float4 stage[NDT_NSW][128];    // per search warp, double-buffered: [lane] source point, [32 + lane] transformed point
+    float4 stage[NDT_NSW][192];    // per search warp, three slots: [lane] source point, [32 + lane] transformed point
 };
 
 __device__ __forceinline__ void cta_barrier() { asm volatile("bar.sync 0, %0;" ::"n"(NDT_THREADS) : "memory"); }
@@ -455,6 +482,62 @@ __device__ __forceinline__ double acc_finish(const double *t /*NACC*/, const Ang
         }
     }
     return v;
+}
+
+// Warp-cooperative version of lu_solve6 (b2_ndt_math.cuh): lane r < 6 owns row r of the augmented matrix
+// [H^T | -g]; pivot search, row exchange and elimination use shuffles, every operation on a matrix entry is
+// the one the serial code performs (same pivot rule: first row with the largest |entry|; same f = a*inv,
+// a -= f*p arithmetic), so the solution is the serial one.  All lanes return the solution and the
+// min|pivot| / max|pivot| estimate (0 when a pivot is zero or NaN).
+__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+
+__device__ __noinline__ double warp_lu_solve6(const double *__restrict__ H, const double *__restrict__ g, int lane, double x[6]) {
+    const int r = (lane < 6) ? lane : 5;
+    double a[7];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) a[c] = H[c * 6 + r];
+    a[6] = -g[r];
+    double pmin = DBL_MAX, pmax = 0.0;
+    bool singular = false;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        const double mine = fabs(a[k]);
+        double best = shfl_d(mine, k);
+        int pl = k;
+#pragma unroll
+        for (int rr = k + 1; rr < 6; ++rr) {
+            const double v = shfl_d(mine, rr);
+            if (v > best) { best = v; pl = rr; }
+        }
+        if (!(best > 0.0)) singular = true;   // zero or NaN pivot
+        pmin = fmin(pmin, best);
+        pmax = fmax(pmax, best);
+        double pr[7];
+#pragma unroll
+        for (int c = k; c < 7; ++c) {
+            pr[c] = shfl_d(a[c], pl);
+            const double kr = shfl_d(a[c], k);
+            if (lane == pl) a[c] = kr;        // row exchange k <-> pl (no-op when pl == k)
+            if (lane == k) a[c] = pr[c];
+        }
+        const double inv = 1.0 / pr[k];
+        if (lane > k && lane < 6) {
+            const double f = a[k] * inv;
+#pragma unroll
+            for (int c = k + 1; c < 7; ++c) a[c] -= f * pr[c];
+        }
+    }
+    double xs[6];
+#pragma unroll
+    for (int rr = 5; rr >= 0; --rr) {
+        double sacc = a[6];
+#pragma unroll
+        for (int c = rr + 1; c < 6; ++c) sacc -= a[c] * xs[c];
+        xs[rr] = shfl_d(sacc / a[rr], rr);
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) x[i] = xs[i];
+    return singular ? 0.0 : pmin / pmax;
 }
 
 // warp 0 completes a pass request: the twelve sin/cos evaluations run on twelve lanes
@@ -583,16 +666,28 @@ __global__ void __launch_bounds__(NDT_THREADS, NDT_MIN_CTAS) ndt_match_kernel(Gr
                 S.stage[sw][buf * 64 + lane] = pt;
                 S.stage[sw][buf * 64 + 32 + lane] = make_float4(tx, ty, tz, 0.f);
             };
-            int buf = 0;
-            uint32_t off, cnt, off_n = 0, cnt_n = 0;
+            // three rounds in flight: r (searched now), r+1 (header loaded, its list lines being pulled into
+            // L1), r+2 (points loaded, header load issued); stage slot = round % 3
+            uint32_t off, cnt, off_1 = 0, cnt_1 = 0, off_2 = 0, cnt_2 = 0;
             prepare(b0, load_pt(b0), 0, off, cnt);
-            float4 pt_nn = load_pt(b0 + stride);              // points of the round after
-            for (uint32_t base = b0; base < last; base += stride, buf ^= 1) {
-                // kick off the next two rounds, then search this one
+            prepare(b0 + stride, load_pt(b0 + stride), 1, off_1, cnt_1);
+            float4 pt_3 = load_pt(b0 + 2u * stride);
+            int slot = 0;
+            for (uint32_t base = b0; base < last; base += stride, slot = (slot == 2) ? 0 : slot + 1) {
                 __syncwarp();
-                prepare(base + stride, pt_nn, buf ^ 1, off_n, cnt_n);
-                pt_nn = load_pt(base + 2u * stride);
-                const float4 *stage = &S.stage[sw][buf * 64];
+#if NDT_LPF
+                if (cnt_1 != IRREGULAR) {
+                    const float4 *lp = G.nbr_list + off_1;
+                    for (uint32_t k = 0; k < cnt_1; k += 8u) asm volatile("prefetch.global.L1 [%0];" ::"l"(lp + k));
+                    if (cnt_1) asm volatile("prefetch.global.L1 [%0];" ::"l"(lp + cnt_1 - 1u));
+                }
+#endif
+                {
+                    const int slot2 = (slot == 0) ? 2 : slot - 1;       // (slot + 2) % 3
+                    prepare(base + 2u * stride, pt_3, slot2, off_2, cnt_2);
+                    pt_3 = load_pt(base + 3u * stride);
+                }
+                const float4 *stage = &S.stage[sw][slot * 64];
                 const bool irregular = (cnt == IRREGULAR);
                 if (irregular) cnt = 0u;
                 // ---- regular lanes: the warp walks the concatenation of its 32 neighbour lists, 32 entries
@@ -617,26 +712,35 @@ __global__ void __launch_bounds__(NDT_THREADS, NDT_MIN_CTAS) ndt_match_kernel(Gr
                     if (e < total) c = __ldg(&G.nbr_list[o_off + (e - o_excl)]);
                     return c;
                 };
-                int o_nx = 0;
-                float4 c_nx = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (total) c_nx = fetch(lane, o_nx);
-                for (uint32_t e0 = 0; e0 < total; e0 += 32u) {
-                    const float4 c = c_nx;
-                    const int o = o_nx;
-                    if (e0 + 32u < total) c_nx = fetch(e0 + 32u + lane, o_nx);      // next batch in flight
-                    ring_room(32u);
-                    const float4 q = stage[32 + o];
+                // two batches (64 entries) per step: their owner searches, loads and tests are independent
+                // instruction streams the scheduler can interleave
+#pragma unroll 1
+                for (uint32_t e0 = 0; e0 < total; e0 += 64u) {
+                    int oa, ob;
+                    const float4 ca = fetch(e0 + lane, oa);
+                    const float4 cb = fetch(e0 + 32u + lane, ob);
+                    ring_room(64u);
+                    const float4 qa = stage[32 + oa], qb = stage[32 + ob];
                     // flann::L2_Simple<float>: (dx*dx + dy*dy) + dz*dz, accepted when < (float)(r*r)
-                    const float dx = __fsub_rn(q.x, c.x), dy = __fsub_rn(q.y, c.y), dz = __fsub_rn(q.z, c.z);
-                    const float d2f = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-                    const bool hit = (e0 + lane < total) && (d2f < G.r2);
-                    const uint32_t b = __ballot_sync(0xffffffffu, hit);
-                    if (hit) {
-                        const float4 sp = stage[o];
-                        ring[(my_tail + __popc(b & lt)) & (RING - 1u)] = make_float4(sp.x, sp.y, sp.z, c.w);
+                    const float dxa = __fsub_rn(qa.x, ca.x), dya = __fsub_rn(qa.y, ca.y), dza = __fsub_rn(qa.z, ca.z);
+                    const float dxb = __fsub_rn(qb.x, cb.x), dyb = __fsub_rn(qb.y, cb.y), dzb = __fsub_rn(qb.z, cb.z);
+                    const float d2a = __fadd_rn(__fadd_rn(__fmul_rn(dxa, dxa), __fmul_rn(dya, dya)), __fmul_rn(dza, dza));
+                    const float d2b = __fadd_rn(__fadd_rn(__fmul_rn(dxb, dxb), __fmul_rn(dyb, dyb)), __fmul_rn(dzb, dzb));
+                    const bool hita = (e0 + lane < total) && (d2a < G.r2);
+                    const bool hitb = (e0 + 32u + lane < total) && (d2b < G.r2);
+                    const uint32_t ba = __ballot_sync(0xffffffffu, hita);
+                    const uint32_t bb = __ballot_sync(0xffffffffu, hitb);
+                    const uint32_t na = __popc(ba);
+                    if (hita) {
+                        const float4 sp = stage[oa];
+                        ring[(my_tail + __popc(ba & lt)) & (RING - 1u)] = make_float4(sp.x, sp.y, sp.z, ca.w);
                     }
-                    if (b) {
-                        my_tail += __popc(b);
+                    if (hitb) {
+                        const float4 sp = stage[ob];
+                        ring[(my_tail + na + __popc(bb & lt)) & (RING - 1u)] = make_float4(sp.x, sp.y, sp.z, cb.w);
+                    }
+                    if (ba | bb) {
+                        my_tail += na + __popc(bb);
                         __syncwarp();
                         if (lane == 0) publish_tail(&S.tail[sw], my_tail);
                     }
@@ -692,7 +796,7 @@ __global__ void __launch_bounds__(NDT_THREADS, NDT_MIN_CTAS) ndt_match_kernel(Gr
                         }
                     }
                 }
-                off = off_n; cnt = cnt_n;
+                off = off_1; cnt = cnt_1; off_1 = off_2; cnt_1 = cnt_2;
             }
             // publish the end of this warp's stream for this pass
             __syncwarp();
@@ -837,9 +941,34 @@ __global__ void __launch_bounds__(NDT_THREADS, NDT_MIN_CTAS) ndt_match_kernel(Gr
         if (warp == 0) {
             if (lane < ACC_N) S.total[lane] = acc_finish(S.raw_total, S.ctl.ang, lane);
             __syncwarp();
-            int go = 0;
-            if (lane == 0) { go = A.deriv_only ? 0 : ctl_step(S.ctl, K, S.total); S.go = go; }
-            go = __shfl_sync(0xffffffffu, go, 0);
+            // serial halves on lane 0, the 6x6 Newton solve on the whole warp
+            int code = CTL_DONE;
+            if (!A.deriv_only) {
+                if (lane == 0) code = ctl_pre(S.ctl, K, S.total);
+                code = __shfl_sync(0xffffffffu, code, 0);
+                for (int guard = 0; guard < 8 && code == CTL_NEWTON; ++guard) {
+                    __syncwarp();
+                    double delta[6];
+                    const double rc = warp_lu_solve6(S.ctl.H, S.ctl.g, lane, delta);
+                    if (lane == 0) {
+                        bool fin = true;
+#pragma unroll
+                        for (int i = 0; i < 6; ++i) fin = fin && (delta[i] == delta[i]) && (fabs(delta[i]) <= DBL_MAX);
+                        if (K.force_svd || !(rc > 1e-9 && fin)) {
+                            // (near-)singular Hessian: Eigen's JacobiSVD solve with its rank truncation
+                            double neg_g[6];
+                            for (int i = 0; i < 6; ++i) neg_g[i] = -S.ctl.g[i];
+                            svd_solve6(S.ctl.H, neg_g, delta);
+                        }
+                        code = ctl_post_newton(S.ctl, K, delta);
+                    }
+                    code = __shfl_sync(0xffffffffu, code, 0);
+                }
+                if (code == CTL_NEWTON) { code = CTL_DONE; if (lane == 0) S.ctl.state = ST_DONE; }
+            }
+            const int go = (code == CTL_PASS) ? 1 : 0;
+            if (lane == 0) S.go = go;
+            __syncwarp();
             if (go) finish_request_warp0(S, lane);
         }
         cta_barrier();                              // (3)
@@ -1098,6 +1227,7 @@ static int build_target(b2ndt *h, const float4 *d_pts, size_t n, int nbits_hint)
     B2_CUDA(cudaMemsetAsync(t.counters.p, 0, 64, h->st));
     LayoutArg LA;
     for (int a = 0; a < 3; ++a) { LA.min_b[a] = t.L.min_b[a]; LA.div_b[a] = t.L.div_b[a]; LA.inv[a] = t.L.inv[a]; }
+    LA.res = h->prm.res;
     if (V) {
         unsigned blocks = (V + 7) / 8;
         if (blocks > 148 * 32) blocks = 148 * 32;

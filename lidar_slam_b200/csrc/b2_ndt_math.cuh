@@ -704,18 +704,35 @@ B2_HD_NOINLINE inline void ctl_start(Ctl &c, const NdtConst &k, const float gues
     for (int i = 0; i < 36; ++i) c.H[i] = 0.0;
 }
 
-// Consume the finished pass and decide what happens next.  Returns 1 when another pass is requested
-// (c.T / c.ang / c.hess describe it), 0 when the alignment is finished.
-B2_HD_NOINLINE inline int ctl_step(Ctl &c, const NdtConst &k, const double *acc) {
+// The controller step is split so that the GPU can run the 6x6 Newton solve warp-cooperatively between the
+// two serial halves:  ctl_pre consumes the finished pass (state machine, More-Thuente bookkeeping, pose
+// update + convergence test) and answers CTL_DONE, CTL_PASS (another pass is requested: c.T / c.ang / c.hess
+// describe it) or CTL_NEWTON (solve H delta = -g, then call ctl_post_newton(delta), which answers the same
+// three codes).  ctl_step is the serial composition (host tests, oracle pins).
+enum CtlCode { CTL_DONE = 0, CTL_PASS = 1, CTL_NEWTON = 2 };
+
+// NDTM:368-383: apply the accepted step, test convergence
+B2_HD_NOINLINE inline int ctl_finish_iter(Ctl &c, const NdtConst &k) {
+    double delta_p_norm = c.a_t;
+    for (int i = 0; i < 6; ++i) c.p[i] = c.p[i] + c.dir[i] * delta_p_norm;
+    if (c.nr_iter > k.max_iter || (c.nr_iter && (fabs(delta_p_norm) < k.trans_eps))) c.converged = 1;
+    c.nr_iter++;
+    if (c.converged) {
+        c.trans_probability = (c.npoints > 0) ? c.score / c.npoints : 0.0;
+        c.state = ST_DONE;
+        return CTL_DONE;
+    }
+    return CTL_NEWTON;
+}
+
+B2_HD_NOINLINE inline int ctl_pre(Ctl &c, const NdtConst &k, const double *acc) {
     const double mu = 1.e-4, nu = 0.9;
     const int max_step_iterations = 10;
     bool mt_check = false;      // evaluate the More-Thuente loop condition
-    bool do_newton = false;
-    bool finish_iter = false;
 
     if (c.state == ST_INIT) {
         ctl_unpack_acc(c, acc, true, true);
-        do_newton = true;
+        return CTL_NEWTON;
     } else if (c.state == ST_MT_FIRST) {
         ctl_unpack_acc(c, acc, true, true);
         c.phi_t = -c.score;
@@ -749,9 +766,8 @@ B2_HD_NOINLINE inline int ctl_step(Ctl &c, const NdtConst &k, const double *acc)
         mt_check = true;
     } else if (c.state == ST_MT_HESS) {
         ctl_unpack_acc(c, acc, false, true);      // computeHessian (NDTM:901-936)
-        finish_iter = true;
     } else {
-        return 0;
+        return CTL_DONE;
     }
 
     if (mt_check) {
@@ -763,79 +779,71 @@ B2_HD_NOINLINE inline int ctl_step(Ctl &c, const NdtConst &k, const double *acc)
             c.a_t = (c.a_t > c.step_min) ? c.a_t : c.step_min;
             for (int i = 0; i < 6; ++i) c.x_t[i] = c.p[i] + c.dir[i] * c.a_t;
             ctl_request(c, c.x_t, 0, ST_MT_TRIAL);
-            return 1;
+            return CTL_PASS;
         }
         if (c.step_iterations) {
             // same pose, Hessian only
             c.hess = 1;
             c.state = ST_MT_HESS;
             c.need_trig = 0;
-            return 1;
+            return CTL_PASS;
         }
-        finish_iter = true;
     }
+    return ctl_finish_iter(c, k);
+}
 
-    for (int guard = 0; guard < 100000; ++guard) {
-        if (finish_iter) {
-            // NDTM:368-383
-            double delta_p_norm = c.a_t;
-            for (int i = 0; i < 6; ++i) c.p[i] = c.p[i] + c.dir[i] * delta_p_norm;
-            if (c.nr_iter > k.max_iter || (c.nr_iter && (fabs(delta_p_norm) < k.trans_eps))) c.converged = 1;
-            c.nr_iter++;
-            if (c.converged) {
-                c.trans_probability = (c.npoints > 0) ? c.score / c.npoints : 0.0;
-                c.state = ST_DONE;
-                return 0;
-            }
-            do_newton = true;
-            finish_iter = false;
-        }
-        if (do_newton) {
-            do_newton = false;
-            // NDTM:353-365
-            double neg_g[6], delta[6];
-            for (int i = 0; i < 6; ++i) neg_g[i] = -c.g[i];
-            newton_solve6(c.H, neg_g, delta, k.force_svd);
-            double n2 = 0.0;
-            for (int i = 0; i < 6; ++i) n2 += delta[i] * delta[i];
-            double nrm = sqrt(n2);
-            if (nrm == 0 || nrm != nrm) {
-                c.trans_probability = c.score / c.npoints;
-                c.converged = (nrm == nrm) ? 1 : 0;
-                c.state = ST_DONE;
-                return 0;
-            }
-            for (int i = 0; i < 6; ++i) c.dir[i] = delta[i] / nrm;
-            // computeStepLengthMT prologue NDTM:656-698
-            c.phi_0 = -c.score;
-            double d = 0.0;
-            for (int i = 0; i < 6; ++i) d += c.g[i] * c.dir[i];
-            c.d_phi_0 = -d;
-            if (c.d_phi_0 >= 0) {
-                if (c.d_phi_0 == 0) { c.a_t = 0.0; finish_iter = true; continue; }
-                c.d_phi_0 *= -1;
-                for (int i = 0; i < 6; ++i) c.dir[i] *= -1;
-            }
-            c.step_max = k.step_size;
-            c.step_min = k.trans_eps / 2;
-            c.step_iterations = 0;
-            c.a_l = 0; c.a_u = 0;
-            c.f_l = psi_mt(c.a_l, c.phi_0, c.phi_0, c.d_phi_0, mu);
-            c.g_l = dpsi_mt(c.d_phi_0, c.d_phi_0, mu);
-            c.f_u = psi_mt(c.a_u, c.phi_0, c.phi_0, c.d_phi_0, mu);
-            c.g_u = dpsi_mt(c.d_phi_0, c.d_phi_0, mu);
-            c.interval_converged = k.pcl17_compat ? ((c.step_max - c.step_min) > 0) : ((c.step_max - c.step_min) < 0);
-            c.open_interval = 1;
-            c.a_t = nrm;
-            c.a_t = fmin(c.a_t, c.step_max);
-            c.a_t = fmax(c.a_t, c.step_min);
-            for (int i = 0; i < 6; ++i) c.x_t[i] = c.p[i] + c.dir[i] * c.a_t;
-            ctl_request(c, c.x_t, 1, ST_MT_FIRST);
-            return 1;
-        }
+// NDTM:353-365 after the solve, then the computeStepLengthMT prologue NDTM:656-698
+B2_HD_NOINLINE inline int ctl_post_newton(Ctl &c, const NdtConst &k, const double delta[6]) {
+    const double mu = 1.e-4;
+    double n2 = 0.0;
+    for (int i = 0; i < 6; ++i) n2 += delta[i] * delta[i];
+    double nrm = sqrt(n2);
+    if (nrm == 0 || nrm != nrm) {
+        c.trans_probability = c.score / c.npoints;
+        c.converged = (nrm == nrm) ? 1 : 0;
+        c.state = ST_DONE;
+        return CTL_DONE;
     }
-    c.state = ST_DONE;
-    return 0;
+    for (int i = 0; i < 6; ++i) c.dir[i] = delta[i] / nrm;
+    c.phi_0 = -c.score;
+    double d = 0.0;
+    for (int i = 0; i < 6; ++i) d += c.g[i] * c.dir[i];
+    c.d_phi_0 = -d;
+    if (c.d_phi_0 >= 0) {
+        if (c.d_phi_0 == 0) { c.a_t = 0.0; return ctl_finish_iter(c, k); }
+        c.d_phi_0 *= -1;
+        for (int i = 0; i < 6; ++i) c.dir[i] *= -1;
+    }
+    c.step_max = k.step_size;
+    c.step_min = k.trans_eps / 2;
+    c.step_iterations = 0;
+    c.a_l = 0; c.a_u = 0;
+    c.f_l = psi_mt(c.a_l, c.phi_0, c.phi_0, c.d_phi_0, mu);
+    c.g_l = dpsi_mt(c.d_phi_0, c.d_phi_0, mu);
+    c.f_u = psi_mt(c.a_u, c.phi_0, c.phi_0, c.d_phi_0, mu);
+    c.g_u = dpsi_mt(c.d_phi_0, c.d_phi_0, mu);
+    c.interval_converged = k.pcl17_compat ? ((c.step_max - c.step_min) > 0) : ((c.step_max - c.step_min) < 0);
+    c.open_interval = 1;
+    c.a_t = nrm;
+    c.a_t = fmin(c.a_t, c.step_max);
+    c.a_t = fmax(c.a_t, c.step_min);
+    for (int i = 0; i < 6; ++i) c.x_t[i] = c.p[i] + c.dir[i] * c.a_t;
+    ctl_request(c, c.x_t, 1, ST_MT_FIRST);
+    return CTL_PASS;
+}
+
+// Consume the finished pass and decide what happens next.  Returns 1 when another pass is requested
+// (c.T / c.ang / c.hess describe it), 0 when the alignment is finished.
+B2_HD_NOINLINE inline int ctl_step(Ctl &c, const NdtConst &k, const double *acc) {
+    int code = ctl_pre(c, k, acc);
+    for (int guard = 0; guard < 100000 && code == CTL_NEWTON; ++guard) {
+        double neg_g[6], delta[6];
+        for (int i = 0; i < 6; ++i) neg_g[i] = -c.g[i];
+        newton_solve6(c.H, neg_g, delta, k.force_svd);
+        code = ctl_post_newton(c, k, delta);
+    }
+    if (code == CTL_NEWTON) { c.state = ST_DONE; code = CTL_DONE; }
+    return code == CTL_PASS;
 }
 
 }  // namespace b2
