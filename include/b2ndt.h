@@ -141,6 +141,34 @@ int  b2vf_filter(b2vf *h, const void *in, size_t n, size_t stride, size_t ioff,
 int  b2vf_filter_batch_device(b2vf *h, const void *d_in_f4, size_t n_total, const uint32_t *h_offsets,
                               size_t B, void *d_out_f4, uint32_t *d_out_offsets);
 
+/* ------------------------------------------------------------------ device-resident clouds --
+ * The callers either side of the hot path keep their clouds in HBM: the front end's
+ * local map = sum of key frames transformed by their poses (front_end.cpp:375-410), the matching node's
+ * BoxFilter crop of the global map (box_filter.cpp:27-37, matching.cpp:166-183), VoxelFilter and
+ * SetInputTarget / ScanMatch on the result -- no host round trip between the steps.  A b2cloud is a packed
+ * float4 {x,y,z,intensity} array on one device; handles are not thread-safe. */
+typedef struct b2cloud b2cloud;
+
+int  b2cloud_create(int device, b2cloud **out);
+void b2cloud_destroy(b2cloud *c);
+int  b2cloud_upload(b2cloud *c, const void *pts, size_t n, size_t stride, size_t ioff);
+/* out: capacity points with byte stride / intensity offset as in b2vf_filter; *n receives the size */
+int  b2cloud_download(b2cloud *c, void *out, size_t capacity, size_t stride, size_t ioff, size_t *n);
+int  b2cloud_size(b2cloud *c, size_t *n);
+int  b2cloud_clear(b2cloud *c);
+int  b2cloud_device_ptr(b2cloud *c, void **d_f4);
+/* dst += pcl::transformPointCloud(src, T) (T column-major float 4x4; intensity kept; order kept) */
+int  b2cloud_append_transformed(b2cloud *dst, b2cloud *src, const float T[16]);
+/* pcl::CropBox: dst = points of src with edge[0] <= x <= edge[1], edge[2] <= y <= edge[3],
+ * edge[4] <= z <= edge[5] (BoxFilter::GetEdge order), input order kept, non-finite points dropped */
+int  b2cloud_box_filter(b2cloud *src, const float edge[6], b2cloud *dst);
+/* VoxelFilter::Filter on device clouds (src == dst allowed) */
+int  b2vf_filter_cloud(b2vf *h, b2cloud *src, b2cloud *dst);
+/* SetInputTarget / ScanMatch on device clouds; result_cloud may be NULL */
+int  b2ndt_set_target_cloud(b2ndt *h, b2cloud *target);
+int  b2ndt_align_cloud(b2ndt *h, b2cloud *src, const float guess[16], float pose_out[16], b2ndt_result *res,
+                       b2cloud *result_cloud);
+
 #ifdef __cplusplus
 }
 #endif

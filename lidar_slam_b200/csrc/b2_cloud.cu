@@ -1,0 +1,279 @@
+// b2_cloud.cu -- device-resident clouds for the callers either side of the registration hot path
+// (SURVEY 8(f) rows 1-2): local-map assembly and map cropping without leaving HBM.
+//
+// Reference semantics (paths relative to /root/reference/lidar_localization/):
+//   local map   = sum over key frames of pcl::transformPointCloud(frame, pose)   src/mapping/front_end/front_end.cpp:375-410
+//   BoxFilter   = pcl::CropBox with min/max = origin + size, identity box pose    src/models/cloud_filter/box_filter.cpp:27-37
+//                 (callers: src/matching/matching.cpp:166-183, 255-262)
+// Both are HBM-streaming kernels: 16 B read + 16 B written per point kept, coalesced float4 accesses,
+// order-preserving (pcl::CropBox keeps the input order; operator+= appends).
+#include "b2_cloud.cuh"
+
+namespace b2 {
+int check_device(int device);
+
+// pcl::transformPointCloud on PointXYZI: xyz through the float 4x4 (left-to-right, no contraction),
+// intensity copied; non-finite points are copied unchanged (is_dense == false path).
+__global__ void __launch_bounds__(256) transform_append_kernel(const float4 *__restrict__ src, uint32_t n, const float *__restrict__ Tg,
+                                                               float4 *__restrict__ dst) {
+    __shared__ float T[16];
+    if (threadIdx.x < 16) T[threadIdx.x] = Tg[threadIdx.x];
+    __syncthreads();
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 p = __ldg(&src[i]);
+        float4 o = p;
+        if (finite3(p.x, p.y, p.z)) transform_f32(T, p.x, p.y, p.z, o.x, o.y, o.z);
+        dst[i] = o;
+    }
+}
+
+// pcl::CropBox (negative = false, identity transform): keep finite points with min <= p <= max on every axis.
+constexpr int CROP_THREADS = 256;
+constexpr int CROP_PER_THREAD = 8;
+constexpr uint32_t CROP_TILE = CROP_THREADS * CROP_PER_THREAD;
+struct BoxArg { float mn[3], mx[3]; };
+
+__device__ __forceinline__ bool box_keep(const float4 p, const BoxArg &B) {
+    if (!finite3(p.x, p.y, p.z)) return false;
+    return !(p.x < B.mn[0] || p.y < B.mn[1] || p.z < B.mn[2] || p.x > B.mx[0] || p.y > B.mx[1] || p.z > B.mx[2]);
+}
+
+// pass 1: kept points per tile
+__global__ void __launch_bounds__(CROP_THREADS) crop_count_kernel(const float4 *__restrict__ src, uint32_t n, BoxArg B,
+                                                                  uint32_t *__restrict__ tile_cnt) {
+    __shared__ uint32_t wsum[CROP_THREADS / 32];
+    uint32_t c = 0;
+#pragma unroll
+    for (int r = 0; r < CROP_PER_THREAD; ++r) {
+        const uint32_t i = blockIdx.x * CROP_TILE + r * CROP_THREADS + threadIdx.x;
+        if (i < n) c += box_keep(__ldg(&src[i]), B) ? 1u : 0u;
+    }
+    c = __reduce_add_sync(0xffffffffu, c);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int w = 0; w < CROP_THREADS / 32; ++w) t += wsum[w];
+        tile_cnt[blockIdx.x] = t;
+    }
+}
+
+// pass 2 (single CTA): exclusive scan of the tile counts in place; total -> tile_cnt[ntiles]
+__global__ void __launch_bounds__(1024) crop_scan_kernel(uint32_t *__restrict__ tile_cnt, uint32_t ntiles) {
+    __shared__ uint32_t wt[33];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t base = 0;
+    for (uint32_t t0 = 0; t0 < ntiles; t0 += 1024) {
+        const uint32_t t = t0 + threadIdx.x;
+        const uint32_t v = (t < ntiles) ? tile_cnt[t] : 0u;
+        uint32_t incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += u; }
+        if (lane == 31) wt[w] = incl;
+        __syncthreads();
+        if (w == 0) {
+            const uint32_t x = wt[lane];
+            uint32_t xi = x;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, xi, d); if (lane >= d) xi += u; }
+            wt[lane] = xi - x;
+            if (lane == 31) wt[32] = xi;
+        }
+        __syncthreads();
+        if (t < ntiles) tile_cnt[t] = base + wt[w] + incl - v;
+        base += wt[32];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) tile_cnt[ntiles] = base;
+}
+
+// pass 3: stable scatter (input order kept): rank inside the tile = rounds before + warps before + lanes before
+__global__ void __launch_bounds__(CROP_THREADS) crop_scatter_kernel(const float4 *__restrict__ src, uint32_t n, BoxArg B,
+                                                                    const uint32_t *__restrict__ tile_off, float4 *__restrict__ dst) {
+    __shared__ uint32_t wcnt[CROP_THREADS / 32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t base = tile_off[blockIdx.x];
+#pragma unroll 1
+    for (int r = 0; r < CROP_PER_THREAD; ++r) {
+        const uint32_t i = blockIdx.x * CROP_TILE + r * CROP_THREADS + threadIdx.x;
+        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+        bool keep = false;
+        if (i < n) { p = __ldg(&src[i]); keep = box_keep(p, B); }
+        const uint32_t b = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) wcnt[w] = __popc(b);
+        __syncthreads();
+        uint32_t before = 0, total = 0;
+#pragma unroll
+        for (int k = 0; k < CROP_THREADS / 32; ++k) { const uint32_t c = wcnt[k]; if (k < w) before += c; total += c; }
+        if (keep) dst[base + before + __popc(b & ((1u << lane) - 1u))] = p;
+        base += total;
+        __syncthreads();
+    }
+}
+
+}  // namespace b2
+
+using namespace b2;
+
+// host-side packers live in b2_voxel.cu
+namespace b2 {
+void pack_cloud_f4(const void *src, size_t n, size_t stride, size_t ioff, float *dst_f4);
+}
+
+// One pinned staging buffer per process for cloud uploads / downloads (cudaMallocHost costs milliseconds;
+// clouds are created per frame).  Handles are not thread-safe, the pool is.
+#include <mutex>
+static b2::PinBuf g_stage;
+static std::mutex g_stage_mu;
+
+static int cloud_check(const char *fn, const b2cloud *c) {
+    if (!c) { set_error("%s: NULL cloud handle", fn); return B2_ERR_INVALID; }
+    return 0;
+}
+
+extern "C" int b2cloud_create(int device, b2cloud **out) {
+    if (!out) { set_error("b2cloud_create: out is NULL"); return B2_ERR_INVALID; }
+    *out = nullptr;
+    int rc = check_device(device);
+    if (rc) return rc;
+    B2_CUDA(cudaSetDevice(device));
+    b2cloud *c = new b2cloud();
+    c->device = device;
+    cudaError_t e = cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { set_error("cudaStreamCreate failed: %s", cudaGetErrorString(e)); delete c; return B2_ERR_CUDA; }
+    *out = c;
+    return 0;
+}
+
+extern "C" void b2cloud_destroy(b2cloud *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->st);
+    c->pts.release(); c->scratch.release(); c->h_stage.release(); c->h_small.release();
+    if (c->st) cudaStreamDestroy(c->st);
+    delete c;
+}
+
+extern "C" int b2cloud_size(b2cloud *c, size_t *n) {
+    int rc = cloud_check("b2cloud_size", c);
+    if (rc) return rc;
+    if (!n) { set_error("b2cloud_size: n is NULL"); return B2_ERR_INVALID; }
+    *n = c->n;
+    return 0;
+}
+
+extern "C" int b2cloud_clear(b2cloud *c) {
+    int rc = cloud_check("b2cloud_clear", c);
+    if (rc) return rc;
+    c->n = 0;
+    return 0;
+}
+
+extern "C" int b2cloud_device_ptr(b2cloud *c, void **d_f4) {
+    int rc = cloud_check("b2cloud_device_ptr", c);
+    if (rc) return rc;
+    if (!d_f4) { set_error("b2cloud_device_ptr: NULL argument"); return B2_ERR_INVALID; }
+    *d_f4 = c->pts.p;
+    return 0;
+}
+
+extern "C" int b2cloud_upload(b2cloud *c, const void *pts, size_t n, size_t stride, size_t ioff) {
+    int rc = cloud_check("b2cloud_upload", c);
+    if (rc) return rc;
+    if (n && !pts) { set_error("b2cloud_upload: NULL cloud"); return B2_ERR_INVALID; }
+    if (stride < 16 || (stride & 3) || ioff + 4 > stride || (ioff & 3)) { set_error("b2cloud_upload: bad stride %zu / intensity offset %zu", stride, ioff); return B2_ERR_INVALID; }
+    if (n >= 0xFFFFFFF0ull) { set_error("b2cloud_upload: cloud too large"); return B2_ERR_INVALID; }
+    B2_CUDA(cudaSetDevice(c->device));
+    c->n = 0;
+    if ((rc = c->reserve(n))) return rc;
+    if (n) {
+        std::lock_guard<std::mutex> lk(g_stage_mu);
+        if ((rc = g_stage.reserve(n * 16))) return rc;
+        pack_cloud_f4(pts, n, stride, ioff, g_stage.as<float>());
+        B2_CUDA(cudaMemcpyAsync(c->pts.p, g_stage.p, n * 16, cudaMemcpyHostToDevice, c->st));
+        B2_CUDA(cudaStreamSynchronize(c->st));
+    }
+    c->n = n;
+    return 0;
+}
+
+extern "C" int b2cloud_download(b2cloud *c, void *out, size_t capacity, size_t stride, size_t ioff, size_t *n) {
+    int rc = cloud_check("b2cloud_download", c);
+    if (rc) return rc;
+    if (!n) { set_error("b2cloud_download: n is NULL"); return B2_ERR_INVALID; }
+    *n = c->n;
+    if (c->n == 0) return 0;
+    if (!out) { set_error("b2cloud_download: NULL output"); return B2_ERR_INVALID; }
+    if (stride < 16 || (stride & 3) || ioff + 4 > stride || (ioff & 3)) { set_error("b2cloud_download: bad stride / intensity offset"); return B2_ERR_INVALID; }
+    if (capacity < c->n) { set_error("b2cloud_download: capacity %zu < %zu points", capacity, c->n); return B2_ERR_CAPACITY; }
+    B2_CUDA(cudaSetDevice(c->device));
+    std::lock_guard<std::mutex> lk(g_stage_mu);
+    if ((rc = g_stage.reserve(c->n * 16))) return rc;
+    B2_CUDA(cudaMemcpyAsync(g_stage.p, c->pts.p, c->n * 16, cudaMemcpyDeviceToHost, c->st));
+    B2_CUDA(cudaStreamSynchronize(c->st));
+    const float *res = g_stage.as<float>();
+    if (stride == 16 && ioff == 12) { memcpy(out, res, c->n * 16); return 0; }
+    char *o = (char *)out;
+    for (size_t j = 0; j < c->n; ++j) {
+        float *q = (float *)(o + j * stride);
+        if (stride >= 32) memset(q, 0, stride);
+        q[0] = res[4 * j]; q[1] = res[4 * j + 1]; q[2] = res[4 * j + 2];
+        if (stride >= 32 || ioff != 12) q[3] = 1.0f;     // PointXYZI padding data[3]
+        *(float *)(o + j * stride + ioff) = res[4 * j + 3];
+    }
+    return 0;
+}
+
+extern "C" int b2cloud_append_transformed(b2cloud *dst, b2cloud *src, const float T[16]) {
+    int rc = cloud_check("b2cloud_append_transformed", dst);
+    if (rc) return rc;
+    if ((rc = cloud_check("b2cloud_append_transformed", src))) return rc;
+    if (!T) { set_error("b2cloud_append_transformed: NULL transform"); return B2_ERR_INVALID; }
+    if (dst == src) { set_error("b2cloud_append_transformed: dst == src"); return B2_ERR_INVALID; }
+    if (dst->device != src->device) { set_error("b2cloud_append_transformed: clouds live on different devices"); return B2_ERR_INVALID; }
+    if (src->n == 0) return 0;
+    if (dst->n + src->n >= 0xFFFFFFF0ull) { set_error("b2cloud_append_transformed: cloud too large"); return B2_ERR_INVALID; }
+    B2_CUDA(cudaSetDevice(dst->device));
+    if ((rc = dst->reserve(dst->n + src->n))) return rc;
+    if ((rc = dst->h_small.reserve(256))) return rc;
+    if ((rc = dst->scratch.reserve(256))) return rc;
+    memcpy(dst->h_small.p, T, 64);
+    B2_CUDA(cudaMemcpyAsync(dst->scratch.p, dst->h_small.p, 64, cudaMemcpyHostToDevice, dst->st));
+    unsigned blocks = (unsigned)((src->n + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    transform_append_kernel<<<blocks, 256, 0, dst->st>>>(src->d(), (uint32_t)src->n, dst->scratch.as<float>(), dst->d() + dst->n);
+    B2_LAUNCH_CHECK();
+    B2_CUDA(cudaStreamSynchronize(dst->st));
+    dst->n += src->n;
+    return 0;
+}
+
+extern "C" int b2cloud_box_filter(b2cloud *src, const float edge[6], b2cloud *dst) {
+    int rc = cloud_check("b2cloud_box_filter", src);
+    if (rc) return rc;
+    if ((rc = cloud_check("b2cloud_box_filter", dst))) return rc;
+    if (!edge) { set_error("b2cloud_box_filter: NULL edge"); return B2_ERR_INVALID; }
+    if (dst == src) { set_error("b2cloud_box_filter: dst == src"); return B2_ERR_INVALID; }
+    if (dst->device != src->device) { set_error("b2cloud_box_filter: clouds live on different devices"); return B2_ERR_INVALID; }
+    B2_CUDA(cudaSetDevice(dst->device));
+    dst->n = 0;
+    const size_t n = src->n;
+    if (n == 0) return 0;
+    BoxArg B;
+    for (int a = 0; a < 3; ++a) { B.mn[a] = edge[2 * a]; B.mx[a] = edge[2 * a + 1]; }
+    const uint32_t ntiles = (uint32_t)((n + CROP_TILE - 1) / CROP_TILE);
+    if ((rc = dst->reserve(n))) return rc;
+    if ((rc = dst->scratch.reserve((size_t)(ntiles + 1) * 4 + 256))) return rc;
+    if ((rc = dst->h_small.reserve(256))) return rc;
+    uint32_t *tiles = dst->scratch.as<uint32_t>() + 64;     // first 256 bytes hold the transform of append
+    crop_count_kernel<<<ntiles, CROP_THREADS, 0, dst->st>>>(src->d(), (uint32_t)n, B, tiles);
+    B2_LAUNCH_CHECK();
+    crop_scan_kernel<<<1, 1024, 0, dst->st>>>(tiles, ntiles);
+    B2_LAUNCH_CHECK();
+    crop_scatter_kernel<<<ntiles, CROP_THREADS, 0, dst->st>>>(src->d(), (uint32_t)n, B, tiles, dst->d());
+    B2_LAUNCH_CHECK();
+    B2_CUDA(cudaMemcpyAsync(dst->h_small.p, tiles + ntiles, 4, cudaMemcpyDeviceToHost, dst->st));
+    B2_CUDA(cudaStreamSynchronize(dst->st));
+    dst->n = *dst->h_small.as<uint32_t>();
+    return 0;
+}

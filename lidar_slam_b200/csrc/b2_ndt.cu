@@ -29,6 +29,7 @@
 #include "b2_common.cuh"
 #include "b2_ndt_math.cuh"
 #include "b2_voxel.cuh"
+#include "b2_cloud.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -1109,6 +1110,7 @@ struct b2ndt {
     DevBuf d_src, d_guess, d_pose, d_res, d_off, d_p6, d_acc, d_fit_sum, d_fit_cnt;
     PinBuf h_stage, h_small, h_res;
     size_t last_n = 0;
+    const float4 *last_src = nullptr;     // device source of the last ScanMatch (GetFitnessScore)
     float last_pose[16];
     bool have_last = false;
     int cl_single = 8, cl_batch = 1;
@@ -1490,6 +1492,7 @@ extern "C" int b2ndt_align(b2ndt *h, const void *src, size_t n, size_t stride, s
     rc = align_host(h, src, n, stride, ioff, nullptr, 1, guess, pose_out, res, C < 1 ? 1 : C);
     if (rc) return rc;
     h->last_n = n;
+    h->last_src = h->d_src.as<float4>();
     memcpy(h->last_pose, pose_out, 64);
     h->have_last = true;
     return 0;
@@ -1587,7 +1590,7 @@ extern "C" int b2ndt_fitness(b2ndt *h, double max_range, double *out) {
     if (!h || !out) { set_error("b2ndt_fitness: NULL argument"); return B2_ERR_INVALID; }
     if (!h->tgt.valid || !h->have_last) { set_error("b2ndt_fitness: no completed ScanMatch on this handle"); return B2_ERR_STATE; }
     B2_CUDA(cudaSetDevice(h->device));
-    return fitness_device(h, h->d_src.as<float4>(), h->last_n, h->last_pose, max_range, out);
+    return fitness_device(h, h->last_src, h->last_n, h->last_pose, max_range, out);
 }
 
 extern "C" int b2ndt_fitness_ex(b2ndt *h, const void *src, size_t n, size_t stride, size_t ioff, const float pose[16],
@@ -1605,4 +1608,58 @@ extern "C" int b2ndt_fitness_ex(b2ndt *h, const void *src, size_t n, size_t stri
     }
     h->have_last = false;
     return fitness_device(h, h->d_src.as<float4>(), n, pose, max_range, out);
+}
+
+// ------------------------------------------------------------------ device-resident clouds -----
+extern "C" int b2cloud_append_transformed(b2cloud *dst, b2cloud *src, const float T[16]);
+
+// SetInputTarget from a cloud that already lives in HBM (local map assembled / cropped on the device).
+extern "C" int b2ndt_set_target_cloud(b2ndt *h, b2cloud *target) {
+    if (!h || !target) { set_error("b2ndt_set_target_cloud: NULL argument"); return B2_ERR_INVALID; }
+    if (target->device != h->device) { set_error("b2ndt_set_target_cloud: handle and cloud live on different devices"); return B2_ERR_INVALID; }
+    B2_CUDA(cudaSetDevice(h->device));
+    return build_target(h, target->d(), target->n, 0);
+}
+
+// ScanMatch with a device-resident source; result_cloud (may be NULL) receives the source transformed by the
+// final pose (registration_interface.hpp:19-22).  The source cloud must stay unchanged until the next
+// ScanMatch if GetFitnessScore is going to be called (PCL keeps the source pointer the same way).
+extern "C" int b2ndt_align_cloud(b2ndt *h, b2cloud *src, const float guess[16], float pose_out[16], b2ndt_result *res,
+                                 b2cloud *result_cloud) {
+    if (!h || !src || !guess || !pose_out) { set_error("b2ndt_align_cloud: NULL argument"); return B2_ERR_INVALID; }
+    if (!h->tgt.valid) { set_error("b2ndt_align_cloud: SetInputTarget has not been called"); return B2_ERR_STATE; }
+    if (src->device != h->device) { set_error("b2ndt_align_cloud: handle and cloud live on different devices"); return B2_ERR_INVALID; }
+    if (result_cloud == src) { set_error("b2ndt_align_cloud: result_cloud == source"); return B2_ERR_INVALID; }
+    B2_CUDA(cudaSetDevice(h->device));
+    int rc;
+    const size_t n = src->n;
+    if ((rc = h->h_stage.reserve(256))) return rc;
+    if ((rc = h->d_guess.reserve(64))) return rc;
+    if ((rc = h->d_pose.reserve(64))) return rc;
+    if ((rc = h->d_res.reserve(sizeof(b2ndt_result)))) return rc;
+    if ((rc = h->h_res.reserve(64 + sizeof(b2ndt_result)))) return rc;
+    memcpy(h->h_stage.p, guess, 64);
+    B2_CUDA(cudaMemcpyAsync(h->d_guess.p, h->h_stage.p, 64, cudaMemcpyHostToDevice, h->st));
+    MatchArgs A;
+    memset(&A, 0, sizeof(A));
+    A.src = src->d(); A.n_shared = (uint32_t)n; A.guesses = h->d_guess.as<float>(); A.poses_out = h->d_pose.as<float>();
+    A.results = h->d_res.as<b2ndt_result>();
+    int C = h->cl_single;
+    while (C > 1 && (size_t)C * NDT_NSW * 32 > n) C >>= 1;
+    if ((rc = launch_match(h, A, 1, C < 1 ? 1 : C))) return rc;
+    char *hres = h->h_res.as<char>();
+    B2_CUDA(cudaMemcpyAsync(hres, h->d_pose.p, 64, cudaMemcpyDeviceToHost, h->st));
+    B2_CUDA(cudaMemcpyAsync(hres + 64, h->d_res.p, sizeof(b2ndt_result), cudaMemcpyDeviceToHost, h->st));
+    B2_CUDA(cudaStreamSynchronize(h->st));
+    memcpy(pose_out, hres, 64);
+    if (res) memcpy(res, hres + 64, sizeof(b2ndt_result));
+    h->last_n = n;
+    h->last_src = src->d();
+    memcpy(h->last_pose, pose_out, 64);
+    h->have_last = true;
+    if (result_cloud) {
+        result_cloud->n = 0;
+        if ((rc = b2cloud_append_transformed(result_cloud, src, pose_out))) return rc;
+    }
+    return 0;
 }

@@ -6,6 +6,7 @@
 // All of this is HBM-bound integer / byte work: coalesced 16-byte point loads, one CTA per 4096-key
 // tile, no tensor cores.
 #include "b2_voxel.cuh"
+#include "b2_cloud.cuh"
 
 #include <float.h>
 #include <stdarg.h>
@@ -776,5 +777,54 @@ extern "C" int b2vf_filter_batch_device(b2vf *h, const void *d_in_f4, size_t n_t
     if ((rc = h->pipe.run((const float4 *)d_in_f4, h->leaf[0], h->leaf[1], h->leaf[2], 0, h->st))) return rc;
     if ((rc = vf_launch_centroids(h, (const float4 *)d_in_f4, (float4 *)d_out_f4, nullptr, nullptr, n_total))) return rc;
     B2_CUDA(cudaMemcpyAsync(d_out_offsets, h->pipe.run_seg_off(), (B + 1) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, h->st));
+    return 0;
+}
+
+// Device-resident VoxelFilter::Filter: src and dst are clouds in HBM (src == dst allowed, as the reference
+// calls Filter in place: matching.cpp:158, viewer.cpp:207).  Same results as b2vf_filter.
+extern "C" int b2vf_filter_cloud(b2vf *h, b2cloud *src, b2cloud *dst) {
+    if (!h || !src || !dst) { set_error("b2vf_filter_cloud: NULL argument"); return B2_ERR_INVALID; }
+    if (src->device != h->device || dst->device != h->device) { set_error("b2vf_filter_cloud: handle and clouds live on different devices"); return B2_ERR_INVALID; }
+    B2_CUDA(cudaSetDevice(h->device));
+    const size_t n = src->n;
+    if (n == 0) { dst->n = 0; return 0; }
+    int rc;
+    const bool in_place = (dst == src);
+    float4 *out;
+    if (in_place) {
+        if ((rc = h->d_out.reserve(n * 16))) return rc;
+        out = h->d_out.as<float4>();
+    } else {
+        dst->n = 0;
+        if ((rc = dst->reserve(n))) return rc;
+        out = dst->d();
+    }
+    if ((rc = h->h_misc.reserve(256))) return rc;
+    uint32_t off[2] = {0u, (uint32_t)n};
+    if ((rc = h->pipe.plan(off, 1, h->st))) return rc;
+    if ((rc = h->pipe.run(src->d(), h->leaf[0], h->leaf[1], h->leaf[2], 0, h->st))) return rc;
+    if ((rc = vf_launch_centroids(h, src->d(), out, nullptr, nullptr, n))) return rc;
+    uint32_t *misc = h->h_misc.as<uint32_t>();
+    B2_CUDA(cudaMemcpyAsync(misc, h->pipe.scalars(), 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->st));
+    B2_CUDA(cudaMemcpyAsync(misc + 8, h->pipe.layouts(), sizeof(VoxLayout), cudaMemcpyDeviceToHost, h->st));
+    B2_CUDA(cudaStreamSynchronize(h->st));
+    VoxLayout L;
+    memcpy(&L, misc + 8, sizeof(L));
+    if (!L.ok) {
+        if (L.n_finite == 0) { dst->n = 0; return 0; }
+        // PCL: "Leaf size is too small for the input dataset" -> output = *input
+        if (!in_place) {
+            B2_CUDA(cudaMemcpyAsync(dst->pts.p, src->pts.p, n * 16, cudaMemcpyDeviceToDevice, h->st));
+            B2_CUDA(cudaStreamSynchronize(h->st));
+        }
+        dst->n = n;
+        return 0;
+    }
+    const size_t M = misc[1];
+    if (in_place && M) {
+        B2_CUDA(cudaMemcpyAsync(src->pts.p, out, M * 16, cudaMemcpyDeviceToDevice, h->st));
+        B2_CUDA(cudaStreamSynchronize(h->st));
+    }
+    dst->n = M;
     return 0;
 }

@@ -42,6 +42,58 @@ def transform_cloud(cloud, T):
     return c
 
 
+class DeviceCloud:
+    """A point cloud resident in HBM (b2cloud of include/b2ndt.h): what CloudData::CLOUD_PTR becomes when the
+    callers either side of the hot path keep their clouds on the device."""
+
+    def __init__(self, cloud=None, device=0):
+        self._h = C.c_void_p()
+        capi.check(capi.lib().b2cloud_create(int(device), C.byref(self._h)))
+        if cloud is not None:
+            self.Upload(cloud)
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h and capi is not None and getattr(capi, "_LIB", None) is not None:
+            try:
+                capi._LIB.b2cloud_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    def __len__(self):
+        n = C.c_size_t(0)
+        capi.check(capi.lib().b2cloud_size(self._h, C.byref(n)))
+        return int(n.value)
+
+    def Upload(self, cloud):
+        a, ptr, n, stride, ioff = capi.cloud_args(cloud)
+        capi.check(capi.lib().b2cloud_upload(self._h, ptr, n, stride, ioff))
+        return self
+
+    def Download(self, layout=4):
+        """-> numpy (n,4) packed or (n,8) PointXYZI layout."""
+        n = len(self)
+        out = np.zeros((n, layout), np.float32)
+        m = C.c_size_t(0)
+        capi.check(capi.lib().b2cloud_download(self._h, out.ctypes.data, n, layout * 4, 12 if layout == 4 else 16, C.byref(m)))
+        return out[:m.value]
+
+    def Clear(self):
+        capi.check(capi.lib().b2cloud_clear(self._h))
+
+    def DevicePtr(self):
+        p = C.c_void_p()
+        capi.check(capi.lib().b2cloud_device_ptr(self._h, C.byref(p)))
+        return p.value
+
+    def AppendTransformed(self, src, pose):
+        """*this += pcl::transformPointCloud(src, pose)  (front_end.cpp:402-407)."""
+        T = capi.pose_to_colmajor(pose)
+        capi.check(capi.lib().b2cloud_append_transformed(self._h, src._h, capi._fp(T)))
+        return self
+
+
 class RegistrationInterface:
     def SetInputTarget(self, input_target):
         raise NotImplementedError
@@ -192,6 +244,24 @@ class NDTRegistration(RegistrationInterface):
     def Synchronize(self):
         capi.check(capi.lib().b2ndt_synchronize(self._h))
 
+    # device-resident clouds (DeviceCloud): same semantics as SetInputTarget / ScanMatch, no host round trip
+    def SetInputTargetCloud(self, target):
+        capi.check(capi.lib().b2ndt_set_target_cloud(self._h, target._h))
+        return True
+
+    def ScanMatchCloud(self, source, predict_pose, result_cloud=None):
+        """-> (True, result_cloud (DeviceCloud or None), result_pose)."""
+        g = capi.pose_to_colmajor(predict_pose)
+        out = np.zeros(16, np.float32)
+        res = capi.Result()
+        capi.check(capi.lib().b2ndt_align_cloud(self._h, source._h, capi._fp(g), capi._fp(out), C.byref(res),
+                                                result_cloud._h if result_cloud is not None else None))
+        pose = capi.colmajor_to_pose(out)
+        self.last_result = dict(iterations=res.iterations, converged=bool(res.converged), score=res.score,
+                                trans_probability=res.trans_probability, p=np.array(res.p[:]), passes=res.passes,
+                                mt_trials=res.mt_trials, pairs=res.pairs)
+        return True, result_cloud, pose
+
     # device-resident entry points (torch tensors' data_ptr()); asynchronous on the handle's stream
     def SetInputTargetDevice(self, d_ptr, n):
         capi.check(capi.lib().b2ndt_set_target_device(self._h, C.c_void_p(d_ptr), n))
@@ -202,6 +272,54 @@ class NDTRegistration(RegistrationInterface):
                                                        C.c_void_p(d_offsets) if d_offsets else None, B,
                                                        C.c_void_p(d_guesses), C.c_void_p(d_poses_out),
                                                        C.c_void_p(d_results) if d_results else None))
+
+
+def src_device(cloud):
+    return getattr(cloud, "device", 0)
+
+
+class BoxFilter(CloudFilterInterface):
+    """BoxFilter(node) with node["box_filter_size"] = [min_x, max_x, min_y, max_y, min_z, max_z] or BoxFilter(size)
+    (box_filter.cpp:12-24); SetSize / SetOrigin / GetEdge as box_filter.cpp:39-75; Filter = pcl::CropBox."""
+
+    def __init__(self, size=None, device=0):
+        if isinstance(size, dict):
+            size = size["box_filter_size"]
+        self.size_ = [0.0] * 6 if size is None else [float(np.float32(v)) for v in size]
+        self.origin_ = [0.0, 0.0, 0.0]
+        self.edge_ = [0.0] * 6
+        self.device = int(device)
+        self.CalculateEdge()
+
+    def SetSize(self, size):
+        self.size_ = [float(np.float32(v)) for v in size]
+        self.CalculateEdge()
+
+    def SetOrigin(self, origin):
+        self.origin_ = [float(np.float32(v)) for v in origin]
+        self.CalculateEdge()
+
+    def CalculateEdge(self):
+        for i in range(3):
+            self.edge_[2 * i] = float(np.float32(self.size_[2 * i]) + np.float32(self.origin_[i]))
+            self.edge_[2 * i + 1] = float(np.float32(self.size_[2 * i + 1]) + np.float32(self.origin_[i]))
+
+    def GetEdge(self):
+        return list(self.edge_)
+
+    def FilterCloud(self, src, dst=None):
+        """Device clouds in, device cloud out (order kept)."""
+        if dst is None:
+            dst = DeviceCloud(device=self.device)
+        e = np.asarray(self.edge_, np.float32)
+        capi.check(capi.lib().b2cloud_box_filter(src._h, capi._fp(e), dst._h))
+        return dst
+
+    def Filter(self, input_cloud):
+        """-> (True, cropped cloud) in the layout of the input."""
+        a = np.asarray(input_cloud)
+        out = self.FilterCloud(DeviceCloud(input_cloud, device=self.device)).Download(layout=a.shape[1])
+        return True, out
 
 
 class VoxelFilter(CloudFilterInterface):
@@ -242,6 +360,13 @@ class VoxelFilter(CloudFilterInterface):
 
     def SetStream(self, cuda_stream_ptr):
         capi.check(capi.lib().b2vf_set_stream(self._h, C.c_void_p(cuda_stream_ptr) if cuda_stream_ptr else None))
+
+    def FilterCloud(self, src, dst=None):
+        """Device cloud in, device cloud out; dst may be src (in place, matching.cpp:158)."""
+        if dst is None:
+            dst = DeviceCloud(device=src_device(src))
+        capi.check(capi.lib().b2vf_filter_cloud(self._h, src._h, dst._h))
+        return dst
 
     def FilterBatchDevice(self, d_in, n_total, h_offsets, d_out, d_out_offsets):
         off = np.ascontiguousarray(h_offsets, np.uint32)

@@ -350,3 +350,29 @@ def fitness_score(target, src, pose, max_range=np.finfo(np.float64).max):
     cs, ks = as_cloud(src)
     P = np.ascontiguousarray(np.asarray(pose, np.float32).reshape(4, 4).flatten(order="F"))
     return lib().orc_fitness_score(ct, cs, _fp(P), max_range)
+
+
+def box_filter(cloud, edge):
+    """pcl::CropBox as BoxFilter::Filter configures it (lidar_localization/src/models/cloud_filter/box_filter.cpp:27-37):
+    identity box pose, min = (edge[0], edge[2], edge[4]), max = (edge[1], edge[3], edge[5]); a finite point is kept
+    unless a coordinate is < min or > max (PCL 1.7 crop_box.hpp applyFilter), input order kept.  TEST ORACLE."""
+    c = np.ascontiguousarray(cloud, dtype=np.float32)
+    e = np.asarray(edge, np.float32)
+    xyz = c[:, :3]
+    fin = np.isfinite(xyz).all(axis=1)
+    lo = np.array([e[0], e[2], e[4]], np.float32)
+    hi = np.array([e[1], e[3], e[5]], np.float32)
+    with np.errstate(invalid="ignore"):
+        keep = fin & ~((xyz < lo).any(axis=1) | (xyz > hi).any(axis=1))
+    return c[keep].copy()
+
+
+def transform_cloud(cloud, T):
+    """pcl::transformPointCloud on PointXYZI with a float 4x4 (front_end.cpp:402-407): xyz through transform_points
+    (the float expression pinned against the vendored Eigen), intensity copied, non-finite points copied unchanged.
+    TEST ORACLE."""
+    c = np.array(cloud, dtype=np.float32, copy=True)
+    fin = np.isfinite(c[:, :3]).all(axis=1)
+    if fin.any():
+        c[fin, :3] = transform_points(np.asarray(T, np.float32).reshape(4, 4), c[fin, :3])
+    return c

@@ -7,6 +7,7 @@
 #include <memory>
 #include <vector>
 
+#include "lidar_localization/models/cloud_filter/box_filter.hpp"
 #include "lidar_localization/models/cloud_filter/voxel_filter.hpp"
 #include "lidar_localization/models/registration/ndt_registration.hpp"
 
@@ -53,6 +54,21 @@ int main(int argc, char** argv) {
     std::printf("M %zu\nPOSE", filtered->points.size());
     for (int i = 0; i < 16; ++i) std::printf(" %.9g", pose.data()[i]);
     std::printf("\nFIT %.9g\nITER %d\n", fit, static_cast<NDTRegistration*>(registration.get())->LastResult().iterations);
+    // BoxFilter as matching.cpp:166-183 uses it: SetSize, SetOrigin at the pose, Filter, GetEdge
+    {
+        BoxFilter box(std::vector<float>{-20.f, 20.f, -15.f, 15.f, -2.f, 10.f});
+        box.SetOrigin(std::vector<float>{pose(0, 3), pose(1, 3), pose(2, 3)});
+        CloudData::CLOUD_PTR cropped(new CloudData::CLOUD());
+        box.Filter(target, cropped);
+        std::vector<float> e = box.GetEdge();
+        size_t expect = 0;
+        double sx = 0.0;
+        for (const auto& p : target->points)
+            if (!(p.x < e[0] || p.y < e[2] || p.z < e[4] || p.x > e[1] || p.y > e[3] || p.z > e[5])) { ++expect; sx += p.x; }
+        double gx = 0.0;
+        for (const auto& p : cropped->points) gx += p.x;
+        std::printf("BOX %zu %zu %.9g %.9g\n", cropped->points.size(), expect, gx, sx);
+    }
     // result cloud = source under the final pose
     if (result->points.size() != filtered->points.size()) return 1;
     std::printf("R0 %.9g %.9g %.9g %.9g\n", result->points[0].x, result->points[0].y, result->points[0].z, result->points[0].intensity);

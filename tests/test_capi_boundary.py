@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_header_symbols_are_exported():
     hdr = open(os.path.join(ROOT, "include", "b2ndt.h")).read()
-    declared = set(re.findall(r"\b(b2(?:ndt|vf)?_[a-z0-9_]+)\s*\(", hdr))
+    declared = set(re.findall(r"\b(b2(?:ndt|vf|cloud)?_[a-z0-9_]+)\s*\(", hdr))
     declared.discard("b2_status")
     assert declared == set(capi.EXPORTS), declared ^ set(capi.EXPORTS)
     path = build.build_cuda()
@@ -49,6 +49,9 @@ def test_no_cpu_fallback_without_gpu():
     assert e.value.code == capi.B2_ERR_CUDA and "no CPU fallback" in str(e.value)
     with pytest.raises(capi.B2Error):
         VoxelFilter(1.3, 1.3, 1.3)
+    from lidar_slam_b200.registration import DeviceCloud
+    with pytest.raises(capi.B2Error):
+        DeviceCloud()
 
 
 def test_invalid_arguments_are_rejected_before_any_cuda_call():

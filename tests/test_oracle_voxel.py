@@ -111,3 +111,28 @@ def test_target_grid_semantics(oracle, small_map):
         slots, dd = g.radius_search(q)
         assert sorted(slots.tolist()) == sorted(want.tolist())
         assert np.all(np.diff(dd) >= 0)
+
+
+def test_box_filter_oracle_semantics():
+    """pcl::CropBox as BoxFilter uses it: inclusive bounds, order kept, non-finite points dropped."""
+    from oracle import oracle as O
+    rng = np.random.default_rng(11)
+    c = (rng.uniform(-10, 10, size=(5000, 4))).astype(np.float32)
+    c[5, 1] = np.nan
+    edge = [-3.0, 4.0, -2.0, 2.0, -1.0, 8.0]
+    out = O.box_filter(c, edge)
+    keep = [i for i in range(len(c)) if np.isfinite(c[i, :3]).all() and edge[0] <= c[i, 0] <= edge[1]
+            and edge[2] <= c[i, 1] <= edge[3] and edge[4] <= c[i, 2] <= edge[5]]
+    assert np.array_equal(out, c[keep])
+    on_edge = np.array([[-3.0, -2.0, -1.0, 0.5], [4.0, 2.0, 8.0, 0.25]], np.float32)
+    assert np.array_equal(O.box_filter(on_edge, edge), on_edge)
+    assert O.box_filter(np.zeros((0, 4), np.float32), edge).shape == (0, 4)
+
+
+def test_transform_cloud_oracle_keeps_intensity_and_nonfinite():
+    from oracle import oracle as O
+    c = np.array([[1, 2, 3, 0.5], [np.nan, 0, 0, 0.7]], np.float32)
+    T = np.eye(4, dtype=np.float32); T[:3, 3] = [1, 1, 1]
+    out = O.transform_cloud(c, T)
+    assert np.array_equal(out[0], np.array([2, 3, 4, 0.5], np.float32))
+    assert np.isnan(out[1, 0]) and out[1, 3] == np.float32(0.7)

@@ -22,7 +22,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from lidar_slam_b200 import synth  # noqa: E402
-from lidar_slam_b200.registration import NDTRegistration, VoxelFilter, transform_cloud  # noqa: E402
+from lidar_slam_b200.registration import BoxFilter, DeviceCloud, NDTRegistration, VoxelFilter, transform_cloud  # noqa: E402
 from oracle import oracle as O  # noqa: E402
 
 
@@ -83,13 +83,15 @@ class FrontEnd:
         self.key_dist, self.local_frames = key_dist, local_frames
         self.keyframes = []           # (pose, unfiltered cloud)
         self.pose = None; self.last = None; self.predict = None; self.last_key = None
-        self.t_match, self.t_target = [], []
+        self.t_match, self.t_target, self.t_assemble = [], [], []
 
     def _new_keyframe(self, cloud, pose):
         self.keyframes.append((pose.copy(), cloud))
         if len(self.keyframes) > self.local_frames:
             self.keyframes.pop(0)
+        t0 = time.perf_counter()
         local = np.concatenate([transform_cloud(c, T) for T, c in self.keyframes], axis=0)
+        self.t_assemble.append(1e3 * (time.perf_counter() - t0))
         t = time.perf_counter()
         if len(self.keyframes) >= 10:
             local = self.local_filt(local)
@@ -114,6 +116,52 @@ class FrontEnd:
         return pose
 
 
+class FrontEndDevice(FrontEnd):
+    """The same front end with every cloud resident in HBM: the raw frame is uploaded once,
+    key frames stay on the device, the local map is assembled (AppendTransformed), filtered (FilterCloud, in
+    place) and handed to SetInputTargetCloud without a host round trip."""
+
+    def __init__(self, vf, lvf, reg, key_dist=2.0, local_frames=20):
+        super().__init__(None, None, None, None, key_dist, local_frames)
+        self.vf, self.lvf, self.reg = vf, lvf, reg
+        self.local = DeviceCloud()
+        self.filtered = DeviceCloud()
+        self.t_upload = []
+
+    def _new_keyframe(self, cloud, pose):
+        self.keyframes.append((pose.copy(), cloud))
+        if len(self.keyframes) > self.local_frames:
+            self.keyframes.pop(0)
+        t0 = time.perf_counter()
+        self.local.Clear()
+        for T, c in self.keyframes:
+            self.local.AppendTransformed(c, T)
+        self.t_assemble.append(1e3 * (time.perf_counter() - t0))
+        t = time.perf_counter()
+        if len(self.keyframes) >= 10:
+            self.lvf.FilterCloud(self.local, self.local)
+        self.reg.SetInputTargetCloud(self.local)
+        self.t_target.append(1e3 * (time.perf_counter() - t))
+        self.last_key = pose.copy()
+
+    def update(self, cloud, init_pose):
+        t = time.perf_counter(); d_cloud = DeviceCloud(cloud); self.t_upload.append(1e3 * (time.perf_counter() - t))
+        if self.pose is None:
+            self.pose = init_pose.astype(np.float32).copy(); self.last = self.pose.copy(); self.predict = self.pose.copy()
+            self._new_keyframe(d_cloud, self.pose)
+            return self.pose
+        t = time.perf_counter()
+        self.vf.FilterCloud(d_cloud, self.filtered)
+        pose = self.reg.ScanMatchCloud(self.filtered, self.predict)[2]
+        self.t_match.append(1e3 * (time.perf_counter() - t))          # frame filter + ScanMatch, both on the device
+        step = np.linalg.inv(self.last.astype(np.float64)) @ pose.astype(np.float64)
+        self.predict = (pose.astype(np.float64) @ step).astype(np.float32)
+        self.last = pose.copy(); self.pose = pose
+        if np.sum(np.abs(self.last_key[:3, 3] - pose[:3, 3])) > self.key_dist:
+            self._new_keyframe(d_cloud, pose)
+        return pose
+
+
 def config2(scene, frames, oracle_frames):
     s = 60.0 + 1.0 * np.arange(frames)
     truth = np.stack([scene.path_pose(v) for v in s])
@@ -124,6 +172,10 @@ def config2(scene, frames, oracle_frames):
                   lambda src, g: reg.ScanMatch(src, g, want_cloud=False)[2])
     T0 = synth.pose6_to_matrix(truth[0])
     traj = [fe.update(scans[k], T0) for k in range(frames)]
+    # the same run with device-resident clouds
+    fed = FrontEndDevice(VoxelFilter(1.3, 1.3, 1.3), VoxelFilter(0.6, 0.6, 0.6), NDTRegistration(**PRM))
+    trajd = [fed.update(scans[k], T0) for k in range(frames)]
+    dev_equal = all(np.array_equal(a, b) for a, b in zip(traj, trajd))
     # oracle on the first oracle_frames frames
     state = {}
 
@@ -138,6 +190,12 @@ def config2(scene, frames, oracle_frames):
     err_truth = [float(np.linalg.norm(traj[k][:3, 3] - synth.pose6_to_matrix(truth[k])[:3, 3])) for k in range(frames)]
     return {"frames": frames, "key_frames": len(fe.t_target), "scan_match_ms": {"p50": pct(fe.t_match, 50), "p99": pct(fe.t_match, 99)},
             "target_rebuild_ms": {"p50": pct(fe.t_target, 50), "max": max(fe.t_target)},
+            "local_map_assemble_host_ms_p50": pct(fe.t_assemble, 50),
+            "device_resident": {"frame_upload_ms_p50": pct(fed.t_upload, 50),
+                                "filter_plus_scan_match_ms": {"p50": pct(fed.t_match, 50), "p99": pct(fed.t_match, 99)},
+                                "local_map_assemble_ms_p50": pct(fed.t_assemble, 50),
+                                "filter_plus_set_target_ms": {"p50": pct(fed.t_target, 50), "max": max(fed.t_target)},
+                                "trajectory_identical_to_host_path": bool(dev_equal)},
             "oracle": {"frames": len(otraj), "scan_match_ms_p50": pct(ofe.t_match, 50), "target_rebuild_ms_p50": pct(ofe.t_target, 50),
                        "max_traj_dt_m": dt, "max_traj_dR": dR},
             "drift_vs_truth_m": {"final": err_truth[-1], "max": max(err_truth)}}
@@ -145,9 +203,11 @@ def config2(scene, frames, oracle_frames):
 
 # ---------------------------------------------------------------------------------------------- config 3
 def box_crop(cloud, origin, size=100.0):
-    lo, hi = origin - size, origin + size
-    m = np.all((cloud[:, :3] >= lo) & (cloud[:, :3] <= hi), axis=1)
-    return cloud[m]
+    """host-side pcl::CropBox with BoxFilter's float edges (box_filter.cpp:63-70)."""
+    o = np.asarray(origin, np.float32)
+    edge = [np.float32(-size) + o[0], np.float32(size) + o[0], np.float32(-size) + o[1], np.float32(size) + o[1],
+            np.float32(-size) + o[2], np.float32(size) + o[2]]
+    return O.box_filter(cloud, edge)
 
 
 def config3(scene, frames, oracle_frames, map_points):
@@ -160,6 +220,18 @@ def config3(scene, frames, oracle_frames, map_points):
     reg = NDTRegistration(**PRM)
     origin = truth[0][:3].copy()
     t = time.perf_counter(); local = box_crop(fmap, origin); reg.SetInputTarget(local); t_reset = [1e3 * (time.perf_counter() - t)]
+    # device-resident global map: BoxFilter crop + SetInputTarget without host copies
+    d_map = DeviceCloud(fmap); d_local = DeviceCloud(); box = BoxFilter([-100.0, 100.0, -100.0, 100.0, -100.0, 100.0])
+    reg_d = NDTRegistration(**PRM)
+    t_reset_dev, dev_same = [], []
+
+    def reset_dev(org):
+        t = time.perf_counter()
+        box.SetOrigin(org); box.FilterCloud(d_map, d_local); reg_d.SetInputTargetCloud(d_local)
+        t_reset_dev.append(1e3 * (time.perf_counter() - t))
+        dev_same.append(bool(reg_d.TargetInfo() == reg.TargetInfo() and len(d_local) == len(local)))
+
+    reset_dev(origin)
     grid = O.Grid(local, 1.0)
     pose = synth.pose6_to_matrix(truth[0] + np.array([0.2, -0.2, 0.05, 0, 0, 0.01])).astype(np.float32)
     last = pose.copy(); predict = pose.copy()
@@ -176,11 +248,13 @@ def config3(scene, frames, oracle_frames, map_points):
         if np.any(np.abs(pose[:3, 3] - origin) > 50.0):      # within 50 m of a box edge -> re-crop (matching.cpp:255-262)
             origin = pose[:3, 3].astype(np.float64).copy()
             t = time.perf_counter(); local = box_crop(fmap, origin); reg.SetInputTarget(local); t_reset.append(1e3 * (time.perf_counter() - t))
+            reset_dev(origin)
             if k < oracle_frames:
                 grid = O.Grid(local, 1.0)
     return {"map_points": len(gmap), "map_filtered": len(fmap), "map_filter_ms": t_mapfilter, "local_map_points": len(local),
             "frames": frames, "frame_filter_ms_p50": pct(t_filter, 50), "scan_match_ms": {"p50": pct(t_match, 50), "p99": pct(t_match, 99)},
-            "reset_local_map_ms": t_reset, "oracle": {"frames": len(o_ms), "scan_match_ms_p50": pct(o_ms, 50),
+            "reset_local_map_ms": t_reset, "reset_local_map_device_resident_ms": t_reset_dev[1:] or t_reset_dev,
+            "device_target_identical": all(dev_same), "oracle": {"frames": len(o_ms), "scan_match_ms_p50": pct(o_ms, 50),
                                                       "max_dt_m": max(dts) if dts else None, "max_dR": max(dRs) if dRs else None},
             "err_vs_truth_m": {"p50": pct(errs, 50), "max": max(errs)}}
 
