@@ -11,7 +11,7 @@
 //   pts_sorted  float4[N]      target points permuted into voxel order (fitness NN buckets)
 //   leaf_idx    int32[V]       voxel linear index, ascending;  leaf_n int32[V];  leaf_start uint32[V]
 //   centroid4   float4[V]      float centroid (the kd-tree search point of PCL), intensity mean in .w
-//   gauss       double[10][V]  80-byte records {mean[3], icov xx,xy,xz,yy,yz,zz, pad}
+//   gauss       double[12][V]  96-byte records {mean[3], icov xx | xy,xz,yy,yz | zz, pad[3]}: two 256-bit loads + one 64-bit
 //   cells       float4[ncells] dense grid record {centroid x,y,z, code}: code = +(leaf+1) searchable (n >= min_pts),
 //                              -(leaf+1) sparse, 0 empty
 //   nbr_head    uint2[ncells]  {first entry, count} of the cell's neighbour list
@@ -95,6 +95,7 @@ __global__ void __launch_bounds__(256) leaf_stats_kernel(const float4 *__restric
 // One thread per voxel: mean, single-pass covariance, eigen inflation, inverse (leaf_finish), the
 // 80-byte gather record, and the dense-grid entry.
 struct LayoutArg { int32_t min_b[3], div_b[3]; float inv[3]; float res; };
+constexpr int GAUSS_STRIDE = 12;     // doubles per voxel record (96 bytes, 32-byte aligned)
 
 // Can the leaf with float centroid (cx,cy,cz) be within the search radius of ANY query that falls into
 // cell (kx,ky,kz)?  Distance from the centroid to the cell's box, against the radius plus a generous slack
@@ -131,10 +132,10 @@ __global__ void __launch_bounds__(128) leaf_finish_kernel(uint32_t V, int min_pt
     // a leaf that fails PCL's eigenvalue checks (nr_points = -1) stays in the centroid kd-tree with the
     // icov_ it has at that moment (zero, or the non-finite inverse), exactly what leaf_finish leaves here
     (void)leaf_finish(sum, acc, n, min_pts, eig_mult, mean, cov, icov, ev);
-    double *g = gauss + (size_t)j * 10;
+    double *g = gauss + (size_t)j * GAUSS_STRIDE;
     g[0] = mean[0]; g[1] = mean[1]; g[2] = mean[2];
     g[3] = icov[0]; g[4] = icov[1]; g[5] = icov[2]; g[6] = icov[4]; g[7] = icov[5]; g[8] = icov[8];
-    g[9] = 0.0;
+    g[9] = 0.0; g[10] = 0.0; g[11] = 0.0;
     double *ic = icov9 + (size_t)j * 9;
     for (int a = 0; a < 9; ++a) ic[a] = icov[a];
     const bool tree = n >= min_pts;
@@ -336,33 +337,50 @@ struct MatchArgs {
     b2ndt_result *results;       // B
     double *acc_out;             // B*ACC_N (deriv-only mode)
     int deriv_only;
-    unsigned long long *timing;  // NDT_TIMING builds only: per-phase SM-cycle totals (tools/ sweeps)
+    unsigned long long *timing;  // NDT_TIMING builds only (tools/ sweeps): per-phase SM-cycle totals of the batch kernel
 };
 
 #ifdef NDT_TIMING
-#define TM_NOW() clock64()
-#define TM_ADD(slot, t0) do { if (lane == 0) tm[slot] += (unsigned long long)(clock64() - (t0)); } while (0)
-#define TM_EV(k) do { if (lane == 0 && blockIdx.x == 0 && pass_id <= 4 && A.timing) A.timing[32 + (pass_id - 1) * 16 + (k)] = (unsigned long long)clock64(); } while (0)
+#define TMB_DECL unsigned long long tmb[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long tmb_t = clock64(); (void)tmb_t
+#define TMB_LAP(k) do { const long long _n = clock64(); tmb[k] += (unsigned long long)(_n - tmb_t); tmb_t = _n; } while (0)
+#define TMB_FLUSH(base, cond) do { if ((cond) && lane == 0 && A.timing) for (int _k = 0; _k < 8; ++_k) atomicAdd(&A.timing[(base) + _k], tmb[_k]); } while (0)
 #else
-#define TM_NOW() 0ll
-#define TM_ADD(slot, t0) do { (void)(t0); } while (0)
-#define TM_EV(k) do { } while (0)
+#define TMB_DECL do { } while (0)
+#define TMB_LAP(k) do { } while (0)
+#define TMB_FLUSH(base, cond) do { } while (0)
 #endif
 
-struct NdtSmem {
+
+#ifndef NDT_SLOTS_N
+#define NDT_SLOTS_N 2
+#endif
+constexpr int NDT_SLOTS = NDT_SLOTS_N;          // matches in flight per CTA (batch kernel)
+static_assert(NDT_SLOTS <= NDT_NCW, "slot s is controlled by compute warp s");
+
+struct Slot {                      // one match in flight
     Ctl ctl;
     double warp_part[NDT_NCW][NACC];
-    double cta_part[2][NACC];      // double-buffered per-CTA partial, read by cluster peers over DSMEM
+    double cta_part[2][NACC];      // cluster mode: double-buffered per-CTA partial, read by cluster peers over DSMEM
     double raw_total[NACC];        // reduced pair sums (NACC layout)
     double total[ACC_N];           // contracted with the angle tables: what the controller consumes
     double trig_d[6];              // snapped double sin x3, cos x3 of the requested pose
     float  trig_f[6];              // float sin x3, cos x3
+    uint32_t first, last;          // source range of the match
+    uint32_t match;                // match index
+    uint32_t seq;                  // batch kernel: passes requested so far for this slot (monotonic)
+    uint32_t dead;                 // batch kernel: no more work for this slot
     int go;
-    int pad_;
+};
+
+struct NdtSmem {
+    Slot slot[NDT_SLOTS];
     // producer -> consumer rings (monotonic counters, never reset)
     uint32_t tail[NDT_NSW];        // entries produced by search warp s
     uint32_t head[NDT_NSW];        // entries consumed from search warp s
-    uint32_t finished[NDT_NSW];    // last pass id search warp s has completed
+    uint32_t finished[NDT_NSW];    // passes search warp s has completed
+    uint32_t pass_end[NDT_NSW][4]; // ring position at which pass p of search warp s ended (p & 3); producers run at
+                                   // most two passes ahead of the consumers
+    uint32_t pass_dead[NDT_NSW][4];// batch kernel: "pass" p is only the marker that its slot has no more work
     float4 ring[NDT_NSW][RING];    // (source point x, y, z, leaf index): consumers never touch the source cloud
     float4 stage[NDT_NSW][192];    // per search warp, three slots: [lane] source point, [32 + lane] transformed point
 };
@@ -405,11 +423,13 @@ __device__ __forceinline__ void ndt_pair(const float px, const float py, const f
                                          double *acc) {
     float tx, ty, tz;
     transform_f32(T, px, py, pz, tx, ty, tz);
-    const double2 *g2 = reinterpret_cast<const double2 *>(g);      // 80-byte record, five 16-byte loads
-    const double2 a0 = __ldg(g2 + 0), a1 = __ldg(g2 + 1), a2 = __ldg(g2 + 2), a3 = __ldg(g2 + 3), a4 = __ldg(g2 + 4);
+    // 96-byte record: two 256-bit loads (LDG.E.256, sm_100) + one 64-bit load = 3 L1 requests instead of 5
+    double mx, my, mz, ixx, ixy, ixz, iyy, iyz, izz;
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(mx), "=d"(my), "=d"(mz), "=d"(ixx) : "l"(g));
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(ixy), "=d"(ixz), "=d"(iyy), "=d"(iyz) : "l"(g + 4));
+    izz = __ldg(g + 8);
     acc[34] += 1.0;
-    const double xq = (double)tx - a0.x, yq = (double)ty - a0.y, zq = (double)tz - a1.x;
-    const double ixx = a1.y, ixy = a2.x, ixz = a2.y, iyy = a3.x, iyz = a3.y, izz = a4.x;
+    const double xq = (double)tx - mx, yq = (double)ty - my, zq = (double)tz - mz;
     const double q0 = ixx * xq + ixy * yq + ixz * zq;
     const double q1 = ixy * xq + iyy * yq + iyz * zq;
     const double q2 = ixz * xq + iyz * yq + izz * zq;
@@ -541,8 +561,8 @@ __device__ __noinline__ double warp_lu_solve6(const double *__restrict__ H, cons
     return singular ? 0.0 : pmin / pmax;
 }
 
-// warp 0 completes a pass request: the twelve sin/cos evaluations run on twelve lanes
-__device__ __forceinline__ void finish_request_warp0(NdtSmem &S, int lane) {
+// a warp completes a pass request: the twelve sin/cos evaluations run on twelve lanes
+__device__ __forceinline__ void finish_request_warp(Slot &S, int lane) {
     __syncwarp();
     if (S.ctl.need_trig) {
         if (lane < 12) {
@@ -559,83 +579,96 @@ __device__ __forceinline__ void finish_request_warp0(NdtSmem &S, int lane) {
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(NDT_THREADS, NDT_MIN_CTAS) ndt_match_kernel(GridView G, NdtConst K, MatchArgs A) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    NdtSmem &S = *reinterpret_cast<NdtSmem *>(smem_raw);
-    cg::cluster_group cluster = cg::this_cluster();
-    const unsigned C = cluster.num_blocks();
-    const unsigned crank = cluster.block_rank();
-    const unsigned match = blockIdx.x / C;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const bool is_compute = warp < NDT_NCW;
-    const uint32_t lt = (1u << lane) - 1u;
-
-    uint32_t first = 0, last = A.n_shared;
-    if (A.offsets) { first = A.offsets[match]; last = A.offsets[match + 1]; }
-    const uint32_t npts = last - first;
-
-    if (tid < NDT_NSW) { S.tail[tid] = 0u; S.head[tid] = 0u; S.finished[tid] = 0u; }
-    if (warp == 0) {
-        if (lane == 0) {
-            if (A.deriv_only) {
-                const double *p = A.poses6 + (size_t)match * 6;
-                for (int i = 0; i < 6; ++i) S.ctl.p[i] = S.ctl.x_t[i] = p[i];
-                ctl_request(S.ctl, p, 1, ST_INIT);
-                S.ctl.passes = 0; S.ctl.pairs = 0;
-            } else {
-                ctl_start(S.ctl, K, A.guesses + (size_t)match * 16, (double)npts);
-            }
-            S.go = 1;
-        }
-        finish_request_warp0(S, lane);
-    }
-    __syncthreads();
-
-    const uint32_t stride = C * NDT_NSW * 32u;
-    // The two roles never share code after this point (ptxas sizes each branch for its own register
-    // budget); they meet at CTA-wide barriers issued from both branches.
-    if (!is_compute) {
-        // =========================== search warps (producers) ===========================
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(NDT_REG_SEARCH));
-        const int sw = warp - NDT_NCW;
-        float4 *ring = S.ring[sw];
-        uint32_t pass_id = 0;
-        uint32_t my_tail = 0;                       // entries produced so far (warp-uniform)
-        uint32_t hd_seen = 0;                       // last consumer position read (warp-uniform)
-#ifdef NDT_TIMING
-        unsigned long long tm[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        const long long t_life = clock64();
-#endif
-        // wait until the ring has room for `need` more entries
-        auto ring_room = [&](uint32_t need) {
-            if (my_tail - hd_seen > RING - need) {
-                const long long tw = TM_NOW();
-                uint32_t hd = 0;
-                if (lane == 0) {
-                    hd = ld_vol(&S.head[sw]);
-                    while (my_tail - hd > RING - need) { __nanosleep(64); hd = ld_vol(&S.head[sw]); }
+// One warp runs the controller of a slot on the reduced sums S.raw_total: contraction with the angle tables,
+// serial halves on lane 0, the 6x6 Newton solve on the whole warp, then the next pass request.  Returns 1
+// when another pass was requested (S.ctl.T / ang / hess describe it), 0 when the match is finished.
+__device__ __forceinline__ int controller_step(Slot &S, const NdtConst &K, int deriv_only, int lane) {
+    if (lane < ACC_N) S.total[lane] = acc_finish(S.raw_total, S.ctl.ang, lane);
+    __syncwarp();
+    int code = CTL_DONE;
+    if (!deriv_only) {
+        if (lane == 0) code = ctl_pre(S.ctl, K, S.total);
+        code = __shfl_sync(0xffffffffu, code, 0);
+        for (int guard = 0; guard < 8 && code == CTL_NEWTON; ++guard) {
+            __syncwarp();
+            double delta[6];
+            const double rc = warp_lu_solve6(S.ctl.H, S.ctl.g, lane, delta);
+            if (lane == 0) {
+                bool fin = true;
+#pragma unroll
+                for (int i = 0; i < 6; ++i) fin = fin && (delta[i] == delta[i]) && (fabs(delta[i]) <= DBL_MAX);
+                if (K.force_svd || !(rc > 1e-9 && fin)) {
+                    // (near-)singular Hessian: Eigen's JacobiSVD solve with its rank truncation
+                    double neg_g[6];
+                    for (int i = 0; i < 6; ++i) neg_g[i] = -S.ctl.g[i];
+                    svd_solve6(S.ctl.H, neg_g, delta);
                 }
-                hd_seen = __shfl_sync(0xffffffffu, hd, 0);
-                TM_ADD(1, tw);
+                code = ctl_post_newton(S.ctl, K, delta);
             }
-        };
-        // Software pipeline over rounds of 32 points: while round r is searched, the neighbour-list header
-        // of round r+1 and the source points of round r+2 are in flight.
-        //   prepare(b, pt, buf): transform the points of the round starting at b, park (point, transformed
-        //   point) in stage buffer `buf`, and issue the header load -> (off, cnt); cnt = IRREGULAR marks a
-        //   lane that needs the dense-window fallback (4-cell window or centre cell outside the grid).
-        constexpr uint32_t IRREGULAR = 0xffffffffu;
-        const uint32_t b0 = first + (crank * NDT_NSW + sw) * 32u;
-        auto load_pt = [&](uint32_t b) {
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (b < last && b + lane < last) v = __ldg(&A.src[b + lane]);
-            return v;
-        };
-        while (true) {
-            ++pass_id;
-            const float *T = S.ctl.T;
-            const long long t_pass = TM_NOW();
-            if (sw == 0) TM_EV(0);
+            code = __shfl_sync(0xffffffffu, code, 0);
+        }
+        if (code == CTL_NEWTON) { code = CTL_DONE; if (lane == 0) S.ctl.state = ST_DONE; }
+    }
+    const int go = (code == CTL_PASS) ? 1 : 0;
+    __syncwarp();
+    if (go) finish_request_warp(S, lane);
+    return go;
+}
+
+__device__ __forceinline__ void write_result(const Slot &S, const MatchArgs &A, size_t match) {
+    for (int i = 0; i < 16; ++i) A.poses_out[match * 16 + i] = S.ctl.finalT[i];
+    if (A.results) {
+        b2ndt_result r;
+        r.iterations = S.ctl.nr_iter; r.converged = S.ctl.converged;
+        r.score = S.ctl.score; r.trans_probability = S.ctl.trans_probability;
+        for (int i = 0; i < 6; ++i) r.p[i] = S.ctl.p[i];
+        r.passes = S.ctl.passes; r.mt_trials = S.ctl.mt_trials; r.pairs = S.ctl.pairs;
+        A.results[match] = r;
+    }
+}
+
+// ---------------------------------------------------------------- search warps (producers) -----
+// One derivative pass of one search warp over its share of the source points [first, last): lane = source
+// point; neighbour lists walked warp-cooperatively; hits appended to the warp's ring.  The end of the pass is
+// published through finished[sw].
+struct SearchState {
+    uint32_t my_tail = 0;      // entries produced so far (warp-uniform)
+    uint32_t hd_seen = 0;      // last consumer position read (warp-uniform)
+    uint32_t pass_id = 0;      // passes produced so far
+};
+
+__device__ __forceinline__ void search_pass(NdtSmem &S, const GridView &G, const float4 *__restrict__ src, uint32_t first,
+                                            uint32_t last, uint32_t b0, uint32_t stride, const float *T, int sw, int lane,
+                                            SearchState &st) {
+    (void)first;
+    const uint32_t lt = (1u << lane) - 1u;
+    float4 *ring = S.ring[sw];
+    float4 *stage_all = S.stage[sw];
+    uint32_t my_tail = st.my_tail, hd_seen = st.hd_seen;
+    ++st.pass_id;
+    // wait until the ring has room for `need` more entries
+    auto ring_room = [&](uint32_t need) {
+        if (my_tail - hd_seen > RING - need) {
+            uint32_t hd = 0;
+            if (lane == 0) {
+                hd = ld_vol(&S.head[sw]);
+                while (my_tail - hd > RING - need) { __nanosleep(64); hd = ld_vol(&S.head[sw]); }
+            }
+            hd_seen = __shfl_sync(0xffffffffu, hd, 0);
+        }
+    };
+    // Software pipeline over rounds of 32 points: while round r is searched, the neighbour-list header
+    // of round r+1 and the source points of round r+2 are in flight.
+    //   prepare(b, pt, buf): transform the points of the round starting at b, park (point, transformed
+    //   point) in stage buffer `buf`, and issue the header load -> (off, cnt); cnt = IRREGULAR marks a
+    //   lane that needs the dense-window fallback (4-cell window or centre cell outside the grid).
+    constexpr uint32_t IRREGULAR = 0xffffffffu;
+    auto load_pt = [&](uint32_t b) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (b < last && b + lane < last) v = __ldg(&src[b + lane]);
+        return v;
+    };
+    {
             auto prepare = [&](uint32_t b, const float4 pt, int buf, uint32_t &off, uint32_t &cnt) {
                 off = 0u; cnt = 0u;
                 float tx = 0.f, ty = 0.f, tz = 0.f;
@@ -664,8 +697,8 @@ __global__ void __launch_bounds__(NDT_THREADS, NDT_MIN_CTAS) ndt_match_kernel(Gr
                         }
                     }
                 }
-                S.stage[sw][buf * 64 + lane] = pt;
-                S.stage[sw][buf * 64 + 32 + lane] = make_float4(tx, ty, tz, 0.f);
+                stage_all[buf * 64 + lane] = pt;
+                stage_all[buf * 64 + 32 + lane] = make_float4(tx, ty, tz, 0.f);
             };
             // three rounds in flight: r (searched now), r+1 (header loaded, its list lines being pulled into
             // L1), r+2 (points loaded, header load issued); stage slot = round % 3
@@ -688,7 +721,7 @@ __global__ void __launch_bounds__(NDT_THREADS, NDT_MIN_CTAS) ndt_match_kernel(Gr
                     prepare(base + 2u * stride, pt_3, slot2, off_2, cnt_2);
                     pt_3 = load_pt(base + 3u * stride);
                 }
-                const float4 *stage = &S.stage[sw][slot * 64];
+                const float4 *stage = &stage_all[slot * 64];
                 const bool irregular = (cnt == IRREGULAR);
                 if (irregular) cnt = 0u;
                 // ---- regular lanes: the warp walks the concatenation of its 32 neighbour lists, 32 entries
@@ -799,50 +832,53 @@ __global__ void __launch_bounds__(NDT_THREADS, NDT_MIN_CTAS) ndt_match_kernel(Gr
                 }
                 off = off_1; cnt = cnt_1; off_1 = off_2; cnt_1 = cnt_2;
             }
-            // publish the end of this warp's stream for this pass
-            __syncwarp();
-            if (lane == 0) { __threadfence_block(); st_vol(&S.tail[sw], my_tail); __threadfence_block(); st_vol(&S.finished[sw], pass_id); }
-            TM_ADD(0, t_pass);
-            if (sw == 0) TM_EV(1);
-            cta_barrier();                          // (1) all pairs of the pass consumed, partials written
-            TM_ADD(2, t_pass);
-            if (sw == 0) TM_EV(2);
-            if (C > 1) cluster.sync();
-            cta_barrier();                          // (2) totals ready
-            if (sw == 0) TM_EV(3);
-            cta_barrier();                          // (3) controller done
-            if (sw == 0) TM_EV(4);
-            TM_ADD(3, t_pass);
-            if (!ld_vol(reinterpret_cast<const uint32_t *>(&S.go))) break;
-        }
-        if (C > 1) cluster.sync();
-#ifdef NDT_TIMING
-        if (sw == 0 && lane == 0 && A.timing) {
-            tm[4] = (unsigned long long)(clock64() - t_life);
-            for (int k = 0; k < 5; ++k) atomicAdd(&A.timing[k], tm[k]);
-        }
-#endif
-    } else {
-    // =========================== compute warps (consumers) ===========================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(NDT_REG_COMPUTE));
-    int parity = 0;
-    uint32_t pass_id = 0;
-#ifdef NDT_TIMING
-    unsigned long long tm[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#endif
-    uint32_t cpos[NDT_PPC];                         // entries consumed per producer
+    }
+    // publish the end of this warp's stream for this pass
+    __syncwarp();
+    if (lane == 0) {
+        __threadfence_block();
+        st_vol(&S.tail[sw], my_tail);
+        st_vol(&S.pass_end[sw][st.pass_id & 3u], my_tail);
+        st_vol(&S.pass_dead[sw][st.pass_id & 3u], 0u);
+        __threadfence_block();
+        st_vol(&S.finished[sw], st.pass_id);
+    }
+    st.my_tail = my_tail; st.hd_seen = hd_seen;
+}
+
+// batch kernel: tell this warp's consumer that the slot whose turn it is has no more work (an empty pass
+// carrying the dead marker keeps producer and consumer sequences aligned)
+__device__ __forceinline__ void search_dead_marker(NdtSmem &S, int sw, int lane, SearchState &st) {
+    ++st.pass_id;
+    __syncwarp();
+    if (lane == 0) {
+        st_vol(&S.pass_end[sw][st.pass_id & 3u], st.my_tail);
+        st_vol(&S.pass_dead[sw][st.pass_id & 3u], 1u);
+        __threadfence_block();
+        st_vol(&S.finished[sw], st.pass_id);
+    }
+}
+
+// ---------------------------------------------------------------- compute warps (consumers) ----
+// Drain one pass from this compute warp's rings: lane = (point, voxel) pair, fixed round-robin over the
+// producers, 32 pairs at a time; the warp's partial sums (butterfly, fixed order) go to `part`.
+struct DrainState {
+    uint32_t cpos[NDT_PPC];    // entries consumed per producer
+    uint32_t pass_id;          // passes drained so far
+};
+
+// Returns false when the "pass" was the marker of a dead slot (batch kernel).  The pass description (ctl.T, ctl.ang,
+// ctl.hess) is read only once the producers have delivered data or finished, i.e. after its request was published.
+__device__ __forceinline__ bool compute_drain(NdtSmem &S, const GridView &G, const NdtConst &K, const Ctl &ctl, int warp, int lane,
+                                              DrainState &ds, double *__restrict__ part) {
+    ++ds.pass_id;
+    const float *T = ctl.T;
+    bool hess = false, have_desc = false, slot_dead = false;
+    const AngTab &ang = ctl.ang;
+    double acc[NACC];
 #pragma unroll
-    for (int k = 0; k < NDT_PPC; ++k) cpos[k] = 0;
-    while (true) {
-        ++pass_id;
-        {
-            const float *T = S.ctl.T;
-            const bool hess = S.ctl.hess != 0;
-            const AngTab &ang = S.ctl.ang;
-            double acc[NACC];
-#pragma unroll
-            for (int i = 0; i < NACC; ++i) acc[i] = 0.0;
-            if (warp == 0) TM_EV(8);
+    for (int i = 0; i < NACC; ++i) acc[i] = 0.0;
+    {
             uint32_t done_mask = 0;                         // bit k: producer k exhausted for this pass
             int turn = 0;
             while (done_mask != (1u << NDT_PPC) - 1u) {
@@ -853,34 +889,43 @@ __global__ void __launch_bounds__(NDT_THREADS, NDT_MIN_CTAS) ndt_match_kernel(Gr
                 const int sw = warp + k * NDT_NCW;
                 uint32_t pos = 0;
 #pragma unroll
-                for (int kk = 0; kk < NDT_PPC; ++kk) if (kk == k) pos = cpos[kk];
+                for (int kk = 0; kk < NDT_PPC; ++kk) if (kk == k) pos = ds.cpos[kk];
                 // wait for a full chunk of 32 pairs, or for the producer to finish the pass
                 uint32_t n = 0;
                 uint32_t avail_all = 0;
-                const long long tw = TM_NOW();
                 if (lane == 0) {
                     while (true) {
-                        const uint32_t fin = ld_vol(&S.finished[sw]);
+                        // tail first, finished second: when the pass is not finished yet, everything up to the
+                        // tail read before belongs to it; once finished, the pass ends at pass_end (the producer
+                        // may already be appending the next pass)
+                        const uint32_t tl = ld_vol(&S.tail[sw]);
                         __threadfence_block();
-                        const uint32_t avail = ld_vol(&S.tail[sw]) - pos;
+                        const uint32_t fin = ld_vol(&S.finished[sw]);
+                        const bool done = (int32_t)(fin - ds.pass_id) >= 0;
+                        __threadfence_block();
+                        const uint32_t end = done ? ld_vol(&S.pass_end[sw][ds.pass_id & 3u]) : tl;
+                        const uint32_t avail = end - pos;
                         avail_all = avail;
                         if (avail >= 32u) { n = 32u; break; }
-                        if (fin == pass_id) { n = avail | 0x80000000u; break; }     // final (possibly empty) chunk
+                        if (done) {     // final (possibly empty) chunk; bit 30: dead-slot marker
+                            n = avail | 0x80000000u | (ld_vol(&S.pass_dead[sw][ds.pass_id & 3u]) ? 0x40000000u : 0u);
+                            break;
+                        }
                         __nanosleep(32);
                     }
                 }
                 n = __shfl_sync(0xffffffffu, n, 0);
-                TM_ADD(0, tw);
-                const long long tb = TM_NOW();
                 const bool final_chunk = (n & 0x80000000u) != 0;
-                n &= 0x7fffffffu;
+                if (n & 0x40000000u) slot_dead = true;
+                n &= 0x3fffffffu;
                 __threadfence_block();
+                if (!have_desc) { hess = ctl.hess != 0; have_desc = true; }
 #if NDT_PF
                 {   // pull the records of this ring's NEXT chunk towards L1 while this chunk is computed
                     avail_all = __shfl_sync(0xffffffffu, avail_all, 0);
                     if (avail_all > 32u + (uint32_t)lane) {
                         const float lw = S.ring[sw][(pos + 32u + lane) & (RING - 1u)].w;
-                        const char *gp = reinterpret_cast<const char *>(G.gauss + (size_t)__float_as_uint(lw) * 10);
+                        const char *gp = reinterpret_cast<const char *>(G.gauss + (size_t)__float_as_uint(lw) * GAUSS_STRIDE);
                         asm volatile("prefetch.global.L1 [%0];" ::"l"(gp));
                         asm volatile("prefetch.global.L1 [%0];" ::"l"(gp + 72));
                     }
@@ -888,120 +933,265 @@ __global__ void __launch_bounds__(NDT_THREADS, NDT_MIN_CTAS) ndt_match_kernel(Gr
 #endif
                 if ((uint32_t)lane < n) {
                     const float4 e = S.ring[sw][(pos + lane) & (RING - 1u)];
-                    ndt_pair(e.x, e.y, e.z, T, ang, G.gauss + (size_t)__float_as_uint(e.w) * 10, K.d1, K.d2, hess, acc);
+                    ndt_pair(e.x, e.y, e.z, T, ang, G.gauss + (size_t)__float_as_uint(e.w) * GAUSS_STRIDE, K.d1, K.d2, hess, acc);
                 }
                 pos += n;
 #pragma unroll
-                for (int kk = 0; kk < NDT_PPC; ++kk) if (kk == k) cpos[kk] = pos;
+                for (int kk = 0; kk < NDT_PPC; ++kk) if (kk == k) ds.cpos[kk] = pos;
                 __syncwarp();
                 if (lane == 0 && n) st_vol(&S.head[sw], pos);
                 if (final_chunk) done_mask |= (1u << k);
-                TM_ADD(1, tb);
-#ifdef NDT_TIMING
-                if (lane == 0) { tm[5] += 1; tm[6] += n; }
-#endif
             }
-            if (warp == 0) TM_EV(9);
-            // warp butterfly (fixed order) -> one partial per compute warp
+    }
+    // warp butterfly (fixed order) -> one partial per compute warp
 #pragma unroll
-            for (int i = 0; i < NACC; ++i) {
-                double vsum = acc[i];
+    for (int i = 0; i < NACC; ++i) {
+        double vsum = acc[i];
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) vsum += __shfl_xor_sync(0xffffffffu, vsum, o);
-                if (lane == 0) S.warp_part[warp][i] = vsum;
+        for (int o = 16; o > 0; o >>= 1) vsum += __shfl_xor_sync(0xffffffffu, vsum, o);
+        if (lane == 0) part[i] = vsum;
+    }
+    return !slot_dead;
+}
+
+// ================================================================ kernel 1: one match per cluster ======
+// One thread-block cluster (1..16 CTAs) per match: lowest latency for a single ScanMatch, also the
+// derivatives-only entry point.  Passes are separated by CTA / cluster barriers.
+__global__ void __launch_bounds__(NDT_THREADS, NDT_MIN_CTAS) ndt_match_kernel(GridView G, NdtConst K, MatchArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    NdtSmem &S = *reinterpret_cast<NdtSmem *>(smem_raw);
+    Slot &SL = S.slot[0];
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned C = cluster.num_blocks();
+    const unsigned crank = cluster.block_rank();
+    const unsigned match = blockIdx.x / C;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool is_compute = warp < NDT_NCW;
+
+    uint32_t first = 0, last = A.n_shared;
+    if (A.offsets) { first = A.offsets[match]; last = A.offsets[match + 1]; }
+    const uint32_t npts = last - first;
+
+    if (tid < NDT_NSW) { S.tail[tid] = 0u; S.head[tid] = 0u; S.finished[tid] = 0u; }
+    if (warp == 0) {
+        if (lane == 0) {
+            if (A.deriv_only) {
+                const double *p = A.poses6 + (size_t)match * 6;
+                for (int i = 0; i < 6; ++i) SL.ctl.p[i] = SL.ctl.x_t[i] = p[i];
+                ctl_request(SL.ctl, p, 1, ST_INIT);
+                SL.ctl.passes = 0; SL.ctl.pairs = 0;
+            } else {
+                ctl_start(SL.ctl, K, A.guesses + (size_t)match * 16, (double)npts);
             }
+            SL.go = 1;
         }
-        const long long t_b1 = TM_NOW();
-        if (warp == 0) TM_EV(10);
-        cta_barrier();                              // (1)
-        if (warp == 0) TM_EV(11);
-        TM_ADD(2, t_b1);
-        const long long t_red = TM_NOW();
-        // ---------------- deterministic reduction: CTA -> cluster (fixed order) ----------------
-        if (tid < NACC) {
-            double s = 0.0;
+        finish_request_warp(SL, lane);
+    }
+    __syncthreads();
+
+    const uint32_t stride = C * NDT_NSW * 32u;
+    // The two roles never share code after this point (ptxas sizes each branch for its own register
+    // budget); they meet at CTA-wide barriers issued from both branches.
+    if (!is_compute) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(NDT_REG_SEARCH));
+        const int sw = warp - NDT_NCW;
+        SearchState st;
+        while (true) {
+            search_pass(S, G, A.src, first, last, first + (crank * NDT_NSW + sw) * 32u, stride, SL.ctl.T, sw, lane, st);
+            cta_barrier();                          // (1) all pairs of the pass consumed, partials written
+            if (C > 1) cluster.sync();
+            cta_barrier();                          // (2) totals ready
+            cta_barrier();                          // (3) controller done
+            if (!ld_vol(reinterpret_cast<const uint32_t *>(&SL.go))) break;
+        }
+        if (C > 1) cluster.sync();
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(NDT_REG_COMPUTE));
+        int parity = 0;
+        DrainState ds;
 #pragma unroll
-            for (int w = 0; w < NDT_NCW; ++w) s += S.warp_part[w][tid];
-            S.cta_part[parity][tid] = s;
-        }
-        if (C > 1) {
-            cluster.sync();
+        for (int k = 0; k < NDT_PPC; ++k) ds.cpos[k] = 0;
+        ds.pass_id = 0;
+        while (true) {
+            (void)compute_drain(S, G, K, SL.ctl, warp, lane, ds, SL.warp_part[warp]);
+            cta_barrier();                              // (1)
+            // ---------------- deterministic reduction: CTA -> cluster (fixed order) ----------------
             if (tid < NACC) {
-                double tot = 0.0;
-                for (unsigned r = 0; r < C; ++r) tot += *cluster.map_shared_rank(&S.cta_part[parity][tid], r);
-                S.raw_total[tid] = tot;
-            }
-        } else {
-            if (tid < NACC) S.raw_total[tid] = S.cta_part[parity][tid];
-        }
-        cta_barrier();                              // (2)
-        if (warp == 0) TM_EV(12);
-        TM_ADD(3, t_red);
-        const long long t_ctl = TM_NOW();
-        // ---------------- controller: Newton step + More-Thuente state machine (warp 0) ----------------
-        if (warp == 0) {
-            if (lane < ACC_N) S.total[lane] = acc_finish(S.raw_total, S.ctl.ang, lane);
-            __syncwarp();
-            // serial halves on lane 0, the 6x6 Newton solve on the whole warp
-            int code = CTL_DONE;
-            if (!A.deriv_only) {
-                if (lane == 0) code = ctl_pre(S.ctl, K, S.total);
-                code = __shfl_sync(0xffffffffu, code, 0);
-                for (int guard = 0; guard < 8 && code == CTL_NEWTON; ++guard) {
-                    __syncwarp();
-                    double delta[6];
-                    const double rc = warp_lu_solve6(S.ctl.H, S.ctl.g, lane, delta);
-                    if (lane == 0) {
-                        bool fin = true;
+                double s = 0.0;
 #pragma unroll
-                        for (int i = 0; i < 6; ++i) fin = fin && (delta[i] == delta[i]) && (fabs(delta[i]) <= DBL_MAX);
-                        if (K.force_svd || !(rc > 1e-9 && fin)) {
-                            // (near-)singular Hessian: Eigen's JacobiSVD solve with its rank truncation
-                            double neg_g[6];
-                            for (int i = 0; i < 6; ++i) neg_g[i] = -S.ctl.g[i];
-                            svd_solve6(S.ctl.H, neg_g, delta);
-                        }
-                        code = ctl_post_newton(S.ctl, K, delta);
-                    }
-                    code = __shfl_sync(0xffffffffu, code, 0);
+                for (int w = 0; w < NDT_NCW; ++w) s += SL.warp_part[w][tid];
+                SL.cta_part[parity][tid] = s;
+            }
+            if (C > 1) {
+                cluster.sync();
+                if (tid < NACC) {
+                    double tot = 0.0;
+                    for (unsigned r = 0; r < C; ++r) tot += *cluster.map_shared_rank(&SL.cta_part[parity][tid], r);
+                    SL.raw_total[tid] = tot;
                 }
-                if (code == CTL_NEWTON) { code = CTL_DONE; if (lane == 0) S.ctl.state = ST_DONE; }
+            } else {
+                if (tid < NACC) SL.raw_total[tid] = SL.cta_part[parity][tid];
             }
-            const int go = (code == CTL_PASS) ? 1 : 0;
-            if (lane == 0) S.go = go;
-            __syncwarp();
-            if (go) finish_request_warp0(S, lane);
+            cta_barrier();                              // (2)
+            // ---------------- controller: Newton step + More-Thuente state machine (warp 0) ----------------
+            if (warp == 0) {
+                const int go = controller_step(SL, K, A.deriv_only, lane);
+                if (lane == 0) SL.go = go;
+            }
+            cta_barrier();                              // (3)
+            if (!SL.go) break;
+            parity ^= 1;
         }
-        cta_barrier();                              // (3)
-        if (warp == 0) TM_EV(13);
-        TM_ADD(4, t_ctl);
-        if (!S.go) break;
-        parity ^= 1;
+        if (C > 1) cluster.sync();    // peers may still be reading this CTA's partials
+        if (tid == 0 && crank == 0) {
+            if (A.deriv_only) {
+                for (int i = 0; i < ACC_N; ++i) A.acc_out[(size_t)match * ACC_N + i] = SL.total[i];
+                if (A.poses_out) for (int i = 0; i < 16; ++i) A.poses_out[(size_t)match * 16 + i] = SL.ctl.T[i];
+            } else {
+                write_result(SL, A, match);
+            }
+        }
     }
+}
+
+// ================================================================ kernel 2: batches, two matches per CTA =
+// Persistent CTAs (one wave), NDT_SLOTS matches in flight per CTA, work fetched from a global counter.  The
+// search warps alternate between the slots pass by pass and never wait at a pass boundary: while the compute
+// warps drain the tail of slot A's pass and compute warp A runs A's Newton step, the search warps are already
+// producing slot B's pass.  Compute warps hand their partial sums to the slot's controller warp through a named
+// barrier (bar.arrive for the others, bar.sync for the controller) and move on.  Every warp walks the same
+// deterministic sequence (slot 0, slot 1, slot 0, ...; a slot's next item is "pass seq+1" or "dead"), and a
+// match's sums are accumulated in the same fixed order as in kernel 1, so results do not depend on scheduling.
+__global__ void __launch_bounds__(NDT_THREADS, NDT_MIN_CTAS) ndt_batch_kernel(GridView G, NdtConst K, MatchArgs A, uint32_t B,
+                                                                             uint32_t *__restrict__ work_counter) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    NdtSmem &S = *reinterpret_cast<NdtSmem *>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool is_compute = warp < NDT_NCW;
+
+    // fetch the next match for a slot (controller warp, all lanes): returns 1 and requests its first pass, or 0
+    auto fetch_match = [&](Slot &SL) -> int {
+        uint32_t m = 0;
+        if (lane == 0) m = atomicAdd(work_counter, 1u);
+        m = __shfl_sync(0xffffffffu, m, 0);
+        if (m >= B) return 0;
+        if (lane == 0) {
+            uint32_t first = 0, last = A.n_shared;
+            if (A.offsets) { first = A.offsets[m]; last = A.offsets[m + 1]; }
+            SL.first = first; SL.last = last; SL.match = m;
+            ctl_start(SL.ctl, K, A.guesses + (size_t)m * 16, (double)(last - first));
+        }
+        finish_request_warp(SL, lane);
+        return 1;
+    };
+    // Pass requests reach the SEARCH warps through named barrier 1 + NDT_SLOTS + s: the slot's controller warp
+    // publishes (seq, or dead) and arrives without waiting, the search warps wait in the hardware barrier (no
+    // polling of shared memory while a controller runs).  The first request of a slot was published before the
+    // initial __syncthreads.  The compute warps never wait for requests: they follow the ring streams, where a
+    // dead slot shows up as an empty pass carrying the dead marker.
+    constexpr int REQ_THREADS = (NDT_NSW + 1) * 32;
+    auto next_item = [&](int s, uint32_t seen) -> int {
+        if (seen != 0u) asm volatile("bar.sync %0, %1;" ::"r"(1 + NDT_SLOTS + s), "n"(REQ_THREADS) : "memory");
+        return ld_vol(&S.slot[s].dead) ? 0 : 1;
+    };
+
+    if (tid < NDT_NSW) { S.tail[tid] = 0u; S.head[tid] = 0u; S.finished[tid] = 0u; }
+    if (warp < NDT_SLOTS) {
+        Slot &SL = S.slot[warp];
+        const int ok = fetch_match(SL);
+        if (lane == 0) { SL.seq = ok ? 1u : 0u; SL.dead = ok ? 0u : 1u; }
+    }
+    __syncthreads();
+
+    if (!is_compute) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(NDT_REG_SEARCH));
+        const int sw = warp - NDT_NCW;
+        SearchState st;
+        TMB_DECL;
+        // every warp walks the same sequence: slot 0, slot 1, slot 0, ... (one code copy: s is a run-time value)
+        uint32_t seen0 = 0u, seen1 = 0u;
+        bool dead0 = false, dead1 = (NDT_SLOTS < 2);
+        int s = 0;
+        while (!(dead0 && dead1)) {
+            if (!(s ? dead1 : dead0)) {
+                TMB_LAP(2);
+                const int item = next_item(s, s ? seen1 : seen0);
+                TMB_LAP(0);                                    // [0] waiting for the next pass request
+                if (item) {
+                    if (s) ++seen1; else ++seen0;
+                    Slot &SL = S.slot[s];
+                    const uint32_t first = ld_vol(&SL.first), last = ld_vol(&SL.last);
+                    search_pass(S, G, A.src, first, last, first + sw * 32u, NDT_NSW * 32u, SL.ctl.T, sw, lane, st);
+                    TMB_LAP(1);                                // [1] producing
+                } else {
+                    search_dead_marker(S, sw, lane, st);
+                    if (s) dead1 = true; else dead0 = true;
+                }
+            }
+            s = (NDT_SLOTS > 1) ? (s ^ 1) : 0;
+        }
+        TMB_FLUSH(0, sw == 0);
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(NDT_REG_COMPUTE));
+        TMB_DECL;
+        DrainState ds;
+#pragma unroll
+        for (int k = 0; k < NDT_PPC; ++k) ds.cpos[k] = 0;
+        ds.pass_id = 0;
+        uint32_t seen0 = 0u, seen1 = 0u;
+        bool dead0 = false, dead1 = (NDT_SLOTS < 2);
+        int s = 0;
+        while (!(dead0 && dead1)) {
+            const int s_now = s;
+            s = (NDT_SLOTS > 1) ? (s ^ 1) : 0;
+            {
+                const int s = s_now;
+                if (s ? dead1 : dead0) continue;
+                TMB_LAP(7);
+                if (s) ++seen1; else ++seen0;
+                const uint32_t seen_s = s ? seen1 : seen0;
+                Slot &SL = S.slot[s];
+                const bool live = compute_drain(S, G, K, SL.ctl, warp, lane, ds, SL.warp_part[warp]);
+                if (!live) { if (s) dead1 = true; else dead0 = true; continue; }
+                TMB_LAP(1);                                    // [1] draining (incl. waiting for chunks)
+                if (warp != s) {
+                    // hand the partial sums to the slot's controller warp and move on
+                    __syncwarp();
+                    asm volatile("bar.arrive %0, %1;" ::"r"(1 + s), "n"(NDT_NCW * 32) : "memory");
+                } else {
+                    asm volatile("bar.sync %0, %1;" ::"r"(1 + s), "n"(NDT_NCW * 32) : "memory");
+                    TMB_LAP(2);                                // [2] controller warp waiting for the other compute warps
+                    // ---- controller of slot s: fixed-order reduction, Newton step, next request / next match
+                    for (int i = lane; i < NACC; i += 32) {
+                        double sum = 0.0;
+#pragma unroll
+                        for (int w = 0; w < NDT_NCW; ++w) sum += SL.warp_part[w][i];
+                        SL.raw_total[i] = sum;
+                    }
+                    __syncwarp();
+                    int go = controller_step(SL, K, 0, lane);
+                    TMB_LAP(3);                                // [3] controller
+                    if (!go) {
+                        if (lane == 0) write_result(SL, A, SL.match);
+                        __syncwarp();
+                        go = fetch_match(SL);
+                        TMB_LAP(4);                            // [4] result + next match
+                    }
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (go) st_vol(&SL.seq, seen_s + 1u); else st_vol(&SL.dead, 1u);
+                    }
+                    __syncwarp();
+                    asm volatile("bar.arrive %0, %1;" ::"r"(1 + NDT_SLOTS + s), "n"(REQ_THREADS) : "memory");
+                }
+            }
+        }
+        TMB_FLUSH(8, warp == 0);
+        TMB_FLUSH(16, warp == NDT_NCW - 1);
 #ifdef NDT_TIMING
-    if (warp == 0 && lane == 0 && A.timing) {
-        for (int k = 0; k < 7; ++k) atomicAdd(&A.timing[8 + k], tm[k]);
-        atomicAdd(&A.timing[15], 1ull);
-    }
+        if (warp == 0 && lane == 0 && A.timing) atomicAdd(&A.timing[24], 1ull);
 #endif
-    if (C > 1) cluster.sync();    // peers may still be reading this CTA's partials
-    if (tid == 0 && crank == 0) {
-        if (A.deriv_only) {
-            for (int i = 0; i < ACC_N; ++i) A.acc_out[(size_t)match * ACC_N + i] = S.total[i];
-            if (A.poses_out) for (int i = 0; i < 16; ++i) A.poses_out[(size_t)match * 16 + i] = S.ctl.T[i];
-        } else {
-            for (int i = 0; i < 16; ++i) A.poses_out[(size_t)match * 16 + i] = S.ctl.finalT[i];
-            if (A.results) {
-                b2ndt_result r;
-                r.iterations = S.ctl.nr_iter; r.converged = S.ctl.converged;
-                r.score = S.ctl.score; r.trans_probability = S.ctl.trans_probability;
-                for (int i = 0; i < 6; ++i) r.p[i] = S.ctl.p[i];
-                r.passes = S.ctl.passes; r.mt_trials = S.ctl.mt_trials; r.pairs = S.ctl.pairs;
-                A.results[match] = r;
-            }
-        }
     }
-    }   // compute branch
 }
 
 // ------------------------------------------------------------------ fitness score -------------
@@ -1114,7 +1304,10 @@ struct b2ndt {
     float last_pose[16];
     bool have_last = false;
     int cl_single = 8, cl_batch = 1;
-    bool attrs_set = false;
+    bool attrs_set = false, batch_attrs_set = false;
+    bool use_batch_kernel = true;          // B2NDT_BATCH_KERNEL=0 falls back to one-match-per-CTA launches (A/B testing)
+    int batch_ctas = 0;
+    DevBuf d_work;
 };
 
 static void gauss_constants(double outlier_ratio, float resolution, double *d1, double *d2) {
@@ -1151,6 +1344,7 @@ extern "C" int b2ndt_create(const b2ndt_params *p, int device, b2ndt **out) {
     cudaError_t e = cudaStreamCreateWithFlags(&h->own, cudaStreamNonBlocking);
     if (e != cudaSuccess) { set_error("cudaStreamCreate failed: %s", cudaGetErrorString(e)); delete h; return B2_ERR_CUDA; }
     h->st = h->own;
+    if (const char *e = getenv("B2NDT_BATCH_KERNEL")) h->use_batch_kernel = atoi(e) != 0;
     *out = h;
     return 0;
 }
@@ -1165,6 +1359,7 @@ extern "C" void b2ndt_destroy(b2ndt *h) {
     t.centroid4.release(); t.gauss.release(); t.sums.release(); t.icov9.release(); t.cells.release(); t.counters.release();
     t.nbr_head.release(); t.nbr_list.release(); t.nbr_tiles.release();
     h->d_src.release(); h->d_guess.release(); h->d_pose.release(); h->d_res.release(); h->d_off.release();
+    h->d_work.release();
     h->d_p6.release(); h->d_acc.release(); h->d_fit_sum.release(); h->d_fit_cnt.release();
     h->h_stage.release(); h->h_small.release(); h->h_res.release();
     if (h->own) cudaStreamDestroy(h->own);
@@ -1218,7 +1413,7 @@ static int build_target(b2ndt *h, const float4 *d_pts, size_t n, int nbits_hint)
     if ((rc = t.leaf_n.reserve((V + 1) * 4))) return rc;
     if ((rc = t.leaf_start.reserve((V + 1) * 4))) return rc;
     if ((rc = t.centroid4.reserve((V + 1) * sizeof(float4)))) return rc;
-    if ((rc = t.gauss.reserve((size_t)(V + 1) * 80))) return rc;
+    if ((rc = t.gauss.reserve((size_t)(V + 1) * GAUSS_STRIDE * 8))) return rc;
     if ((rc = t.sums.reserve((size_t)(V + 1) * 72))) return rc;
     if ((rc = t.icov9.reserve((size_t)(V + 1) * 72))) return rc;
     if ((rc = t.cells.reserve((size_t)t.L.ncells * 16 + 16))) return rc;
@@ -1319,9 +1514,11 @@ extern "C" int b2ndt_target_leaves(b2ndt *h, int32_t *idx, int32_t *n_raw, float
     if (centroid4) B2_CUDA(cudaMemcpy(centroid4, t.centroid4.p, V * 16, cudaMemcpyDeviceToHost));
     if (icov9) B2_CUDA(cudaMemcpy(icov9, t.icov9.p, V * 72, cudaMemcpyDeviceToHost));
     if (mean3) {
-        std::vector<double> g(V * 10);
-        B2_CUDA(cudaMemcpy(g.data(), t.gauss.p, V * 80, cudaMemcpyDeviceToHost));
-        for (size_t j = 0; j < V; ++j) { mean3[3 * j] = g[10 * j]; mean3[3 * j + 1] = g[10 * j + 1]; mean3[3 * j + 2] = g[10 * j + 2]; }
+        std::vector<double> g(V * GAUSS_STRIDE);
+        B2_CUDA(cudaMemcpy(g.data(), t.gauss.p, V * GAUSS_STRIDE * 8, cudaMemcpyDeviceToHost));
+        for (size_t j = 0; j < V; ++j) {
+            mean3[3 * j] = g[GAUSS_STRIDE * j]; mean3[3 * j + 1] = g[GAUSS_STRIDE * j + 1]; mean3[3 * j + 2] = g[GAUSS_STRIDE * j + 2];
+        }
     }
     return 0;
 }
@@ -1351,6 +1548,47 @@ static int launch_match(b2ndt *h, const MatchArgs &A, size_t B, int C) {
         h->attrs_set = true;
     }
     GridView G = make_grid_view(h);
+    if (C == 1 && !A.deriv_only && B >= 2 && h->use_batch_kernel) {
+        // batches: persistent CTAs (one wave), two matches in flight per CTA, work fetched from a counter
+        if (!h->batch_attrs_set) {
+            B2_CUDA(cudaFuncSetAttribute(ndt_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NdtSmem)));
+            // one wave of resident CTAs: NDT_MIN_CTAS per SM (__launch_bounds__); CTAs do not depend on one
+            // another (work comes from a counter), so a CTA that is not resident at once just starts later
+            int sms = 0;
+            B2_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
+            h->batch_ctas = NDT_MIN_CTAS * sms;
+            h->batch_attrs_set = true;
+        }
+        int rc;
+        if ((rc = h->d_work.reserve(64))) return rc;
+        B2_CUDA(cudaMemsetAsync(h->d_work.p, 0, 4, h->st));
+        const size_t want = (B + NDT_SLOTS - 1) / NDT_SLOTS;
+        const unsigned grid = (unsigned)(want < (size_t)h->batch_ctas ? want : (size_t)h->batch_ctas);
+        NdtConst Kb = h->K;
+        MatchArgs Ab = A;
+#ifdef NDT_TIMING
+        static unsigned long long *d_tm = nullptr;
+        if (!d_tm) cudaMalloc(&d_tm, 32 * 8);
+        cudaMemsetAsync(d_tm, 0, 32 * 8, h->st);
+        Ab.timing = d_tm;
+#endif
+        ndt_batch_kernel<<<grid, NDT_THREADS, sizeof(NdtSmem), h->st>>>(G, Kb, Ab, (uint32_t)B, h->d_work.as<uint32_t>());
+        b2::count_launch();
+        cudaError_t eb = cudaGetLastError();
+        if (eb != cudaSuccess) { set_error("ndt_batch_kernel launch failed: %s", cudaGetErrorString(eb)); return B2_ERR_CUDA; }
+#ifdef NDT_TIMING
+        {
+            unsigned long long t[32];
+            cudaStreamSynchronize(h->st);
+            cudaMemcpy(t, d_tm, sizeof(t), cudaMemcpyDeviceToHost);
+            const double n = t[24] ? (double)t[24] : 1.0;
+            fprintf(stderr, "[ndt batch timing] ctas %.0f matches %zu | search0: wait %.0f produce %.0f other %.0f | compute0(ctl): wait %.0f drain %.0f barwait %.0f ctl %.0f fetch %.0f other %.0f | compute%d: wait %.0f drain %.0f other %.0f (cycles per CTA)\n",
+                    n, B, t[0] / n, t[1] / n, t[2] / n, t[8] / n, t[9] / n, t[10] / n, t[11] / n, t[12] / n, t[15] / n, NDT_NCW - 1,
+                    t[16] / n, t[17] / n, t[23] / n);
+        }
+#endif
+        return 0;
+    }
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)(B * (size_t)C));
@@ -1363,34 +1601,9 @@ static int launch_match(b2ndt *h, const MatchArgs &A, size_t B, int C) {
     cfg.attrs = at; cfg.numAttrs = 1;
     NdtConst K = h->K;
     MatchArgs Ac = A;
-#ifdef NDT_TIMING
-    static unsigned long long *d_tm = nullptr;
-    if (!d_tm) cudaMalloc(&d_tm, 96 * 8);
-    cudaMemsetAsync(d_tm, 0, 96 * 8, h->st);
-    Ac.timing = d_tm;
-#endif
     cudaError_t e = cudaLaunchKernelEx(&cfg, ndt_match_kernel, G, K, Ac);
     b2::count_launch();
     if (e != cudaSuccess) { set_error("ndt_match_kernel launch failed: %s", cudaGetErrorString(e)); return B2_ERR_CUDA; }
-#ifdef NDT_TIMING
-    {
-        unsigned long long t[96];
-        cudaStreamSynchronize(h->st);
-        cudaMemcpy(t, d_tm, sizeof(t), cudaMemcpyDeviceToHost);
-        const double n = (double)t[15] > 0 ? (double)t[15] : 1.0;
-        fprintf(stderr, "[ndt timing] ctas %.0f | search0: pass %.0f ring-wait %.0f to-bar1 %.0f to-bar3 %.0f life %.0f | compute0: wait %.0f busy %.0f bar1 %.0f reduce %.0f ctl %.0f chunks %.0f pairs %.0f (cycles per CTA)\n",
-                n, t[0] / n, t[1] / n, t[2] / n, t[3] / n, t[4] / n, t[8] / n, t[9] / n, t[10] / n, t[11] / n, t[12] / n, t[13] / n, t[14] / n);
-        // event trace of CTA 0, first 4 passes, relative to the search warp's first pass start
-        const unsigned long long t0 = t[32];
-        for (int ps = 0; ps < 4; ++ps) {
-            const unsigned long long *e = t + 32 + ps * 16;
-            if (!e[0]) break;
-            fprintf(stderr, "[ndt trace] pass %d search: start %lld finish %lld b1 %lld b2 %lld b3 %lld | compute: start %lld drained %lld bfly %lld b1 %lld b2 %lld b3 %lld\n",
-                    ps + 1, (long long)(e[0] - t0), (long long)(e[1] - t0), (long long)(e[2] - t0), (long long)(e[3] - t0), (long long)(e[4] - t0),
-                    (long long)(e[8] - t0), (long long)(e[9] - t0), (long long)(e[10] - t0), (long long)(e[11] - t0), (long long)(e[12] - t0), (long long)(e[13] - t0));
-        }
-    }
-#endif
     return 0;
 }
 
