@@ -204,7 +204,7 @@ def main():
     import torch
     import torch.distributed as dist
     from lidar_slam_b200 import capi
-    from lidar_slam_b200.registration import NDTRegistration, VoxelFilter
+    from lidar_slam_b200.registration import DeviceCloud, NDTRegistration, VoxelFilter
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the registration path has no CPU fallback (use --impl reference for the CPU arm)")
@@ -247,6 +247,32 @@ def main():
     reg.SetInputTarget(target)
     set_target_ms = min(set_target_ms, 1e3 * (time.perf_counter() - t_tgt))
     info = reg.TargetInfo()
+
+    # the two other subsystems of the path with everything resident in HBM (device clouds): VoxelFilter of one raw
+    # scan and the target-grid build of the map; algorithmic bytes per SURVEY 8(d)
+    def timed_ms(fn, reps=10):
+        fn()
+        ts = []
+        for _ in range(reps):
+            t = time.perf_counter(); fn(); ts.append(1e3 * (time.perf_counter() - t))
+        return float(np.median(ts))
+
+    raw0 = scene.scan(0x5EED0000 + 17, truth[0])
+    d_raw, d_filt, d_map = DeviceCloud(raw0, device=local_rank), DeviceCloud(device=local_rank), DeviceCloud(target, device=local_rank)
+    vf_ms = timed_ms(lambda: vf.FilterCloud(d_raw, d_filt))
+    tg_ms = timed_ms(lambda: reg.SetInputTargetCloud(d_map), reps=5)
+    peak_hbm = measured_peaks()[0]
+    vf_bytes = 16.0 * len(raw0) + 16.0 * len(d_filt)
+    tg_bytes = 16.0 * len(target) + 80.0 * info["n_leaves"]
+    resident = {
+        "voxel_filter_scan": {"n_in": len(raw0), "n_out": len(d_filt), "ms": vf_ms, "algorithmic_bytes": vf_bytes,
+                              "GBps": vf_bytes / vf_ms / 1e6, "frac_of_hbm_peak": vf_bytes / vf_ms / 1e6 / peak_hbm,
+                              "note": "one call = ~17 launches + one 32-byte D2H of the count; latency-bound at this size"},
+        "set_target_map": {"n_points": len(target), "voxels": info["n_leaves"], "ms": tg_ms, "algorithmic_bytes": tg_bytes,
+                           "GBps": tg_bytes / tg_ms / 1e6, "frac_of_hbm_peak": tg_bytes / tg_ms / 1e6 / peak_hbm},
+    }
+    reg.SetInputTarget(target)       # back to the host-path target (identical grid)
+    del d_raw, d_filt, d_map
 
     cat = np.ascontiguousarray(np.concatenate(sources, axis=0))
     offsets = np.zeros(B + 1, np.uint32)
@@ -350,7 +376,7 @@ def main():
 
     if rank == 0:
         peak, peak_src = measured_peaks()
-        # roofline of ndt_match_kernel (one launch per step on this rank): SURVEY 8(d) algorithmic bytes
+        # roofline of ndt_batch_kernel (one launch per step on this rank): SURVEY 8(d) algorithmic bytes
         from oracle import oracle as O
         O.build(ref=False)
         grid = O.Grid(target, NDT["res"])
@@ -377,7 +403,9 @@ def main():
                 traffic = float(tj["dram_bytes_read"] + tj["dram_bytes_write"])
         except Exception:
             pass
-        flops = float(np.sum(passes * 60.0 * npts) + 450.0 * res["pairs"].sum())
+        # FP64 work actually issued: ~300 flops per (point, voxel) pair in the Q/P/M formulation (150 DFMA-class
+        # operations, csrc/b2_ndt.cu ndt_pair) + ~30 per point and pass for the float transform / cell lookup
+        flops = float(np.sum(passes * 30.0 * npts) + 300.0 * res["pairs"].sum())
 
         # CPU baseline: the oracle, single thread, bounded sample of the same frames
         prm = O.params(res=NDT["res"], step_size=f32(NDT["step_size"]), trans_eps=f32(NDT["trans_eps"]), max_iter=NDT["max_iter"])
@@ -406,7 +434,7 @@ def main():
                 "frames_per_gpu": B, "l2": "256 MB flush between timed steps", "batch_cluster": args.batch_cluster,
                 "mean_iterations": float(res["iterations"].mean()), "converged_frac": float(res["converged"].mean()),
                 "mean_passes": float(res["passes"].mean()), "pairs_per_pass_per_point": float(res["pairs"].sum() / np.sum(passes * npts)),
-                "set_target_ms": set_target_ms, "setup_s": setup_s,
+                "set_target_ms": set_target_ms, "setup_s": setup_s, "device_resident": resident,
                 "voxel_filter": {"raw_pts_per_frame": filt_stats["raw_pts"] / max(1, B), "ms_per_frame_host_api": 1e3 * filt_stats["sec"] / max(1, B)},
                 "single_match_ms": {"p50": float(np.percentile(lat, 50)), "p99": float(np.percentile(lat, 99)), "n": len(lat)},
                 "step_ms": step_ms, "wall_ms_per_step_incl_flush": max_wall_ms / args.steps,
@@ -415,9 +443,9 @@ def main():
             "gpu_launches": int(tot[1].item()),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "kernel": "ndt_match_kernel", "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+                         "kernel": "ndt_batch_kernel", "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                          "v_touched_per_source_point": rho, "fp64_gflops_est": flops / launch_s / 1e9,
-                         "note": "working set is L2-resident (DRAM traffic << algorithmic bytes): bound by L1/LSU wavefronts + load latency, see profiles/README.md"},
+                         "note": "working set is L2-resident (DRAM traffic << algorithmic bytes): bound by the L1 data pipe (LSU wavefronts of the gathers + shared-memory rings) and instruction latency, see profiles/README.md"},
             "cpu_baseline": ({"value": cpu_value, "unit": UNIT, "cores": 1, "kind": "port",
                               "sample": "%d of the %d frames, oracle align, 1 thread" % (len(sample), B)} if cpu_value else None),
             "parity": parity,
