@@ -337,6 +337,8 @@ struct MatchArgs {
     b2ndt_result *results;       // B
     double *acc_out;             // B*ACC_N (deriv-only mode)
     int deriv_only;
+    const uint32_t *ready;       // batch kernel, host-streamed sources: number of leading matches whose points have
+                                 // arrived in HBM (written by the copy stream between chunk copies); NULL = all resident
     unsigned long long *timing;  // NDT_TIMING builds only (tools/ sweeps): per-phase SM-cycle totals of the batch kernel
 };
 
@@ -665,7 +667,9 @@ __device__ __forceinline__ void search_pass(NdtSmem &S, const GridView &G, const
     constexpr uint32_t IRREGULAR = 0xffffffffu;
     auto load_pt = [&](uint32_t b) {
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (b < last && b + lane < last) v = __ldg(&src[b + lane]);
+        // ld.global.cg (L2 only): the sources may still be streaming in from the host while the kernel runs, and a
+        // 32-byte sector can hold points of two matches that arrive in different chunks
+        if (b < last && b + lane < last) v = __ldcg(&src[b + lane]);
         return v;
     };
     {
@@ -1075,6 +1079,14 @@ __global__ void __launch_bounds__(NDT_THREADS, NDT_MIN_CTAS) ndt_batch_kernel(Gr
         if (lane == 0) m = atomicAdd(work_counter, 1u);
         m = __shfl_sync(0xffffffffu, m, 0);
         if (m >= B) return 0;
+        if (A.ready) {
+            // host-streamed batch: wait until the copy stream has delivered this match's points
+            if (lane == 0) {
+                while (*reinterpret_cast<const volatile uint32_t *>(A.ready) <= m) __nanosleep(2000);
+                __threadfence();
+            }
+            __syncwarp();
+        }
         if (lane == 0) {
             uint32_t first = 0, last = A.n_shared;
             if (A.offsets) { first = A.offsets[m]; last = A.offsets[m + 1]; }
@@ -1307,7 +1319,11 @@ struct b2ndt {
     bool attrs_set = false, batch_attrs_set = false;
     bool use_batch_kernel = true;          // B2NDT_BATCH_KERNEL=0 falls back to one-match-per-CTA launches (A/B testing)
     int batch_ctas = 0;
-    DevBuf d_work;
+    DevBuf d_work;                         // [0] next match to fetch, [1] matches whose sources are resident
+    cudaStream_t copy_st = nullptr;        // H2D stream of host-streamed batches
+    cudaEvent_t ev = nullptr;
+    PinBuf h_ready;
+    bool stream_batches = true;            // B2NDT_STREAM=0: copy everything, then launch
 };
 
 static void gauss_constants(double outlier_ratio, float resolution, double *d1, double *d2) {
@@ -1345,6 +1361,7 @@ extern "C" int b2ndt_create(const b2ndt_params *p, int device, b2ndt **out) {
     if (e != cudaSuccess) { set_error("cudaStreamCreate failed: %s", cudaGetErrorString(e)); delete h; return B2_ERR_CUDA; }
     h->st = h->own;
     if (const char *e = getenv("B2NDT_BATCH_KERNEL")) h->use_batch_kernel = atoi(e) != 0;
+    if (const char *e = getenv("B2NDT_STREAM")) h->stream_batches = atoi(e) != 0;
     *out = h;
     return 0;
 }
@@ -1359,7 +1376,9 @@ extern "C" void b2ndt_destroy(b2ndt *h) {
     t.centroid4.release(); t.gauss.release(); t.sums.release(); t.icov9.release(); t.cells.release(); t.counters.release();
     t.nbr_head.release(); t.nbr_list.release(); t.nbr_tiles.release();
     h->d_src.release(); h->d_guess.release(); h->d_pose.release(); h->d_res.release(); h->d_off.release();
-    h->d_work.release();
+    h->d_work.release(); h->h_ready.release();
+    if (h->copy_st) { cudaStreamSynchronize(h->copy_st); cudaStreamDestroy(h->copy_st); }
+    if (h->ev) cudaEventDestroy(h->ev);
     h->d_p6.release(); h->d_acc.release(); h->d_fit_sum.release(); h->d_fit_cnt.release();
     h->h_stage.release(); h->h_small.release(); h->h_res.release();
     if (h->own) cudaStreamDestroy(h->own);
@@ -1561,7 +1580,7 @@ static int launch_match(b2ndt *h, const MatchArgs &A, size_t B, int C) {
         }
         int rc;
         if ((rc = h->d_work.reserve(64))) return rc;
-        B2_CUDA(cudaMemsetAsync(h->d_work.p, 0, 4, h->st));
+        if (!A.ready) B2_CUDA(cudaMemsetAsync(h->d_work.p, 0, 8, h->st));     // streamed batches: the caller zeroed it
         const size_t want = (B + NDT_SLOTS - 1) / NDT_SLOTS;
         const unsigned grid = (unsigned)(want < (size_t)h->batch_ctas ? want : (size_t)h->batch_ctas);
         NdtConst Kb = h->K;
@@ -1653,6 +1672,59 @@ static int align_host(b2ndt *h, const void *src, size_t n_total, size_t stride, 
         memcpy(ost, offsets, (B + 1) * 4);
         B2_CUDA(cudaMemcpyAsync(h->d_off.p, ost, (B + 1) * 4, cudaMemcpyHostToDevice, h->st));
         d_off = h->d_off.as<uint32_t>();
+    }
+    // Large batches of separate sources: ONE persistent-kernel launch, and the sources stream in behind it.  The
+    // kernel is launched first; the copy stream then delivers the sources chunk by chunk, bumping a counter of
+    // resident matches after every chunk; a CTA that fetches a match whose points have not arrived yet waits on
+    // that counter.  The H2D copy (and the host repack of unpinned / strided clouds) overlaps the matching.
+    if (offsets && C == 1 && B >= 256 && h->use_batch_kernel && h->stream_batches) {
+        if (!h->copy_st) B2_CUDA(cudaStreamCreateWithFlags(&h->copy_st, cudaStreamNonBlocking));
+        if (!h->ev) B2_CUDA(cudaEventCreateWithFlags(&h->ev, cudaEventDisableTiming));
+        const size_t nch = 16;
+        if ((rc = h->d_work.reserve(64))) return rc;
+        if ((rc = h->h_ready.reserve(nch * 4 + 64))) return rc;
+        B2_CUDA(cudaMemsetAsync(h->d_work.p, 0, 8, h->st));
+        B2_CUDA(cudaEventRecord(h->ev, h->st));                     // counters zeroed, guesses + offsets queued
+        B2_CUDA(cudaStreamWaitEvent(h->copy_st, h->ev, 0));
+        MatchArgs A;
+        memset(&A, 0, sizeof(A));
+        A.src = h->d_src.as<float4>(); A.offsets = d_off; A.n_shared = (uint32_t)n_total;
+        A.guesses = h->d_guess.as<float>(); A.poses_out = h->d_pose.as<float>(); A.results = h->d_res.as<b2ndt_result>();
+        A.ready = h->d_work.as<uint32_t>() + 1;
+        if ((rc = launch_match(h, A, B, 1))) return rc;
+        uint32_t *hr = h->h_ready.as<uint32_t>();
+        const size_t per_c = (B + nch - 1) / nch;
+        size_t ci = 0;
+        for (size_t c0 = 0; c0 < B; c0 += per_c, ++ci) {
+            const size_t c1 = (c0 + per_c < B) ? c0 + per_c : B;
+            const size_t p0 = offsets[c0], p1 = offsets[c1];
+            cudaError_t ce = cudaSuccess;
+            if (p1 > p0) {
+                const char *from;
+                if (direct) from = (const char *)src + p0 * 16;
+                else {
+                    pack_cloud_f4((const char *)src + p0 * stride, p1 - p0, stride, ioff, (float *)(stage + p0 * 16));
+                    from = stage + p0 * 16;
+                }
+                ce = cudaMemcpyAsync(h->d_src.as<char>() + p0 * 16, from, (p1 - p0) * 16, cudaMemcpyHostToDevice, h->copy_st);
+            }
+            hr[ci] = (ce == cudaSuccess) ? (uint32_t)c1 : (uint32_t)B;      // on failure release the kernel, then report
+            cudaError_t ce2 = cudaMemcpyAsync(h->d_work.as<uint32_t>() + 1, hr + ci, 4, cudaMemcpyHostToDevice, h->copy_st);
+            if (ce != cudaSuccess || ce2 != cudaSuccess) {
+                cudaStreamSynchronize(h->copy_st);
+                cudaStreamSynchronize(h->st);
+                set_error("b2ndt_align_batch: streamed H2D copy failed: %s", cudaGetErrorString(ce != cudaSuccess ? ce : ce2));
+                return B2_ERR_CUDA;
+            }
+        }
+        char *hres2 = h->h_res.as<char>();
+        B2_CUDA(cudaMemcpyAsync(hres2, h->d_pose.p, B * 64, cudaMemcpyDeviceToHost, h->st));
+        B2_CUDA(cudaMemcpyAsync(hres2 + B * 64, h->d_res.p, B * sizeof(b2ndt_result), cudaMemcpyDeviceToHost, h->st));
+        B2_CUDA(cudaStreamSynchronize(h->copy_st));
+        B2_CUDA(cudaStreamSynchronize(h->st));
+        memcpy(poses_out, hres2, B * 64);
+        if (res) memcpy(res, hres2 + B * 64, B * sizeof(b2ndt_result));
+        return 0;
     }
     // Chunked launches would overlap the H2D copy with compute, but every extra launch ends in a partial
     // wave that lasts as long as one whole match (~1 ms): measured on B200, 2000 matches take 9.6 ms in one

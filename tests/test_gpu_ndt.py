@@ -288,3 +288,33 @@ def test_cpp_dropin_classes(oracle, small_map, scans, tmp_path):
     assert abs(float(kv["FIT"][0]) - ofit) <= 1e-4 * ofit
     r0 = np.array([float(v) for v in kv["R0"]])
     assert np.max(np.abs(r0[:3] - ref["cloud"][0])) <= 2e-3 and abs(r0[3] - filt[0, 3]) < 1e-6
+
+
+@pytest.mark.gpu
+def test_streamed_host_batch_equals_resident_batch(setup, scans, small_map):
+    """Large host batches run as ONE persistent launch with the sources streaming in behind it (16 chunks, a
+    counter of resident matches): same poses / iterations as the same batch with everything copied first, for
+    packed pinned-or-not sources and for the 32-byte PointXYZI layout (host repack per chunk)."""
+    import os
+    from lidar_slam_b200.registration import NDTRegistration, to_xyzi8
+    reg, grid, prm, srcs = setup
+    rng = np.random.default_rng(16)
+    B = 300
+    sources, guesses = [], []
+    for b in range(B):
+        k = b % len(srcs)
+        sources.append(srcs[k][: len(srcs[k]) - (b % 11)])
+        guesses.append(synth.pose6_to_matrix(synth.perturb_pose(scans[k][0], rng)).astype(np.float32))
+    sources[7] = np.zeros((0, 4), np.float32)                      # an empty member inside a chunk
+    poses, res = reg.ScanMatchBatch(sources, guesses)              # streamed (B >= 256)
+    poses8, res8 = reg.ScanMatchBatch([to_xyzi8(s) for s in sources], guesses)
+    os.environ["B2NDT_STREAM"] = "0"
+    try:
+        reg0 = NDTRegistration(1.0, 0.1, 0.01, 30)
+        reg0.SetInputTarget(small_map)
+        poses0, res0 = reg0.ScanMatchBatch(sources, guesses)
+    finally:
+        del os.environ["B2NDT_STREAM"]
+    assert np.array_equal(poses, poses0) and np.array_equal(res["iterations"], res0["iterations"])
+    assert np.array_equal(poses8, poses0) and np.array_equal(res8["pairs"], res0["pairs"])
+    assert res[7]["iterations"] == 0
