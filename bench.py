@@ -210,6 +210,11 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the registration path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # stdout carries exactly ONE line (the JSON): anything a library prints to fd 1 meanwhile (NCCL prints its
+    # version at communicator creation when NCCL_DEBUG=VERSION) goes to stderr; fd 1 is restored for the result
+    sys.stdout.flush()
+    saved_stdout_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     # a dedicated (non-default) stream: the library launches on it and the CUDA events are recorded on it
@@ -452,7 +457,10 @@ def main():
                               "sample": "%d of the %d frames, oracle align, 1 thread" % (len(sample), B)} if cpu_value else None),
             "parity": parity,
         }
+        sys.stdout.flush()
+        os.dup2(saved_stdout_fd, 1)
         print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
