@@ -244,7 +244,7 @@ def main():
                                                                      nthreads, gpu_filter)
     B = len(sources)
     reg = NDTRegistration(NDT["res"], NDT["step_size"], NDT["trans_eps"], NDT["max_iter"], device=local_rank)
-    reg.SetCluster(8, args.batch_cluster)
+    reg.SetCluster(16, args.batch_cluster)      # single ScanMatch: up to 16 CTAs per match (the library picks by size)
     t_tgt = time.perf_counter()
     reg.SetInputTarget(target)
     set_target_ms = 1e3 * (time.perf_counter() - t_tgt)

@@ -1029,8 +1029,13 @@ __global__ void __launch_bounds__(NDT_THREADS, NDT_MIN_CTAS) ndt_match_kernel(Gr
             if (C > 1) {
                 cluster.sync();
                 if (tid < NACC) {
+                    // all remote (DSMEM) loads are issued before the first one is consumed; summed in rank order
+                    double v[16];
+#pragma unroll
+                    for (unsigned r = 0; r < 16; ++r) v[r] = (r < C) ? *cluster.map_shared_rank(&SL.cta_part[parity][tid], r) : 0.0;
                     double tot = 0.0;
-                    for (unsigned r = 0; r < C; ++r) tot += *cluster.map_shared_rank(&SL.cta_part[parity][tid], r);
+#pragma unroll
+                    for (unsigned r = 0; r < 16; ++r) if (r < C) tot += v[r];
                     SL.raw_total[tid] = tot;
                 }
             } else {
@@ -1315,7 +1320,7 @@ struct b2ndt {
     const float4 *last_src = nullptr;     // device source of the last ScanMatch (GetFitnessScore)
     float last_pose[16];
     bool have_last = false;
-    int cl_single = 8, cl_batch = 1;
+    int cl_single = 16, cl_batch = 1;
     bool attrs_set = false, batch_attrs_set = false;
     bool use_batch_kernel = true;          // B2NDT_BATCH_KERNEL=0 falls back to one-match-per-CTA launches (A/B testing)
     int batch_ctas = 0;
@@ -1476,6 +1481,15 @@ static int build_target(b2ndt *h, const float4 *d_pts, size_t n, int nbits_hint)
         B2_LAUNCH_CHECK();
     }
     return 0;
+}
+
+// CTAs per single match: as many as give every search warp at most one round of 32 source points (a warp with two
+// rounds makes every CTA of the cluster wait at the pass barrier), capped by b2ndt_set_cluster; any size 1..16
+static int single_match_cluster(const b2ndt *h, size_t n) {
+    const size_t rounds = (n + 31) / 32;
+    size_t want = (rounds + NDT_NSW - 1) / NDT_NSW;
+    if (want < 1) want = 1;
+    return (int)(want < (size_t)h->cl_single ? want : (size_t)h->cl_single);
 }
 
 static int check_cloud_args(const char *fn, const void *pts, size_t n, size_t stride, size_t ioff) {
@@ -1772,8 +1786,7 @@ extern "C" int b2ndt_align(b2ndt *h, const void *src, size_t n, size_t stride, s
     if (rc) return rc;
     B2_CUDA(cudaSetDevice(h->device));
     // spread a single match over a cluster only when there is enough work per CTA
-    int C = h->cl_single;
-    while (C > 1 && (size_t)C * NDT_NSW * 32 > n) C >>= 1;
+    int C = single_match_cluster(h, n);
     rc = align_host(h, src, n, stride, ioff, nullptr, 1, guess, pose_out, res, C < 1 ? 1 : C);
     if (rc) return rc;
     h->last_n = n;
@@ -1822,8 +1835,7 @@ extern "C" int b2ndt_derivatives(b2ndt *h, const void *src, size_t n, size_t str
     memset(&A, 0, sizeof(A));
     A.src = h->d_src.as<float4>(); A.n_shared = (uint32_t)n; A.poses6 = h->d_p6.as<double>();
     A.acc_out = h->d_acc.as<double>(); A.deriv_only = 1;
-    int C = h->cl_single;
-    while (C > 1 && (size_t)C * NDT_NSW * 32 > n) C >>= 1;
+    int C = single_match_cluster(h, n);
     if ((rc = launch_match(h, A, 1, C < 1 ? 1 : C))) return rc;
     double *acc = h->h_res.as<double>();
     B2_CUDA(cudaMemcpyAsync(acc, h->d_acc.p, ACC_N * 8, cudaMemcpyDeviceToHost, h->st));
@@ -1929,8 +1941,7 @@ extern "C" int b2ndt_align_cloud(b2ndt *h, b2cloud *src, const float guess[16], 
     memset(&A, 0, sizeof(A));
     A.src = src->d(); A.n_shared = (uint32_t)n; A.guesses = h->d_guess.as<float>(); A.poses_out = h->d_pose.as<float>();
     A.results = h->d_res.as<b2ndt_result>();
-    int C = h->cl_single;
-    while (C > 1 && (size_t)C * NDT_NSW * 32 > n) C >>= 1;
+    int C = single_match_cluster(h, n);
     if ((rc = launch_match(h, A, 1, C < 1 ? 1 : C))) return rc;
     char *hres = h->h_res.as<char>();
     B2_CUDA(cudaMemcpyAsync(hres, h->d_pose.p, 64, cudaMemcpyDeviceToHost, h->st));

@@ -31,11 +31,11 @@ out["set_target_1M"] = dict(zip(("p50_ms", "min_ms"), med(lambda: reg.SetInputTa
 src = VoxelFilter(1.3, 1.3, 1.3).Filter(scan)[1]
 rng = np.random.default_rng(3)
 guess = synth.pose6_to_matrix(synth.perturb_pose(p, rng)).astype(np.float32)
-for C_ in (1, 2, 4, 8, 16):
+for C_ in (1, 2, 4, 8, 10, 11, 12, 16):
     reg.SetCluster(C_, 1)
     t = med(lambda: reg.ScanMatch(src, guess, want_cloud=False), 31, 5)
     out["align_cluster%d" % C_] = dict(p50_ms=t[0], min_ms=t[1], iterations=reg.last_result["iterations"], n_src=len(src))
-reg.SetCluster(8, 1)
+reg.SetCluster(16, 1)
 out["fitness"] = dict(zip(("p50_ms", "min_ms"), med(lambda: reg.GetFitnessScore())))
 out["align_raw_scan_120k_cluster16"] = None
 reg.SetCluster(16, 1)
