@@ -162,12 +162,31 @@ int  b2cloud_append_transformed(b2cloud *dst, b2cloud *src, const float T[16]);
 /* pcl::CropBox: dst = points of src with edge[0] <= x <= edge[1], edge[2] <= y <= edge[3],
  * edge[4] <= z <= edge[5] (BoxFilter::GetEdge order), input order kept, non-finite points dropped */
 int  b2cloud_box_filter(b2cloud *src, const float edge[6], b2cloud *dst);
+/* pcl::removeNaNFromPointCloud: dst = points of src with finite x, y, z, input order kept (front_end.cpp:92) */
+int  b2cloud_remove_nan(b2cloud *src, b2cloud *dst);
 /* VoxelFilter::Filter on device clouds (src == dst allowed) */
 int  b2vf_filter_cloud(b2vf *h, b2cloud *src, b2cloud *dst);
 /* SetInputTarget / ScanMatch on device clouds; result_cloud may be NULL */
 int  b2ndt_set_target_cloud(b2ndt *h, b2cloud *target);
 int  b2ndt_align_cloud(b2ndt *h, b2cloud *src, const float guess[16], float pose_out[16], b2ndt_result *res,
                        b2cloud *result_cloud);
+
+/* ------------------------------------------------------------------ initial-yaw search -------
+ * The matching node's position-only initialisation: Matching::generateGauss2DMapCells
+ * (matching.cpp:344-394: 2-D grid over the local map minus its origin, per cell the running mean / variance of z
+ * in input order) and Matching::getInitialYawAngle (matching.cpp:267-308: angle_size yaw bins, the scan rotated
+ * about z and scored against the grid, first maximal bin wins).  grid_resolution is the reference's double
+ * `grid_resolution` (clamped to >= 0.1, matching.cpp:138). */
+typedef struct b2hmap b2hmap;
+
+int  b2hmap_create(int device, double grid_resolution, b2hmap **out);
+void b2hmap_destroy(b2hmap *h);
+int  b2hmap_build(b2hmap *h, b2cloud *local_map, const float origin[3]);
+int  b2hmap_info(b2hmap *h, int32_t *width, int32_t *height, float min_xyz[3], float max_xyz[3]);
+/* cell arrays [width][height] (cell = x * height + y): mu, sigma, point_cnt; any may be NULL */
+int  b2hmap_cells(b2hmap *h, float *mu, float *sigma, int32_t *point_cnt);
+/* probs (angle_size doubles, may be NULL) receives the per-bin scores, *best_angle the winning yaw in radians */
+int  b2hmap_yaw_search(b2hmap *h, b2cloud *scan, int angle_size, double *probs, double *best_angle);
 
 #ifdef __cplusplus
 }

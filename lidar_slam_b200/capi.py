@@ -23,8 +23,9 @@ EXPORTS = [
     "b2ndt_derivatives", "b2ndt_fitness", "b2ndt_fitness_ex",
     "b2vf_create", "b2vf_destroy", "b2vf_set_stream", "b2vf_filter", "b2vf_filter_batch_device",
     "b2cloud_create", "b2cloud_destroy", "b2cloud_upload", "b2cloud_download", "b2cloud_size", "b2cloud_clear",
-    "b2cloud_device_ptr", "b2cloud_append_transformed", "b2cloud_box_filter", "b2vf_filter_cloud",
+    "b2cloud_device_ptr", "b2cloud_append_transformed", "b2cloud_box_filter", "b2cloud_remove_nan", "b2vf_filter_cloud",
     "b2ndt_set_target_cloud", "b2ndt_align_cloud",
+    "b2hmap_create", "b2hmap_destroy", "b2hmap_build", "b2hmap_info", "b2hmap_cells", "b2hmap_yaw_search",
 ]
 
 
@@ -109,9 +110,17 @@ def lib():
     L.b2cloud_device_ptr.argtypes = [vp, C.POINTER(vp)]
     L.b2cloud_append_transformed.argtypes = [vp, vp, fp]
     L.b2cloud_box_filter.argtypes = [vp, fp, vp]
+    L.b2cloud_remove_nan.argtypes = [vp, vp]
     L.b2vf_filter_cloud.argtypes = [vp, vp, vp]
     L.b2ndt_set_target_cloud.argtypes = [vp, vp]
     L.b2ndt_align_cloud.argtypes = [vp, vp, fp, fp, C.POINTER(Result), vp]
+    L.b2hmap_create.argtypes = [C.c_int, C.c_double, C.POINTER(vp)]
+    L.b2hmap_destroy.argtypes = [vp]
+    L.b2hmap_destroy.restype = None
+    L.b2hmap_build.argtypes = [vp, vp, fp]
+    L.b2hmap_info.argtypes = [vp, i32p, i32p, fp, fp]
+    L.b2hmap_cells.argtypes = [vp, fp, fp, i32p]
+    L.b2hmap_yaw_search.argtypes = [vp, vp, C.c_int, dp, dp]
     _LIB = L
     return L
 

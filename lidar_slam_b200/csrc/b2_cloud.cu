@@ -277,3 +277,11 @@ extern "C" int b2cloud_box_filter(b2cloud *src, const float edge[6], b2cloud *ds
     dst->n = *dst->h_small.as<uint32_t>();
     return 0;
 }
+
+// pcl::removeNaNFromPointCloud (front_end.cpp:92, matching.cpp:188): dst = the points of src whose x, y and z are
+// finite, input order kept.  Same compaction kernels as the crop with an unbounded box.
+extern "C" int b2cloud_remove_nan(b2cloud *src, b2cloud *dst) {
+    const float inf = __builtin_huge_valf();
+    const float edge[6] = {-inf, inf, -inf, inf, -inf, inf};
+    return b2cloud_box_filter(src, edge, dst);
+}

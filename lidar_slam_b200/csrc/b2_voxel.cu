@@ -531,6 +531,54 @@ int VoxPipeline::run(const float4 *d_pts, float lx, float ly, float lz, int nbit
     return 0;
 }
 
+__global__ void prepared_layout_kernel(VoxLayout *layouts, uint32_t *scalars, uint32_t B, uint32_t invalid_key, int nbits) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < B) {
+        VoxLayout L;
+        memset(&L, 0, sizeof(L));
+        L.ok = 1; L.ncells = invalid_key; L.nbits = nbits;
+        layouts[s] = L;
+    }
+    if (s == 0) { scalars[0] = (uint32_t)nbits; scalars[1] = 0u; }
+}
+
+int VoxPipeline::run_prepared(uint32_t invalid_key, int nbits, cudaStream_t st) {
+    const uint32_t nB = (uint32_t)B, nt = (uint32_t)ntiles;
+    uint32_t *sc = d_scalars.as<uint32_t>();
+    const TileDesc *tiles = d_tiles.as<TileDesc>();
+    const SegDesc *segs = d_segs.as<SegDesc>();
+    VoxLayout *lay = d_layouts.as<VoxLayout>();
+    prepared_layout_kernel<<<(nB + 127) / 128, 128, 0, st>>>(lay, sc, nB, invalid_key, nbits);
+    B2_LAUNCH_CHECK();
+    final_buf = 0;
+    if (nt) {
+        const int passes = (nbits + RADIX_BITS - 1) / RADIX_BITS;
+        for (int p = 0; p < passes; ++p) {
+            int shift = p * RADIX_BITS;
+            uint32_t *ki = d_keys[final_buf].as<uint32_t>(), *vi = d_vals[final_buf].as<uint32_t>();
+            uint32_t *ko = d_keys[final_buf ^ 1].as<uint32_t>(), *vo = d_vals[final_buf ^ 1].as<uint32_t>();
+            radix_hist_kernel<<<nt, SORT_THREADS, 0, st>>>(ki, tiles, segs, d_tilehist.as<uint32_t>(), shift, sc);
+            B2_LAUNCH_CHECK();
+            radix_scan_kernel<<<nB * (RADIX / (SORT_THREADS / 32)), SORT_THREADS, 0, st>>>(segs, d_tilehist.as<uint32_t>(), d_binbase.as<uint32_t>(), shift, sc);
+            B2_LAUNCH_CHECK();
+            radix_scatter_kernel<<<nt, SORT_THREADS, 0, st>>>(ki, vi, ko, vo, tiles, segs, d_tilehist.as<uint32_t>(),
+                                                             d_binbase.as<uint32_t>(), shift, sc);
+            B2_LAUNCH_CHECK();
+            final_buf ^= 1;
+        }
+        head_kernel<false><<<nt, SORT_THREADS, 0, st>>>(sorted_keys(), tiles, segs, lay, d_tile_heads.as<uint32_t>(), nullptr, nullptr);
+        B2_LAUNCH_CHECK();
+    }
+    scan_tiles_kernel<<<1, 1024, 0, st>>>(d_tile_heads.as<uint32_t>(), nt, segs, nB, d_run_seg_off.as<uint32_t>(), sc);
+    B2_LAUNCH_CHECK();
+    if (nt) {
+        head_kernel<true><<<nt, SORT_THREADS, 0, st>>>(sorted_keys(), tiles, segs, lay, d_tile_heads.as<uint32_t>(),
+                                                      d_run_start.as<uint32_t>(), d_run_seg.as<uint32_t>());
+        B2_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
 void VoxPipeline::release() {
     d_tiles.release(); d_segs.release(); d_bbox.release(); d_layouts.release(); d_scalars.release();
     for (int i = 0; i < 2; ++i) { d_keys[i].release(); d_vals[i].release(); }

@@ -38,6 +38,12 @@ struct VoxPipeline {
     // Run bbox/layout/keys/sort/run-heads on packed float4 points (device).  nbits_hint > 0 limits the
     // number of radix passes from the host side (must be >= the true key width); 0 = decide on device.
     int run(const float4 *d_pts, float lx, float ly, float lz, int nbits_hint, cudaStream_t st);
+    // Generic stable sort + run detection for keys the caller wrote itself: after plan(), fill keys0()/vals0() (one
+    // uint32 key per element, key == invalid_key drops the element to the end / out of the runs) and call this with
+    // the key width in bits.  Results as after run(): sorted_keys(), sorted_vals(), run_start(), scalars()[1] = runs.
+    int run_prepared(uint32_t invalid_key, int nbits, cudaStream_t st);
+    uint32_t *keys0() { return d_keys[0].as<uint32_t>(); }
+    uint32_t *vals0() { return d_vals[0].as<uint32_t>(); }
 
     const uint32_t *sorted_keys() const { return d_keys[final_buf].as<uint32_t>(); }
     const uint32_t *sorted_vals() const { return d_vals[final_buf].as<uint32_t>(); }

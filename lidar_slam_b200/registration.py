@@ -87,6 +87,13 @@ class DeviceCloud:
         capi.check(capi.lib().b2cloud_device_ptr(self._h, C.byref(p)))
         return p.value
 
+    def RemoveNaN(self, dst=None):
+        """pcl::removeNaNFromPointCloud (front_end.cpp:92): finite points of *this, order kept -> dst (new cloud if None)."""
+        if dst is None:
+            dst = DeviceCloud()
+        capi.check(capi.lib().b2cloud_remove_nan(self._h, dst._h))
+        return dst
+
     def AppendTransformed(self, src, pose):
         """*this += pcl::transformPointCloud(src, pose)  (front_end.cpp:402-407)."""
         T = capi.pose_to_colmajor(pose)
@@ -373,3 +380,48 @@ class VoxelFilter(CloudFilterInterface):
         capi.check(capi.lib().b2vf_filter_batch_device(self._h, C.c_void_p(d_in), n_total,
                                                        off.ctypes.data_as(C.POINTER(C.c_uint32)), len(off) - 1,
                                                        C.c_void_p(d_out), C.c_void_p(d_out_offsets)))
+
+
+class InitialYawSearch:
+    """The matching node's position-only initialisation (matching.cpp:327-342 SetInitPose with
+    init_type OnlyPosition, :344-394 generateGauss2DMapCells, :267-308 getInitialYawAngle) on device clouds."""
+
+    def __init__(self, grid_resolution=0.8, device=0):
+        self._h = C.c_void_p()
+        capi.check(capi.lib().b2hmap_create(int(device), float(grid_resolution), C.byref(self._h)))
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h and capi is not None and getattr(capi, "_LIB", None) is not None:
+            try:
+                capi._LIB.b2hmap_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    def GenerateGauss2DMapCells(self, local_map, origin):
+        """local_map: DeviceCloud (the BoxFilter crop around `origin`, matching.cpp:166-183)."""
+        o = np.asarray(origin, np.float32)
+        capi.check(capi.lib().b2hmap_build(self._h, local_map._h, capi._fp(o)))
+        return self.Info()
+
+    def Info(self):
+        w, h = C.c_int32(), C.c_int32()
+        mn, mx = np.zeros(3, np.float32), np.zeros(3, np.float32)
+        capi.check(capi.lib().b2hmap_info(self._h, C.byref(w), C.byref(h), capi._fp(mn), capi._fp(mx)))
+        return dict(width=w.value, height=h.value, min_xyz=mn, max_xyz=mx)
+
+    def Cells(self):
+        info = self.Info()
+        n = info["width"] * info["height"]
+        mu, sg, cnt = np.zeros(n, np.float32), np.zeros(n, np.float32), np.zeros(n, np.int32)
+        capi.check(capi.lib().b2hmap_cells(self._h, capi._fp(mu), capi._fp(sg), cnt.ctypes.data_as(C.POINTER(C.c_int32))))
+        shp = (info["width"], info["height"])
+        return mu.reshape(shp), sg.reshape(shp), cnt.reshape(shp)
+
+    def GetInitialYawAngle(self, scan, angle_size=270):
+        """scan: DeviceCloud in the sensor frame -> (best yaw in radians, per-bin scores)."""
+        probs = np.zeros(angle_size, np.float64)
+        best = C.c_double()
+        capi.check(capi.lib().b2hmap_yaw_search(self._h, scan._h, int(angle_size), capi._dp(probs), C.byref(best)))
+        return best.value, probs

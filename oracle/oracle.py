@@ -376,3 +376,88 @@ def transform_cloud(cloud, T):
     if fin.any():
         c[fin, :3] = transform_points(np.asarray(T, np.float32).reshape(4, 4), c[fin, :3])
     return c
+
+
+def gauss2d_map_cells(local_map, origin, grid_resolution=0.8):
+    """Matching::generateGauss2DMapCells + resetMapRange (lidar_localization/src/matching/matching.cpp:344-424) with the
+    reference's C++ arithmetic (float unless an operand is double; grid_map_resolution_ is double, std::pow(float, int)
+    is double).  Sequential over the points in input order.  TEST ORACLE (pure-Python loop: small maps only).
+    -> dict(width, height, min_xyz, max_xyz, mu[w,h], sigma[w,h], cnt[w,h])"""
+    f32 = np.float32
+    res = max(0.1, float(grid_resolution))
+    c = np.ascontiguousarray(local_map, dtype=np.float32)
+    fin = np.isfinite(c[:, :3]).all(axis=1)
+    pts = (c[fin, :3] - np.asarray(origin, f32)[None, :]).astype(f32)
+    mn = np.full(3, np.finfo(f32).max, f32)
+    mx = np.full(3, -np.finfo(f32).max, f32)
+    if len(pts):
+        mn = np.minimum(mn, pts.min(axis=0)); mx = np.maximum(mx, pts.max(axis=0))
+
+    def cround(v):                      # std::round: half away from zero
+        return float(np.floor(abs(v) + 0.5) * (1.0 if v >= 0 else -1.0))
+
+    w = int(cround(float(f32(mx[0] - mn[0])) / res)) if len(pts) else 0
+    h = int(cround(float(f32(mx[1] - mn[1])) / res)) if len(pts) else 0
+    mu = np.zeros((w, h), f32); sg = np.zeros((w, h), f32); cnt = np.zeros((w, h), np.int32)
+    cx = np.array([int(cround(float(f32(p - mn[0])) / res)) for p in pts[:, 0]], np.int64)
+    cy = np.array([int(cround(float(f32(p - mn[1])) / res)) for p in pts[:, 1]], np.int64)
+    for i in range(len(pts)):
+        x, y = cx[i], cy[i]
+        if x < 0 or y < 0 or x >= w or y >= h:
+            continue
+        z = f32(pts[i, 2]); m = mu[x, y]; s = sg[x, y]; n = int(cnt[x, y])
+        if n == 0:
+            mu[x, y] = z; sg[x, y] = 0; cnt[x, y] = 1
+        else:
+            mn_new = f32(f32(f32(f32(n) * m) + z) / f32(n + 1))
+            a = float(f32(f32(n - 1) * s))
+            b = float(f32(z - m)) ** 2
+            cc = float(n + 1) * (float(f32(mn_new - m)) ** 2)
+            d = float(f32(f32(f32(2) * f32(mn_new - m)) * f32(z - mn_new)))
+            tot = ((a + b) + cc) + d
+            sg[x, y] = f32(f32(tot) / f32(n))
+            mu[x, y] = mn_new
+            cnt[x, y] = n + 1
+    return dict(width=w, height=h, min_xyz=mn, max_xyz=mx, mu=mu, sigma=sg, cnt=cnt, res=res)
+
+
+def initial_yaw_angle(cells, scan, angle_size=270):
+    """Matching::getInitialYawAngle (matching.cpp:267-308) on the grid of gauss2d_map_cells.  float sin/cos here are
+    numpy's (the reference's are libm's): scores agree to float round-off, not bit for bit.  TEST ORACLE.
+    -> (best yaw angle, probs[angle_size])"""
+    f32 = np.float32
+    s = np.ascontiguousarray(scan, dtype=np.float32)
+    delta = f32(2 * np.pi / angle_size)
+    w, h, res = cells["width"], cells["height"], cells["res"]
+    mn = cells["min_xyz"]
+    probs = np.zeros(angle_size, np.float64)
+    x0, y0, z0 = s[:, 0], s[:, 1], s[:, 2]
+    for i in range(angle_size):
+        a = f32(delta * f32(i))
+        c, sn = f32(np.cos(np.float64(a))), f32(np.sin(np.float64(a)))       # correctly rounded float cos / sin
+        m22 = f32(f32(f32(1) - c) + c)
+        with np.errstate(invalid="ignore"):
+            x = ((c * x0 + (-sn) * y0) + f32(0) * z0) + f32(0)
+            y = ((sn * x0 + c * y0) + f32(0) * z0) + f32(0)
+            z = ((f32(0) * x0 + f32(0) * y0) + m22 * z0) + f32(0)
+        fin = np.isfinite(x) & np.isfinite(y) & np.isfinite(z)
+        with np.errstate(invalid="ignore", divide="ignore", over="ignore"):
+            qx = (x - mn[0]).astype(np.float64) / res
+            qy = (y - mn[1]).astype(np.float64) / res
+            cx = (np.floor(np.abs(qx) + 0.5) * np.sign(qx)); cy = (np.floor(np.abs(qy) + 0.5) * np.sign(qy))
+            ok = fin & (cx >= 0) & (cy >= 0) & (cx < w) & (cy < h)
+            ix, iy = cx[ok].astype(np.int64), cy[ok].astype(np.int64)
+            occ = cells["cnt"][ix, iy] > 0
+            ix, iy = ix[occ], iy[occ]
+            d = (z[ok][occ] - cells["mu"][ix, iy]).astype(np.float64)
+            term = np.exp(-(d * d) / (f32(2) * cells["sigma"][ix, iy]).astype(np.float64))
+        acc = 0.0
+        for t in term:                      # sequential double sum in point order
+            acc += t
+        probs[i] = acc
+    max_prob = -np.finfo(f32).max
+    best = 0.0
+    for it in range(angle_size):
+        if probs[it] > max_prob:
+            max_prob = f32(probs[it]); best = float(f32(f32(it) * delta))
+    return best, probs

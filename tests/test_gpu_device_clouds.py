@@ -118,3 +118,19 @@ def test_crop_then_target_like_matching_node(scene):
     Ld, Lh = reg_d.TargetLeaves(), reg_h.TargetLeaves()
     for k in ("idx", "n", "centroid", "mean", "icov"):
         assert np.array_equal(Ld[k], Lh[k], equal_nan=True), k
+
+
+def test_remove_nan_keeps_finite_points_in_order(scene):
+    """pcl::removeNaNFromPointCloud as front_end.cpp:92 / matching.cpp:188 call it before Filter + ScanMatch."""
+    from lidar_slam_b200.registration import DeviceCloud
+    scan = scene.scan(9, scene.path_pose(12.0)).copy()
+    rng = np.random.default_rng(2)
+    bad = rng.choice(len(scan), 500, replace=False)
+    scan[bad[:200], 0] = np.nan
+    scan[bad[200:350], 1] = np.inf
+    scan[bad[350:], 2] = -np.inf
+    scan[bad[:10], 3] = np.nan            # intensity is not tested by PCL
+    out = DeviceCloud(scan).RemoveNaN().Download()
+    keep = np.isfinite(scan[:, :3]).all(axis=1)
+    assert len(out) == keep.sum() and np.array_equal(out, scan[keep], equal_nan=True)
+    assert len(DeviceCloud(np.full((7, 4), np.nan, np.float32)).RemoveNaN()) == 0

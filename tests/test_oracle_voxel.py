@@ -136,3 +136,30 @@ def test_transform_cloud_oracle_keeps_intensity_and_nonfinite():
     out = O.transform_cloud(c, T)
     assert np.array_equal(out[0], np.array([2, 3, 4, 0.5], np.float32))
     assert np.isnan(out[1, 0]) and out[1, 3] == np.float32(0.7)
+
+
+def test_gauss2d_cells_and_yaw_oracle_small_case():
+    """Matching::generateGauss2DMapCells / getInitialYawAngle restatement: hand-checkable grid, heading recovered."""
+    from oracle import oracle as O
+    pts = np.array([[0, 0, 1, 0], [0.1, 0.1, 3, 0], [4, 0, 5, 0], [4, 4, 7, 0], [0, 4, 2, 0], [0.2, 0, 2, 0]], np.float32)
+    c = O.gauss2d_map_cells(pts, [0, 0, 0], 0.8)
+    assert c["width"] == 5 and c["height"] == 5           # round(4 / 0.8)
+    assert c["cnt"][0, 0] == 3 and c["mu"][0, 0] == np.float32(2.0)          # z = 1, 3, 2
+    assert c["cnt"].sum() == 3                             # the points on the max edge fall outside [0, width)
+    # the reference's recurrence for z = 1, 3, 2: after z=3: (0 + 4 + 2*1 + 2*1*1)/1 = 8; after z=2: (1*8 + 0 + 0 + 0)/2 = 4
+    assert c["sigma"][0, 0] == np.float32(4.0)
+    # an L-shaped wall: rotating the scan by the right yaw maximises the score
+    def world(seed, n):
+        rng = np.random.default_rng(seed)
+        w = np.concatenate([np.stack([rng.uniform(0, 20, n), np.zeros(n) + 10, rng.uniform(0, 3, n)], 1),
+                            np.stack([np.zeros(n) + 15, rng.uniform(-10, 10, n), rng.uniform(0, 3, n)], 1),
+                            np.stack([rng.uniform(-20, 20, 2 * n), rng.uniform(-20, 20, 2 * n), rng.normal(0, 0.02, 2 * n)], 1)])
+        return np.concatenate([w, np.zeros((len(w), 1))], 1).astype(np.float32)
+
+    cells = O.gauss2d_map_cells(world(0, 4000), [0, 0, 0], 0.8)
+    yaw = 1.0
+    R = np.array([[np.cos(-yaw), -np.sin(-yaw)], [np.sin(-yaw), np.cos(-yaw)]])
+    scan = world(1, 800)                                  # other samples of the same surfaces
+    scan[:, :2] = scan[:, :2] @ R.T                       # what the sensor sees when the vehicle is yawed by +1 rad
+    best, probs = O.initial_yaw_angle(cells, scan, 90)
+    assert abs(best - yaw) <= 2 * np.pi / 90

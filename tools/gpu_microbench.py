@@ -41,4 +41,15 @@ out["align_raw_scan_120k_cluster16"] = None
 reg.SetCluster(16, 1)
 t = med(lambda: reg.ScanMatch(scan, guess, want_cloud=False), 7, 2)
 out["align_raw_scan_120k_cluster16"] = dict(p50_ms=t[0], min_ms=t[1], iterations=reg.last_result["iterations"], n_src=len(scan))
+# position-only initialisation of the matching node (matching.cpp:327-342): crop +-100 m, height grid, 270-bin yaw scan
+from lidar_slam_b200.registration import BoxFilter, DeviceCloud, InitialYawSearch
+d_map = DeviceCloud(m1)
+box = BoxFilter([-100.0, 100.0, -100.0, 100.0, -100.0, 100.0]); box.SetOrigin(p[:3])
+d_local = box.FilterCloud(d_map)
+ys = InitialYawSearch(0.8)
+out["height_grid_build"] = dict(zip(("p50_ms", "min_ms"), med(lambda: ys.GenerateGauss2DMapCells(d_local, p[:3]), 9, 2)),
+                                local_map_points=len(d_local), info={k: (v.tolist() if hasattr(v, "tolist") else v) for k, v in ys.Info().items()})
+d_scan = DeviceCloud(scan)
+out["yaw_search_270_bins"] = dict(zip(("p50_ms", "min_ms"), med(lambda: ys.GetInitialYawAngle(d_scan, 270), 9, 2)), n_scan=len(scan),
+                                  best_yaw=ys.GetInitialYawAngle(d_scan, 270)[0], truth_yaw=float(p[5]))
 print(json.dumps(out, indent=1))
