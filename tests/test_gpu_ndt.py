@@ -318,3 +318,34 @@ def test_streamed_host_batch_equals_resident_batch(setup, scans, small_map):
     assert np.array_equal(poses, poses0) and np.array_equal(res["iterations"], res0["iterations"])
     assert np.array_equal(poses8, poses0) and np.array_equal(res8["pairs"], res0["pairs"])
     assert res[7]["iterations"] == 0
+
+
+@pytest.mark.gpu
+def test_batch_kernel_edge_cases(setup, scans, small_map):
+    """Persistent two-slot batch kernel: tiny batches (a slot with no work), far-off guesses that run to the iteration
+    cap, all-empty sources and a target without searchable voxels give the same answers as single matches."""
+    reg, grid, prm, srcs = setup
+    rng = np.random.default_rng(23)
+    guesses = [synth.pose6_to_matrix(synth.perturb_pose(scans[k % len(srcs)][0], rng)).astype(np.float32) for k in range(5)]
+    far = synth.pose6_to_matrix(scans[0][0] + np.array([6.0, -5.0, 1.0, 0.05, -0.04, 0.6])).astype(np.float32)
+    for B in (2, 3, 5):
+        sources = [srcs[k % len(srcs)] for k in range(B)]
+        g = list(guesses[:B])
+        g[B - 1] = far
+        poses, res = reg.ScanMatchBatch(sources, g)
+        for b in range(B):
+            ok, _, p1 = reg.ScanMatch(sources[b], g[b], want_cloud=False)
+            assert np.array_equal(p1, poses[b]), (B, b)
+            assert reg.last_result["iterations"] == res[b]["iterations"] and reg.last_result["pairs"] == res[b]["pairs"]
+    # every source empty
+    poses, res = reg.ScanMatchBatch([np.zeros((0, 4), np.float32)] * 4, guesses[:4])
+    assert all(r["iterations"] == 0 for r in res)
+    # a target whose voxels all hold fewer than min_points_per_voxel points: no pairs anywhere
+    sparse = small_map[::40].copy()
+    reg2 = NDTRegistration(0.3, 0.1, 0.01, 30)
+    reg2.SetInputTarget(sparse)
+    assert reg2.TargetInfo()["n_tree"] == 0
+    poses, res = reg2.ScanMatchBatch([srcs[0], srcs[1], srcs[0]], guesses[:3])
+    for b in range(3):
+        ok, _, p1 = reg2.ScanMatch([srcs[0], srcs[1], srcs[0]][b], guesses[b], want_cloud=False)
+        assert np.array_equal(p1, poses[b]) and res[b]["pairs"] == 0
