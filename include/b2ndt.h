@@ -164,6 +164,11 @@ int  b2cloud_append_transformed(b2cloud *dst, b2cloud *src, const float T[16]);
 int  b2cloud_box_filter(b2cloud *src, const float edge[6], b2cloud *dst);
 /* pcl::removeNaNFromPointCloud: dst = points of src with finite x, y, z, input order kept (front_end.cpp:92) */
 int  b2cloud_remove_nan(b2cloud *src, b2cloud *dst);
+/* DistortionAdjust::SetMotionInfo + AdjustCloud (src/models/scan_adjust/distortion_adjust.cpp:10-69): undo the sensor's
+ * motion inside one sweep of scan_period seconds (velocities in the sensor frame); drops point 0 and the 5 degree
+ * sector around the first point's azimuth, output intensity is 0, input order kept */
+int  b2cloud_distortion_adjust(b2cloud *src, float scan_period, const double linear_velocity[3],
+                               const double angular_velocity[3], b2cloud *dst);
 /* VoxelFilter::Filter on device clouds (src == dst allowed) */
 int  b2vf_filter_cloud(b2vf *h, b2cloud *src, b2cloud *dst);
 /* SetInputTarget / ScanMatch on device clouds; result_cloud may be NULL */

@@ -23,7 +23,7 @@ EXPORTS = [
     "b2ndt_derivatives", "b2ndt_fitness", "b2ndt_fitness_ex",
     "b2vf_create", "b2vf_destroy", "b2vf_set_stream", "b2vf_filter", "b2vf_filter_batch_device",
     "b2cloud_create", "b2cloud_destroy", "b2cloud_upload", "b2cloud_download", "b2cloud_size", "b2cloud_clear",
-    "b2cloud_device_ptr", "b2cloud_append_transformed", "b2cloud_box_filter", "b2cloud_remove_nan", "b2vf_filter_cloud",
+    "b2cloud_device_ptr", "b2cloud_append_transformed", "b2cloud_box_filter", "b2cloud_remove_nan", "b2cloud_distortion_adjust", "b2vf_filter_cloud",
     "b2ndt_set_target_cloud", "b2ndt_align_cloud",
     "b2hmap_create", "b2hmap_destroy", "b2hmap_build", "b2hmap_info", "b2hmap_cells", "b2hmap_yaw_search",
 ]
@@ -111,6 +111,7 @@ def lib():
     L.b2cloud_append_transformed.argtypes = [vp, vp, fp]
     L.b2cloud_box_filter.argtypes = [vp, fp, vp]
     L.b2cloud_remove_nan.argtypes = [vp, vp]
+    L.b2cloud_distortion_adjust.argtypes = [vp, C.c_float, dp, dp, vp]
     L.b2vf_filter_cloud.argtypes = [vp, vp, vp]
     L.b2ndt_set_target_cloud.argtypes = [vp, vp]
     L.b2ndt_align_cloud.argtypes = [vp, vp, fp, fp, C.POINTER(Result), vp]

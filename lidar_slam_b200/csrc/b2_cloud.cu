@@ -7,6 +7,8 @@
 //                 (callers: src/matching/matching.cpp:166-183, 255-262)
 // Both are HBM-streaming kernels: 16 B read + 16 B written per point kept, coalesced float4 accesses,
 // order-preserving (pcl::CropBox keeps the input order; operator+= appends).
+#include <cmath>
+
 #include "b2_cloud.cuh"
 
 namespace b2 {
@@ -31,22 +33,62 @@ __global__ void __launch_bounds__(256) transform_append_kernel(const float4 *__r
 constexpr int CROP_THREADS = 256;
 constexpr int CROP_PER_THREAD = 8;
 constexpr uint32_t CROP_TILE = CROP_THREADS * CROP_PER_THREAD;
-struct BoxArg { float mn[3], mx[3]; };
+// The compaction passes take a functor Op: bool op(point, index, out_point) -- keep the point? and what to write.
+struct BoxArg {
+    float mn[3], mx[3];
+    __device__ __forceinline__ bool operator()(const float4 p, uint32_t, float4 &out) const {
+        out = p;
+        if (!finite3(p.x, p.y, p.z)) return false;
+        return !(p.x < mn[0] || p.y < mn[1] || p.z < mn[2] || p.x > mx[0] || p.y > mx[1] || p.z > mx[2]);
+    }
+};
 
-__device__ __forceinline__ bool box_keep(const float4 p, const BoxArg &B) {
-    if (!finite3(p.x, p.y, p.z)) return false;
-    return !(p.x < B.mn[0] || p.y < B.mn[1] || p.z < B.mn[2] || p.x > B.mx[0] || p.y > B.mx[1] || p.z > B.mx[2]);
-}
+// DistortionAdjust::AdjustCloud (src/models/scan_adjust/distortion_adjust.cpp:16-69), one point:
+//   rotate about z so that the scan's first point has azimuth 0, azimuth -> time inside the sweep, undo the
+//   motion p' = Rz(wz t) Ry(wy t) Rx(wx t) p + v t, rotate back.  Point 0 and the 5 degree sector around azimuth 0
+//   are dropped; intensity is not carried over (the reference builds fresh points).
+struct DeskewArg {
+    float rin[9];        // rotation by -start_orientation (row-major)
+    float rout[9];       // rotation by +start_orientation
+    float vel[3], rate[3];
+    float scan_period;
+    __device__ __forceinline__ bool operator()(const float4 p, uint32_t i, float4 &out) const {
+        out = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i == 0) return false;
+        const float x = rin[0] * p.x + rin[1] * p.y + rin[2] * p.z;
+        const float y = rin[3] * p.x + rin[4] * p.y + rin[5] * p.z;
+        const float z = rin[6] * p.x + rin[7] * p.y + rin[8] * p.z;
+        float o = atan2f(y, x);
+        if (o < 0.0f) o = (float)((double)o + 2.0 * 3.14159265358979323846);
+        const float delete_space = (float)(5.0 * 3.14159265358979323846 / 180.0);
+        if (o < delete_space || (2.0 * 3.14159265358979323846 - (double)o) < (double)delete_space) return false;
+        const float t = (float)((double)fabsf(o) / (double)(float)(2.0 * 3.14159265358979323846) * (double)scan_period - (double)scan_period / 2.0);
+        float sx, cx, sy, cy, sz, cz;
+        sincosf(rate[0] * t, &sx, &cx);
+        sincosf(rate[1] * t, &sy, &cy);
+        sincosf(rate[2] * t, &sz, &cz);
+        const float x1 = x, y1 = cx * y - sx * z, z1 = sx * y + cx * z;             // Rx
+        const float x2 = cy * x1 + sy * z1, y2 = y1, z2 = -sy * x1 + cy * z1;       // Ry
+        const float x3 = cz * x2 - sz * y2, y3 = sz * x2 + cz * y2, z3 = z2;        // Rz
+        const float ax = x3 + vel[0] * t, ay = y3 + vel[1] * t, az = z3 + vel[2] * t;
+        out.x = rout[0] * ax + rout[1] * ay + rout[2] * az;
+        out.y = rout[3] * ax + rout[4] * ay + rout[5] * az;
+        out.z = rout[6] * ax + rout[7] * ay + rout[8] * az;
+        return true;
+    }
+};
 
 // pass 1: kept points per tile
-__global__ void __launch_bounds__(CROP_THREADS) crop_count_kernel(const float4 *__restrict__ src, uint32_t n, BoxArg B,
+template <class Op>
+__global__ void __launch_bounds__(CROP_THREADS) crop_count_kernel(const float4 *__restrict__ src, uint32_t n, Op B,
                                                                   uint32_t *__restrict__ tile_cnt) {
     __shared__ uint32_t wsum[CROP_THREADS / 32];
     uint32_t c = 0;
 #pragma unroll
     for (int r = 0; r < CROP_PER_THREAD; ++r) {
         const uint32_t i = blockIdx.x * CROP_TILE + r * CROP_THREADS + threadIdx.x;
-        if (i < n) c += box_keep(__ldg(&src[i]), B) ? 1u : 0u;
+        float4 o;
+        if (i < n) c += B(__ldg(&src[i]), i, o) ? 1u : 0u;
     }
     c = __reduce_add_sync(0xffffffffu, c);
     if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = c;
@@ -88,7 +130,8 @@ __global__ void __launch_bounds__(1024) crop_scan_kernel(uint32_t *__restrict__ 
 }
 
 // pass 3: stable scatter (input order kept): rank inside the tile = rounds before + warps before + lanes before
-__global__ void __launch_bounds__(CROP_THREADS) crop_scatter_kernel(const float4 *__restrict__ src, uint32_t n, BoxArg B,
+template <class Op>
+__global__ void __launch_bounds__(CROP_THREADS) crop_scatter_kernel(const float4 *__restrict__ src, uint32_t n, Op B,
                                                                     const uint32_t *__restrict__ tile_off, float4 *__restrict__ dst) {
     __shared__ uint32_t wcnt[CROP_THREADS / 32];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -98,7 +141,7 @@ __global__ void __launch_bounds__(CROP_THREADS) crop_scatter_kernel(const float4
         const uint32_t i = blockIdx.x * CROP_TILE + r * CROP_THREADS + threadIdx.x;
         float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
         bool keep = false;
-        if (i < n) { p = __ldg(&src[i]); keep = box_keep(p, B); }
+        if (i < n) { const float4 q = __ldg(&src[i]); keep = B(q, i, p); }
         const uint32_t b = __ballot_sync(0xffffffffu, keep);
         if (lane == 0) wcnt[w] = __popc(b);
         __syncthreads();
@@ -248,19 +291,18 @@ extern "C" int b2cloud_append_transformed(b2cloud *dst, b2cloud *src, const floa
     return 0;
 }
 
-extern "C" int b2cloud_box_filter(b2cloud *src, const float edge[6], b2cloud *dst) {
-    int rc = cloud_check("b2cloud_box_filter", src);
+// order-preserving compaction of src into dst under Op (count per tile, scan, stable scatter)
+template <class Op>
+static int compact_cloud(const char *fn, b2cloud *src, b2cloud *dst, const Op &B) {
+    int rc = cloud_check(fn, src);
     if (rc) return rc;
-    if ((rc = cloud_check("b2cloud_box_filter", dst))) return rc;
-    if (!edge) { set_error("b2cloud_box_filter: NULL edge"); return B2_ERR_INVALID; }
-    if (dst == src) { set_error("b2cloud_box_filter: dst == src"); return B2_ERR_INVALID; }
-    if (dst->device != src->device) { set_error("b2cloud_box_filter: clouds live on different devices"); return B2_ERR_INVALID; }
+    if ((rc = cloud_check(fn, dst))) return rc;
+    if (dst == src) { set_error("%s: dst == src", fn); return B2_ERR_INVALID; }
+    if (dst->device != src->device) { set_error("%s: clouds live on different devices", fn); return B2_ERR_INVALID; }
     B2_CUDA(cudaSetDevice(dst->device));
     dst->n = 0;
     const size_t n = src->n;
     if (n == 0) return 0;
-    BoxArg B;
-    for (int a = 0; a < 3; ++a) { B.mn[a] = edge[2 * a]; B.mx[a] = edge[2 * a + 1]; }
     const uint32_t ntiles = (uint32_t)((n + CROP_TILE - 1) / CROP_TILE);
     if ((rc = dst->reserve(n))) return rc;
     if ((rc = dst->scratch.reserve((size_t)(ntiles + 1) * 4 + 256))) return rc;
@@ -276,6 +318,42 @@ extern "C" int b2cloud_box_filter(b2cloud *src, const float edge[6], b2cloud *ds
     B2_CUDA(cudaStreamSynchronize(dst->st));
     dst->n = *dst->h_small.as<uint32_t>();
     return 0;
+}
+
+extern "C" int b2cloud_box_filter(b2cloud *src, const float edge[6], b2cloud *dst) {
+    if (!edge) { set_error("b2cloud_box_filter: NULL edge"); return B2_ERR_INVALID; }
+    BoxArg B;
+    for (int a = 0; a < 3; ++a) { B.mn[a] = edge[2 * a]; B.mx[a] = edge[2 * a + 1]; }
+    return compact_cloud("b2cloud_box_filter", src, dst, B);
+}
+
+// DistortionAdjust::SetMotionInfo + AdjustCloud (distortion_adjust.cpp:10-69): scan_period in seconds, velocities of
+// the sensor in its own frame (VelocityData linear / angular, double in the reference, used as float).
+extern "C" int b2cloud_distortion_adjust(b2cloud *src, float scan_period, const double linear_velocity[3],
+                                         const double angular_velocity[3], b2cloud *dst) {
+    if (!src || !dst || !linear_velocity || !angular_velocity) { set_error("b2cloud_distortion_adjust: NULL argument"); return B2_ERR_INVALID; }
+    if (src->n == 0) { dst->n = 0; return 0; }
+    B2_CUDA(cudaSetDevice(src->device));
+    int rc;
+    if ((rc = src->h_small.reserve(256))) return rc;
+    // start_orientation = atan2(points[0].y, points[0].x)
+    B2_CUDA(cudaMemcpyAsync(src->h_small.p, src->pts.p, 16, cudaMemcpyDeviceToHost, src->st));
+    B2_CUDA(cudaStreamSynchronize(src->st));
+    const float *p0 = src->h_small.as<float>();
+    const float start = atan2f(p0[1], p0[0]);
+    const float c = (float)std::cos((double)start), s = (float)std::sin((double)start);
+    DeskewArg D;
+    const float rot[9] = {c, -s, 0.f, s, c, 0.f, 0.f, 0.f, 1.f};          // AngleAxisf(start, UnitZ).matrix()
+    const float inv[9] = {c, s, 0.f, -s, c, 0.f, 0.f, 0.f, 1.f};          // its inverse
+    for (int k = 0; k < 9; ++k) { D.rin[k] = inv[k]; D.rout[k] = rot[k]; }
+    const float v[3] = {(float)linear_velocity[0], (float)linear_velocity[1], (float)linear_velocity[2]};
+    const float w[3] = {(float)angular_velocity[0], (float)angular_velocity[1], (float)angular_velocity[2]};
+    for (int r = 0; r < 3; ++r) {                                         // velocity_ = rotate_matrix * velocity_ (:31-32)
+        D.vel[r] = rot[3 * r] * v[0] + rot[3 * r + 1] * v[1] + rot[3 * r + 2] * v[2];
+        D.rate[r] = rot[3 * r] * w[0] + rot[3 * r + 1] * w[1] + rot[3 * r + 2] * w[2];
+    }
+    D.scan_period = scan_period;
+    return compact_cloud("b2cloud_distortion_adjust", src, dst, D);
 }
 
 // pcl::removeNaNFromPointCloud (front_end.cpp:92, matching.cpp:188): dst = the points of src whose x, y and z are

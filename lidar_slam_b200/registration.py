@@ -425,3 +425,33 @@ class InitialYawSearch:
         best = C.c_double()
         capi.check(capi.lib().b2hmap_yaw_search(self._h, scan._h, int(angle_size), capi._dp(probs), C.byref(best)))
         return best.value, probs
+
+
+class DistortionAdjust:
+    """DistortionAdjust (lidar_localization/src/models/scan_adjust/distortion_adjust.cpp): SetMotionInfo(scan_period,
+    velocity) then AdjustCloud(cloud).  velocity = (linear xyz, angular xyz) in the sensor frame.  Unlike the reference,
+    whose AdjustCloud rotates its stored velocities in place (so SetMotionInfo has to precede every call, as
+    data_pretreat_flow does), the stored motion is left untouched."""
+
+    def __init__(self, device=0):
+        self.device = int(device)
+        self.scan_period_ = 0.1
+        self.velocity_ = np.zeros(3, np.float64)
+        self.angular_rate_ = np.zeros(3, np.float64)
+
+    def SetMotionInfo(self, scan_period, linear_velocity, angular_velocity):
+        self.scan_period_ = float(np.float32(scan_period))
+        self.velocity_ = np.ascontiguousarray(linear_velocity, np.float64)
+        self.angular_rate_ = np.ascontiguousarray(angular_velocity, np.float64)
+
+    def AdjustCloudDevice(self, src, dst=None):
+        if dst is None:
+            dst = DeviceCloud(device=self.device)
+        capi.check(capi.lib().b2cloud_distortion_adjust(src._h, self.scan_period_, capi._dp(self.velocity_),
+                                                        capi._dp(self.angular_rate_), dst._h))
+        return dst
+
+    def AdjustCloud(self, input_cloud):
+        """-> (True, adjusted cloud) in the layout of the input."""
+        a = np.asarray(input_cloud)
+        return True, self.AdjustCloudDevice(DeviceCloud(input_cloud, device=self.device)).Download(layout=a.shape[1])

@@ -461,3 +461,75 @@ def initial_yaw_angle(cells, scan, angle_size=270):
         if probs[it] > max_prob:
             max_prob = f32(probs[it]); best = float(f32(f32(it) * delta))
     return best, probs
+
+
+# ------------------------------------------------------------------ scan de-skew (data_pretreat) -------------
+_DESKEW = None
+
+
+def deskew_ref_lib():
+    """oracle/_ref/libdeskew_ref.so: the reference's own distortion_adjust.cpp compiled against stub headers."""
+    global _DESKEW
+    if _DESKEW is not None:
+        return _DESKEW
+    path = os.path.join(_HERE, "_ref", "libdeskew_ref.so")
+    if not os.path.exists(path):
+        return None
+    R = C.CDLL(path)
+    R.ref_distortion_adjust.argtypes = [C.POINTER(C.c_float), C.c_int, C.c_float, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                        C.POINTER(C.c_float), C.c_int]
+    R.ref_distortion_adjust.restype = C.c_int
+    _DESKEW = R
+    return R
+
+
+def distortion_adjust_reference(cloud, scan_period, linear_velocity, angular_velocity):
+    """Run the reference's own DistortionAdjust::AdjustCloud (only where oracle/_ref was built)."""
+    R = deskew_ref_lib()
+    c = np.ascontiguousarray(cloud, dtype=np.float32)
+    out = np.zeros_like(c)
+    lin = np.ascontiguousarray(linear_velocity, np.float64); ang = np.ascontiguousarray(angular_velocity, np.float64)
+    m = R.ref_distortion_adjust(_fp(c), len(c), float(scan_period), _dp(lin), _dp(ang), _fp(out), len(c))
+    return out[:m].copy()
+
+
+def distortion_adjust(cloud, scan_period, linear_velocity, angular_velocity):
+    """DistortionAdjust::AdjustCloud (lidar_localization/src/models/scan_adjust/distortion_adjust.cpp:16-69) restated in
+    float64 numpy (the reference computes in float through Eigen: agreement is to float round-off, ~1e-5 m):
+      * the scan is rotated about z so that its first point has azimuth 0 (:22-29); velocity and angular rate are
+        rotated by the SAME (not the inverse) matrix (:31-32);
+      * point 0 is skipped (:34); a point with azimuth o in [0, 2 pi) is dropped inside the 5 degree sector around
+        0 (:39-40); its time is o / (2 pi) * period - period / 2 (:42);
+      * p' = Rz(wz t) Ry(wy t) Rx(wx t) p + v t (:48-51, UpdateMatrix :60-68); intensity is NOT carried over (:52-56);
+      * the result is rotated back (:59).
+    The sector test is evaluated in float like the reference.  TEST ORACLE.  -> (n_out, 4) float32"""
+    c = np.ascontiguousarray(cloud, dtype=np.float32)
+    if len(c) == 0:
+        return np.zeros((0, 4), np.float32)
+    f32 = np.float32
+    start = np.arctan2(f32(c[0, 1]), f32(c[0, 0])).astype(f32)
+    cs, sn = np.cos(np.float64(start)), np.sin(np.float64(start))
+    R = np.array([[cs, -sn, 0.0], [sn, cs, 0.0], [0.0, 0.0, 1.0]])
+    Rinv = R.T
+    p = c[:, :3].astype(np.float64) @ Rinv.T
+    vel = R @ np.asarray(linear_velocity, np.float64).astype(f32).astype(np.float64)
+    rate = R @ np.asarray(angular_velocity, np.float64).astype(f32).astype(np.float64)
+    pf = p.astype(f32)
+    o = np.arctan2(pf[:, 1], pf[:, 0]).astype(f32)
+    o = np.where(o < 0, (o.astype(np.float64) + 2.0 * np.pi).astype(f32), o)
+    delete_space = f32(5.0 * np.pi / 180.0)
+    keep = ~((o < delete_space) | ((2.0 * np.pi - o.astype(np.float64)) < np.float64(delete_space)))
+    keep[0] = False
+    t = (np.abs(o.astype(np.float64)) / np.float64(f32(2.0 * np.pi)) * np.float64(f32(scan_period)) - np.float64(f32(scan_period)) / 2.0)
+    t = t.astype(f32).astype(np.float64)[keep]
+    q = p[keep]
+    ax, ay, az = rate[0] * t, rate[1] * t, rate[2] * t
+    cx, sx, cy, sy, cz, sz = np.cos(ax), np.sin(ax), np.cos(ay), np.sin(ay), np.cos(az), np.sin(az)
+    # Rz Ry Rx applied to q
+    x1, y1, z1 = q[:, 0], cx * q[:, 1] - sx * q[:, 2], sx * q[:, 1] + cx * q[:, 2]
+    x2, y2, z2 = cy * x1 + sy * z1, y1, -sy * x1 + cy * z1
+    x3, y3, z3 = cz * x2 - sz * y2, sz * x2 + cz * y2, z2
+    adj = np.stack([x3, y3, z3], 1) + vel[None, :] * t[:, None]
+    out = np.zeros((len(adj), 4), np.float32)
+    out[:, :3] = (adj @ R.T).astype(f32)
+    return out

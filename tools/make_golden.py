@@ -182,8 +182,27 @@ def intree_ndt():
     print("intree_ndt.npz: voxels", len(ijk), "iterations", al_it)
 
 
+def deskew():
+    """Outputs of the reference's OWN DistortionAdjust (oracle/_ref/libdeskew_ref.so = distortion_adjust.cpp compiled
+    where it lies against oracle/ref_stubs + the vendored Eigen) on a seeded synthetic sweep."""
+    from lidar_slam_b200 import synth
+    scene = synth.Scene(leg=60.0)
+    scan = scene.scan(31, scene.path_pose(14.0))[::16].copy()
+    cases = []
+    for lin, ang, period in (([8.0, 0.3, -0.1], [0.02, -0.01, 0.35], 0.1), ([0.0, 0.0, 0.0], [0.0, 0.0, 0.0], 0.1),
+                             ([-3.0, 1.5, 0.2], [0.3, 0.2, -0.6], 0.05)):
+        out = O.distortion_adjust_reference(scan, period, lin, ang)
+        cases.append((np.array(lin), np.array(ang), period, out))
+    np.savez_compressed(os.path.join(OUT, "deskew.npz"), scan=scan,
+                        lin=np.stack([c[0] for c in cases]), ang=np.stack([c[1] for c in cases]),
+                        period=np.array([c[2] for c in cases]), n_out=np.array([len(c[3]) for c in cases]),
+                        **{"out%d" % i: c[3] for i, c in enumerate(cases)})
+    print("deskew.npz: scan", len(scan), "outputs", [len(c[3]) for c in cases])
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     eigen_numerics()
     ndt_small()
     intree_ndt()
+    deskew()
