@@ -44,3 +44,37 @@ def gather_rows(local_rows, n_items, dist=None, device=None):
 def best_hypothesis(rows, score_col=0):
     """config 5: index of the best-scoring hypothesis (highest NDT score)."""
     return int(np.argmax(rows[:, score_col]))
+
+
+def scan_match_batch_multi_device(registrations, sources, predict_poses):
+    """One process, several devices: `registrations` holds one NDTRegistration per device (each with the
+    same target set); the batch is split into contiguous blocks, every block runs on its own host thread / handle /
+    stream, and the results come back in batch order.  No communication between the devices.
+    -> (poses (B,4,4) float32, results structured array)"""
+    import threading
+    B = len(predict_poses)
+    shared = not isinstance(sources, (list, tuple))
+    world = len(registrations)
+    out = [None] * world
+    err = [None] * world
+
+    def work(r):
+        lo, hi = shard_range(B, r, world)
+        if hi == lo:
+            return
+        try:
+            src = sources if shared else list(sources[lo:hi])
+            out[r] = registrations[r].ScanMatchBatch(src, list(predict_poses[lo:hi]))
+        except Exception as e:      # surfaced on the caller's thread
+            err[r] = e
+
+    threads = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for e in err:
+        if e is not None:
+            raise e
+    parts = [o for o in out if o is not None]
+    return np.concatenate([p[0] for p in parts], axis=0), np.concatenate([p[1] for p in parts], axis=0)

@@ -349,3 +349,31 @@ def test_batch_kernel_edge_cases(setup, scans, small_map):
     for b in range(3):
         ok, _, p1 = reg2.ScanMatch([srcs[0], srcs[1], srcs[0]][b], guesses[b], want_cloud=False)
         assert np.array_equal(p1, poses[b]) and res[b]["pairs"] == 0
+
+
+@pytest.mark.gpu
+def test_one_process_several_handles_in_threads(setup, scans, small_map):
+    """one host thread + handle + stream per device from ONE process.  On a single-GPU box the handles
+    share device 0; results equal the single-handle batch, so handles are independent and the library is safe to
+    drive from several threads (one handle per thread)."""
+    import torch
+    from lidar_slam_b200 import batch
+    reg, grid, prm, srcs = setup
+    ndev = max(1, torch.cuda.device_count())
+    regs = []
+    for r in range(3):
+        h = NDTRegistration(1.0, 0.1, 0.01, 30, device=r % ndev)
+        h.SetInputTarget(small_map)
+        regs.append(h)
+    rng = np.random.default_rng(31)
+    B = 41
+    sources = [srcs[b % len(srcs)][: len(srcs[b % len(srcs)]) - (b % 5)] for b in range(B)]
+    guesses = [synth.pose6_to_matrix(synth.perturb_pose(scans[b % len(srcs)][0], rng)).astype(np.float32) for b in range(B)]
+    poses, res = batch.scan_match_batch_multi_device(regs, sources, guesses)
+    poses1, res1 = reg.ScanMatchBatch(sources, guesses)
+    assert np.array_equal(poses, poses1) and np.array_equal(res["iterations"], res1["iterations"])
+    assert np.array_equal(res["pairs"], res1["pairs"])
+    # one shared source x B hypotheses (config 5), split over the handles
+    ph, rh = batch.scan_match_batch_multi_device(regs, srcs[0], guesses)
+    p1, r1 = reg.ScanMatchBatch(srcs[0], guesses)
+    assert np.array_equal(ph, p1) and np.array_equal(rh["iterations"], r1["iterations"])
