@@ -1001,7 +1001,9 @@ __global__ void __launch_bounds__(NDT_THREADS, NDT_MIN_CTAS) ndt_match_kernel(Gr
         const int sw = warp - NDT_NCW;
         SearchState st;
         while (true) {
-            search_pass(S, G, A.src, first, last, first + (crank * NDT_NSW + sw) * 32u, stride, SL.ctl.T, sw, lane, st);
+            // rounds are dealt out CTA-first (round = sw * C + crank): the source is in voxel order, so consecutive
+            // rounds are spatial neighbours with similar hit counts and every CTA gets an even sample of the scan
+            search_pass(S, G, A.src, first, last, first + (sw * C + crank) * 32u, stride, SL.ctl.T, sw, lane, st);
             cta_barrier();                          // (1) all pairs of the pass consumed, partials written
             if (C > 1) cluster.sync();
             cta_barrier();                          // (2) totals ready
