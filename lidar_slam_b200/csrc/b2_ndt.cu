@@ -1173,7 +1173,10 @@ __global__ void __launch_bounds__(NDT_THREADS, NDT_MIN_CTAS) ndt_batch_kernel(Gr
                 const bool live = compute_drain(S, G, K, SL.ctl, warp, lane, ds, SL.warp_part[warp]);
                 if (!live) { if (s) dead1 = true; else dead0 = true; continue; }
                 TMB_LAP(1);                                    // [1] draining (incl. waiting for chunks)
-                if (warp != s) {
+                // the controller role of a slot rotates over the compute warps pass by pass (every warp knows the
+                // slot's pass count), so the Newton steps do not always delay the same two ring consumers
+                const int ctl_warp = (s + NDT_SLOTS * (int)(seen_s & 1u)) % NDT_NCW;
+                if (warp != ctl_warp) {
                     // hand the partial sums to the slot's controller warp and move on
                     __syncwarp();
                     asm volatile("bar.arrive %0, %1;" ::"r"(1 + s), "n"(NDT_NCW * 32) : "memory");
