@@ -40,6 +40,7 @@ class BoxFilter : public CloudFilterInterface {
     std::vector<float> origin_;
     std::vector<float> size_;
     std::vector<float> edge_;
+    decltype(CloudData::CLOUD().points) tmp_;      // output staging, reused across calls
 };
 }  // namespace lidar_localization
 #endif

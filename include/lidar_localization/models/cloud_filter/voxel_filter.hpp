@@ -6,6 +6,8 @@
 #ifndef LIDAR_LOCALIZATION_MODELS_CLOUD_FILTER_VOXEL_FILTER_HPP_
 #define LIDAR_LOCALIZATION_MODELS_CLOUD_FILTER_VOXEL_FILTER_HPP_
 
+#include <vector>
+
 #include "b2ndt.h"
 #include "lidar_localization/models/cloud_filter/cloud_filter_interface.hpp"
 
@@ -27,6 +29,7 @@ class VoxelFilter : public CloudFilterInterface {
 
   private:
     b2vf* vf_ = nullptr;
+    decltype(CloudData::CLOUD().points) tmp_;   // output staging (same vector type / allocator as the cloud), reused across calls
 };
 }  // namespace lidar_localization
 #endif

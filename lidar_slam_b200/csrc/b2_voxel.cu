@@ -755,10 +755,15 @@ extern "C" int b2vf_filter(b2vf *h, const void *in, size_t n, size_t stride, siz
         // large packed cloud: DMA straight from the caller's memory (full PCIe rate when it is pinned, the
         // driver's staging otherwise); the key width is then decided on the device
         h2d_from = in;
-    } else {
+    } else if (n > 400000) {
+        // big cloud: the (threaded) repack also bounds the key width, which saves whole radix passes over N keys
         float mn[3], mx[3];
         pack_cloud_f4_bbox(in, n, stride, ioff, h->h_in.as<float>(), mn, mx);
         nbits_hint = key_bits_from_bbox(mn, mx, h->leaf[0], h->leaf[1], h->leaf[2]);
+    } else {
+        // a scan: a plain (vectorisable) repack is cheaper than a bounding-box pass on one host core, and a radix
+        // pass over ~1e5 keys costs microseconds; the key width is decided on the device
+        pack_cloud_f4(in, n, stride, ioff, h->h_in.as<float>());
     }
     B2_CUDA(cudaMemcpyAsync(h->d_in.p, h2d_from, n * 16, cudaMemcpyHostToDevice, h->st));
     uint32_t off[2] = {0u, (uint32_t)n};

@@ -36,17 +36,16 @@ BoxFilter::~BoxFilter() {
 
 bool BoxFilter::Filter(const CloudData::CLOUD_PTR& input_cloud_ptr, CloudData::CLOUD_PTR& output_cloud_ptr) {
     const std::size_t n = input_cloud_ptr->points.size();
-    std::vector<CloudData::POINT> tmp(n);
+    if (tmp_.size() < n) tmp_.resize(n);           // staging that only grows (no per-call construction of n points)
     std::size_t m = 0;
     if (!in_ || !out_ || b2cloud_upload(in_, input_cloud_ptr->points.data(), n, kStride, kIntensityOffset) != B2_OK ||
         b2cloud_box_filter(in_, edge_.data(), out_) != B2_OK ||
-        b2cloud_download(out_, tmp.data(), n, kStride, kIntensityOffset, &m) != B2_OK) {
+        b2cloud_download(out_, tmp_.data(), n, kStride, kIntensityOffset, &m) != B2_OK) {
         std::cerr << "[BoxFilter::Filter] " << b2_last_error() << std::endl;
         return true;
     }
-    tmp.resize(m);
     CloudData::CLOUD& out = *output_cloud_ptr;     // output_cloud_ptr->clear() + filter, as the reference
-    out.points.assign(tmp.begin(), tmp.end());
+    out.points.assign(tmp_.begin(), tmp_.begin() + m);
     out.width = static_cast<uint32_t>(m);
     out.height = 1;
     out.is_dense = true;

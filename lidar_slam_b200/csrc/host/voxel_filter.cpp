@@ -38,17 +38,17 @@ bool VoxelFilter::SetFilterParam(float leaf_size_x, float leaf_size_y, float lea
 
 bool VoxelFilter::Filter(const CloudData::CLOUD_PTR& input_cloud_ptr, CloudData::CLOUD_PTR& filtered_cloud_ptr) {
     const std::size_t n = input_cloud_ptr->points.size();
-    // pcl::Filter::filter computes into a temporary when output aliases the input; same here
-    std::vector<CloudData::POINT> tmp(n);
+    // pcl::Filter::filter computes into a temporary when output aliases the input; same here.  The temporary is a
+    // member that only grows: constructing n points (3.7 MB for a raw HDL-64 frame) per call costs more than the filter
+    if (tmp_.size() < n) tmp_.resize(n);
     std::size_t m = 0;
-    if (!vf_ || b2vf_filter(vf_, input_cloud_ptr->points.data(), n, kStride, kIntensityOffset, tmp.data(), n, kStride,
+    if (!vf_ || b2vf_filter(vf_, input_cloud_ptr->points.data(), n, kStride, kIntensityOffset, tmp_.data(), n, kStride,
                             kIntensityOffset, &m, nullptr, nullptr) != B2_OK) {
         std::cerr << "[VoxelFilter::Filter] " << b2_last_error() << std::endl;
         return true;
     }
-    tmp.resize(m);
     CloudData::CLOUD& out = *filtered_cloud_ptr;
-    out.points.assign(tmp.begin(), tmp.end());
+    out.points.assign(tmp_.begin(), tmp_.begin() + m);
     out.width = static_cast<uint32_t>(m);
     out.height = 1;
     out.is_dense = true;

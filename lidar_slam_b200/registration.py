@@ -353,13 +353,14 @@ class VoxelFilter(CloudFilterInterface):
     def Filter(self, input_cloud, with_info=False):
         """-> (True, filtered_cloud) in the layout of the input; with_info adds (voxel idx, counts)."""
         a, ptr, n, stride, ioff = capi.cloud_args(input_cloud)
-        out = np.zeros_like(a)
+        out = np.empty_like(a)                  # the library writes every byte of the records it returns
         m = C.c_size_t(0)
-        idx = np.zeros(max(n, 1), np.int32)
-        cnt = np.zeros(max(n, 1), np.int32)
+        ip = C.POINTER(C.c_int32)
+        idx = np.empty(max(n, 1), np.int32) if with_info else None
+        cnt = np.empty(max(n, 1), np.int32) if with_info else None
         capi.check(capi.lib().b2vf_filter(self._h, ptr, n, stride, ioff, out.ctypes.data, n, stride, ioff, C.byref(m),
-                                          idx.ctypes.data_as(C.POINTER(C.c_int32)),
-                                          cnt.ctypes.data_as(C.POINTER(C.c_int32))))
+                                          idx.ctypes.data_as(ip) if with_info else None,
+                                          cnt.ctypes.data_as(ip) if with_info else None))
         M = m.value
         if with_info:
             return True, out[:M].copy(), idx[:M].copy(), cnt[:M].copy()
