@@ -312,7 +312,13 @@ constexpr int NACC = 35;                       // per-lane accumulators of a der
 constexpr int NDT_WARPS = NDT_NCW + NDT_NSW;
 constexpr int NDT_THREADS = NDT_WARPS * 32;
 constexpr int NDT_PPC = NDT_NSW / NDT_NCW;     // producers (search warps) per compute warp
-constexpr uint32_t RING = 512;                 // ring entries per search warp (power of two, >= 128 + 32)
+#ifndef NDT_RING
+#define NDT_RING 512
+#endif
+#ifndef NDT_DRAIN_SLEEP
+#define NDT_DRAIN_SLEEP 32
+#endif
+constexpr uint32_t RING = NDT_RING;            // ring entries per search warp (power of two, >= 128 + 32)
 static_assert(NDT_NCW % 4 == 0 && NDT_NSW % 4 == 0 && NDT_NSW % NDT_NCW == 0, "warp-group multiples");
 
 struct GridView {
@@ -915,7 +921,7 @@ __device__ __forceinline__ bool compute_drain(NdtSmem &S, const GridView &G, con
                             n = avail | 0x80000000u | (ld_vol(&S.pass_dead[sw][ds.pass_id & 3u]) ? 0x40000000u : 0u);
                             break;
                         }
-                        __nanosleep(32);
+                        __nanosleep(NDT_DRAIN_SLEEP);
                     }
                 }
                 n = __shfl_sync(0xffffffffu, n, 0);
