@@ -176,6 +176,17 @@ int  b2ndt_set_target_cloud(b2ndt *h, b2cloud *target);
 int  b2ndt_align_cloud(b2ndt *h, b2cloud *src, const float guess[16], float pose_out[16], b2ndt_result *res,
                        b2cloud *result_cloud);
 
+/* ------------------------------------------------------------------ PCD files ----------------
+ * PCD v0.7 I/O for PointXYZI clouds (pcl::io::loadPCDFile at matching.cpp:155, loop_closing.cpp:134,286,304;
+ * pcl::io::savePCDFileBinary at back_end.cpp:194, viewer.cpp:202,210).  DATA ascii and binary are read (any field
+ * set containing x y z, intensity optional), binary PointXYZI is written; binary_compressed is not supported.
+ * b2_pcd_read returns a malloc'ed packed {x,y,z,intensity} array (release with b2_pcd_free); host-only calls. */
+int  b2_pcd_read(const char *path, float **xyzi, size_t *n_points);
+void b2_pcd_free(float *xyzi);
+int  b2_pcd_write_binary(const char *path, const float *xyzi, size_t n_points);
+int  b2cloud_load_pcd(b2cloud *c, const char *path);
+int  b2cloud_save_pcd(b2cloud *c, const char *path);
+
 /* ------------------------------------------------------------------ initial-yaw search -------
  * The matching node's position-only initialisation: Matching::generateGauss2DMapCells
  * (matching.cpp:344-394: 2-D grid over the local map minus its origin, per cell the running mean / variance of z

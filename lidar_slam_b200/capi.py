@@ -25,6 +25,7 @@ EXPORTS = [
     "b2cloud_create", "b2cloud_destroy", "b2cloud_upload", "b2cloud_download", "b2cloud_size", "b2cloud_clear",
     "b2cloud_device_ptr", "b2cloud_append_transformed", "b2cloud_box_filter", "b2cloud_remove_nan", "b2cloud_distortion_adjust", "b2vf_filter_cloud",
     "b2ndt_set_target_cloud", "b2ndt_align_cloud",
+    "b2_pcd_read", "b2_pcd_free", "b2_pcd_write_binary", "b2cloud_load_pcd", "b2cloud_save_pcd",
     "b2hmap_create", "b2hmap_destroy", "b2hmap_build", "b2hmap_info", "b2hmap_cells", "b2hmap_yaw_search",
 ]
 
@@ -115,6 +116,12 @@ def lib():
     L.b2vf_filter_cloud.argtypes = [vp, vp, vp]
     L.b2ndt_set_target_cloud.argtypes = [vp, vp]
     L.b2ndt_align_cloud.argtypes = [vp, vp, fp, fp, C.POINTER(Result), vp]
+    L.b2_pcd_read.argtypes = [C.c_char_p, C.POINTER(fp), C.POINTER(sz)]
+    L.b2_pcd_free.argtypes = [fp]
+    L.b2_pcd_free.restype = None
+    L.b2_pcd_write_binary.argtypes = [C.c_char_p, fp, sz]
+    L.b2cloud_load_pcd.argtypes = [vp, C.c_char_p]
+    L.b2cloud_save_pcd.argtypes = [vp, C.c_char_p]
     L.b2hmap_create.argtypes = [C.c_int, C.c_double, C.POINTER(vp)]
     L.b2hmap_destroy.argtypes = [vp]
     L.b2hmap_destroy.restype = None
@@ -157,3 +164,23 @@ def pose_to_colmajor(T):
 
 def colmajor_to_pose(v):
     return np.asarray(v, np.float32).reshape(4, 4, order="F").copy()
+
+
+def pcd_read(path):
+    """pcl::io::loadPCDFile for PointXYZI clouds -> numpy (n,4) float32 {x,y,z,intensity} (host only)."""
+    p = C.POINTER(C.c_float)()
+    n = C.c_size_t(0)
+    check(lib().b2_pcd_read(os.fsencode(path), C.byref(p), C.byref(n)))
+    try:
+        out = np.ctypeslib.as_array(p, shape=(max(n.value, 1) * 4,))[:n.value * 4].reshape(-1, 4).copy() if n.value else np.zeros((0, 4), np.float32)
+    finally:
+        lib().b2_pcd_free(p)
+    return out
+
+
+def pcd_write_binary(path, cloud):
+    """pcl::io::savePCDFileBinary of a PointXYZI cloud given as numpy (n,4) or (n,8) (host only)."""
+    a = np.ascontiguousarray(cloud, dtype=np.float32)
+    if a.ndim == 2 and a.shape[1] == 8:
+        a = np.ascontiguousarray(np.concatenate([a[:, :3], a[:, 4:5]], axis=1))
+    check(lib().b2_pcd_write_binary(os.fsencode(path), _fp(a), a.shape[0]))

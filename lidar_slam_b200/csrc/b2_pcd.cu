@@ -1,0 +1,158 @@
+// b2_pcd.cu -- PCD v0.7 file I/O for PointXYZI clouds (host code; SURVEY 8(f) row 4: the on-disk format either side
+// of the hot path).  The reference reads maps and key frames with pcl::io::loadPCDFile (src/matching/matching.cpp:155,
+// src/mapping/loop_closing/loop_closing.cpp:134,286,304) and writes them with pcl::io::savePCDFileBinary
+// (src/mapping/back_end/back_end.cpp:194, src/mapping/viewer/viewer.cpp:202,210).  PCL is not available here, so this
+// follows the published PCD v0.7 format: an ASCII header (VERSION, FIELDS, SIZE, TYPE, COUNT, WIDTH, HEIGHT, VIEWPOINT,
+// POINTS, DATA) followed by ascii rows or packed binary records.  pcl::PointXYZI is stored as the four float32 fields
+// x y z intensity = 16 bytes per point, which is exactly the device layout {x,y,z,intensity}: a binary PointXYZI file is
+// uploaded without any repacking.  DATA binary_compressed (LZF) is not supported.
+#include <cerrno>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "b2_cloud.cuh"
+
+using namespace b2;
+
+namespace {
+struct PcdField { std::string name; int size = 4; char type = 'F'; int count = 1; size_t offset = 0; };
+
+double field_value(const unsigned char *p, const PcdField &f) {
+    switch (f.type) {
+        case 'F': if (f.size == 4) { float v; memcpy(&v, p, 4); return v; } else { double v; memcpy(&v, p, 8); return v; }
+        case 'U': if (f.size == 1) return *p; if (f.size == 2) { uint16_t v; memcpy(&v, p, 2); return v; }
+                  if (f.size == 4) { uint32_t v; memcpy(&v, p, 4); return v; } { uint64_t v; memcpy(&v, p, 8); return (double)v; }
+        default:  if (f.size == 1) return *(const signed char *)p; if (f.size == 2) { int16_t v; memcpy(&v, p, 2); return v; }
+                  if (f.size == 4) { int32_t v; memcpy(&v, p, 4); return v; } { int64_t v; memcpy(&v, p, 8); return (double)v; }
+    }
+}
+}  // namespace
+
+// Read a PCD file into a malloc'ed packed float4 {x,y,z,intensity} array (*xyzi, release with b2_pcd_free).
+extern "C" int b2_pcd_read(const char *path, float **xyzi, size_t *n_points) {
+    if (!path || !xyzi || !n_points) { set_error("b2_pcd_read: NULL argument"); return B2_ERR_INVALID; }
+    *xyzi = nullptr; *n_points = 0;
+    FILE *f = fopen(path, "rb");
+    if (!f) { set_error("b2_pcd_read: cannot open %s: %s", path, strerror(errno)); return B2_ERR_INVALID; }
+    std::vector<PcdField> fields;
+    size_t width = 0, height = 1, points = 0;
+    bool have_points = false;
+    std::string data;
+    char line[4096];
+    while (fgets(line, sizeof line, f)) {
+        if (line[0] == '#') continue;
+        std::vector<std::string> tok;
+        for (char *t = strtok(line, " \t\r\n"); t; t = strtok(nullptr, " \t\r\n")) tok.push_back(t);
+        if (tok.empty()) continue;
+        const std::string &k = tok[0];
+        if (k == "FIELDS" || k == "COLUMNS") { fields.assign(tok.size() - 1, PcdField()); for (size_t i = 1; i < tok.size(); ++i) fields[i - 1].name = tok[i]; }
+        else if (k == "SIZE")  { for (size_t i = 1; i < tok.size() && i - 1 < fields.size(); ++i) fields[i - 1].size = atoi(tok[i].c_str()); }
+        else if (k == "TYPE")  { for (size_t i = 1; i < tok.size() && i - 1 < fields.size(); ++i) fields[i - 1].type = tok[i][0]; }
+        else if (k == "COUNT") { for (size_t i = 1; i < tok.size() && i - 1 < fields.size(); ++i) fields[i - 1].count = atoi(tok[i].c_str()); }
+        else if (k == "WIDTH"  && tok.size() > 1) width = strtoull(tok[1].c_str(), nullptr, 10);
+        else if (k == "HEIGHT" && tok.size() > 1) height = strtoull(tok[1].c_str(), nullptr, 10);
+        else if (k == "POINTS" && tok.size() > 1) { points = strtoull(tok[1].c_str(), nullptr, 10); have_points = true; }
+        else if (k == "DATA"   && tok.size() > 1) { data = tok[1]; break; }
+    }
+    if (data.empty() || fields.empty()) { fclose(f); set_error("b2_pcd_read: %s has no PCD header (FIELDS / DATA)", path); return B2_ERR_INVALID; }
+    if (!have_points) points = width * height;
+    size_t stride = 0;
+    int fx = -1, fy = -1, fz = -1, fi = -1;
+    for (size_t i = 0; i < fields.size(); ++i) {
+        PcdField &fd = fields[i];
+        if (fd.size != 1 && fd.size != 2 && fd.size != 4 && fd.size != 8) { fclose(f); set_error("b2_pcd_read: bad SIZE %d", fd.size); return B2_ERR_INVALID; }
+        if (fd.count < 1) fd.count = 1;
+        fd.offset = stride;
+        stride += (size_t)fd.size * (size_t)fd.count;
+        if (fd.name == "x") fx = (int)i; else if (fd.name == "y") fy = (int)i; else if (fd.name == "z") fz = (int)i;
+        else if (fd.name == "intensity") fi = (int)i;
+    }
+    if (fx < 0 || fy < 0 || fz < 0) { fclose(f); set_error("b2_pcd_read: %s has no x / y / z fields", path); return B2_ERR_INVALID; }
+    if (points >= 0xFFFFFFF0ull) { fclose(f); set_error("b2_pcd_read: cloud too large"); return B2_ERR_INVALID; }
+    float *out = (float *)malloc(points ? points * 16 : 16);
+    if (!out) { fclose(f); set_error("b2_pcd_read: out of memory (%zu points)", points); return B2_ERR_INVALID; }
+    size_t got = 0;
+    if (data == "binary") {
+        const bool direct = fields.size() == 4 && fx == 0 && fy == 1 && fz == 2 && fi == 3 && stride == 16 &&
+                            fields[0].type == 'F' && fields[1].type == 'F' && fields[2].type == 'F' && fields[3].type == 'F';
+        if (direct) {
+            got = fread(out, 16, points, f);           // pcl::PointXYZI on disk == the device layout
+        } else {
+            std::vector<unsigned char> rec(stride);
+            for (; got < points && fread(rec.data(), stride, 1, f) == 1; ++got) {
+                out[4 * got + 0] = (float)field_value(rec.data() + fields[fx].offset, fields[fx]);
+                out[4 * got + 1] = (float)field_value(rec.data() + fields[fy].offset, fields[fy]);
+                out[4 * got + 2] = (float)field_value(rec.data() + fields[fz].offset, fields[fz]);
+                out[4 * got + 3] = fi >= 0 ? (float)field_value(rec.data() + fields[fi].offset, fields[fi]) : 0.f;
+            }
+        }
+    } else if (data == "ascii") {
+        while (got < points && fgets(line, sizeof line, f)) {
+            size_t col = 0;
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            bool any = false;
+            char *t = strtok(line, " \t\r\n");
+            for (size_t i = 0; i < fields.size() && t; ++i)
+                for (int c = 0; c < fields[i].count && t; ++c, ++col, t = strtok(nullptr, " \t\r\n")) {
+                    if (c) continue;
+                    const float val = (float)strtod(t, nullptr);        // "nan" parses to NaN as in PCL
+                    if ((int)i == fx) v[0] = val; else if ((int)i == fy) v[1] = val; else if ((int)i == fz) v[2] = val;
+                    else if ((int)i == fi) v[3] = val;
+                    any = true;
+                }
+            if (!any) continue;
+            memcpy(out + 4 * got, v, 16);
+            ++got;
+        }
+    } else {
+        fclose(f); free(out);
+        set_error("b2_pcd_read: DATA %s is not supported (ascii and binary are)", data.c_str());
+        return B2_ERR_INVALID;
+    }
+    fclose(f);
+    if (got != points) { free(out); set_error("b2_pcd_read: %s is truncated (%zu of %zu points)", path, got, points); return B2_ERR_INVALID; }
+    *xyzi = out; *n_points = points;
+    return 0;
+}
+
+extern "C" void b2_pcd_free(float *xyzi) { free(xyzi); }
+
+// Write packed float4 points as pcl::io::savePCDFileBinary writes a pcl::PointCloud<pcl::PointXYZI> (unorganised).
+extern "C" int b2_pcd_write_binary(const char *path, const float *xyzi, size_t n_points) {
+    if (!path || (n_points && !xyzi)) { set_error("b2_pcd_write_binary: NULL argument"); return B2_ERR_INVALID; }
+    FILE *f = fopen(path, "wb");
+    if (!f) { set_error("b2_pcd_write_binary: cannot open %s: %s", path, strerror(errno)); return B2_ERR_INVALID; }
+    fprintf(f, "# .PCD v0.7 - Point Cloud Data file format\nVERSION 0.7\nFIELDS x y z intensity\nSIZE 4 4 4 4\nTYPE F F F F\n"
+               "COUNT 1 1 1 1\nWIDTH %zu\nHEIGHT 1\nVIEWPOINT 0 0 0 1 0 0 0\nPOINTS %zu\nDATA binary\n", n_points, n_points);
+    const size_t w = n_points ? fwrite(xyzi, 16, n_points, f) : 0;
+    const int rc = fclose(f);
+    if (w != n_points || rc != 0) { set_error("b2_pcd_write_binary: short write to %s", path); return B2_ERR_INVALID; }
+    return 0;
+}
+
+// loadPCDFile straight into a device cloud / savePCDFileBinary from one
+extern "C" int b2cloud_upload(b2cloud *c, const void *pts, size_t n, size_t stride, size_t ioff);
+extern "C" int b2cloud_download(b2cloud *c, void *out, size_t capacity, size_t stride, size_t ioff, size_t *n);
+
+extern "C" int b2cloud_load_pcd(b2cloud *c, const char *path) {
+    if (!c) { set_error("b2cloud_load_pcd: NULL cloud handle"); return B2_ERR_INVALID; }
+    float *pts = nullptr;
+    size_t n = 0;
+    int rc = b2_pcd_read(path, &pts, &n);
+    if (rc) return rc;
+    rc = b2cloud_upload(c, pts, n, 16, 12);
+    free(pts);
+    return rc;
+}
+
+extern "C" int b2cloud_save_pcd(b2cloud *c, const char *path) {
+    if (!c) { set_error("b2cloud_save_pcd: NULL cloud handle"); return B2_ERR_INVALID; }
+    std::vector<float> host(c->n * 4 + 4);
+    size_t n = 0;
+    int rc = b2cloud_download(c, host.data(), c->n, 16, 12, &n);
+    if (rc) return rc;
+    return b2_pcd_write_binary(path, host.data(), n);
+}

@@ -87,6 +87,17 @@ class DeviceCloud:
         capi.check(capi.lib().b2cloud_device_ptr(self._h, C.byref(p)))
         return p.value
 
+    def LoadPCD(self, path):
+        """pcl::io::loadPCDFile(path, *cloud) (matching.cpp:155) straight into HBM."""
+        import os
+        capi.check(capi.lib().b2cloud_load_pcd(self._h, os.fsencode(path)))
+        return self
+
+    def SavePCD(self, path):
+        """pcl::io::savePCDFileBinary(path, *cloud) (back_end.cpp:194)."""
+        import os
+        capi.check(capi.lib().b2cloud_save_pcd(self._h, os.fsencode(path)))
+
     def RemoveNaN(self, dst=None):
         """pcl::removeNaNFromPointCloud (front_end.cpp:92): finite points of *this, order kept -> dst (new cloud if None)."""
         if dst is None:
