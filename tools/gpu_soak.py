@@ -1,0 +1,42 @@
+"""Soak test of the batch kernels on a GPU box: random batch sizes / compositions, every result compared with the
+same match run alone (bit for bit).  usage: python tools/gpu_soak.py [seconds]"""
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np  # noqa: E402
+
+from lidar_slam_b200 import synth  # noqa: E402
+from lidar_slam_b200.registration import NDTRegistration, VoxelFilter  # noqa: E402
+
+budget = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
+scene = synth.Scene(leg=120.0)
+target = scene.make_map(300000, 2.0)
+s = np.linspace(10.0, scene.path_length - 10.0, 24)
+truth = np.stack([scene.path_pose(v) for v in s])
+vf = VoxelFilter(1.3, 1.3, 1.3)
+srcs = [vf.Filter(r)[1] for r in scene.scans(9000 + np.arange(len(s)), truth)]
+reg = NDTRegistration(1.0, 0.1, 0.01, 30)
+reg.SetInputTarget(target)
+rng = np.random.default_rng(int(time.time()))
+single = {}
+t0 = time.time()
+rounds = matches = 0
+while time.time() - t0 < budget:
+    B = int(rng.choice([1, 2, 3, 4, 7, 16, 63, 64, 65, 255, 256, 257, 300, 600]))
+    ks = rng.integers(0, len(srcs), B)
+    cut = rng.integers(0, 40, B)
+    sources, guesses = [], []
+    for k, c in zip(ks, cut):
+        src = srcs[k][: len(srcs[k]) - c] if rng.random() > 0.02 else np.zeros((0, 4), np.float32)
+        sources.append(src)
+        scale = 1.0 if rng.random() > 0.05 else 8.0                      # a few far-off guesses (iteration cap)
+        guesses.append(synth.pose6_to_matrix(synth.perturb_pose(truth[k], rng, 0.5 * scale, 2.0 * scale)).astype(np.float32))
+    poses, res = reg.ScanMatchBatch(sources, guesses)
+    for b in rng.choice(B, min(B, 6), replace=False):
+        ok, _, p1 = reg.ScanMatch(sources[b], guesses[b], want_cloud=False)
+        assert np.array_equal(p1, poses[b], equal_nan=True), ("pose differs", B, b)
+        assert reg.last_result["iterations"] == res[b]["iterations"] and reg.last_result["pairs"] == res[b]["pairs"], (B, b)
+    rounds += 1; matches += B
+print("soak ok: %d batches, %d matches in %.0f s" % (rounds, matches, time.time() - t0))
