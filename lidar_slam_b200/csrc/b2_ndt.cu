@@ -1238,28 +1238,24 @@ struct FitView {
 struct PoseArg { float T[16]; };
 
 constexpr int FIT_THREADS = 128;
+constexpr int FIT_WARPS = FIT_THREADS / 32;
 constexpr int FIT_RMAX = 8;
 
-__device__ __forceinline__ void fit_cell(const FitView &F, int kx, int ky, int kz, float qx, float qy, float qz, float &best) {
-    const int32_t v = __float_as_int(__ldg(F.cells + (size_t)kx + (size_t)ky * F.mul[1] + (size_t)kz * F.mul[2]).w);
-    if (v == 0) return;
-    const int j = (v > 0 ? v : -v) - 1;
-    const uint32_t s = __ldg(&F.leaf_start[j]);
-    const uint32_t n = (uint32_t)__ldg(&F.leaf_n[j]);
-    for (uint32_t k = s; k < s + n; ++k) {
-        const float4 p = __ldg(&F.pts_sorted[k]);
-        const float dx = __fsub_rn(qx, p.x), dy = __fsub_rn(qy, p.y), dz = __fsub_rn(qz, p.z);
-        const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-        best = fminf(best, d2);
-    }
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
 }
 
+// One WARP per source point: the ring walk is warp-uniform (all lanes share the query), the points of every
+// bucket are split over the lanes, and the minimum is exact whatever the split (min is order independent).
 __global__ void __launch_bounds__(FIT_THREADS) fitness_kernel(FitView F, const float4 *__restrict__ src, uint32_t n, PoseArg P,
                                                               double max_range, double *__restrict__ part_sum,
                                                               unsigned long long *__restrict__ part_cnt) {
-    double sum = 0.0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double sum = 0.0;                    // lane 0 of each warp accumulates its points in index order
     unsigned long long cnt = 0;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    for (uint32_t i = blockIdx.x * FIT_WARPS + warp; i < n; i += gridDim.x * FIT_WARPS) {
         const float4 pt = __ldg(&src[i]);
         float qx, qy, qz;
         transform_f32(P.T, pt.x, pt.y, pt.z, qx, qy, qz);
@@ -1269,46 +1265,66 @@ __global__ void __launch_bounds__(FIT_THREADS) fitness_kernel(FitView F, const f
         const int cz = (int)floorf(qz * F.inv_leaf) - F.min_b[2];
         float best = FLT_MAX;
         bool done = false;
-        for (int r = 0; r <= FIT_RMAX && !done; ++r) {
-            const int z0 = max(cz - r, 0), z1 = min(cz + r, F.div_b[2] - 1);
-            const int y0 = max(cy - r, 0), y1 = min(cy + r, F.div_b[1] - 1);
-            const int x0 = max(cx - r, 0), x1 = min(cx + r, F.div_b[0] - 1);
-            for (int kz = z0; kz <= z1; ++kz)
-                for (int ky = y0; ky <= y1; ++ky) {
-                    const bool face = (abs(kz - cz) == r) || (abs(ky - cy) == r);
-                    if (face) {
-                        for (int kx = x0; kx <= x1; ++kx) fit_cell(F, kx, ky, kz, qx, qy, qz, best);
-                    } else {
-                        if (cx - r >= 0 && cx - r < F.div_b[0]) fit_cell(F, cx - r, ky, kz, qx, qy, qz, best);
-                        if (r > 0 && cx + r >= 0 && cx + r < F.div_b[0]) fit_cell(F, cx + r, ky, kz, qx, qy, qz, best);
+        // Chebyshev shells r = 1 (the whole 3x3x3 block, the usual case ends there), 2, 3, ...: the lanes test 32
+        // cells of the (2r+1)^3 cube at a time (interior cells were visited by the previous shells), so the cell
+        // records and bucket descriptors are fetched in parallel; only occupied buckets are then scanned, their
+        // points split over the lanes
+        for (int r = 1; r <= FIT_RMAX && !done; ++r) {
+            const int side = 2 * r + 1, cube = side * side * side;
+            for (int c0 = 0; c0 < cube; c0 += 32) {
+                const int c = c0 + lane;
+                uint32_t bs = 0, bn = 0;
+                if (c < cube) {
+                    const int dx = c % side - r, dy = (c / side) % side - r, dz = c / (side * side) - r;
+                    const bool shell = (r == 1) || (abs(dx) == r) || (abs(dy) == r) || (abs(dz) == r);
+                    const int kx = cx + dx, ky = cy + dy, kz = cz + dz;
+                    if (shell && kx >= 0 && ky >= 0 && kz >= 0 && kx < F.div_b[0] && ky < F.div_b[1] && kz < F.div_b[2]) {
+                        const int32_t v = __float_as_int(__ldg(F.cells + (size_t)kx + (size_t)ky * F.mul[1] + (size_t)kz * F.mul[2]).w);
+                        if (v != 0) {
+                            const int j = (v > 0 ? v : -v) - 1;
+                            bs = __ldg(&F.leaf_start[j]);
+                            bn = (uint32_t)__ldg(&F.leaf_n[j]);
+                        }
                     }
                 }
+                uint32_t occ = __ballot_sync(0xffffffffu, bn != 0u);
+                while (occ) {
+                    const int src_lane = __ffs(occ) - 1;
+                    occ &= occ - 1u;
+                    const uint32_t s0 = __shfl_sync(0xffffffffu, bs, src_lane), n0 = __shfl_sync(0xffffffffu, bn, src_lane);
+                    for (uint32_t k = s0 + lane; k < s0 + n0; k += 32u) {
+                        const float4 p = __ldg(&F.pts_sorted[k]);
+                        const float dx = __fsub_rn(qx, p.x), dy = __fsub_rn(qy, p.y), dz = __fsub_rn(qz, p.z);
+                        best = fminf(best, __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+                    }
+                }
+            }
+            best = warp_min(best);
             // everything not yet visited lies at least r cells away from the query
             const double lim = (double)r * (double)F.res * (1.0 - 1e-4);
             if (best < FLT_MAX && (double)best * (1.0 + 1e-5) <= lim * lim) done = true;
-            // the rings already cover the whole grid
+            // the shells already cover the whole grid
             if (cx - r <= 0 && cy - r <= 0 && cz - r <= 0 && cx + r >= F.div_b[0] - 1 && cy + r >= F.div_b[1] - 1 &&
                 cz + r >= F.div_b[2] - 1)
                 done = true;
         }
         if (!done) {   // rare: isolated query, exact brute force over all target points
-            for (uint32_t k = 0; k < F.N; ++k) {
+            for (uint32_t k = lane; k < F.N; k += 32u) {
                 const float4 p = __ldg(&F.pts_sorted[k]);
                 const float dx = __fsub_rn(qx, p.x), dy = __fsub_rn(qy, p.y), dz = __fsub_rn(qz, p.z);
                 best = fminf(best, __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
             }
+            best = warp_min(best);
         }
         if (best < FLT_MAX && (double)best <= max_range) { sum += (double)best; ++cnt; }
     }
-    __shared__ double ssum[FIT_THREADS / 32];
-    __shared__ unsigned long long scnt[FIT_THREADS / 32];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { sum += __shfl_xor_sync(0xffffffffu, sum, o); cnt += __shfl_xor_sync(0xffffffffu, cnt, o); }
-    if ((threadIdx.x & 31) == 0) { ssum[threadIdx.x >> 5] = sum; scnt[threadIdx.x >> 5] = cnt; }
+    __shared__ double ssum[FIT_WARPS];
+    __shared__ unsigned long long scnt[FIT_WARPS];
+    if (lane == 0) { ssum[warp] = sum; scnt[warp] = cnt; }
     __syncthreads();
     if (threadIdx.x == 0) {
         double s = 0.0; unsigned long long c = 0;
-        for (int w = 0; w < FIT_THREADS / 32; ++w) { s += ssum[w]; c += scnt[w]; }
+        for (int w = 0; w < FIT_WARPS; ++w) { s += ssum[w]; c += scnt[w]; }
         part_sum[blockIdx.x] = s; part_cnt[blockIdx.x] = c;
     }
 }
@@ -1873,8 +1889,8 @@ static int fitness_device(b2ndt *h, const float4 *d_src, size_t n, const float p
     F.res = h->prm.res; F.inv_leaf = 1.0f / h->prm.res; F.ok = 1;
     PoseArg P;
     memcpy(P.T, pose, 64);
-    unsigned blocks = (unsigned)((n + FIT_THREADS - 1) / FIT_THREADS);
-    if (blocks > 148 * 8) blocks = 148 * 8;
+    unsigned blocks = (unsigned)((n + FIT_WARPS - 1) / FIT_WARPS);        // one warp per source point
+    if (blocks > 148 * 16) blocks = 148 * 16;
     int rc;
     if ((rc = h->d_fit_sum.reserve(blocks * 8))) return rc;
     if ((rc = h->d_fit_cnt.reserve(blocks * 8))) return rc;
