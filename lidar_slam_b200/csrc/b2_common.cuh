@@ -41,21 +41,46 @@ inline void count_launch(uint64_t n = 1) { g_launches.fetch_add(n, std::memory_o
         }                                                                                     \
     } while (0)
 
-// growable device / pinned buffers (never shrink; reused across calls)
+// growable device / pinned buffers (never shrink; reused across calls).  Device memory comes from the device's
+// stream-ordered pool (cudaMallocAsync) with an unlimited release threshold: a buffer that has to grow -- the local
+// map of the front end grows for its first 20 key frames -- gets its new block from the pool instead of paying a
+// cudaFree / cudaMalloc pair (tens of milliseconds per key frame over the ~15 buffers of a target build).
+inline void devbuf_pool_setup() {
+    static thread_local int done_dev = -1;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return; }
+    if (dev == done_dev) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    } else {
+        cudaGetLastError();
+    }
+    done_dev = dev;
+}
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
+    // contents are NOT preserved when the buffer grows
     int reserve(size_t bytes) {
         if (bytes <= cap) return 0;
-        if (p) cudaFree(p);
-        p = nullptr; cap = 0;
-        size_t want = bytes + bytes / 4 + 256;
-        cudaError_t e = cudaMalloc(&p, want);
-        if (e != cudaSuccess) { set_error("cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e)); p = nullptr; return B2_ERR_CUDA; }
+        devbuf_pool_setup();
+        release();
+        size_t want = bytes + bytes / 2 + 256;
+        cudaError_t e = cudaMallocAsync(&p, want, cudaStreamPerThread);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(cudaStreamPerThread);     // usable from every stream from here on
+        if (e != cudaSuccess) { set_error("cudaMallocAsync(%zu) failed: %s", want, cudaGetErrorString(e)); p = nullptr; return B2_ERR_CUDA; }
         cap = want;
         return 0;
     }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    void release() {
+        if (p) {
+            cudaDeviceSynchronize();                       // work on other streams may still use the block (as cudaFree would wait)
+            cudaFreeAsync(p, cudaStreamPerThread);
+        }
+        p = nullptr; cap = 0;
+    }
     template <class T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 struct PinBuf {

@@ -126,6 +126,7 @@ class FrontEndDevice(FrontEnd):
         self.vf, self.lvf, self.reg = vf, lvf, reg
         self.local = DeviceCloud()
         self.filtered = DeviceCloud()
+        self.frame = DeviceCloud()          # upload target, reused; a key frame takes it over and a new one is made
         self.t_upload = []
 
     def _new_keyframe(self, cloud, pose):
@@ -145,10 +146,11 @@ class FrontEndDevice(FrontEnd):
         self.last_key = pose.copy()
 
     def update(self, cloud, init_pose):
-        t = time.perf_counter(); d_cloud = DeviceCloud(cloud); self.t_upload.append(1e3 * (time.perf_counter() - t))
+        t = time.perf_counter(); d_cloud = self.frame.Upload(cloud); self.t_upload.append(1e3 * (time.perf_counter() - t))
         if self.pose is None:
             self.pose = init_pose.astype(np.float32).copy(); self.last = self.pose.copy(); self.predict = self.pose.copy()
             self._new_keyframe(d_cloud, self.pose)
+            self.frame = DeviceCloud()
             return self.pose
         t = time.perf_counter()
         self.vf.FilterCloud(d_cloud, self.filtered)
@@ -159,6 +161,7 @@ class FrontEndDevice(FrontEnd):
         self.last = pose.copy(); self.pose = pose
         if np.sum(np.abs(self.last_key[:3, 3] - pose[:3, 3])) > self.key_dist:
             self._new_keyframe(d_cloud, pose)
+            self.frame = DeviceCloud()
         return pose
 
 
@@ -194,7 +197,7 @@ def config2(scene, frames, oracle_frames):
             "device_resident": {"frame_upload_ms_p50": pct(fed.t_upload, 50),
                                 "filter_plus_scan_match_ms": {"p50": pct(fed.t_match, 50), "p99": pct(fed.t_match, 99)},
                                 "local_map_assemble_ms_p50": pct(fed.t_assemble, 50),
-                                "filter_plus_set_target_ms": {"p50": pct(fed.t_target, 50), "max": max(fed.t_target)},
+                                "filter_plus_set_target_ms": {"p50": pct(fed.t_target, 50), "p90": pct(fed.t_target, 90), "max_incl_first_call_module_load": max(fed.t_target)},
                                 "trajectory_identical_to_host_path": bool(dev_equal)},
             "oracle": {"frames": len(otraj), "scan_match_ms_p50": pct(ofe.t_match, 50), "target_rebuild_ms_p50": pct(ofe.t_target, 50),
                        "max_traj_dt_m": dt, "max_traj_dR": dR},
