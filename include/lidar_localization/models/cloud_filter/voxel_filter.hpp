@@ -12,6 +12,14 @@
 #include "lidar_localization/models/cloud_filter/cloud_filter_interface.hpp"
 
 namespace lidar_localization {
+
+// What Filter computes (pcl::VoxelGrid semantics, reproduced bit for bit on voxel indices and point counts):
+//   * bounding box of the finite points, inverse leaf = 1.0f / leaf, voxel (i,j,k) = floor(p * inverse leaf) - min;
+//   * one output point per occupied voxel = float mean of x, y, z and intensity of its members (summed in input
+//     order), voxels emitted in ascending linear index i + j*dx + k*dx*dy;
+//   * "leaf size too small" (more than 2^31 cells): the input is returned unchanged, as PCL does.
+// The work runs on the GPU behind b2vf_filter (radix sort by voxel key + per-voxel reduction); FilterDevice-style
+// use with resident clouds goes through b2vf_filter_cloud (include/b2ndt.h).
 class VoxelFilter : public CloudFilterInterface {
   public:
 #ifdef B2_WITH_YAML
