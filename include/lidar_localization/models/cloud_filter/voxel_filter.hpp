@@ -31,6 +31,8 @@ class VoxelFilter : public CloudFilterInterface {
     VoxelFilter& operator=(const VoxelFilter&) = delete;
 
     bool Filter(const CloudData::CLOUD_PTR& input_cloud_ptr, CloudData::CLOUD_PTR& filtered_cloud_ptr) override;
+    // device-resident variant (input == output allowed)
+    bool FilterDevice(b2cloud* input, b2cloud* output);
 
   private:
     bool SetFilterParam(float leaf_size_x, float leaf_size_y, float leaf_size_z);

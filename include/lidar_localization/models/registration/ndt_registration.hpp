@@ -36,6 +36,11 @@ class NDTRegistration : public RegistrationInterface {
                         const std::vector<Eigen::Matrix4f>& predict_poses,
                         std::vector<Eigen::Matrix4f>& result_poses,
                         std::vector<b2ndt_result>* details = nullptr);
+    // Extension: clouds that already live in HBM (b2cloud, include/b2ndt.h): the front end's local map assembled on the
+    // device, the matching node's cropped map, a frame filtered on the device -- no host copies.  result_cloud may be null.
+    bool SetInputTargetDevice(b2cloud* input_target);
+    bool ScanMatchDevice(b2cloud* input_source, const Eigen::Matrix4f& predict_pose, b2cloud* result_cloud,
+                         Eigen::Matrix4f& result_pose);
     // details of the last ScanMatch (iterations, converged, score ...)
     const b2ndt_result& LastResult() const { return last_; }
     // device ordinal used by objects constructed afterwards (default 0 or $B2NDT_DEVICE)

@@ -1392,6 +1392,13 @@ extern "C" int b2ndt_create(const b2ndt_params *p, int device, b2ndt **out) {
     cudaError_t e = cudaStreamCreateWithFlags(&h->own, cudaStreamNonBlocking);
     if (e != cudaSuccess) { set_error("cudaStreamCreate failed: %s", cudaGetErrorString(e)); delete h; return B2_ERR_CUDA; }
     h->st = h->own;
+    {
+        // load the two large match kernels now (CUDA loads kernels lazily, ~0.1-0.25 s each on first launch): the
+        // cost belongs to construction, not to the first ScanMatch of a 10 Hz pipeline
+        cudaFuncAttributes fa;
+        if (cudaFuncGetAttributes(&fa, ndt_match_kernel) != cudaSuccess) cudaGetLastError();
+        if (cudaFuncGetAttributes(&fa, ndt_batch_kernel) != cudaSuccess) cudaGetLastError();
+    }
     if (const char *e = getenv("B2NDT_BATCH_KERNEL")) h->use_batch_kernel = atoi(e) != 0;
     if (const char *e = getenv("B2NDT_STREAM")) h->stream_batches = atoi(e) != 0;
     *out = h;

@@ -86,6 +86,23 @@ bool NDTRegistration::ScanMatch(const CloudData::CLOUD_PTR& input_source, const 
     return true;
 }
 
+bool NDTRegistration::SetInputTargetDevice(b2cloud* input_target) {
+    if (!ndt_ || b2ndt_set_target_cloud(ndt_, input_target) != B2_OK)
+        std::cerr << "[NDTRegistration::SetInputTargetDevice] " << b2_last_error() << std::endl;
+    return true;
+}
+
+bool NDTRegistration::ScanMatchDevice(b2cloud* input_source, const Eigen::Matrix4f& predict_pose, b2cloud* result_cloud,
+                                      Eigen::Matrix4f& result_pose) {
+    float pose[16];
+    if (!ndt_ || b2ndt_align_cloud(ndt_, input_source, predict_pose.data(), pose, &last_, result_cloud) != B2_OK) {
+        std::cerr << "[NDTRegistration::ScanMatchDevice] " << b2_last_error() << std::endl;
+        return true;
+    }
+    std::memcpy(result_pose.data(), pose, sizeof(pose));
+    return true;
+}
+
 float NDTRegistration::GetFitnessScore() {
     double v = 0.0;
     if (!ndt_ || b2ndt_fitness(ndt_, 1.7976931348623157e308, &v) != B2_OK) {

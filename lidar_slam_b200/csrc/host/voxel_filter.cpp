@@ -54,4 +54,9 @@ bool VoxelFilter::Filter(const CloudData::CLOUD_PTR& input_cloud_ptr, CloudData:
     out.is_dense = true;
     return true;
 }
+bool VoxelFilter::FilterDevice(b2cloud* input, b2cloud* output) {
+    if (!vf_ || b2vf_filter_cloud(vf_, input, output) != B2_OK)
+        std::cerr << "[VoxelFilter::FilterDevice] " << b2_last_error() << std::endl;
+    return true;
+}
 }  // namespace lidar_localization

@@ -69,6 +69,25 @@ int main(int argc, char** argv) {
         for (const auto& p : cropped->points) gx += p.x;
         std::printf("BOX %zu %zu %.9g %.9g\n", cropped->points.size(), expect, gx, sx);
     }
+    // device-resident use of the same classes: crop the map on the device, filter the frame there, match, same answer
+    {
+        b2cloud *d_map = nullptr, *d_scan = nullptr, *d_filt = nullptr, *d_res = nullptr;
+        b2cloud_create(0, &d_map); b2cloud_create(0, &d_scan); b2cloud_create(0, &d_filt); b2cloud_create(0, &d_res);
+        b2cloud_upload(d_map, target->points.data(), target->points.size(), 32, 16);
+        b2cloud_upload(d_scan, scan->points.data(), scan->points.size(), 32, 16);
+        VoxelFilter ff(1.3f, 1.3f, 1.3f);
+        ff.FilterDevice(d_scan, d_filt);
+        NDTRegistration reg2(1.0f, 0.1f, 0.01f, 30);
+        reg2.SetInputTargetDevice(d_map);
+        Eigen::Matrix4f pose2 = Eigen::Matrix4f::Identity();
+        reg2.ScanMatchDevice(d_filt, guess, d_res, pose2);
+        size_t nf = 0, nr = 0;
+        b2cloud_size(d_filt, &nf); b2cloud_size(d_res, &nr);
+        bool same = nf == filtered->points.size() && nr == nf;
+        for (int i = 0; i < 16; ++i) same = same && pose2.data()[i] == pose.data()[i];
+        std::printf("DEV %d %d\n", same ? 1 : 0, reg2.LastResult().iterations);
+        b2cloud_destroy(d_map); b2cloud_destroy(d_scan); b2cloud_destroy(d_filt); b2cloud_destroy(d_res);
+    }
     // result cloud = source under the final pose
     if (result->points.size() != filtered->points.size()) return 1;
     std::printf("R0 %.9g %.9g %.9g %.9g\n", result->points[0].x, result->points[0].y, result->points[0].z, result->points[0].intensity);
