@@ -203,6 +203,9 @@ int  b2hmap_info(b2hmap *h, int32_t *width, int32_t *height, float min_xyz[3], f
 int  b2hmap_cells(b2hmap *h, float *mu, float *sigma, int32_t *point_cnt);
 /* probs (angle_size doubles, may be NULL) receives the per-bin scores, *best_angle the winning yaw in radians */
 int  b2hmap_yaw_search(b2hmap *h, b2cloud *scan, int angle_size, double *probs, double *best_angle);
+/* the same score for (x, y, yaw) hypotheses: n_offsets sensor positions (dx, dy relative to the grid origin) x
+ * angle_size yaw bins -> probs[o * angle_size + bin] (BASELINE.json config 5: hypotheses for batched NDT) */
+int  b2hmap_pose_search(b2hmap *h, b2cloud *scan, int angle_size, const float *offsets_xy, int n_offsets, double *probs);
 
 #ifdef __cplusplus
 }

@@ -78,3 +78,28 @@ def scan_match_batch_multi_device(registrations, sources, predict_poses):
             raise e
     parts = [o for o in out if o is not None]
     return np.concatenate([p[0] for p in parts], axis=0), np.concatenate([p[1] for p in parts], axis=0)
+
+
+def relocalize(registration, yaw_search, scan_filtered, scan_device, position, lattice=9, pitch=1.0, top=16, angle_size=270):
+    """Global relocalisation from a position prior (BASELINE.json config 5, generalising the reference's yaw-only scan,
+    matching.cpp:199-232,267-308, to (x, y, yaw)): the Gaussian height grid (`yaw_search`: an InitialYawSearch built
+    around `position`; `scan_device`: the scan as a DeviceCloud) scores lattice x lattice sensor positions (pitch
+    metres) x angle_size yaw bins in one launch, the `top` best poses become the initial guesses of ONE batched NDT
+    launch (`registration.ScanMatchBatch` with a shared source), and the best final NDT score wins.
+    -> (best pose 4x4, index into the candidates, candidate poses after NDT (top,4,4), results)"""
+    from . import synth
+    half = (lattice - 1) / 2.0
+    offs = np.array([[(ix - half) * pitch, (iy - half) * pitch] for iy in range(lattice) for ix in range(lattice)], np.float32)
+    probs = yaw_search.PoseSearch(scan_device, offs, angle_size)
+    flat = np.where(np.isfinite(probs), probs, -np.inf).ravel()
+    cand = np.argsort(-flat)[:max(1, int(top))]
+    delta = np.float32(2 * np.pi / angle_size)
+    guesses = []
+    for c in cand:
+        o, b = divmod(int(c), angle_size)
+        pose6 = np.array([position[0] + offs[o, 0], position[1] + offs[o, 1], position[2], 0.0, 0.0, float(np.float32(b) * delta)])
+        guesses.append(synth.pose6_to_matrix(pose6).astype(np.float32))
+    poses, res = registration.ScanMatchBatch(scan_filtered, guesses)
+    score = np.where(res["converged"] > 0, res["score"], -np.inf)
+    k = int(np.argmax(score))
+    return poses[k], k, poses, res

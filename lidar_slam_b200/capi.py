@@ -26,7 +26,7 @@ EXPORTS = [
     "b2cloud_device_ptr", "b2cloud_append_transformed", "b2cloud_box_filter", "b2cloud_remove_nan", "b2cloud_distortion_adjust", "b2vf_filter_cloud",
     "b2ndt_set_target_cloud", "b2ndt_align_cloud",
     "b2_pcd_read", "b2_pcd_free", "b2_pcd_write_binary", "b2cloud_load_pcd", "b2cloud_save_pcd",
-    "b2hmap_create", "b2hmap_destroy", "b2hmap_build", "b2hmap_info", "b2hmap_cells", "b2hmap_yaw_search",
+    "b2hmap_create", "b2hmap_destroy", "b2hmap_build", "b2hmap_info", "b2hmap_cells", "b2hmap_yaw_search", "b2hmap_pose_search",
 ]
 
 
@@ -129,6 +129,7 @@ def lib():
     L.b2hmap_info.argtypes = [vp, i32p, i32p, fp, fp]
     L.b2hmap_cells.argtypes = [vp, fp, fp, i32p]
     L.b2hmap_yaw_search.argtypes = [vp, vp, C.c_int, dp, dp]
+    L.b2hmap_pose_search.argtypes = [vp, vp, C.c_int, fp, C.c_int, dp]
     _LIB = L
     return L
 

@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(128) hmap_cell_kernel(const float4 *__restrict
 
 // getInitialYawAngle: one CTA per yaw bin; per-thread partial sums in double, combined in a fixed order
 constexpr int YAW_THREADS = 256;
-struct YawRot { float c, s, m22; };     // Eigen::AngleAxisf(angle, UnitZ).matrix(): [c -s 0; s c 0; 0 0 (1-c)+c]
+struct YawRot { float c, s, m22, tx, ty; };   // Eigen::AngleAxisf(angle, UnitZ).matrix(): [c -s 0; s c 0; 0 0 (1-c)+c]; translation (tx, ty, 0)
 
 __global__ void __launch_bounds__(YAW_THREADS) hmap_yaw_kernel(const float4 *__restrict__ scan, uint32_t n, HmapGrid G,
                                                               const float *__restrict__ mu, const float *__restrict__ sigma,
@@ -126,8 +126,8 @@ __global__ void __launch_bounds__(YAW_THREADS) hmap_yaw_kernel(const float4 *__r
     for (uint32_t i = threadIdx.x; i < n; i += YAW_THREADS) {
         const float4 p = __ldg(&scan[i]);
         // pcl::transformPointCloud with the 4x4 built from the rotation (translation 0), left to right in float
-        const float x = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(R.c, p.x), __fmul_rn(-R.s, p.y)), __fmul_rn(0.f, p.z)), 0.f);
-        const float y = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(R.s, p.x), __fmul_rn(R.c, p.y)), __fmul_rn(0.f, p.z)), 0.f);
+        const float x = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(R.c, p.x), __fmul_rn(-R.s, p.y)), __fmul_rn(0.f, p.z)), R.tx);
+        const float y = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(R.s, p.x), __fmul_rn(R.c, p.y)), __fmul_rn(0.f, p.z)), R.ty);
         const float z = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(0.f, p.x), __fmul_rn(0.f, p.y)), __fmul_rn(R.m22, p.z)), 0.f);
         if (!finite3(x, y, z)) continue;
         const int cx = hmap_cell(x, G.min_x, G.res), cy = hmap_cell(y, G.min_y, G.res);
@@ -272,40 +272,60 @@ extern "C" int b2hmap_cells(b2hmap *h, float *mu, float *sigma, int32_t *point_c
     return 0;
 }
 
-extern "C" int b2hmap_yaw_search(b2hmap *h, b2cloud *scan, int angle_size, double *probs, double *best_angle) {
-    if (!h || !scan || !best_angle) { set_error("b2hmap_yaw_search: NULL argument"); return B2_ERR_INVALID; }
-    if (!h->built) { set_error("b2hmap_yaw_search: no map built"); return B2_ERR_STATE; }
-    if (angle_size < 1 || angle_size > 65535) { set_error("b2hmap_yaw_search: angle_size out of range"); return B2_ERR_INVALID; }
-    if (scan->device != h->device) { set_error("b2hmap_yaw_search: handle and cloud live on different devices"); return B2_ERR_INVALID; }
+// (x, y, yaw) hypothesis scoring: for every offset (dx, dy) of the sensor position relative to the grid origin and
+// every yaw bin, the score getInitialYawAngle computes for that pose.  probs[o * angle_size + bin].
+extern "C" int b2hmap_pose_search(b2hmap *h, b2cloud *scan, int angle_size, const float *offsets_xy, int n_offsets, double *probs) {
+    if (!h || !scan || !probs || (n_offsets > 0 && !offsets_xy)) { set_error("b2hmap_pose_search: NULL argument"); return B2_ERR_INVALID; }
+    if (!h->built) { set_error("b2hmap_pose_search: no map built"); return B2_ERR_STATE; }
+    if (angle_size < 1 || angle_size > 65535 || n_offsets < 1 || (long long)angle_size * n_offsets > (1 << 24)) {
+        set_error("b2hmap_pose_search: angle_size / n_offsets out of range"); return B2_ERR_INVALID;
+    }
+    if (scan->device != h->device) { set_error("b2hmap_pose_search: handle and cloud live on different devices"); return B2_ERR_INVALID; }
     B2_CUDA(cudaSetDevice(h->device));
+    const size_t nh = (size_t)angle_size * (size_t)n_offsets;
     int rc;
-    if ((rc = h->rot.reserve((size_t)angle_size * sizeof(YawRot)))) return rc;
-    if ((rc = h->probs.reserve((size_t)angle_size * 8))) return rc;
-    if ((rc = h->h_small.reserve((size_t)angle_size * (sizeof(YawRot) + 8) + 64))) return rc;
+    if ((rc = h->rot.reserve(nh * sizeof(YawRot)))) return rc;
+    if ((rc = h->probs.reserve(nh * 8))) return rc;
+    const size_t rot_bytes = ((nh * sizeof(YawRot) + 63) / 64) * 64;
+    if ((rc = h->h_small.reserve(rot_bytes + nh * 8 + 64))) return rc;
     YawRot *hr = h->h_small.as<YawRot>();
     const float delta_angle = (float)(2 * M_PI / angle_size);          // float delta_angle = 2 * M_PI / angle_size
-    for (int i = 0; i < angle_size; ++i) {
-        // Eigen::AngleAxisf(delta_angle * i, UnitZ).matrix() (AngleAxis.h toRotationMatrix): c, s in float,
-        // diagonal = (1 - c) * axis^2 + c
-        const float a = delta_angle * (float)i;
-        // float sin / cos evaluated as float(f(double(a))): correctly rounded in practice, platform independent
-        const float s = (float)std::sin((double)a), c = (float)std::cos((double)a);
-        hr[i].c = c; hr[i].s = s; hr[i].m22 = (1.0f - c) * 1.0f * 1.0f + c;
-    }
-    B2_CUDA(cudaMemcpyAsync(h->rot.p, hr, (size_t)angle_size * sizeof(YawRot), cudaMemcpyHostToDevice, h->st));
+    for (int o = 0; o < n_offsets; ++o)
+        for (int i = 0; i < angle_size; ++i) {
+            // Eigen::AngleAxisf(delta_angle * i, UnitZ).matrix() (AngleAxis.h toRotationMatrix): c, s in float,
+            // diagonal = (1 - c) * axis^2 + c; float sin / cos evaluated as float(f(double(a))): correctly rounded in
+            // practice, platform independent
+            const float a = delta_angle * (float)i;
+            const float s = (float)std::sin((double)a), c = (float)std::cos((double)a);
+            YawRot &r = hr[(size_t)o * angle_size + i];
+            r.c = c; r.s = s; r.m22 = (1.0f - c) * 1.0f * 1.0f + c;
+            r.tx = offsets_xy[2 * o]; r.ty = offsets_xy[2 * o + 1];
+        }
+    B2_CUDA(cudaMemcpyAsync(h->rot.p, hr, nh * sizeof(YawRot), cudaMemcpyHostToDevice, h->st));
     const size_t cells = (size_t)h->G.width * (size_t)h->G.height;
-    std::vector<double> pr((size_t)angle_size, 0.0);
+    for (size_t i = 0; i < nh; ++i) probs[i] = 0.0;
     if (cells && scan->n) {
-        hmap_yaw_kernel<<<angle_size, YAW_THREADS, 0, h->st>>>(scan->d(), (uint32_t)scan->n, h->G, h->mu.as<float>(), h->sigma.as<float>(),
-                                                              h->cnt.as<int32_t>(), h->rot.as<YawRot>(), h->probs.as<double>());
+        hmap_yaw_kernel<<<(unsigned)nh, YAW_THREADS, 0, h->st>>>(scan->d(), (uint32_t)scan->n, h->G, h->mu.as<float>(), h->sigma.as<float>(),
+                                                                h->cnt.as<int32_t>(), h->rot.as<YawRot>(), h->probs.as<double>());
         B2_LAUNCH_CHECK();
-        double *hp = reinterpret_cast<double *>(h->h_small.as<char>() + (((size_t)angle_size * sizeof(YawRot) + 63) / 64) * 64);
-        B2_CUDA(cudaMemcpyAsync(hp, h->probs.p, (size_t)angle_size * 8, cudaMemcpyDeviceToHost, h->st));
+        double *hp = reinterpret_cast<double *>(h->h_small.as<char>() + rot_bytes);
+        B2_CUDA(cudaMemcpyAsync(hp, h->probs.p, nh * 8, cudaMemcpyDeviceToHost, h->st));
         B2_CUDA(cudaStreamSynchronize(h->st));
-        for (int i = 0; i < angle_size; ++i) pr[i] = hp[i];
+        for (size_t i = 0; i < nh; ++i) probs[i] = hp[i];
     } else {
         B2_CUDA(cudaStreamSynchronize(h->st));
     }
+    return 0;
+}
+
+extern "C" int b2hmap_yaw_search(b2hmap *h, b2cloud *scan, int angle_size, double *probs, double *best_angle) {
+    if (!h || !scan || !best_angle) { set_error("b2hmap_yaw_search: NULL argument"); return B2_ERR_INVALID; }
+    if (angle_size < 1 || angle_size > 65535) { set_error("b2hmap_yaw_search: angle_size out of range"); return B2_ERR_INVALID; }
+    std::vector<double> pr((size_t)angle_size, 0.0);
+    const float zero[2] = {0.f, 0.f};
+    int rc = b2hmap_pose_search(h, scan, angle_size, zero, 1, pr.data());
+    if (rc) return rc;
+    const float delta_angle = (float)(2 * M_PI / angle_size);
     // first strictly larger bin wins; NaN bins never win (matching.cpp:298-306)
     float max_prob = -FLT_MAX;
     double best = 0.0;

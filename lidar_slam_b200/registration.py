@@ -438,6 +438,13 @@ class InitialYawSearch:
         capi.check(capi.lib().b2hmap_yaw_search(self._h, scan._h, int(angle_size), capi._dp(probs), C.byref(best)))
         return best.value, probs
 
+    def PoseSearch(self, scan, offsets_xy, angle_size=270):
+        """(x, y, yaw) hypothesis scores: offsets_xy (n,2) sensor positions relative to the grid origin -> (n, angle_size)."""
+        off = np.ascontiguousarray(offsets_xy, np.float32).reshape(-1, 2)
+        probs = np.zeros((len(off), angle_size), np.float64)
+        capi.check(capi.lib().b2hmap_pose_search(self._h, scan._h, int(angle_size), capi._fp(off), len(off), capi._dp(probs)))
+        return probs
+
 
 class DistortionAdjust:
     """DistortionAdjust (lidar_localization/src/models/scan_adjust/distortion_adjust.cpp): SetMotionInfo(scan_period,

@@ -57,3 +57,27 @@ def test_yaw_search_finds_heading_and_agrees_with_oracle(world):
     ys2 = InitialYawSearch(0.8)
     info = ys2.GenerateGauss2DMapCells(DeviceCloud(np.zeros((0, 4), np.float32)), [0, 0, 0])
     assert info["width"] == 0 and ys2.GetInitialYawAngle(DeviceCloud(scan), 90)[0] == 0.0
+
+
+def test_relocalize_from_position_prior(world):
+    """Config 5 in miniature: position prior off by ~3 m, heading unknown -> yaw scan + lattice of batched NDT matches."""
+    from lidar_slam_b200 import batch
+    from lidar_slam_b200.registration import DeviceCloud, InitialYawSearch, NDTRegistration, VoxelFilter
+    scene, local, truth = world
+    gmap = scene.make_map(200000, 2.0)
+    reg = NDTRegistration(1.0, 0.1, 0.01, 30)
+    reg.SetInputTarget(gmap)
+    prior = truth[:3] + np.array([2.5, -1.5, 0.0])
+    ys = InitialYawSearch(0.8)
+    edge = [prior[0] - 40, prior[0] + 40, prior[1] - 40, prior[1] + 40, prior[2] - 40, prior[2] + 40]
+    ys.GenerateGauss2DMapCells(DeviceCloud(O.box_filter(gmap, edge)), prior)
+    scan = scene.scan(777, truth)
+    filt = VoxelFilter(1.3, 1.3, 1.3).Filter(scan)[1]
+    d_scan = DeviceCloud(scan)
+    # PoseSearch with a zero offset is the yaw scan
+    assert np.array_equal(ys.PoseSearch(d_scan, [[0.0, 0.0]], 270)[0], ys.GetInitialYawAngle(d_scan, 270)[1], equal_nan=True)
+    pose, k, poses, res = batch.relocalize(reg, ys, filt, d_scan, prior, lattice=9, pitch=1.0, top=16)
+    T = synth.pose6_to_matrix(truth)
+    assert len(poses) == 16
+    assert np.linalg.norm(pose[:3, 3] - T[:3, 3]) < 0.15, (pose[:3, 3], T[:3, 3])
+    assert np.max(np.abs(pose[:3, :3] - T[:3, :3])) < 0.02
