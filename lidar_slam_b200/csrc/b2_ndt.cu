@@ -274,19 +274,22 @@ __global__ void __launch_bounds__(NBR_TPB) nbr_fill_kernel(uint2 *__restrict__ h
     }
 }
 
-// ------------------------------------------------------------------ the NDT match kernel ------
-// One thread-block cluster (1..16 CTAs) per match; the whole Newton / More-Thuente loop runs inside the
-// kernel.  Every CTA is WARP-SPECIALISED (producer / consumer, registers re-balanced with setmaxnreg):
-//   search warps  (NDT_NSW, 56 registers): lane = source point.  Float transform, then one z-plane of the
-//     3x3x3 window of the dense cell grid per step: nine independent 16-byte loads bring the voxel code
-//     AND its float centroid (no second dependent load), float L2 tests, hits appended to the warp's ring
-//     buffer in shared memory at positions given by ballots (deterministic order, no atomics);
-//   compute warps (NDT_NCW, 128 registers): lane = (point, voxel) pair.  Each compute warp drains the
-//     rings of its search warps in a fixed round-robin, 32 pairs at a time, so every lane is busy:
-//     80-byte record gather, exp, score / gradient / Hessian terms of updateDerivatives (NDTM:485-520)
-//     accumulated in 29 FP64 registers.
-// The latency-bound gather and the FP64-bound arithmetic thus run concurrently on different warps, and
-// the cheap search warps raise the number of resident warps per SM.
+// ------------------------------------------------------------------ the NDT match kernels -----
+// The whole Newton / More-Thuente loop of a match runs inside a kernel (no host round trip per iteration).  Two
+// kernels share the same building blocks (search_pass, compute_drain, controller_step, below):
+//   ndt_batch_kernel  batches: persistent CTAs, NDT_SLOTS matches in flight per CTA, work fetched from a counter;
+//   ndt_match_kernel  a single ScanMatch / the derivatives-only entry: one thread-block cluster (1..16 CTAs) per match.
+// Every CTA is WARP-SPECIALISED (producer / consumer, registers re-balanced with setmaxnreg):
+//   search warps  (NDT_NSW, 56 registers): lane = source point.  Float transform, ONE 8-byte neighbour-list header
+//     per query, then the warp walks the concatenation of its 32 lists (coalesced 16-byte entries {centroid, leaf},
+//     owner by binary search over the scan of list lengths), float L2 tests, hits {source point, leaf} appended to the
+//     warp's ring in shared memory at positions given by ballots (deterministic order, no atomics);
+//   compute warps (NDT_NCW, 128 registers): lane = (point, voxel) pair.  Each compute warp drains the rings of its
+//     search warps in a fixed round-robin, 32 pairs at a time, so every lane is busy: 96-byte record gather (two
+//     256-bit loads + one 64-bit), exp, and the pair's contribution in Q/P/M form (ndt_pair) accumulated in NACC = 35
+//     FP64 registers.
+// The latency-bound gather and the FP64-bound arithmetic thus run concurrently on different warps, and the cheap
+// search warps raise the number of resident warps per SM.
 #ifndef NDT_NCW
 #define NDT_NCW 4
 #endif
