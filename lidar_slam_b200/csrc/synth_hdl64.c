@@ -51,10 +51,11 @@ static inline double gauss(uint64_t h1, uint64_t h2) {
     return sqrt(-2.0 * log(u1)) * cos(6.283185307179586 * u2);
 }
 
-/* --- path: an L-shaped drive: leg along +x on the street y=25, quarter turn, leg along +y on the
- * street x = 25 + leg + turn_r ... ; s in [0, 2*leg + arc] --- */
+/* --- path: an L-shaped drive along two streets: leg along +x on the street y = 25, a quarter turn of radius
+ * turn_r inside the intersection with the street x = 25 + leg, then a leg along +y on that street;
+ * s in [0, 2*leg + arc] (the straight part of the first leg is leg - turn_r long) --- */
 void synth_path_pose(const scene_t *sc, double s, double pose6[6]) {
-    double L = sc->leg, r = sc->turn_r;
+    double L = sc->leg - sc->turn_r, r = sc->turn_r;
     double arc = 1.5707963267948966 * r;
     double x, y, yaw;
     if (s < 0) s = 0;
