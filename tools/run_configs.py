@@ -201,7 +201,8 @@ def config2(scene, frames, oracle_frames):
                                 "trajectory_identical_to_host_path": bool(dev_equal)},
             "oracle": {"frames": len(otraj), "scan_match_ms_p50": pct(ofe.t_match, 50), "target_rebuild_ms_p50": pct(ofe.t_target, 50),
                        "max_traj_dt_m": dt, "max_traj_dR": dR},
-            "drift_vs_truth_m": {"final": err_truth[-1], "max": max(err_truth)}}
+            "drift_vs_truth_m": {"final": err_truth[-1], "max": max(err_truth), "every_50_frames": err_truth[::50],
+                                 "oracle_final": float(np.linalg.norm(otraj[-1][:3, 3] - synth.pose6_to_matrix(truth[len(otraj) - 1])[:3, 3]))}}
 
 
 # ---------------------------------------------------------------------------------------------- config 3
