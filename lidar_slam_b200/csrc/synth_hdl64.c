@@ -120,6 +120,9 @@ scene_t *synth_scene_create(uint64_t seed, double leg) {
         }
     /* parked cars (4.2 x 1.8 x 1.5 m) and poles along the driven corridor */
     double plen = synth_path_length(sc);
+    /* the quarter turn occupies s in [s_turn0 - margin, s_turn1 + margin]: keep kerb-side objects out of it (they
+     * are offset sideways from the centre line with the heading of the straight they stand on) */
+    double s_turn0 = sc->leg - sc->turn_r - 6.0, s_turn1 = sc->leg - sc->turn_r + 1.5707963267948966 * sc->turn_r + 6.0;
     int ncar = (int)(plen / 14.0), npol = (int)(plen / 18.0);
     for (int k = 0; k < ncar && nb < max_box; ++k) {
         uint64_t h = hash3(seed, 0xCA5, (uint64_t)k);
@@ -128,7 +131,7 @@ scene_t *synth_scene_create(uint64_t seed, double leg) {
         /* un-weaved centre line */
         scene_t tmp = *sc;
         synth_path_pose(&tmp, s, p);
-        double yaw = (s <= sc->leg) ? 0.0 : ((s >= sc->leg + 1.5707963267948966 * sc->turn_r) ? 1.5707963267948966 : -1.0);
+        double yaw = (s <= s_turn0) ? 0.0 : ((s >= s_turn1) ? 1.5707963267948966 : -1.0);
         if (yaw < 0) continue; /* no cars in the corner */
         double side = (splitmix64(h ^ 2) & 1) ? 1.0 : -1.0;
         double off = side * (3.2 + 0.8 * u01(splitmix64(h ^ 3)));
@@ -144,7 +147,8 @@ scene_t *synth_scene_create(uint64_t seed, double leg) {
         double s = plen * (k + u01(splitmix64(h ^ 1))) / npol;
         double p[6];
         synth_path_pose(sc, s, p);
-        double yaw = (s <= sc->leg) ? 0.0 : 1.5707963267948966;
+        if (s > s_turn0 && s < s_turn1) continue; /* no poles in the corner */
+        double yaw = (s <= s_turn0) ? 0.0 : 1.5707963267948966;
         double side = (splitmix64(h ^ 2) & 1) ? 1.0 : -1.0;
         double off = side * (4.4 + 0.4 * u01(splitmix64(h ^ 3)));
         pole_t *q = &sc->pole[np++];
@@ -153,6 +157,13 @@ scene_t *synth_scene_create(uint64_t seed, double leg) {
     }
     sc->n_box = nb; sc->n_pole = np;
     return sc;
+}
+/* 1 when (x, y) lies inside the footprint of any box of the scene (building or car) grown by `margin` */
+int synth_point_in_box(const scene_t *sc, double x, double y, double margin) {
+    for (int i = 0; i < sc->n_box; ++i)
+        if (x > sc->box[i].lo[0] - margin && x < sc->box[i].hi[0] + margin && y > sc->box[i].lo[1] - margin && y < sc->box[i].hi[1] + margin)
+            return 1;
+    return 0;
 }
 void synth_scene_free(scene_t *sc) { if (sc) { free(sc->box); free(sc->pole); free(sc); } }
 

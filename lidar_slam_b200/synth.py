@@ -35,6 +35,8 @@ def _lib():
                                   C.POINTER(C.c_float), C.POINTER(C.c_size_t), C.c_int]
         L.synth_map.argtypes = [C.c_void_p, C.c_size_t, C.c_double, C.POINTER(C.c_float), C.c_int]
         L.synth_map.restype = C.c_size_t
+        L.synth_point_in_box.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double]
+        L.synth_point_in_box.restype = C.c_int
         _LIB = L
     return _LIB
 
@@ -67,6 +69,10 @@ class Scene:
         p = np.zeros(6)
         _lib().synth_path_pose(self.h, float(s), p.ctypes.data_as(C.POINTER(C.c_double)))
         return p
+
+    def point_in_box(self, x, y, margin=0.0):
+        """True when (x, y) is inside the footprint of a building or car grown by `margin` metres."""
+        return bool(_lib().synth_point_in_box(self.h, float(x), float(y), float(margin)))
 
     def scan(self, frame_id, pose6, world=False):
         """One scan in the sensor frame -> (n,4) float32 {x,y,z,intensity}."""

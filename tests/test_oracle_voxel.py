@@ -163,3 +163,21 @@ def test_gauss2d_cells_and_yaw_oracle_small_case():
     scan[:, :2] = scan[:, :2] @ R.T                       # what the sensor sees when the vehicle is yawed by +1 rad
     best, probs = O.initial_yaw_angle(cells, scan, 90)
     assert abs(best - yaw) <= 2 * np.pi / 90
+
+
+def test_synthetic_drive_stays_on_the_streets():
+    """The L-shaped drive of the synthetic scene (street canyon) must never enter the footprint of
+    a building or a parked car, on either leg or in the corner -- a scan taken from inside a box is not a street
+    scene and the NDT (oracle and GPU alike) loses track there."""
+    from lidar_slam_b200 import synth
+    scene = synth.Scene(leg=500.0)
+    s = np.arange(0.0, scene.path_length, 0.25)
+    poses = np.stack([scene.path_pose(v) for v in s])
+    inside = [v for v, p in zip(s, poses) if scene.point_in_box(p[0], p[1], margin=0.5)]
+    assert not inside, "drive enters a box at s = %s" % inside[:5]
+    # both legs are street centre lines of the 50 m lattice (x or y = 25 + 50 k) up to the 0.6 m lane weave; the
+    # quarter turn (r = 12 m) cuts the intersection by at most r (1 - cos 45 deg) = 3.5 m, inside the 5 m clearance
+    on_street = np.minimum(np.abs((poses[:, 0] - 25.0 + 25.0) % 50.0 - 25.0), np.abs((poses[:, 1] - 25.0 + 25.0) % 50.0 - 25.0))
+    assert on_street.max() < 3.6 and np.percentile(on_street, 95) < 0.7
+    # the heading is continuous (no jump at the ends of the quarter turn)
+    assert np.abs(np.diff(poses[:, 5])).max() < 0.25 / 12.0 + 1e-3
