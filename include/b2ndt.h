@@ -179,7 +179,7 @@ int  b2ndt_align_cloud(b2ndt *h, b2cloud *src, const float guess[16], float pose
 /* ------------------------------------------------------------------ PCD files ----------------
  * PCD v0.7 I/O for PointXYZI clouds (pcl::io::loadPCDFile at matching.cpp:155, loop_closing.cpp:134,286,304;
  * pcl::io::savePCDFileBinary at back_end.cpp:194, viewer.cpp:202,210).  DATA ascii and binary are read (any field
- * set containing x y z, intensity optional), binary PointXYZI is written; binary_compressed is not supported.
+ * set containing x y z, intensity optional), binary PointXYZI is written; binary_compressed (LZF) files are read as well.
  * b2_pcd_read returns a malloc'ed packed {x,y,z,intensity} array (release with b2_pcd_free); host-only calls. */
 int  b2_pcd_read(const char *path, float **xyzi, size_t *n_points);
 void b2_pcd_free(float *xyzi);

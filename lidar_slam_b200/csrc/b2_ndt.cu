@@ -1465,8 +1465,7 @@ static int build_target(b2ndt *h, const float4 *d_pts, size_t n, int nbits_hint)
     B2_CUDA(cudaMemcpyAsync(misc + 8, h->pipe.layouts(), sizeof(VoxLayout), cudaMemcpyDeviceToHost, h->st));
     B2_CUDA(cudaStreamSynchronize(h->st));
     memcpy(&t.L, misc + 8, sizeof(VoxLayout));
-    t.valid = true;
-    if (!t.L.ok) return 0;     // empty cloud or PCL's int32 guard: no cells (PCL warns and clears)
+    if (!t.L.ok) { t.valid = true; return 0; }     // empty cloud or PCL's int32 guard: no cells (PCL warns and clears)
     t.V = misc[1];
     const uint32_t V = t.V;
     if ((rc = t.pts_sorted.reserve((n + 1) * sizeof(float4)))) return rc;
@@ -1517,6 +1516,7 @@ static int build_target(b2ndt *h, const float4 *d_pts, size_t n, int nbits_hint)
                                                        t.nbr_tiles.as<uint32_t>(), LA, t.nbr_list.as<float4>());
         B2_LAUNCH_CHECK();
     }
+    t.valid = true;     // only a completely built target is usable: a failed allocation above leaves "no target set"
     return 0;
 }
 
@@ -1866,6 +1866,7 @@ extern "C" int b2ndt_derivatives(b2ndt *h, const void *src, size_t n, size_t str
         pack_cloud_f4(src, n, stride, ioff, (float *)stage);
         B2_CUDA(cudaMemcpyAsync(h->d_src.p, stage, n * 16, cudaMemcpyHostToDevice, h->st));
     }
+    h->have_last = false;      // d_src no longer holds the source of the last ScanMatch (GetFitnessScore needs a new one)
     memcpy(stage + n * 16, p, 48);
     B2_CUDA(cudaMemcpyAsync(h->d_p6.p, stage + n * 16, 48, cudaMemcpyHostToDevice, h->st));
     MatchArgs A;

@@ -5,7 +5,9 @@
 // follows the published PCD v0.7 format: an ASCII header (VERSION, FIELDS, SIZE, TYPE, COUNT, WIDTH, HEIGHT, VIEWPOINT,
 // POINTS, DATA) followed by ascii rows or packed binary records.  pcl::PointXYZI is stored as the four float32 fields
 // x y z intensity = 16 bytes per point, which is exactly the device layout {x,y,z,intensity}: a binary PointXYZI file is
-// uploaded without any repacking.  DATA binary_compressed (LZF) is not supported.
+// uploaded without any repacking.  DATA binary_compressed (field-major records in one LZF stream, what
+// pcl::io::savePCDFileBinaryCompressed and most third-party map tools write) is read as well; files are written as
+// DATA binary only, like the reference.
 #include <cerrno>
 #include <cstdio>
 #include <cstdlib>
@@ -28,6 +30,32 @@ double field_value(const unsigned char *p, const PcdField &f) {
         default:  if (f.size == 1) return *(const signed char *)p; if (f.size == 2) { int16_t v; memcpy(&v, p, 2); return v; }
                   if (f.size == 4) { int32_t v; memcpy(&v, p, 4); return v; } { int64_t v; memcpy(&v, p, 8); return (double)v; }
     }
+}
+
+// LZF decompression (the codec of PCD "binary_compressed"): a control byte < 32 starts a literal run of ctrl + 1
+// bytes; otherwise the top three bits are the match length - 2 (7 = extended by the next byte) and the low five
+// bits plus the following byte the distance - 1 of a back reference into the output.  Returns the number of bytes
+// produced, 0 on a malformed stream.
+size_t lzf_decompress(const unsigned char *in, size_t in_len, unsigned char *out, size_t out_len) {
+    size_t ip = 0, op = 0;
+    while (ip < in_len) {
+        unsigned ctrl = in[ip++];
+        if (ctrl < 32) {
+            const size_t run = ctrl + 1;
+            if (ip + run > in_len || op + run > out_len) return 0;
+            memcpy(out + op, in + ip, run);
+            ip += run; op += run;
+        } else {
+            size_t len = ctrl >> 5;
+            if (len == 7) { if (ip >= in_len) return 0; len += in[ip++]; }
+            if (ip >= in_len) return 0;
+            const size_t dist = ((size_t)(ctrl & 0x1f) << 8) + in[ip++] + 1;
+            len += 2;
+            if (dist > op || op + len > out_len) return 0;
+            for (size_t k = 0; k < len; ++k, ++op) out[op] = out[op - dist];      // the ranges may overlap
+        }
+    }
+    return op;
 }
 }  // namespace
 
@@ -89,6 +117,26 @@ extern "C" int b2_pcd_read(const char *path, float **xyzi, size_t *n_points) {
                 out[4 * got + 3] = fi >= 0 ? (float)field_value(rec.data() + fields[fi].offset, fields[fi]) : 0.f;
             }
         }
+    } else if (data == "binary_compressed") {
+        // pcl::PCDWriter::writeBinaryCompressed: u32 compressed size, u32 uncompressed size, one LZF stream holding
+        // the cloud field by field (all x, then all y, ...), each field block points * SIZE * COUNT bytes
+        uint32_t hdr[2];
+        if (fread(hdr, 4, 2, f) != 2) { fclose(f); free(out); set_error("b2_pcd_read: %s: truncated compressed header", path); return B2_ERR_INVALID; }
+        const size_t csize = hdr[0], usize = hdr[1];
+        if (usize != stride * points) { fclose(f); free(out); set_error("b2_pcd_read: %s: uncompressed size %zu != %zu points x %zu bytes", path, usize, points, stride); return B2_ERR_INVALID; }
+        std::vector<unsigned char> comp(csize ? csize : 1), raw(usize ? usize : 1);
+        if (fread(comp.data(), 1, csize, f) != csize || lzf_decompress(comp.data(), csize, raw.data(), usize) != usize) {
+            fclose(f); free(out); set_error("b2_pcd_read: %s: corrupt LZF stream", path); return B2_ERR_INVALID;
+        }
+        auto block = [&](int fld) { return raw.data() + fields[fld].offset * points; };       // offset = bytes of the fields before it
+        const size_t sx = (size_t)fields[fx].size * fields[fx].count, sy = (size_t)fields[fy].size * fields[fy].count,
+                     sz = (size_t)fields[fz].size * fields[fz].count, si = fi >= 0 ? (size_t)fields[fi].size * fields[fi].count : 0;
+        for (; got < points; ++got) {
+            out[4 * got + 0] = (float)field_value(block(fx) + got * sx, fields[fx]);
+            out[4 * got + 1] = (float)field_value(block(fy) + got * sy, fields[fy]);
+            out[4 * got + 2] = (float)field_value(block(fz) + got * sz, fields[fz]);
+            out[4 * got + 3] = fi >= 0 ? (float)field_value(block(fi) + got * si, fields[fi]) : 0.f;
+        }
     } else if (data == "ascii") {
         while (got < points && fgets(line, sizeof line, f)) {
             size_t col = 0;
@@ -109,7 +157,7 @@ extern "C" int b2_pcd_read(const char *path, float **xyzi, size_t *n_points) {
         }
     } else {
         fclose(f); free(out);
-        set_error("b2_pcd_read: DATA %s is not supported (ascii and binary are)", data.c_str());
+        set_error("b2_pcd_read: DATA %s is not supported (ascii, binary and binary_compressed are)", data.c_str());
         return B2_ERR_INVALID;
     }
     fclose(f);

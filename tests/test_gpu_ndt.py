@@ -240,6 +240,11 @@ def test_degenerate_inputs(oracle, small_map):
     fit = reg.GetFitnessScore()
     ofit = oracle.fitness_score(small_map, far, np.eye(4, dtype=np.float32))
     assert abs(fit - ofit) <= 1e-4 * ofit
+    # a derivative pass or a batch reuses the handle's source buffer: the "last ScanMatch" is gone
+    reg.Derivatives(far, np.zeros(6))
+    with pytest.raises(capi.B2Error) as e:
+        reg.GetFitnessScore()
+    assert e.value.code == capi.B2_ERR_STATE
     # empty target: PCL leaves no cells
     reg.SetInputTarget(np.zeros((0, 4), np.float32))
     ok, cloud, pose = reg.ScanMatch(far, np.eye(4, dtype=np.float32))

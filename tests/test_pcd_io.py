@@ -59,7 +59,7 @@ def test_errors_are_reported(tmp_path):
         capi.pcd_read(str(t))
     assert "truncated" in str(e.value)
     z = tmp_path / "z.pcd"
-    z.write_bytes(b"VERSION 0.7\nFIELDS x y z\nSIZE 4 4 4\nTYPE F F F\nCOUNT 1 1 1\nWIDTH 1\nHEIGHT 1\nPOINTS 1\nDATA binary_compressed\n")
+    z.write_bytes(b"VERSION 0.7\nFIELDS x y z\nSIZE 4 4 4\nTYPE F F F\nCOUNT 1 1 1\nWIDTH 1\nHEIGHT 1\nPOINTS 1\nDATA binary_zstd\n")
     with pytest.raises(capi.B2Error) as e:
         capi.pcd_read(str(z))
     assert "not supported" in str(e.value)
@@ -67,6 +67,73 @@ def test_errors_are_reported(tmp_path):
     n.write_text("hello\n")
     with pytest.raises(capi.B2Error):
         capi.pcd_read(str(n))
+
+
+def _lzf_compress(data: bytes) -> bytes:
+    """Greedy LZF encoder (test helper): literal runs of <= 32 bytes, back references of 3..264 bytes within 8 KiB."""
+    out, lit, i, n, last = bytearray(), bytearray(), 0, len(data), {}
+
+    def flush():
+        for k in range(0, len(lit), 32):
+            run = lit[k:k + 32]
+            out.append(len(run) - 1); out.extend(run)
+        lit.clear()
+
+    while i < n:
+        key = data[i:i + 3]
+        j = last.get(key, -1) if len(key) == 3 else -1
+        last[key] = i
+        if j >= 0 and i - j <= 8192:
+            m = 3
+            while i + m < n and m < 264 and data[j + m] == data[i + m]:
+                m += 1
+            flush()
+            dist, ln = i - j - 1, m - 2
+            if ln < 7:
+                out.append((ln << 5) | (dist >> 8))
+            else:
+                out.append((7 << 5) | (dist >> 8)); out.append(ln - 7)
+            out.append(dist & 0xFF)
+            i += m
+        else:
+            lit.append(data[i]); i += 1
+    flush()
+    return bytes(out)
+
+
+def test_binary_compressed(tmp_path):
+    """DATA binary_compressed: u32 sizes + one LZF stream holding the cloud field by field (PCD v0.7)."""
+    rng = np.random.default_rng(7)
+    n = 5000
+    c = np.zeros((n, 4), np.float32)
+    c[:, 0] = np.round(rng.uniform(-50, 50, n), 1); c[:, 1] = np.round(rng.uniform(-50, 50, n), 1)
+    c[:, 2] = 0.0                                     # a constant field: long overlapping back references
+    c[:, 3] = rng.integers(0, 4, n) / 4.0
+    c[17, 0] = np.nan
+    # fields in a foreign order with an extra u16 ring field in the middle
+    ring = rng.integers(0, 64, n).astype(np.uint16)
+    raw = c[:, 3].tobytes() + c[:, 0].tobytes() + ring.tobytes() + c[:, 1].tobytes() + c[:, 2].tobytes()
+    comp = _lzf_compress(raw)
+    assert len(comp) < 0.7 * len(raw)                 # the helper really emits back references
+    hdr = ("# .PCD v0.7 - Point Cloud Data file format\nVERSION 0.7\nFIELDS intensity x ring y z\nSIZE 4 4 2 4 4\nTYPE F F U F F\n"
+           "COUNT 1 1 1 1 1\nWIDTH %d\nHEIGHT 1\nVIEWPOINT 0 0 0 1 0 0 0\nPOINTS %d\nDATA binary_compressed\n" % (n, n)).encode()
+    p = tmp_path / "bc.pcd"
+    p.write_bytes(hdr + struct.pack("<II", len(comp), len(raw)) + comp)
+    assert np.array_equal(capi.pcd_read(str(p)), c, equal_nan=True)
+    # literal-only stream (incompressible data), empty cloud
+    lit = b"".join(bytes([len(raw[k:k + 32]) - 1]) + raw[k:k + 32] for k in range(0, len(raw), 32))
+    p.write_bytes(hdr + struct.pack("<II", len(lit), len(raw)) + lit)
+    assert np.array_equal(capi.pcd_read(str(p)), c, equal_nan=True)
+    e0 = tmp_path / "e0.pcd"
+    e0.write_bytes(b"VERSION 0.7\nFIELDS x y z\nSIZE 4 4 4\nTYPE F F F\nCOUNT 1 1 1\nWIDTH 0\nHEIGHT 1\nPOINTS 0\nDATA binary_compressed\n" + struct.pack("<II", 0, 0))
+    assert capi.pcd_read(str(e0)).shape == (0, 4)
+    # corrupt streams are reported, not read out of bounds: truncated payload, wrong size word, reference before the start
+    for bad in (hdr + struct.pack("<II", len(comp), len(raw)) + comp[:len(comp) // 2],
+                hdr + struct.pack("<II", len(comp), len(raw) - 4) + comp,
+                hdr + struct.pack("<II", 3, len(raw)) + bytes([0x20, 0x05, 0x00])):
+        p.write_bytes(bad)
+        with pytest.raises(capi.B2Error):
+            capi.pcd_read(str(p))
 
 
 @pytest.mark.gpu
