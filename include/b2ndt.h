@@ -160,7 +160,9 @@ int  b2cloud_device_ptr(b2cloud *c, void **d_f4);
 /* dst += pcl::transformPointCloud(src, T) (T column-major float 4x4; intensity kept; order kept) */
 int  b2cloud_append_transformed(b2cloud *dst, b2cloud *src, const float T[16]);
 /* pcl::CropBox: dst = points of src with edge[0] <= x <= edge[1], edge[2] <= y <= edge[3],
- * edge[4] <= z <= edge[5] (BoxFilter::GetEdge order), input order kept, non-finite points dropped */
+ * edge[4] <= z <= edge[5] (BoxFilter::GetEdge order), input order kept, non-finite points dropped.
+ * For this call, b2cloud_remove_nan and b2cloud_distortion_adjust dst may be src (the reference's in == out calls):
+ * the survivors are written to the cloud's second buffer and the buffers swapped, so b2cloud_device_ptr changes. */
 int  b2cloud_box_filter(b2cloud *src, const float edge[6], b2cloud *dst);
 /* pcl::removeNaNFromPointCloud: dst = points of src with finite x, y, z, input order kept (front_end.cpp:92) */
 int  b2cloud_remove_nan(b2cloud *src, b2cloud *dst);

@@ -192,7 +192,7 @@ extern "C" void b2cloud_destroy(b2cloud *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->st);
-    c->pts.release(); c->scratch.release(); c->h_stage.release(); c->h_small.release();
+    c->pts.release(); c->alt.release(); c->scratch.release(); c->h_stage.release(); c->h_small.release();
     if (c->st) cudaStreamDestroy(c->st);
     delete c;
 }
@@ -297,25 +297,30 @@ static int compact_cloud(const char *fn, b2cloud *src, b2cloud *dst, const Op &B
     int rc = cloud_check(fn, src);
     if (rc) return rc;
     if ((rc = cloud_check(fn, dst))) return rc;
-    if (dst == src) { set_error("%s: dst == src", fn); return B2_ERR_INVALID; }
     if (dst->device != src->device) { set_error("%s: clouds live on different devices", fn); return B2_ERR_INVALID; }
     B2_CUDA(cudaSetDevice(dst->device));
-    dst->n = 0;
+    // dst == src (the reference calls its filters with in == out, e.g. matching.cpp:158): the survivors go to the
+    // cloud's second buffer and the two buffers are swapped, so the cloud's device pointer changes
+    const bool in_place = (dst == src);
     const size_t n = src->n;
+    if (!in_place) dst->n = 0;
     if (n == 0) return 0;
     const uint32_t ntiles = (uint32_t)((n + CROP_TILE - 1) / CROP_TILE);
-    if ((rc = dst->reserve(n))) return rc;
+    if (in_place) { if ((rc = dst->alt.reserve(n * 16 + 16))) return rc; }
+    else if ((rc = dst->reserve(n))) return rc;
     if ((rc = dst->scratch.reserve((size_t)(ntiles + 1) * 4 + 256))) return rc;
     if ((rc = dst->h_small.reserve(256))) return rc;
     uint32_t *tiles = dst->scratch.as<uint32_t>() + 64;     // first 256 bytes hold the transform of append
+    float4 *out = in_place ? dst->alt.as<float4>() : dst->d();
     crop_count_kernel<<<ntiles, CROP_THREADS, 0, dst->st>>>(src->d(), (uint32_t)n, B, tiles);
     B2_LAUNCH_CHECK();
     crop_scan_kernel<<<1, 1024, 0, dst->st>>>(tiles, ntiles);
     B2_LAUNCH_CHECK();
-    crop_scatter_kernel<<<ntiles, CROP_THREADS, 0, dst->st>>>(src->d(), (uint32_t)n, B, tiles, dst->d());
+    crop_scatter_kernel<<<ntiles, CROP_THREADS, 0, dst->st>>>(src->d(), (uint32_t)n, B, tiles, out);
     B2_LAUNCH_CHECK();
     B2_CUDA(cudaMemcpyAsync(dst->h_small.p, tiles + ntiles, 4, cudaMemcpyDeviceToHost, dst->st));
     B2_CUDA(cudaStreamSynchronize(dst->st));
+    if (in_place) { const DevBuf t = dst->pts; dst->pts = dst->alt; dst->alt = t; }
     dst->n = *dst->h_small.as<uint32_t>();
     return 0;
 }
@@ -332,7 +337,7 @@ extern "C" int b2cloud_box_filter(b2cloud *src, const float edge[6], b2cloud *ds
 extern "C" int b2cloud_distortion_adjust(b2cloud *src, float scan_period, const double linear_velocity[3],
                                          const double angular_velocity[3], b2cloud *dst) {
     if (!src || !dst || !linear_velocity || !angular_velocity) { set_error("b2cloud_distortion_adjust: NULL argument"); return B2_ERR_INVALID; }
-    if (src->n == 0) { dst->n = 0; return 0; }
+    if (src->n == 0) { dst->n = 0; return 0; }     // in == out is allowed (data_pretreat_flow.cpp calls AdjustCloud that way)
     B2_CUDA(cudaSetDevice(src->device));
     int rc;
     if ((rc = src->h_small.reserve(256))) return rc;

@@ -11,6 +11,7 @@ struct b2cloud {
     b2::DevBuf pts;               // float4[capacity]
     cudaStream_t st = nullptr;    // stream of the cloud's own operations (upload, append, crop)
     b2::DevBuf scratch;           // compaction bookkeeping (tile counts)
+    b2::DevBuf alt;               // second point buffer: in-place compaction writes here, then the two are swapped
     b2::PinBuf h_stage, h_small;
     int reserve(size_t npts) {
         if (npts * 16 + 16 <= pts.cap) return 0;

@@ -99,7 +99,8 @@ class DeviceCloud:
         capi.check(capi.lib().b2cloud_save_pcd(self._h, os.fsencode(path)))
 
     def RemoveNaN(self, dst=None):
-        """pcl::removeNaNFromPointCloud (front_end.cpp:92): finite points of *this, order kept -> dst (new cloud if None)."""
+        """pcl::removeNaNFromPointCloud (front_end.cpp:92): finite points of *this, order kept -> dst (new cloud if
+        None; dst may be this cloud: in place, the device pointer changes)."""
         if dst is None:
             dst = DeviceCloud()
         capi.check(capi.lib().b2cloud_remove_nan(self._h, dst._h))
@@ -326,7 +327,7 @@ class BoxFilter(CloudFilterInterface):
         return list(self.edge_)
 
     def FilterCloud(self, src, dst=None):
-        """Device clouds in, device cloud out (order kept)."""
+        """Device clouds in, device cloud out (order kept); dst may be src (in place)."""
         if dst is None:
             dst = DeviceCloud(device=self.device)
         e = np.asarray(self.edge_, np.float32)

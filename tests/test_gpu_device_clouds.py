@@ -134,3 +134,30 @@ def test_remove_nan_keeps_finite_points_in_order(scene):
     keep = np.isfinite(scan[:, :3]).all(axis=1)
     assert len(out) == keep.sum() and np.array_equal(out, scan[keep], equal_nan=True)
     assert len(DeviceCloud(np.full((7, 4), np.nan, np.float32)).RemoveNaN()) == 0
+
+
+def test_in_place_compaction_like_the_reference_calls_it(scene):
+    """The reference hands its filters the same pointer as input and output (matching.cpp:158, data_pretreat_flow's
+    AdjustCloud): crop, NaN removal and de-skew with dst == src give what the two-cloud call gives, repeatedly."""
+    from lidar_slam_b200.registration import BoxFilter, DeviceCloud, DistortionAdjust
+    scan = scene.scan(21, scene.path_pose(40.0)).copy()
+    scan[::97, 1] = np.nan
+    bf = BoxFilter({"box_filter_size": [-40.0, 40.0, -20.0, 20.0, -3.0, 8.0]})
+    bf.SetOrigin([0.0, 0.0, 0.0])
+    da = DistortionAdjust()
+    da.SetMotionInfo(0.1, [8.0, 0.2, 0.0], [0.0, 0.01, 0.3])
+    c = DeviceCloud(scan)
+    want = c.RemoveNaN()
+    assert c.RemoveNaN(c) is c and np.array_equal(c.Download(), want.Download())
+    want = bf.FilterCloud(c)
+    n_before = len(c)
+    assert bf.FilterCloud(c, c) is c and 0 < len(c) < n_before and np.array_equal(c.Download(), want.Download())
+    assert np.array_equal(bf.FilterCloud(c, c).Download(), want.Download())          # idempotent, buffers swap back
+    want = da.AdjustCloudDevice(c)
+    assert da.AdjustCloudDevice(c, c) is c and np.array_equal(c.Download(), want.Download())
+    # the cloud is still a normal cloud afterwards: append and target build work on the swapped buffer
+    d = DeviceCloud()
+    d.AppendTransformed(c, np.eye(4, dtype=np.float32))
+    assert np.array_equal(d.Download(), c.Download())
+    e = DeviceCloud(np.zeros((0, 4), np.float32))
+    assert len(bf.FilterCloud(e, e)) == 0
