@@ -51,25 +51,99 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region.  NVML is polled from a thread every ~5 ms with
+    wall-clock stamps, and the samples between mark_begin() / mark_end() (the timed steps) are the ones reported;
+    without NVML bindings the nvidia-smi loop (-lms 20) of the profiling recipe is used instead."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,"
          "utilization.gpu")
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.f = None
         self.p = None
+        self.nv = None
+        self.samples = []           # (t, sm_mhz, reasons bitmask)
+        self.windows = []           # [t_begin, t_end] of every timed region
+        self._stop = False
+        self.thread = None
+        self.sm_max = None
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            import torch
+            uuid = str(torch.cuda.get_device_properties(self.gpu).uuid)
+            return pynvml, pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+        except Exception:
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.gpu]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else self.gpu
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(idx)
+
+    def _poll(self):
+        nv, h = self.nv
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self._stop:
+            try:
+                self.samples.append((time.perf_counter(), float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), int(get_reasons(h))))
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def start(self):
         try:
+            self.nv = self._nvml_handle()
+            self.sm_max = float(self.nv[0].nvmlDeviceGetMaxClockInfo(self.nv[1], self.nv[0].NVML_CLOCK_SM))
+            import threading
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nv = None
+        try:
+            self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
             self.p = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20",
                                        "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
+    def mark_begin(self):
+        self.windows.append([time.perf_counter(), None])
+
+    def mark_end(self):
+        if self.windows:
+            self.windows[-1][1] = time.perf_counter()
+
+    def _stop_nvml(self):
+        self._stop = True
+        self.thread.join(timeout=2)
+        nv = self.nv[0]
+        names = (("hw_slowdown", "HwSlowdown"), ("hw_thermal_slowdown", "HwThermalSlowdown"),
+                 ("sw_thermal_slowdown", "SwThermalSlowdown"), ("sw_power_cap", "SwPowerCap"))
+        masks = {}
+        for key, suffix in names:
+            for prefix in ("nvmlClocksEventReason", "nvmlClocksThrottleReason"):
+                if hasattr(nv, prefix + suffix):
+                    masks[key] = int(getattr(nv, prefix + suffix)); break
+        inside = [x for x in self.samples if any(b is not None and e is not None and b <= x[0] <= e for b, e in self.windows)]
+        use = inside if inside else self.samples
+        out = {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": [], "samples": len(self.samples), "source": "nvml"}
+        if use:
+            bits = 0
+            for x in use:
+                bits |= x[2]
+            out.update(sm_mhz=float(np.median([x[1] for x in use])), reasons=sorted(k for k, m in masks.items() if bits & m),
+                       samples_under_load=len(inside))
+        return out
+
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.nv is not None and self.thread is not None:
+            try:
+                return self._stop_nvml()
+            except Exception:
+                return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": [], "samples": len(self.samples), "source": "nvml"}
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": "nvidia-smi"}
         if self.p is None:
             return out
         time.sleep(0.15)
@@ -315,6 +389,7 @@ def main():
     barrier()
     if args.profile_range:
         torch.cuda.profiler.start()
+    sampler.mark_begin()
     wall0 = time.perf_counter()
     for _ in range(args.steps):
         flush.fill_(0.0)                      # L2 flush between timed steps (outside the event pair)
@@ -325,6 +400,7 @@ def main():
         evs.append((e0, e1))
     barrier()
     wall_s = time.perf_counter() - wall0
+    sampler.mark_end()
     if args.profile_range:
         torch.cuda.profiler.stop()
     gpu_launches = capi.launches() - launches0
@@ -354,12 +430,14 @@ def main():
     for _ in range(args.warmup):
         step_e2e()
     barrier()
+    sampler.mark_begin()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step_e2e()
     barrier()
     e2e_s = time.perf_counter() - t0
-    clocks = sampler.stop()                # samples cover the device-resident and the end-to-end timed regions
+    sampler.mark_end()
+    clocks = sampler.stop()                # the samples inside the device-resident and the end-to-end timed regions
     assert np.array_equal(out_res["iterations"], res["iterations"]), "host and device batch paths disagree"
 
     # single-match latency through b2ndt_align (p50 over a sample of frames, cluster of 8 CTAs)
