@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <string>
 #include <vector>
 
@@ -60,11 +61,12 @@ size_t lzf_decompress(const unsigned char *in, size_t in_len, unsigned char *out
 }  // namespace
 
 // Read a PCD file into a malloc'ed packed float4 {x,y,z,intensity} array (*xyzi, release with b2_pcd_free).
-extern "C" int b2_pcd_read(const char *path, float **xyzi, size_t *n_points) {
+static int pcd_read_impl(const char *path, float **xyzi, size_t *n_points) {
     if (!path || !xyzi || !n_points) { set_error("b2_pcd_read: NULL argument"); return B2_ERR_INVALID; }
     *xyzi = nullptr; *n_points = 0;
     FILE *f = fopen(path, "rb");
     if (!f) { set_error("b2_pcd_read: cannot open %s: %s", path, strerror(errno)); return B2_ERR_INVALID; }
+    struct Closer { FILE *f; ~Closer() { fclose(f); } } closer{f};      // every return below closes the file
     std::vector<PcdField> fields;
     size_t width = 0, height = 1, points = 0;
     bool have_points = false;
@@ -85,23 +87,37 @@ extern "C" int b2_pcd_read(const char *path, float **xyzi, size_t *n_points) {
         else if (k == "POINTS" && tok.size() > 1) { points = strtoull(tok[1].c_str(), nullptr, 10); have_points = true; }
         else if (k == "DATA"   && tok.size() > 1) { data = tok[1]; break; }
     }
-    if (data.empty() || fields.empty()) { fclose(f); set_error("b2_pcd_read: %s has no PCD header (FIELDS / DATA)", path); return B2_ERR_INVALID; }
+    if (data.empty() || fields.empty()) { set_error("b2_pcd_read: %s has no PCD header (FIELDS / DATA)", path); return B2_ERR_INVALID; }
     if (!have_points) points = width * height;
     size_t stride = 0;
     int fx = -1, fy = -1, fz = -1, fi = -1;
     for (size_t i = 0; i < fields.size(); ++i) {
         PcdField &fd = fields[i];
-        if (fd.size != 1 && fd.size != 2 && fd.size != 4 && fd.size != 8) { fclose(f); set_error("b2_pcd_read: bad SIZE %d", fd.size); return B2_ERR_INVALID; }
+        if (fd.size != 1 && fd.size != 2 && fd.size != 4 && fd.size != 8) { set_error("b2_pcd_read: bad SIZE %d", fd.size); return B2_ERR_INVALID; }
         if (fd.count < 1) fd.count = 1;
         fd.offset = stride;
         stride += (size_t)fd.size * (size_t)fd.count;
         if (fd.name == "x") fx = (int)i; else if (fd.name == "y") fy = (int)i; else if (fd.name == "z") fz = (int)i;
         else if (fd.name == "intensity") fi = (int)i;
     }
-    if (fx < 0 || fy < 0 || fz < 0) { fclose(f); set_error("b2_pcd_read: %s has no x / y / z fields", path); return B2_ERR_INVALID; }
-    if (points >= 0xFFFFFFF0ull) { fclose(f); set_error("b2_pcd_read: cloud too large"); return B2_ERR_INVALID; }
+    if (fx < 0 || fy < 0 || fz < 0) { set_error("b2_pcd_read: %s has no x / y / z fields", path); return B2_ERR_INVALID; }
+    if (points >= 0xFFFFFFF0ull) { set_error("b2_pcd_read: cloud too large"); return B2_ERR_INVALID; }
+    if (stride > (1u << 20)) { set_error("b2_pcd_read: %s: %zu bytes per point is not a point cloud", path, stride); return B2_ERR_INVALID; }
+    {
+        // the header must not promise more than the file holds (before anything is allocated for it): binary needs
+        // stride bytes per point, ascii at least two characters per row, a compressed byte expands at most 88-fold
+        const long here = ftell(f);
+        long end = here;
+        if (here >= 0 && fseek(f, 0, SEEK_END) == 0) { end = ftell(f); fseek(f, here, SEEK_SET); }
+        const size_t left = (here >= 0 && end >= here) ? (size_t)(end - here) : 0;
+        const bool fits = data == "binary" ? points <= left / (stride ? stride : 1)
+                        : data == "ascii" ? points <= left / 2 + 1
+                        : data == "binary_compressed" ? points <= (left * 88) / (stride ? stride : 1) + 1 : true;
+        if (!fits) { set_error("b2_pcd_read: %s is truncated (%zu points announced, %zu data bytes present)", path, points, left); return B2_ERR_INVALID; }
+    }
     float *out = (float *)malloc(points ? points * 16 : 16);
-    if (!out) { fclose(f); set_error("b2_pcd_read: out of memory (%zu points)", points); return B2_ERR_INVALID; }
+    if (!out) { set_error("b2_pcd_read: out of memory (%zu points)", points); return B2_ERR_INVALID; }
+    struct Owner { float *p; ~Owner() { free(p); } } owner{out};          // released on every error path below
     size_t got = 0;
     if (data == "binary") {
         const bool direct = fields.size() == 4 && fx == 0 && fy == 1 && fz == 2 && fi == 3 && stride == 16 &&
@@ -121,12 +137,18 @@ extern "C" int b2_pcd_read(const char *path, float **xyzi, size_t *n_points) {
         // pcl::PCDWriter::writeBinaryCompressed: u32 compressed size, u32 uncompressed size, one LZF stream holding
         // the cloud field by field (all x, then all y, ...), each field block points * SIZE * COUNT bytes
         uint32_t hdr[2];
-        if (fread(hdr, 4, 2, f) != 2) { fclose(f); free(out); set_error("b2_pcd_read: %s: truncated compressed header", path); return B2_ERR_INVALID; }
+        if (fread(hdr, 4, 2, f) != 2) { set_error("b2_pcd_read: %s: truncated compressed header", path); return B2_ERR_INVALID; }
         const size_t csize = hdr[0], usize = hdr[1];
-        if (usize != stride * points) { fclose(f); free(out); set_error("b2_pcd_read: %s: uncompressed size %zu != %zu points x %zu bytes", path, usize, points, stride); return B2_ERR_INVALID; }
+        {
+            const long here = ftell(f);
+            long end = here;
+            if (here >= 0 && fseek(f, 0, SEEK_END) == 0) { end = ftell(f); fseek(f, here, SEEK_SET); }
+            if (here < 0 || end < here || (size_t)(end - here) < csize) { set_error("b2_pcd_read: %s: compressed payload of %zu bytes is truncated", path, csize); return B2_ERR_INVALID; }
+        }
+        if (usize != stride * points) { set_error("b2_pcd_read: %s: uncompressed size %zu != %zu points x %zu bytes", path, usize, points, stride); return B2_ERR_INVALID; }
         std::vector<unsigned char> comp(csize ? csize : 1), raw(usize ? usize : 1);
         if (fread(comp.data(), 1, csize, f) != csize || lzf_decompress(comp.data(), csize, raw.data(), usize) != usize) {
-            fclose(f); free(out); set_error("b2_pcd_read: %s: corrupt LZF stream", path); return B2_ERR_INVALID;
+            set_error("b2_pcd_read: %s: corrupt LZF stream", path); return B2_ERR_INVALID;
         }
         auto block = [&](int fld) { return raw.data() + fields[fld].offset * points; };       // offset = bytes of the fields before it
         const size_t sx = (size_t)fields[fx].size * fields[fx].count, sy = (size_t)fields[fy].size * fields[fy].count,
@@ -156,14 +178,23 @@ extern "C" int b2_pcd_read(const char *path, float **xyzi, size_t *n_points) {
             ++got;
         }
     } else {
-        fclose(f); free(out);
         set_error("b2_pcd_read: DATA %s is not supported (ascii, binary and binary_compressed are)", data.c_str());
         return B2_ERR_INVALID;
     }
-    fclose(f);
-    if (got != points) { free(out); set_error("b2_pcd_read: %s is truncated (%zu of %zu points)", path, got, points); return B2_ERR_INVALID; }
+    if (got != points) { set_error("b2_pcd_read: %s is truncated (%zu of %zu points)", path, got, points); return B2_ERR_INVALID; }
+    owner.p = nullptr;
     *xyzi = out; *n_points = points;
     return 0;
+}
+
+// C entry point: no C++ exception (an allocation a hostile header asks for) crosses the ABI
+extern "C" int b2_pcd_read(const char *path, float **xyzi, size_t *n_points) {
+    try {
+        return pcd_read_impl(path, xyzi, n_points);
+    } catch (const std::exception &e) {
+        set_error("b2_pcd_read: %s: %s", path ? path : "(null)", e.what());
+        return B2_ERR_INVALID;
+    }
 }
 
 extern "C" void b2_pcd_free(float *xyzi) { free(xyzi); }

@@ -146,3 +146,55 @@ def test_device_cloud_load_save(tmp_path):
     assert np.array_equal(capi.pcd_read(str(p)), c)
     d = DeviceCloud().LoadPCD(str(p))
     assert len(d) == len(c) and np.array_equal(d.Download(), c)
+
+
+def test_compressed_reader_survives_corruption(tmp_path):
+    """Random byte flips / truncations of a valid binary_compressed file either decode to n points or raise B2Error;
+    the decoder never reads or writes outside its buffers (a crash would take the test process down)."""
+    rng = np.random.default_rng(11)
+    n = 600
+    c = np.round(rng.uniform(-20, 20, (n, 4)), 1).astype(np.float32)
+    raw = b"".join(c[:, k].tobytes() for k in range(4))
+    comp = _lzf_compress(raw)
+    hdr = ("VERSION 0.7\nFIELDS x y z intensity\nSIZE 4 4 4 4\nTYPE F F F F\nCOUNT 1 1 1 1\nWIDTH %d\nHEIGHT 1\nPOINTS %d\n"
+           "DATA binary_compressed\n" % (n, n)).encode()
+    good = hdr + struct.pack("<II", len(comp), len(raw)) + comp
+    p = tmp_path / "f.pcd"
+    p.write_bytes(good)
+    assert np.array_equal(capi.pcd_read(str(p)), c)
+    ok = bad = 0
+    for trial in range(300):
+        b = bytearray(good)
+        kind = trial % 3
+        if kind == 0:                                   # flip bytes in the LZF payload
+            for pos in rng.integers(len(hdr) + 8, len(b), rng.integers(1, 6)):
+                b[pos] = rng.integers(0, 256)
+        elif kind == 1:                                 # lie in the size words
+            struct.pack_into("<I", b, len(hdr) + 4 * int(rng.integers(0, 2)), int(rng.integers(0, 2 * len(raw))))
+        else:                                           # truncate
+            b = b[:int(rng.integers(len(hdr), len(b)))]
+        p.write_bytes(bytes(b))
+        try:
+            out = capi.pcd_read(str(p))
+            assert out.shape == (n, 4)
+            ok += 1
+        except capi.B2Error:
+            bad += 1
+    assert bad > 100 and ok + bad == 300
+
+
+def test_hostile_headers_are_errors_not_crashes(tmp_path):
+    """Headers that ask for absurd allocations (huge COUNT / POINTS / compressed sizes) come back as B2Error."""
+    p = tmp_path / "h.pcd"
+    cases = [
+        b"VERSION 0.7\nFIELDS x y z\nSIZE 4 4 4\nTYPE F F F\nCOUNT 1 1 2000000000\nWIDTH 2\nHEIGHT 1\nPOINTS 2\nDATA binary\n" + b"\0" * 64,
+        b"VERSION 0.7\nFIELDS x y z\nSIZE 4 4 4\nTYPE F F F\nCOUNT 1 1 1\nWIDTH 4000000000\nHEIGHT 1\nPOINTS 4000000000\nDATA binary\n",
+        b"VERSION 0.7\nFIELDS x y z\nSIZE 4 4 4\nTYPE F F F\nCOUNT 1 1 1\nWIDTH 1000000000000\nHEIGHT 1000000\nDATA ascii\n1 2 3\n",
+        b"VERSION 0.7\nFIELDS x y z\nSIZE 4 4 4\nTYPE F F F\nCOUNT 1 1 1\nWIDTH 2\nHEIGHT 1\nPOINTS 2\nDATA binary_compressed\n"
+        + struct.pack("<II", 0xFFFFFFF0, 24) + b"\x00" * 16,
+        b"VERSION 0.7\nFIELDS x y z\nSIZE 4 4 3\nTYPE F F F\nCOUNT 1 1 1\nWIDTH 1\nHEIGHT 1\nPOINTS 1\nDATA binary\n" + b"\0" * 16,
+    ]
+    for blob in cases:
+        p.write_bytes(blob)
+        with pytest.raises(capi.B2Error):
+            capi.pcd_read(str(p))
