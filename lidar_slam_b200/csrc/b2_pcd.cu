@@ -229,9 +229,11 @@ extern "C" int b2cloud_load_pcd(b2cloud *c, const char *path) {
 
 extern "C" int b2cloud_save_pcd(b2cloud *c, const char *path) {
     if (!c) { set_error("b2cloud_save_pcd: NULL cloud handle"); return B2_ERR_INVALID; }
-    std::vector<float> host(c->n * 4 + 4);
+    float *host = (float *)malloc(c->n * 16 + 16);
+    if (!host) { set_error("b2cloud_save_pcd: out of host memory (%zu points)", c->n); return B2_ERR_INVALID; }
     size_t n = 0;
-    int rc = b2cloud_download(c, host.data(), c->n, 16, 12, &n);
-    if (rc) return rc;
-    return b2_pcd_write_binary(path, host.data(), n);
+    int rc = b2cloud_download(c, host, c->n, 16, 12, &n);
+    if (!rc) rc = b2_pcd_write_binary(path, host, n);
+    free(host);
+    return rc;
 }
