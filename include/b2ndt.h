@@ -117,7 +117,9 @@ int  b2ndt_align_batch_device(b2ndt *h, const void *d_src_f4, size_t n_total, co
 /* one derivative pass at a 6-vector pose (parity gate): H is column-major 6x6 */
 int  b2ndt_derivatives(b2ndt *h, const void *src, size_t n, size_t stride, size_t ioff, const double p[6],
                        double *score, double grad[6], double H[36], int64_t *pairs);
-/* getFitnessScore of the last b2ndt_align (source + final pose are retained on the device) */
+/* getFitnessScore of the last b2ndt_align / b2ndt_align_cloud (source + final pose are retained on the device).
+ * Any other call that takes a source (align_batch, derivatives, fitness_ex) or a new target ends that state:
+ * B2_ERR_STATE until the next single align. */
 int  b2ndt_fitness(b2ndt *h, double max_range, double *out);
 /* explicit variant: any source / pose against the current target points */
 int  b2ndt_fitness_ex(b2ndt *h, const void *src, size_t n, size_t stride, size_t ioff, const float pose[16],
