@@ -46,6 +46,18 @@ def best_hypothesis(rows, score_col=0):
     return int(np.argmax(rows[:, score_col]))
 
 
+def pose6_to_matrix(p):
+    """(x, y, z, roll, pitch, yaw) -> 4x4, R = Rx(roll) Ry(pitch) Rz(yaw): the convention of the reference's 6-vector
+    (NormalDistributionsTransform.cpp:370-373: Translation * AngleAxis(X) * AngleAxis(Y) * AngleAxis(Z))."""
+    cx, sx, cy, sy, cz, sz = np.cos(p[3]), np.sin(p[3]), np.cos(p[4]), np.sin(p[4]), np.cos(p[5]), np.sin(p[5])
+    T = np.eye(4)
+    T[:3, :3] = [[cy * cz, -cy * sz, sy],
+                 [cx * sz + sx * sy * cz, cx * cz - sx * sy * sz, -sx * cy],
+                 [sx * sz - cx * sy * cz, sx * cz + cx * sy * sz, cx * cy]]
+    T[:3, 3] = p[:3]
+    return T
+
+
 def scan_match_batch_multi_device(registrations, sources, predict_poses):
     """One process, several devices: `registrations` holds one NDTRegistration per device (each with the
     same target set); the batch is split into contiguous blocks, every block runs on its own host thread / handle /
@@ -87,7 +99,6 @@ def relocalize(registration, yaw_search, scan_filtered, scan_device, position, l
     metres) x angle_size yaw bins in one launch, the `top` best poses become the initial guesses of ONE batched NDT
     launch (`registration.ScanMatchBatch` with a shared source), and the best final NDT score wins.
     -> (best pose 4x4, index into the candidates, candidate poses after NDT (top,4,4), results)"""
-    from . import synth
     half = (lattice - 1) / 2.0
     offs = np.array([[(ix - half) * pitch, (iy - half) * pitch] for iy in range(lattice) for ix in range(lattice)], np.float32)
     probs = yaw_search.PoseSearch(scan_device, offs, angle_size)
@@ -98,7 +109,7 @@ def relocalize(registration, yaw_search, scan_filtered, scan_device, position, l
     for c in cand:
         o, b = divmod(int(c), angle_size)
         pose6 = np.array([position[0] + offs[o, 0], position[1] + offs[o, 1], position[2], 0.0, 0.0, float(np.float32(b) * delta)])
-        guesses.append(synth.pose6_to_matrix(pose6).astype(np.float32))
+        guesses.append(pose6_to_matrix(pose6).astype(np.float32))
     poses, res = registration.ScanMatchBatch(scan_filtered, guesses)
     score = np.where(res["converged"] > 0, res["score"], -np.inf)
     k = int(np.argmax(score))

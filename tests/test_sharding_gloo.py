@@ -49,3 +49,16 @@ def test_gather_rows_gloo_world2():
     assert np.array_equal(table[:, 1], np.arange(n_items))
     assert np.array_equal(table[:, 2], np.array([0] * 19 + [1] * 18))
     assert batch.best_hypothesis(table, 0) == n_items - 1
+
+
+def test_pose6_to_matrix_convention():
+    """batch.pose6_to_matrix (used by relocalize) = the generator's and the oracle's Rx Ry Rz convention."""
+    import numpy as np
+    from lidar_slam_b200 import batch, synth
+    from oracle import oracle as O
+    rng = np.random.default_rng(0)
+    for _ in range(50):
+        p = rng.uniform(-3, 3, 6)
+        T = batch.pose6_to_matrix(p)
+        assert np.allclose(T, synth.pose6_to_matrix(p), atol=1e-15)
+        assert np.allclose(T, O.pose_to_matrix(p), atol=1e-6)        # the oracle builds its matrix in float
