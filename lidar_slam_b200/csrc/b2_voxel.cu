@@ -738,7 +738,7 @@ extern "C" int b2vf_filter(b2vf *h, const void *in, size_t n, size_t stride, siz
     *m = 0;
     if (n == 0) return 0;
     if (!in || !out) { set_error("b2vf_filter: NULL cloud pointer"); return B2_ERR_INVALID; }
-    if (stride < 16 || ioff + 4 > stride || out_stride < 16 || out_ioff + 4 > out_stride) {
+    if (stride < 16 || ioff + 4 > stride || out_stride < 16 || out_ioff + 4 > out_stride || ((stride | ioff | out_stride | out_ioff) & 3)) {
         set_error("b2vf_filter: bad stride / intensity offset"); return B2_ERR_INVALID;
     }
     if (n >= 0xFFFFFFF0ull) { set_error("b2vf_filter: cloud too large"); return B2_ERR_INVALID; }
