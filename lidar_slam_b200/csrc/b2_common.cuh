@@ -151,10 +151,12 @@ __device__ __forceinline__ void transform_f32(const float *T /*col-major 4x4*/, 
 #endif
 
 // ------------------------------------------------------------------ sort plan ----------------
-// A "tile" is a run of at most TILE consecutive elements of ONE cloud (segment) of a concatenated
-// batch; kernels are launched one CTA per tile.
-constexpr int SORT_TILE = 4096;      // 256 threads x 16 keys
+// A "tile" is a run of at most tile_elems consecutive elements of ONE cloud (segment) of a concatenated
+// batch; kernels are launched one CTA per tile.  Two tile sizes: 256 threads x 4 keys for small inputs (enough
+// CTAs to fill 148 SMs from ~1e5 points), 256 x 16 for large ones (less look-back work per key).
 constexpr int SORT_THREADS = 256;
+constexpr int SORT_ITEMS_SMALL = 4, SORT_ITEMS_LARGE = 16;
+constexpr size_t SORT_LARGE_FROM = 2u << 20;      // points in the batch from which the large tile is used
 constexpr int RADIX_BITS = 8;
 constexpr int RADIX = 1 << RADIX_BITS;
 

@@ -56,8 +56,7 @@ __device__ __forceinline__ int hmap_cell(float c, float mn, double res) {
 }
 
 __global__ void __launch_bounds__(256) hmap_key_kernel(const float4 *__restrict__ pts, uint32_t n, float ox, float oy, HmapGrid G,
-                                                       uint32_t *__restrict__ keys, uint32_t *__restrict__ vals,
-                                                       uint32_t *__restrict__ n_valid) {
+                                                       uint32_t *__restrict__ keys, uint32_t *__restrict__ n_valid) {
     uint32_t cnt = 0;
     const uint32_t invalid = (uint32_t)G.width * (uint32_t)G.height;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -68,20 +67,20 @@ __global__ void __launch_bounds__(256) hmap_key_kernel(const float4 *__restrict_
             const int cy = hmap_cell(__fsub_rn(p.y, oy), G.min_y, G.res);
             if (!(cx < 0 || cy < 0 || cx >= G.width || cy >= G.height)) { key = (uint32_t)cx * (uint32_t)G.height + (uint32_t)cy; ++cnt; }
         }
-        keys[i] = key;
-        vals[i] = i;
+        keys[i] = key;          // the payload of the sort is the element index itself (first radix pass)
     }
     cnt = __reduce_add_sync(0xffffffffu, cnt);
     if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(n_valid, cnt);
 }
 
 // one thread per occupied cell: the reference's recurrence over the cell's points in input order (matching.cpp:374-392)
-__global__ void __launch_bounds__(128) hmap_cell_kernel(const float4 *__restrict__ pts, const uint32_t *__restrict__ keys,
-                                                        const uint32_t *__restrict__ vals, const uint32_t *__restrict__ run_start,
-                                                        const uint32_t *__restrict__ scalars, const uint32_t *__restrict__ n_valid,
+__global__ void __launch_bounds__(128) hmap_cell_kernel(const float4 *__restrict__ pts, SortView sv, const uint32_t *__restrict__ run_start,
+                                                        const uint32_t *__restrict__ n_valid,
                                                         float oz, float *__restrict__ mu_out, float *__restrict__ sigma_out,
                                                         int32_t *__restrict__ cnt_out) {
-    const uint32_t runs = scalars[1];
+    const uint32_t runs = sv.scalars[1];
+    const uint32_t *__restrict__ keys = sv.keys();
+    const uint32_t *__restrict__ vals = sv.vals();
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= runs) return;
     const uint32_t s = run_start[j];
@@ -237,13 +236,12 @@ extern "C" int b2hmap_build(b2hmap *h, b2cloud *local_map, const float origin[3]
     unsigned blocks = (unsigned)((n + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
     uint32_t *n_valid = h->misc.as<uint32_t>() + 6;
-    hmap_key_kernel<<<blocks, 256, 0, h->st>>>(local_map->d(), (uint32_t)n, origin[0], origin[1], G, h->pipe.keys0(), h->pipe.vals0(), n_valid);
+    hmap_key_kernel<<<blocks, 256, 0, h->st>>>(local_map->d(), (uint32_t)n, origin[0], origin[1], G, h->pipe.keys0(), n_valid);
     B2_LAUNCH_CHECK();
     int nbits = 1;
     while (nbits < 32 && (1ull << nbits) <= cells) ++nbits;          // keys lie in [0, cells]
     if ((rc = h->pipe.run_prepared((uint32_t)cells, nbits, h->st))) return rc;
-    hmap_cell_kernel<<<(unsigned)((n + 127) / 128), 128, 0, h->st>>>(local_map->d(), h->pipe.sorted_keys(), h->pipe.sorted_vals(),
-                                                                     h->pipe.run_start(), h->pipe.scalars(), n_valid, origin[2],
+    hmap_cell_kernel<<<(unsigned)((n + 127) / 128), 128, 0, h->st>>>(local_map->d(), h->pipe.view(), h->pipe.run_start(), n_valid, origin[2],
                                                                      h->mu.as<float>(), h->sigma.as<float>(), h->cnt.as<int32_t>());
     B2_LAUNCH_CHECK();
     B2_CUDA(cudaStreamSynchronize(h->st));

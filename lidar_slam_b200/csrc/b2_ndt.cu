@@ -48,47 +48,147 @@ struct TargetDev {
 };
 
 // ------------------------------------------------------------------ target build kernels -----
-// One warp per occupied voxel: lanes gather 32 member points (stable = input order), then every lane
-// folds them in sequentially via shuffles, reproducing PCL's per-leaf accumulation order exactly:
-// mean_ += p (double), cov_ += p p^T (double, from Identity), centroid += (x,y,z,i) (float).
-__global__ void __launch_bounds__(256) leaf_stats_kernel(const float4 *__restrict__ pts, const uint32_t *__restrict__ keys,
-                                                         const uint32_t *__restrict__ vals,
+// Per occupied voxel, PCL's per-leaf accumulation in PCL's order and precision: mean_ += p (double),
+// cov_ += p p^T (double, from Identity), centroid += (x,y,z,i) (float), members in input order (the stable sort
+// keeps it).  Two kernels, like the VoxelFilter centroids (b2_voxel.cu):
+//   leaf_stats_kernel   a warp takes 32 consecutive voxels; a voxel of up to LS_SEQ points is accumulated by ONE
+//                       lane; crowded voxels go to a work list;
+//   leaf_crowded_kernel one warp per crowded voxel: lanes gather 64 members at a time one group ahead of the fold,
+//                       every lane folds them sequentially through shuffles.
+constexpr uint32_t LS_SEQ = 32;
+
+struct LeafOut {
+    float4 *pts_sorted;
+    int32_t *leaf_idx, *leaf_n;
+    uint32_t *leaf_start;
+    float4 *centroid4;
+    double *sums;
+};
+
+__device__ __forceinline__ void leaf_emit(const LeafOut &O, uint32_t j, uint32_t s, uint32_t n, uint32_t key, float cx, float cy,
+                                          float cz, float ci, double sx, double sy, double sz, double cxx, double cxy, double cxz,
+                                          double cyy, double cyz, double czz) {
+    const float fn = (float)n;
+    O.leaf_idx[j] = (int32_t)key;
+    O.leaf_n[j] = (int32_t)n;
+    O.leaf_start[j] = s;
+    O.centroid4[j] = make_float4(__fdiv_rn(cx, fn), __fdiv_rn(cy, fn), __fdiv_rn(cz, fn), __fdiv_rn(ci, fn));
+    double *o = O.sums + (size_t)j * 9;
+    o[0] = sx; o[1] = sy; o[2] = sz; o[3] = cxx; o[4] = cxy; o[5] = cxz; o[6] = cyy; o[7] = cyz; o[8] = czz;
+}
+
+#define B2_LEAF_ACC(x, y, z, w)                                                                        \
+    do {                                                                                               \
+        cx = __fadd_rn(cx, x); cy = __fadd_rn(cy, y); cz = __fadd_rn(cz, z); ci = __fadd_rn(ci, w);    \
+        const double dx = (double)(x), dy = (double)(y), dz = (double)(z);                             \
+        sx = __dadd_rn(sx, dx); sy = __dadd_rn(sy, dy); sz = __dadd_rn(sz, dz);                        \
+        cxx = __dadd_rn(cxx, __dmul_rn(dx, dx)); cxy = __dadd_rn(cxy, __dmul_rn(dx, dy));              \
+        cxz = __dadd_rn(cxz, __dmul_rn(dx, dz)); cyy = __dadd_rn(cyy, __dmul_rn(dy, dy));              \
+        cyz = __dadd_rn(cyz, __dmul_rn(dy, dz)); czz = __dadd_rn(czz, __dmul_rn(dz, dz));              \
+    } while (0)
+
+__global__ void __launch_bounds__(256) leaf_stats_kernel(const float4 *__restrict__ pts, SortView sv,
                                                          const uint32_t *__restrict__ run_start, uint32_t V, uint32_t n_finite,
-                                                         float4 *__restrict__ pts_sorted, int32_t *__restrict__ leaf_idx,
-                                                         int32_t *__restrict__ leaf_n, uint32_t *__restrict__ leaf_start,
-                                                         float4 *__restrict__ centroid4, double *__restrict__ sums) {
+                                                         LeafOut O, uint32_t *__restrict__ crowded, uint32_t *__restrict__ n_crowded) {
+    const uint32_t *__restrict__ keys = sv.keys();
+    const uint32_t *__restrict__ vals = sv.vals();
     const int l = threadIdx.x & 31;
-    for (uint32_t j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < V; j += (gridDim.x * blockDim.x) >> 5) {
+    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t j0 = ((threadIdx.x >> 5) * gridDim.x + blockIdx.x) * 32u; j0 < V; j0 += nwarps * 32u) {
+        const uint32_t j = j0 + l;
+        const bool valid = j < V;
+        uint32_t s = 0, e = 0;
+        if (valid) { s = run_start[j]; e = (j + 1 < V) ? run_start[j + 1] : n_finite; }
+        const uint32_t len = e - s;
+        const bool is_crowded = len > LS_SEQ;
+        {
+            const uint32_t m = __ballot_sync(0xffffffffu, is_crowded);
+            if (m) {
+                uint32_t base = 0;
+                if (l == 0) base = atomicAdd(n_crowded, (uint32_t)__popc(m));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (is_crowded) crowded[base + __popc(m & ((1u << l) - 1u))] = j;
+            }
+        }
+        if (valid && !is_crowded) {
+            float cx = 0.f, cy = 0.f, cz = 0.f, ci = 0.f;
+            double sx = 0, sy = 0, sz = 0, cxx = 1, cxy = 0, cxz = 0, cyy = 1, cyz = 0, czz = 1;
+            uint32_t k = s;
+            for (; k + 4 <= e; k += 4) {
+                const uint32_t v0 = vals[k], v1 = vals[k + 1], v2 = vals[k + 2], v3 = vals[k + 3];
+                const float4 p0 = __ldg(&pts[v0]), p1 = __ldg(&pts[v1]), p2 = __ldg(&pts[v2]), p3 = __ldg(&pts[v3]);
+                O.pts_sorted[k] = p0; O.pts_sorted[k + 1] = p1; O.pts_sorted[k + 2] = p2; O.pts_sorted[k + 3] = p3;
+                B2_LEAF_ACC(p0.x, p0.y, p0.z, p0.w);
+                B2_LEAF_ACC(p1.x, p1.y, p1.z, p1.w);
+                B2_LEAF_ACC(p2.x, p2.y, p2.z, p2.w);
+                B2_LEAF_ACC(p3.x, p3.y, p3.z, p3.w);
+            }
+            for (; k < e; ++k) {
+                const float4 p = __ldg(&pts[vals[k]]);
+                O.pts_sorted[k] = p;
+                B2_LEAF_ACC(p.x, p.y, p.z, p.w);
+            }
+            leaf_emit(O, j, s, len, keys[s], cx, cy, cz, ci, sx, sy, sz, cxx, cxy, cxz, cyy, cyz, czz);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) leaf_crowded_kernel(const float4 *__restrict__ pts, SortView sv,
+                                                           const uint32_t *__restrict__ run_start, uint32_t V, uint32_t n_finite,
+                                                           LeafOut O, const uint32_t *__restrict__ crowded,
+                                                           const uint32_t *__restrict__ n_crowded) {
+    const uint32_t n = *n_crowded;
+    const uint32_t *__restrict__ keys = sv.keys();
+    const uint32_t *__restrict__ vals = sv.vals();
+    const int l = threadIdx.x & 31;
+    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t i = (threadIdx.x >> 5) * gridDim.x + blockIdx.x; i < n; i += nwarps) {
+        const uint32_t j = crowded[i];
         const uint32_t s = run_start[j];
         const uint32_t e = (j + 1 < V) ? run_start[j + 1] : n_finite;
         float cx = 0.f, cy = 0.f, cz = 0.f, ci = 0.f;
         double sx = 0, sy = 0, sz = 0, cxx = 1, cxy = 0, cxz = 0, cyy = 1, cyz = 0, czz = 1;
-        for (uint32_t c = s; c < e; c += 32) {
-            float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (c + l < e) { p = __ldg(&pts[vals[c + l]]); pts_sorted[c + l] = p; }
-            const int m = (e - c < 32u) ? (int)(e - c) : 32;
-#pragma unroll 4
-            for (int k = 0; k < m; ++k) {
-                float x = __shfl_sync(0xffffffffu, p.x, k), y = __shfl_sync(0xffffffffu, p.y, k);
-                float z = __shfl_sync(0xffffffffu, p.z, k), w = __shfl_sync(0xffffffffu, p.w, k);
-                cx = __fadd_rn(cx, x); cy = __fadd_rn(cy, y); cz = __fadd_rn(cz, z); ci = __fadd_rn(ci, w);
-                double dx = (double)x, dy = (double)y, dz = (double)z;
-                sx = __dadd_rn(sx, dx); sy = __dadd_rn(sy, dy); sz = __dadd_rn(sz, dz);
-                cxx = __dadd_rn(cxx, __dmul_rn(dx, dx)); cxy = __dadd_rn(cxy, __dmul_rn(dx, dy));
-                cxz = __dadd_rn(cxz, __dmul_rn(dx, dz)); cyy = __dadd_rn(cyy, __dmul_rn(dy, dy));
-                cyz = __dadd_rn(cyz, __dmul_rn(dy, dz)); czz = __dadd_rn(czz, __dmul_rn(dz, dz));
+        uint32_t va[2], vb[2];
+        float4 pa[2], pb[2];
+        auto ldv = [&](uint32_t c, uint32_t (&v)[2]) {
+#pragma unroll
+            for (int d = 0; d < 2; ++d) { const uint32_t idx = c + d * 32 + l; v[d] = (idx < e) ? __ldg(&vals[idx]) : 0xFFFFFFFFu; }
+        };
+        auto ldp = [&](const uint32_t (&v)[2], float4 (&p)[2], uint32_t c) {
+#pragma unroll
+            for (int d = 0; d < 2; ++d) {
+                p[d] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (v[d] != 0xFFFFFFFFu) { p[d] = __ldg(&pts[v[d]]); O.pts_sorted[c + d * 32 + l] = p[d]; }
             }
+        };
+        auto fold = [&](const float4 (&p)[2], uint32_t c) {
+#pragma unroll
+            for (int d = 0; d < 2; ++d) {
+                const uint32_t c0 = c + d * 32;
+                if (c0 >= e) break;
+                const int m = (e - c0 < 32u) ? (int)(e - c0) : 32;
+#pragma unroll 4
+                for (int k = 0; k < m; ++k) {
+                    const float x = __shfl_sync(0xffffffffu, p[d].x, k), y = __shfl_sync(0xffffffffu, p[d].y, k);
+                    const float z = __shfl_sync(0xffffffffu, p[d].z, k), w = __shfl_sync(0xffffffffu, p[d].w, k);
+                    B2_LEAF_ACC(x, y, z, w);
+                }
+            }
+        };
+        // group g is folded while the points of g+1 and the indices of g+2 are in flight
+        ldv(s, va);
+        ldv(s + 64u, vb);
+        ldp(va, pa, s);
+        for (uint32_t c = s; c < e; c += 128u) {
+            ldp(vb, pb, c + 64u);
+            ldv(c + 128u, va);
+            fold(pa, c);
+            if (c + 64u >= e) break;
+            ldp(va, pa, c + 128u);
+            ldv(c + 192u, vb);
+            fold(pb, c + 64u);
         }
-        if (l == 0) {
-            const uint32_t n = e - s;
-            const float fn = (float)n;
-            leaf_idx[j] = (int32_t)keys[s];
-            leaf_n[j] = (int32_t)n;
-            leaf_start[j] = s;
-            centroid4[j] = make_float4(__fdiv_rn(cx, fn), __fdiv_rn(cy, fn), __fdiv_rn(cz, fn), __fdiv_rn(ci, fn));
-            double *o = sums + (size_t)j * 9;
-            o[0] = sx; o[1] = sy; o[2] = sz; o[3] = cxx; o[4] = cxy; o[5] = cxz; o[6] = cyy; o[7] = cyz; o[8] = czz;
-        }
+        if (l == 0) leaf_emit(O, j, s, e - s, keys[s], cx, cy, cz, ci, sx, sy, sz, cxx, cxy, cxz, cyy, cyz, czz);
     }
 }
 
@@ -176,13 +276,16 @@ __global__ void __launch_bounds__(128) leaf_finish_kernel(uint32_t V, int min_pt
 }
 
 // ------------------------------------------------------------------ neighbour lists ----------
-// nbr_head[c].y holds the number of searchable leaves in the 3x3x3 window of cell c (counted by
-// leaf_finish_kernel).  Three steps lay the lists out in cell order: per-tile sums, a scan of the tile
-// sums, and a fill pass that scans inside each tile, writes the list offsets and gathers the entries
-// in fixed (z, y, x) window order -- the layout and the order are deterministic.
+// nbr_head[c].y holds the number of searchable leaves in the 3x3x3 window of cell c that can be reached from it
+// (counted by leaf_finish_kernel).  Two kernels lay the lists out in cell order:
+//   nbr_scan_kernel  one pass over the dense grid: exclusive scan of the counts (decoupled look-back over 2048-cell
+//                    tiles) -> nbr_head[c].x, and the cells with a non-empty list appended to a work list;
+//   nbr_fill_kernel  one thread per listed cell gathers its entries in fixed (z, y, x) window order.
+// The layout and the entry order are deterministic (the order of the work list is not, and does not matter).
 constexpr int NBR_TPB = 256;
 constexpr int NBR_ROUNDS = 8;
 constexpr uint32_t NBR_TILE = NBR_TPB * NBR_ROUNDS;
+constexpr uint32_t NB_PART = 1u << 30, NB_INCL = 2u << 30, NB_MASK = 0x3FFFFFFFu;
 
 __device__ __forceinline__ uint32_t block_excl_scan_256(uint32_t v, uint32_t *warp_tot /*smem[9]*/, uint32_t &block_total) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -206,71 +309,113 @@ __device__ __forceinline__ uint32_t block_excl_scan_256(uint32_t v, uint32_t *wa
     return r;
 }
 
-__global__ void __launch_bounds__(NBR_TPB) nbr_tile_sum_kernel(const uint2 *__restrict__ head, uint32_t ncells,
-                                                               uint32_t *__restrict__ tile_sum) {
-    __shared__ uint32_t wsum[8];
-    uint32_t s = 0;
-#pragma unroll
-    for (int r = 0; r < NBR_ROUNDS; ++r) {
-        const size_t c = (size_t)blockIdx.x * NBR_TILE + (size_t)r * NBR_TPB + threadIdx.x;
-        if (c < ncells) s += __ldg(&head[c]).y;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = s;
+// counters: [0] searchable leaves, [1] max centroid displacement (float bits), [2] tile ticket, [3] listed cells,
+// [4] list entries in total; state: one look-back word per tile (zeroed with the counters)
+__global__ void __launch_bounds__(NBR_TPB) nbr_scan_kernel(uint2 *__restrict__ head, uint32_t ncells, uint32_t ntiles,
+                                                           uint32_t *__restrict__ counters, uint32_t *__restrict__ state,
+                                                           uint32_t *__restrict__ active) {
+    __shared__ uint32_t wt[9];
+    __shared__ uint32_t s_tile, s_excl;
+    if (threadIdx.x == 0) s_tile = atomicAdd(&counters[2], 1u);
     __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t t = 0;
-        for (int w = 0; w < 8; ++w) t += wsum[w];
-        tile_sum[blockIdx.x] = t;
-    }
-}
-
-// single CTA: exclusive scan of the tile sums in place
-__global__ void __launch_bounds__(NBR_TPB) nbr_tile_scan_kernel(uint32_t *__restrict__ tile_sum, uint32_t ntiles) {
-    __shared__ uint32_t wt[9];
-    uint32_t base = 0;
-    for (uint32_t t0 = 0; t0 < ntiles; t0 += NBR_TPB) {
-        const uint32_t t = t0 + threadIdx.x;
-        const uint32_t v = (t < ntiles) ? tile_sum[t] : 0u;
-        uint32_t tot;
-        const uint32_t ex = block_excl_scan_256(v, wt, tot);
-        if (t < ntiles) tile_sum[t] = base + ex;
-        base += tot;
-    }
-}
-
-__global__ void __launch_bounds__(NBR_TPB) nbr_fill_kernel(uint2 *__restrict__ head, const float4 *__restrict__ cells,
-                                                           uint32_t ncells, const uint32_t *__restrict__ tile_base, LayoutArg LA,
-                                                           float4 *__restrict__ list) {
-    __shared__ uint32_t wt[9];
-    uint32_t base = tile_base[blockIdx.x];
-    const int dx_n = LA.div_b[0], dy_n = LA.div_b[1], dz_n = LA.div_b[2];
+    const uint32_t tile = s_tile;
+    // blocked arrangement: thread t owns NBR_ROUNDS consecutive cells (two 32-byte loads)
+    const size_t c0 = (size_t)tile * NBR_TILE + (size_t)threadIdx.x * NBR_ROUNDS;
+    uint32_t cnt[NBR_ROUNDS];
+    uint32_t mine = 0;
+#pragma unroll
     for (int r = 0; r < NBR_ROUNDS; ++r) {
-        const size_t c = (size_t)blockIdx.x * NBR_TILE + (size_t)r * NBR_TPB + threadIdx.x;
-        const uint32_t cnt = (c < ncells) ? head[c].y : 0u;
-        uint32_t tot;
-        const uint32_t off = base + block_excl_scan_256(cnt, wt, tot);
-        base += tot;
-        if (cnt) {
-            head[c].x = off;
-            const int iz = (int)(c / ((size_t)dx_n * dy_n));
-            const int rem = (int)(c - (size_t)iz * dx_n * dy_n);
-            const int iy = rem / dx_n, ix = rem - iy * dx_n;
-            uint32_t k = 0;
-            for (int dz = -1; dz <= 1; ++dz)
-                for (int dy = -1; dy <= 1; ++dy)
-                    for (int dx = -1; dx <= 1; ++dx) {
-                        const int kx = ix + dx, ky = iy + dy, kz = iz + dz;
-                        if (kx < 0 || ky < 0 || kz < 0 || kx >= dx_n || ky >= dy_n || kz >= dz_n) continue;
-                        const float4 e = __ldg(&cells[(size_t)kx + (size_t)ky * dx_n + (size_t)kz * dx_n * dy_n]);
-                        const int code = __float_as_int(e.w);
-                        if (code > 0 && nbr_keep(e.x, e.y, e.z, ix, iy, iz, LA)) {
-                            list[off + k] = make_float4(e.x, e.y, e.z, __int_as_float(code - 1));
-                            ++k;
-                        }
-                    }
+        cnt[r] = (c0 + r < ncells) ? __ldcs(&head[c0 + r]).y : 0u;
+        mine += cnt[r];
+    }
+    uint32_t total;
+    const uint32_t lex = block_excl_scan_256(mine, wt, total);
+    if (threadIdx.x < 32) {
+        const int l = threadIdx.x;
+        uint32_t excl = 0;
+        volatile uint32_t *st = state;
+        if (tile == 0) {
+            if (l == 0) st[0] = total | NB_INCL;
+        } else {
+            if (l == 0) st[tile] = total | NB_PART;
+            int base = (int)tile;
+            while (true) {
+                const int j = base - 1 - l;
+                uint32_t v = NB_INCL;
+                if (j >= 0) { do { v = st[j]; } while ((v & ~NB_MASK) == 0u); }
+                const uint32_t incl_mask = __ballot_sync(0xffffffffu, (v & NB_INCL) != 0u);
+                const int stop = __ffs(incl_mask) - 1;
+                uint32_t c = (stop < 0 || l <= stop) ? (v & NB_MASK) : 0u;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+                excl += c;
+                if (stop >= 0) break;
+                base -= 32;
+            }
+            if (l == 0) st[tile] = (excl + total) | NB_INCL;
         }
+        if (l == 0) {
+            s_excl = excl;
+            if (tile == ntiles - 1u) counters[4] = excl + total;
+        }
+    }
+    __syncthreads();
+    uint32_t off = s_excl + lex;
+    uint32_t n_act = 0;
+#pragma unroll
+    for (int r = 0; r < NBR_ROUNDS; ++r) n_act += cnt[r] ? 1u : 0u;
+    // work-list slots: one atomic per warp
+    uint32_t inc = n_act;
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+    uint32_t wbase = 0;
+    if (lane == 31 && inc) wbase = atomicAdd(&counters[3], inc);
+    wbase = __shfl_sync(0xffffffffu, wbase, 31);
+    uint32_t slot = wbase + inc - n_act;
+#pragma unroll
+    for (int r = 0; r < NBR_ROUNDS; ++r) {
+        if (cnt[r]) {
+            head[c0 + r].x = off;
+            active[slot++] = (uint32_t)(c0 + r);
+            off += cnt[r];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(NBR_TPB) nbr_fill_kernel(const uint2 *__restrict__ head, const float4 *__restrict__ cells,
+                                                           const uint32_t *__restrict__ counters,
+                                                           const uint32_t *__restrict__ active, LayoutArg LA,
+                                                           float4 *__restrict__ list) {
+    const uint32_t n = counters[3];
+    const int dx_n = LA.div_b[0], dy_n = LA.div_b[1], dz_n = LA.div_b[2];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t c = active[i];
+        const uint32_t off = head[c].x;
+        const int iz = (int)(c / ((uint32_t)dx_n * dy_n));
+        const int rem = (int)(c - (uint32_t)iz * dx_n * dy_n);
+        const int iy = rem / dx_n, ix = rem - iy * dx_n;
+        uint32_t k = 0;
+        for (int dz = -1; dz <= 1; ++dz)
+            for (int dy = -1; dy <= 1; ++dy) {
+                const int ky = iy + dy, kz = iz + dz;
+                if (ky < 0 || kz < 0 || ky >= dy_n || kz >= dz_n) continue;
+                const float4 *row = cells + (size_t)ky * dx_n + (size_t)kz * dx_n * dy_n;
+                float4 e3[3];
+#pragma unroll
+                for (int dx = -1; dx <= 1; ++dx) {
+                    const int kx = ix + dx;
+                    e3[dx + 1] = (kx >= 0 && kx < dx_n) ? __ldg(&row[kx]) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int dx = 0; dx < 3; ++dx) {
+                    const int code = __float_as_int(e3[dx].w);
+                    if (code > 0 && nbr_keep(e3[dx].x, e3[dx].y, e3[dx].z, ix, iy, iz, LA)) {
+                        list[off + k] = make_float4(e3[dx].x, e3[dx].y, e3[dx].z, __int_as_float(code - 1));
+                        ++k;
+                    }
+                }
+            }
     }
 }
 
@@ -346,8 +491,9 @@ struct MatchArgs {
     b2ndt_result *results;       // B
     double *acc_out;             // B*ACC_N (deriv-only mode)
     int deriv_only;
-    const uint32_t *ready;       // batch kernel, host-streamed sources: number of leading matches whose points have
-                                 // arrived in HBM (written by the copy stream between chunk copies); NULL = all resident
+    const uint32_t *ready;       // batch kernel, host-streamed sources: ready[0] = number of leading matches whose points
+                                 // have arrived in HBM (written by the copy stream between chunk copies), ready[1] = set
+                                 // by the kernel when that wait timed out; NULL = all resident
     unsigned long long *timing;  // NDT_TIMING builds only (tools/ sweeps): per-phase SM-cycle totals of the batch kernel
 };
 
@@ -1096,12 +1242,27 @@ __global__ void __launch_bounds__(NDT_THREADS, NDT_MIN_CTAS) ndt_batch_kernel(Gr
         m = __shfl_sync(0xffffffffu, m, 0);
         if (m >= B) return 0;
         if (A.ready) {
-            // host-streamed batch: wait until the copy stream has delivered this match's points
+            // host-streamed batch: wait until the copy stream has delivered this match's points.  Every copy this
+            // waits for was ENQUEUED BEFORE the kernel was launched (align_host), so the wait does not depend on
+            // host progress; it is bounded all the same (a lost copy must not hang the GPU): after ~4 s the CTA
+            // raises A.ready[1] and retires, and the host reports the call as failed.
+            int ok = 1;
             if (lane == 0) {
-                while (*reinterpret_cast<const volatile uint32_t *>(A.ready) <= m) __nanosleep(2000);
+                unsigned long long t0 = 0;
+                uint32_t spins = 0;
+                while (*reinterpret_cast<const volatile uint32_t *>(A.ready) <= m) {
+                    __nanosleep(2000);
+                    if ((++spins & 1023u) == 0u) {
+                        unsigned long long now;
+                        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                        if (t0 == 0) t0 = now;
+                        else if (now - t0 > 4000000000ull) { atomicExch(const_cast<uint32_t *>(A.ready) + 1, 1u); ok = 0; break; }
+                    }
+                }
                 __threadfence();
             }
-            __syncwarp();
+            ok = __shfl_sync(0xffffffffu, ok, 0);
+            if (!ok) return 0;
         }
         if (lane == 0) {
             uint32_t first = 0, last = A.n_shared;
@@ -1461,6 +1622,7 @@ static int build_target(b2ndt *h, const float4 *d_pts, size_t n, int nbits_hint)
     if ((rc = h->pipe.run(d_pts, res, res, res, nbits_hint, h->st))) return rc;
     if ((rc = h->h_small.reserve(4096))) return rc;
     uint32_t *misc = h->h_small.as<uint32_t>();
+    // the one host round trip of the build: the array sizes (occupied voxels, dense-grid cells) are data dependent
     B2_CUDA(cudaMemcpyAsync(misc, h->pipe.scalars(), 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->st));
     B2_CUDA(cudaMemcpyAsync(misc + 8, h->pipe.layouts(), sizeof(VoxLayout), cudaMemcpyDeviceToHost, h->st));
     B2_CUDA(cudaStreamSynchronize(h->st));
@@ -1468,6 +1630,7 @@ static int build_target(b2ndt *h, const float4 *d_pts, size_t n, int nbits_hint)
     if (!t.L.ok) { t.valid = true; return 0; }     // empty cloud or PCL's int32 guard: no cells (PCL warns and clears)
     t.V = misc[1];
     const uint32_t V = t.V;
+    const uint32_t ntiles = (uint32_t)(((size_t)t.L.ncells + NBR_TILE - 1) / NBR_TILE);
     if ((rc = t.pts_sorted.reserve((n + 1) * sizeof(float4)))) return rc;
     if ((rc = t.leaf_idx.reserve((V + 1) * 4))) return rc;
     if ((rc = t.leaf_n.reserve((V + 1) * 4))) return rc;
@@ -1477,45 +1640,47 @@ static int build_target(b2ndt *h, const float4 *d_pts, size_t n, int nbits_hint)
     if ((rc = t.sums.reserve((size_t)(V + 1) * 72))) return rc;
     if ((rc = t.icov9.reserve((size_t)(V + 1) * 72))) return rc;
     if ((rc = t.cells.reserve((size_t)t.L.ncells * 16 + 16))) return rc;
-    if ((rc = t.counters.reserve(64))) return rc;
+    if ((rc = t.counters.reserve(((size_t)ntiles + 16) * 4))) return rc;               // counters[16] + one look-back word per tile
     if ((rc = t.nbr_head.reserve((size_t)t.L.ncells * 8 + 16))) return rc;
+    if ((rc = t.nbr_tiles.reserve(((size_t)t.L.ncells + (size_t)n / LS_SEQ + 64) * 4))) return rc;  // work lists: cells with a list | crowded voxels
+    // every searchable leaf enters at most 27 lists: no second round trip to size the lists
+    if ((rc = t.nbr_list.reserve(((size_t)(n / (size_t)(h->prm.min_pts > 0 ? h->prm.min_pts : 1) + 1) * 27 + 1) * sizeof(float4)))) return rc;
     B2_CUDA(cudaMemsetAsync(t.nbr_head.p, 0, (size_t)t.L.ncells * 8, h->st));
     B2_CUDA(cudaMemsetAsync(t.cells.p, 0, (size_t)t.L.ncells * 16, h->st));
-    B2_CUDA(cudaMemsetAsync(t.counters.p, 0, 64, h->st));
+    B2_CUDA(cudaMemsetAsync(t.counters.p, 0, ((size_t)ntiles + 16) * 4, h->st));
     LayoutArg LA;
     for (int a = 0; a < 3; ++a) { LA.min_b[a] = t.L.min_b[a]; LA.div_b[a] = t.L.div_b[a]; LA.inv[a] = t.L.inv[a]; }
     LA.res = h->prm.res;
+    uint32_t *cnt = t.counters.as<uint32_t>();
+    uint32_t *active = t.nbr_tiles.as<uint32_t>();
+    uint32_t *crowded = active + t.L.ncells;
     if (V) {
-        unsigned blocks = (V + 7) / 8;
-        if (blocks > 148 * 32) blocks = 148 * 32;
-        leaf_stats_kernel<<<blocks, 256, 0, h->st>>>(d_pts, h->pipe.sorted_keys(), h->pipe.sorted_vals(), h->pipe.run_start(), V,
-                                                    t.L.n_finite, t.pts_sorted.as<float4>(), t.leaf_idx.as<int32_t>(),
-                                                    t.leaf_n.as<int32_t>(), t.leaf_start.as<uint32_t>(), t.centroid4.as<float4>(),
-                                                    t.sums.as<double>());
+        LeafOut O;
+        O.pts_sorted = t.pts_sorted.as<float4>(); O.leaf_idx = t.leaf_idx.as<int32_t>(); O.leaf_n = t.leaf_n.as<int32_t>();
+        O.leaf_start = t.leaf_start.as<uint32_t>(); O.centroid4 = t.centroid4.as<float4>(); O.sums = t.sums.as<double>();
+        unsigned blocks = ((V / 256 + 147) / 148) * 148u;
+        if (blocks < 148) blocks = 148;
+        if (blocks > 148 * 16) blocks = 148 * 16;
+        leaf_stats_kernel<<<blocks, 256, 0, h->st>>>(d_pts, h->pipe.view(), h->pipe.run_start(), V, t.L.n_finite, O, crowded, cnt + 5);
+        B2_LAUNCH_CHECK();
+        leaf_crowded_kernel<<<148 * 4, 256, 0, h->st>>>(d_pts, h->pipe.view(), h->pipe.run_start(), V, t.L.n_finite, O, crowded, cnt + 5);
         B2_LAUNCH_CHECK();
         leaf_finish_kernel<<<(V + 127) / 128, 128, 0, h->st>>>(V, h->prm.min_pts, h->prm.eig_mult, LA, t.leaf_idx.as<int32_t>(),
                                                               t.leaf_n.as<int32_t>(), t.centroid4.as<float4>(), t.sums.as<double>(),
                                                               t.gauss.as<double>(), t.icov9.as<double>(), t.cells.as<float4>(),
-                                                              t.nbr_head.as<uint2>(), t.counters.as<uint32_t>());
+                                                              t.nbr_head.as<uint2>(), cnt);
+        B2_LAUNCH_CHECK();
+        // neighbour lists, laid out in cell order
+        nbr_scan_kernel<<<ntiles, NBR_TPB, 0, h->st>>>(t.nbr_head.as<uint2>(), t.L.ncells, ntiles, cnt, cnt + 16, active);
+        B2_LAUNCH_CHECK();
+        nbr_fill_kernel<<<148 * 8, NBR_TPB, 0, h->st>>>(t.nbr_head.as<uint2>(), t.cells.as<float4>(), cnt, active, LA, t.nbr_list.as<float4>());
         B2_LAUNCH_CHECK();
     }
-    B2_CUDA(cudaMemcpyAsync(misc, t.counters.p, 8, cudaMemcpyDeviceToHost, h->st));
+    B2_CUDA(cudaMemcpyAsync(misc, t.counters.p, 32, cudaMemcpyDeviceToHost, h->st));
     B2_CUDA(cudaStreamSynchronize(h->st));
     t.n_tree = misc[0];
     memcpy(&t.max_disp, &misc[1], 4);
-    // neighbour lists (27 entries per searchable leaf at most), laid out in cell order
-    if ((rc = t.nbr_list.reserve(((size_t)t.n_tree * 27 + 1) * sizeof(float4)))) return rc;
-    if (t.n_tree) {
-        const uint32_t ntiles = (uint32_t)(((size_t)t.L.ncells + NBR_TILE - 1) / NBR_TILE);
-        if ((rc = t.nbr_tiles.reserve((size_t)ntiles * 4 + 16))) return rc;
-        nbr_tile_sum_kernel<<<ntiles, NBR_TPB, 0, h->st>>>(t.nbr_head.as<uint2>(), t.L.ncells, t.nbr_tiles.as<uint32_t>());
-        B2_LAUNCH_CHECK();
-        nbr_tile_scan_kernel<<<1, NBR_TPB, 0, h->st>>>(t.nbr_tiles.as<uint32_t>(), ntiles);
-        B2_LAUNCH_CHECK();
-        nbr_fill_kernel<<<ntiles, NBR_TPB, 0, h->st>>>(t.nbr_head.as<uint2>(), t.cells.as<float4>(), t.L.ncells,
-                                                       t.nbr_tiles.as<uint32_t>(), LA, t.nbr_list.as<float4>());
-        B2_LAUNCH_CHECK();
-    }
+    if (misc[4] >= NB_MASK) { set_error("SetInputTarget: %u neighbour-list entries exceed the 2^30 limit", misc[4]); return B2_ERR_INVALID; }
     t.valid = true;     // only a completely built target is usable: a failed allocation above leaves "no target set"
     return 0;
 }
@@ -1532,7 +1697,7 @@ static int single_match_cluster(const b2ndt *h, size_t n) {
 static int check_cloud_args(const char *fn, const void *pts, size_t n, size_t stride, size_t ioff) {
     if (n && !pts) { set_error("%s: NULL cloud", fn); return B2_ERR_INVALID; }
     if (stride < 16 || (stride & 3) || ioff + 4 > stride || (ioff & 3)) { set_error("%s: bad stride %zu / intensity offset %zu", fn, stride, ioff); return B2_ERR_INVALID; }
-    if (n >= 0xFFFFFFF0ull) { set_error("%s: cloud too large", fn); return B2_ERR_INVALID; }
+    if (n >= B2_MAX_POINTS) { set_error("%s: cloud too large", fn); return B2_ERR_INVALID; }
     return 0;
 }
 
@@ -1556,7 +1721,7 @@ extern "C" int b2ndt_set_target(b2ndt *h, const void *pts, size_t n, size_t stri
 extern "C" int b2ndt_set_target_device(b2ndt *h, const void *d_pts_f4, size_t n) {
     if (!h) { set_error("b2ndt_set_target_device: NULL handle"); return B2_ERR_INVALID; }
     if (n && !d_pts_f4) { set_error("b2ndt_set_target_device: NULL cloud"); return B2_ERR_INVALID; }
-    if (n >= 0xFFFFFFF0ull) { set_error("b2ndt_set_target_device: cloud too large"); return B2_ERR_INVALID; }
+    if (n >= B2_MAX_POINTS) { set_error("b2ndt_set_target_device: cloud too large"); return B2_ERR_INVALID; }
     B2_CUDA(cudaSetDevice(h->device));
     return build_target(h, (const float4 *)d_pts_f4, n, 0);
 }
@@ -1724,32 +1889,29 @@ static int align_host(b2ndt *h, const void *src, size_t n_total, size_t stride, 
         B2_CUDA(cudaMemcpyAsync(h->d_off.p, ost, (B + 1) * 4, cudaMemcpyHostToDevice, h->st));
         d_off = h->d_off.as<uint32_t>();
     }
-    // Large batches of separate sources: ONE persistent-kernel launch, and the sources stream in behind it.  The
-    // kernel is launched first; the copy stream then delivers the sources chunk by chunk, bumping a counter of
-    // resident matches after every chunk; a CTA that fetches a match whose points have not arrived yet waits on
-    // that counter.  The H2D copy (and the host repack of unpinned / strided clouds) overlaps the matching.
+    // Large batches of separate sources: ONE persistent-kernel launch whose sources stream in while it runs.  The
+    // copy stream first gets ALL chunk copies (each followed by a bump of the counter of resident matches), then the
+    // kernel is launched on the compute stream; a CTA that fetches a match whose points have not arrived yet waits
+    // on that counter.  Everything the kernel waits for is already enqueued when it starts, so its progress never
+    // depends on the host (CUDA_LAUNCH_BLOCKING, a single hardware queue or a profiler serialising launches cannot
+    // dead-lock it), and the wait is bounded on the device.  Strided / unpinned clouds are repacked chunk by chunk
+    // before the launch, each chunk's copy overlapping the repack of the next.
     if (offsets && C == 1 && B >= 256 && h->use_batch_kernel && h->stream_batches) {
         if (!h->copy_st) B2_CUDA(cudaStreamCreateWithFlags(&h->copy_st, cudaStreamNonBlocking));
         if (!h->ev) B2_CUDA(cudaEventCreateWithFlags(&h->ev, cudaEventDisableTiming));
         const size_t nch = 16;
         if ((rc = h->d_work.reserve(64))) return rc;
         if ((rc = h->h_ready.reserve(nch * 4 + 64))) return rc;
-        B2_CUDA(cudaMemsetAsync(h->d_work.p, 0, 8, h->st));
+        B2_CUDA(cudaMemsetAsync(h->d_work.p, 0, 16, h->st));        // [0] work counter, [1] resident matches, [2] time-out flag
         B2_CUDA(cudaEventRecord(h->ev, h->st));                     // counters zeroed, guesses + offsets queued
         B2_CUDA(cudaStreamWaitEvent(h->copy_st, h->ev, 0));
-        MatchArgs A;
-        memset(&A, 0, sizeof(A));
-        A.src = h->d_src.as<float4>(); A.offsets = d_off; A.n_shared = (uint32_t)n_total;
-        A.guesses = h->d_guess.as<float>(); A.poses_out = h->d_pose.as<float>(); A.results = h->d_res.as<b2ndt_result>();
-        A.ready = h->d_work.as<uint32_t>() + 1;
-        if ((rc = launch_match(h, A, B, 1))) return rc;
         uint32_t *hr = h->h_ready.as<uint32_t>();
         const size_t per_c = (B + nch - 1) / nch;
         size_t ci = 0;
-        for (size_t c0 = 0; c0 < B; c0 += per_c, ++ci) {
+        cudaError_t ce = cudaSuccess;
+        for (size_t c0 = 0; c0 < B && ce == cudaSuccess; c0 += per_c, ++ci) {
             const size_t c1 = (c0 + per_c < B) ? c0 + per_c : B;
             const size_t p0 = offsets[c0], p1 = offsets[c1];
-            cudaError_t ce = cudaSuccess;
             if (p1 > p0) {
                 const char *from;
                 if (direct) from = (const char *)src + p0 * 16;
@@ -1759,20 +1921,28 @@ static int align_host(b2ndt *h, const void *src, size_t n_total, size_t stride, 
                 }
                 ce = cudaMemcpyAsync(h->d_src.as<char>() + p0 * 16, from, (p1 - p0) * 16, cudaMemcpyHostToDevice, h->copy_st);
             }
-            hr[ci] = (ce == cudaSuccess) ? (uint32_t)c1 : (uint32_t)B;      // on failure release the kernel, then report
-            cudaError_t ce2 = cudaMemcpyAsync(h->d_work.as<uint32_t>() + 1, hr + ci, 4, cudaMemcpyHostToDevice, h->copy_st);
-            if (ce != cudaSuccess || ce2 != cudaSuccess) {
-                cudaStreamSynchronize(h->copy_st);
-                cudaStreamSynchronize(h->st);
-                set_error("b2ndt_align_batch: streamed H2D copy failed: %s", cudaGetErrorString(ce != cudaSuccess ? ce : ce2));
-                return B2_ERR_CUDA;
-            }
+            hr[ci] = (uint32_t)c1;
+            if (ce == cudaSuccess) ce = cudaMemcpyAsync(h->d_work.as<uint32_t>() + 1, hr + ci, 4, cudaMemcpyHostToDevice, h->copy_st);
         }
+        if (ce != cudaSuccess) {
+            cudaStreamSynchronize(h->copy_st);
+            cudaStreamSynchronize(h->st);
+            set_error("b2ndt_align_batch: streamed H2D copy failed: %s", cudaGetErrorString(ce));
+            return B2_ERR_CUDA;
+        }
+        MatchArgs A;
+        memset(&A, 0, sizeof(A));
+        A.src = h->d_src.as<float4>(); A.offsets = d_off; A.n_shared = (uint32_t)n_total;
+        A.guesses = h->d_guess.as<float>(); A.poses_out = h->d_pose.as<float>(); A.results = h->d_res.as<b2ndt_result>();
+        A.ready = h->d_work.as<uint32_t>() + 1;
+        if ((rc = launch_match(h, A, B, 1))) { cudaStreamSynchronize(h->copy_st); return rc; }
         char *hres2 = h->h_res.as<char>();
         B2_CUDA(cudaMemcpyAsync(hres2, h->d_pose.p, B * 64, cudaMemcpyDeviceToHost, h->st));
         B2_CUDA(cudaMemcpyAsync(hres2 + B * 64, h->d_res.p, B * sizeof(b2ndt_result), cudaMemcpyDeviceToHost, h->st));
+        B2_CUDA(cudaMemcpyAsync(hr + nch, h->d_work.as<uint32_t>() + 2, 4, cudaMemcpyDeviceToHost, h->st));
         B2_CUDA(cudaStreamSynchronize(h->copy_st));
         B2_CUDA(cudaStreamSynchronize(h->st));
+        if (hr[nch]) { set_error("b2ndt_align_batch: streamed sources did not arrive on the device (timed out)"); return B2_ERR_CUDA; }
         memcpy(poses_out, hres2, B * 64);
         if (res) memcpy(res, hres2 + B * 64, B * sizeof(b2ndt_result));
         return 0;

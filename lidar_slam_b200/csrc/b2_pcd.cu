@@ -94,6 +94,8 @@ static int pcd_read_impl(const char *path, float **xyzi, size_t *n_points) {
     for (size_t i = 0; i < fields.size(); ++i) {
         PcdField &fd = fields[i];
         if (fd.size != 1 && fd.size != 2 && fd.size != 4 && fd.size != 8) { set_error("b2_pcd_read: bad SIZE %d", fd.size); return B2_ERR_INVALID; }
+        if (fd.type != 'F' && fd.type != 'U' && fd.type != 'I') { set_error("b2_pcd_read: bad TYPE %c", fd.type); return B2_ERR_INVALID; }
+        if (fd.type == 'F' && fd.size != 4 && fd.size != 8) { set_error("b2_pcd_read: TYPE F needs SIZE 4 or 8, not %d", fd.size); return B2_ERR_INVALID; }
         if (fd.count < 1) fd.count = 1;
         fd.offset = stride;
         stride += (size_t)fd.size * (size_t)fd.count;
@@ -120,8 +122,8 @@ static int pcd_read_impl(const char *path, float **xyzi, size_t *n_points) {
     struct Owner { float *p; ~Owner() { free(p); } } owner{out};          // released on every error path below
     size_t got = 0;
     if (data == "binary") {
-        const bool direct = fields.size() == 4 && fx == 0 && fy == 1 && fz == 2 && fi == 3 && stride == 16 &&
-                            fields[0].type == 'F' && fields[1].type == 'F' && fields[2].type == 'F' && fields[3].type == 'F';
+        bool direct = fields.size() == 4 && fx == 0 && fy == 1 && fz == 2 && fi == 3 && stride == 16;
+        for (size_t i = 0; direct && i < 4; ++i) direct = fields[i].type == 'F' && fields[i].size == 4 && fields[i].count == 1;
         if (direct) {
             got = fread(out, 16, points, f);           // pcl::PointXYZI on disk == the device layout
         } else {
@@ -160,7 +162,20 @@ static int pcd_read_impl(const char *path, float **xyzi, size_t *n_points) {
             out[4 * got + 3] = fi >= 0 ? (float)field_value(block(fi) + got * si, fields[fi]) : 0.f;
         }
     } else if (data == "ascii") {
-        while (got < points && fgets(line, sizeof line, f)) {
+        std::string row;
+        while (got < points) {
+            // one ROW per point whatever its length (a row longer than the buffer must not become two points)
+            row.clear();
+            bool eof = true;
+            while (fgets(line, sizeof line, f)) {
+                eof = false;
+                row += line;
+                if (!row.empty() && row.back() == '\n') break;
+            }
+            if (eof) break;
+            std::vector<char> rowbuf(row.begin(), row.end());
+            rowbuf.push_back('\0');
+            char *line = rowbuf.data();
             size_t col = 0;
             float v[4] = {0.f, 0.f, 0.f, 0.f};
             bool any = false;

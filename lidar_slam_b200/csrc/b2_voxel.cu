@@ -66,17 +66,19 @@ void pack_cloud_f4_bbox(const void *src, size_t n, size_t stride, size_t ioff, f
     };
     unsigned hw = std::thread::hardware_concurrency();
     size_t nt = n > 400000 ? (hw > 8 ? 8 : (hw ? hw : 1)) : 1;
-    std::vector<BB> bbs(nt);
+    BB bbs[8];
+    for (size_t t = 0; t < 8; ++t) for (int k = 0; k < 3; ++k) { bbs[t].mn[k] = FLT_MAX; bbs[t].mx[k] = -FLT_MAX; }
     if (nt <= 1) work(0, n, &bbs[0]);
     else {
-        std::vector<std::thread> th;
+        // no C++ exception may cross the C ABI: if a worker thread cannot be created, its share is done here
+        std::thread th[8];
         size_t chunk = (n + nt - 1) / nt;
         for (size_t t = 0; t < nt; ++t) {
             size_t a = t * chunk, b = a + chunk < n ? a + chunk : n;
-            if (a >= b) { for (int k = 0; k < 3; ++k) { bbs[t].mn[k] = FLT_MAX; bbs[t].mx[k] = -FLT_MAX; } continue; }
-            th.emplace_back(work, a, b, &bbs[t]);
+            if (a >= b) continue;
+            try { th[t] = std::thread(work, a, b, &bbs[t]); } catch (...) { work(a, b, &bbs[t]); }
         }
-        for (auto &t : th) t.join();
+        for (size_t t = 0; t < nt; ++t) if (th[t].joinable()) th[t].join();
     }
     for (int k = 0; k < 3; ++k) { mn[k] = FLT_MAX; mx[k] = -FLT_MAX; }
     for (size_t t = 0; t < nt; ++t)
@@ -96,38 +98,87 @@ void pack_cloud_f4(const void *src, size_t n, size_t stride, size_t ioff, float 
     unsigned hw = std::thread::hardware_concurrency();
     size_t nt = n > 400000 ? (hw > 8 ? 8 : (hw ? hw : 1)) : 1;
     if (nt <= 1) { work(0, n); return; }
-    std::vector<std::thread> th;
+    std::thread th[8];
     size_t chunk = (n + nt - 1) / nt;
     for (size_t t = 0; t < nt; ++t) {
         size_t a = t * chunk, b = a + chunk < n ? a + chunk : n;
-        if (a < b) th.emplace_back(work, a, b);
+        if (a >= b) continue;
+        try { th[t] = std::thread(work, a, b); } catch (...) { work(a, b); }     // see pack_cloud_f4_bbox
     }
-    for (auto &t : th) t.join();
+    for (size_t t = 0; t < nt; ++t) if (th[t].joinable()) th[t].join();
 }
 
-#ifndef B2_SCATTER_MIN_BLOCKS
-#define B2_SCATTER_MIN_BLOCKS 4      // resident CTAs per SM the scatter kernel is compiled for (register cap 64): 5 M-point filter 0.65 -> 0.53 ms
-#endif
 // ------------------------------------------------------------------ kernels -----------------
-__global__ void bbox_init_kernel(uint32_t *bbox, uint32_t *scalars, uint32_t B) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < B) {
-        uint32_t *b = bbox + 8 * i;
-        b[0] = b[1] = b[2] = 0xFFFFFFFFu;
-        b[3] = b[4] = b[5] = 0u;
-        b[6] = 0u; b[7] = 0u;
+// Look-back words: two flag bits + a 30-bit count (B2_MAX_POINTS < 2^30).
+constexpr uint32_t LB_PART = 1u << 30, LB_INCL = 2u << 30, LB_MASK = 0x3FFFFFFFu;
+__device__ __forceinline__ uint32_t ld_vol_g(const uint32_t *p) { return *reinterpret_cast<const volatile uint32_t *>(p); }
+__device__ __forceinline__ void st_vol_g(uint32_t *p, uint32_t v) { *reinterpret_cast<volatile uint32_t *>(p) = v; }
+
+// exclusive scan of one value per thread over a 256-thread CTA; *total = the CTA's sum
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *wsum /*smem[9]*/, uint32_t *total) {
+    const int l = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t n = __shfl_up_sync(0xffffffffu, inc, o); if (l >= o) inc += n; }
+    if (l == 31) wsum[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        const uint32_t t = (l < SORT_THREADS / 32) ? wsum[l] : 0u;
+        uint32_t ti = t;
+#pragma unroll
+        for (int o = 1; o < SORT_THREADS / 32; o <<= 1) { const uint32_t n = __shfl_up_sync(0xffffffffu, ti, o); if (l >= o) ti += n; }
+        if (l < SORT_THREADS / 32) wsum[l] = ti - t;
+        if (l == SORT_THREADS / 32 - 1) wsum[SORT_THREADS / 32] = ti;
     }
-    if (i < 8) scalars[i] = 0u;
+    __syncthreads();
+    const uint32_t r = wsum[w] + inc - v;
+    if (total) *total = wsum[SORT_THREADS / 32];
+    __syncthreads();
+    return r;
 }
 
-__global__ void __launch_bounds__(SORT_THREADS) bbox_kernel(const float4 *__restrict__ pts,
-                                                            const TileDesc *__restrict__ tiles,
-                                                            uint32_t *__restrict__ bbox) {
-    const TileDesc t = tiles[blockIdx.x];
+// pcl::VoxelGrid::applyFilter prologue: inverse leaf, int64 overflow guard, min_b / div_b / divb_mul
+__device__ void compute_layout(const float mn[3], const float mx[3], uint32_t n_finite, float lx, float ly, float lz, VoxLayout &L) {
+    memset(&L, 0, sizeof(L));
+    const float leaf[3] = {lx, ly, lz};
+    for (int a = 0; a < 3; ++a) L.inv[a] = __fdiv_rn(1.0f, leaf[a]);
+    L.n_finite = n_finite;
+    if (L.n_finite > 0) {
+        long long d[3];
+        for (int a = 0; a < 3; ++a) {
+            L.min_p[a] = mn[a];
+            L.max_p[a] = mx[a];
+            d[a] = (long long)__fmul_rn(__fsub_rn(L.max_p[a], L.min_p[a]), L.inv[a]) + 1;
+        }
+        bool ok = (d[0] * d[1] * d[2]) <= 2147483647LL;
+        if (ok) {
+            unsigned long long nc = 1;
+            for (int a = 0; a < 3; ++a) {
+                L.min_b[a] = (int)floorf(__fmul_rn(L.min_p[a], L.inv[a]));
+                int mxb = (int)floorf(__fmul_rn(L.max_p[a], L.inv[a]));
+                L.div_b[a] = mxb - L.min_b[a] + 1;
+                nc *= (unsigned long long)L.div_b[a];
+            }
+            L.mul[0] = 1; L.mul[1] = L.div_b[0]; L.mul[2] = L.div_b[0] * L.div_b[1];
+            if (nc > 0x7FFFFFF0ull) ok = false;   // div_b can exceed the guard's estimate by one per axis
+            L.ncells = (uint32_t)nc;
+        }
+        L.ok = ok ? 1 : 0;
+    }
+    if (L.ok) L.nbits = 32 - __clz(L.ncells);   // keys lie in [0, ncells] (ncells = non-finite points)
+}
+
+// ---- kernel 1: per-tile bounding boxes; the LAST CTA to finish (ticket in scalars[2]) folds them per cloud, writes
+// the PCL layouts and resets the tickets of the kernels that follow.  Also clears the digit histograms.
+__global__ void __launch_bounds__(SORT_THREADS) bbox_layout_kernel(const float4 *__restrict__ pts, PlanView P, float lx, float ly,
+                                                                   float lz, float *__restrict__ part,
+                                                                   VoxLayout *__restrict__ layouts, uint32_t *__restrict__ scalars,
+                                                                   uint32_t *__restrict__ hist, uint32_t hist_words) {
+    const TileDesc t = get_tile(P, blockIdx.x);
     float mn0 = FLT_MAX, mn1 = FLT_MAX, mn2 = FLT_MAX, mx0 = -FLT_MAX, mx1 = -FLT_MAX, mx2 = -FLT_MAX;
     uint32_t cnt = 0;
     for (uint32_t k = threadIdx.x; k < t.count; k += SORT_THREADS) {
-        float4 p = __ldg(&pts[t.begin + k]);
+        const float4 p = __ldg(&pts[t.begin + k]);
         if (finite3(p.x, p.y, p.z)) {
             mn0 = fminf(mn0, p.x); mn1 = fminf(mn1, p.y); mn2 = fminf(mn2, p.z);
             mx0 = fmaxf(mx0, p.x); mx1 = fmaxf(mx1, p.y); mx2 = fmaxf(mx2, p.z);
@@ -146,8 +197,14 @@ __global__ void __launch_bounds__(SORT_THREADS) bbox_kernel(const float4 *__rest
     }
     __shared__ float s[SORT_THREADS / 32][6];
     __shared__ uint32_t sc[SORT_THREADS / 32];
-    int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __shared__ uint32_t s_last, s_bits;
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
     if (l == 0) { s[w][0] = mn0; s[w][1] = mn1; s[w][2] = mn2; s[w][3] = mx0; s[w][4] = mx1; s[w][5] = mx2; sc[w] = cnt; }
+    {   // this CTA's slice of the histogram words
+        const uint32_t chunk = (hist_words + gridDim.x - 1) / gridDim.x;
+        const uint32_t lo = blockIdx.x * chunk, hi = (lo + chunk < hist_words) ? lo + chunk : hist_words;
+        for (uint32_t i = lo + threadIdx.x; i < hi; i += SORT_THREADS) hist[i] = 0u;
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
         uint32_t c = 0;
@@ -156,156 +213,150 @@ __global__ void __launch_bounds__(SORT_THREADS) bbox_kernel(const float4 *__rest
             mn0 = fminf(mn0, s[i][0]); mn1 = fminf(mn1, s[i][1]); mn2 = fminf(mn2, s[i][2]);
             mx0 = fmaxf(mx0, s[i][3]); mx1 = fmaxf(mx1, s[i][4]); mx2 = fmaxf(mx2, s[i][5]);
         }
-        if (c) {
-            uint32_t *b = bbox + 8 * t.seg;
-            atomicMin(&b[0], f2ord(mn0)); atomicMin(&b[1], f2ord(mn1)); atomicMin(&b[2], f2ord(mn2));
-            atomicMax(&b[3], f2ord(mx0)); atomicMax(&b[4], f2ord(mx1)); atomicMax(&b[5], f2ord(mx2));
-            atomicAdd(&b[6], c);
-        }
+        float *o = part + (size_t)blockIdx.x * 8;
+        o[0] = mn0; o[1] = mn1; o[2] = mn2; o[3] = mx0; o[4] = mx1; o[5] = mx2; o[6] = __uint_as_float(c);
+        __threadfence();
+        s_last = (atomicAdd(&scalars[2], 1u) == gridDim.x - 1u) ? 1u : 0u;
+        s_bits = 0u;
     }
-}
-
-// pcl::VoxelGrid::applyFilter prologue: inverse leaf, int64 overflow guard, min_b / div_b / divb_mul
-__global__ void layout_kernel(const uint32_t *__restrict__ bbox, float lx, float ly, float lz,
-                              VoxLayout *__restrict__ layouts, uint32_t *__restrict__ scalars, uint32_t B) {
-    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= B) return;
-    const uint32_t *b = bbox + 8 * s;
-    VoxLayout L;
-    memset(&L, 0, sizeof(L));
-    const float leaf[3] = {lx, ly, lz};
-    for (int a = 0; a < 3; ++a) L.inv[a] = __fdiv_rn(1.0f, leaf[a]);
-    L.n_finite = b[6];
-    if (L.n_finite > 0) {
-        long long d[3];
-        for (int a = 0; a < 3; ++a) {
-            L.min_p[a] = ord2f(b[a]);
-            L.max_p[a] = ord2f(b[3 + a]);
-            d[a] = (long long)__fmul_rn(__fsub_rn(L.max_p[a], L.min_p[a]), L.inv[a]) + 1;
-        }
-        bool ok = (d[0] * d[1] * d[2]) <= 2147483647LL;
-        if (ok) {
-            unsigned long long nc = 1;
-            for (int a = 0; a < 3; ++a) {
-                L.min_b[a] = (int)floorf(__fmul_rn(L.min_p[a], L.inv[a]));
-                int mxb = (int)floorf(__fmul_rn(L.max_p[a], L.inv[a]));
-                L.div_b[a] = mxb - L.min_b[a] + 1;
-                nc *= (unsigned long long)L.div_b[a];
-            }
-            L.mul[0] = 1; L.mul[1] = L.div_b[0]; L.mul[2] = L.div_b[0] * L.div_b[1];
-            if (nc > 0x7FFFFFF0ull) ok = false;   // div_b can exceed the guard's estimate by one per axis
-            L.ncells = (uint32_t)nc;
-        }
-        L.ok = ok ? 1 : 0;
-    }
-    if (L.ok) {
-        L.nbits = 32 - __clz(L.ncells);   // keys lie in [0, ncells] (ncells = non-finite points)
-        atomicMax(&scalars[0], (uint32_t)L.nbits);
-    }
-    layouts[s] = L;
-}
-
-__global__ void __launch_bounds__(SORT_THREADS) key_kernel(const float4 *__restrict__ pts,
-                                                           const TileDesc *__restrict__ tiles,
-                                                           const VoxLayout *__restrict__ layouts,
-                                                           uint32_t *__restrict__ keys, uint32_t *__restrict__ vals) {
-    const TileDesc t = tiles[blockIdx.x];
-    __shared__ VoxLayout L;
-    if (threadIdx.x == 0) L = layouts[t.seg];
     __syncthreads();
-    for (uint32_t k = threadIdx.x; k < t.count; k += SORT_THREADS) {
-        uint32_t i = t.begin + k;
-        float4 p = __ldg(&pts[i]);
-        uint32_t key = L.ncells;
-        if (L.ok && finite3(p.x, p.y, p.z)) key = (uint32_t)vox_index(L, p.x, p.y, p.z);
-        keys[i] = key;
-        vals[i] = i;
-    }
-}
-
-// ---- radix pass: per-tile digit histogram -> [seg][bin][tile] table
-__global__ void __launch_bounds__(SORT_THREADS) radix_hist_kernel(const uint32_t *__restrict__ keys,
-                                                                  const TileDesc *__restrict__ tiles,
-                                                                  const SegDesc *__restrict__ segs,
-                                                                  uint32_t *__restrict__ tilehist, int shift,
-                                                                  const uint32_t *__restrict__ scalars) {
-    if ((uint32_t)shift >= scalars[0]) return;
-    const TileDesc t = tiles[blockIdx.x];
-    const SegDesc sg = segs[t.seg];
-    __shared__ uint32_t h[RADIX];
-    h[threadIdx.x] = 0;
-    __syncthreads();
-    for (uint32_t k = threadIdx.x; k < t.count; k += SORT_THREADS)
-        atomicAdd(&h[(__ldg(&keys[t.begin + k]) >> shift) & (RADIX - 1)], 1u);
-    __syncthreads();
-    tilehist[(size_t)sg.tile_begin * RADIX + (size_t)threadIdx.x * sg.ntiles + t.tile_in_seg] = h[threadIdx.x];
-}
-
-// ---- radix pass: exclusive scan of every (cloud, bin) row over the cloud's tiles.  One warp per row,
-// eight rows per CTA, 32 CTAs per cloud (a single CTA per cloud took 330 us per pass on a 5 M-point map).
-// The row totals go to binbase[cloud][bin]; the scatter kernel turns them into bin offsets itself.
-__global__ void __launch_bounds__(SORT_THREADS) radix_scan_kernel(const SegDesc *__restrict__ segs,
-                                                                  uint32_t *__restrict__ tilehist,
-                                                                  uint32_t *__restrict__ binbase, int shift,
-                                                                  const uint32_t *__restrict__ scalars) {
-    if ((uint32_t)shift >= scalars[0]) return;
-    constexpr int ROWS_PER_CTA = SORT_THREADS / 32;
-    const uint32_t seg = blockIdx.x / (RADIX / ROWS_PER_CTA);
-    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-    const int bin = (blockIdx.x % (RADIX / ROWS_PER_CTA)) * ROWS_PER_CTA + w;
-    const SegDesc sg = segs[seg];
-    uint32_t *row = tilehist + (size_t)sg.tile_begin * RADIX + (size_t)bin * sg.ntiles;
-    uint32_t running = 0;
-    for (uint32_t t0 = 0; t0 < sg.ntiles; t0 += 32) {
-        uint32_t v = (t0 + l < sg.ntiles) ? row[t0 + l] : 0u;
-        uint32_t inc = v;
+    if (!s_last) return;
+    __threadfence();
+    for (uint32_t sg_i = w; sg_i < P.B; sg_i += SORT_THREADS / 32) {      // one warp per cloud
+        const SegDesc sg = get_seg(P, sg_i);
+        float a0 = FLT_MAX, a1 = FLT_MAX, a2 = FLT_MAX, b0 = -FLT_MAX, b1 = -FLT_MAX, b2 = -FLT_MAX;
+        uint32_t c = 0;
+        for (uint32_t k = l; k < sg.ntiles; k += 32) {
+            const float *o = part + (size_t)(sg.tile_begin + k) * 8;
+            const float4 lo4 = __ldcg(reinterpret_cast<const float4 *>(o)), hi4 = __ldcg(reinterpret_cast<const float4 *>(o) + 1);
+            a0 = fminf(a0, lo4.x); a1 = fminf(a1, lo4.y); a2 = fminf(a2, lo4.z);
+            b0 = fmaxf(b0, lo4.w); b1 = fmaxf(b1, hi4.x); b2 = fmaxf(b2, hi4.y);
+            c += __float_as_uint(hi4.z);
+        }
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t n = __shfl_up_sync(0xffffffffu, inc, o);
-            if (l >= o) inc += n;
+        for (int o = 16; o > 0; o >>= 1) {
+            a0 = fminf(a0, __shfl_xor_sync(0xffffffffu, a0, o)); a1 = fminf(a1, __shfl_xor_sync(0xffffffffu, a1, o));
+            a2 = fminf(a2, __shfl_xor_sync(0xffffffffu, a2, o)); b0 = fmaxf(b0, __shfl_xor_sync(0xffffffffu, b0, o));
+            b1 = fmaxf(b1, __shfl_xor_sync(0xffffffffu, b1, o)); b2 = fmaxf(b2, __shfl_xor_sync(0xffffffffu, b2, o));
+            c += __shfl_xor_sync(0xffffffffu, c, o);
         }
-        if (t0 + l < sg.ntiles) row[t0 + l] = running + inc - v;
-        running += __shfl_sync(0xffffffffu, inc, 31);
+        if (l == 0) {
+            const float mn[3] = {a0, a1, a2}, mx[3] = {b0, b1, b2};
+            VoxLayout L;
+            compute_layout(mn, mx, c, lx, ly, lz, L);
+            layouts[sg_i] = L;
+            if (L.ok) atomicMax(&s_bits, (uint32_t)L.nbits);
+        }
     }
-    if (l == 0) binbase[(size_t)seg * RADIX + bin] = running;      // row total
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        scalars[0] = s_bits; scalars[1] = 0u; scalars[2] = 0u;
+        for (int i = 4; i < 12; ++i) scalars[i] = 0u;      // tickets of the kernels that follow + work-list counters
+    }
 }
 
-// ---- radix pass: stable scatter.  Warp w owns elements [512w, 512w+512) of the tile in 16 rounds of
-// 32 consecutive keys; ranks come from match_any + per-warp digit counters in shared memory.
-__global__ void __launch_bounds__(SORT_THREADS, B2_SCATTER_MIN_BLOCKS) radix_scatter_kernel(
-    const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in, uint32_t *__restrict__ keys_out,
-    uint32_t *__restrict__ vals_out, const TileDesc *__restrict__ tiles, const SegDesc *__restrict__ segs,
-    const uint32_t *__restrict__ tilehist, const uint32_t *__restrict__ binbase, int shift,
-    const uint32_t *__restrict__ scalars) {
-    const TileDesc t = tiles[blockIdx.x];
-    if ((uint32_t)shift >= scalars[0]) {   // digit is zero everywhere: identity pass
-        for (uint32_t k = threadIdx.x; k < t.count; k += SORT_THREADS) {
-            keys_out[t.begin + k] = keys_in[t.begin + k];
-            vals_out[t.begin + k] = vals_in[t.begin + k];
-        }
-        return;
-    }
-    const SegDesc sg = segs[t.seg];
-    constexpr int NW = SORT_THREADS / 32;
-    constexpr int ROUNDS = SORT_TILE / SORT_THREADS;
-    __shared__ uint32_t wcnt[NW][RADIX];
-    __shared__ uint32_t gbase[RADIX];
-    __shared__ uint32_t wtot[NW];
-    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-    for (int i = threadIdx.x; i < NW * RADIX; i += SORT_THREADS) (&wcnt[0][0])[i] = 0;
+// ---- kernel 2: voxel key per point + the digit histograms of EVERY radix pass (one read of the points), and the
+// clearing of this tile's look-back words.  Pass 0 digits are diverse (plain shared-memory atomics); the digits of the
+// higher passes are mostly equal inside a warp, so they are aggregated with match.any first.
+template <bool FROM_POINTS>
+__global__ void __launch_bounds__(SORT_THREADS) key_hist_kernel(const float4 *__restrict__ pts, PlanView P,
+                                                                const VoxLayout *__restrict__ layouts, uint32_t *__restrict__ keys,
+                                                                uint32_t *__restrict__ hist, uint32_t *__restrict__ state,
+                                                                const uint32_t *__restrict__ scalars) {
+    const TileDesc t = get_tile(P, blockIdx.x);
+    __shared__ VoxLayout L;
+    __shared__ uint32_t h[4][RADIX];
+    if (FROM_POINTS && threadIdx.x == 0) L = layouts[t.seg];
+    for (int i = threadIdx.x; i < 4 * RADIX; i += SORT_THREADS) (&h[0][0])[i] = 0u;
     __syncthreads();
-    uint32_t key[ROUNDS], val[ROUNDS];
-    uint16_t loc[ROUNDS];
+    const int npass = (int)((scalars[0] + RADIX_BITS - 1) / RADIX_BITS);
+    const int l = threadIdx.x & 31;
+    for (uint32_t k0 = threadIdx.x & ~31u; k0 < t.count; k0 += SORT_THREADS) {      // warp-uniform trip count
+        const uint32_t k = k0 + l;
+        const bool valid = k < t.count;
+        uint32_t key = 0u;
+        if (valid) {
+            if (FROM_POINTS) {
+                const float4 p = __ldg(&pts[t.begin + k]);
+                key = L.ncells;
+                if (L.ok && finite3(p.x, p.y, p.z)) key = (uint32_t)vox_index(L, p.x, p.y, p.z);
+                keys[t.begin + k] = key;
+            } else {
+                key = __ldg(&keys[t.begin + k]);
+            }
+            atomicAdd(&h[0][key & (RADIX - 1)], 1u);
+        }
+        for (int p = 1; p < npass; ++p) {
+            const uint32_t d = valid ? ((key >> (p * RADIX_BITS)) & (RADIX - 1)) : (uint32_t)RADIX;
+            const uint32_t peers = __match_any_sync(0xffffffffu, d);
+            if (valid && l == __ffs(peers) - 1) atomicAdd(&h[p][d], (uint32_t)__popc(peers));
+        }
+    }
+    __syncthreads();
+    for (int p = 0; p < npass; ++p) {
+        const uint32_t v = h[p][threadIdx.x];
+        if (v) atomicAdd(&hist[((size_t)t.seg * 4 + p) * RADIX + threadIdx.x], v);
+    }
+    for (int p = 0; p < 4; ++p) state[((size_t)p * P.ntiles + blockIdx.x) * RADIX + threadIdx.x] = 0u;
+    if (threadIdx.x == 0) state[(size_t)4 * P.ntiles * RADIX + blockIdx.x] = 0u;
+}
+
+// ---- kernel 3: ONE radix pass in ONE kernel ("onesweep"): every tile ranks its keys (match.any + per-warp digit
+// counters, stable by construction), publishes its digit counts, obtains the counts of the tiles before it by
+// decoupled look-back (tiles take their index from a ticket, so every predecessor is already running), reorders the
+// tile in shared memory and writes each digit's run to its final place with coalesced stores.  Pass 0 has no payload
+// to read: the payload is the element index.  A pass at or above the key width returns at once.
+template <int ITEMS>
+__global__ void __launch_bounds__(SORT_THREADS, (ITEMS > 8 ? 3 : 6)) onesweep_kernel(SortView sv, PlanView P, const uint32_t *__restrict__ hist,
+                                                                uint32_t *__restrict__ state, uint32_t *__restrict__ ticket,
+                                                                int pass) {
+    const int shift = pass * RADIX_BITS;
+    if ((uint32_t)shift >= __ldg(&sv.scalars[0])) return;
+    const bool odd = (pass & 1) != 0;
+    const uint32_t *__restrict__ kin = odd ? sv.k[1] : sv.k[0];
+    const uint32_t *__restrict__ vin = odd ? sv.v[1] : sv.v[0];
+    uint32_t *__restrict__ kout = const_cast<uint32_t *>(odd ? sv.k[0] : sv.k[1]);
+    uint32_t *__restrict__ vout = const_cast<uint32_t *>(odd ? sv.v[0] : sv.v[1]);
+    constexpr int NW = SORT_THREADS / 32;
+    constexpr int TILE = SORT_THREADS * ITEMS;
+    __shared__ uint32_t wcnt[NW][RADIX];
+    __shared__ uint32_t gbase[RADIX], lstart[RADIX];
+    __shared__ uint32_t skey[TILE], sval[TILE];
+    __shared__ uint32_t wsum[NW + 1];
+    __shared__ uint32_t s_tile;
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    for (int i = threadIdx.x; i < NW * RADIX; i += SORT_THREADS) (&wcnt[0][0])[i] = 0u;
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const TileDesc t = get_tile(P, tile);
+    const SegDesc sg = get_seg(P, t.seg);
+    // all loads of the tile are in flight before the first rank is computed
+    uint32_t key[ITEMS], val[ITEMS];
+    uint16_t loc[ITEMS];
+#pragma unroll
+    for (int r = 0; r < ITEMS; ++r) {
+        const uint32_t e = w * (32 * ITEMS) + r * 32 + l;
+        key[r] = (e < t.count) ? __ldcs(&kin[t.begin + e]) : 0xFFFFFFFFu;
+    }
+    if (pass == 0) {
+#pragma unroll
+        for (int r = 0; r < ITEMS; ++r) val[r] = t.begin + w * (32 * ITEMS) + r * 32 + l;
+    } else {
+#pragma unroll
+        for (int r = 0; r < ITEMS; ++r) {
+            const uint32_t e = w * (32 * ITEMS) + r * 32 + l;
+            val[r] = (e < t.count) ? __ldcs(&vin[t.begin + e]) : 0u;
+        }
+    }
     const uint32_t lt = (1u << l) - 1u;
 #pragma unroll
-    for (int r = 0; r < ROUNDS; ++r) {
-        uint32_t e = w * (32 * ROUNDS) + r * 32 + l;
-        bool valid = e < t.count;
-        key[r] = valid ? keys_in[t.begin + e] : 0u;
-        val[r] = valid ? vals_in[t.begin + e] : 0u;
-        uint32_t digit = valid ? ((key[r] >> shift) & (RADIX - 1)) : (uint32_t)RADIX;
-        uint32_t peers = __match_any_sync(0xffffffffu, digit);
-        int leader = __ffs(peers) - 1;
+    for (int r = 0; r < ITEMS; ++r) {
+        const uint32_t e = w * (32 * ITEMS) + r * 32 + l;
+        const bool valid = e < t.count;
+        const uint32_t digit = valid ? ((key[r] >> shift) & (RADIX - 1)) : (uint32_t)RADIX;
+        const uint32_t peers = __match_any_sync(0xffffffffu, digit);
+        const int leader = __ffs(peers) - 1;
         uint32_t base = 0;
         if (valid && l == leader) {
             base = wcnt[w][digit];
@@ -316,327 +367,438 @@ __global__ void __launch_bounds__(SORT_THREADS, B2_SCATTER_MIN_BLOCKS) radix_sca
         __syncwarp();
     }
     __syncthreads();
-    {
-        uint32_t d = threadIdx.x, run = 0;
+    // thread d owns digit d from here on
+    const uint32_t d = threadIdx.x;
+    uint32_t cnt_d = 0;
 #pragma unroll
-        for (int i = 0; i < NW; ++i) { uint32_t c = wcnt[i][d]; wcnt[i][d] = run; run += c; }
-        // exclusive scan of the cloud's 256 bin totals (block scan)
-        const uint32_t v = binbase[(size_t)t.seg * RADIX + d];
-        uint32_t inc = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t n = __shfl_up_sync(0xffffffffu, inc, o);
-            if (l >= o) inc += n;
+    for (int i = 0; i < NW; ++i) { const uint32_t c = wcnt[i][d]; wcnt[i][d] = cnt_d; cnt_d += c; }
+    uint32_t *st = state + (size_t)tile * RADIX;
+    uint32_t excl = 0;
+    if (t.tile_in_seg == 0) {
+        st_vol_g(&st[d], cnt_d | LB_INCL);
+    } else {
+        st_vol_g(&st[d], cnt_d | LB_PART);
+        for (uint32_t j = tile - 1;; --j) {
+            uint32_t v;
+            do { v = ld_vol_g(&state[(size_t)j * RADIX + d]); } while ((v & ~LB_MASK) == 0u);
+            excl += v & LB_MASK;
+            if (v & LB_INCL) break;            // the cloud's first tile always publishes an inclusive count
         }
-        if (l == 31) wtot[w] = inc;
-        __syncthreads();
-        uint32_t add = 0;
-        for (int i = 0; i < w; ++i) add += wtot[i];
-        gbase[d] = sg.begin + (add + inc - v) +
-                   tilehist[(size_t)sg.tile_begin * RADIX + (size_t)d * sg.ntiles + t.tile_in_seg];
+        st_vol_g(&st[d], (excl + cnt_d) | LB_INCL);
+    }
+    // digit bases: cloud-wide (histogram) and tile-local
+    const uint32_t hd = __ldg(&hist[((size_t)t.seg * 4 + pass) * RADIX + d]);
+    const uint32_t hex = block_excl_scan(hd, wsum, nullptr);
+    const uint32_t lex = block_excl_scan(cnt_d, wsum, nullptr);
+    gbase[d] = sg.begin + hex + excl;
+    lstart[d] = lex;
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < ITEMS; ++r) {
+        const uint32_t e = w * (32 * ITEMS) + r * 32 + l;
+        if (e < t.count) {
+            const uint32_t digit = (key[r] >> shift) & (RADIX - 1);
+            const uint32_t pos = lstart[digit] + wcnt[w][digit] + loc[r];
+            skey[pos] = key[r];
+            sval[pos] = val[r];
+        }
     }
     __syncthreads();
 #pragma unroll
-    for (int r = 0; r < ROUNDS; ++r) {
-        uint32_t e = w * (32 * ROUNDS) + r * 32 + l;
-        if (e < t.count) {
-            uint32_t digit = (key[r] >> shift) & (RADIX - 1);
-            uint32_t pos = gbase[digit] + wcnt[w][digit] + loc[r];
-            keys_out[pos] = key[r];
-            vals_out[pos] = val[r];
+    for (int i = 0; i < ITEMS; ++i) {
+        const uint32_t pos = i * SORT_THREADS + threadIdx.x;
+        if (pos < t.count) {
+            const uint32_t k = skey[pos];
+            const uint32_t digit = (k >> shift) & (RADIX - 1);
+            const uint32_t g = gbase[digit] + (pos - lstart[digit]);
+            kout[g] = k;
+            vout[g] = sval[pos];
         }
     }
 }
 
-// ---- run heads (one run = one occupied voxel).  Blocked arrangement: thread t owns 16 consecutive keys.
-template <bool WRITE>
-__global__ void __launch_bounds__(SORT_THREADS) head_kernel(const uint32_t *__restrict__ keys,
-                                                            const TileDesc *__restrict__ tiles,
-                                                            const SegDesc *__restrict__ segs,
-                                                            const VoxLayout *__restrict__ layouts,
-                                                            uint32_t *__restrict__ tile_heads,
-                                                            uint32_t *__restrict__ run_start,
-                                                            uint32_t *__restrict__ run_seg) {
-    const TileDesc t = tiles[blockIdx.x];
-    const SegDesc sg = segs[t.seg];
-    __shared__ uint32_t s_ok, s_inv;
-    __shared__ uint32_t wsum[SORT_THREADS / 32];
+// ---- kernel 4: run heads (one run = one occupied voxel) in one kernel: per-tile head flags (blocked arrangement,
+// thread t owns ITEMS consecutive keys), a decoupled look-back over the tiles' head counts (one chain over the whole
+// batch: run indices are global), then the compacted run table {first element, cloud}, the per-cloud first-run table
+// and the total.
+template <int ITEMS>
+__global__ void __launch_bounds__(SORT_THREADS) runs_kernel(SortView sv, PlanView P, const VoxLayout *__restrict__ layouts,
+                                                            uint32_t *__restrict__ state, uint32_t *__restrict__ ticket,
+                                                            uint32_t *__restrict__ run_start, uint32_t *__restrict__ run_seg,
+                                                            uint32_t *__restrict__ run_seg_off, uint32_t *__restrict__ scalars) {
+    const uint32_t *__restrict__ keys = sv.keys();
+    __shared__ uint32_t s_tile, s_ok, s_inv, s_excl;
+    __shared__ uint32_t wsum[SORT_THREADS / 32 + 1];
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const TileDesc t = get_tile(P, tile);
+    const SegDesc sg = get_seg(P, t.seg);
     if (threadIdx.x == 0) { s_ok = layouts[t.seg].ok; s_inv = layouts[t.seg].ncells; }
     __syncthreads();
-    constexpr int PER = SORT_TILE / SORT_THREADS;
-    const uint32_t e0 = threadIdx.x * PER;
+    const uint32_t e0 = threadIdx.x * ITEMS;
     uint32_t flags = 0;
     if (s_ok && e0 < t.count) {
-        uint32_t gi = t.begin + e0;
+        const uint32_t gi = t.begin + e0;
         uint32_t prev = (gi > sg.begin) ? keys[gi - 1] : 0xFFFFFFFFu;
 #pragma unroll
-        for (int j = 0; j < PER; ++j) {
+        for (int j = 0; j < ITEMS; ++j) {
             if (e0 + j < t.count) {
-                uint32_t k = keys[gi + j];
-                bool head = (k != s_inv) && ((gi + j == sg.begin) || (k != prev));
+                const uint32_t k = keys[gi + j];
+                const bool head = (k != s_inv) && ((gi + j == sg.begin) || (k != prev));
                 flags |= head ? (1u << j) : 0u;
                 prev = k;
             }
         }
     }
-    uint32_t cnt = __popc(flags), inc = cnt;
-    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    const uint32_t cnt = __popc(flags);
+    uint32_t total;
+    const uint32_t lex = block_excl_scan(cnt, wsum, &total);
+    if (threadIdx.x < 32) {
+        // warp-parallel look-back: lane i inspects tile - 1 - i (a virtual tile before tile 0 holds an inclusive 0)
+        const int l = threadIdx.x;
+        uint32_t excl = 0;
+        if (tile == 0) {
+            if (l == 0) st_vol_g(&state[0], total | LB_INCL);
+        } else {
+            if (l == 0) st_vol_g(&state[tile], total | LB_PART);
+            int base = (int)tile;
+            while (true) {
+                const int j = base - 1 - l;
+                uint32_t v = LB_INCL;
+                if (j >= 0) { do { v = ld_vol_g(&state[j]); } while ((v & ~LB_MASK) == 0u); }
+                const uint32_t incl_mask = __ballot_sync(0xffffffffu, (v & LB_INCL) != 0u);
+                const int stop = __ffs(incl_mask) - 1;                    // nearest predecessor with an inclusive count
+                uint32_t c = (stop < 0 || l <= stop) ? (v & LB_MASK) : 0u;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        uint32_t n = __shfl_up_sync(0xffffffffu, inc, o);
-        if (l >= o) inc += n;
+                for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+                excl += c;
+                if (stop >= 0) break;
+                base -= 32;
+            }
+            if (l == 0) st_vol_g(&state[tile], (excl + total) | LB_INCL);
+        }
+        if (l == 0) s_excl = excl;
     }
-    if (l == 31) wsum[w] = inc;
     __syncthreads();
-    uint32_t add = 0;
-    for (int i = 0; i < w; ++i) add += wsum[i];
-    if (!WRITE) {
-        if (threadIdx.x == SORT_THREADS - 1) tile_heads[blockIdx.x] = add + inc;
-    } else {
-        uint32_t o = tile_heads[blockIdx.x] + add + inc - cnt;
+    const uint32_t excl = s_excl;
+    uint32_t o = excl + lex;
 #pragma unroll
-        for (int j = 0; j < PER; ++j)
-            if (flags & (1u << j)) { run_start[o] = t.begin + e0 + j; run_seg[o] = t.seg; ++o; }
+    for (int j = 0; j < ITEMS; ++j)
+        if (flags & (1u << j)) { run_start[o] = t.begin + e0 + j; run_seg[o] = t.seg; ++o; }
+    if (threadIdx.x == 0) {
+        if (t.tile_in_seg == 0) {
+            // first tile of a cloud: the first-run entry of this cloud and of the empty clouds just before it
+            uint32_t s = t.seg;
+            run_seg_off[s] = excl;
+            while (s > 0 && get_seg(P, s - 1).count == 0u) { --s; run_seg_off[s] = excl; }
+        }
+        if (tile == P.ntiles - 1u) {
+            for (uint32_t s = t.seg + 1; s <= P.B; ++s) run_seg_off[s] = excl + total;
+            scalars[1] = excl + total;
+        }
     }
 }
 
-// single-CTA exclusive scan of the per-tile head counts (+ per-cloud first-run table)
-__global__ void __launch_bounds__(1024) scan_tiles_kernel(uint32_t *__restrict__ tile_heads, uint32_t ntiles,
-                                                          const SegDesc *__restrict__ segs, uint32_t B,
-                                                          uint32_t *__restrict__ run_seg_off,
-                                                          uint32_t *__restrict__ scalars) {
-    __shared__ uint32_t wsum[32];
-    __shared__ uint32_t carry;
-    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
-    for (uint32_t t0 = 0; t0 < ntiles; t0 += 1024) {
-        uint32_t i = t0 + threadIdx.x;
-        uint32_t v = i < ntiles ? tile_heads[i] : 0u, inc = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t n = __shfl_up_sync(0xffffffffu, inc, o);
-            if (l >= o) inc += n;
-        }
-        if (l == 31) wsum[w] = inc;
-        __syncthreads();
-        if (w == 0) {
-            uint32_t x = wsum[l], xi = x;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                uint32_t n = __shfl_up_sync(0xffffffffu, xi, o);
-                if (l >= o) xi += n;
-            }
-            wsum[l] = xi - x;
-        }
-        __syncthreads();
-        uint32_t excl = carry + wsum[w] + inc - v;
-        if (i < ntiles) tile_heads[i] = excl;
-        __syncthreads();
-        if (threadIdx.x == 1023) carry = excl + v;
-        __syncthreads();
+// no tiles at all (every cloud of the batch is empty): layouts, totals and the per-cloud run table
+__global__ void empty_plan_kernel(VoxLayout *layouts, uint32_t *scalars, uint32_t *run_seg_off, uint32_t B, float lx, float ly,
+                                  float lz) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < B) {
+        const float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+        VoxLayout L;
+        compute_layout(mn, mx, 0u, lx, ly, lz, L);
+        layouts[s] = L;
     }
-    if (threadIdx.x == 0) { tile_heads[ntiles] = carry; scalars[1] = carry; }
-    __syncthreads();
-    for (uint32_t s = threadIdx.x; s <= B; s += 1024) {
-        uint32_t tb = (s < B) ? segs[s].tile_begin : ntiles;
-        run_seg_off[s] = tile_heads[tb];
+    if (s <= B) run_seg_off[s] = 0u;
+    if (s == 0) { scalars[0] = 0u; scalars[1] = 0u; scalars[10] = 0u; scalars[11] = 0u; }
+}
+
+__global__ void prepared_layout_kernel(VoxLayout *layouts, uint32_t *scalars, uint32_t *hist, uint32_t hist_words, uint32_t B,
+                                       uint32_t invalid_key, int nbits) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    for (uint32_t i = s; i < B; i += gridDim.x * blockDim.x) {
+        VoxLayout L;
+        memset(&L, 0, sizeof(L));
+        L.ok = 1; L.ncells = invalid_key; L.nbits = nbits;
+        layouts[i] = L;
+    }
+    for (uint32_t i = s; i < hist_words; i += gridDim.x * blockDim.x) hist[i] = 0u;
+    if (s == 0) {
+        scalars[0] = (uint32_t)nbits; scalars[1] = 0u; scalars[2] = 0u;
+        for (int i = 4; i < 12; ++i) scalars[i] = 0u;
     }
 }
 
 // ------------------------------------------------------------------ VoxPipeline -------------
 int VoxPipeline::plan(const uint32_t *off, size_t nB, cudaStream_t st) {
+    if ((size_t)off[nB] >= B2_MAX_POINTS) { set_error("cloud too large: %u points (limit %zu per call)", off[nB], (size_t)B2_MAX_POINTS); return B2_ERR_INVALID; }
+    const bool same = (nB == B && nB > 1 && h_off.size() == nB + 1 && memcmp(h_off.data(), off, (nB + 1) * 4) == 0);
     B = nB;
     N = off[nB];
-    h_tiles.clear();
-    h_segs.resize(nB);
-    for (size_t s = 0; s < nB; ++s) {
-        uint32_t b = off[s], c = off[s + 1] - off[s];
-        SegDesc sd;
-        sd.begin = b; sd.count = c; sd.tile_begin = (uint32_t)h_tiles.size();
-        sd.ntiles = (c + SORT_TILE - 1) / SORT_TILE;
-        for (uint32_t t = 0; t < sd.ntiles; ++t) {
-            TileDesc td;
-            td.seg = (uint32_t)s; td.begin = b + t * SORT_TILE;
-            td.count = (c - t * SORT_TILE < (uint32_t)SORT_TILE) ? c - t * SORT_TILE : SORT_TILE;
-            td.tile_in_seg = t;
-            h_tiles.push_back(td);
-        }
-        h_segs[s] = sd;
-    }
-    ntiles = h_tiles.size();
+    tile_elems = SORT_THREADS * (N >= SORT_LARGE_FROM ? SORT_ITEMS_LARGE : SORT_ITEMS_SMALL);
     int rc;
-    if ((rc = d_tiles.reserve((ntiles + 1) * sizeof(TileDesc)))) return rc;
-    if ((rc = d_segs.reserve((B + 1) * sizeof(SegDesc)))) return rc;
-    if ((rc = d_bbox.reserve((B + 1) * 8 * sizeof(uint32_t)))) return rc;
+    if (nB <= 1) {
+        ntiles = (N + tile_elems - 1) / tile_elems;
+        h_off.clear();
+    } else if (!same) {
+        h_tiles.clear();
+        h_segs.resize(nB);
+        for (size_t s = 0; s < nB; ++s) {
+            uint32_t b = off[s], c = off[s + 1] - off[s];
+            SegDesc sd;
+            sd.begin = b; sd.count = c; sd.tile_begin = (uint32_t)h_tiles.size();
+            sd.ntiles = (c + tile_elems - 1) / tile_elems;
+            for (uint32_t t = 0; t < sd.ntiles; ++t) {
+                TileDesc td;
+                td.seg = (uint32_t)s; td.begin = b + t * tile_elems;
+                td.count = (c - t * tile_elems < tile_elems) ? c - t * tile_elems : tile_elems;
+                td.tile_in_seg = t;
+                h_tiles.push_back(td);
+            }
+            h_segs[s] = sd;
+        }
+        ntiles = h_tiles.size();
+        if ((rc = d_tiles.reserve((ntiles + 1) * sizeof(TileDesc)))) return rc;
+        if ((rc = d_segs.reserve((B + 1) * sizeof(SegDesc)))) return rc;
+        if (ntiles) B2_CUDA(cudaMemcpyAsync(d_tiles.p, h_tiles.data(), ntiles * sizeof(TileDesc), cudaMemcpyHostToDevice, st));
+        B2_CUDA(cudaMemcpyAsync(d_segs.p, h_segs.data(), B * sizeof(SegDesc), cudaMemcpyHostToDevice, st));
+        // the async copies read h_tiles / h_segs (pageable): the runtime stages them before returning
+        h_off.assign(off, off + nB + 1);
+    }
     if ((rc = d_layouts.reserve((B + 1) * sizeof(VoxLayout)))) return rc;
-    if ((rc = d_scalars.reserve(8 * sizeof(uint32_t)))) return rc;
+    if (d_scalars.cap < 16 * sizeof(uint32_t)) scalars_ready = false;
+    if ((rc = d_scalars.reserve(16 * sizeof(uint32_t)))) return rc;
+    if (!scalars_ready) {
+        // the tickets are self-resetting from here on (bbox_layout_kernel / prepared_layout_kernel)
+        B2_CUDA(cudaMemsetAsync(d_scalars.p, 0, 16 * sizeof(uint32_t), st));
+        scalars_ready = true;
+    }
+    if ((rc = d_hist.reserve((B + 1) * 4 * RADIX * sizeof(uint32_t)))) return rc;
     for (int i = 0; i < 2; ++i) {
         if ((rc = d_keys[i].reserve((N + 1) * sizeof(uint32_t)))) return rc;
         if ((rc = d_vals[i].reserve((N + 1) * sizeof(uint32_t)))) return rc;
     }
-    if ((rc = d_tilehist.reserve((ntiles + 1) * RADIX * sizeof(uint32_t)))) return rc;
-    if ((rc = d_binbase.reserve((B + 1) * RADIX * sizeof(uint32_t)))) return rc;
-    if ((rc = d_tile_heads.reserve((ntiles + 2) * sizeof(uint32_t)))) return rc;
+    if ((rc = d_bbox_part.reserve((ntiles + 1) * 8 * sizeof(float)))) return rc;
+    if ((rc = d_state.reserve(((size_t)ntiles * (4 * RADIX + 1) + 16) * sizeof(uint32_t)))) return rc;
     if ((rc = d_run_start.reserve((N + 2) * sizeof(uint32_t)))) return rc;
     if ((rc = d_run_seg.reserve((N + 2) * sizeof(uint32_t)))) return rc;
     if ((rc = d_run_seg_off.reserve((B + 2) * sizeof(uint32_t)))) return rc;
-    if (ntiles) B2_CUDA(cudaMemcpyAsync(d_tiles.p, h_tiles.data(), ntiles * sizeof(TileDesc), cudaMemcpyHostToDevice, st));
-    if (B) B2_CUDA(cudaMemcpyAsync(d_segs.p, h_segs.data(), B * sizeof(SegDesc), cudaMemcpyHostToDevice, st));
-    // the async copies read h_tiles/h_segs (pageable): the runtime stages them before returning
+    return 0;
+}
+
+int VoxPipeline::sort_and_runs(int npass_launch, cudaStream_t st) {
+    const uint32_t nt = (uint32_t)ntiles;
+    const SortView sv = view();
+    const PlanView P = plan_view();
+    uint32_t *sc = d_scalars.as<uint32_t>();
+    uint32_t *state = d_state.as<uint32_t>();
+    const bool large = tile_elems == SORT_THREADS * SORT_ITEMS_LARGE;
+    for (int p = 0; p < npass_launch; ++p) {
+        uint32_t *stp = state + (size_t)p * nt * RADIX;
+        if (large) onesweep_kernel<SORT_ITEMS_LARGE><<<nt, SORT_THREADS, 0, st>>>(sv, P, d_hist.as<uint32_t>(), stp, sc + 4 + p, p);
+        else onesweep_kernel<SORT_ITEMS_SMALL><<<nt, SORT_THREADS, 0, st>>>(sv, P, d_hist.as<uint32_t>(), stp, sc + 4 + p, p);
+        B2_LAUNCH_CHECK();
+    }
+    uint32_t *str = state + (size_t)4 * nt * RADIX;
+    if (large)
+        runs_kernel<SORT_ITEMS_LARGE><<<nt, SORT_THREADS, 0, st>>>(sv, P, layouts(), str, sc + 8, d_run_start.as<uint32_t>(),
+                                                                   d_run_seg.as<uint32_t>(), d_run_seg_off.as<uint32_t>(), sc);
+    else
+        runs_kernel<SORT_ITEMS_SMALL><<<nt, SORT_THREADS, 0, st>>>(sv, P, layouts(), str, sc + 8, d_run_start.as<uint32_t>(),
+                                                                   d_run_seg.as<uint32_t>(), d_run_seg_off.as<uint32_t>(), sc);
+    B2_LAUNCH_CHECK();
     return 0;
 }
 
 int VoxPipeline::run(const float4 *d_pts, float lx, float ly, float lz, int nbits_hint, cudaStream_t st) {
     const uint32_t nB = (uint32_t)B, nt = (uint32_t)ntiles;
-    uint32_t *bbox = d_bbox.as<uint32_t>(), *sc = d_scalars.as<uint32_t>();
-    const TileDesc *tiles = d_tiles.as<TileDesc>();
-    const SegDesc *segs = d_segs.as<SegDesc>();
+    uint32_t *sc = d_scalars.as<uint32_t>();
     VoxLayout *lay = d_layouts.as<VoxLayout>();
-    bbox_init_kernel<<<(nB + 8 + 255) / 256, 256, 0, st>>>(bbox, sc, nB);
+    if (nt == 0) {
+        empty_plan_kernel<<<(nB + 1 + 127) / 128, 128, 0, st>>>(lay, sc, d_run_seg_off.as<uint32_t>(), nB, lx, ly, lz);
+        B2_LAUNCH_CHECK();
+        return 0;
+    }
+    const PlanView P = plan_view();
+    bbox_layout_kernel<<<nt, SORT_THREADS, 0, st>>>(d_pts, P, lx, ly, lz, d_bbox_part.as<float>(), lay, sc, d_hist.as<uint32_t>(),
+                                                   nB * 4 * RADIX);
     B2_LAUNCH_CHECK();
-    if (nt) {
-        bbox_kernel<<<nt, SORT_THREADS, 0, st>>>(d_pts, tiles, bbox);
-        B2_LAUNCH_CHECK();
-    }
-    layout_kernel<<<(nB + 127) / 128, 128, 0, st>>>(bbox, lx, ly, lz, lay, sc, nB);
+    key_hist_kernel<true><<<nt, SORT_THREADS, 0, st>>>(d_pts, P, lay, d_keys[0].as<uint32_t>(), d_hist.as<uint32_t>(),
+                                                      d_state.as<uint32_t>(), sc);
     B2_LAUNCH_CHECK();
-    final_buf = 0;
-    if (nt) {
-        key_kernel<<<nt, SORT_THREADS, 0, st>>>(d_pts, tiles, lay, d_keys[0].as<uint32_t>(), d_vals[0].as<uint32_t>());
-        B2_LAUNCH_CHECK();
-        int passes = 32 / RADIX_BITS;
-        if (nbits_hint > 0) passes = (nbits_hint + RADIX_BITS - 1) / RADIX_BITS;
-        for (int p = 0; p < passes; ++p) {
-            int shift = p * RADIX_BITS;
-            uint32_t *ki = d_keys[final_buf].as<uint32_t>(), *vi = d_vals[final_buf].as<uint32_t>();
-            uint32_t *ko = d_keys[final_buf ^ 1].as<uint32_t>(), *vo = d_vals[final_buf ^ 1].as<uint32_t>();
-            radix_hist_kernel<<<nt, SORT_THREADS, 0, st>>>(ki, tiles, segs, d_tilehist.as<uint32_t>(), shift, sc);
-            B2_LAUNCH_CHECK();
-            radix_scan_kernel<<<nB * (RADIX / (SORT_THREADS / 32)), SORT_THREADS, 0, st>>>(segs, d_tilehist.as<uint32_t>(), d_binbase.as<uint32_t>(), shift, sc);
-            B2_LAUNCH_CHECK();
-            radix_scatter_kernel<<<nt, SORT_THREADS, 0, st>>>(ki, vi, ko, vo, tiles, segs, d_tilehist.as<uint32_t>(),
-                                                             d_binbase.as<uint32_t>(), shift, sc);
-            B2_LAUNCH_CHECK();
-            final_buf ^= 1;
-        }
-        head_kernel<false><<<nt, SORT_THREADS, 0, st>>>(sorted_keys(), tiles, segs, lay, d_tile_heads.as<uint32_t>(),
-                                                       nullptr, nullptr);
-        B2_LAUNCH_CHECK();
-    }
-    scan_tiles_kernel<<<1, 1024, 0, st>>>(d_tile_heads.as<uint32_t>(), nt, segs, nB, d_run_seg_off.as<uint32_t>(), sc);
-    B2_LAUNCH_CHECK();
-    if (nt) {
-        head_kernel<true><<<nt, SORT_THREADS, 0, st>>>(sorted_keys(), tiles, segs, lay, d_tile_heads.as<uint32_t>(),
-                                                      d_run_start.as<uint32_t>(), d_run_seg.as<uint32_t>());
-        B2_LAUNCH_CHECK();
-    }
-    return 0;
-}
-
-__global__ void prepared_layout_kernel(VoxLayout *layouts, uint32_t *scalars, uint32_t B, uint32_t invalid_key, int nbits) {
-    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s < B) {
-        VoxLayout L;
-        memset(&L, 0, sizeof(L));
-        L.ok = 1; L.ncells = invalid_key; L.nbits = nbits;
-        layouts[s] = L;
-    }
-    if (s == 0) { scalars[0] = (uint32_t)nbits; scalars[1] = 0u; }
+    int passes = 32 / RADIX_BITS;
+    if (nbits_hint > 0) passes = (nbits_hint + RADIX_BITS - 1) / RADIX_BITS;
+    return sort_and_runs(passes, st);
 }
 
 int VoxPipeline::run_prepared(uint32_t invalid_key, int nbits, cudaStream_t st) {
     const uint32_t nB = (uint32_t)B, nt = (uint32_t)ntiles;
     uint32_t *sc = d_scalars.as<uint32_t>();
-    const TileDesc *tiles = d_tiles.as<TileDesc>();
-    const SegDesc *segs = d_segs.as<SegDesc>();
     VoxLayout *lay = d_layouts.as<VoxLayout>();
-    prepared_layout_kernel<<<(nB + 127) / 128, 128, 0, st>>>(lay, sc, nB, invalid_key, nbits);
-    B2_LAUNCH_CHECK();
-    final_buf = 0;
-    if (nt) {
-        const int passes = (nbits + RADIX_BITS - 1) / RADIX_BITS;
-        for (int p = 0; p < passes; ++p) {
-            int shift = p * RADIX_BITS;
-            uint32_t *ki = d_keys[final_buf].as<uint32_t>(), *vi = d_vals[final_buf].as<uint32_t>();
-            uint32_t *ko = d_keys[final_buf ^ 1].as<uint32_t>(), *vo = d_vals[final_buf ^ 1].as<uint32_t>();
-            radix_hist_kernel<<<nt, SORT_THREADS, 0, st>>>(ki, tiles, segs, d_tilehist.as<uint32_t>(), shift, sc);
-            B2_LAUNCH_CHECK();
-            radix_scan_kernel<<<nB * (RADIX / (SORT_THREADS / 32)), SORT_THREADS, 0, st>>>(segs, d_tilehist.as<uint32_t>(), d_binbase.as<uint32_t>(), shift, sc);
-            B2_LAUNCH_CHECK();
-            radix_scatter_kernel<<<nt, SORT_THREADS, 0, st>>>(ki, vi, ko, vo, tiles, segs, d_tilehist.as<uint32_t>(),
-                                                             d_binbase.as<uint32_t>(), shift, sc);
-            B2_LAUNCH_CHECK();
-            final_buf ^= 1;
-        }
-        head_kernel<false><<<nt, SORT_THREADS, 0, st>>>(sorted_keys(), tiles, segs, lay, d_tile_heads.as<uint32_t>(), nullptr, nullptr);
+    if (nt == 0) {
+        empty_plan_kernel<<<(nB + 1 + 127) / 128, 128, 0, st>>>(lay, sc, d_run_seg_off.as<uint32_t>(), nB, 1.f, 1.f, 1.f);
         B2_LAUNCH_CHECK();
+        return 0;
     }
-    scan_tiles_kernel<<<1, 1024, 0, st>>>(d_tile_heads.as<uint32_t>(), nt, segs, nB, d_run_seg_off.as<uint32_t>(), sc);
+    const PlanView P = plan_view();
+    prepared_layout_kernel<<<(nB * 4 * RADIX + 255) / 256 < 64 ? (nB * 4 * RADIX + 255) / 256 : 64, 256, 0, st>>>(
+        lay, sc, d_hist.as<uint32_t>(), nB * 4 * RADIX, nB, invalid_key, nbits);
     B2_LAUNCH_CHECK();
-    if (nt) {
-        head_kernel<true><<<nt, SORT_THREADS, 0, st>>>(sorted_keys(), tiles, segs, lay, d_tile_heads.as<uint32_t>(),
-                                                      d_run_start.as<uint32_t>(), d_run_seg.as<uint32_t>());
-        B2_LAUNCH_CHECK();
-    }
-    return 0;
+    key_hist_kernel<false><<<nt, SORT_THREADS, 0, st>>>(nullptr, P, lay, d_keys[0].as<uint32_t>(), d_hist.as<uint32_t>(),
+                                                       d_state.as<uint32_t>(), sc);
+    B2_LAUNCH_CHECK();
+    return sort_and_runs((nbits + RADIX_BITS - 1) / RADIX_BITS, st);
 }
 
 void VoxPipeline::release() {
-    d_tiles.release(); d_segs.release(); d_bbox.release(); d_layouts.release(); d_scalars.release();
+    d_tiles.release(); d_segs.release(); d_layouts.release(); d_scalars.release(); d_hist.release();
     for (int i = 0; i < 2; ++i) { d_keys[i].release(); d_vals[i].release(); }
-    d_tilehist.release(); d_binbase.release(); d_tile_heads.release();
+    d_bbox_part.release(); d_state.release();
     d_run_start.release(); d_run_seg.release(); d_run_seg_off.release();
+    scalars_ready = false;
 }
 
 // ------------------------------------------------------------------ voxel filter ------------
-// One warp per occupied voxel.  Lanes gather 32 member points at a time (in stable, i.e. input,
-// order) and every lane then folds them in sequentially through shuffles, so the float centroid is the
-// same left-to-right float sum pcl::VoxelGrid forms for that member order.
-__global__ void __launch_bounds__(256) vf_centroid_kernel(const float4 *__restrict__ pts,
-                                                          const uint32_t *__restrict__ keys,
-                                                          const uint32_t *__restrict__ vals,
+// Centroid of every occupied voxel = the float sum of its member points in input order (the stable sort keeps it),
+// formed left to right exactly as pcl::VoxelGrid does for that member order, then divided by the count.
+//   vf_centroid_kernel: a warp takes 32 consecutive voxels; a voxel of up to VF_SEQ points is folded by ONE lane
+//     (32 voxels in parallel, gathers four deep); crowded voxels are only appended to a work list;
+//   vf_crowded_kernel: one warp per crowded voxel: the lanes gather 128 members at a time, two groups ahead of the
+//     fold (index load -> point load -> fold are software-pipelined), every lane folds them through shuffles, so the
+//     cost is the order-exact add chain itself (4 cycles per member).
+// Output in ascending voxel index.
+constexpr uint32_t VF_SEQ = 32;
+
+__device__ __forceinline__ void run_bounds(uint32_t j, const uint32_t *__restrict__ run_start, const uint32_t *__restrict__ run_seg,
+                                           const uint32_t *__restrict__ run_seg_off, const PlanView &P,
+                                           const VoxLayout *__restrict__ layouts, uint32_t &s, uint32_t &e) {
+    const uint32_t sg = run_seg[j];
+    s = run_start[j];
+    e = (j + 1 < run_seg_off[sg + 1]) ? run_start[j + 1] : get_seg(P, sg).begin + layouts[sg].n_finite;
+}
+
+__global__ void __launch_bounds__(256) vf_centroid_kernel(const float4 *__restrict__ pts, SortView sv,
                                                           const uint32_t *__restrict__ run_start,
                                                           const uint32_t *__restrict__ run_seg,
-                                                          const uint32_t *__restrict__ run_seg_off,
-                                                          const SegDesc *__restrict__ segs,
-                                                          const VoxLayout *__restrict__ layouts,
-                                                          const uint32_t *__restrict__ scalars,
+                                                          const uint32_t *__restrict__ run_seg_off, PlanView P,
+                                                          const VoxLayout *__restrict__ layouts, uint32_t *__restrict__ crowded,
+                                                          uint32_t *__restrict__ n_crowded,
                                                           float4 *__restrict__ out, int32_t *__restrict__ out_idx,
                                                           int32_t *__restrict__ out_cnt) {
-    const uint32_t total = scalars[1];
+    const uint32_t total = sv.scalars[1];
+    const uint32_t *__restrict__ keys = sv.keys();
+    const uint32_t *__restrict__ vals = sv.vals();
     const int l = threadIdx.x & 31;
-    for (uint32_t j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < total; j += (gridDim.x * blockDim.x) >> 5) {
-        const uint32_t sg = run_seg[j];
-        const uint32_t s = run_start[j];
-        const uint32_t e = (j + 1 < run_seg_off[sg + 1]) ? run_start[j + 1] : segs[sg].begin + layouts[sg].n_finite;
-        float ax = 0.f, ay = 0.f, az = 0.f, ai = 0.f;
-        for (uint32_t c = s; c < e; c += 32) {
-            float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (c + l < e) p = __ldg(&pts[vals[c + l]]);
-            const int m = (e - c < 32u) ? (int)(e - c) : 32;
-            if (m == 32) {
-                // full chunk: all 128 shuffles are independent of the four add chains, so the fold costs
-                // ~one FADD latency per member (crowded voxels hold thousands of points)
-#pragma unroll
-                for (int k = 0; k < 32; ++k) {
-                    ax = __fadd_rn(ax, __shfl_sync(0xffffffffu, p.x, k));
-                    ay = __fadd_rn(ay, __shfl_sync(0xffffffffu, p.y, k));
-                    az = __fadd_rn(az, __shfl_sync(0xffffffffu, p.z, k));
-                    ai = __fadd_rn(ai, __shfl_sync(0xffffffffu, p.w, k));
-                }
-            } else {
-                for (int k = 0; k < m; ++k) {
-                    ax = __fadd_rn(ax, __shfl_sync(0xffffffffu, p.x, k));
-                    ay = __fadd_rn(ay, __shfl_sync(0xffffffffu, p.y, k));
-                    az = __fadd_rn(az, __shfl_sync(0xffffffffu, p.z, k));
-                    ai = __fadd_rn(ai, __shfl_sync(0xffffffffu, p.w, k));
-                }
+    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    // consecutive groups of 32 voxels go to different CTAs (a small cloud still spreads over the SMs)
+    for (uint32_t j0 = ((threadIdx.x >> 5) * gridDim.x + blockIdx.x) * 32u; j0 < total; j0 += nwarps * 32u) {
+        const uint32_t j = j0 + l;
+        const bool valid = j < total;
+        uint32_t s = 0, e = 0;
+        if (valid) run_bounds(j, run_start, run_seg, run_seg_off, P, layouts, s, e);
+        const uint32_t len = e - s;
+        const bool is_crowded = len > VF_SEQ;
+        {
+            const uint32_t m = __ballot_sync(0xffffffffu, is_crowded);
+            if (m) {
+                uint32_t base = 0;
+                if (l == 0) base = atomicAdd(n_crowded, (uint32_t)__popc(m));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (is_crowded) crowded[base + __popc(m & ((1u << l) - 1u))] = j;
             }
         }
-        if (l == 0) {
-            const float n = (float)(e - s);
+        if (valid && !is_crowded) {
+            float ax = 0.f, ay = 0.f, az = 0.f, ai = 0.f;
+            uint32_t k = s;
+            for (; k + 4 <= e; k += 4) {
+                const uint32_t v0 = vals[k], v1 = vals[k + 1], v2 = vals[k + 2], v3 = vals[k + 3];
+                const float4 p0 = __ldg(&pts[v0]), p1 = __ldg(&pts[v1]), p2 = __ldg(&pts[v2]), p3 = __ldg(&pts[v3]);
+                ax = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(ax, p0.x), p1.x), p2.x), p3.x);
+                ay = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(ay, p0.y), p1.y), p2.y), p3.y);
+                az = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(az, p0.z), p1.z), p2.z), p3.z);
+                ai = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(ai, p0.w), p1.w), p2.w), p3.w);
+            }
+            for (; k < e; ++k) {
+                const float4 p = __ldg(&pts[vals[k]]);
+                ax = __fadd_rn(ax, p.x); ay = __fadd_rn(ay, p.y); az = __fadd_rn(az, p.z); ai = __fadd_rn(ai, p.w);
+            }
+            const float n = (float)len;
             out[j] = make_float4(__fdiv_rn(ax, n), __fdiv_rn(ay, n), __fdiv_rn(az, n), __fdiv_rn(ai, n));
+            if (out_idx) out_idx[j] = (int32_t)keys[s];
+            if (out_cnt) out_cnt[j] = (int32_t)len;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) vf_crowded_kernel(const float4 *__restrict__ pts, SortView sv,
+                                                         const uint32_t *__restrict__ run_start,
+                                                         const uint32_t *__restrict__ run_seg,
+                                                         const uint32_t *__restrict__ run_seg_off, PlanView P,
+                                                         const VoxLayout *__restrict__ layouts, const uint32_t *__restrict__ crowded,
+                                                         const uint32_t *__restrict__ n_crowded,
+                                                         float4 *__restrict__ out, int32_t *__restrict__ out_idx,
+                                                         int32_t *__restrict__ out_cnt) {
+    const uint32_t n = *n_crowded;
+    const uint32_t *__restrict__ keys = sv.keys();
+    const uint32_t *__restrict__ vals = sv.vals();
+    const int l = threadIdx.x & 31;
+    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t i = (threadIdx.x >> 5) * gridDim.x + blockIdx.x; i < n; i += nwarps) {
+        const uint32_t j = crowded[i];
+        uint32_t s, e;
+        run_bounds(j, run_start, run_seg, run_seg_off, P, layouts, s, e);
+        uint32_t va[4], vb[4];
+        float4 pa[4], pb[4];
+        auto ldv = [&](uint32_t c, uint32_t (&v)[4]) {
+#pragma unroll
+            for (int d = 0; d < 4; ++d) { const uint32_t idx = c + d * 32 + l; v[d] = (idx < e) ? __ldg(&vals[idx]) : 0xFFFFFFFFu; }
+        };
+        auto ldp = [&](const uint32_t (&v)[4], float4 (&p)[4]) {
+#pragma unroll
+            for (int d = 0; d < 4; ++d) p[d] = (v[d] != 0xFFFFFFFFu) ? __ldg(&pts[v[d]]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        };
+        float ax = 0.f, ay = 0.f, az = 0.f, ai = 0.f;
+        auto fold = [&](const float4 (&p)[4], uint32_t c) {
+#pragma unroll
+            for (int d = 0; d < 4; ++d) {
+                const uint32_t c0 = c + d * 32;
+                if (c0 >= e) break;
+                const int m = (e - c0 < 32u) ? (int)(e - c0) : 32;
+                if (m == 32) {
+#pragma unroll
+                    for (int k = 0; k < 32; ++k) {
+                        ax = __fadd_rn(ax, __shfl_sync(0xffffffffu, p[d].x, k));
+                        ay = __fadd_rn(ay, __shfl_sync(0xffffffffu, p[d].y, k));
+                        az = __fadd_rn(az, __shfl_sync(0xffffffffu, p[d].z, k));
+                        ai = __fadd_rn(ai, __shfl_sync(0xffffffffu, p[d].w, k));
+                    }
+                } else {
+                    for (int k = 0; k < m; ++k) {
+                        ax = __fadd_rn(ax, __shfl_sync(0xffffffffu, p[d].x, k));
+                        ay = __fadd_rn(ay, __shfl_sync(0xffffffffu, p[d].y, k));
+                        az = __fadd_rn(az, __shfl_sync(0xffffffffu, p[d].z, k));
+                        ai = __fadd_rn(ai, __shfl_sync(0xffffffffu, p[d].w, k));
+                    }
+                }
+            }
+        };
+        // group g is folded while the points of g+1 and the indices of g+2 are in flight
+        ldv(s, va);
+        ldv(s + 128u, vb);
+        ldp(va, pa);
+        for (uint32_t c = s; c < e; c += 256u) {
+            ldp(vb, pb);
+            ldv(c + 256u, va);
+            fold(pa, c);
+            if (c + 128u >= e) break;
+            ldp(va, pa);
+            ldv(c + 384u, vb);
+            fold(pb, c + 128u);
+        }
+        if (l == 0) {
+            const float nn = (float)(e - s);
+            out[j] = make_float4(__fdiv_rn(ax, nn), __fdiv_rn(ay, nn), __fdiv_rn(az, nn), __fdiv_rn(ai, nn));
             if (out_idx) out_idx[j] = (int32_t)keys[s];
             if (out_cnt) out_cnt[j] = (int32_t)(e - s);
         }
@@ -653,7 +815,7 @@ struct b2vf {
     float leaf[3];
     cudaStream_t own = nullptr, st = nullptr;
     VoxPipeline pipe;
-    DevBuf d_in, d_out, d_idx, d_cnt;
+    DevBuf d_in, d_out, d_idx, d_cnt, d_crowded;
     PinBuf h_in, h_out, h_idx, h_cnt, h_misc;
 };
 
@@ -707,7 +869,7 @@ extern "C" void b2vf_destroy(b2vf *h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->st);
     h->pipe.release();
-    h->d_in.release(); h->d_out.release(); h->d_idx.release(); h->d_cnt.release();
+    h->d_in.release(); h->d_out.release(); h->d_idx.release(); h->d_cnt.release(); h->d_crowded.release();
     h->h_in.release(); h->h_out.release(); h->h_idx.release(); h->h_cnt.release(); h->h_misc.release();
     if (h->own) cudaStreamDestroy(h->own);
     delete h;
@@ -721,13 +883,18 @@ extern "C" int b2vf_set_stream(b2vf *h, void *stream) {
 
 static int vf_launch_centroids(b2vf *h, const float4 *d_in, float4 *d_out, int32_t *d_idx, int32_t *d_cnt, size_t n) {
     if (n == 0) return 0;
-    // enough warps for every voxel of a typical cloud, grid-stride beyond that; multiple of 148 SMs
-    unsigned blocks = (unsigned)((n / 8 + 7) / 8);
+    int rc;
+    if ((rc = h->d_crowded.reserve((n / VF_SEQ + 64) * 4))) return rc;
+    // a warp takes 32 voxels at a time; enough warps for a typical cloud, grid-stride beyond that; multiple of 148 SMs
+    unsigned blocks = (unsigned)((n / 256 + 147) / 148) * 148u;
     if (blocks < 148) blocks = 148;
     if (blocks > 148 * 16) blocks = 148 * 16;
-    vf_centroid_kernel<<<blocks, 256, 0, h->st>>>(d_in, h->pipe.sorted_keys(), h->pipe.sorted_vals(), h->pipe.run_start(),
-                                                 h->pipe.run_seg(), h->pipe.run_seg_off(), h->pipe.d_segs.as<SegDesc>(),
-                                                 h->pipe.layouts(), h->pipe.scalars(), d_out, d_idx, d_cnt);
+    uint32_t *ncr = const_cast<uint32_t *>(h->pipe.scalars()) + 10;
+    vf_centroid_kernel<<<blocks, 256, 0, h->st>>>(d_in, h->pipe.view(), h->pipe.run_start(), h->pipe.run_seg(), h->pipe.run_seg_off(),
+                                                 h->pipe.plan_view(), h->pipe.layouts(), h->d_crowded.as<uint32_t>(), ncr, d_out, d_idx, d_cnt);
+    B2_LAUNCH_CHECK();
+    vf_crowded_kernel<<<148 * 4, 256, 0, h->st>>>(d_in, h->pipe.view(), h->pipe.run_start(), h->pipe.run_seg(), h->pipe.run_seg_off(),
+                                                 h->pipe.plan_view(), h->pipe.layouts(), h->d_crowded.as<uint32_t>(), ncr, d_out, d_idx, d_cnt);
     B2_LAUNCH_CHECK();
     return 0;
 }
@@ -741,7 +908,7 @@ extern "C" int b2vf_filter(b2vf *h, const void *in, size_t n, size_t stride, siz
     if (stride < 16 || ioff + 4 > stride || out_stride < 16 || out_ioff + 4 > out_stride || ((stride | ioff | out_stride | out_ioff) & 3)) {
         set_error("b2vf_filter: bad stride / intensity offset"); return B2_ERR_INVALID;
     }
-    if (n >= 0xFFFFFFF0ull) { set_error("b2vf_filter: cloud too large"); return B2_ERR_INVALID; }
+    if (n >= B2_MAX_POINTS) { set_error("b2vf_filter: cloud too large"); return B2_ERR_INVALID; }
     B2_CUDA(cudaSetDevice(h->device));
     int rc;
     if ((rc = h->h_in.reserve(n * 16))) return rc;

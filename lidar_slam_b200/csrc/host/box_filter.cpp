@@ -3,6 +3,8 @@
 
 #include <cstdlib>
 #include <iostream>
+#include <stdexcept>
+#include <string>
 
 namespace lidar_localization {
 namespace {
@@ -15,8 +17,14 @@ constexpr std::size_t kIntensityOffset = 16;
 }  // namespace
 
 BoxFilter::BoxFilter() : origin_(3, 0.f), size_(6, 0.f), edge_(6, 0.f) {
-    if (b2cloud_create(DefaultDevice(), &in_) != B2_OK || b2cloud_create(DefaultDevice(), &out_) != B2_OK)
-        std::cerr << "[BoxFilter] " << b2_last_error() << std::endl;
+    if (b2cloud_create(DefaultDevice(), &in_) != B2_OK || b2cloud_create(DefaultDevice(), &out_) != B2_OK) {
+        // no CPU fallback: construction fails hard instead of leaving a filter that returns untouched clouds
+        const std::string why = std::string("[BoxFilter] ") + b2_last_error();
+        std::cerr << why << std::endl;
+        b2cloud_destroy(in_); b2cloud_destroy(out_);
+        in_ = out_ = nullptr;
+        throw std::runtime_error(why);
+    }
 }
 
 BoxFilter::BoxFilter(const std::vector<float>& size) : BoxFilter() { SetSize(size); }
@@ -42,7 +50,9 @@ bool BoxFilter::Filter(const CloudData::CLOUD_PTR& input_cloud_ptr, CloudData::C
         b2cloud_box_filter(in_, edge_.data(), out_) != B2_OK ||
         b2cloud_download(out_, tmp_.data(), n, kStride, kIntensityOffset, &m) != B2_OK) {
         std::cerr << "[BoxFilter::Filter] " << b2_last_error() << std::endl;
-        return true;
+        output_cloud_ptr->points.clear();          // engine failure: defined (empty) output, reported
+        output_cloud_ptr->width = 0; output_cloud_ptr->height = 1;
+        return false;
     }
     CloudData::CLOUD& out = *output_cloud_ptr;     // output_cloud_ptr->clear() + filter, as the reference
     out.points.assign(tmp_.begin(), tmp_.begin() + m);
@@ -53,8 +63,10 @@ bool BoxFilter::Filter(const CloudData::CLOUD_PTR& input_cloud_ptr, CloudData::C
 }
 
 bool BoxFilter::FilterDevice(b2cloud* input, b2cloud* output) {
-    if (b2cloud_box_filter(input, edge_.data(), output) != B2_OK)
+    if (b2cloud_box_filter(input, edge_.data(), output) != B2_OK) {
         std::cerr << "[BoxFilter::FilterDevice] " << b2_last_error() << std::endl;
+        return false;
+    }
     return true;
 }
 

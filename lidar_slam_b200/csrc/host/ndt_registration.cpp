@@ -4,6 +4,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <iostream>
+#include <stdexcept>
+#include <string>
 
 namespace lidar_localization {
 namespace {
@@ -39,9 +41,14 @@ bool NDTRegistration::SetRegistrationParam(float res, float step_size, float tra
     p.step_size = step_size;   // float -> double exactly as pcl::NDT::setStepSize(double) receives it
     p.trans_eps = trans_eps;
     p.max_iter = max_iter;
+    if (ndt_) { b2ndt_destroy(ndt_); ndt_ = nullptr; }
     if (b2ndt_create(&p, DefaultDevice(), &ndt_) != B2_OK) {
-        std::cerr << "[NDTRegistration] " << b2_last_error() << std::endl;
+        // there is no CPU fallback behind this class: an object without an engine would hand stale poses to the
+        // front end, so construction fails hard (the reference's PCL constructor cannot fail this way)
         ndt_ = nullptr;
+        const std::string why = std::string("[NDTRegistration] ") + b2_last_error();
+        std::cerr << why << std::endl;
+        throw std::runtime_error(why);
     }
     std::cout << "NDT params: res: " << res << ", step_size: " << step_size << ", trans_eps: " << trans_eps
               << ", max_iter: " << max_iter << std::endl;
@@ -49,8 +56,10 @@ bool NDTRegistration::SetRegistrationParam(float res, float step_size, float tra
 }
 
 bool NDTRegistration::SetInputTarget(const CloudData::CLOUD_PTR& input_target) {
-    if (ndt_ && b2ndt_set_target(ndt_, input_target->points.data(), input_target->points.size(), kStride, kIntensityOffset) != B2_OK)
+    if (!ndt_ || b2ndt_set_target(ndt_, input_target->points.data(), input_target->points.size(), kStride, kIntensityOffset) != B2_OK) {
         std::cerr << "[NDTRegistration::SetInputTarget] " << b2_last_error() << std::endl;
+        return false;   // engine failure (device lost, out of memory): PCL cannot fail here, so this is reported
+    }
     return true;
 }
 
@@ -59,9 +68,14 @@ bool NDTRegistration::ScanMatch(const CloudData::CLOUD_PTR& input_source, const 
     const std::size_t n = input_source->points.size();
     float pose[16];
     std::memcpy(pose, predict_pose.data(), sizeof(pose));
-    if (!ndt_ || b2ndt_align(ndt_, input_source->points.data(), n, kStride, kIntensityOffset, predict_pose.data(), pose, &last_) != B2_OK) {
+    const bool ok = ndt_ && b2ndt_align(ndt_, input_source->points.data(), n, kStride, kIntensityOffset, predict_pose.data(), pose,
+                                        &last_) == B2_OK;
+    if (!ok) {
+        // engine failure: the outputs are still defined (pose = prediction, cloud = source moved by it) and the call
+        // reports false -- the reference's `return true` (ndt_registration.cpp:60) holds for PCL, which cannot fail
         std::cerr << "[NDTRegistration::ScanMatch] " << b2_last_error() << std::endl;
-        return true;   // the reference wrapper never reports failure either (ndt_registration.cpp:60)
+        std::memcpy(pose, predict_pose.data(), sizeof(pose));
+        std::memset(&last_, 0, sizeof(last_));
     }
     std::memcpy(result_pose.data(), pose, sizeof(pose));
     // align(output): the source transformed by the final pose, float arithmetic of pcl::transformPointCloud
@@ -83,12 +97,14 @@ bool NDTRegistration::ScanMatch(const CloudData::CLOUD_PTR& input_source, const 
             out.points[i] = o;
         }
     }
-    return true;
+    return ok;
 }
 
 bool NDTRegistration::SetInputTargetDevice(b2cloud* input_target) {
-    if (!ndt_ || b2ndt_set_target_cloud(ndt_, input_target) != B2_OK)
+    if (!ndt_ || b2ndt_set_target_cloud(ndt_, input_target) != B2_OK) {
         std::cerr << "[NDTRegistration::SetInputTargetDevice] " << b2_last_error() << std::endl;
+        return false;
+    }
     return true;
 }
 
@@ -97,7 +113,9 @@ bool NDTRegistration::ScanMatchDevice(b2cloud* input_source, const Eigen::Matrix
     float pose[16];
     if (!ndt_ || b2ndt_align_cloud(ndt_, input_source, predict_pose.data(), pose, &last_, result_cloud) != B2_OK) {
         std::cerr << "[NDTRegistration::ScanMatchDevice] " << b2_last_error() << std::endl;
-        return true;
+        std::memcpy(result_pose.data(), predict_pose.data(), sizeof(pose));
+        std::memset(&last_, 0, sizeof(last_));
+        return false;
     }
     std::memcpy(result_pose.data(), pose, sizeof(pose));
     return true;

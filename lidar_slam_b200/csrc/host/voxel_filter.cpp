@@ -3,6 +3,8 @@
 
 #include <cstdlib>
 #include <iostream>
+#include <stdexcept>
+#include <string>
 #include <vector>
 
 namespace lidar_localization {
@@ -28,9 +30,13 @@ VoxelFilter::VoxelFilter(float leaf_size_x, float leaf_size_y, float leaf_size_z
 VoxelFilter::~VoxelFilter() { b2vf_destroy(vf_); }
 
 bool VoxelFilter::SetFilterParam(float leaf_size_x, float leaf_size_y, float leaf_size_z) {
+    if (vf_) { b2vf_destroy(vf_); vf_ = nullptr; }
     if (b2vf_create(leaf_size_x, leaf_size_y, leaf_size_z, DefaultDevice(), &vf_) != B2_OK) {
-        std::cerr << "[VoxelFilter] " << b2_last_error() << std::endl;
+        // no CPU fallback: a filter without an engine would return untouched clouds, so construction fails hard
         vf_ = nullptr;
+        const std::string why = std::string("[VoxelFilter] ") + b2_last_error();
+        std::cerr << why << std::endl;
+        throw std::runtime_error(why);
     }
     std::cout << "Voxel Filter params: " << leaf_size_x << ", " << leaf_size_y << ", " << leaf_size_z << std::endl;
     return true;
@@ -44,8 +50,11 @@ bool VoxelFilter::Filter(const CloudData::CLOUD_PTR& input_cloud_ptr, CloudData:
     std::size_t m = 0;
     if (!vf_ || b2vf_filter(vf_, input_cloud_ptr->points.data(), n, kStride, kIntensityOffset, tmp_.data(), n, kStride,
                             kIntensityOffset, &m, nullptr, nullptr) != B2_OK) {
+        // engine failure: PCL cannot fail here; define the output (a copy of the input, what pcl::VoxelGrid itself
+        // emits when it gives up) and report false
         std::cerr << "[VoxelFilter::Filter] " << b2_last_error() << std::endl;
-        return true;
+        if (filtered_cloud_ptr.get() != input_cloud_ptr.get()) *filtered_cloud_ptr = *input_cloud_ptr;
+        return false;
     }
     CloudData::CLOUD& out = *filtered_cloud_ptr;
     out.points.assign(tmp_.begin(), tmp_.begin() + m);
@@ -55,8 +64,10 @@ bool VoxelFilter::Filter(const CloudData::CLOUD_PTR& input_cloud_ptr, CloudData:
     return true;
 }
 bool VoxelFilter::FilterDevice(b2cloud* input, b2cloud* output) {
-    if (!vf_ || b2vf_filter_cloud(vf_, input, output) != B2_OK)
+    if (!vf_ || b2vf_filter_cloud(vf_, input, output) != B2_OK) {
         std::cerr << "[VoxelFilter::FilterDevice] " << b2_last_error() << std::endl;
+        return false;
+    }
     return true;
 }
 }  // namespace lidar_localization

@@ -57,9 +57,12 @@ class Scene:
         self.leg = leg
 
     def __del__(self):
-        if getattr(self, "h", None):
-            _lib().synth_scene_free(self.h)
-            self.h = None
+        h, self.h = getattr(self, "h", None), None
+        if h:
+            try:
+                _lib().synth_scene_free(h)
+            except Exception:       # interpreter shutdown: module globals may already be gone
+                pass
 
     @property
     def path_length(self):

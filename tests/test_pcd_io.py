@@ -193,8 +193,25 @@ def test_hostile_headers_are_errors_not_crashes(tmp_path):
         b"VERSION 0.7\nFIELDS x y z\nSIZE 4 4 4\nTYPE F F F\nCOUNT 1 1 1\nWIDTH 2\nHEIGHT 1\nPOINTS 2\nDATA binary_compressed\n"
         + struct.pack("<II", 0xFFFFFFF0, 24) + b"\x00" * 16,
         b"VERSION 0.7\nFIELDS x y z\nSIZE 4 4 3\nTYPE F F F\nCOUNT 1 1 1\nWIDTH 1\nHEIGHT 1\nPOINTS 1\nDATA binary\n" + b"\0" * 16,
+        # TYPE F with SIZE 1 / 2 would make the reader fetch 8 bytes from a 2-byte field (past the record)
+        b"VERSION 0.7\nFIELDS x y z\nSIZE 2 2 2\nTYPE F F F\nCOUNT 1 1 1\nWIDTH 1\nHEIGHT 1\nPOINTS 1\nDATA binary\n" + b"\0" * 6,
+        b"VERSION 0.7\nFIELDS x y z\nSIZE 1 1 1\nTYPE F F F\nCOUNT 1 1 1\nWIDTH 1\nHEIGHT 1\nPOINTS 1\nDATA binary\n" + b"\0" * 3,
+        b"VERSION 0.7\nFIELDS x y z\nSIZE 4 4 4\nTYPE F Q F\nCOUNT 1 1 1\nWIDTH 1\nHEIGHT 1\nPOINTS 1\nDATA binary\n" + b"\0" * 12,
     ]
     for blob in cases:
         p.write_bytes(blob)
         with pytest.raises(capi.B2Error):
             capi.pcd_read(str(p))
+
+
+def test_direct_path_needs_four_float32_fields_and_long_ascii_rows(tmp_path):
+    """SIZE 8 4 2 2 also has a 16-byte record but is not x,y,z,intensity float32: it must take the per-field path;
+    an ascii row longer than the reader's line buffer stays ONE point."""
+    p = tmp_path / "m.pcd"
+    rec = struct.pack("<dfhH", 1.5, 2.5, -3, 7)
+    p.write_bytes(b"VERSION 0.7\nFIELDS x y z intensity\nSIZE 8 4 2 2\nTYPE F F I U\nCOUNT 1 1 1 1\nWIDTH 2\nHEIGHT 1\nPOINTS 2\nDATA binary\n" + rec * 2)
+    assert np.array_equal(capi.pcd_read(str(p)), np.array([[1.5, 2.5, -3.0, 7.0]] * 2, np.float32))
+    pad = " ".join(["0"] * 3000)
+    p.write_bytes(("VERSION 0.7\nFIELDS x y z pad\nSIZE 4 4 4 4\nTYPE F F F F\nCOUNT 1 1 1 3000\nWIDTH 2\nHEIGHT 1\nPOINTS 2\nDATA ascii\n"
+                   "1 2 3 %s\n4 5 6 %s\n" % (pad, pad)).encode())
+    assert np.array_equal(capi.pcd_read(str(p))[:, :3], np.array([[1, 2, 3], [4, 5, 6]], np.float32))
