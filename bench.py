@@ -15,7 +15,15 @@ NDTRegistration::ScanMatch (step 0.1, eps 0.01, iter 30) for every frame.
   roofline  the dominant kernel (ndt_match_kernel): algorithmic bytes / event time / measured HBM peak.
   cpu_baseline  the CPU oracle (restatement of pcl::NDT 1.7; PCL is not installable here) on a bounded sample.
 
-`--impl reference` times that CPU implementation alone on all host threads (rank 0 only).
+  strong    the same batch as BASELINE.json states config 4: `--frames` frames IN TOTAL, block-sharded over the ranks
+            (measured in every run beside the weak-scaling headline; `--scaling strong` makes it the headline)
+  config5   one scan x 1024 initial-pose hypotheses sharded over the ranks, best-fit gather (all_gather of one row per
+            rank) inside the timed region (`--workload config5` makes it the headline)
+  e2e_raw   raw scan -> pose: pinned raw 119 k-point frames -> H2D (double-buffered chunks) -> batched VoxelFilter on the
+            device (appended, no host round trip) -> one batched align -> poses D2H, all inside the timed region
+
+`--impl reference` times that CPU implementation alone on all host threads (rank 0 only), on a bounded sample of the
+SAME frames (same generator, same indices) the GPU arm matches.
 """
 import argparse
 import json
@@ -180,44 +188,59 @@ class ClockSampler:
         return out
 
 
-def build_workload(frames, seed_base, rank, world, map_points, nthreads, gen_filter):
-    """-> scene, map (N,4), list of filtered sources, truth poses (frames,6), guesses (frames,4,4)."""
+def build_workload(frames, seed_base, rank, world, map_points, nthreads, gen_filter, select=None, keep_raw=0):
+    """The `frames` frames of rank `rank` (of `world`): frame k sits at arclength s along the drive, ranks interleave so
+    every rank covers the whole map; guess = truth + perturbation (seed 4000 + rank).  `select` (indices into those
+    frames) generates only a subset of the SAME frames (the CPU arm's bounded sample).  The first `keep_raw` raw scans
+    are kept (for the raw-scan end-to-end measurement).
+    -> scene, map (N,4), list of filtered sources, truth poses (n,6), guesses (n,4,4), raw point count, kept raw scans"""
     from lidar_slam_b200 import synth
     scene = synth.Scene(leg=500.0)
     target = scene.make_map(map_points, 2.0)
     plen = scene.path_length
-    # frame k of rank r sits at arclength s along the drive; ranks interleave so every rank covers the whole map
     gidx = np.arange(frames) * world + rank
     s = 5.0 + (plen - 10.0) * (gidx + 0.5) / (frames * world)
-    truth = np.stack([scene.path_pose(v) for v in s])
     rng = np.random.default_rng(4000 + rank)
     pert = np.concatenate([rng.uniform(-0.5, 0.5, (frames, 3)), np.deg2rad(rng.uniform(-2.0, 2.0, (frames, 3)))], axis=1)
-    guesses = np.stack([synth.pose6_to_matrix(truth[k] + pert[k]).astype(np.float32) for k in range(frames)])
-    sources, raw_pts = [], 0
+    sel = np.arange(frames) if select is None else np.asarray(select, np.int64)
+    truth = np.stack([scene.path_pose(v) for v in s[sel]])
+    guesses = np.stack([synth.pose6_to_matrix(truth[i] + pert[k]).astype(np.float32) for i, k in enumerate(sel)])
+    sources, raw_pts, kept = [], 0, []
     chunk = 256
-    for c0 in range(0, frames, chunk):
-        ids = seed_base + gidx[c0:c0 + chunk]
+    for c0 in range(0, len(sel), chunk):
+        ids = seed_base + gidx[sel[c0:c0 + chunk]]
         raws = scene.scans(ids, truth[c0:c0 + chunk], nthreads=nthreads)
         raw_pts += sum(len(r) for r in raws)
+        if len(kept) < keep_raw:
+            kept += raws[:keep_raw - len(kept)]
         sources += gen_filter(raws)
-    return scene, target, sources, truth, guesses, raw_pts
+    return scene, target, sources, truth, guesses, raw_pts, kept
+
+
+def workload_name(frames, map_points):
+    """config.workload: the same string in both arms (the reference arm matches a sample of these frames)"""
+    return ("config4 batched scan-to-map NDT: %d HDL-64 frames/GPU (VoxelFilter 1.3 m) vs %d-pt map, res 1.0 step 0.1 "
+            "eps 0.01 iter 30, guesses = truth+U[0.5m,2deg]" % (frames, map_points))
 
 
 def run_reference(args, rank, world):
-    """CPU arm: the oracle (port of pcl::NDT 1.7 as the reference calls it) on all host threads."""
+    """CPU arm: the oracle (port of pcl::NDT 1.7 as the reference calls it) on all host threads, on a bounded sample
+    (evenly spaced) of the SAME frames rank 0 of the GPU arm matches."""
     if rank != 0:
         return
     from oracle import oracle as O
     O.build(ref=False)
     cores = os.cpu_count() or 1
-    per_step = max(cores * 2, 16)
-    frames = per_step
+    per_step = min(args.frames, max(cores * 2, 16))
+    select = np.linspace(0, args.frames - 1, per_step).astype(np.int64)
     t0 = time.time()
 
     def cpu_filter(raws):
         return [O.voxel_filter(r, FRAME_LEAF, FRAME_LEAF, FRAME_LEAF)[0] for r in raws]
 
-    scene, target, sources, truth, guesses, _ = build_workload(frames, 0x5EED0000, 0, 1, args.map_points, cores, cpu_filter)
+    scene, target, sources, truth, guesses, _, _ = build_workload(args.frames, 0x5EED0000, 0, max(1, args.gpus), args.map_points, cores,
+                                                                  cpu_filter, select=select)
+    frames = len(sources)
     grid = O.Grid(target, NDT["res"])
     prm = O.params(res=NDT["res"], step_size=f32(NDT["step_size"]), trans_eps=f32(NDT["trans_eps"]), max_iter=NDT["max_iter"])
     setup_s = time.time() - t0
@@ -239,13 +262,14 @@ def run_reference(args, rank, world):
     value = frames * args.steps / dt
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "config4 batched scan-to-map NDT: HDL-64 frames (VoxelFilter 1.3) vs %d-pt map, res 1.0 step 0.1 eps 0.01 iter 30"
-                   % len(target), "frames_per_step": frames, "mean_iterations": float(np.mean(its)),
+        "config": {"workload": workload_name(args.frames, len(target)), "frames_per_gpu": args.frames,
+                   "frames_per_step": frames, "mean_iterations": float(np.mean(its)),
                    "mean_source_points": float(np.mean([len(s) for s in sources])), "setup_s": setup_s},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": "%d frames per step, one oracle align per thread over %d threads" % (frames, cores)},
+                         "sample": "%d of the %d frames of rank 0 (evenly spaced) per step, one oracle align per thread over %d threads"
+                                   % (frames, args.frames, cores)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -258,10 +282,16 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--frames", type=int, default=4000, help="frames (matches) per GPU per step")
+    ap.add_argument("--frames", type=int, default=4000, help="frames (matches) per GPU per step (weak); in total (strong)")
     ap.add_argument("--map-points", type=int, default=1_000_000)
     ap.add_argument("--cpu-sample", type=int, default=48, help="frames of the CPU baseline sample (rank 0, N=1)")
-    ap.add_argument("--batch-cluster", type=int, default=1, help="CTAs per match in batch mode")
+    ap.add_argument("--batch-cluster", type=int, default=0, help="CTAs per match in batch mode (0 = chosen by batch size)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="headline: weak = --frames per GPU; strong = --frames in total, block-sharded (BASELINE config 4 as stated)")
+    ap.add_argument("--workload", default="config4", choices=["config4", "config5"],
+                    help="headline: config4 batched map matching; config5 = one scan x --hypotheses initial poses, best-fit gather")
+    ap.add_argument("--hypotheses", type=int, default=1024)
+    ap.add_argument("--raw-frames", type=int, default=512, help="raw frames per step of the raw-scan end-to-end measurement (0 = skip)")
     ap.add_argument("--profile-range", action="store_true",
                     help="bracket the timed device-resident steps with cudaProfilerStart/Stop (ncu --profile-from-start off)")
     args = ap.parse_args()
@@ -275,9 +305,13 @@ def main():
     if args.warmup < 3:
         args.warmup = 3
 
+    import ctypes as C
+
     import torch
     import torch.distributed as dist
-    from lidar_slam_b200 import capi
+    from lidar_slam_b200 import batch as shard
+    from lidar_slam_b200 import capi, synth
+    from lidar_slam_b200.callers import hypothesis_lattice
     from lidar_slam_b200.registration import DeviceCloud, NDTRegistration, VoxelFilter
 
     if not torch.cuda.is_available():
@@ -314,8 +348,16 @@ def main():
 
     nthreads = max(1, (os.cpu_count() or 1) // world)
     t_setup = time.time()
-    scene, target, sources, truth, guesses, raw_pts = build_workload(args.frames, 0x5EED0000, rank, world, args.map_points,
-                                                                     nthreads, gpu_filter)
+    # weak (default headline): --frames per rank.  strong headline: only this rank's block of the --frames frames is
+    # generated (contiguous block of the rank's own frame list, so the union over the ranks is --frames distinct frames)
+    strong_B = shard.shard_range(args.frames, rank, world)
+    strong_B = strong_B[1] - strong_B[0]
+    gen_frames = strong_B if (args.scaling == "strong" and args.workload == "config4") else args.frames
+    if args.workload == "config5":
+        gen_frames = min(args.frames, 64)
+    raw_keep = min(args.raw_frames, gen_frames) if args.workload == "config4" else 0
+    scene, target, sources, truth, guesses, raw_pts, raws_kept = build_workload(
+        args.frames, 0x5EED0000, rank, world, args.map_points, nthreads, gpu_filter, select=np.arange(gen_frames), keep_raw=raw_keep)
     B = len(sources)
     reg = NDTRegistration(NDT["res"], NDT["step_size"], NDT["trans_eps"], NDT["max_iter"], device=local_rank)
     reg.SetCluster(16, args.batch_cluster)      # single ScanMatch: up to 16 CTAs per match (the library picks by size)
@@ -338,16 +380,18 @@ def main():
 
     raw0 = scene.scan(0x5EED0000 + 17, truth[0])
     d_raw, d_filt, d_map = DeviceCloud(raw0, device=local_rank), DeviceCloud(device=local_rank), DeviceCloud(target, device=local_rank)
-    vf_ms = timed_ms(lambda: vf.FilterCloud(d_raw, d_filt))
-    tg_ms = timed_ms(lambda: reg.SetInputTargetCloud(d_map), reps=5)
+    l0 = capi.launches(); vf.FilterCloud(d_raw, d_filt); vf_launches = capi.launches() - l0
+    vf_ms = timed_ms(lambda: vf.FilterCloud(d_raw, d_filt), reps=20)
+    l0 = capi.launches(); reg.SetInputTargetCloud(d_map); tg_launches = capi.launches() - l0
+    tg_ms = timed_ms(lambda: reg.SetInputTargetCloud(d_map), reps=7)
     peak_hbm = measured_peaks()[0]
     vf_bytes = 16.0 * len(raw0) + 16.0 * len(d_filt)
     tg_bytes = 16.0 * len(target) + 80.0 * info["n_leaves"]
     resident = {
-        "voxel_filter_scan": {"n_in": len(raw0), "n_out": len(d_filt), "ms": vf_ms, "algorithmic_bytes": vf_bytes,
+        "voxel_filter_scan": {"n_in": len(raw0), "n_out": len(d_filt), "ms": vf_ms, "launches": vf_launches, "algorithmic_bytes": vf_bytes,
                               "GBps": vf_bytes / vf_ms / 1e6, "frac_of_hbm_peak": vf_bytes / vf_ms / 1e6 / peak_hbm,
-                              "note": "one call = ~17 launches + one 32-byte D2H of the count; latency-bound at this size"},
-        "set_target_map": {"n_points": len(target), "voxels": info["n_leaves"], "ms": tg_ms, "algorithmic_bytes": tg_bytes,
+                              "note": "wall clock of one call incl. its one sync (count D2H); launch-latency-bound at this size"},
+        "set_target_map": {"n_points": len(target), "voxels": info["n_leaves"], "ms": tg_ms, "launches": tg_launches, "algorithmic_bytes": tg_bytes,
                            "GBps": tg_bytes / tg_ms / 1e6, "frac_of_hbm_peak": tg_bytes / tg_ms / 1e6 / peak_hbm},
     }
     reg.SetInputTarget(target)       # back to the host-path target (identical grid)
@@ -368,52 +412,117 @@ def main():
 
     reg.SetStream(sptr)
 
-    def step_device():
-        reg.ScanMatchBatchDevice(d_src.data_ptr(), n_total, d_off.data_ptr(), B, d_guess.data_ptr(), d_pose.data_ptr(), d_res.data_ptr())
-
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---------------- device-resident timing -------------------------------------------------------------
+    def time_device(fn, steps, warmup):
+        """W warm-up + K timed steps of fn() on the stream: CUDA events per step, 256 MB L2 flush between steps.
+        -> (per-step ms, wall seconds incl. the flushes)"""
+        for _ in range(warmup):
+            flush.fill_(1.0)
+            fn()
+        barrier()
+        evs = []
+        barrier()
+        w0 = time.perf_counter()
+        for _ in range(steps):
+            flush.fill_(0.0)                      # L2 flush between timed steps (outside the event pair)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            fn()
+            e1.record(stream)
+            evs.append((e0, e1))
+        barrier()
+        return [a.elapsed_time(b) for a, b in evs], time.perf_counter() - w0
+
+    def step_device(nb=B):
+        reg.ScanMatchBatchDevice(d_src.data_ptr(), int(offsets[nb]), d_off.data_ptr(), nb, d_guess.data_ptr(), d_pose.data_ptr(), d_res.data_ptr())
+
+    # ---------------- device-resident timing (headline batch) -------------------------------------------------
     sampler = ClockSampler(local_rank)
     sampler.start()
     time.sleep(0.5)                        # nvidia-smi needs a moment before its first sample
-    for _ in range(args.warmup):
-        flush.fill_(1.0)
-        step_device()
-    barrier()
-    launches0 = capi.launches()
-    evs = []
-    barrier()
     if args.profile_range:
+        for _ in range(args.warmup):
+            flush.fill_(1.0); step_device()
+        barrier()
         torch.cuda.profiler.start()
+    launches0 = capi.launches()
     sampler.mark_begin()
-    wall0 = time.perf_counter()
-    for _ in range(args.steps):
-        flush.fill_(0.0)                      # L2 flush between timed steps (outside the event pair)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        step_device()
-        e1.record(stream)
-        evs.append((e0, e1))
-    barrier()
-    wall_s = time.perf_counter() - wall0
+    step_ms, wall_s = time_device(step_device, args.steps, 0 if args.profile_range else args.warmup)
     sampler.mark_end()
     if args.profile_range:
         torch.cuda.profiler.stop()
-    gpu_launches = capi.launches() - launches0
-    step_ms = [a.elapsed_time(b) for a, b in evs]
+    gpu_launches = capi.launches() - launches0 - (0 if args.profile_range else args.warmup)
     dev_ms = float(np.sum(step_ms))
-    res = np.frombuffer(d_res.cpu().numpy().tobytes(), dtype=capi.RESULT_DTYPE)
-    poses_dev = d_pose.cpu().numpy().reshape(B, 4, 4).transpose(0, 2, 1)
+    res = np.frombuffer(d_res.cpu().numpy().tobytes(), dtype=capi.RESULT_DTYPE).copy()
+    poses_dev = d_pose.cpu().numpy().reshape(B, 4, 4).transpose(0, 2, 1).copy()
+
+    # ---------------- strong scaling: --frames frames IN TOTAL, this rank's block (config 4 as BASELINE states it) ----
+    if strong_B == B:
+        strong_ms = list(step_ms)
+    elif strong_B > 0:
+        strong_ms, _ = time_device(lambda: step_device(strong_B), args.steps, args.warmup)
+        assert np.array_equal(np.frombuffer(d_res[:strong_B].cpu().numpy().tobytes(), dtype=capi.RESULT_DTYPE)["iterations"],
+                              res["iterations"][:strong_B]), "a block of the batch must give the same answers as the whole batch"
+    else:
+        strong_ms = [0.0] * args.steps
+
+    # ---------------- config 5: one scan x H hypotheses sharded over the ranks, best-fit gather -------------------
+    H = args.hypotheses
+    k5 = B // 2
+    src5 = sources[k5]
+    hyp = hypothesis_lattice(truth[k5], synth.pose6_to_matrix, side=int(round(np.sqrt(H))))
+    H = len(hyp)
+    lo5, hi5 = shard.shard_range(H, rank, world)
+    Hl = hi5 - lo5
+    d_src5 = torch.from_numpy(np.ascontiguousarray(src5)).to(dev)
+    d_g5 = torch.from_numpy(np.ascontiguousarray(hyp[lo5:hi5].transpose(0, 2, 1).reshape(Hl, 16))).to(dev)
+    d_pose5 = torch.zeros((max(Hl, 1), 16), dtype=torch.float32, device=dev)
+    d_res5 = torch.zeros((max(Hl, 1), capi.RESULT_DTYPE.itemsize), dtype=torch.uint8, device=dev)
+    best5 = {}
+
+    def step_config5():
+        """all of this rank's hypotheses in one launch (shared source), then the best-fit gather: every rank
+        contributes ONE row (its best score, the hypothesis index, the pose)"""
+        if Hl:
+            reg.ScanMatchBatchDevice(d_src5.data_ptr(), len(src5), 0, Hl, d_g5.data_ptr(), d_pose5.data_ptr(), d_res5.data_ptr())
+        r5 = np.frombuffer(d_res5.cpu().numpy().tobytes(), dtype=capi.RESULT_DTYPE)[:Hl]       # D2H of the results (syncs the stream)
+        row = torch.full((18,), -np.inf, dtype=torch.float64, device=dev)
+        if Hl:
+            sc = np.where(r5["converged"] > 0, r5["score"], -np.inf)
+            kb = int(np.argmax(sc))
+            row[0] = float(sc[kb]); row[1] = float(lo5 + kb)
+            row[2:18] = d_pose5[kb].to(torch.float64)
+        if world > 1:
+            rows = [torch.empty_like(row) for _ in range(world)]
+            dist.all_gather(rows, row)
+            rows = torch.stack(rows).cpu().numpy()
+        else:
+            rows = row.cpu().numpy()[None]
+        w = int(np.argmax(rows[:, 0]))
+        best5.update(score=float(rows[w, 0]), index=int(rows[w, 1]), pose=rows[w, 2:18].reshape(4, 4).T.copy())
+
+    for _ in range(max(2, args.warmup)):
+        step_config5()
+    barrier()
+    c5_ms = []
+    for _ in range(max(5, args.steps)):
+        flush.fill_(0.0)
+        barrier()
+        t0 = time.perf_counter()
+        step_config5()
+        torch.cuda.synchronize()
+        c5_ms.append(1e3 * (time.perf_counter() - t0))
+    c5_launches = 1
+    c5_err = float(np.linalg.norm(best5["pose"][:3, 3] - synth.pose6_to_matrix(truth[k5])[:3, 3]))
 
     # ---------------- end to end through the host-buffer C ABI -------------------------------------------
     reg.SetStream(None)
     h2d = n_total * 16 + B * 64 + (B + 1) * 4
     d2h = B * (64 + capi.RESULT_DTYPE.itemsize)
-    import ctypes as C
     L = capi.lib()
     # the caller's cloud lives in page-locked host memory (as a ROS/driver ring buffer would): the library
     # then DMAs straight from it
@@ -437,26 +546,104 @@ def main():
     barrier()
     e2e_s = time.perf_counter() - t0
     sampler.mark_end()
-    clocks = sampler.stop()                # the samples inside the device-resident and the end-to-end timed regions
     assert np.array_equal(out_res["iterations"], res["iterations"]), "host and device batch paths disagree"
 
-    # single-match latency through b2ndt_align (p50 over a sample of frames, cluster of 8 CTAs)
+    # ---------------- raw scan -> pose, end to end (front_end.cpp:92,106-107,224-231 per frame of a replay) ----------
+    raw = None
+    R = len(raws_kept)
+    if R:
+        CH = 64                                                       # frames per H2D chunk
+        r_off = np.zeros(R + 1, np.int64)
+        r_off[1:] = np.cumsum([len(r) for r in raws_kept])
+        raw_pin = torch.empty((int(r_off[-1]), 4), dtype=torch.float32).pin_memory()
+        raw_np = raw_pin.numpy()
+        for i, r in enumerate(raws_kept):
+            raw_np[r_off[i]:r_off[i + 1]] = r
+        chunks = [(c0, min(R, c0 + CH)) for c0 in range(0, R, CH)]
+        cmax = max(int(r_off[b] - r_off[a]) for a, b in chunks)
+        d_rawbuf = [torch.empty((cmax, 4), dtype=torch.float32, device=dev) for _ in range(2)]
+        cap = int(sum(len(s) for s in sources[:R]) * 1.25) + 4096   # filtered points of the R frames (+ slack)
+        d_filt_all = torch.empty((cap, 4), dtype=torch.float32, device=dev)
+        d_foff = torch.zeros(R + 1, dtype=torch.int32, device=dev)
+        d_cursor = torch.zeros(4, dtype=torch.int32, device=dev)
+        g_pin = torch.from_numpy(g_cm[:R].copy()).pin_memory()
+        d_g_raw = torch.empty((R, 16), dtype=torch.float32, device=dev)
+        pose_pin = torch.empty((R, 16), dtype=torch.float32).pin_memory()
+        res_pin = torch.empty((R, capi.RESULT_DTYPE.itemsize), dtype=torch.uint8).pin_memory()
+        copy_stream = torch.cuda.Stream(device=dev)
+        vf.SetStream(sptr); reg.SetStream(sptr)
+        ev_copied = [torch.cuda.Event() for _ in chunks]
+        ev_filtered = [torch.cuda.Event() for _ in chunks]
+
+        def step_raw():
+            d_cursor.zero_()
+            d_g_raw.copy_(g_pin, non_blocking=True)
+            for ci, (a, b) in enumerate(chunks):
+                buf = d_rawbuf[ci & 1]
+                n_c = int(r_off[b] - r_off[a])
+                with torch.cuda.stream(copy_stream):
+                    if ci >= 2:
+                        copy_stream.wait_event(ev_filtered[ci - 2])           # the buffer's previous chunk has been filtered
+                    buf[:n_c].copy_(raw_pin[int(r_off[a]):int(r_off[b])], non_blocking=True)
+                    ev_copied[ci].record(copy_stream)
+                stream.wait_event(ev_copied[ci])
+                vf.FilterBatchAppendDevice(buf.data_ptr(), n_c, (r_off[a:b + 1] - r_off[a]).astype(np.uint32), d_filt_all.data_ptr(), cap,
+                                           d_foff.data_ptr(), a, d_cursor.data_ptr())
+                ev_filtered[ci].record(stream)
+            reg.ScanMatchBatchDevice(d_filt_all.data_ptr(), cap, d_foff.data_ptr(), R, d_g_raw.data_ptr(), d_pose.data_ptr(), d_res.data_ptr())
+            pose_pin.copy_(d_pose[:R], non_blocking=True)
+            res_pin.copy_(d_res[:R], non_blocking=True)
+            stream.synchronize()
+
+        for _ in range(args.warmup):
+            step_raw()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_raw()
+        barrier()
+        raw_s = time.perf_counter() - t0
+        # parity of the batched ingest with the per-frame path: same filtered clouds, same matches
+        foff = d_foff.cpu().numpy().astype(np.int64)
+        assert int(d_cursor[1].item()) == 0, "filtered output overflowed its capacity"
+        assert np.array_equal(foff, offsets[:R + 1].astype(np.int64)), "batched ingest and per-frame VoxelFilter disagree on the voxel counts"
+        assert np.array_equal(d_filt_all[:int(foff[-1])].cpu().numpy(), cat[:int(foff[-1])]), "batched ingest and per-frame VoxelFilter disagree"
+        r_raw = np.frombuffer(res_pin.numpy().tobytes(), dtype=capi.RESULT_DTYPE)
+        assert np.array_equal(r_raw["iterations"], res["iterations"][:R])
+        # PCIe ceiling: the raw bytes of one step at the H2D rate measured right here (one big pinned copy)
+        big = d_rawbuf[0]
+        nbig = min(cmax, int(r_off[-1]))
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        for _ in range(3):
+            big[:nbig].copy_(raw_pin[:nbig], non_blocking=True)
+        torch.cuda.synchronize()
+        h2d_gbs = 3 * nbig * 16 / (time.perf_counter() - t0) / 1e9
+        raw_bytes = int(r_off[-1]) * 16 + R * 64
+        raw = {"frames_per_step": R, "raw_points_per_frame": float(r_off[-1]) / R, "seconds": raw_s,
+               "h2d_bytes_per_step": raw_bytes, "d2h_bytes_per_step": R * (64 + capi.RESULT_DTYPE.itemsize),
+               "h2d_GBps_measured": h2d_gbs, "chunk_frames": CH}
+        vf.SetStream(None); reg.SetStream(None)
+        del d_rawbuf, d_filt_all, raw_pin
+    clocks = sampler.stop()                # the samples inside the device-resident and the end-to-end timed regions
+
+    # single-match latency through b2ndt_align (p50 over a sample of frames)
     lat = []
     for k in range(3):                          # warm-up: first launch of the cluster kernel loads its module
-        reg.ScanMatch(sources[k], guesses[k], want_cloud=False)
+        reg.ScanMatch(sources[k % B], guesses[k % B], want_cloud=False)
     for k in range(0, B, max(1, B // 64)):
         t = time.perf_counter()
         reg.ScanMatch(sources[k], guesses[k], want_cloud=False)
         lat.append(1e3 * (time.perf_counter() - t))
 
     # ---------------- aggregate over ranks ----------------------------------------------------------------
-    t_dev = torch.tensor([dev_ms, e2e_s * 1e3, wall_s * 1e3], dtype=torch.float64, device=dev)
-    tot = torch.tensor([float(B), float(gpu_launches), float(res["passes"].sum()), float(res["pairs"].sum()), float(n_total)],
-                       dtype=torch.float64, device=dev)
+    t_dev = torch.tensor([dev_ms, e2e_s * 1e3, wall_s * 1e3, float(np.sum(strong_ms)), float(np.median(c5_ms)),
+                          (raw["seconds"] * 1e3 if raw else 0.0)], dtype=torch.float64, device=dev)
+    tot = torch.tensor([float(B), float(gpu_launches), float(res["passes"].sum()), float(res["pairs"].sum()), float(n_total),
+                        float(strong_B), float(R)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    max_dev_ms, max_e2e_ms, max_wall_ms = [float(v) for v in t_dev.cpu()]
+    max_dev_ms, max_e2e_ms, max_wall_ms, max_strong_ms, max_c5_ms, max_raw_ms = [float(v) for v in t_dev.cpu()]
     all_B = float(tot[0].item())
 
     if rank == 0:
@@ -479,15 +666,19 @@ def main():
         alg_bytes = float(np.sum(passes * (16.0 * npts + 80.0 * rho * npts + 224.0)) + 64.0 * B)
         launch_s = (dev_ms / args.steps) * 1e-3
         achieved = alg_bytes / launch_s / 1e9
-        # DRAM traffic of one launch from the committed ncu --set full capture (same command, same frames)
-        traffic = None
-        try:
-            with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
-                tj = json.load(f)
-            if tj.get("frames_per_launch") == B:
-                traffic = float(tj["dram_bytes_read"] + tj["dram_bytes_write"])
-        except Exception:
-            pass
+        # DRAM traffic of one launch: from the committed ncu --set full capture of the same command (not measured in
+        # this run -- a number printed under a profiler is never a bench value)
+        traffic, traffic_src = None, None
+        for name in ("r2_traffic.json", "r1_traffic.json"):
+            try:
+                with open(os.path.join(ROOT, "profiles", name)) as f:
+                    tj = json.load(f)
+                if tj.get("frames_per_launch") == B:
+                    traffic = float(tj["dram_bytes_read"] + tj["dram_bytes_write"])
+                    traffic_src = "profiles/" + name
+                    break
+            except Exception:
+                pass
         # FP64 work actually issued: ~300 flops per (point, voxel) pair in the Q/P/M formulation (150 DFMA-class
         # operations, csrc/b2_ndt.cu ndt_pair) + ~30 per point and pass for the float transform / cell lookup
         flops = float(np.sum(passes * 30.0 * npts) + 300.0 * res["pairs"].sum())
@@ -505,18 +696,44 @@ def main():
             dr = max(float(np.max(np.abs(res["p"][k][3:] - refs[i]["p"][3:]))) for i, k in enumerate(sample))
             it_eq = all(int(res["iterations"][k]) == refs[i]["iterations"] for i, k in enumerate(sample))
             parity = {"checked": len(sample), "max_dt_m": dt, "max_dr_rad": dr, "iterations_equal": it_eq}
+            # config 5 winner vs the oracle on the winning hypothesis
+            r5 = O.align(grid, prm, src5, hyp[best5["index"]])
+            parity["config5_best_dt_m"] = float(np.max(np.abs(best5["pose"][:3, 3] - r5["pose"][:3, 3])))
 
-        value = all_B * args.steps / (max_dev_ms * 1e-3)
+        weak_value = all_B * args.steps / (max_dev_ms * 1e-3)
         e2e_value = all_B * args.steps / (max_e2e_ms * 1e-3)
+        strong_total = float(tot[5].item())
+        strong = {"frames_total": int(strong_total), "frames_per_gpu": [shard.shard_sizes(args.frames, world)[0], shard.shard_sizes(args.frames, world)[-1]],
+                  "value": (strong_total * args.steps / (max_strong_ms * 1e-3)) if max_strong_ms > 0 else None, "unit": UNIT,
+                  "ms_per_step": max_strong_ms / args.steps,
+                  "note": "BASELINE config 4 as stated: %d frames in total, contiguous blocks over %d GPU(s), map replicated, no collective" % (args.frames, world)}
+        config5 = {"hypotheses": H, "per_gpu": [shard.shard_sizes(H, world)[0], shard.shard_sizes(H, world)[-1]], "n_source": len(src5),
+                   "wall_ms_all": max_c5_ms, "hyp_per_s": 1e3 * H / max_c5_ms, "best_index": best5["index"], "best_err_vs_truth_m": c5_err,
+                   "note": "one scan x %d poses (lattice 2 m pitch), one launch per GPU with the scan shared, results D2H, best-fit all_gather of one row per rank; wall clock max over ranks, p50 of %d" % (H, len(c5_ms))}
+        e2e_raw = None
+        if raw:
+            r_total = float(tot[6].item())
+            fps = r_total * args.steps / (max_raw_ms * 1e-3)
+            e2e_raw = {"value": fps, "unit": "frames/s", "frames_per_step_per_gpu": raw["frames_per_step"],
+                       "raw_points_per_frame": raw["raw_points_per_frame"], "ms_per_step": max_raw_ms / args.steps,
+                       "h2d_bytes_per_step": raw["h2d_bytes_per_step"], "d2h_bytes_per_step": raw["d2h_bytes_per_step"],
+                       "pcie_h2d_GBps_measured": raw["h2d_GBps_measured"],
+                       "pcie_ceiling_frames_per_s_per_gpu": raw["h2d_GBps_measured"] * 1e9 / (raw["h2d_bytes_per_step"] / raw["frames_per_step"]),
+                       "note": "pinned raw frames -> H2D in %d-frame chunks (two device buffers) -> b2vf_filter_batch_append_device -> one b2ndt_align_batch_device -> poses + results D2H; filtered clouds and matches asserted equal to the per-frame path" % raw["chunk_frames"]}
+        headline_value, headline_ms, scaling = weak_value, max_dev_ms / args.steps, "weak"
+        if args.workload == "config5":
+            headline_value, headline_ms, scaling = config5["hyp_per_s"], max_c5_ms, "strong"
+        elif args.scaling == "strong":
+            headline_value, headline_ms, scaling = strong["value"], strong["ms_per_step"], "strong"
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": max_dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "metric": METRIC, "value": headline_value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": headline_ms, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {
-                "workload": "config4 batched scan-to-map NDT: %d HDL-64 frames/GPU (VoxelFilter 1.3 m -> mean %.0f pts) vs %d-pt map "
-                            "(V=%d voxels, %d searchable), res 1.0 step 0.1 eps 0.01 iter 30, guesses = truth+U[0.5m,2deg]"
-                            % (B, n_total / B, info["n_points"], info["n_leaves"], info["n_tree"]),
-                "frames_per_gpu": B, "l2": "256 MB flush between timed steps", "batch_cluster": args.batch_cluster,
+                "workload": workload_name(args.frames, info["n_points"]) if args.workload == "config4" else
+                            "config5 global relocalisation: one HDL-64 scan (VoxelFilter 1.3 m) x %d initial poses vs %d-pt map, best-fit gather" % (H, info["n_points"]),
+                "frames_per_gpu": B, "mean_source_points": n_total / B, "map_voxels": info["n_leaves"], "map_voxels_searchable": info["n_tree"],
+                "l2": "256 MB flush between timed steps", "batch_cluster": args.batch_cluster,
                 "mean_iterations": float(res["iterations"].mean()), "converged_frac": float(res["converged"].mean()),
                 "mean_passes": float(res["passes"].mean()), "pairs_per_pass_per_point": float(res["pairs"].sum() / np.sum(passes * npts)),
                 "set_target_ms": set_target_ms, "setup_s": setup_s, "device_resident": resident,
@@ -524,13 +741,15 @@ def main():
                 "single_match_ms": {"p50": float(np.percentile(lat, 50)), "p99": float(np.percentile(lat, 99)), "n": len(lat)},
                 "step_ms": step_ms, "wall_ms_per_step_incl_flush": max_wall_ms / args.steps,
             },
+            "weak": {"value": weak_value, "unit": UNIT, "frames_per_gpu": B, "ms_per_step": max_dev_ms / args.steps},
+            "strong": strong, "config5": config5, "e2e_raw": e2e_raw,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(tot[1].item()),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "kernel": "ndt_batch_kernel", "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
-                         "v_touched_per_source_point": rho, "fp64_gflops_est": flops / launch_s / 1e9,
-                         "note": "working set is L2-resident (DRAM traffic << algorithmic bytes): bound by the L1 data pipe (LSU wavefronts of the gathers + shared-memory rings) and instruction latency, see profiles/README.md"},
+                         "traffic_source": traffic_src, "kernel": "ndt_batch_kernel", "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes, "v_touched_per_source_point": rho, "fp64_gflops_est": flops / launch_s / 1e9,
+                         "note": "working set is L2-resident (DRAM traffic << algorithmic bytes): bound by instruction issue and the L1 data pipe, see profiles/README.md; the HBM-streaming subsystems (VoxelFilter, target build) are under config.device_resident"},
             "cpu_baseline": ({"value": cpu_value, "unit": UNIT, "cores": 1, "kind": "port",
                               "sample": "%d of the %d frames, oracle align, 1 thread" % (len(sample), B)} if cpu_value else None),
             "parity": parity,

@@ -93,7 +93,9 @@ void b2ndt_destroy(b2ndt *h);
 /* run on an existing CUDA stream (cudaStream_t) instead of the handle's own; NULL restores it */
 int  b2ndt_set_stream(b2ndt *h, void *cuda_stream);
 int  b2ndt_synchronize(b2ndt *h);
-/* thread-block cluster width per match: 1..16 (single match default 8, batch default 1) */
+/* thread-block cluster width per match.  single_match_ctas 1..16: upper bound for one ScanMatch (default 16; the
+ * library picks by source size).  batch_ctas 0..16: 0 (default) = by batch size (1 = persistent batch kernel for
+ * batches that fill the GPU, clusters of 2 / 4 / 8 CTAs per match for batches smaller than half a wave). */
 int  b2ndt_set_cluster(b2ndt *h, int single_match_ctas, int batch_ctas);
 
 int  b2ndt_set_target(b2ndt *h, const void *pts, size_t n, size_t stride, size_t ioff);
@@ -142,6 +144,15 @@ int  b2vf_filter(b2vf *h, const void *in, size_t n, size_t stride, size_t ioff,
  * n_total), d_out_offsets (B+1) receives the output ranges (compacted, same order). Asynchronous. */
 int  b2vf_filter_batch_device(b2vf *h, const void *d_in_f4, size_t n_total, const uint32_t *h_offsets,
                               size_t B, void *d_out_f4, uint32_t *d_out_offsets);
+/* Batched ingest (raw frames streaming in chunk by chunk: front_end.cpp:106-107 for every frame of a replay): as
+ * above, but the filtered clouds are APPENDED to d_out_f4 (capacity out_capacity points) behind what earlier calls
+ * left there, with no host round trip: d_cursor[0] (device; zero it before the first call) counts the points in
+ * d_out_f4, d_cursor[1] is set when a batch did not fit (that batch is dropped as a whole).
+ * d_out_offsets[first_index + s], s = 0..B, receives where cloud s of this batch starts: after K calls the array is
+ * the offsets table b2ndt_align_batch_device takes.  Asynchronous. */
+int  b2vf_filter_batch_append_device(b2vf *h, const void *d_in_f4, size_t n_total, const uint32_t *h_offsets,
+                                     size_t B, void *d_out_f4, size_t out_capacity, uint32_t *d_out_offsets,
+                                     size_t first_index, uint32_t *d_cursor);
 
 /* ------------------------------------------------------------------ device-resident clouds --
  * The callers either side of the hot path keep their clouds in HBM: the front end's

@@ -21,7 +21,7 @@ EXPORTS = [
     "b2ndt_set_cluster", "b2ndt_set_target", "b2ndt_set_target_device", "b2ndt_target_info_get",
     "b2ndt_target_leaves", "b2ndt_align", "b2ndt_align_batch", "b2ndt_align_batch_device",
     "b2ndt_derivatives", "b2ndt_fitness", "b2ndt_fitness_ex",
-    "b2vf_create", "b2vf_destroy", "b2vf_set_stream", "b2vf_filter", "b2vf_filter_batch_device",
+    "b2vf_create", "b2vf_destroy", "b2vf_set_stream", "b2vf_filter", "b2vf_filter_batch_device", "b2vf_filter_batch_append_device",
     "b2cloud_create", "b2cloud_destroy", "b2cloud_upload", "b2cloud_download", "b2cloud_size", "b2cloud_clear",
     "b2cloud_device_ptr", "b2cloud_append_transformed", "b2cloud_box_filter", "b2cloud_remove_nan", "b2cloud_distortion_adjust", "b2vf_filter_cloud",
     "b2ndt_set_target_cloud", "b2ndt_align_cloud",
@@ -101,6 +101,7 @@ def lib():
     L.b2vf_set_stream.argtypes = [vp, vp]
     L.b2vf_filter.argtypes = [vp, vp, sz, sz, sz, vp, sz, sz, sz, C.POINTER(sz), i32p, i32p]
     L.b2vf_filter_batch_device.argtypes = [vp, vp, sz, u32p, sz, vp, vp]
+    L.b2vf_filter_batch_append_device.argtypes = [vp, vp, sz, u32p, sz, vp, sz, vp, sz, vp]
     L.b2cloud_create.argtypes = [C.c_int, C.POINTER(vp)]
     L.b2cloud_destroy.argtypes = [vp]
     L.b2cloud_destroy.restype = None

@@ -512,7 +512,8 @@ struct MatchArgs {
 #define NDT_SLOTS_N 2
 #endif
 constexpr int NDT_SLOTS = NDT_SLOTS_N;          // matches in flight per CTA (batch kernel)
-static_assert(NDT_SLOTS <= NDT_NCW, "slot s is controlled by compute warp s");
+static_assert(NDT_SLOTS >= 1 && NDT_SLOTS <= NDT_NCW && NDT_SLOTS <= 8, "the first match of slot s is started by compute warp s");
+constexpr uint32_t PASS_RING = 8;               // pass markers kept per search warp (power of two >= NDT_SLOTS)
 
 struct Slot {                      // one match in flight
     Ctl ctl;
@@ -535,9 +536,11 @@ struct NdtSmem {
     uint32_t tail[NDT_NSW];        // entries produced by search warp s
     uint32_t head[NDT_NSW];        // entries consumed from search warp s
     uint32_t finished[NDT_NSW];    // passes search warp s has completed
-    uint32_t pass_end[NDT_NSW][4]; // ring position at which pass p of search warp s ended (p & 3); producers run at
-                                   // most two passes ahead of the consumers
-    uint32_t pass_dead[NDT_NSW][4];// batch kernel: "pass" p is only the marker that its slot has no more work
+    uint64_t req_bar[NDT_SLOTS];   // batch kernel: one mbarrier per slot, a phase = one pass request (controller arrives)
+    uint32_t pass_end[NDT_NSW][PASS_RING]; // ring position at which pass p of search warp s ended (p % PASS_RING): a producer is
+                                   // at most NDT_SLOTS passes ahead of its consumer (a slot's next pass is requested
+                                   // only after its previous one was drained by every compute warp)
+    uint32_t pass_dead[NDT_NSW][PASS_RING];// batch kernel: "pass" p is only the marker that its slot has no more work
     float4 ring[NDT_NSW][RING];    // (source point x, y, z, leaf index): consumers never touch the source cloud
     float4 stage[NDT_NSW][192];    // per search warp, three slots: [lane] source point, [32 + lane] transformed point
 };
@@ -997,8 +1000,8 @@ __device__ __forceinline__ void search_pass(NdtSmem &S, const GridView &G, const
     if (lane == 0) {
         __threadfence_block();
         st_vol(&S.tail[sw], my_tail);
-        st_vol(&S.pass_end[sw][st.pass_id & 3u], my_tail);
-        st_vol(&S.pass_dead[sw][st.pass_id & 3u], 0u);
+        st_vol(&S.pass_end[sw][st.pass_id & (PASS_RING - 1u)], my_tail);
+        st_vol(&S.pass_dead[sw][st.pass_id & (PASS_RING - 1u)], 0u);
         __threadfence_block();
         st_vol(&S.finished[sw], st.pass_id);
     }
@@ -1011,8 +1014,8 @@ __device__ __forceinline__ void search_dead_marker(NdtSmem &S, int sw, int lane,
     ++st.pass_id;
     __syncwarp();
     if (lane == 0) {
-        st_vol(&S.pass_end[sw][st.pass_id & 3u], st.my_tail);
-        st_vol(&S.pass_dead[sw][st.pass_id & 3u], 1u);
+        st_vol(&S.pass_end[sw][st.pass_id & (PASS_RING - 1u)], st.my_tail);
+        st_vol(&S.pass_dead[sw][st.pass_id & (PASS_RING - 1u)], 1u);
         __threadfence_block();
         st_vol(&S.finished[sw], st.pass_id);
     }
@@ -1062,12 +1065,12 @@ __device__ __forceinline__ bool compute_drain(NdtSmem &S, const GridView &G, con
                         const uint32_t fin = ld_vol(&S.finished[sw]);
                         const bool done = (int32_t)(fin - ds.pass_id) >= 0;
                         __threadfence_block();
-                        const uint32_t end = done ? ld_vol(&S.pass_end[sw][ds.pass_id & 3u]) : tl;
+                        const uint32_t end = done ? ld_vol(&S.pass_end[sw][ds.pass_id & (PASS_RING - 1u)]) : tl;
                         const uint32_t avail = end - pos;
                         avail_all = avail;
                         if (avail >= 32u) { n = 32u; break; }
                         if (done) {     // final (possibly empty) chunk; bit 30: dead-slot marker
-                            n = avail | 0x80000000u | (ld_vol(&S.pass_dead[sw][ds.pass_id & 3u]) ? 0x40000000u : 0u);
+                            n = avail | 0x80000000u | (ld_vol(&S.pass_dead[sw][ds.pass_id & (PASS_RING - 1u)]) ? 0x40000000u : 0u);
                             break;
                         }
                         __nanosleep(NDT_DRAIN_SLEEP);
@@ -1220,26 +1223,44 @@ __global__ void __launch_bounds__(NDT_THREADS, NDT_MIN_CTAS) ndt_match_kernel(Gr
     }
 }
 
-// ================================================================ kernel 2: batches, two matches per CTA =
+// ================================================================ kernel 2: batches, NDT_SLOTS matches per CTA =
 // Persistent CTAs (one wave), NDT_SLOTS matches in flight per CTA, work fetched from a global counter.  The
-// search warps alternate between the slots pass by pass and never wait at a pass boundary: while the compute
-// warps drain the tail of slot A's pass and compute warp A runs A's Newton step, the search warps are already
-// producing slot B's pass.  Compute warps hand their partial sums to the slot's controller warp through a named
-// barrier (bar.arrive for the others, bar.sync for the controller) and move on.  Every warp walks the same
-// deterministic sequence (slot 0, slot 1, slot 0, ...; a slot's next item is "pass seq+1" or "dead"), and a
-// match's sums are accumulated in the same fixed order as in kernel 1, so results do not depend on scheduling.
+// search warps cycle over the slots pass by pass and never wait at a pass boundary: while the compute warps drain
+// the tail of slot A's pass and a compute warp runs A's Newton step, the search warps are already producing the
+// passes of the other slots.  Compute warps hand their partial sums to the slot's controller warp through a named
+// barrier (bar.arrive for the others, bar.sync for the controller) and move on.  Pass requests reach the search
+// warps through one mbarrier per slot: the controller publishes the request and arrives; EACH search warp waits on
+// the phase on its own (hardware sleep, no polling of shared memory), so a search warp that is done with its share
+// of a pass starts on the next slot without waiting for the slowest search warp (the former named barrier joined
+// all eight at every pass end: 17.5 % of the stall samples, profiles/r1_ndt_batch_kernel_ncu_full.txt).  Every warp
+// walks the same deterministic sequence (slot 0, 1, .., 0, ..; a slot's next item is its next pass or "dead"), and
+// a match's sums are accumulated in the same fixed order as in kernel 1, so results do not depend on scheduling.
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n"
+        "B2_MBAR_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra B2_MBAR_DONE;\n\t"
+        "bra B2_MBAR_WAIT;\n"
+        "B2_MBAR_DONE:\n\t}" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+
 __global__ void __launch_bounds__(NDT_THREADS, NDT_MIN_CTAS) ndt_batch_kernel(GridView G, NdtConst K, MatchArgs A, uint32_t B,
                                                                              uint32_t *__restrict__ work_counter) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     NdtSmem &S = *reinterpret_cast<NdtSmem *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool is_compute = warp < NDT_NCW;
+    constexpr uint32_t ALL_SLOTS = (1u << NDT_SLOTS) - 1u;
 
-    // fetch the next match for a slot (controller warp, all lanes): returns 1 and requests its first pass, or 0
-    auto fetch_match = [&](Slot &SL) -> int {
-        uint32_t m = 0;
-        if (lane == 0) m = atomicAdd(work_counter, 1u);
-        m = __shfl_sync(0xffffffffu, m, 0);
+    // start match m in a slot (controller warp, all lanes): returns 1 and requests its first pass, or 0
+    auto start_match = [&](Slot &SL, uint32_t m) -> int {
         if (m >= B) return 0;
         if (A.ready) {
             // host-streamed batch: wait until the copy stream has delivered this match's points.  Every copy this
@@ -1273,21 +1294,23 @@ __global__ void __launch_bounds__(NDT_THREADS, NDT_MIN_CTAS) ndt_batch_kernel(Gr
         finish_request_warp(SL, lane);
         return 1;
     };
-    // Pass requests reach the SEARCH warps through named barrier 1 + NDT_SLOTS + s: the slot's controller warp
-    // publishes (seq, or dead) and arrives without waiting, the search warps wait in the hardware barrier (no
-    // polling of shared memory while a controller runs).  The first request of a slot was published before the
-    // initial __syncthreads.  The compute warps never wait for requests: they follow the ring streams, where a
-    // dead slot shows up as an empty pass carrying the dead marker.
-    constexpr int REQ_THREADS = (NDT_NSW + 1) * 32;
-    auto next_item = [&](int s, uint32_t seen) -> int {
-        if (seen != 0u) asm volatile("bar.sync %0, %1;" ::"r"(1 + NDT_SLOTS + s), "n"(REQ_THREADS) : "memory");
-        return ld_vol(&S.slot[s].dead) ? 0 : 1;
+    // the next match from the global counter (it starts behind the statically dealt first round)
+    auto fetch_match = [&](Slot &SL) -> int {
+        uint32_t m = 0;
+        if (lane == 0) m = atomicAdd(work_counter, 1u);
+        m = __shfl_sync(0xffffffffu, m, 0);
+        return start_match(SL, gridDim.x * NDT_SLOTS + m);
     };
 
     if (tid < NDT_NSW) { S.tail[tid] = 0u; S.head[tid] = 0u; S.finished[tid] = 0u; }
+    if (tid < NDT_SLOTS) mbar_init(&S.req_bar[tid], 1u);
     if (warp < NDT_SLOTS) {
+        // first round dealt statically.  A batch that fills every slot: CTA b takes matches b * NDT_SLOTS + j (in
+        // batch order, so a host-streamed batch can start on its first chunk); a smaller one: slot j of CTA b takes
+        // j * grid + b, so it still spreads over all CTAs
         Slot &SL = S.slot[warp];
-        const int ok = fetch_match(SL);
+        const uint32_t m0 = (B >= gridDim.x * NDT_SLOTS) ? blockIdx.x * NDT_SLOTS + (uint32_t)warp : (uint32_t)warp * gridDim.x + blockIdx.x;
+        const int ok = start_match(SL, m0);
         if (lane == 0) { SL.seq = ok ? 1u : 0u; SL.dead = ok ? 0u : 1u; }
     }
     __syncthreads();
@@ -1297,27 +1320,30 @@ __global__ void __launch_bounds__(NDT_THREADS, NDT_MIN_CTAS) ndt_batch_kernel(Gr
         const int sw = warp - NDT_NCW;
         SearchState st;
         TMB_DECL;
-        // every warp walks the same sequence: slot 0, slot 1, slot 0, ... (one code copy: s is a run-time value)
-        uint32_t seen0 = 0u, seen1 = 0u;
-        bool dead0 = false, dead1 = (NDT_SLOTS < 2);
+        // every warp walks the same sequence: slot 0, 1, .., 0, .. (one code copy: s is a run-time value); per-slot
+        // state lives in bit masks: dead, any request seen, parity of the mbarrier phase to wait for
+        uint32_t dead_mask = 0u, seen_mask = 0u, par_mask = 0u;
         int s = 0;
-        while (!(dead0 && dead1)) {
-            if (!(s ? dead1 : dead0)) {
+        while (dead_mask != ALL_SLOTS) {
+            const uint32_t bit = 1u << s;
+            if (!(dead_mask & bit)) {
                 TMB_LAP(2);
-                const int item = next_item(s, s ? seen1 : seen0);
+                // the first request of a slot was published before the initial __syncthreads
+                if (seen_mask & bit) { mbar_wait(&S.req_bar[s], (par_mask & bit) ? 1u : 0u); par_mask ^= bit; }
+                seen_mask |= bit;
+                const int item = ld_vol(&S.slot[s].dead) ? 0 : 1;
                 TMB_LAP(0);                                    // [0] waiting for the next pass request
                 if (item) {
-                    if (s) ++seen1; else ++seen0;
                     Slot &SL = S.slot[s];
                     const uint32_t first = ld_vol(&SL.first), last = ld_vol(&SL.last);
                     search_pass(S, G, A.src, first, last, first + sw * 32u, NDT_NSW * 32u, SL.ctl.T, sw, lane, st);
                     TMB_LAP(1);                                // [1] producing
                 } else {
                     search_dead_marker(S, sw, lane, st);
-                    if (s) dead1 = true; else dead0 = true;
+                    dead_mask |= bit;
                 }
             }
-            s = (NDT_SLOTS > 1) ? (s ^ 1) : 0;
+            s = (s + 1 == NDT_SLOTS) ? 0 : s + 1;
         }
         TMB_FLUSH(0, sw == 0);
     } else {
@@ -1327,25 +1353,25 @@ __global__ void __launch_bounds__(NDT_THREADS, NDT_MIN_CTAS) ndt_batch_kernel(Gr
 #pragma unroll
         for (int k = 0; k < NDT_PPC; ++k) ds.cpos[k] = 0;
         ds.pass_id = 0;
-        uint32_t seen0 = 0u, seen1 = 0u;
-        bool dead0 = false, dead1 = (NDT_SLOTS < 2);
+        uint32_t dead_mask = 0u;
+        uint32_t cnt_pack = 0u;                 // passes drained per slot, 4 bits each (only the low bits matter)
         int s = 0;
-        while (!(dead0 && dead1)) {
+        while (dead_mask != ALL_SLOTS) {
             const int s_now = s;
-            s = (NDT_SLOTS > 1) ? (s ^ 1) : 0;
+            s = (s + 1 == NDT_SLOTS) ? 0 : s + 1;
             {
                 const int s = s_now;
-                if (s ? dead1 : dead0) continue;
+                if (dead_mask & (1u << s)) continue;
                 TMB_LAP(7);
-                if (s) ++seen1; else ++seen0;
-                const uint32_t seen_s = s ? seen1 : seen0;
+                cnt_pack = (cnt_pack & ~(0xFu << (4 * s))) | ((((cnt_pack >> (4 * s)) + 1u) & 0xFu) << (4 * s));
+                const uint32_t seen_s = (cnt_pack >> (4 * s)) & 0xFu;
                 Slot &SL = S.slot[s];
                 const bool live = compute_drain(S, G, K, SL.ctl, warp, lane, ds, SL.warp_part[warp]);
-                if (!live) { if (s) dead1 = true; else dead0 = true; continue; }
+                if (!live) { dead_mask |= 1u << s; continue; }
                 TMB_LAP(1);                                    // [1] draining (incl. waiting for chunks)
                 // the controller role of a slot rotates over the compute warps pass by pass (every warp knows the
-                // slot's pass count), so the Newton steps do not always delay the same two ring consumers
-                const int ctl_warp = (s + NDT_SLOTS * (int)(seen_s & 1u)) % NDT_NCW;
+                // slot's pass count), so the Newton steps do not always delay the same ring consumers
+                const int ctl_warp = (int)((uint32_t)s + seen_s) % NDT_NCW;
                 if (warp != ctl_warp) {
                     // hand the partial sums to the slot's controller warp and move on
                     __syncwarp();
@@ -1370,11 +1396,11 @@ __global__ void __launch_bounds__(NDT_THREADS, NDT_MIN_CTAS) ndt_batch_kernel(Gr
                         TMB_LAP(4);                            // [4] result + next match
                     }
                     __syncwarp();
-                    if (lane == 0) {
-                        if (go) st_vol(&SL.seq, seen_s + 1u); else st_vol(&SL.dead, 1u);
-                    }
+                    if (lane == 0 && !go) st_vol(&SL.dead, 1u);
+                    // publish: the request written by the lanes of this warp, then one arrival on the slot's mbarrier
+                    __threadfence_block();
                     __syncwarp();
-                    asm volatile("bar.arrive %0, %1;" ::"r"(1 + NDT_SLOTS + s), "n"(REQ_THREADS) : "memory");
+                    if (lane == 0) mbar_arrive(&S.req_bar[s]);
                 }
             }
         }
@@ -1511,7 +1537,7 @@ struct b2ndt {
     const float4 *last_src = nullptr;     // device source of the last ScanMatch (GetFitnessScore)
     float last_pose[16];
     bool have_last = false;
-    int cl_single = 16, cl_batch = 1;
+    int cl_single = 16, cl_batch = 0;      // CTAs per match: single ScanMatch (upper bound) / batches (0 = by batch size)
     bool attrs_set = false, batch_attrs_set = false;
     bool use_batch_kernel = true;          // B2NDT_BATCH_KERNEL=0 falls back to one-match-per-CTA launches (A/B testing)
     int batch_ctas = 0;
@@ -1520,6 +1546,7 @@ struct b2ndt {
     cudaEvent_t ev = nullptr;
     PinBuf h_ready;
     bool stream_batches = true;            // B2NDT_STREAM=0: copy everything, then launch
+    bool small_batch_clusters = true;      // B2NDT_SMALL_BATCH=0: never widen the matches of a small batch to clusters
 };
 
 static void gauss_constants(double outlier_ratio, float resolution, double *d1, double *d2) {
@@ -1565,6 +1592,7 @@ extern "C" int b2ndt_create(const b2ndt_params *p, int device, b2ndt **out) {
     }
     if (const char *e = getenv("B2NDT_BATCH_KERNEL")) h->use_batch_kernel = atoi(e) != 0;
     if (const char *e = getenv("B2NDT_STREAM")) h->stream_batches = atoi(e) != 0;
+    if (const char *e = getenv("B2NDT_SMALL_BATCH")) h->small_batch_clusters = atoi(e) != 0;
     *out = h;
     return 0;
 }
@@ -1603,8 +1631,8 @@ extern "C" int b2ndt_synchronize(b2ndt *h) {
 
 extern "C" int b2ndt_set_cluster(b2ndt *h, int single_match_ctas, int batch_ctas) {
     if (!h) { set_error("b2ndt_set_cluster: NULL handle"); return B2_ERR_INVALID; }
-    if (single_match_ctas < 1 || single_match_ctas > 16 || batch_ctas < 1 || batch_ctas > 16) {
-        set_error("b2ndt_set_cluster: cluster width must be 1..16"); return B2_ERR_INVALID;
+    if (single_match_ctas < 1 || single_match_ctas > 16 || batch_ctas < 0 || batch_ctas > 16) {
+        set_error("b2ndt_set_cluster: cluster width must be 1..16 (batch: 0 = chosen by batch size)"); return B2_ERR_INVALID;
     }
     h->cl_single = single_match_ctas; h->cl_batch = batch_ctas;
     return 0;
@@ -1783,22 +1811,33 @@ static int launch_match(b2ndt *h, const MatchArgs &A, size_t B, int C) {
         h->attrs_set = true;
     }
     GridView G = make_grid_view(h);
-    if (C == 1 && !A.deriv_only && B >= 2 && h->use_batch_kernel) {
-        // batches: persistent CTAs (one wave), two matches in flight per CTA, work fetched from a counter
-        if (!h->batch_attrs_set) {
-            B2_CUDA(cudaFuncSetAttribute(ndt_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NdtSmem)));
-            // one wave of resident CTAs: NDT_MIN_CTAS per SM (__launch_bounds__); CTAs do not depend on one
-            // another (work comes from a counter), so a CTA that is not resident at once just starts later
-            int sms = 0;
-            B2_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
-            h->batch_ctas = NDT_MIN_CTAS * sms;
-            h->batch_attrs_set = true;
+    if (!h->batch_attrs_set) {
+        B2_CUDA(cudaFuncSetAttribute(ndt_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NdtSmem)));
+        // one wave of resident CTAs: NDT_MIN_CTAS per SM (__launch_bounds__); CTAs do not depend on one
+        // another (work comes from a counter), so a CTA that is not resident at once just starts later
+        int sms = 0;
+        B2_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
+        h->batch_ctas = NDT_MIN_CTAS * sms;
+        h->batch_attrs_set = true;
+    }
+    if (C == 0) {
+        // CTAs per match chosen by batch size: a batch with fewer matches than half the resident CTAs (a shard of a
+        // relocalisation batch: 1024 hypotheses over 8 GPUs = 128 each) would leave SMs idle with one CTA per
+        // match, so each match gets a cluster of 2 / 4 / 8 CTAs (as many as keep the launch within one wave)
+        C = 1;
+        if (!A.deriv_only && B >= 1 && h->small_batch_clusters && B * 2 <= (size_t)h->batch_ctas) {
+            const size_t c = (size_t)h->batch_ctas / B;
+            C = c >= 8 ? 8 : c >= 4 ? 4 : 2;
         }
+    }
+    if (C == 1 && !A.deriv_only && B >= 2 && h->use_batch_kernel) {
+        // batches: persistent CTAs (one wave), NDT_SLOTS matches in flight per CTA, work fetched from a counter
         int rc;
         if ((rc = h->d_work.reserve(64))) return rc;
         if (!A.ready) B2_CUDA(cudaMemsetAsync(h->d_work.p, 0, 8, h->st));     // streamed batches: the caller zeroed it
-        const size_t want = (B + NDT_SLOTS - 1) / NDT_SLOTS;
-        const unsigned grid = (unsigned)(want < (size_t)h->batch_ctas ? want : (size_t)h->batch_ctas);
+        // a batch smaller than the number of resident CTAs gets one CTA per match (the first round of matches is dealt
+        // CTA-major, so the other slots of those CTAs simply stay empty)
+        const unsigned grid = (unsigned)(B < (size_t)h->batch_ctas ? B : (size_t)h->batch_ctas);
         NdtConst Kb = h->K;
         MatchArgs Ab = A;
 #ifdef NDT_TIMING
@@ -1896,7 +1935,7 @@ static int align_host(b2ndt *h, const void *src, size_t n_total, size_t stride, 
     // depends on the host (CUDA_LAUNCH_BLOCKING, a single hardware queue or a profiler serialising launches cannot
     // dead-lock it), and the wait is bounded on the device.  Strided / unpinned clouds are repacked chunk by chunk
     // before the launch, each chunk's copy overlapping the repack of the next.
-    if (offsets && C == 1 && B >= 256 && h->use_batch_kernel && h->stream_batches) {
+    if (offsets && (C == 1 || C == 0) && B >= 256 && h->use_batch_kernel && h->stream_batches) {
         if (!h->copy_st) B2_CUDA(cudaStreamCreateWithFlags(&h->copy_st, cudaStreamNonBlocking));
         if (!h->ev) B2_CUDA(cudaEventCreateWithFlags(&h->ev, cudaEventDisableTiming));
         const size_t nch = 16;

@@ -378,11 +378,31 @@ __global__ void __launch_bounds__(SORT_THREADS, (ITEMS > 8 ? 3 : 6)) onesweep_ke
         st_vol_g(&st[d], cnt_d | LB_INCL);
     } else {
         st_vol_g(&st[d], cnt_d | LB_PART);
-        for (uint32_t j = tile - 1;; --j) {
-            uint32_t v;
-            do { v = ld_vol_g(&state[(size_t)j * RADIX + d]); } while ((v & ~LB_MASK) == 0u);
-            excl += v & LB_MASK;
-            if (v & LB_INCL) break;            // the cloud's first tile always publishes an inclusive count
+        // Look-back, LB words at a time: the loads of a batch are independent (all in flight together), so a tile that
+        // starts together with its predecessors (small inputs: every tile is resident at once) pays one L2 round trip
+        // per LB predecessors instead of one per predecessor.  The cloud's first tile always publishes an inclusive
+        // count, so the walk never leaves the cloud; words below it read as "inclusive 0".
+        constexpr int LB = 8;
+        const int jmin = (int)sg.tile_begin;
+        int j = (int)tile - 1;
+        while (true) {
+            uint32_t v[LB];
+#pragma unroll
+            for (int q = 0; q < LB; ++q) v[q] = (j - q >= jmin) ? ld_vol_g(&state[(size_t)(j - q) * RADIX + d]) : LB_INCL;
+            bool done = false;
+            int used = 0;
+#pragma unroll
+            for (int q = 0; q < LB; ++q) {
+                if (!done && used == q) {
+                    if ((v[q] & ~LB_MASK) != 0u) {
+                        excl += v[q] & LB_MASK;
+                        ++used;
+                        if (v[q] & LB_INCL) done = true;
+                    }
+                }
+            }
+            if (done) break;
+            j -= used;                      // re-poll from the first word that was not ready
         }
         st_vol_g(&st[d], (excl + cnt_d) | LB_INCL);
     }
@@ -683,10 +703,16 @@ __global__ void __launch_bounds__(256) vf_centroid_kernel(const float4 *__restri
                                                           const uint32_t *__restrict__ run_seg,
                                                           const uint32_t *__restrict__ run_seg_off, PlanView P,
                                                           const VoxLayout *__restrict__ layouts, uint32_t *__restrict__ crowded,
-                                                          uint32_t *__restrict__ n_crowded,
+                                                          uint32_t *__restrict__ n_crowded, const uint32_t *__restrict__ out_base,
+                                                          uint32_t out_capacity,
                                                           float4 *__restrict__ out, int32_t *__restrict__ out_idx,
                                                           int32_t *__restrict__ out_cnt) {
     const uint32_t total = sv.scalars[1];
+    // append mode (batched ingest): the output starts at the cursor another call left on the device; a batch that
+    // would not fit is dropped as a whole (vf_append_kernel raises the overflow flag)
+    const uint32_t ob = out_base ? *out_base : 0u;
+    if ((size_t)ob + total > (size_t)out_capacity) return;
+    out += ob;
     const uint32_t *__restrict__ keys = sv.keys();
     const uint32_t *__restrict__ vals = sv.vals();
     const int l = threadIdx.x & 31;
@@ -736,10 +762,14 @@ __global__ void __launch_bounds__(256) vf_crowded_kernel(const float4 *__restric
                                                          const uint32_t *__restrict__ run_seg,
                                                          const uint32_t *__restrict__ run_seg_off, PlanView P,
                                                          const VoxLayout *__restrict__ layouts, const uint32_t *__restrict__ crowded,
-                                                         const uint32_t *__restrict__ n_crowded,
+                                                         const uint32_t *__restrict__ n_crowded, const uint32_t *__restrict__ out_base,
+                                                         uint32_t out_capacity,
                                                          float4 *__restrict__ out, int32_t *__restrict__ out_idx,
                                                          int32_t *__restrict__ out_cnt) {
     const uint32_t n = *n_crowded;
+    const uint32_t ob = out_base ? *out_base : 0u;
+    if ((size_t)ob + sv.scalars[1] > (size_t)out_capacity) return;
+    out += ob;
     const uint32_t *__restrict__ keys = sv.keys();
     const uint32_t *__restrict__ vals = sv.vals();
     const int l = threadIdx.x & 31;
@@ -803,6 +833,20 @@ __global__ void __launch_bounds__(256) vf_crowded_kernel(const float4 *__restric
             if (out_cnt) out_cnt[j] = (int32_t)(e - s);
         }
     }
+}
+
+// append mode: publish the per-cloud offsets of this batch relative to the whole output and advance the cursor
+// (cursor[0] = points in the output so far, cursor[1] = overflow flag)
+__global__ void __launch_bounds__(256) vf_append_kernel(const uint32_t *__restrict__ run_seg_off, uint32_t B,
+                                                        uint32_t *__restrict__ out_offsets, uint32_t *__restrict__ cursor,
+                                                        uint32_t out_capacity) {
+    __shared__ uint32_t s_cur, s_tot;
+    if (threadIdx.x == 0) { s_cur = cursor[0]; s_tot = run_seg_off[B]; }
+    __syncthreads();
+    const uint32_t cur = s_cur;
+    const bool fits = (size_t)cur + s_tot <= (size_t)out_capacity;
+    for (uint32_t s = threadIdx.x; s <= B; s += blockDim.x) out_offsets[s] = cur + (fits ? run_seg_off[s] : 0u);
+    if (threadIdx.x == 0) { if (fits) cursor[0] = cur + s_tot; else cursor[1] = 1u; }
 }
 
 }  // namespace b2
@@ -881,7 +925,8 @@ extern "C" int b2vf_set_stream(b2vf *h, void *stream) {
     return 0;
 }
 
-static int vf_launch_centroids(b2vf *h, const float4 *d_in, float4 *d_out, int32_t *d_idx, int32_t *d_cnt, size_t n) {
+static int vf_launch_centroids(b2vf *h, const float4 *d_in, float4 *d_out, int32_t *d_idx, int32_t *d_cnt, size_t n,
+                               const uint32_t *d_out_base = nullptr, uint32_t out_capacity = 0xFFFFFFFFu) {
     if (n == 0) return 0;
     int rc;
     if ((rc = h->d_crowded.reserve((n / VF_SEQ + 64) * 4))) return rc;
@@ -891,10 +936,12 @@ static int vf_launch_centroids(b2vf *h, const float4 *d_in, float4 *d_out, int32
     if (blocks > 148 * 16) blocks = 148 * 16;
     uint32_t *ncr = const_cast<uint32_t *>(h->pipe.scalars()) + 10;
     vf_centroid_kernel<<<blocks, 256, 0, h->st>>>(d_in, h->pipe.view(), h->pipe.run_start(), h->pipe.run_seg(), h->pipe.run_seg_off(),
-                                                 h->pipe.plan_view(), h->pipe.layouts(), h->d_crowded.as<uint32_t>(), ncr, d_out, d_idx, d_cnt);
+                                                 h->pipe.plan_view(), h->pipe.layouts(), h->d_crowded.as<uint32_t>(), ncr, d_out_base,
+                                                 out_capacity, d_out, d_idx, d_cnt);
     B2_LAUNCH_CHECK();
     vf_crowded_kernel<<<148 * 4, 256, 0, h->st>>>(d_in, h->pipe.view(), h->pipe.run_start(), h->pipe.run_seg(), h->pipe.run_seg_off(),
-                                                 h->pipe.plan_view(), h->pipe.layouts(), h->d_crowded.as<uint32_t>(), ncr, d_out, d_idx, d_cnt);
+                                                 h->pipe.plan_view(), h->pipe.layouts(), h->d_crowded.as<uint32_t>(), ncr, d_out_base,
+                                                 out_capacity, d_out, d_idx, d_cnt);
     B2_LAUNCH_CHECK();
     return 0;
 }
@@ -1000,6 +1047,29 @@ extern "C" int b2vf_filter_batch_device(b2vf *h, const void *d_in_f4, size_t n_t
     if ((rc = h->pipe.run((const float4 *)d_in_f4, h->leaf[0], h->leaf[1], h->leaf[2], 0, h->st))) return rc;
     if ((rc = vf_launch_centroids(h, (const float4 *)d_in_f4, (float4 *)d_out_f4, nullptr, nullptr, n_total))) return rc;
     B2_CUDA(cudaMemcpyAsync(d_out_offsets, h->pipe.run_seg_off(), (B + 1) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, h->st));
+    return 0;
+}
+
+// Batched ingest: like b2vf_filter_batch_device, but the filtered clouds are APPENDED to d_out_f4 behind the ones
+// earlier calls left there, without a host round trip: d_cursor[0] (device) counts the points in d_out_f4 so far
+// (zero it before the first call), d_cursor[1] becomes 1 when a batch did not fit into out_capacity points (that
+// batch is dropped as a whole).  d_out_offsets[first_index + s] receives where cloud s of this batch starts,
+// s = 0..B (the last entry is the new cursor, i.e. the first entry of the next batch): after K calls the array is the
+// (sum of B) + 1 offsets table b2ndt_align_batch_device takes.
+extern "C" int b2vf_filter_batch_append_device(b2vf *h, const void *d_in_f4, size_t n_total, const uint32_t *h_offsets, size_t B,
+                                               void *d_out_f4, size_t out_capacity, uint32_t *d_out_offsets, size_t first_index,
+                                               uint32_t *d_cursor) {
+    if (!h || !h_offsets || !d_out_offsets || !d_cursor || !d_out_f4) { set_error("b2vf_filter_batch_append_device: NULL argument"); return B2_ERR_INVALID; }
+    if (B == 0) return 0;
+    if (h_offsets[B] != n_total) { set_error("b2vf_filter_batch_append_device: offsets[B] != n_total"); return B2_ERR_INVALID; }
+    if (out_capacity >= B2_MAX_POINTS) out_capacity = B2_MAX_POINTS;
+    B2_CUDA(cudaSetDevice(h->device));
+    int rc;
+    if ((rc = h->pipe.plan(h_offsets, B, h->st))) return rc;
+    if ((rc = h->pipe.run((const float4 *)d_in_f4, h->leaf[0], h->leaf[1], h->leaf[2], 0, h->st))) return rc;
+    if ((rc = vf_launch_centroids(h, (const float4 *)d_in_f4, (float4 *)d_out_f4, nullptr, nullptr, n_total, d_cursor, (uint32_t)out_capacity))) return rc;
+    vf_append_kernel<<<1, 256, 0, h->st>>>(h->pipe.run_seg_off(), (uint32_t)B, d_out_offsets + first_index, d_cursor, (uint32_t)out_capacity);
+    B2_LAUNCH_CHECK();
     return 0;
 }
 

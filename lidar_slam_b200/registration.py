@@ -254,7 +254,7 @@ class NDTRegistration(RegistrationInterface):
                                                       capi._dp(mean), capi._dp(icov)))
         return dict(idx=idx, n=n, centroid=cen, mean=mean, icov=icov)
 
-    def SetCluster(self, single_match_ctas, batch_ctas=1):
+    def SetCluster(self, single_match_ctas, batch_ctas=0):
         capi.check(capi.lib().b2ndt_set_cluster(self._h, single_match_ctas, batch_ctas))
 
     def SetStream(self, cuda_stream_ptr):
@@ -393,6 +393,15 @@ class VoxelFilter(CloudFilterInterface):
         capi.check(capi.lib().b2vf_filter_batch_device(self._h, C.c_void_p(d_in), n_total,
                                                        off.ctypes.data_as(C.POINTER(C.c_uint32)), len(off) - 1,
                                                        C.c_void_p(d_out), C.c_void_p(d_out_offsets)))
+
+    def FilterBatchAppendDevice(self, d_in, n_total, h_offsets, d_out, out_capacity, d_out_offsets, first_index, d_cursor):
+        """Batched ingest: filter B device clouds and append the results behind the ones earlier calls left in d_out
+        (device cursor, no host round trip); see b2vf_filter_batch_append_device."""
+        off = np.ascontiguousarray(h_offsets, np.uint32)
+        capi.check(capi.lib().b2vf_filter_batch_append_device(self._h, C.c_void_p(d_in), n_total,
+                                                              off.ctypes.data_as(C.POINTER(C.c_uint32)), len(off) - 1,
+                                                              C.c_void_p(d_out), out_capacity, C.c_void_p(d_out_offsets),
+                                                              first_index, C.c_void_p(d_cursor)))
 
 
 class InitialYawSearch:

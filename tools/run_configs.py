@@ -22,7 +22,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from lidar_slam_b200 import synth  # noqa: E402
-from lidar_slam_b200.registration import BoxFilter, DeviceCloud, NDTRegistration, VoxelFilter, transform_cloud  # noqa: E402
+from lidar_slam_b200.callers import FrontEnd, FrontEndDevice  # noqa: E402
+from lidar_slam_b200.registration import BoxFilter, DeviceCloud, NDTRegistration, VoxelFilter  # noqa: E402
 from oracle import oracle as O  # noqa: E402
 
 
@@ -75,96 +76,6 @@ def config1(scene):
 
 
 # ---------------------------------------------------------------------------------------------- config 2
-class FrontEnd:
-    """The front end's use of the two plug-ins (front_end.cpp:88-341, 348-424), backend-agnostic."""
-
-    def __init__(self, filt, local_filt, set_target, scan_match, key_dist=2.0, local_frames=20):
-        self.filt, self.local_filt, self.set_target, self.scan_match = filt, local_filt, set_target, scan_match
-        self.key_dist, self.local_frames = key_dist, local_frames
-        self.keyframes = []           # (pose, unfiltered cloud)
-        self.pose = None; self.last = None; self.predict = None; self.last_key = None
-        self.t_match, self.t_target, self.t_assemble = [], [], []
-
-    def _new_keyframe(self, cloud, pose):
-        self.keyframes.append((pose.copy(), cloud))
-        if len(self.keyframes) > self.local_frames:
-            self.keyframes.pop(0)
-        t0 = time.perf_counter()
-        local = np.concatenate([transform_cloud(c, T) for T, c in self.keyframes], axis=0)
-        self.t_assemble.append(1e3 * (time.perf_counter() - t0))
-        t = time.perf_counter()
-        if len(self.keyframes) >= 10:
-            local = self.local_filt(local)
-        self.set_target(local)
-        self.t_target.append(1e3 * (time.perf_counter() - t))
-        self.last_key = pose.copy()
-
-    def update(self, cloud, init_pose):
-        filtered = self.filt(cloud)
-        if self.pose is None:
-            self.pose = init_pose.astype(np.float32).copy(); self.last = self.pose.copy(); self.predict = self.pose.copy()
-            self._new_keyframe(cloud, self.pose)
-            return self.pose
-        t = time.perf_counter()
-        pose = self.scan_match(filtered, self.predict)
-        self.t_match.append(1e3 * (time.perf_counter() - t))
-        step = np.linalg.inv(self.last.astype(np.float64)) @ pose.astype(np.float64)
-        self.predict = (pose.astype(np.float64) @ step).astype(np.float32)
-        self.last = pose.copy(); self.pose = pose
-        if np.sum(np.abs(self.last_key[:3, 3] - pose[:3, 3])) > self.key_dist:
-            self._new_keyframe(cloud, pose)
-        return pose
-
-
-class FrontEndDevice(FrontEnd):
-    """The same front end with every cloud resident in HBM: the raw frame is uploaded once,
-    key frames stay on the device, the local map is assembled (AppendTransformed), filtered (FilterCloud, in
-    place) and handed to SetInputTargetCloud without a host round trip."""
-
-    def __init__(self, vf, lvf, reg, key_dist=2.0, local_frames=20):
-        super().__init__(None, None, None, None, key_dist, local_frames)
-        self.vf, self.lvf, self.reg = vf, lvf, reg
-        self.local = DeviceCloud()
-        self.filtered = DeviceCloud()
-        self.frame = DeviceCloud()          # upload target, reused; a key frame takes it over and a new one is made
-        self.t_upload = []
-
-    def _new_keyframe(self, cloud, pose):
-        self.keyframes.append((pose.copy(), cloud))
-        if len(self.keyframes) > self.local_frames:
-            self.keyframes.pop(0)
-        t0 = time.perf_counter()
-        self.local.Clear()
-        for T, c in self.keyframes:
-            self.local.AppendTransformed(c, T)
-        self.t_assemble.append(1e3 * (time.perf_counter() - t0))
-        t = time.perf_counter()
-        if len(self.keyframes) >= 10:
-            self.lvf.FilterCloud(self.local, self.local)
-        self.reg.SetInputTargetCloud(self.local)
-        self.t_target.append(1e3 * (time.perf_counter() - t))
-        self.last_key = pose.copy()
-
-    def update(self, cloud, init_pose):
-        t = time.perf_counter(); d_cloud = self.frame.Upload(cloud); self.t_upload.append(1e3 * (time.perf_counter() - t))
-        if self.pose is None:
-            self.pose = init_pose.astype(np.float32).copy(); self.last = self.pose.copy(); self.predict = self.pose.copy()
-            self._new_keyframe(d_cloud, self.pose)
-            self.frame = DeviceCloud()
-            return self.pose
-        t = time.perf_counter()
-        self.vf.FilterCloud(d_cloud, self.filtered)
-        pose = self.reg.ScanMatchCloud(self.filtered, self.predict)[2]
-        self.t_match.append(1e3 * (time.perf_counter() - t))          # frame filter + ScanMatch, both on the device
-        step = np.linalg.inv(self.last.astype(np.float64)) @ pose.astype(np.float64)
-        self.predict = (pose.astype(np.float64) @ step).astype(np.float32)
-        self.last = pose.copy(); self.pose = pose
-        if np.sum(np.abs(self.last_key[:3, 3] - pose[:3, 3])) > self.key_dist:
-            self._new_keyframe(d_cloud, pose)
-            self.frame = DeviceCloud()
-        return pose
-
-
 def config2(scene, frames, oracle_frames):
     s = 60.0 + 1.0 * np.arange(frames)
     truth = np.stack([scene.path_pose(v) for v in s])
