@@ -156,7 +156,7 @@ __device__ __forceinline__ void transform_f32(const float *T /*col-major 4x4*/, 
 // CTAs to fill 148 SMs from ~1e5 points), 256 x 16 for large ones (less look-back work per key).
 constexpr int SORT_THREADS = 256;
 constexpr int SORT_ITEMS_SMALL = 4, SORT_ITEMS_LARGE = 16;
-constexpr size_t SORT_LARGE_FROM = 2u << 20;      // points in the batch from which the large tile is used
+constexpr size_t SORT_LARGE_FROM = 600000;         // points in the batch from which the large tile is used (>= 147 tiles)
 constexpr int RADIX_BITS = 8;
 constexpr int RADIX = 1 << RADIX_BITS;
 

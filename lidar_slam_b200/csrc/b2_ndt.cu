@@ -140,55 +140,75 @@ __global__ void __launch_bounds__(256) leaf_crowded_kernel(const float4 *__restr
     const uint32_t n = *n_crowded;
     const uint32_t *__restrict__ keys = sv.keys();
     const uint32_t *__restrict__ vals = sv.vals();
-    const int l = threadIdx.x & 31;
+    const int l = threadIdx.x & 31, w = threadIdx.x >> 5;
     const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t i = (threadIdx.x >> 5) * gridDim.x + blockIdx.x; i < n; i += nwarps) {
+    // Per warp two staging groups of 128 points.  The 13 sums of a leaf are spread over the lanes: lane a < 9 owns one
+    // double sum  acc += u * v  with (u, v) = (x,1) (y,1) (z,1) (x,x) (x,y) (x,z) (y,y) (y,z) (z,z)  [mean_ += p and
+    // cov_ += p p^T; a product by 1.0 is exact], lanes 9..12 own the float centroid sums of x, y, z, intensity.  A
+    // member then costs two 4-byte shared loads, one DMUL, one DADD and one FADD per lane instead of 15 FP64
+    // operations executed redundantly by every lane; the per-sum order is still the input order.
+    __shared__ float4 stage[8][2][128];
+    __shared__ float s_one;
+    if (threadIdx.x == 0) s_one = 1.0f;
+    __syncthreads();
+    // (u, v) component offsets in floats; v == -1: the constant 1
+    const int a = (l < 13) ? l : 12;
+    const int iu = (a == 0 || a == 3 || a == 4 || a == 5 || a == 9) ? 0 : (a == 1 || a == 6 || a == 7 || a == 10) ? 1 : (a == 12) ? 3 : 2;
+    const int iv = (a == 3) ? 0 : (a == 4 || a == 6) ? 1 : (a == 5 || a == 7 || a == 8) ? 2 : -1;
+    for (uint32_t i = w * gridDim.x + blockIdx.x; i < n; i += nwarps) {
         const uint32_t j = crowded[i];
         const uint32_t s = run_start[j];
         const uint32_t e = (j + 1 < V) ? run_start[j + 1] : n_finite;
-        float cx = 0.f, cy = 0.f, cz = 0.f, ci = 0.f;
-        double sx = 0, sy = 0, sz = 0, cxx = 1, cxy = 0, cxz = 0, cyy = 1, cyz = 0, czz = 1;
-        uint32_t va[2], vb[2];
-        float4 pa[2], pb[2];
-        auto ldv = [&](uint32_t c, uint32_t (&v)[2]) {
+        uint32_t va[4], vb[4];
+        auto ldv = [&](uint32_t c, uint32_t (&v)[4]) {
 #pragma unroll
-            for (int d = 0; d < 2; ++d) { const uint32_t idx = c + d * 32 + l; v[d] = (idx < e) ? __ldg(&vals[idx]) : 0xFFFFFFFFu; }
+            for (int d = 0; d < 4; ++d) { const uint32_t idx = c + d * 32 + l; v[d] = (idx < e) ? __ldg(&vals[idx]) : 0xFFFFFFFFu; }
         };
-        auto ldp = [&](const uint32_t (&v)[2], float4 (&p)[2], uint32_t c) {
+        auto ldp = [&](const uint32_t (&v)[4], int buf, uint32_t c) {
+            float4 p[4];
 #pragma unroll
-            for (int d = 0; d < 2; ++d) {
-                p[d] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (v[d] != 0xFFFFFFFFu) { p[d] = __ldg(&pts[v[d]]); O.pts_sorted[c + d * 32 + l] = p[d]; }
+            for (int d = 0; d < 4; ++d) p[d] = (v[d] != 0xFFFFFFFFu) ? __ldg(&pts[v[d]]) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int d = 0; d < 4; ++d) {
+                stage[w][buf][d * 32 + l] = p[d];
+                if (v[d] != 0xFFFFFFFFu) O.pts_sorted[c + d * 32 + l] = p[d];
             }
         };
-        auto fold = [&](const float4 (&p)[2], uint32_t c) {
-#pragma unroll
-            for (int d = 0; d < 2; ++d) {
-                const uint32_t c0 = c + d * 32;
-                if (c0 >= e) break;
-                const int m = (e - c0 < 32u) ? (int)(e - c0) : 32;
-#pragma unroll 4
-                for (int k = 0; k < m; ++k) {
-                    const float x = __shfl_sync(0xffffffffu, p[d].x, k), y = __shfl_sync(0xffffffffu, p[d].y, k);
-                    const float z = __shfl_sync(0xffffffffu, p[d].z, k), w = __shfl_sync(0xffffffffu, p[d].w, k);
-                    B2_LEAF_ACC(x, y, z, w);
-                }
+        double dacc = (a == 3 || a == 6 || a == 8) ? 1.0 : 0.0;       // cov_ starts from Identity
+        float facc = 0.f;
+        auto fold = [&](int buf, uint32_t c) {
+            __syncwarp();
+            const float *qu = reinterpret_cast<const float *>(stage[w][buf]) + iu;
+            const float *qv = (iv >= 0) ? reinterpret_cast<const float *>(stage[w][buf]) + iv : &s_one;
+            const int sv_stride = (iv >= 0) ? 4 : 0;
+            const int m = (e - c < 128u) ? (int)(e - c) : 128;
+#pragma unroll 8
+            for (int k = 0; k < m; ++k) {
+                const float u = qu[4 * k], v = qv[sv_stride * k];
+                facc = __fadd_rn(facc, u);
+                dacc = __dadd_rn(dacc, __dmul_rn((double)u, (double)v));
             }
+            __syncwarp();
         };
         // group g is folded while the points of g+1 and the indices of g+2 are in flight
         ldv(s, va);
-        ldv(s + 64u, vb);
-        ldp(va, pa, s);
-        for (uint32_t c = s; c < e; c += 128u) {
-            ldp(vb, pb, c + 64u);
-            ldv(c + 128u, va);
-            fold(pa, c);
-            if (c + 64u >= e) break;
-            ldp(va, pa, c + 128u);
-            ldv(c + 192u, vb);
-            fold(pb, c + 64u);
+        ldv(s + 128u, vb);
+        ldp(va, 0, s);
+        for (uint32_t c = s; c < e; c += 256u) {
+            ldp(vb, 1, c + 128u);
+            ldv(c + 256u, va);
+            fold(0, c);
+            if (c + 128u >= e) break;
+            ldp(va, 0, c + 256u);
+            ldv(c + 384u, vb);
+            fold(1, c + 128u);
         }
-        if (l == 0) leaf_emit(O, j, s, e - s, keys[s], cx, cy, cz, ci, sx, sy, sz, cxx, cxy, cxz, cyy, cyz, czz);
+        double d9[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) d9[k] = __shfl_sync(0xffffffffu, dacc, k);
+        const float cx = __shfl_sync(0xffffffffu, facc, 9), cy = __shfl_sync(0xffffffffu, facc, 10);
+        const float cz = __shfl_sync(0xffffffffu, facc, 11), ci = __shfl_sync(0xffffffffu, facc, 12);
+        if (l == 0) leaf_emit(O, j, s, e - s, keys[s], cx, cy, cz, ci, d9[0], d9[1], d9[2], d9[3], d9[4], d9[5], d9[6], d9[7], d9[8]);
     }
 }
 

@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(SORT_THREADS) key_hist_kernel(const float4 *__
 // tile in shared memory and writes each digit's run to its final place with coalesced stores.  Pass 0 has no payload
 // to read: the payload is the element index.  A pass at or above the key width returns at once.
 template <int ITEMS>
-__global__ void __launch_bounds__(SORT_THREADS, (ITEMS > 8 ? 3 : 6)) onesweep_kernel(SortView sv, PlanView P, const uint32_t *__restrict__ hist,
+__global__ void __launch_bounds__(SORT_THREADS, (ITEMS > 8 ? 3 : 4)) onesweep_kernel(SortView sv, PlanView P, const uint32_t *__restrict__ hist,
                                                                 uint32_t *__restrict__ state, uint32_t *__restrict__ ticket,
                                                                 int pass) {
     const int shift = pass * RADIX_BITS;
@@ -382,7 +382,7 @@ __global__ void __launch_bounds__(SORT_THREADS, (ITEMS > 8 ? 3 : 6)) onesweep_ke
         // starts together with its predecessors (small inputs: every tile is resident at once) pays one L2 round trip
         // per LB predecessors instead of one per predecessor.  The cloud's first tile always publishes an inclusive
         // count, so the walk never leaves the cloud; words below it read as "inclusive 0".
-        constexpr int LB = 8;
+        constexpr int LB = 16;
         const int jmin = (int)sg.tile_begin;
         int j = (int)tile - 1;
         while (true) {
@@ -556,6 +556,8 @@ int VoxPipeline::plan(const uint32_t *off, size_t nB, cudaStream_t st) {
     const bool same = (nB == B && nB > 1 && h_off.size() == nB + 1 && memcmp(h_off.data(), off, (nB + 1) * 4) == 0);
     B = nB;
     N = off[nB];
+    // small tiles only while they are needed to fill the SMs: the look-back of a radix pass walks over the tiles that
+    // started together, so fewer, larger tiles are cheaper as soon as there are enough of them
     tile_elems = SORT_THREADS * (N >= SORT_LARGE_FROM ? SORT_ITEMS_LARGE : SORT_ITEMS_SMALL);
     int rc;
     if (nB <= 1) {
@@ -772,60 +774,60 @@ __global__ void __launch_bounds__(256) vf_crowded_kernel(const float4 *__restric
     out += ob;
     const uint32_t *__restrict__ keys = sv.keys();
     const uint32_t *__restrict__ vals = sv.vals();
-    const int l = threadIdx.x & 31;
+    const int l = threadIdx.x & 31, w = threadIdx.x >> 5;
     const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t i = (threadIdx.x >> 5) * gridDim.x + blockIdx.x; i < n; i += nwarps) {
+    // per warp, two staging groups of 128 points: the fold reads them back with ONE broadcast 16-byte load per member
+    // (a shuffle per component would cost four instructions, and their latency, per member)
+    __shared__ float4 stage[8][2][128];
+    for (uint32_t i = w * gridDim.x + blockIdx.x; i < n; i += nwarps) {
         const uint32_t j = crowded[i];
         uint32_t s, e;
         run_bounds(j, run_start, run_seg, run_seg_off, P, layouts, s, e);
         uint32_t va[4], vb[4];
-        float4 pa[4], pb[4];
         auto ldv = [&](uint32_t c, uint32_t (&v)[4]) {
 #pragma unroll
             for (int d = 0; d < 4; ++d) { const uint32_t idx = c + d * 32 + l; v[d] = (idx < e) ? __ldg(&vals[idx]) : 0xFFFFFFFFu; }
         };
-        auto ldp = [&](const uint32_t (&v)[4], float4 (&p)[4]) {
+        // points of a group: global -> registers -> this warp's staging buffer `buf`
+        auto ldp = [&](const uint32_t (&v)[4], int buf) {
+            float4 p[4];
 #pragma unroll
             for (int d = 0; d < 4; ++d) p[d] = (v[d] != 0xFFFFFFFFu) ? __ldg(&pts[v[d]]) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int d = 0; d < 4; ++d) stage[w][buf][d * 32 + l] = p[d];
         };
-        float ax = 0.f, ay = 0.f, az = 0.f, ai = 0.f;
-        auto fold = [&](const float4 (&p)[4], uint32_t c) {
-#pragma unroll
-            for (int d = 0; d < 4; ++d) {
-                const uint32_t c0 = c + d * 32;
-                if (c0 >= e) break;
-                const int m = (e - c0 < 32u) ? (int)(e - c0) : 32;
-                if (m == 32) {
-#pragma unroll
-                    for (int k = 0; k < 32; ++k) {
-                        ax = __fadd_rn(ax, __shfl_sync(0xffffffffu, p[d].x, k));
-                        ay = __fadd_rn(ay, __shfl_sync(0xffffffffu, p[d].y, k));
-                        az = __fadd_rn(az, __shfl_sync(0xffffffffu, p[d].z, k));
-                        ai = __fadd_rn(ai, __shfl_sync(0xffffffffu, p[d].w, k));
-                    }
-                } else {
-                    for (int k = 0; k < m; ++k) {
-                        ax = __fadd_rn(ax, __shfl_sync(0xffffffffu, p[d].x, k));
-                        ay = __fadd_rn(ay, __shfl_sync(0xffffffffu, p[d].y, k));
-                        az = __fadd_rn(az, __shfl_sync(0xffffffffu, p[d].z, k));
-                        ai = __fadd_rn(ai, __shfl_sync(0xffffffffu, p[d].w, k));
-                    }
-                }
+        // lane c (0..3) folds component c: one 4-byte shared load + one FADD per member, i.e. the order-exact add
+        // chain itself (4 cycles per member) is the cost
+        float acc = 0.f;
+        const int comp = l & 3;
+        auto fold = [&](int buf, uint32_t c) {
+            __syncwarp();
+            const float *q = reinterpret_cast<const float *>(stage[w][buf]) + comp;
+            const int m = (e - c < 128u) ? (int)(e - c) : 128;
+            if (m == 128) {
+#pragma unroll 32
+                for (int k = 0; k < 128; ++k) acc = __fadd_rn(acc, q[4 * k]);
+            } else {
+#pragma unroll 4
+                for (int k = 0; k < m; ++k) acc = __fadd_rn(acc, q[4 * k]);
             }
+            __syncwarp();
         };
         // group g is folded while the points of g+1 and the indices of g+2 are in flight
         ldv(s, va);
         ldv(s + 128u, vb);
-        ldp(va, pa);
+        ldp(va, 0);
         for (uint32_t c = s; c < e; c += 256u) {
-            ldp(vb, pb);
+            ldp(vb, 1);
             ldv(c + 256u, va);
-            fold(pa, c);
+            fold(0, c);
             if (c + 128u >= e) break;
-            ldp(va, pa);
+            ldp(va, 0);
             ldv(c + 384u, vb);
-            fold(pb, c + 128u);
+            fold(1, c + 128u);
         }
+        const float ax = __shfl_sync(0xffffffffu, acc, 0), ay = __shfl_sync(0xffffffffu, acc, 1);
+        const float az = __shfl_sync(0xffffffffu, acc, 2), ai = __shfl_sync(0xffffffffu, acc, 3);
         if (l == 0) {
             const float nn = (float)(e - s);
             out[j] = make_float4(__fdiv_rn(ax, nn), __fdiv_rn(ay, nn), __fdiv_rn(az, nn), __fdiv_rn(ai, nn));

@@ -70,7 +70,7 @@ def test_config2_front_end_trajectory_equals_oracle_front_end():
 
 
 def test_config3_map_matching_with_recrops_every_frame_vs_oracle():
-    """5 M-point map -> VoxelFilter 0.6 (bit-exact vs the oracle filter) -> BoxFilter +-100 m -> SetInputTarget; >= 50
+    """5 M-point map -> VoxelFilter 0.6 (bit-exact vs the oracle filter) -> BoxFilter +-100 m -> SetInputTarget; 125
     frames with >= 2 re-crops; every frame's pose vs the oracle running the same loop on the same filtered map; the
     device-resident crop + target build gives the same target as the host path at every re-crop."""
     from lidar_slam_b200.registration import BoxFilter, DeviceCloud, NDTRegistration, VoxelFilter
@@ -81,8 +81,8 @@ def test_config3_map_matching_with_recrops_every_frame_vs_oracle():
     o_fmap, o_idx, o_cnt, _ = O.voxel_filter(gmap, 0.6, 0.6, 0.6)
     assert np.array_equal(idx, o_idx) and np.array_equal(cnt, o_cnt) and np.array_equal(fmap, o_fmap)
 
-    frames = 64
-    s = 150.0 + 2.5 * np.arange(frames)                 # 157.5 m of driving: the +-100 m box is re-centred every ~50 m
+    frames = 125
+    s = 150.0 + 1.0 * np.arange(frames)                 # 125 m of driving: the +-100 m box is re-centred every ~50 m
     truth = np.stack([scene.path_pose(v) for v in s])
     scans = scene.scans(np.arange(frames) + 9000, truth, nthreads=max(1, (os.cpu_count() or 2) // 2))
     vf = VoxelFilter(1.3, 1.3, 1.3)
