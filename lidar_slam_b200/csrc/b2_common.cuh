@@ -150,6 +150,16 @@ __device__ __forceinline__ void transform_f32(const float *T /*col-major 4x4*/, 
 }
 #endif
 
+#ifdef __CUDACC__
+// 16-byte asynchronous copy global -> shared (LDGSTS), grouped: the gathers of the crowded-voxel kernels go straight
+// into the staging ring without holding a register (and the issuing warp) until they arrive
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+#endif
+
 // ------------------------------------------------------------------ sort plan ----------------
 // A "tile" is a run of at most tile_elems consecutive elements of ONE cloud (segment) of a concatenated
 // batch; kernels are launched one CTA per tile.  Two tile sizes: 256 threads x 4 keys for small inputs (enough

@@ -133,21 +133,26 @@ __global__ void __launch_bounds__(256) leaf_stats_kernel(const float4 *__restric
     }
 }
 
-__global__ void __launch_bounds__(256) leaf_crowded_kernel(const float4 *__restrict__ pts, SortView sv,
-                                                           const uint32_t *__restrict__ run_start, uint32_t V, uint32_t n_finite,
-                                                           LeafOut O, const uint32_t *__restrict__ crowded,
-                                                           const uint32_t *__restrict__ n_crowded) {
+constexpr int LCROWD_THREADS = 128;    // 4 warps, each with a ring of LCROWD_RING staging groups of LCROWD_GROUP points
+constexpr int LCROWD_GROUP = 128;
+constexpr int LCROWD_RING = 4;
+__global__ void __launch_bounds__(LCROWD_THREADS) leaf_crowded_kernel(const float4 *__restrict__ pts, SortView sv,
+                                                                      const uint32_t *__restrict__ run_start, uint32_t V,
+                                                                      uint32_t n_finite, LeafOut O,
+                                                                      const uint32_t *__restrict__ crowded,
+                                                                      const uint32_t *__restrict__ n_crowded) {
     const uint32_t n = *n_crowded;
     const uint32_t *__restrict__ keys = sv.keys();
     const uint32_t *__restrict__ vals = sv.vals();
     const int l = threadIdx.x & 31, w = threadIdx.x >> 5;
     const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
-    // Per warp two staging groups of 128 points.  The 13 sums of a leaf are spread over the lanes: lane a < 9 owns one
-    // double sum  acc += u * v  with (u, v) = (x,1) (y,1) (z,1) (x,x) (x,y) (x,z) (y,y) (y,z) (z,z)  [mean_ += p and
-    // cov_ += p p^T; a product by 1.0 is exact], lanes 9..12 own the float centroid sums of x, y, z, intensity.  A
-    // member then costs two 4-byte shared loads, one DMUL, one DADD and one FADD per lane instead of 15 FP64
-    // operations executed redundantly by every lane; the per-sum order is still the input order.
-    __shared__ float4 stage[8][2][128];
+    // The 13 sums of a leaf are spread over the lanes: lane a < 9 owns one double sum  acc += u * v  with (u, v) =
+    // (x,1) (y,1) (z,1) (x,x) (x,y) (x,z) (y,y) (y,z) (z,z)  [mean_ += p and cov_ += p p^T; a product by 1.0 is exact],
+    // lanes 9..12 own the float centroid sums of x, y, z, intensity.  A member then costs two 4-byte shared loads, one
+    // DMUL, one DADD and one FADD per lane instead of 15 FP64 operations executed redundantly by every lane; every sum
+    // is still formed in input order.  The members reach shared memory through asynchronous copies, three groups
+    // ahead of the fold.
+    __shared__ float4 stage[LCROWD_THREADS / 32][LCROWD_RING][LCROWD_GROUP];
     __shared__ float s_one;
     if (threadIdx.x == 0) s_one = 1.0f;
     __syncthreads();
@@ -159,50 +164,48 @@ __global__ void __launch_bounds__(256) leaf_crowded_kernel(const float4 *__restr
         const uint32_t j = crowded[i];
         const uint32_t s = run_start[j];
         const uint32_t e = (j + 1 < V) ? run_start[j + 1] : n_finite;
-        uint32_t va[4], vb[4];
         auto ldv = [&](uint32_t c, uint32_t (&v)[4]) {
 #pragma unroll
             for (int d = 0; d < 4; ++d) { const uint32_t idx = c + d * 32 + l; v[d] = (idx < e) ? __ldg(&vals[idx]) : 0xFFFFFFFFu; }
         };
-        auto ldp = [&](const uint32_t (&v)[4], int buf, uint32_t c) {
-            float4 p[4];
+        auto gather = [&](const uint32_t (&v)[4], int buf) {
 #pragma unroll
-            for (int d = 0; d < 4; ++d) p[d] = (v[d] != 0xFFFFFFFFu) ? __ldg(&pts[v[d]]) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int d = 0; d < 4; ++d) {
-                stage[w][buf][d * 32 + l] = p[d];
-                if (v[d] != 0xFFFFFFFFu) O.pts_sorted[c + d * 32 + l] = p[d];
-            }
+            for (int d = 0; d < 4; ++d)
+                if (v[d] != 0xFFFFFFFFu) cp_async16(&stage[w][buf][d * 32 + l], &pts[v[d]]);
+            cp_async_commit();
         };
         double dacc = (a == 3 || a == 6 || a == 8) ? 1.0 : 0.0;       // cov_ starts from Identity
         float facc = 0.f;
         auto fold = [&](int buf, uint32_t c) {
-            __syncwarp();
+            const int m = (e - c < (uint32_t)LCROWD_GROUP) ? (int)(e - c) : LCROWD_GROUP;
+            // the target keeps its points in voxel order (fitness buckets): this group's slice, coalesced
+#pragma unroll
+            for (int d = 0; d < 4; ++d)
+                if (d * 32 + l < m) O.pts_sorted[c + d * 32 + l] = stage[w][buf][d * 32 + l];
             const float *qu = reinterpret_cast<const float *>(stage[w][buf]) + iu;
             const float *qv = (iv >= 0) ? reinterpret_cast<const float *>(stage[w][buf]) + iv : &s_one;
-            const int sv_stride = (iv >= 0) ? 4 : 0;
-            const int m = (e - c < 128u) ? (int)(e - c) : 128;
+            const int v_stride = (iv >= 0) ? 4 : 0;
 #pragma unroll 8
             for (int k = 0; k < m; ++k) {
-                const float u = qu[4 * k], v = qv[sv_stride * k];
+                const float u = qu[4 * k], v = qv[v_stride * k];
                 facc = __fadd_rn(facc, u);
                 dacc = __dadd_rn(dacc, __dmul_rn((double)u, (double)v));
             }
-            __syncwarp();
         };
-        // group g is folded while the points of g+1 and the indices of g+2 are in flight
-        ldv(s, va);
-        ldv(s + 128u, vb);
-        ldp(va, 0, s);
-        for (uint32_t c = s; c < e; c += 256u) {
-            ldp(vb, 1, c + 128u);
-            ldv(c + 256u, va);
-            fold(0, c);
-            if (c + 128u >= e) break;
-            ldp(va, 0, c + 256u);
-            ldv(c + 384u, vb);
-            fold(1, c + 128u);
+        uint32_t v0[4], v1[4], v2[4], vn[4];
+        ldv(s, v0); ldv(s + LCROWD_GROUP, v1); ldv(s + 2 * LCROWD_GROUP, v2); ldv(s + 3 * LCROWD_GROUP, vn);
+        gather(v0, 0); gather(v1, 1); gather(v2, 2);
+        int buf = 0;
+        for (uint32_t c = s; c < e; c += LCROWD_GROUP) {
+            gather(vn, (buf + 3) & (LCROWD_RING - 1));
+            ldv(c + 4 * LCROWD_GROUP, vn);
+            cp_async_wait<3>();
+            __syncwarp();
+            fold(buf, c);
+            __syncwarp();
+            buf = (buf + 1) & (LCROWD_RING - 1);
         }
+        cp_async_wait<0>();
         double d9[9];
 #pragma unroll
         for (int k = 0; k < 9; ++k) d9[k] = __shfl_sync(0xffffffffu, dacc, k);
@@ -1711,7 +1714,7 @@ static int build_target(b2ndt *h, const float4 *d_pts, size_t n, int nbits_hint)
         if (blocks > 148 * 16) blocks = 148 * 16;
         leaf_stats_kernel<<<blocks, 256, 0, h->st>>>(d_pts, h->pipe.view(), h->pipe.run_start(), V, t.L.n_finite, O, crowded, cnt + 5);
         B2_LAUNCH_CHECK();
-        leaf_crowded_kernel<<<148 * 4, 256, 0, h->st>>>(d_pts, h->pipe.view(), h->pipe.run_start(), V, t.L.n_finite, O, crowded, cnt + 5);
+        leaf_crowded_kernel<<<148 * 8, LCROWD_THREADS, 0, h->st>>>(d_pts, h->pipe.view(), h->pipe.run_start(), V, t.L.n_finite, O, crowded, cnt + 5);
         B2_LAUNCH_CHECK();
         leaf_finish_kernel<<<(V + 127) / 128, 128, 0, h->st>>>(V, h->prm.min_pts, h->prm.eig_mult, LA, t.leaf_idx.as<int32_t>(),
                                                               t.leaf_n.as<int32_t>(), t.centroid4.as<float4>(), t.sums.as<double>(),

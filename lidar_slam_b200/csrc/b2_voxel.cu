@@ -759,15 +759,19 @@ __global__ void __launch_bounds__(256) vf_centroid_kernel(const float4 *__restri
     }
 }
 
-__global__ void __launch_bounds__(256) vf_crowded_kernel(const float4 *__restrict__ pts, SortView sv,
-                                                         const uint32_t *__restrict__ run_start,
-                                                         const uint32_t *__restrict__ run_seg,
-                                                         const uint32_t *__restrict__ run_seg_off, PlanView P,
-                                                         const VoxLayout *__restrict__ layouts, const uint32_t *__restrict__ crowded,
-                                                         const uint32_t *__restrict__ n_crowded, const uint32_t *__restrict__ out_base,
-                                                         uint32_t out_capacity,
-                                                         float4 *__restrict__ out, int32_t *__restrict__ out_idx,
-                                                         int32_t *__restrict__ out_cnt) {
+constexpr int CROWD_THREADS = 128;     // 4 warps, each with a ring of CROWD_RING staging groups of CROWD_GROUP points
+constexpr int CROWD_GROUP = 128;
+constexpr int CROWD_RING = 4;
+__global__ void __launch_bounds__(CROWD_THREADS) vf_crowded_kernel(const float4 *__restrict__ pts, SortView sv,
+                                                                   const uint32_t *__restrict__ run_start,
+                                                                   const uint32_t *__restrict__ run_seg,
+                                                                   const uint32_t *__restrict__ run_seg_off, PlanView P,
+                                                                   const VoxLayout *__restrict__ layouts,
+                                                                   const uint32_t *__restrict__ crowded,
+                                                                   const uint32_t *__restrict__ n_crowded,
+                                                                   const uint32_t *__restrict__ out_base, uint32_t out_capacity,
+                                                                   float4 *__restrict__ out, int32_t *__restrict__ out_idx,
+                                                                   int32_t *__restrict__ out_cnt) {
     const uint32_t n = *n_crowded;
     const uint32_t ob = out_base ? *out_base : 0u;
     if ((size_t)ob + sv.scalars[1] > (size_t)out_capacity) return;
@@ -776,56 +780,54 @@ __global__ void __launch_bounds__(256) vf_crowded_kernel(const float4 *__restric
     const uint32_t *__restrict__ vals = sv.vals();
     const int l = threadIdx.x & 31, w = threadIdx.x >> 5;
     const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
-    // per warp, two staging groups of 128 points: the fold reads them back with ONE broadcast 16-byte load per member
-    // (a shuffle per component would cost four instructions, and their latency, per member)
-    __shared__ float4 stage[8][2][128];
+    __shared__ float4 stage[CROWD_THREADS / 32][CROWD_RING][CROWD_GROUP];
     for (uint32_t i = w * gridDim.x + blockIdx.x; i < n; i += nwarps) {
         const uint32_t j = crowded[i];
         uint32_t s, e;
         run_bounds(j, run_start, run_seg, run_seg_off, P, layouts, s, e);
-        uint32_t va[4], vb[4];
+        // indices of a group of 128 members (four per lane)
         auto ldv = [&](uint32_t c, uint32_t (&v)[4]) {
 #pragma unroll
             for (int d = 0; d < 4; ++d) { const uint32_t idx = c + d * 32 + l; v[d] = (idx < e) ? __ldg(&vals[idx]) : 0xFFFFFFFFu; }
         };
-        // points of a group: global -> registers -> this warp's staging buffer `buf`
-        auto ldp = [&](const uint32_t (&v)[4], int buf) {
-            float4 p[4];
+        // the group's points: asynchronous 16-byte copies straight into ring slot `buf` (one commit group per call)
+        auto gather = [&](const uint32_t (&v)[4], int buf) {
 #pragma unroll
-            for (int d = 0; d < 4; ++d) p[d] = (v[d] != 0xFFFFFFFFu) ? __ldg(&pts[v[d]]) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int d = 0; d < 4; ++d) stage[w][buf][d * 32 + l] = p[d];
+            for (int d = 0; d < 4; ++d)
+                if (v[d] != 0xFFFFFFFFu) cp_async16(&stage[w][buf][d * 32 + l], &pts[v[d]]);
+            cp_async_commit();
         };
         // lane c (0..3) folds component c: one 4-byte shared load + one FADD per member, i.e. the order-exact add
         // chain itself (4 cycles per member) is the cost
         float acc = 0.f;
         const int comp = l & 3;
         auto fold = [&](int buf, uint32_t c) {
-            __syncwarp();
             const float *q = reinterpret_cast<const float *>(stage[w][buf]) + comp;
-            const int m = (e - c < 128u) ? (int)(e - c) : 128;
-            if (m == 128) {
+            const int m = (e - c < (uint32_t)CROWD_GROUP) ? (int)(e - c) : CROWD_GROUP;
+            if (m == CROWD_GROUP) {
 #pragma unroll 32
-                for (int k = 0; k < 128; ++k) acc = __fadd_rn(acc, q[4 * k]);
+                for (int k = 0; k < CROWD_GROUP; ++k) acc = __fadd_rn(acc, q[4 * k]);
             } else {
 #pragma unroll 4
                 for (int k = 0; k < m; ++k) acc = __fadd_rn(acc, q[4 * k]);
             }
-            __syncwarp();
         };
-        // group g is folded while the points of g+1 and the indices of g+2 are in flight
-        ldv(s, va);
-        ldv(s + 128u, vb);
-        ldp(va, 0);
-        for (uint32_t c = s; c < e; c += 256u) {
-            ldp(vb, 1);
-            ldv(c + 256u, va);
-            fold(0, c);
-            if (c + 128u >= e) break;
-            ldp(va, 0);
-            ldv(c + 384u, vb);
-            fold(1, c + 128u);
+        // Software pipeline over groups: while group g is folded, the points of g+1 .. g+3 are in flight into the
+        // ring and the indices of g+4 into registers.
+        uint32_t v0[4], v1[4], v2[4], vn[4];
+        ldv(s, v0); ldv(s + CROWD_GROUP, v1); ldv(s + 2 * CROWD_GROUP, v2); ldv(s + 3 * CROWD_GROUP, vn);
+        gather(v0, 0); gather(v1, 1); gather(v2, 2);
+        int buf = 0;
+        for (uint32_t c = s; c < e; c += CROWD_GROUP) {
+            gather(vn, (buf + 3) & (CROWD_RING - 1));            // group g+3 (an empty commit group past the end)
+            ldv(c + 4 * CROWD_GROUP, vn);
+            cp_async_wait<3>();                                   // group g has landed (this lane's copies) ...
+            __syncwarp();                                         // ... and every other lane's
+            fold(buf, c);
+            __syncwarp();                                         // slot `buf` is rewritten three groups from now
+            buf = (buf + 1) & (CROWD_RING - 1);
         }
+        cp_async_wait<0>();
         const float ax = __shfl_sync(0xffffffffu, acc, 0), ay = __shfl_sync(0xffffffffu, acc, 1);
         const float az = __shfl_sync(0xffffffffu, acc, 2), ai = __shfl_sync(0xffffffffu, acc, 3);
         if (l == 0) {
@@ -941,7 +943,7 @@ static int vf_launch_centroids(b2vf *h, const float4 *d_in, float4 *d_out, int32
                                                  h->pipe.plan_view(), h->pipe.layouts(), h->d_crowded.as<uint32_t>(), ncr, d_out_base,
                                                  out_capacity, d_out, d_idx, d_cnt);
     B2_LAUNCH_CHECK();
-    vf_crowded_kernel<<<148 * 4, 256, 0, h->st>>>(d_in, h->pipe.view(), h->pipe.run_start(), h->pipe.run_seg(), h->pipe.run_seg_off(),
+    vf_crowded_kernel<<<148 * 8, CROWD_THREADS, 0, h->st>>>(d_in, h->pipe.view(), h->pipe.run_start(), h->pipe.run_seg(), h->pipe.run_seg_off(),
                                                  h->pipe.plan_view(), h->pipe.layouts(), h->d_crowded.as<uint32_t>(), ncr, d_out_base,
                                                  out_capacity, d_out, d_idx, d_cnt);
     B2_LAUNCH_CHECK();
