@@ -186,6 +186,14 @@ int  b2cloud_distortion_adjust(b2cloud *src, float scan_period, const double lin
                                const double angular_velocity[3], b2cloud *dst);
 /* VoxelFilter::Filter on device clouds (src == dst allowed) */
 int  b2vf_filter_cloud(b2vf *h, b2cloud *src, b2cloud *dst);
+/* Fused ingest of a raw scan in HBM: DistortionAdjust::AdjustCloud (distortion_adjust.cpp:16-69; both velocities NULL
+ * = no de-skew) + pcl::removeNaNFromPointCloud (front_end.cpp:92) + VoxelFilter::Filter (front_end.cpp:106-107) with
+ * the first two folded into the first kernel of the filter (one pass over the raw points, no compaction, no extra
+ * host round trip).  filtered == VoxelFilter(removeNaN(deskew(src))) bit for bit.  ingested (may be NULL; not src)
+ * receives the de-skewed scan with src's size and NaN points where a point was dropped: consumers of device clouds
+ * skip non-finite points, b2cloud_remove_nan compacts them away. */
+int  b2vf_ingest_filter_cloud(b2vf *h, b2cloud *src, float scan_period, const double linear_velocity[3],
+                              const double angular_velocity[3], b2cloud *filtered, b2cloud *ingested);
 /* SetInputTarget / ScanMatch on device clouds; result_cloud may be NULL */
 int  b2ndt_set_target_cloud(b2ndt *h, b2cloud *target);
 int  b2ndt_align_cloud(b2ndt *h, b2cloud *src, const float guess[16], float pose_out[16], b2ndt_result *res,

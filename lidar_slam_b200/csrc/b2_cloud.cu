@@ -43,41 +43,6 @@ struct BoxArg {
     }
 };
 
-// DistortionAdjust::AdjustCloud (src/models/scan_adjust/distortion_adjust.cpp:16-69), one point:
-//   rotate about z so that the scan's first point has azimuth 0, azimuth -> time inside the sweep, undo the
-//   motion p' = Rz(wz t) Ry(wy t) Rx(wx t) p + v t, rotate back.  Point 0 and the 5 degree sector around azimuth 0
-//   are dropped; intensity is not carried over (the reference builds fresh points).
-struct DeskewArg {
-    float rin[9];        // rotation by -start_orientation (row-major)
-    float rout[9];       // rotation by +start_orientation
-    float vel[3], rate[3];
-    float scan_period;
-    __device__ __forceinline__ bool operator()(const float4 p, uint32_t i, float4 &out) const {
-        out = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (i == 0) return false;
-        const float x = rin[0] * p.x + rin[1] * p.y + rin[2] * p.z;
-        const float y = rin[3] * p.x + rin[4] * p.y + rin[5] * p.z;
-        const float z = rin[6] * p.x + rin[7] * p.y + rin[8] * p.z;
-        float o = atan2f(y, x);
-        if (o < 0.0f) o = (float)((double)o + 2.0 * 3.14159265358979323846);
-        const float delete_space = (float)(5.0 * 3.14159265358979323846 / 180.0);
-        if (o < delete_space || (2.0 * 3.14159265358979323846 - (double)o) < (double)delete_space) return false;
-        const float t = (float)((double)fabsf(o) / (double)(float)(2.0 * 3.14159265358979323846) * (double)scan_period - (double)scan_period / 2.0);
-        float sx, cx, sy, cy, sz, cz;
-        sincosf(rate[0] * t, &sx, &cx);
-        sincosf(rate[1] * t, &sy, &cy);
-        sincosf(rate[2] * t, &sz, &cz);
-        const float x1 = x, y1 = cx * y - sx * z, z1 = sx * y + cx * z;             // Rx
-        const float x2 = cy * x1 + sy * z1, y2 = y1, z2 = -sy * x1 + cy * z1;       // Ry
-        const float x3 = cz * x2 - sz * y2, y3 = sz * x2 + cz * y2, z3 = z2;        // Rz
-        const float ax = x3 + vel[0] * t, ay = y3 + vel[1] * t, az = z3 + vel[2] * t;
-        out.x = rout[0] * ax + rout[1] * ay + rout[2] * az;
-        out.y = rout[3] * ax + rout[4] * ay + rout[5] * az;
-        out.z = rout[6] * ax + rout[7] * ay + rout[8] * az;
-        return true;
-    }
-};
-
 // pass 1: kept points per tile
 template <class Op>
 __global__ void __launch_bounds__(CROP_THREADS) crop_count_kernel(const float4 *__restrict__ src, uint32_t n, Op B,
@@ -228,6 +193,7 @@ extern "C" int b2cloud_upload(b2cloud *c, const void *pts, size_t n, size_t stri
     if (n >= 0xFFFFFFF0ull) { set_error("b2cloud_upload: cloud too large"); return B2_ERR_INVALID; }
     B2_CUDA(cudaSetDevice(c->device));
     c->n = 0;
+    c->first_known = false;
     if ((rc = c->reserve(n))) return rc;
     if (n) {
         std::lock_guard<std::mutex> lk(g_stage_mu);
@@ -237,6 +203,11 @@ extern "C" int b2cloud_upload(b2cloud *c, const void *pts, size_t n, size_t stri
         B2_CUDA(cudaStreamSynchronize(c->st));
     }
     c->n = n;
+    if (n) {     // the de-skew needs the azimuth of the scan's first point: known here, so no device read later
+        const char *q = (const char *)pts;
+        c->first_xy[0] = ((const float *)q)[0]; c->first_xy[1] = ((const float *)q)[1];
+        c->first_known = true;
+    }
     return 0;
 }
 
@@ -288,6 +259,7 @@ extern "C" int b2cloud_append_transformed(b2cloud *dst, b2cloud *src, const floa
     B2_LAUNCH_CHECK();
     B2_CUDA(cudaStreamSynchronize(dst->st));
     dst->n += src->n;
+    dst->first_known = false;
     return 0;
 }
 
@@ -322,6 +294,7 @@ static int compact_cloud(const char *fn, b2cloud *src, b2cloud *dst, const Op &B
     B2_CUDA(cudaStreamSynchronize(dst->st));
     if (in_place) { const DevBuf t = dst->pts; dst->pts = dst->alt; dst->alt = t; }
     dst->n = *dst->h_small.as<uint32_t>();
+    dst->first_known = false;
     return 0;
 }
 
@@ -345,19 +318,8 @@ extern "C" int b2cloud_distortion_adjust(b2cloud *src, float scan_period, const 
     B2_CUDA(cudaMemcpyAsync(src->h_small.p, src->pts.p, 16, cudaMemcpyDeviceToHost, src->st));
     B2_CUDA(cudaStreamSynchronize(src->st));
     const float *p0 = src->h_small.as<float>();
-    const float start = atan2f(p0[1], p0[0]);
-    const float c = (float)std::cos((double)start), s = (float)std::sin((double)start);
     DeskewArg D;
-    const float rot[9] = {c, -s, 0.f, s, c, 0.f, 0.f, 0.f, 1.f};          // AngleAxisf(start, UnitZ).matrix()
-    const float inv[9] = {c, s, 0.f, -s, c, 0.f, 0.f, 0.f, 1.f};          // its inverse
-    for (int k = 0; k < 9; ++k) { D.rin[k] = inv[k]; D.rout[k] = rot[k]; }
-    const float v[3] = {(float)linear_velocity[0], (float)linear_velocity[1], (float)linear_velocity[2]};
-    const float w[3] = {(float)angular_velocity[0], (float)angular_velocity[1], (float)angular_velocity[2]};
-    for (int r = 0; r < 3; ++r) {                                         // velocity_ = rotate_matrix * velocity_ (:31-32)
-        D.vel[r] = rot[3 * r] * v[0] + rot[3 * r + 1] * v[1] + rot[3 * r + 2] * v[2];
-        D.rate[r] = rot[3 * r] * w[0] + rot[3 * r + 1] * w[1] + rot[3 * r + 2] * w[2];
-    }
-    D.scan_period = scan_period;
+    make_deskew_arg(p0[0], p0[1], scan_period, linear_velocity, angular_velocity, D);
     return compact_cloud("b2cloud_distortion_adjust", src, dst, D);
 }
 

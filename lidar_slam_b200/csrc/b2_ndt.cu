@@ -1175,6 +1175,15 @@ __global__ void __launch_bounds__(NDT_THREADS, NDT_MIN_CTAS) ndt_match_kernel(Gr
     __syncthreads();
 
     const uint32_t stride = C * NDT_NSW * 32u;
+#ifdef NDT_TIMING
+    // single-match trace (tools/ only): per pass, clock64 at the phase boundaries seen by CTA `A.trace_rank`
+#define TRC(slot_) do { if (A.timing && crank == 0 && match == 0 && trc_pass < 6 && (tid == trc_tid)) A.timing[32 + trc_pass * 8 + (slot_)] = (unsigned long long)(clock64() - trc_t0); } while (0)
+    const long long trc_t0 = clock64();
+    int trc_pass = 0;
+    const int trc_tid = is_compute ? 0 : NDT_NCW * 32;
+#else
+#define TRC(slot_) do { } while (0)
+#endif
     // The two roles never share code after this point (ptxas sizes each branch for its own register
     // budget); they meet at CTA-wide barriers issued from both branches.
     if (!is_compute) {
@@ -1184,7 +1193,12 @@ __global__ void __launch_bounds__(NDT_THREADS, NDT_MIN_CTAS) ndt_match_kernel(Gr
         while (true) {
             // rounds are dealt out CTA-first (round = sw * C + crank): the source is in voxel order, so consecutive
             // rounds are spatial neighbours with similar hit counts and every CTA gets an even sample of the scan
+            TRC(0);
             search_pass(S, G, A.src, first, last, first + (sw * C + crank) * 32u, stride, SL.ctl.T, sw, lane, st);
+            TRC(1);
+#ifdef NDT_TIMING
+            ++trc_pass;
+#endif
             cta_barrier();                          // (1) all pairs of the pass consumed, partials written
             if (C > 1) cluster.sync();
             cta_barrier();                          // (2) totals ready
@@ -1201,7 +1215,9 @@ __global__ void __launch_bounds__(NDT_THREADS, NDT_MIN_CTAS) ndt_match_kernel(Gr
         ds.pass_id = 0;
         while (true) {
             (void)compute_drain(S, G, K, SL.ctl, warp, lane, ds, SL.warp_part[warp]);
+            TRC(2);
             cta_barrier();                              // (1)
+            TRC(3);
             // ---------------- deterministic reduction: CTA -> cluster (fixed order) ----------------
             if (tid < NACC) {
                 double s = 0.0;
@@ -1211,6 +1227,7 @@ __global__ void __launch_bounds__(NDT_THREADS, NDT_MIN_CTAS) ndt_match_kernel(Gr
             }
             if (C > 1) {
                 cluster.sync();
+                TRC(4);
                 if (tid < NACC) {
                     // all remote (DSMEM) loads are issued before the first one is consumed; summed in rank order
                     double v[16];
@@ -1225,12 +1242,17 @@ __global__ void __launch_bounds__(NDT_THREADS, NDT_MIN_CTAS) ndt_match_kernel(Gr
                 if (tid < NACC) SL.raw_total[tid] = SL.cta_part[parity][tid];
             }
             cta_barrier();                              // (2)
+            TRC(5);
             // ---------------- controller: Newton step + More-Thuente state machine (warp 0) ----------------
             if (warp == 0) {
                 const int go = controller_step(SL, K, A.deriv_only, lane);
                 if (lane == 0) SL.go = go;
             }
             cta_barrier();                              // (3)
+            TRC(6);
+#ifdef NDT_TIMING
+            ++trc_pass;
+#endif
             if (!SL.go) break;
             parity ^= 1;
         }
@@ -1898,9 +1920,25 @@ static int launch_match(b2ndt *h, const MatchArgs &A, size_t B, int C) {
     cfg.attrs = at; cfg.numAttrs = 1;
     NdtConst K = h->K;
     MatchArgs Ac = A;
+#ifdef NDT_TIMING
+    static unsigned long long *d_tr = nullptr;
+    if (!d_tr) cudaMalloc(&d_tr, 96 * 8);
+    cudaMemsetAsync(d_tr, 0, 96 * 8, h->st);
+    Ac.timing = d_tr;
+#endif
     cudaError_t e = cudaLaunchKernelEx(&cfg, ndt_match_kernel, G, K, Ac);
     b2::count_launch();
     if (e != cudaSuccess) { set_error("ndt_match_kernel launch failed: %s", cudaGetErrorString(e)); return B2_ERR_CUDA; }
+#ifdef NDT_TIMING
+    if (B == 1 && !A.deriv_only) {
+        unsigned long long t[96];
+        cudaStreamSynchronize(h->st);
+        cudaMemcpy(t, d_tr, sizeof(t), cudaMemcpyDeviceToHost);
+        for (int p = 0; p < 3; ++p)
+            fprintf(stderr, "[ndt trace] C %d pass %d | search: start %llu finish %llu | compute: drained %llu b1 %llu csync %llu totals(b2) %llu ctl(b3) %llu\n",
+                    C, p, t[32 + p * 8 + 0], t[32 + p * 8 + 1], t[32 + p * 8 + 2], t[32 + p * 8 + 3], t[32 + p * 8 + 4], t[32 + p * 8 + 5], t[32 + p * 8 + 6]);
+    }
+#endif
     return 0;
 }
 

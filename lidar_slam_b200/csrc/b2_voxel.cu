@@ -170,16 +170,23 @@ __device__ void compute_layout(const float mn[3], const float mx[3], uint32_t n_
 
 // ---- kernel 1: per-tile bounding boxes; the LAST CTA to finish (ticket in scalars[2]) folds them per cloud, writes
 // the PCL layouts and resets the tickets of the kernels that follow.  Also clears the digit histograms.
-__global__ void __launch_bounds__(SORT_THREADS) bbox_layout_kernel(const float4 *__restrict__ pts, PlanView P, float lx, float ly,
+// Op is the fused ingest (b2_cloud.cuh): the point is transformed / dropped first, the result (a dropped point = a NaN point)
+// is written to pts_out for the kernels that follow, and the box is taken over the results.
+template <class Op>
+__global__ void __launch_bounds__(SORT_THREADS) bbox_layout_kernel(const float4 *__restrict__ pts, float4 *__restrict__ pts_out, Op op,
+                                                                   PlanView P, float lx, float ly,
                                                                    float lz, float *__restrict__ part,
                                                                    VoxLayout *__restrict__ layouts, uint32_t *__restrict__ scalars,
                                                                    uint32_t *__restrict__ hist, uint32_t hist_words) {
     const TileDesc t = get_tile(P, blockIdx.x);
     float mn0 = FLT_MAX, mn1 = FLT_MAX, mn2 = FLT_MAX, mx0 = -FLT_MAX, mx1 = -FLT_MAX, mx2 = -FLT_MAX;
     uint32_t cnt = 0;
+    const uint32_t seg_begin = get_seg(P, t.seg).begin;
     for (uint32_t k = threadIdx.x; k < t.count; k += SORT_THREADS) {
-        const float4 p = __ldg(&pts[t.begin + k]);
-        if (finite3(p.x, p.y, p.z)) {
+        float4 p;
+        const bool keep = op(__ldg(&pts[t.begin + k]), t.begin + k - seg_begin, p);
+        if (pts_out) pts_out[t.begin + k] = p;
+        if (keep) {
             mn0 = fminf(mn0, p.x); mn1 = fminf(mn1, p.y); mn2 = fminf(mn2, p.z);
             mx0 = fmaxf(mx0, p.x); mx1 = fmaxf(mx1, p.y); mx2 = fmaxf(mx2, p.z);
             ++cnt;
@@ -633,25 +640,35 @@ int VoxPipeline::sort_and_runs(int npass_launch, cudaStream_t st) {
     return 0;
 }
 
-int VoxPipeline::run(const float4 *d_pts, float lx, float ly, float lz, int nbits_hint, cudaStream_t st) {
-    const uint32_t nB = (uint32_t)B, nt = (uint32_t)ntiles;
-    uint32_t *sc = d_scalars.as<uint32_t>();
-    VoxLayout *lay = d_layouts.as<VoxLayout>();
+template <class Op>
+static int run_pipeline(VoxPipeline &pp, const float4 *d_pts, float4 *d_pts_out, const Op &op, float lx, float ly, float lz,
+                        int nbits_hint, cudaStream_t st, int (VoxPipeline::*tail)(int, cudaStream_t)) {
+    const uint32_t nB = (uint32_t)pp.B, nt = (uint32_t)pp.ntiles;
+    uint32_t *sc = pp.d_scalars.as<uint32_t>();
+    VoxLayout *lay = pp.d_layouts.as<VoxLayout>();
     if (nt == 0) {
-        empty_plan_kernel<<<(nB + 1 + 127) / 128, 128, 0, st>>>(lay, sc, d_run_seg_off.as<uint32_t>(), nB, lx, ly, lz);
+        empty_plan_kernel<<<(nB + 1 + 127) / 128, 128, 0, st>>>(lay, sc, pp.d_run_seg_off.as<uint32_t>(), nB, lx, ly, lz);
         B2_LAUNCH_CHECK();
         return 0;
     }
-    const PlanView P = plan_view();
-    bbox_layout_kernel<<<nt, SORT_THREADS, 0, st>>>(d_pts, P, lx, ly, lz, d_bbox_part.as<float>(), lay, sc, d_hist.as<uint32_t>(),
-                                                   nB * 4 * RADIX);
+    const PlanView P = pp.plan_view();
+    bbox_layout_kernel<Op><<<nt, SORT_THREADS, 0, st>>>(d_pts, d_pts_out, op, P, lx, ly, lz, pp.d_bbox_part.as<float>(), lay, sc,
+                                                       pp.d_hist.as<uint32_t>(), nB * 4 * RADIX);
     B2_LAUNCH_CHECK();
-    key_hist_kernel<true><<<nt, SORT_THREADS, 0, st>>>(d_pts, P, lay, d_keys[0].as<uint32_t>(), d_hist.as<uint32_t>(),
-                                                      d_state.as<uint32_t>(), sc);
+    key_hist_kernel<true><<<nt, SORT_THREADS, 0, st>>>(d_pts_out ? d_pts_out : d_pts, P, lay, pp.d_keys[0].as<uint32_t>(),
+                                                      pp.d_hist.as<uint32_t>(), pp.d_state.as<uint32_t>(), sc);
     B2_LAUNCH_CHECK();
     int passes = 32 / RADIX_BITS;
     if (nbits_hint > 0) passes = (nbits_hint + RADIX_BITS - 1) / RADIX_BITS;
-    return sort_and_runs(passes, st);
+    return (pp.*tail)(passes, st);
+}
+
+int VoxPipeline::run(const float4 *d_pts, float lx, float ly, float lz, int nbits_hint, cudaStream_t st) {
+    return run_pipeline(*this, d_pts, nullptr, NoIngest(), lx, ly, lz, nbits_hint, st, &VoxPipeline::sort_and_runs);
+}
+
+int VoxPipeline::run_ingest(const float4 *d_raw, float4 *d_ingested, const IngestOp &op, float lx, float ly, float lz, cudaStream_t st) {
+    return run_pipeline(*this, d_raw, d_ingested, op, lx, ly, lz, 0, st, &VoxPipeline::sort_and_runs);
 }
 
 int VoxPipeline::run_prepared(uint32_t invalid_key, int nbits, cudaStream_t st) {
@@ -1040,6 +1057,8 @@ extern "C" int b2vf_filter(b2vf *h, const void *in, size_t n, size_t stride, siz
     return 0;
 }
 
+extern "C" int b2cloud_remove_nan(b2cloud *src, b2cloud *dst);
+
 extern "C" int b2vf_filter_batch_device(b2vf *h, const void *d_in_f4, size_t n_total, const uint32_t *h_offsets, size_t B,
                                         void *d_out_f4, uint32_t *d_out_offsets) {
     if (!h || !h_offsets || !d_out_offsets) { set_error("b2vf_filter_batch_device: NULL argument"); return B2_ERR_INVALID; }
@@ -1074,6 +1093,66 @@ extern "C" int b2vf_filter_batch_append_device(b2vf *h, const void *d_in_f4, siz
     if ((rc = vf_launch_centroids(h, (const float4 *)d_in_f4, (float4 *)d_out_f4, nullptr, nullptr, n_total, d_cursor, (uint32_t)out_capacity))) return rc;
     vf_append_kernel<<<1, 256, 0, h->st>>>(h->pipe.run_seg_off(), (uint32_t)B, d_out_offsets + first_index, d_cursor, (uint32_t)out_capacity);
     B2_LAUNCH_CHECK();
+    return 0;
+}
+
+// Fused ingest + VoxelFilter for a raw scan in HBM: scan de-skew (DistortionAdjust::AdjustCloud, data_pretreat;
+// linear_velocity == angular_velocity == NULL skips it) + pcl::removeNaNFromPointCloud (front_end.cpp:92) +
+// VoxelFilter::Filter (front_end.cpp:106-107) in ONE pass over the raw points in front of the sort: the de-skewed
+// point (or a NaN point for a dropped one) and the bounding box come out of the same kernel.  `filtered` receives
+// exactly VoxelFilter(removeNaN(deskew(src))); `ingested` (may be NULL, must not be src) receives the de-skewed cloud
+// with src's size, dropped points as NaN points (every consumer of a device cloud skips those; b2cloud_remove_nan
+// compacts them away when the count matters).
+extern "C" int b2vf_ingest_filter_cloud(b2vf *h, b2cloud *src, float scan_period, const double linear_velocity[3],
+                                        const double angular_velocity[3], b2cloud *filtered, b2cloud *ingested) {
+    if (!h || !src || !filtered) { set_error("b2vf_ingest_filter_cloud: NULL argument"); return B2_ERR_INVALID; }
+    if ((linear_velocity == nullptr) != (angular_velocity == nullptr)) { set_error("b2vf_ingest_filter_cloud: give both velocities or neither"); return B2_ERR_INVALID; }
+    if (filtered == src || ingested == src || (ingested && ingested == filtered)) { set_error("b2vf_ingest_filter_cloud: outputs must be distinct from the source and from each other"); return B2_ERR_INVALID; }
+    if (src->device != h->device || filtered->device != h->device || (ingested && ingested->device != h->device)) {
+        set_error("b2vf_ingest_filter_cloud: handle and clouds live on different devices"); return B2_ERR_INVALID;
+    }
+    B2_CUDA(cudaSetDevice(h->device));
+    const size_t n = src->n;
+    filtered->n = 0; filtered->first_known = false;
+    if (ingested) { ingested->n = 0; ingested->first_known = false; }
+    if (n == 0) return 0;
+    int rc;
+    IngestOp op;
+    memset(&op, 0, sizeof(op));
+    if (linear_velocity) {
+        float x0 = src->first_xy[0], y0 = src->first_xy[1];
+        if (!src->first_known) {       // a cloud produced on the device: fetch its first point (the start azimuth)
+            if ((rc = h->h_misc.reserve(256))) return rc;
+            B2_CUDA(cudaMemcpyAsync(h->h_misc.p, src->pts.p, 16, cudaMemcpyDeviceToHost, h->st));
+            B2_CUDA(cudaStreamSynchronize(h->st));
+            x0 = h->h_misc.as<float>()[0]; y0 = h->h_misc.as<float>()[1];
+        }
+        make_deskew_arg(x0, y0, scan_period, linear_velocity, angular_velocity, op.D);
+        op.deskew = 1;
+    }
+    float4 *ing;
+    if (ingested) { if ((rc = ingested->reserve(n))) return rc; ing = ingested->d(); }
+    else { if ((rc = h->d_in.reserve(n * 16))) return rc; ing = h->d_in.as<float4>(); }
+    if ((rc = filtered->reserve(n))) return rc;
+    if ((rc = h->h_misc.reserve(256))) return rc;
+    uint32_t off[2] = {0u, (uint32_t)n};
+    if ((rc = h->pipe.plan(off, 1, h->st))) return rc;
+    if ((rc = h->pipe.run_ingest(src->d(), ing, op, h->leaf[0], h->leaf[1], h->leaf[2], h->st))) return rc;
+    if ((rc = vf_launch_centroids(h, ing, filtered->d(), nullptr, nullptr, n))) return rc;
+    uint32_t *misc = h->h_misc.as<uint32_t>();
+    B2_CUDA(cudaMemcpyAsync(misc, h->pipe.scalars(), 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->st));
+    B2_CUDA(cudaMemcpyAsync(misc + 8, h->pipe.layouts(), sizeof(VoxLayout), cudaMemcpyDeviceToHost, h->st));
+    B2_CUDA(cudaStreamSynchronize(h->st));
+    VoxLayout L;
+    memcpy(&L, misc + 8, sizeof(L));
+    if (ingested) ingested->n = n;
+    if (!L.ok) {
+        if (L.n_finite == 0) return 0;
+        // PCL: "Leaf size is too small for the input dataset" -> output = *input (here: the kept points, compacted)
+        if (!ingested) { set_error("b2vf_ingest_filter_cloud: leaf size too small for the cloud (PCL would return the input)"); return B2_ERR_INVALID; }
+        return b2cloud_remove_nan(ingested, filtered);
+    }
+    filtered->n = misc[1];
     return 0;
 }
 
@@ -1114,7 +1193,7 @@ extern "C" int b2vf_filter_cloud(b2vf *h, b2cloud *src, b2cloud *dst) {
             B2_CUDA(cudaMemcpyAsync(dst->pts.p, src->pts.p, n * 16, cudaMemcpyDeviceToDevice, h->st));
             B2_CUDA(cudaStreamSynchronize(h->st));
         }
-        dst->n = n;
+        dst->n = n; dst->first_known = false;
         return 0;
     }
     const size_t M = misc[1];
@@ -1122,6 +1201,6 @@ extern "C" int b2vf_filter_cloud(b2vf *h, b2cloud *src, b2cloud *dst) {
         B2_CUDA(cudaMemcpyAsync(src->pts.p, out, M * 16, cudaMemcpyDeviceToDevice, h->st));
         B2_CUDA(cudaStreamSynchronize(h->st));
     }
-    dst->n = M;
+    dst->n = M; dst->first_known = false;
     return 0;
 }

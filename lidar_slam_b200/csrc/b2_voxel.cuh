@@ -61,6 +61,9 @@ struct VoxPipeline {
     // Run bbox/layout/keys/sort/run-heads on packed float4 points (device).  nbits_hint > 0 limits the
     // number of radix passes from the host side (must be >= the true key width); 0 = decide on device.
     int run(const float4 *d_pts, float lx, float ly, float lz, int nbits_hint, cudaStream_t st);
+    // The same with the fused ingest in front (b2_cloud.cuh): d_raw is transformed / marked point by point into
+    // d_ingested by the first kernel, everything after it works on d_ingested.
+    int run_ingest(const float4 *d_raw, float4 *d_ingested, const struct IngestOp &op, float lx, float ly, float lz, cudaStream_t st);
     // Generic stable sort + run detection for keys the caller wrote itself: after plan(), fill keys0() (one
     // uint32 key per element, key == invalid_key drops the element to the end / out of the runs) and call this with
     // the key width in bits.  Results as after run().
@@ -88,7 +91,6 @@ struct VoxPipeline {
     const uint32_t *scalars() const { return d_scalars.as<uint32_t>(); }
     void release();
 
-private:
     int sort_and_runs(int npass_launch, cudaStream_t st);
 };
 

@@ -388,6 +388,23 @@ class VoxelFilter(CloudFilterInterface):
         capi.check(capi.lib().b2vf_filter_cloud(self._h, src._h, dst._h))
         return dst
 
+    def IngestFilterCloud(self, src, filtered=None, ingested=None, scan_period=0.1, linear_velocity=None, angular_velocity=None):
+        """Fused ingest of a raw device scan: de-skew (when velocities are given) + NaN removal + this filter in one
+        pipeline run (b2vf_ingest_filter_cloud).  -> (filtered, ingested); `ingested` keeps src's size with NaN points
+        where a point was dropped."""
+        if filtered is None:
+            filtered = DeviceCloud(device=src_device(src))
+        lin = ang = None
+        if linear_velocity is not None:
+            lin = np.ascontiguousarray(linear_velocity, np.float64)
+            ang = np.ascontiguousarray(angular_velocity, np.float64)
+        dp = C.POINTER(C.c_double)
+        capi.check(capi.lib().b2vf_ingest_filter_cloud(self._h, src._h, float(scan_period),
+                                                       lin.ctypes.data_as(dp) if lin is not None else None,
+                                                       ang.ctypes.data_as(dp) if ang is not None else None,
+                                                       filtered._h, ingested._h if ingested is not None else None))
+        return filtered, ingested
+
     def FilterBatchDevice(self, d_in, n_total, h_offsets, d_out, d_out_offsets):
         off = np.ascontiguousarray(h_offsets, np.uint32)
         capi.check(capi.lib().b2vf_filter_batch_device(self._h, C.c_void_p(d_in), n_total,

@@ -58,3 +58,43 @@ def test_gpu_deskew_matches_reference_and_oracle():
     # device-resident, empty and single-point clouds
     assert len(da.AdjustCloudDevice(DeviceCloud(np.zeros((0, 4), np.float32)))) == 0
     assert len(da.AdjustCloudDevice(DeviceCloud(np.array([[1, 2, 3, 4]], np.float32)))) == 0
+
+
+@pytest.mark.gpu
+def test_gpu_fused_ingest_equals_the_three_call_sequence():
+    """b2vf_ingest_filter_cloud (de-skew + NaN removal folded into the first kernel of the voxel filter, one pipeline
+    run) against DistortionAdjust -> removeNaN -> VoxelFilter as three calls: filtered clouds bit-identical, and the
+    ingested cloud with its NaN holes compacted away == the sequence's cloud.  Also without de-skew (NaN removal only),
+    for a cloud uploaded from the host and for one produced on the device."""
+    from lidar_slam_b200 import capi
+    from lidar_slam_b200.registration import DeviceCloud, DistortionAdjust, VoxelFilter
+    da = DistortionAdjust()
+    vf = VoxelFilter(1.3, 1.3, 1.3)
+    for scan, lin, ang, period, ref in cases():
+        scan = scan.copy()
+        scan[5::97, 1] = np.nan                       # the reference removes NaNs after the de-skew (front_end.cpp:92)
+        scan[11::301, 2] = np.inf
+        for on_device in (False, True):
+            src = DeviceCloud(scan)
+            if on_device:                              # a cloud written by a device operation: no cached first point
+                tmp = DeviceCloud()
+                tmp.AppendTransformed(src, np.eye(4, dtype=np.float32))
+                src = tmp
+            da.SetMotionInfo(period, lin, ang)
+            seq = da.AdjustCloudDevice(src).RemoveNaN()
+            seq_f = vf.FilterCloud(seq)
+            l0 = capi.launches()
+            ing = DeviceCloud()
+            fused_f, _ = vf.IngestFilterCloud(src, ingested=ing, scan_period=period, linear_velocity=lin, angular_velocity=ang)
+            fused_launches = capi.launches() - l0
+            assert np.array_equal(fused_f.Download(), seq_f.Download())
+            assert len(ing) == len(scan)
+            holes = ing.Download()
+            kept = holes[np.isfinite(holes[:, :3]).all(axis=1)]
+            assert np.array_equal(kept, seq.Download()) and np.array_equal(ing.RemoveNaN().Download(), seq.Download())
+            assert fused_launches <= 10, fused_launches   # the whole ingest + filter: bbox/ingest, keys, <= 4 passes, runs, 2 centroid kernels
+    # NaN removal only
+    src = DeviceCloud(scan)
+    a = vf.FilterCloud(src.RemoveNaN()).Download()
+    b, _ = vf.IngestFilterCloud(src)
+    assert np.array_equal(b.Download(), a)
