@@ -85,6 +85,8 @@ typedef struct {
     uint32_t n_leaves;         /* occupied voxels */
     uint32_t n_tree;           /* voxels with >= min_pts points (searchable) */
     float   inv_leaf;
+    uint32_t updates_incremental;  /* b2ndt_update_target calls since the last SetInputTarget that took the incremental path */
+    uint32_t updates_rebuilt;      /* ... that had to rebuild (new points outside the grid's index box) */
 } b2ndt_target_info;
 
 void b2ndt_params_default(b2ndt_params *p);
@@ -100,6 +102,18 @@ int  b2ndt_set_cluster(b2ndt *h, int single_match_ctas, int batch_ctas);
 
 int  b2ndt_set_target(b2ndt *h, const void *pts, size_t n, size_t stride, size_t ioff);
 int  b2ndt_set_target_device(b2ndt *h, const void *d_pts_f4, size_t n);
+/* Incremental target update: NormalDistributionsTransform::updateVoxelGrid(new_cloud) of the reference's in-tree NDT
+ * (ndt_registration_manual/NormalDistributionsTransform.cpp:968-972 -> VoxelGrid::update, VoxelGrid.cpp:545-584,
+ * updateVoxelContent :736-809): add the points of a new cloud to the target.  The new points are sorted by voxel under
+ * the existing layout, every touched voxel continues its stored sums (or a new leaf is opened), only the touched
+ * leaves are finished again, and the neighbour lists are laid out again.  The result equals
+ * b2ndt_set_target(old points ++ new points) BIT FOR BIT (every per-voxel sum continues in the order the full build
+ * would use); when a new point falls outside the grid's index box (PCL's layout of the united cloud differs) the
+ * target is rebuilt from all points instead.  The points handed to the last SetInputTarget must still be alive and
+ * unchanged at the FIRST update (PCL retains its target pointer the same way); from then on the handle owns a copy.
+ * The first b2ndt_fitness* call after an update re-sorts the point buckets (one full build). */
+int  b2ndt_update_target(b2ndt *h, const void *pts, size_t n, size_t stride, size_t ioff);
+int  b2ndt_update_target_device(b2ndt *h, const void *d_pts_f4, size_t n);
 int  b2ndt_target_info_get(b2ndt *h, b2ndt_target_info *info);
 /* copy the leaf table to host (ascending voxel index; arrays sized n_leaves, any may be NULL):
  * idx, n_raw, centroid (4 floats), mean (3 doubles), icov (9 doubles, row-major; zeros when n<min_pts) */
@@ -196,6 +210,7 @@ int  b2vf_ingest_filter_cloud(b2vf *h, b2cloud *src, float scan_period, const do
                               const double angular_velocity[3], b2cloud *filtered, b2cloud *ingested);
 /* SetInputTarget / ScanMatch on device clouds; result_cloud may be NULL */
 int  b2ndt_set_target_cloud(b2ndt *h, b2cloud *target);
+int  b2ndt_update_target_cloud(b2ndt *h, b2cloud *add);     /* see b2ndt_update_target */
 int  b2ndt_align_cloud(b2ndt *h, b2cloud *src, const float guess[16], float pose_out[16], b2ndt_result *res,
                        b2cloud *result_cloud);
 

@@ -39,6 +39,11 @@ class NDTRegistration : public RegistrationInterface {
     // Extension: clouds that already live in HBM (b2cloud, include/b2ndt.h): the front end's local map assembled on the
     // device, the matching node's cropped map, a frame filtered on the device -- no host copies.  result_cloud may be null.
     bool SetInputTargetDevice(b2cloud* input_target);
+    // Extension: the in-tree NDT's NormalDistributionsTransform::updateVoxelGrid(new_cloud)
+    // (ndt_registration_manual/NormalDistributionsTransform.cpp:968-972): add a cloud to the current target without a
+    // full rebuild; same target as SetInputTarget(old + new), bit for bit (include/b2ndt.h: b2ndt_update_target).
+    bool UpdateInputTarget(const CloudData::CLOUD_PTR& new_cloud);
+    bool UpdateInputTargetDevice(b2cloud* new_cloud);
     bool ScanMatchDevice(b2cloud* input_source, const Eigen::Matrix4f& predict_pose, b2cloud* result_cloud,
                          Eigen::Matrix4f& result_pose);
     // details of the last ScanMatch (iterations, converged, score ...)

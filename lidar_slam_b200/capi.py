@@ -19,6 +19,7 @@ EXPORTS = [
     "b2_last_error", "b2_kernel_launch_count", "b2_device_count",
     "b2ndt_params_default", "b2ndt_create", "b2ndt_destroy", "b2ndt_set_stream", "b2ndt_synchronize",
     "b2ndt_set_cluster", "b2ndt_set_target", "b2ndt_set_target_device", "b2ndt_target_info_get",
+    "b2ndt_update_target", "b2ndt_update_target_device", "b2ndt_update_target_cloud",
     "b2ndt_target_leaves", "b2ndt_align", "b2ndt_align_batch", "b2ndt_align_batch_device",
     "b2ndt_derivatives", "b2ndt_fitness", "b2ndt_fitness_ex",
     "b2vf_create", "b2vf_destroy", "b2vf_set_stream", "b2vf_filter", "b2vf_filter_batch_device", "b2vf_filter_batch_append_device",
@@ -55,7 +56,8 @@ RESULT_DTYPE = np.dtype([("iterations", "<i4"), ("converged", "<i4"), ("score", 
 
 class TargetInfo(C.Structure):
     _fields_ = [("ok", C.c_int32), ("min_b", C.c_int32 * 3), ("div_b", C.c_int32 * 3), ("n_points", C.c_uint32),
-                ("n_leaves", C.c_uint32), ("n_tree", C.c_uint32), ("inv_leaf", C.c_float)]
+                ("n_leaves", C.c_uint32), ("n_tree", C.c_uint32), ("inv_leaf", C.c_float),
+                ("updates_incremental", C.c_uint32), ("updates_rebuilt", C.c_uint32)]
 
 
 def lib_path():
@@ -87,6 +89,9 @@ def lib():
     L.b2ndt_set_cluster.argtypes = [vp, C.c_int, C.c_int]
     L.b2ndt_set_target.argtypes = [vp, vp, sz, sz, sz]
     L.b2ndt_set_target_device.argtypes = [vp, vp, sz]
+    L.b2ndt_update_target.argtypes = [vp, vp, sz, sz, sz]
+    L.b2ndt_update_target_device.argtypes = [vp, vp, sz]
+    L.b2ndt_update_target_cloud.argtypes = [vp, vp]
     L.b2ndt_target_info_get.argtypes = [vp, C.POINTER(TargetInfo)]
     L.b2ndt_target_leaves.argtypes = [vp, i32p, i32p, fp, dp, dp]
     L.b2ndt_align.argtypes = [vp, vp, sz, sz, sz, fp, fp, C.POINTER(Result)]

@@ -45,6 +45,16 @@ struct TargetDev {
     DevBuf leaf_idx, leaf_n, leaf_start, centroid4, gauss, sums, icov9, cells, counters;
     DevBuf nbr_head, nbr_list, nbr_tiles;
     bool valid = false;
+    // incremental updates (b2ndt_update_target): the float centroid SUMS per leaf, the run -> leaf table of the last
+    // update, and the points in the order they were handed over (retained pointer until the first update, like PCL's
+    // target_ pointer; an owned copy from then on)
+    DevBuf csum4, touched, pts_all;
+    const float4 *src = nullptr;
+    size_t n_all = 0;
+    bool owns_all = false;
+    bool stale_buckets = false;   // pts_sorted / leaf_start no longer cover every point (fitness rebuilds first)
+    bool unsorted = false;        // leaves appended by updates: the table is no longer in ascending voxel order
+    uint32_t upd_incremental = 0, upd_rebuilt = 0;
 };
 
 // ------------------------------------------------------------------ target build kernels -----
@@ -63,6 +73,17 @@ struct LeafOut {
     uint32_t *leaf_start;
     float4 *centroid4;
     double *sums;
+    float4 *csum4;       // float sums of x, y, z, intensity (an update continues them)
+};
+
+// Incremental update (VoxelGrid::update, reference VoxelGrid.cpp:545-584,736-809): a run of the NEW cloud continues the
+// sums of the leaf that already owns its cell, or opens a new leaf behind the existing ones.
+struct LeafUpd {
+    const float4 *cells;     // dense grid record: .w = +-(leaf + 1), 0 = empty
+    const int32_t *leaf_n;   // current point counts
+    uint32_t V_old;
+    uint32_t *new_ctr;       // leaves opened by this update
+    uint32_t *touched;       // run -> leaf
 };
 
 __device__ __forceinline__ void leaf_emit(const LeafOut &O, uint32_t j, uint32_t s, uint32_t n, uint32_t key, float cx, float cy,
@@ -73,8 +94,19 @@ __device__ __forceinline__ void leaf_emit(const LeafOut &O, uint32_t j, uint32_t
     O.leaf_n[j] = (int32_t)n;
     O.leaf_start[j] = s;
     O.centroid4[j] = make_float4(__fdiv_rn(cx, fn), __fdiv_rn(cy, fn), __fdiv_rn(cz, fn), __fdiv_rn(ci, fn));
+    O.csum4[j] = make_float4(cx, cy, cz, ci);
     double *o = O.sums + (size_t)j * 9;
     o[0] = sx; o[1] = sy; o[2] = sz; o[3] = cxx; o[4] = cxy; o[5] = cxz; o[6] = cyy; o[7] = cyz; o[8] = czz;
+}
+
+// update mode: the leaf a run of new points belongs to (lane-uniform callers pass the run's key); n0 = its points so far
+__device__ __forceinline__ uint32_t upd_find_leaf(const LeafUpd &U, uint32_t key, uint32_t run, uint32_t &n0) {
+    const int code = __float_as_int(__ldg(&U.cells[key]).w);
+    uint32_t j;
+    if (code != 0) { j = (uint32_t)((code > 0 ? code : -code) - 1); n0 = (uint32_t)U.leaf_n[j]; }
+    else { j = U.V_old + atomicAdd(U.new_ctr, 1u); n0 = 0u; }
+    U.touched[run] = j;
+    return j;
 }
 
 #define B2_LEAF_ACC(x, y, z, w)                                                                        \
@@ -87,9 +119,11 @@ __device__ __forceinline__ void leaf_emit(const LeafOut &O, uint32_t j, uint32_t
         cyz = __dadd_rn(cyz, __dmul_rn(dy, dz)); czz = __dadd_rn(czz, __dmul_rn(dz, dz));              \
     } while (0)
 
+template <bool UPD>
 __global__ void __launch_bounds__(256) leaf_stats_kernel(const float4 *__restrict__ pts, SortView sv,
                                                          const uint32_t *__restrict__ run_start, uint32_t V, uint32_t n_finite,
-                                                         LeafOut O, uint32_t *__restrict__ crowded, uint32_t *__restrict__ n_crowded) {
+                                                         LeafOut O, uint32_t *__restrict__ crowded, uint32_t *__restrict__ n_crowded,
+                                                         LeafUpd U) {
     const uint32_t *__restrict__ keys = sv.keys();
     const uint32_t *__restrict__ vals = sv.vals();
     const int l = threadIdx.x & 31;
@@ -113,11 +147,21 @@ __global__ void __launch_bounds__(256) leaf_stats_kernel(const float4 *__restric
         if (valid && !is_crowded) {
             float cx = 0.f, cy = 0.f, cz = 0.f, ci = 0.f;
             double sx = 0, sy = 0, sz = 0, cxx = 1, cxy = 0, cxz = 0, cyy = 1, cyz = 0, czz = 1;
+            uint32_t jo = j, n0 = 0;
+            if (UPD) {
+                jo = upd_find_leaf(U, keys[s], j, n0);
+                if (n0) {       // continue the leaf's sums where the earlier clouds left them
+                    const float4 c = O.csum4[jo];
+                    const double *o = O.sums + (size_t)jo * 9;
+                    cx = c.x; cy = c.y; cz = c.z; ci = c.w;
+                    sx = o[0]; sy = o[1]; sz = o[2]; cxx = o[3]; cxy = o[4]; cxz = o[5]; cyy = o[6]; cyz = o[7]; czz = o[8];
+                }
+            }
             uint32_t k = s;
             for (; k + 4 <= e; k += 4) {
                 const uint32_t v0 = vals[k], v1 = vals[k + 1], v2 = vals[k + 2], v3 = vals[k + 3];
                 const float4 p0 = __ldg(&pts[v0]), p1 = __ldg(&pts[v1]), p2 = __ldg(&pts[v2]), p3 = __ldg(&pts[v3]);
-                O.pts_sorted[k] = p0; O.pts_sorted[k + 1] = p1; O.pts_sorted[k + 2] = p2; O.pts_sorted[k + 3] = p3;
+                if (!UPD) { O.pts_sorted[k] = p0; O.pts_sorted[k + 1] = p1; O.pts_sorted[k + 2] = p2; O.pts_sorted[k + 3] = p3; }
                 B2_LEAF_ACC(p0.x, p0.y, p0.z, p0.w);
                 B2_LEAF_ACC(p1.x, p1.y, p1.z, p1.w);
                 B2_LEAF_ACC(p2.x, p2.y, p2.z, p2.w);
@@ -125,10 +169,10 @@ __global__ void __launch_bounds__(256) leaf_stats_kernel(const float4 *__restric
             }
             for (; k < e; ++k) {
                 const float4 p = __ldg(&pts[vals[k]]);
-                O.pts_sorted[k] = p;
+                if (!UPD) O.pts_sorted[k] = p;
                 B2_LEAF_ACC(p.x, p.y, p.z, p.w);
             }
-            leaf_emit(O, j, s, len, keys[s], cx, cy, cz, ci, sx, sy, sz, cxx, cxy, cxz, cyy, cyz, czz);
+            leaf_emit(O, jo, s, n0 + len, keys[s], cx, cy, cz, ci, sx, sy, sz, cxx, cxy, cxz, cyy, cyz, czz);
         }
     }
 }
@@ -136,11 +180,12 @@ __global__ void __launch_bounds__(256) leaf_stats_kernel(const float4 *__restric
 constexpr int LCROWD_THREADS = 128;    // 4 warps, each with a ring of LCROWD_RING staging groups of LCROWD_GROUP points
 constexpr int LCROWD_GROUP = 128;
 constexpr int LCROWD_RING = 4;
+template <bool UPD>
 __global__ void __launch_bounds__(LCROWD_THREADS) leaf_crowded_kernel(const float4 *__restrict__ pts, SortView sv,
                                                                       const uint32_t *__restrict__ run_start, uint32_t V,
                                                                       uint32_t n_finite, LeafOut O,
                                                                       const uint32_t *__restrict__ crowded,
-                                                                      const uint32_t *__restrict__ n_crowded) {
+                                                                      const uint32_t *__restrict__ n_crowded, LeafUpd U) {
     const uint32_t n = *n_crowded;
     const uint32_t *__restrict__ keys = sv.keys();
     const uint32_t *__restrict__ vals = sv.vals();
@@ -176,12 +221,23 @@ __global__ void __launch_bounds__(LCROWD_THREADS) leaf_crowded_kernel(const floa
         };
         double dacc = (a == 3 || a == 6 || a == 8) ? 1.0 : 0.0;       // cov_ starts from Identity
         float facc = 0.f;
+        uint32_t jo = j, n0 = 0;
+        if (UPD) {
+            if (l == 0) jo = upd_find_leaf(U, keys[s], j, n0);
+            jo = __shfl_sync(0xffffffffu, jo, 0); n0 = __shfl_sync(0xffffffffu, n0, 0);
+            if (n0) {
+                if (l < 9) dacc = O.sums[(size_t)jo * 9 + l];
+                else if (l < 13) facc = reinterpret_cast<const float *>(&O.csum4[jo])[l - 9];
+            }
+        }
         auto fold = [&](int buf, uint32_t c) {
             const int m = (e - c < (uint32_t)LCROWD_GROUP) ? (int)(e - c) : LCROWD_GROUP;
             // the target keeps its points in voxel order (fitness buckets): this group's slice, coalesced
+            if (!UPD) {
 #pragma unroll
-            for (int d = 0; d < 4; ++d)
-                if (d * 32 + l < m) O.pts_sorted[c + d * 32 + l] = stage[w][buf][d * 32 + l];
+                for (int d = 0; d < 4; ++d)
+                    if (d * 32 + l < m) O.pts_sorted[c + d * 32 + l] = stage[w][buf][d * 32 + l];
+            }
             const float *qu = reinterpret_cast<const float *>(stage[w][buf]) + iu;
             const float *qv = (iv >= 0) ? reinterpret_cast<const float *>(stage[w][buf]) + iv : &s_one;
             const int v_stride = (iv >= 0) ? 4 : 0;
@@ -211,7 +267,7 @@ __global__ void __launch_bounds__(LCROWD_THREADS) leaf_crowded_kernel(const floa
         for (int k = 0; k < 9; ++k) d9[k] = __shfl_sync(0xffffffffu, dacc, k);
         const float cx = __shfl_sync(0xffffffffu, facc, 9), cy = __shfl_sync(0xffffffffu, facc, 10);
         const float cz = __shfl_sync(0xffffffffu, facc, 11), ci = __shfl_sync(0xffffffffu, facc, 12);
-        if (l == 0) leaf_emit(O, j, s, e - s, keys[s], cx, cy, cz, ci, d9[0], d9[1], d9[2], d9[3], d9[4], d9[5], d9[6], d9[7], d9[8]);
+        if (l == 0) leaf_emit(O, jo, s, n0 + (e - s), keys[s], cx, cy, cz, ci, d9[0], d9[1], d9[2], d9[3], d9[4], d9[5], d9[6], d9[7], d9[8]);
     }
 }
 
@@ -239,14 +295,23 @@ __device__ __forceinline__ bool nbr_keep(float cx, float cy, float cz, int kx, i
     return d2 < lim * lim;
 }
 
+__device__ __forceinline__ void leaf_nbr_account(uint32_t j, const LayoutArg &LA, const int32_t *__restrict__ leaf_idx,
+                                                 const float4 *__restrict__ centroid4, uint2 *__restrict__ nbr_head,
+                                                 uint32_t *__restrict__ counters);
+
 __global__ void __launch_bounds__(128) leaf_finish_kernel(uint32_t V, int min_pts, double eig_mult, LayoutArg LA,
                                                           const int32_t *__restrict__ leaf_idx, const int32_t *__restrict__ leaf_n,
                                                           const float4 *__restrict__ centroid4,
                                                           const double *__restrict__ sums, double *__restrict__ gauss,
                                                           double *__restrict__ icov9, float4 *__restrict__ cells,
-                                                          uint2 *__restrict__ nbr_head, uint32_t *__restrict__ counters) {
+                                                          uint2 *__restrict__ nbr_head, uint32_t *__restrict__ counters,
+                                                          const uint32_t *__restrict__ list) {
+    // list != NULL (incremental update): V entries of `list` name the leaves to finish, and the neighbour-list
+    // accounting is left to nbr_count_kernel (it has to be redone over ALL leaves)
     uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= V) return;
+    const bool account = (list == nullptr);
+    if (list) j = list[j];
     const double *s = sums + (size_t)j * 9;
     double sum[3] = {s[0], s[1], s[2]};
     double acc[9] = {s[3], s[4], s[5], s[4], s[6], s[7], s[5], s[7], s[8]};
@@ -267,7 +332,15 @@ __global__ void __launch_bounds__(128) leaf_finish_kernel(uint32_t V, int min_pt
         const float4 c = centroid4[j];
         cells[leaf_idx[j]] = make_float4(c.x, c.y, c.z, __int_as_float(tree ? (int32_t)(j + 1) : -(int32_t)(j + 1)));
     }
-    if (tree) {
+    if (tree && account) leaf_nbr_account(j, LA, leaf_idx, centroid4, nbr_head, counters);
+}
+
+// searchable leaf j: count it, add it to the list length of every cell it can be reached from, and fold how far its
+// float centroid lies outside its own cell into the maximum
+__device__ __forceinline__ void leaf_nbr_account(uint32_t j, const LayoutArg &LA, const int32_t *__restrict__ leaf_idx,
+                                                 const float4 *__restrict__ centroid4, uint2 *__restrict__ nbr_head,
+                                                 uint32_t *__restrict__ counters) {
+    {
         atomicAdd(&counters[0], 1u);
         // how far the float centroid (PCL's kd-tree point) lies outside its own cell: bounds the search
         // window margin of the match kernel.  Cell k of an axis spans [k/inv, (k+1)/inv).
@@ -295,6 +368,45 @@ __global__ void __launch_bounds__(128) leaf_finish_kernel(uint32_t V, int min_pt
             disp = fmax(disp, fmax(lo - cc[a], cc[a] - hi));
         }
         if (disp > 0.0) atomicMax(&counters[1], __float_as_uint(__double2float_ru(disp)));   // positive floats order as uints
+    }
+}
+
+// incremental update: the neighbour-list accounting of leaf_finish_kernel redone over every leaf (the list heads were
+// cleared: a leaf that became searchable, or whose centroid moved, changes the lists of up to 27 cells)
+__global__ void __launch_bounds__(128) nbr_count_kernel(uint32_t V, int min_pts, LayoutArg LA, const int32_t *__restrict__ leaf_idx,
+                                                        const int32_t *__restrict__ leaf_n, const float4 *__restrict__ centroid4,
+                                                        uint2 *__restrict__ nbr_head, uint32_t *__restrict__ counters) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= V) return;
+    if (leaf_n[j] >= min_pts) leaf_nbr_account(j, LA, leaf_idx, centroid4, nbr_head, counters);
+}
+
+// incremental update: voxel key of every new point under the EXISTING layout; a finite point outside the grid's index
+// box raises *oob (the layout of old + new points differs: the caller rebuilds); non-finite points get the invalid key
+__global__ void __launch_bounds__(256) upd_key_kernel(const float4 *__restrict__ pts, uint32_t n, VoxLayout L,
+                                                      uint32_t *__restrict__ keys, uint32_t *__restrict__ n_valid,
+                                                      uint32_t *__restrict__ oob) {
+    uint32_t cnt = 0, bad = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 p = __ldg(&pts[i]);
+        uint32_t key = L.ncells;
+        if (finite3(p.x, p.y, p.z)) {
+            const int i0 = (int)(floorf(__fmul_rn(p.x, L.inv[0])) - (float)L.min_b[0]);
+            const int i1 = (int)(floorf(__fmul_rn(p.y, L.inv[1])) - (float)L.min_b[1]);
+            const int i2 = (int)(floorf(__fmul_rn(p.z, L.inv[2])) - (float)L.min_b[2]);
+            if (i0 < 0 || i1 < 0 || i2 < 0 || i0 >= L.div_b[0] || i1 >= L.div_b[1] || i2 >= L.div_b[2]) bad = 1u;
+            else { key = (uint32_t)(i0 * L.mul[0] + i1 * L.mul[1] + i2 * L.mul[2]); ++cnt; }
+        }
+        keys[i] = key;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (cnt) atomicAdd(n_valid, cnt);
+        if (bad) atomicOr(oob, 1u);
     }
 }
 
@@ -1651,6 +1763,7 @@ extern "C" void b2ndt_destroy(b2ndt *h) {
     t.pts_in.release(); t.pts_sorted.release(); t.leaf_idx.release(); t.leaf_n.release(); t.leaf_start.release();
     t.centroid4.release(); t.gauss.release(); t.sums.release(); t.icov9.release(); t.cells.release(); t.counters.release();
     t.nbr_head.release(); t.nbr_list.release(); t.nbr_tiles.release();
+    t.csum4.release(); t.touched.release(); t.pts_all.release();
     h->d_src.release(); h->d_guess.release(); h->d_pose.release(); h->d_res.release(); h->d_off.release();
     h->d_work.release(); h->h_ready.release();
     if (h->copy_st) { cudaStreamSynchronize(h->copy_st); cudaStreamDestroy(h->copy_st); }
@@ -1686,6 +1799,8 @@ extern "C" int b2ndt_set_cluster(b2ndt *h, int single_match_ctas, int batch_ctas
 static int build_target(b2ndt *h, const float4 *d_pts, size_t n, int nbits_hint) {
     TargetDev &t = h->tgt;
     t.valid = false; t.N = (uint32_t)n; t.V = 0; t.n_tree = 0; t.max_disp = 0.f;
+    t.stale_buckets = false; t.unsorted = false;
+    if (d_pts != t.pts_all.as<float4>()) { t.src = d_pts; t.n_all = n; t.owns_all = false; t.upd_incremental = t.upd_rebuilt = 0; }   // else: a rebuild out of the update path
     h->have_last = false;
     memset(&t.L, 0, sizeof(t.L));
     int rc;
@@ -1711,6 +1826,7 @@ static int build_target(b2ndt *h, const float4 *d_pts, size_t n, int nbits_hint)
     if ((rc = t.centroid4.reserve((V + 1) * sizeof(float4)))) return rc;
     if ((rc = t.gauss.reserve((size_t)(V + 1) * GAUSS_STRIDE * 8))) return rc;
     if ((rc = t.sums.reserve((size_t)(V + 1) * 72))) return rc;
+    if ((rc = t.csum4.reserve((V + 1) * sizeof(float4)))) return rc;
     if ((rc = t.icov9.reserve((size_t)(V + 1) * 72))) return rc;
     if ((rc = t.cells.reserve((size_t)t.L.ncells * 16 + 16))) return rc;
     if ((rc = t.counters.reserve(((size_t)ntiles + 16) * 4))) return rc;               // counters[16] + one look-back word per tile
@@ -1731,17 +1847,20 @@ static int build_target(b2ndt *h, const float4 *d_pts, size_t n, int nbits_hint)
         LeafOut O;
         O.pts_sorted = t.pts_sorted.as<float4>(); O.leaf_idx = t.leaf_idx.as<int32_t>(); O.leaf_n = t.leaf_n.as<int32_t>();
         O.leaf_start = t.leaf_start.as<uint32_t>(); O.centroid4 = t.centroid4.as<float4>(); O.sums = t.sums.as<double>();
+        O.csum4 = t.csum4.as<float4>();
+        LeafUpd U;
+        memset(&U, 0, sizeof(U));
         unsigned blocks = ((V / 256 + 147) / 148) * 148u;
         if (blocks < 148) blocks = 148;
         if (blocks > 148 * 16) blocks = 148 * 16;
-        leaf_stats_kernel<<<blocks, 256, 0, h->st>>>(d_pts, h->pipe.view(), h->pipe.run_start(), V, t.L.n_finite, O, crowded, cnt + 5);
+        leaf_stats_kernel<false><<<blocks, 256, 0, h->st>>>(d_pts, h->pipe.view(), h->pipe.run_start(), V, t.L.n_finite, O, crowded, cnt + 5, U);
         B2_LAUNCH_CHECK();
-        leaf_crowded_kernel<<<148 * 8, LCROWD_THREADS, 0, h->st>>>(d_pts, h->pipe.view(), h->pipe.run_start(), V, t.L.n_finite, O, crowded, cnt + 5);
+        leaf_crowded_kernel<false><<<148 * 8, LCROWD_THREADS, 0, h->st>>>(d_pts, h->pipe.view(), h->pipe.run_start(), V, t.L.n_finite, O, crowded, cnt + 5, U);
         B2_LAUNCH_CHECK();
         leaf_finish_kernel<<<(V + 127) / 128, 128, 0, h->st>>>(V, h->prm.min_pts, h->prm.eig_mult, LA, t.leaf_idx.as<int32_t>(),
                                                               t.leaf_n.as<int32_t>(), t.centroid4.as<float4>(), t.sums.as<double>(),
                                                               t.gauss.as<double>(), t.icov9.as<double>(), t.cells.as<float4>(),
-                                                              t.nbr_head.as<uint2>(), cnt);
+                                                              t.nbr_head.as<uint2>(), cnt, nullptr);
         B2_LAUNCH_CHECK();
         // neighbour lists, laid out in cell order
         nbr_scan_kernel<<<ntiles, NBR_TPB, 0, h->st>>>(t.nbr_head.as<uint2>(), t.L.ncells, ntiles, cnt, cnt + 16, active);
@@ -1755,6 +1874,138 @@ static int build_target(b2ndt *h, const float4 *d_pts, size_t n, int nbits_hint)
     memcpy(&t.max_disp, &misc[1], 4);
     if (misc[4] >= NB_MASK) { set_error("SetInputTarget: %u neighbour-list entries exceed the 2^30 limit", misc[4]); return B2_ERR_INVALID; }
     t.valid = true;     // only a completely built target is usable: a failed allocation above leaves "no target set"
+    return 0;
+}
+
+// grow a device buffer keeping its first `keep` bytes
+static int grow_keep(DevBuf &b, size_t bytes, size_t keep, cudaStream_t st) {
+    if (bytes <= b.cap) return 0;
+    DevBuf nb;
+    int rc = nb.reserve(bytes);
+    if (rc) return rc;
+    if (keep && b.p) B2_CUDA(cudaMemcpyAsync(nb.p, b.p, keep, cudaMemcpyDeviceToDevice, st));
+    B2_CUDA(cudaStreamSynchronize(st));
+    b.release();
+    b = nb;
+    return 0;
+}
+
+// Incremental target update = NormalDistributionsTransform::updateVoxelGrid -> VoxelGrid::update of the reference's
+// in-tree NDT (NormalDistributionsTransform.cpp:968-972, VoxelGrid.cpp:545-584: bounds, :736-809 updateVoxelContent: per
+// new point  tmp_centroid += p, tmp_cov += p p^T, then mean / covariance / inverse of the touched voxel again).
+// Here: the new points are keyed under the EXISTING layout and sorted by voxel; each run continues the stored sums of
+// its leaf (or opens a leaf) in input order, only the touched leaves are finished again, and the neighbour lists are
+// laid out again.  Because every sum continues in the order a full build over (old points ++ new points) would use,
+// the updated target is that full build BIT FOR BIT (leaf numbering aside).  A new point outside the grid's index box
+// changes PCL's layout for the united cloud: the target is then rebuilt from all points (same result by definition).
+static int update_target(b2ndt *h, const float4 *d_new, size_t n) {
+    TargetDev &t = h->tgt;
+    if (!t.valid) { set_error("b2ndt_update_target: no target set"); return B2_ERR_STATE; }
+    if (n == 0) return 0;
+    if (t.n_all + n >= B2_MAX_POINTS) { set_error("b2ndt_update_target: target too large"); return B2_ERR_INVALID; }
+    int rc;
+    // the points in hand-over order: an owned copy from the first update on
+    if (!t.owns_all) {
+        if (t.n_all && !t.src) { set_error("b2ndt_update_target: the target's points are not available"); return B2_ERR_STATE; }
+        DevBuf nb;
+        if ((rc = nb.reserve((t.n_all + n + 1) * sizeof(float4)))) return rc;
+        if (t.n_all) B2_CUDA(cudaMemcpyAsync(nb.p, t.src, t.n_all * sizeof(float4), cudaMemcpyDeviceToDevice, h->st));
+        B2_CUDA(cudaStreamSynchronize(h->st));
+        t.pts_all.release();
+        t.pts_all = nb;
+        t.owns_all = true;
+        t.src = t.pts_all.as<float4>();
+    } else {
+        if ((rc = grow_keep(t.pts_all, (t.n_all + n + 1) * sizeof(float4), t.n_all * sizeof(float4), h->st))) return rc;
+        t.src = t.pts_all.as<float4>();
+    }
+    float4 *d_add = t.pts_all.as<float4>() + t.n_all;
+    B2_CUDA(cudaMemcpyAsync(d_add, d_new, n * sizeof(float4), cudaMemcpyDeviceToDevice, h->st));
+    t.n_all += n;
+    h->have_last = false;
+    auto rebuild = [&]() { ++t.upd_rebuilt; return build_target(h, t.pts_all.as<float4>(), t.n_all, 0); };
+    if (!t.L.ok || t.V == 0 || t.L.ncells > (1u << 30)) return rebuild();
+    // keys of the new points under the existing layout, sorted by voxel, runs = touched voxels
+    const uint32_t ntiles = (uint32_t)(((size_t)t.L.ncells + NBR_TILE - 1) / NBR_TILE);
+    uint32_t *cnt = t.counters.as<uint32_t>();
+    B2_CUDA(cudaMemsetAsync(t.counters.p, 0, ((size_t)ntiles + 16) * 4, h->st));
+    uint32_t off[2] = {0u, (uint32_t)n};
+    if ((rc = h->pipe.plan(off, 1, h->st))) return rc;
+    {
+        unsigned blocks = (unsigned)((n + 255) / 256);
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        upd_key_kernel<<<blocks, 256, 0, h->st>>>(d_add, (uint32_t)n, t.L, h->pipe.keys0(), cnt + 7, cnt + 8);
+        B2_LAUNCH_CHECK();
+    }
+    if ((rc = h->pipe.run_prepared(t.L.ncells, t.L.nbits, h->st))) return rc;
+    if ((rc = h->h_small.reserve(4096))) return rc;
+    uint32_t *misc = h->h_small.as<uint32_t>();
+    B2_CUDA(cudaMemcpyAsync(misc, h->pipe.scalars(), 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->st));
+    B2_CUDA(cudaMemcpyAsync(misc + 8, cnt, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->st));
+    B2_CUDA(cudaStreamSynchronize(h->st));
+    const uint32_t R = misc[1], n_valid = misc[8 + 7], oob = misc[8 + 8];
+    if (oob) return rebuild();
+    ++t.upd_incremental;
+    if (R == 0) { t.N = (uint32_t)t.n_all; return 0; }            // only non-finite points
+    const uint32_t V0 = t.V;
+    const size_t Vcap = (size_t)V0 + R + 1;
+    if ((rc = grow_keep(t.leaf_idx, Vcap * 4, (size_t)V0 * 4, h->st))) return rc;
+    if ((rc = grow_keep(t.leaf_n, Vcap * 4, (size_t)V0 * 4, h->st))) return rc;
+    if ((rc = grow_keep(t.leaf_start, Vcap * 4, (size_t)V0 * 4, h->st))) return rc;
+    if ((rc = grow_keep(t.centroid4, Vcap * sizeof(float4), (size_t)V0 * sizeof(float4), h->st))) return rc;
+    if ((rc = grow_keep(t.csum4, Vcap * sizeof(float4), (size_t)V0 * sizeof(float4), h->st))) return rc;
+    if ((rc = grow_keep(t.gauss, Vcap * GAUSS_STRIDE * 8, (size_t)V0 * GAUSS_STRIDE * 8, h->st))) return rc;
+    if ((rc = grow_keep(t.sums, Vcap * 72, (size_t)V0 * 72, h->st))) return rc;
+    if ((rc = grow_keep(t.icov9, Vcap * 72, (size_t)V0 * 72, h->st))) return rc;
+    if ((rc = t.touched.reserve(((size_t)R + 1) * 4))) return rc;
+    // work lists (cells with a list | crowded runs) and the lists themselves are rebuilt: contents need not survive
+    if ((rc = t.nbr_tiles.reserve(((size_t)t.L.ncells + (size_t)n / LS_SEQ + 64) * 4))) return rc;
+    if ((rc = t.nbr_list.reserve(((size_t)(t.n_all / (size_t)(h->prm.min_pts > 0 ? h->prm.min_pts : 1) + 1) * 27 + 1) * sizeof(float4)))) return rc;
+    LayoutArg LA;
+    for (int a = 0; a < 3; ++a) { LA.min_b[a] = t.L.min_b[a]; LA.div_b[a] = t.L.div_b[a]; LA.inv[a] = t.L.inv[a]; }
+    LA.res = h->prm.res;
+    uint32_t *active = t.nbr_tiles.as<uint32_t>();
+    uint32_t *crowded = active + t.L.ncells;
+    LeafOut O;
+    O.pts_sorted = nullptr; O.leaf_idx = t.leaf_idx.as<int32_t>(); O.leaf_n = t.leaf_n.as<int32_t>();
+    O.leaf_start = t.leaf_start.as<uint32_t>(); O.centroid4 = t.centroid4.as<float4>(); O.sums = t.sums.as<double>();
+    O.csum4 = t.csum4.as<float4>();
+    LeafUpd U;
+    U.cells = t.cells.as<float4>(); U.leaf_n = t.leaf_n.as<int32_t>(); U.V_old = V0; U.new_ctr = cnt + 6; U.touched = t.touched.as<uint32_t>();
+    unsigned blocks = ((R / 256 + 147) / 148) * 148u;
+    if (blocks < 148) blocks = 148;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    leaf_stats_kernel<true><<<blocks, 256, 0, h->st>>>(d_add, h->pipe.view(), h->pipe.run_start(), R, n_valid, O, crowded, cnt + 5, U);
+    B2_LAUNCH_CHECK();
+    leaf_crowded_kernel<true><<<148 * 8, LCROWD_THREADS, 0, h->st>>>(d_add, h->pipe.view(), h->pipe.run_start(), R, n_valid, O, crowded, cnt + 5, U);
+    B2_LAUNCH_CHECK();
+    leaf_finish_kernel<<<(R + 127) / 128, 128, 0, h->st>>>(R, h->prm.min_pts, h->prm.eig_mult, LA, t.leaf_idx.as<int32_t>(),
+                                                          t.leaf_n.as<int32_t>(), t.centroid4.as<float4>(), t.sums.as<double>(),
+                                                          t.gauss.as<double>(), t.icov9.as<double>(), t.cells.as<float4>(),
+                                                          t.nbr_head.as<uint2>(), cnt, t.touched.as<uint32_t>());
+    B2_LAUNCH_CHECK();
+    // neighbour lists again, over every leaf (at most V0 + R of them: slots past the leaves opened hold n = 0)
+    B2_CUDA(cudaMemsetAsync(t.nbr_head.p, 0, (size_t)t.L.ncells * 8, h->st));
+    B2_CUDA(cudaMemcpyAsync(misc, cnt, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->st));
+    B2_CUDA(cudaStreamSynchronize(h->st));
+    const uint32_t V1 = V0 + misc[6];
+    nbr_count_kernel<<<(V1 + 127) / 128, 128, 0, h->st>>>(V1, h->prm.min_pts, LA, t.leaf_idx.as<int32_t>(), t.leaf_n.as<int32_t>(),
+                                                         t.centroid4.as<float4>(), t.nbr_head.as<uint2>(), cnt);
+    B2_LAUNCH_CHECK();
+    nbr_scan_kernel<<<ntiles, NBR_TPB, 0, h->st>>>(t.nbr_head.as<uint2>(), t.L.ncells, ntiles, cnt, cnt + 16, active);
+    B2_LAUNCH_CHECK();
+    nbr_fill_kernel<<<148 * 8, NBR_TPB, 0, h->st>>>(t.nbr_head.as<uint2>(), t.cells.as<float4>(), cnt, active, LA, t.nbr_list.as<float4>());
+    B2_LAUNCH_CHECK();
+    B2_CUDA(cudaMemcpyAsync(misc, cnt, 32, cudaMemcpyDeviceToHost, h->st));
+    B2_CUDA(cudaStreamSynchronize(h->st));
+    if (misc[4] >= NB_MASK) { t.valid = false; set_error("b2ndt_update_target: %u neighbour-list entries exceed the 2^30 limit", misc[4]); return B2_ERR_INVALID; }
+    t.n_tree = misc[0];
+    memcpy(&t.max_disp, &misc[1], 4);
+    if (V1 != V0) t.unsorted = true;
+    t.V = V1;
+    t.N = (uint32_t)t.n_all;
+    t.L.n_finite += n_valid;
+    t.stale_buckets = true;
     return 0;
 }
 
@@ -1799,6 +2050,26 @@ extern "C" int b2ndt_set_target_device(b2ndt *h, const void *d_pts_f4, size_t n)
     return build_target(h, (const float4 *)d_pts_f4, n, 0);
 }
 
+extern "C" int b2ndt_update_target(b2ndt *h, const void *pts, size_t n, size_t stride, size_t ioff) {
+    if (!h) { set_error("b2ndt_update_target: NULL handle"); return B2_ERR_INVALID; }
+    int rc = check_cloud_args("b2ndt_update_target", pts, n, stride, ioff);
+    if (rc) return rc;
+    if (n == 0) return h->tgt.valid ? 0 : (set_error("b2ndt_update_target: no target set"), B2_ERR_STATE);
+    B2_CUDA(cudaSetDevice(h->device));
+    if ((rc = h->h_stage.reserve(n * 16 + 16))) return rc;
+    if ((rc = h->d_src.reserve(n * 16 + 16))) return rc;
+    pack_cloud_f4(pts, n, stride, ioff, h->h_stage.as<float>());
+    B2_CUDA(cudaMemcpyAsync(h->d_src.p, h->h_stage.p, n * 16, cudaMemcpyHostToDevice, h->st));
+    return update_target(h, h->d_src.as<float4>(), n);
+}
+
+extern "C" int b2ndt_update_target_device(b2ndt *h, const void *d_pts_f4, size_t n) {
+    if (!h) { set_error("b2ndt_update_target_device: NULL handle"); return B2_ERR_INVALID; }
+    if (n && !d_pts_f4) { set_error("b2ndt_update_target_device: NULL cloud"); return B2_ERR_INVALID; }
+    B2_CUDA(cudaSetDevice(h->device));
+    return update_target(h, (const float4 *)d_pts_f4, n);
+}
+
 extern "C" int b2ndt_target_info_get(b2ndt *h, b2ndt_target_info *info) {
     if (!h || !info) { set_error("b2ndt_target_info_get: NULL argument"); return B2_ERR_INVALID; }
     if (!h->tgt.valid) { set_error("b2ndt_target_info_get: no target set"); return B2_ERR_STATE; }
@@ -1806,6 +2077,7 @@ extern "C" int b2ndt_target_info_get(b2ndt *h, b2ndt_target_info *info) {
     info->ok = t.L.ok;
     for (int a = 0; a < 3; ++a) { info->min_b[a] = t.L.min_b[a]; info->div_b[a] = t.L.div_b[a]; }
     info->n_points = t.L.n_finite; info->n_leaves = t.V; info->n_tree = t.n_tree; info->inv_leaf = t.L.inv[0];
+    info->updates_incremental = t.upd_incremental; info->updates_rebuilt = t.upd_rebuilt;
     return 0;
 }
 
@@ -1827,6 +2099,21 @@ extern "C" int b2ndt_target_leaves(b2ndt *h, int32_t *idx, int32_t *n_raw, float
         for (size_t j = 0; j < V; ++j) {
             mean3[3 * j] = g[GAUSS_STRIDE * j]; mean3[3 * j + 1] = g[GAUSS_STRIDE * j + 1]; mean3[3 * j + 2] = g[GAUSS_STRIDE * j + 2];
         }
+    }
+    if (t.unsorted) {
+        // leaves opened by incremental updates sit behind the original ones: report in ascending voxel order all the same
+        std::vector<int32_t> key(V);
+        B2_CUDA(cudaMemcpy(key.data(), t.leaf_idx.p, V * 4, cudaMemcpyDeviceToHost));
+        std::vector<uint32_t> perm(V);
+        for (size_t j = 0; j < V; ++j) perm[j] = (uint32_t)j;
+        std::sort(perm.begin(), perm.end(), [&](uint32_t a, uint32_t b) { return key[a] < key[b]; });
+        auto apply = [&](auto *arr, size_t width) {
+            if (!arr) return;
+            std::vector<typename std::remove_pointer<decltype(arr)>::type> tmp(arr, arr + V * width);
+            for (size_t j = 0; j < V; ++j)
+                for (size_t k = 0; k < width; ++k) arr[j * width + k] = tmp[(size_t)perm[j] * width + k];
+        };
+        apply(idx, 1); apply(n_raw, 1); apply(centroid4, 4); apply(mean3, 3); apply(icov9, 9);
     }
     return 0;
 }
@@ -2160,6 +2447,13 @@ extern "C" int b2ndt_derivatives(b2ndt *h, const void *src, size_t n, size_t str
 }
 
 static int fitness_device(b2ndt *h, const float4 *d_src, size_t n, const float pose[16], double max_range, double *out) {
+    if (h->tgt.stale_buckets) {
+        // incremental updates left the point buckets behind: rebuild from all points (the same target bit for bit)
+        const bool had_last = h->have_last;
+        int rc = build_target(h, h->tgt.pts_all.as<float4>(), h->tgt.n_all, 0);
+        if (rc) return rc;
+        h->have_last = had_last;
+    }
     const TargetDev &t = h->tgt;
     if (n == 0 || !t.L.ok || t.V == 0) { *out = DBL_MAX; return 0; }
     FitView F;
@@ -2224,6 +2518,13 @@ extern "C" int b2ndt_set_target_cloud(b2ndt *h, b2cloud *target) {
     if (target->device != h->device) { set_error("b2ndt_set_target_cloud: handle and cloud live on different devices"); return B2_ERR_INVALID; }
     B2_CUDA(cudaSetDevice(h->device));
     return build_target(h, target->d(), target->n, 0);
+}
+
+extern "C" int b2ndt_update_target_cloud(b2ndt *h, b2cloud *add) {
+    if (!h || !add) { set_error("b2ndt_update_target_cloud: NULL argument"); return B2_ERR_INVALID; }
+    if (add->device != h->device) { set_error("b2ndt_update_target_cloud: handle and cloud live on different devices"); return B2_ERR_INVALID; }
+    B2_CUDA(cudaSetDevice(h->device));
+    return update_target(h, add->d(), add->n);
 }
 
 // ScanMatch with a device-resident source; result_cloud (may be NULL) receives the source transformed by the

@@ -108,6 +108,22 @@ bool NDTRegistration::SetInputTargetDevice(b2cloud* input_target) {
     return true;
 }
 
+bool NDTRegistration::UpdateInputTarget(const CloudData::CLOUD_PTR& new_cloud) {
+    if (!ndt_ || b2ndt_update_target(ndt_, new_cloud->points.data(), new_cloud->points.size(), kStride, kIntensityOffset) != B2_OK) {
+        std::cerr << "[NDTRegistration::UpdateInputTarget] " << b2_last_error() << std::endl;
+        return false;
+    }
+    return true;
+}
+
+bool NDTRegistration::UpdateInputTargetDevice(b2cloud* new_cloud) {
+    if (!ndt_ || b2ndt_update_target_cloud(ndt_, new_cloud) != B2_OK) {
+        std::cerr << "[NDTRegistration::UpdateInputTargetDevice] " << b2_last_error() << std::endl;
+        return false;
+    }
+    return true;
+}
+
 bool NDTRegistration::ScanMatchDevice(b2cloud* input_source, const Eigen::Matrix4f& predict_pose, b2cloud* result_cloud,
                                       Eigen::Matrix4f& result_pose) {
     float pose[16];

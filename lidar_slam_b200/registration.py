@@ -235,11 +235,23 @@ class NDTRegistration(RegistrationInterface):
                                                 capi._dp(H), C.byref(pairs)))
         return score.value, g, H.reshape(6, 6, order="F").copy(), pairs.value
 
+    def UpdateInputTarget(self, new_cloud):
+        """NormalDistributionsTransform::updateVoxelGrid(new_cloud) of the reference's in-tree NDT
+        (ndt_registration_manual/NormalDistributionsTransform.cpp:968-972): add a cloud to the target without a full
+        rebuild.  Same target as SetInputTarget(old ++ new), bit for bit.  Accepts a host cloud or a DeviceCloud."""
+        if hasattr(new_cloud, "_h"):
+            capi.check(capi.lib().b2ndt_update_target_cloud(self._h, new_cloud._h))
+        else:
+            a, ptr, n, stride, ioff = capi.cloud_args(new_cloud)
+            capi.check(capi.lib().b2ndt_update_target(self._h, ptr, n, stride, ioff))
+        return True
+
     def TargetInfo(self):
         info = capi.TargetInfo()
         capi.check(capi.lib().b2ndt_target_info_get(self._h, C.byref(info)))
         return dict(ok=bool(info.ok), min_b=list(info.min_b), div_b=list(info.div_b), n_points=info.n_points,
-                    n_leaves=info.n_leaves, n_tree=info.n_tree)
+                    n_leaves=info.n_leaves, n_tree=info.n_tree, updates_incremental=info.updates_incremental,
+                    updates_rebuilt=info.updates_rebuilt)
 
     def TargetLeaves(self):
         V = self.TargetInfo()["n_leaves"]

@@ -147,6 +147,7 @@ def refndt_lib():
     R.refndt_new.restype = C.c_void_p
     R.refndt_free.argtypes = [C.c_void_p]
     R.refndt_set_target.argtypes = [C.c_void_p, fp, C.c_size_t]
+    R.refndt_update.argtypes = [C.c_void_p, fp, C.c_size_t]
     R.refndt_grid_info.argtypes = [C.c_void_p, ip]
     R.refndt_voxel.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, dp, dp, dp]
     R.refndt_voxel.restype = C.c_int

@@ -84,6 +84,12 @@ void refndt_set_target(void *h, const float *xyzi, size_t n) {
     r->target = make_cloud(xyzi, n);
     r->ndt.setInputTarget(r->target);
 }
+// NormalDistributionsTransform::updateVoxelGrid (NormalDistributionsTransform.cpp:968-972 -> VoxelGrid::update,
+// VoxelGrid.cpp:545-584, updateVoxelContent :736-809): add a cloud to the current target
+void refndt_update(void *h, const float *xyzi, size_t n) {
+    Ref *r = (Ref *)h;
+    r->ndt.updateVoxelGrid(make_cloud(xyzi, n));
+}
 // grid geometry: min_b (3), vgrid (3), real min (3), real max (3)
 void refndt_grid_info(void *h, int *out12) {
     auto &g = ((Ref *)h)->ndt.voxel_grid_;

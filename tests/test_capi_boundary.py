@@ -36,7 +36,7 @@ def test_library_is_sm100a_only():
 def test_python_structs_match_header_layout():
     assert C.sizeof(capi.Result) == capi.RESULT_DTYPE.itemsize == 88
     assert C.sizeof(capi.Params) == 56
-    assert C.sizeof(capi.TargetInfo) == 44
+    assert C.sizeof(capi.TargetInfo) == 52
 
 
 def test_no_cpu_fallback_without_gpu():

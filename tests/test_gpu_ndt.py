@@ -49,6 +49,86 @@ def test_target_grid_bit_exact(oracle, setup, small_map):
     assert np.mean(np.all(L["icov"][tree] == lv["icov"][tree], axis=1)) > 0.999
 
 
+def _leaves_equal(A, B):
+    return all(np.array_equal(A[k], B[k], equal_nan=True) for k in ("idx", "n", "centroid", "mean", "icov"))
+
+
+def test_incremental_update_equals_full_build(oracle, small_map, scans):
+    """b2ndt_update_target (the in-tree NDT's updateVoxelGrid, VoxelGrid.cpp:545-584,736-809): SetInputTarget(A) followed by
+    updates with B1, B2 gives the target SetInputTarget(A ++ B1 ++ B2) gives -- leaf table, matches and fitness bit for bit --
+    and that target is the oracle's.  Covers: runs that continue a leaf, runs that open a leaf, crowded runs, a leaf that
+    becomes searchable, non-finite points, a cloud outside the index box (rebuild path), host and device clouds."""
+    from lidar_slam_b200.registration import DeviceCloud
+    n = len(small_map)
+    a, b = int(0.6 * n), int(0.85 * n)
+    # the points that span the bounding box go first, so the first part already has the index box of the whole cloud
+    ext = np.unique(np.concatenate([np.argmin(small_map[:, :3], 0), np.argmax(small_map[:, :3], 0)]))
+    small_map = np.concatenate([small_map[ext], np.delete(small_map, ext, 0)])
+    A, B1, B2 = small_map[:a], small_map[a:b].copy(), small_map[b:]
+    B1[::97, 1] = np.nan                                        # non-finite points are carried along and ignored
+    # a dense blob inside one voxel of A's box: a crowded run (> 32 points) that continues / opens a leaf
+    rng = np.random.default_rng(5)
+    c = A[1000, :3]
+    blob = np.concatenate([np.floor(c)[None, :] + rng.uniform(0.05, 0.95, (700, 3)), rng.uniform(0, 1, (700, 1))], 1).astype(np.float32)
+    B1 = np.concatenate([B1, blob]).astype(np.float32)
+    full = np.concatenate([A, B1, B2]).astype(np.float32)
+    ref = NDTRegistration(1.0, 0.1, 0.01, 30)
+    ref.SetInputTarget(full)
+    want = ref.TargetLeaves()
+    lv = oracle.Grid(full, 1.0).leaves()
+    assert np.array_equal(want["idx"], lv["idx"]) and np.array_equal(want["n"], lv["n_raw"]) and np.array_equal(want["mean"], lv["mean"])
+
+    src = oracle.voxel_filter(scans[1][1], 1.3, 1.3, 1.3)[0]
+    guess = synth.pose6_to_matrix(scans[1][0] + np.array([0.2, -0.15, 0.05, 0.01, -0.005, 0.015])).astype(np.float32)
+    _, _, pose_ref = ref.ScanMatch(src, guess)
+    res_ref = dict(ref.last_result)
+    fit_ref = ref.GetFitnessScore()
+
+    def check(reg, tag):
+        info = reg.TargetInfo()
+        assert info["n_leaves"] == len(want["idx"]) and info["n_points"] == int(np.isfinite(full[:, :3]).all(1).sum()), tag
+        assert info["n_tree"] == ref.TargetInfo()["n_tree"], tag
+        assert _leaves_equal(reg.TargetLeaves(), want), tag
+        _, _, pose = reg.ScanMatch(src, guess)
+        assert np.array_equal(pose, pose_ref), tag
+        assert reg.last_result["score"] == res_ref["score"] and reg.last_result["iterations"] == res_ref["iterations"], tag
+        assert reg.last_result["pairs"] == res_ref["pairs"], tag
+        assert reg.GetFitnessScore() == fit_ref, tag
+
+    # host clouds; A's index box holds B1 and B2, so both updates take the incremental path
+    reg = NDTRegistration(1.0, 0.1, 0.01, 30)
+    reg.SetInputTarget(A)
+    n0 = reg.TargetInfo()["n_leaves"]
+    reg.UpdateInputTarget(B1)
+    reg.UpdateInputTarget(B2)
+    info = reg.TargetInfo()
+    assert info["n_leaves"] > n0 and info["updates_incremental"] == 2 and info["updates_rebuilt"] == 0
+    check(reg, "host")
+    # device clouds
+    regd = NDTRegistration(1.0, 0.1, 0.01, 30)
+    dA = DeviceCloud(A)
+    regd.SetInputTargetCloud(dA)
+    regd.UpdateInputTarget(DeviceCloud(B1))
+    regd.UpdateInputTarget(DeviceCloud(B2))
+    check(regd, "device")
+    # rebuild path: the first part lies in a corner of the map, the update reaches outside its index box
+    order = np.argsort(full[:, 0], kind="stable")
+    lo = np.sort(order[: n // 3]); hi = np.sort(order[n // 3:])
+    reg2 = NDTRegistration(1.0, 0.1, 0.01, 30)
+    reg2.SetInputTarget(full[lo])
+    reg2.UpdateInputTarget(full[hi])
+    ref2 = NDTRegistration(1.0, 0.1, 0.01, 30)
+    ref2.SetInputTarget(np.concatenate([full[lo], full[hi]]))
+    assert _leaves_equal(reg2.TargetLeaves(), ref2.TargetLeaves())
+    assert reg2.TargetInfo()["updates_rebuilt"] == 1
+    # an update without a target is an error; an empty update is a no-op
+    reg3 = NDTRegistration(1.0, 0.1, 0.01, 30)
+    with pytest.raises(Exception):
+        reg3.UpdateInputTarget(B2)
+    reg.UpdateInputTarget(np.zeros((0, 4), np.float32))
+    assert _leaves_equal(reg.TargetLeaves(), want)
+
+
 def test_golden_fixture(oracle):
     G = np.load(GOLD)
     reg = NDTRegistration(1.0, 0.1, 0.01, 30)

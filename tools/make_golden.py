@@ -182,6 +182,58 @@ def intree_ndt():
     print("intree_ndt.npz: voxels", len(ijk), "iterations", al_it)
 
 
+def _ref_voxels(R, h):
+    ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int))
+    info = np.zeros(12, np.int32); R.refndt_grid_info(h, ip(info))
+    ijk, cen, icov, npv = [], [], [], []
+    for ix in range(info[6], info[9] + 1):
+        for iy in range(info[7], info[10] + 1):
+            for iz in range(info[8], info[11] + 1):
+                c = np.zeros(3); ic = np.zeros(9); s = C.c_double()
+                n = R.refndt_voxel(h, ix, iy, iz, dp(c), dp(ic), C.byref(s))
+                if n >= 6:
+                    ijk.append((ix, iy, iz)); cen.append(c); icov.append(ic); npv.append(n)
+    return np.array(ijk, np.int32), np.array(cen), np.array(icov), np.array(npv, np.int32)
+
+
+def intree_update():
+    """Outputs of the reference's OWN incremental grid update (NormalDistributionsTransform::updateVoxelGrid ->
+    VoxelGrid::update / updateVoxelContent, VoxelGrid.cpp:545-584,736-809) on the ndt_small target split in three:
+    setInputTarget(first 60 %) then two updateVoxelGrid calls (next 25 %, last 15 % -- the last part reaches outside the
+    first grid, so the reference's updateBoundaries path runs too).  Stored: the searchable voxels after the updates,
+    and how far they are from the reference's own setInputTarget over the whole cloud."""
+    O.build(ref=True)
+    R = O.refndt_lib()
+    assert R is not None, "oracle/_ref/libndt_manual_ref.so missing (needs /root/reference)"
+    G = np.load(os.path.join(OUT, "ndt_small.npz"))
+    target = np.ascontiguousarray(G["target"])
+    # order the cloud so that the last part extends the bounding box (sorted by x within the last 15 %)
+    n = len(target)
+    a, b = int(0.6 * n), int(0.85 * n)
+    order = np.argsort(target[:, 0], kind="stable")
+    tail = order[-(n - b):]
+    rest = np.setdiff1d(np.arange(n), tail)           # ascending: input order kept
+    target = np.ascontiguousarray(np.concatenate([target[rest], target[tail]]))
+    f32 = lambda v: float(np.float32(v))
+    h = R.refndt_new(1.0, f32(0.1), f32(0.01), 30, 0.55)
+    R.refndt_set_target(h, fp(target[:a]), a)
+    R.refndt_update(h, fp(np.ascontiguousarray(target[a:b])), b - a)
+    R.refndt_update(h, fp(np.ascontiguousarray(target[b:])), n - b)
+    ijk, cen, icov, npv = _ref_voxels(R, h)
+    R.refndt_free(h)
+    h = R.refndt_new(1.0, f32(0.1), f32(0.01), 30, 0.55)
+    R.refndt_set_target(h, fp(target), n)
+    ijk2, cen2, icov2, npv2 = _ref_voxels(R, h)
+    R.refndt_free(h)
+    same = np.array_equal(ijk, ijk2) and np.array_equal(npv, npv2)
+    d_mean = float(np.max(np.abs(cen - cen2))) if same else np.inf
+    d_icov = float(np.max(np.abs(icov - icov2).max(1) / np.abs(icov2).max(1))) if same else np.inf
+    np.savez_compressed(os.path.join(OUT, "intree_update.npz"), target=target, split=np.array([a, b]), vox_ijk=ijk, vox_mean=cen,
+                        vox_icov=icov, vox_n=npv, full_build_same_voxels=np.array(same), full_build_max_dmean=np.array(d_mean),
+                        full_build_max_dicov_rel=np.array(d_icov))
+    print("intree_update.npz: voxels", len(ijk), "vs the reference's full build: same voxel set", same, "max |dmean|", d_mean, "max rel dicov", d_icov)
+
+
 def deskew():
     """Outputs of the reference's OWN DistortionAdjust (oracle/_ref/libdeskew_ref.so = distortion_adjust.cpp compiled
     where it lies against oracle/ref_stubs + the vendored Eigen) on a seeded synthetic sweep."""
@@ -205,4 +257,5 @@ if __name__ == "__main__":
     eigen_numerics()
     ndt_small()
     intree_ndt()
+    intree_update()
     deskew()
