@@ -601,6 +601,9 @@ constexpr int NDT_PPC = NDT_NSW / NDT_NCW;     // producers (search warps) per c
 #ifndef NDT_DRAIN_SLEEP
 #define NDT_DRAIN_SLEEP 32
 #endif
+#ifndef NDT_QUANTUM
+#define NDT_QUANTUM 32     // pairs a compute warp takes from a ring per turn: 32 (one per lane) or 64 (two per lane)
+#endif
 constexpr uint32_t RING = NDT_RING;            // ring entries per search warp (power of two, >= 128 + 32)
 static_assert(NDT_NCW % 4 == 0 && NDT_NSW % 4 == 0 && NDT_NSW % NDT_NCW == 0, "warp-group multiples");
 
@@ -713,28 +716,36 @@ __device__ __forceinline__ double dot2v(const double *h, double x, double y) { r
 //   [19..27] H01 = sum M C (3x3)  [28..33] H11c = sum C^T M C (33,34,35,44,45,55)  [34] pair count
 // (~150 FP64 operations per pair instead of ~250, and no angle-table reads for the second-derivative term);
 // acc_finish() contracts P with the tables once per pass and emits the ACC_N-vector the controller consumes.
-__device__ __forceinline__ void ndt_pair(const float px, const float py, const float pz, const float *__restrict__ T,
-                                         const AngTab &ang, const double *__restrict__ g, double d1, double d2, bool hess,
-                                         double *acc) {
+struct PairRec { double mx, my, mz, ixx, ixy, ixz, iyy, iyz, izz; };
+
+// 96-byte record: two 256-bit loads (LDG.E.256, sm_100) + one 64-bit load = 3 L1 requests instead of 5
+__device__ __forceinline__ void ndt_pair_load(const double *__restrict__ g, PairRec &r) {
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.mx), "=d"(r.my), "=d"(r.mz), "=d"(r.ixx) : "l"(g));
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.ixy), "=d"(r.ixz), "=d"(r.iyy), "=d"(r.iyz) : "l"(g + 4));
+    r.izz = __ldg(g + 8);
+}
+
+// `on` = this lane holds a pair.  A pair that fails the rejection test of NDTM:499-501 (or an idle lane) contributes
+// exact zeros instead of branching away, so two pairs per lane form two independent instruction streams.
+__device__ __forceinline__ void ndt_pair_math(const bool on, const float px, const float py, const float pz, const PairRec &r,
+                                              const float *__restrict__ T, const AngTab &ang, double d1, double d2, bool hess,
+                                              double *acc) {
     float tx, ty, tz;
     transform_f32(T, px, py, pz, tx, ty, tz);
-    // 96-byte record: two 256-bit loads (LDG.E.256, sm_100) + one 64-bit load = 3 L1 requests instead of 5
-    double mx, my, mz, ixx, ixy, ixz, iyy, iyz, izz;
-    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(mx), "=d"(my), "=d"(mz), "=d"(ixx) : "l"(g));
-    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(ixy), "=d"(ixz), "=d"(iyy), "=d"(iyz) : "l"(g + 4));
-    izz = __ldg(g + 8);
-    acc[34] += 1.0;
+    const double mx = r.mx, my = r.my, mz = r.mz, ixx = r.ixx, ixy = r.ixy, ixz = r.ixz, iyy = r.iyy, iyz = r.iyz, izz = r.izz;
+    acc[34] += on ? 1.0 : 0.0;
     const double xq = (double)tx - mx, yq = (double)ty - my, zq = (double)tz - mz;
-    const double q0 = ixx * xq + ixy * yq + ixz * zq;
-    const double q1 = ixy * xq + iyy * yq + iyz * zq;
-    const double q2 = ixz * xq + iyz * yq + izz * zq;
+    double q0 = ixx * xq + ixy * yq + ixz * zq;
+    double q1 = ixy * xq + iyy * yq + iyz * zq;
+    double q2 = ixz * xq + iyz * yq + izz * zq;
     const double m = xq * q0 + yq * q1 + zq * q2;
     double e = exp(-d2 * m / 2);
     const double sinc = -d1 * e;
     e = d2 * e;
-    if (e > 1 || e < 0 || e != e) return;      // NDTM:499-501
-    const double w = e * d1;
-    acc[0] += sinc;
+    const bool keep = on && !(e > 1 || e < 0 || e != e);      // NDTM:499-501
+    const double w = keep ? e * d1 : 0.0;
+    if (!keep) { q0 = 0.0; q1 = 0.0; q2 = 0.0; }              // 0 * inf / NaN must not reach the sums
+    acc[0] += keep ? sinc : 0.0;
     const double x = (double)px, y = (double)py, z = (double)pz;
     const double wq0 = w * q0, wq1 = w * q1, wq2 = w * q2;
     acc[1] += wq0; acc[2] += wq1; acc[3] += wq2;
@@ -1203,7 +1214,7 @@ __device__ __forceinline__ bool compute_drain(NdtSmem &S, const GridView &G, con
                         const uint32_t end = done ? ld_vol(&S.pass_end[sw][ds.pass_id & (PASS_RING - 1u)]) : tl;
                         const uint32_t avail = end - pos;
                         avail_all = avail;
-                        if (avail >= 32u) { n = 32u; break; }
+                        if (avail >= (uint32_t)NDT_QUANTUM) { n = (uint32_t)NDT_QUANTUM; break; }
                         if (done) {     // final (possibly empty) chunk; bit 30: dead-slot marker
                             n = avail | 0x80000000u | (ld_vol(&S.pass_dead[sw][ds.pass_id & (PASS_RING - 1u)]) ? 0x40000000u : 0u);
                             break;
@@ -1228,10 +1239,29 @@ __device__ __forceinline__ bool compute_drain(NdtSmem &S, const GridView &G, con
                     }
                 }
 #endif
+#if NDT_QUANTUM == 64
+                {
+                    // two pairs per lane: both record gathers are in flight before the first is used, and the two
+                    // (branch-free) arithmetic chains interleave
+                    const bool on_a = (uint32_t)lane < n, on_b = (uint32_t)lane + 32u < n;
+                    if (on_a) {
+                        float4 ea = S.ring[sw][(pos + lane) & (RING - 1u)];
+                        float4 eb = on_b ? S.ring[sw][(pos + 32u + lane) & (RING - 1u)] : ea;
+                        PairRec ra, rb;
+                        ndt_pair_load(G.gauss + (size_t)__float_as_uint(ea.w) * GAUSS_STRIDE, ra);
+                        ndt_pair_load(G.gauss + (size_t)__float_as_uint(eb.w) * GAUSS_STRIDE, rb);
+                        ndt_pair_math(true, ea.x, ea.y, ea.z, ra, T, ang, K.d1, K.d2, hess, acc);
+                        ndt_pair_math(on_b, eb.x, eb.y, eb.z, rb, T, ang, K.d1, K.d2, hess, acc);
+                    }
+                }
+#else
                 if ((uint32_t)lane < n) {
                     const float4 e = S.ring[sw][(pos + lane) & (RING - 1u)];
-                    ndt_pair(e.x, e.y, e.z, T, ang, G.gauss + (size_t)__float_as_uint(e.w) * GAUSS_STRIDE, K.d1, K.d2, hess, acc);
+                    PairRec r;
+                    ndt_pair_load(G.gauss + (size_t)__float_as_uint(e.w) * GAUSS_STRIDE, r);
+                    ndt_pair_math(true, e.x, e.y, e.z, r, T, ang, K.d1, K.d2, hess, acc);
                 }
+#endif
                 pos += n;
 #pragma unroll
                 for (int kk = 0; kk < NDT_PPC; ++kk) if (kk == k) ds.cpos[kk] = pos;
