@@ -55,6 +55,10 @@ struct TargetDev {
     bool stale_buckets = false;   // pts_sorted / leaf_start no longer cover every point (fitness rebuilds first)
     bool unsorted = false;        // leaves appended by updates: the table is no longer in ascending voxel order
     uint32_t upd_incremental = 0, upd_rebuilt = 0;
+    // what the dense arrays hold: cells[] is non-zero exactly at leaf_idx[0 .. fp_V), nbr_head[] exactly at the first
+    // fp_active entries of the listed-cell table (nbr_tiles); fp_clean = that statement holds (false after a failed build)
+    uint32_t fp_V = 0, fp_active = 0;
+    bool fp_clean = false;
 };
 
 // ------------------------------------------------------------------ target build kernels -----
@@ -241,8 +245,17 @@ __global__ void __launch_bounds__(LCROWD_THREADS) leaf_crowded_kernel(const floa
             const float *qu = reinterpret_cast<const float *>(stage[w][buf]) + iu;
             const float *qv = (iv >= 0) ? reinterpret_cast<const float *>(stage[w][buf]) + iv : &s_one;
             const int v_stride = (iv >= 0) ? 4 : 0;
-#pragma unroll 8
-            for (int k = 0; k < m; ++k) {
+            int k = 0;
+            for (; k + 16 <= m; k += 16) {
+#pragma unroll
+                for (int t = 0; t < 16; ++t) {
+                    const float u = qu[4 * (k + t)], v = qv[v_stride * (k + t)];
+                    facc = __fadd_rn(facc, u);
+                    dacc = __dadd_rn(dacc, __dmul_rn((double)u, (double)v));
+                }
+            }
+#pragma unroll 4
+            for (; k < m; ++k) {
                 const float u = qu[4 * k], v = qv[v_stride * k];
                 facc = __fadd_rn(facc, u);
                 dacc = __dadd_rn(dacc, __dmul_rn((double)u, (double)v));
@@ -297,7 +310,7 @@ __device__ __forceinline__ bool nbr_keep(float cx, float cy, float cz, int kx, i
 
 __device__ __forceinline__ void leaf_nbr_account(uint32_t j, const LayoutArg &LA, const int32_t *__restrict__ leaf_idx,
                                                  const float4 *__restrict__ centroid4, uint2 *__restrict__ nbr_head,
-                                                 uint32_t *__restrict__ counters);
+                                                 uint32_t *__restrict__ counters, uint32_t *__restrict__ active);
 
 __global__ void __launch_bounds__(128) leaf_finish_kernel(uint32_t V, int min_pts, double eig_mult, LayoutArg LA,
                                                           const int32_t *__restrict__ leaf_idx, const int32_t *__restrict__ leaf_n,
@@ -305,7 +318,7 @@ __global__ void __launch_bounds__(128) leaf_finish_kernel(uint32_t V, int min_pt
                                                           const double *__restrict__ sums, double *__restrict__ gauss,
                                                           double *__restrict__ icov9, float4 *__restrict__ cells,
                                                           uint2 *__restrict__ nbr_head, uint32_t *__restrict__ counters,
-                                                          const uint32_t *__restrict__ list) {
+                                                          uint32_t *__restrict__ active, const uint32_t *__restrict__ list) {
     // list != NULL (incremental update): V entries of `list` name the leaves to finish, and the neighbour-list
     // accounting is left to nbr_count_kernel (it has to be redone over ALL leaves)
     uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -332,14 +345,14 @@ __global__ void __launch_bounds__(128) leaf_finish_kernel(uint32_t V, int min_pt
         const float4 c = centroid4[j];
         cells[leaf_idx[j]] = make_float4(c.x, c.y, c.z, __int_as_float(tree ? (int32_t)(j + 1) : -(int32_t)(j + 1)));
     }
-    if (tree && account) leaf_nbr_account(j, LA, leaf_idx, centroid4, nbr_head, counters);
+    if (tree && account) leaf_nbr_account(j, LA, leaf_idx, centroid4, nbr_head, counters, active);
 }
 
 // searchable leaf j: count it, add it to the list length of every cell it can be reached from, and fold how far its
 // float centroid lies outside its own cell into the maximum
 __device__ __forceinline__ void leaf_nbr_account(uint32_t j, const LayoutArg &LA, const int32_t *__restrict__ leaf_idx,
                                                  const float4 *__restrict__ centroid4, uint2 *__restrict__ nbr_head,
-                                                 uint32_t *__restrict__ counters) {
+                                                 uint32_t *__restrict__ counters, uint32_t *__restrict__ active) {
     {
         atomicAdd(&counters[0], 1u);
         // how far the float centroid (PCL's kd-tree point) lies outside its own cell: bounds the search
@@ -356,7 +369,9 @@ __device__ __forceinline__ void leaf_nbr_account(uint32_t j, const LayoutArg &LA
                     const int kx = ix + dx, ky = iy + dy, kz = iz + dz;
                     if (kx < 0 || ky < 0 || kz < 0 || kx >= LA.div_b[0] || ky >= LA.div_b[1] || kz >= LA.div_b[2]) continue;
                     if (!nbr_keep(c0.x, c0.y, c0.z, kx, ky, kz, LA)) continue;
-                    atomicAdd(&nbr_head[(size_t)kx + (size_t)ky * LA.div_b[0] + (size_t)kz * LA.div_b[0] * LA.div_b[1]].y, 1u);
+                    const size_t cell = (size_t)kx + (size_t)ky * LA.div_b[0] + (size_t)kz * LA.div_b[0] * LA.div_b[1];
+                    // the first leaf to reach a cell puts it on the list of cells that own a neighbour list
+                    if (atomicAdd(&nbr_head[cell].y, 1u) == 0u) active[atomicAdd(&counters[3], 1u)] = (uint32_t)cell;
                 }
         const float4 c = centroid4[j];
         const double cc[3] = {(double)c.x, (double)c.y, (double)c.z};
@@ -375,10 +390,11 @@ __device__ __forceinline__ void leaf_nbr_account(uint32_t j, const LayoutArg &LA
 // cleared: a leaf that became searchable, or whose centroid moved, changes the lists of up to 27 cells)
 __global__ void __launch_bounds__(128) nbr_count_kernel(uint32_t V, int min_pts, LayoutArg LA, const int32_t *__restrict__ leaf_idx,
                                                         const int32_t *__restrict__ leaf_n, const float4 *__restrict__ centroid4,
-                                                        uint2 *__restrict__ nbr_head, uint32_t *__restrict__ counters) {
+                                                        uint2 *__restrict__ nbr_head, uint32_t *__restrict__ counters,
+                                                        uint32_t *__restrict__ active) {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= V) return;
-    if (leaf_n[j] >= min_pts) leaf_nbr_account(j, LA, leaf_idx, centroid4, nbr_head, counters);
+    if (leaf_n[j] >= min_pts) leaf_nbr_account(j, LA, leaf_idx, centroid4, nbr_head, counters, active);
 }
 
 // incremental update: voxel key of every new point under the EXISTING layout; a finite point outside the grid's index
@@ -411,122 +427,50 @@ __global__ void __launch_bounds__(256) upd_key_kernel(const float4 *__restrict__
 }
 
 // ------------------------------------------------------------------ neighbour lists ----------
-// nbr_head[c].y holds the number of searchable leaves in the 3x3x3 window of cell c that can be reached from it
-// (counted by leaf_finish_kernel).  Two kernels lay the lists out in cell order:
-//   nbr_scan_kernel  one pass over the dense grid: exclusive scan of the counts (decoupled look-back over 2048-cell
-//                    tiles) -> nbr_head[c].x, and the cells with a non-empty list appended to a work list;
-//   nbr_fill_kernel  one thread per listed cell gathers its entries in fixed (z, y, x) window order.
-// The layout and the entry order are deterministic (the order of the work list is not, and does not matter).
+// nbr_head[c].y holds the number of searchable leaves in the 3x3x3 window of cell c that can be reached from it, and the
+// cells with a non-zero count stand on the `active` list (both written by leaf_nbr_account).  nbr_fill_kernel, one
+// thread per listed cell, takes the cell's run of the list array (one atomicAdd per warp) and gathers the entries in
+// fixed (z, y, x) window order.  WHERE a cell's run lies depends on the scheduling; its content and order do not, so a
+// query reads the same candidates in the same order in every build.
+// The dense arrays (cells: 16 B, nbr_head: 8 B per grid cell, mostly empty) are never cleared as a whole after their
+// allocation: grid_clear_kernel, first thing in the next build, zeroes exactly the entries the previous build wrote
+// (its leaves' cells, its listed cells).
 constexpr int NBR_TPB = 256;
-constexpr int NBR_ROUNDS = 8;
-constexpr uint32_t NBR_TILE = NBR_TPB * NBR_ROUNDS;
-constexpr uint32_t NB_PART = 1u << 30, NB_INCL = 2u << 30, NB_MASK = 0x3FFFFFFFu;
+constexpr uint32_t NB_MASK = 0x3FFFFFFFu;
 
-__device__ __forceinline__ uint32_t block_excl_scan_256(uint32_t v, uint32_t *warp_tot /*smem[9]*/, uint32_t &block_total) {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    uint32_t incl = v;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
-    if (lane == 31) warp_tot[w] = incl;
-    __syncthreads();
-    if (w == 0) {
-        uint32_t t = (lane < 8) ? warp_tot[lane] : 0u;
-        uint32_t ti = t;
-#pragma unroll
-        for (int d = 1; d < 8; d <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, ti, d); if (lane >= d) ti += u; }
-        if (lane < 8) warp_tot[lane] = ti - t;
-        if (lane == 7) warp_tot[8] = ti;
-    }
-    __syncthreads();
-    const uint32_t r = warp_tot[w] + incl - v;
-    block_total = warp_tot[8];
-    __syncthreads();
-    return r;
+// counters: [0] searchable leaves, [1] max centroid displacement (float bits), [3] listed cells, [4] list entries in
+// total, [5] crowded voxels, [6] leaves opened by an update, [7] / [8] update: valid new points / outside-the-box flag
+__global__ void __launch_bounds__(256) grid_clear_kernel(const int32_t *__restrict__ leaf_idx, uint32_t V,
+                                                         const uint32_t *__restrict__ active, uint32_t n_active,
+                                                         float4 *__restrict__ cells, uint2 *__restrict__ head) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cells && i < V) cells[leaf_idx[i]] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < n_active) head[active[i]] = make_uint2(0u, 0u);
 }
 
-// counters: [0] searchable leaves, [1] max centroid displacement (float bits), [2] tile ticket, [3] listed cells,
-// [4] list entries in total; state: one look-back word per tile (zeroed with the counters)
-__global__ void __launch_bounds__(NBR_TPB) nbr_scan_kernel(uint2 *__restrict__ head, uint32_t ncells, uint32_t ntiles,
-                                                           uint32_t *__restrict__ counters, uint32_t *__restrict__ state,
-                                                           uint32_t *__restrict__ active) {
-    __shared__ uint32_t wt[9];
-    __shared__ uint32_t s_tile, s_excl;
-    if (threadIdx.x == 0) s_tile = atomicAdd(&counters[2], 1u);
-    __syncthreads();
-    const uint32_t tile = s_tile;
-    // blocked arrangement: thread t owns NBR_ROUNDS consecutive cells (two 32-byte loads)
-    const size_t c0 = (size_t)tile * NBR_TILE + (size_t)threadIdx.x * NBR_ROUNDS;
-    uint32_t cnt[NBR_ROUNDS];
-    uint32_t mine = 0;
-#pragma unroll
-    for (int r = 0; r < NBR_ROUNDS; ++r) {
-        cnt[r] = (c0 + r < ncells) ? __ldcs(&head[c0 + r]).y : 0u;
-        mine += cnt[r];
-    }
-    uint32_t total;
-    const uint32_t lex = block_excl_scan_256(mine, wt, total);
-    if (threadIdx.x < 32) {
-        const int l = threadIdx.x;
-        uint32_t excl = 0;
-        volatile uint32_t *st = state;
-        if (tile == 0) {
-            if (l == 0) st[0] = total | NB_INCL;
-        } else {
-            if (l == 0) st[tile] = total | NB_PART;
-            int base = (int)tile;
-            while (true) {
-                const int j = base - 1 - l;
-                uint32_t v = NB_INCL;
-                if (j >= 0) { do { v = st[j]; } while ((v & ~NB_MASK) == 0u); }
-                const uint32_t incl_mask = __ballot_sync(0xffffffffu, (v & NB_INCL) != 0u);
-                const int stop = __ffs(incl_mask) - 1;
-                uint32_t c = (stop < 0 || l <= stop) ? (v & NB_MASK) : 0u;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-                excl += c;
-                if (stop >= 0) break;
-                base -= 32;
-            }
-            if (l == 0) st[tile] = (excl + total) | NB_INCL;
-        }
-        if (l == 0) {
-            s_excl = excl;
-            if (tile == ntiles - 1u) counters[4] = excl + total;
-        }
-    }
-    __syncthreads();
-    uint32_t off = s_excl + lex;
-    uint32_t n_act = 0;
-#pragma unroll
-    for (int r = 0; r < NBR_ROUNDS; ++r) n_act += cnt[r] ? 1u : 0u;
-    // work-list slots: one atomic per warp
-    uint32_t inc = n_act;
-    const int lane = threadIdx.x & 31;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
-    uint32_t wbase = 0;
-    if (lane == 31 && inc) wbase = atomicAdd(&counters[3], inc);
-    wbase = __shfl_sync(0xffffffffu, wbase, 31);
-    uint32_t slot = wbase + inc - n_act;
-#pragma unroll
-    for (int r = 0; r < NBR_ROUNDS; ++r) {
-        if (cnt[r]) {
-            head[c0 + r].x = off;
-            active[slot++] = (uint32_t)(c0 + r);
-            off += cnt[r];
-        }
-    }
-}
-
-__global__ void __launch_bounds__(NBR_TPB) nbr_fill_kernel(const uint2 *__restrict__ head, const float4 *__restrict__ cells,
-                                                           const uint32_t *__restrict__ counters,
+__global__ void __launch_bounds__(NBR_TPB) nbr_fill_kernel(uint2 *__restrict__ head, const float4 *__restrict__ cells,
+                                                           uint32_t *__restrict__ counters,
                                                            const uint32_t *__restrict__ active, LayoutArg LA,
                                                            float4 *__restrict__ list) {
     const uint32_t n = counters[3];
     const int dx_n = LA.div_b[0], dy_n = LA.div_b[1], dz_n = LA.div_b[2];
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const uint32_t c = active[i];
-        const uint32_t off = head[c].x;
+    const int lane = threadIdx.x & 31;
+    for (uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; i0 < n; i0 += gridDim.x * blockDim.x) {   // warp-uniform
+        const uint32_t i = i0 + lane;
+        const bool on = i < n;
+        const uint32_t c = on ? active[i] : 0u;
+        const uint32_t cnt = on ? head[c].y : 0u;
+        // this warp's run of the list array
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+        uint32_t base = 0;
+        if (lane == 31) base = atomicAdd(&counters[4], incl);
+        base = __shfl_sync(0xffffffffu, base, 31);
+        if (!on) continue;
+        const uint32_t off = base + incl - cnt;
+        if ((size_t)off + cnt > (size_t)NB_MASK) continue;        // over the entry limit: reported by the host (counters[4])
+        head[c].x = off;
         const int iz = (int)(c / ((uint32_t)dx_n * dy_n));
         const int rem = (int)(c - (uint32_t)iz * dx_n * dy_n);
         const int iy = rem / dx_n, ix = rem - iy * dx_n;
@@ -1831,6 +1775,19 @@ static int build_target(b2ndt *h, const float4 *d_pts, size_t n, int nbits_hint)
     t.valid = false; t.N = (uint32_t)n; t.V = 0; t.n_tree = 0; t.max_disp = 0.f;
     t.stale_buckets = false; t.unsorted = false;
     if (d_pts != t.pts_all.as<float4>()) { t.src = d_pts; t.n_all = n; t.owns_all = false; t.upd_incremental = t.upd_rebuilt = 0; }   // else: a rebuild out of the update path
+    // The dense arrays are cleared entry by entry, not as a whole (117 MB for the headline map): zero what the previous
+    // build wrote, while its leaf table and listed-cell table are still intact.
+    bool dense_zero = false;
+    if (t.fp_clean && t.cells.p && t.nbr_head.p) {
+        const uint32_t m = t.fp_V > t.fp_active ? t.fp_V : t.fp_active;
+        if (m) {
+            grid_clear_kernel<<<(m + 255) / 256, 256, 0, h->st>>>(t.leaf_idx.as<int32_t>(), t.fp_V, t.nbr_tiles.as<uint32_t>(), t.fp_active,
+                                                               t.cells.as<float4>(), t.nbr_head.as<uint2>());
+            B2_LAUNCH_CHECK();
+        }
+        dense_zero = true;
+    }
+    t.fp_clean = false; t.fp_V = 0; t.fp_active = 0;
     h->have_last = false;
     memset(&t.L, 0, sizeof(t.L));
     int rc;
@@ -1845,10 +1802,9 @@ static int build_target(b2ndt *h, const float4 *d_pts, size_t n, int nbits_hint)
     B2_CUDA(cudaMemcpyAsync(misc + 8, h->pipe.layouts(), sizeof(VoxLayout), cudaMemcpyDeviceToHost, h->st));
     B2_CUDA(cudaStreamSynchronize(h->st));
     memcpy(&t.L, misc + 8, sizeof(VoxLayout));
-    if (!t.L.ok) { t.valid = true; return 0; }     // empty cloud or PCL's int32 guard: no cells (PCL warns and clears)
+    if (!t.L.ok) { t.valid = true; t.fp_clean = dense_zero; return 0; }     // empty cloud or PCL's int32 guard: no cells (PCL warns and clears)
     t.V = misc[1];
     const uint32_t V = t.V;
-    const uint32_t ntiles = (uint32_t)(((size_t)t.L.ncells + NBR_TILE - 1) / NBR_TILE);
     if ((rc = t.pts_sorted.reserve((n + 1) * sizeof(float4)))) return rc;
     if ((rc = t.leaf_idx.reserve((V + 1) * 4))) return rc;
     if ((rc = t.leaf_n.reserve((V + 1) * 4))) return rc;
@@ -1858,15 +1814,17 @@ static int build_target(b2ndt *h, const float4 *d_pts, size_t n, int nbits_hint)
     if ((rc = t.sums.reserve((size_t)(V + 1) * 72))) return rc;
     if ((rc = t.csum4.reserve((V + 1) * sizeof(float4)))) return rc;
     if ((rc = t.icov9.reserve((size_t)(V + 1) * 72))) return rc;
+    const void *p_cells = t.cells.p, *p_head = t.nbr_head.p;
     if ((rc = t.cells.reserve((size_t)t.L.ncells * 16 + 16))) return rc;
-    if ((rc = t.counters.reserve(((size_t)ntiles + 16) * 4))) return rc;               // counters[16] + one look-back word per tile
+    if ((rc = t.counters.reserve(64 * 4))) return rc;
     if ((rc = t.nbr_head.reserve((size_t)t.L.ncells * 8 + 16))) return rc;
     if ((rc = t.nbr_tiles.reserve(((size_t)t.L.ncells + (size_t)n / LS_SEQ + 64) * 4))) return rc;  // work lists: cells with a list | crowded voxels
     // every searchable leaf enters at most 27 lists: no second round trip to size the lists
     if ((rc = t.nbr_list.reserve(((size_t)(n / (size_t)(h->prm.min_pts > 0 ? h->prm.min_pts : 1) + 1) * 27 + 1) * sizeof(float4)))) return rc;
-    B2_CUDA(cudaMemsetAsync(t.nbr_head.p, 0, (size_t)t.L.ncells * 8, h->st));
-    B2_CUDA(cudaMemsetAsync(t.cells.p, 0, (size_t)t.L.ncells * 16, h->st));
-    B2_CUDA(cudaMemsetAsync(t.counters.p, 0, ((size_t)ntiles + 16) * 4, h->st));
+    // a fresh (or not provably clean) allocation is zeroed once, over its whole capacity: later builds use more of it
+    if (!dense_zero || t.nbr_head.p != p_head) B2_CUDA(cudaMemsetAsync(t.nbr_head.p, 0, t.nbr_head.cap, h->st));
+    if (!dense_zero || t.cells.p != p_cells) B2_CUDA(cudaMemsetAsync(t.cells.p, 0, t.cells.cap, h->st));
+    B2_CUDA(cudaMemsetAsync(t.counters.p, 0, 64 * 4, h->st));
     LayoutArg LA;
     for (int a = 0; a < 3; ++a) { LA.min_b[a] = t.L.min_b[a]; LA.div_b[a] = t.L.div_b[a]; LA.inv[a] = t.L.inv[a]; }
     LA.res = h->prm.res;
@@ -1890,11 +1848,9 @@ static int build_target(b2ndt *h, const float4 *d_pts, size_t n, int nbits_hint)
         leaf_finish_kernel<<<(V + 127) / 128, 128, 0, h->st>>>(V, h->prm.min_pts, h->prm.eig_mult, LA, t.leaf_idx.as<int32_t>(),
                                                               t.leaf_n.as<int32_t>(), t.centroid4.as<float4>(), t.sums.as<double>(),
                                                               t.gauss.as<double>(), t.icov9.as<double>(), t.cells.as<float4>(),
-                                                              t.nbr_head.as<uint2>(), cnt, nullptr);
+                                                              t.nbr_head.as<uint2>(), cnt, active, nullptr);
         B2_LAUNCH_CHECK();
-        // neighbour lists, laid out in cell order
-        nbr_scan_kernel<<<ntiles, NBR_TPB, 0, h->st>>>(t.nbr_head.as<uint2>(), t.L.ncells, ntiles, cnt, cnt + 16, active);
-        B2_LAUNCH_CHECK();
+        // neighbour lists of the listed cells
         nbr_fill_kernel<<<148 * 8, NBR_TPB, 0, h->st>>>(t.nbr_head.as<uint2>(), t.cells.as<float4>(), cnt, active, LA, t.nbr_list.as<float4>());
         B2_LAUNCH_CHECK();
     }
@@ -1903,6 +1859,7 @@ static int build_target(b2ndt *h, const float4 *d_pts, size_t n, int nbits_hint)
     t.n_tree = misc[0];
     memcpy(&t.max_disp, &misc[1], 4);
     if (misc[4] >= NB_MASK) { set_error("SetInputTarget: %u neighbour-list entries exceed the 2^30 limit", misc[4]); return B2_ERR_INVALID; }
+    t.fp_V = V; t.fp_active = misc[3]; t.fp_clean = true;
     t.valid = true;     // only a completely built target is usable: a failed allocation above leaves "no target set"
     return 0;
 }
@@ -1937,12 +1894,9 @@ static int update_target(b2ndt *h, const float4 *d_new, size_t n) {
     // the points in hand-over order: an owned copy from the first update on
     if (!t.owns_all) {
         if (t.n_all && !t.src) { set_error("b2ndt_update_target: the target's points are not available"); return B2_ERR_STATE; }
-        DevBuf nb;
-        if ((rc = nb.reserve((t.n_all + n + 1) * sizeof(float4)))) return rc;
-        if (t.n_all) B2_CUDA(cudaMemcpyAsync(nb.p, t.src, t.n_all * sizeof(float4), cudaMemcpyDeviceToDevice, h->st));
-        B2_CUDA(cudaStreamSynchronize(h->st));
-        t.pts_all.release();
-        t.pts_all = nb;
+        // (t.src never points into pts_all here: a rebuild out of this path keeps owns_all set)
+        if ((rc = t.pts_all.reserve((t.n_all + n + 1) * sizeof(float4)))) return rc;
+        if (t.n_all) B2_CUDA(cudaMemcpyAsync(t.pts_all.p, t.src, t.n_all * sizeof(float4), cudaMemcpyDeviceToDevice, h->st));
         t.owns_all = true;
         t.src = t.pts_all.as<float4>();
     } else {
@@ -1956,9 +1910,8 @@ static int update_target(b2ndt *h, const float4 *d_new, size_t n) {
     auto rebuild = [&]() { ++t.upd_rebuilt; return build_target(h, t.pts_all.as<float4>(), t.n_all, 0); };
     if (!t.L.ok || t.V == 0 || t.L.ncells > (1u << 30)) return rebuild();
     // keys of the new points under the existing layout, sorted by voxel, runs = touched voxels
-    const uint32_t ntiles = (uint32_t)(((size_t)t.L.ncells + NBR_TILE - 1) / NBR_TILE);
     uint32_t *cnt = t.counters.as<uint32_t>();
-    B2_CUDA(cudaMemsetAsync(t.counters.p, 0, ((size_t)ntiles + 16) * 4, h->st));
+    B2_CUDA(cudaMemsetAsync(t.counters.p, 0, 64 * 4, h->st));
     uint32_t off[2] = {0u, (uint32_t)n};
     if ((rc = h->pipe.plan(off, 1, h->st))) return rc;
     {
@@ -1977,6 +1930,8 @@ static int update_target(b2ndt *h, const float4 *d_new, size_t n) {
     if (oob) return rebuild();
     ++t.upd_incremental;
     if (R == 0) { t.N = (uint32_t)t.n_all; return 0; }            // only non-finite points
+    // from here on the tables are modified in place: a failure leaves "no target set" and dense arrays of unknown content
+    t.valid = false; t.fp_clean = false;
     const uint32_t V0 = t.V;
     const size_t Vcap = (size_t)V0 + R + 1;
     if ((rc = grow_keep(t.leaf_idx, Vcap * 4, (size_t)V0 * 4, h->st))) return rc;
@@ -1988,8 +1943,9 @@ static int update_target(b2ndt *h, const float4 *d_new, size_t n) {
     if ((rc = grow_keep(t.sums, Vcap * 72, (size_t)V0 * 72, h->st))) return rc;
     if ((rc = grow_keep(t.icov9, Vcap * 72, (size_t)V0 * 72, h->st))) return rc;
     if ((rc = t.touched.reserve(((size_t)R + 1) * 4))) return rc;
-    // work lists (cells with a list | crowded runs) and the lists themselves are rebuilt: contents need not survive
-    if ((rc = t.nbr_tiles.reserve(((size_t)t.L.ncells + (size_t)n / LS_SEQ + 64) * 4))) return rc;
+    // the listed-cell table must survive (it names the list heads to zero); the crowded-run list behind it and the
+    // neighbour lists themselves are rebuilt
+    if ((rc = grow_keep(t.nbr_tiles, ((size_t)t.L.ncells + (size_t)n / LS_SEQ + 64) * 4, (size_t)t.fp_active * 4, h->st))) return rc;
     if ((rc = t.nbr_list.reserve(((size_t)(t.n_all / (size_t)(h->prm.min_pts > 0 ? h->prm.min_pts : 1) + 1) * 27 + 1) * sizeof(float4)))) return rc;
     LayoutArg LA;
     for (int a = 0; a < 3; ++a) { LA.min_b[a] = t.L.min_b[a]; LA.div_b[a] = t.L.div_b[a]; LA.inv[a] = t.L.inv[a]; }
@@ -2012,23 +1968,26 @@ static int update_target(b2ndt *h, const float4 *d_new, size_t n) {
     leaf_finish_kernel<<<(R + 127) / 128, 128, 0, h->st>>>(R, h->prm.min_pts, h->prm.eig_mult, LA, t.leaf_idx.as<int32_t>(),
                                                           t.leaf_n.as<int32_t>(), t.centroid4.as<float4>(), t.sums.as<double>(),
                                                           t.gauss.as<double>(), t.icov9.as<double>(), t.cells.as<float4>(),
-                                                          t.nbr_head.as<uint2>(), cnt, t.touched.as<uint32_t>());
+                                                          t.nbr_head.as<uint2>(), cnt, active, t.touched.as<uint32_t>());
     B2_LAUNCH_CHECK();
-    // neighbour lists again, over every leaf (at most V0 + R of them: slots past the leaves opened hold n = 0)
-    B2_CUDA(cudaMemsetAsync(t.nbr_head.p, 0, (size_t)t.L.ncells * 8, h->st));
+    // neighbour lists again, over every leaf: the list heads of the cells listed so far are zeroed, then recounted
+    if (t.fp_active) {
+        grid_clear_kernel<<<(t.fp_active + 255) / 256, 256, 0, h->st>>>(nullptr, 0u, active, t.fp_active, nullptr, t.nbr_head.as<uint2>());
+        B2_LAUNCH_CHECK();
+    }
     B2_CUDA(cudaMemcpyAsync(misc, cnt, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->st));
     B2_CUDA(cudaStreamSynchronize(h->st));
     const uint32_t V1 = V0 + misc[6];
     nbr_count_kernel<<<(V1 + 127) / 128, 128, 0, h->st>>>(V1, h->prm.min_pts, LA, t.leaf_idx.as<int32_t>(), t.leaf_n.as<int32_t>(),
-                                                         t.centroid4.as<float4>(), t.nbr_head.as<uint2>(), cnt);
-    B2_LAUNCH_CHECK();
-    nbr_scan_kernel<<<ntiles, NBR_TPB, 0, h->st>>>(t.nbr_head.as<uint2>(), t.L.ncells, ntiles, cnt, cnt + 16, active);
+                                                         t.centroid4.as<float4>(), t.nbr_head.as<uint2>(), cnt, active);
     B2_LAUNCH_CHECK();
     nbr_fill_kernel<<<148 * 8, NBR_TPB, 0, h->st>>>(t.nbr_head.as<uint2>(), t.cells.as<float4>(), cnt, active, LA, t.nbr_list.as<float4>());
     B2_LAUNCH_CHECK();
     B2_CUDA(cudaMemcpyAsync(misc, cnt, 32, cudaMemcpyDeviceToHost, h->st));
     B2_CUDA(cudaStreamSynchronize(h->st));
-    if (misc[4] >= NB_MASK) { t.valid = false; set_error("b2ndt_update_target: %u neighbour-list entries exceed the 2^30 limit", misc[4]); return B2_ERR_INVALID; }
+    if (misc[4] >= NB_MASK) { set_error("b2ndt_update_target: %u neighbour-list entries exceed the 2^30 limit", misc[4]); return B2_ERR_INVALID; }
+    t.fp_V = V1; t.fp_active = misc[3]; t.fp_clean = true;
+    t.valid = true;
     t.n_tree = misc[0];
     memcpy(&t.max_disp, &misc[1], 4);
     if (V1 != V0) t.unsorted = true;

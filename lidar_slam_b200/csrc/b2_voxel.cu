@@ -10,6 +10,7 @@
 
 #include <float.h>
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <cmath>
 
@@ -565,7 +566,8 @@ int VoxPipeline::plan(const uint32_t *off, size_t nB, cudaStream_t st) {
     N = off[nB];
     // small tiles only while they are needed to fill the SMs: the look-back of a radix pass walks over the tiles that
     // started together, so fewer, larger tiles are cheaper as soon as there are enough of them
-    tile_elems = SORT_THREADS * (N >= SORT_LARGE_FROM ? SORT_ITEMS_LARGE : SORT_ITEMS_SMALL);
+    static const size_t large_from = [] { const char *e = getenv("B2_SORT_LARGE_FROM"); return e ? (size_t)atoll(e) : SORT_LARGE_FROM; }();
+    tile_elems = SORT_THREADS * (N >= large_from ? SORT_ITEMS_LARGE : SORT_ITEMS_SMALL);
     int rc;
     if (nB <= 1) {
         ntiles = (N + tile_elems - 1) / tile_elems;
@@ -708,7 +710,6 @@ void VoxPipeline::release() {
 //     cost is the order-exact add chain itself (4 cycles per member).
 // Output in ascending voxel index.
 constexpr uint32_t VF_SEQ = 32;
-
 __device__ __forceinline__ void run_bounds(uint32_t j, const uint32_t *__restrict__ run_start, const uint32_t *__restrict__ run_seg,
                                            const uint32_t *__restrict__ run_seg_off, const PlanView &P,
                                            const VoxLayout *__restrict__ layouts, uint32_t &s, uint32_t &e) {
@@ -825,8 +826,14 @@ __global__ void __launch_bounds__(CROWD_THREADS) vf_crowded_kernel(const float4 
 #pragma unroll 32
                 for (int k = 0; k < CROWD_GROUP; ++k) acc = __fadd_rn(acc, q[4 * k]);
             } else {
+                // most crowded voxels have fewer members than a group: sixteen at a time, then the rest
+                int k = 0;
+                for (; k + 16 <= m; k += 16) {
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) acc = __fadd_rn(acc, q[4 * (k + u)]);
+                }
 #pragma unroll 4
-                for (int k = 0; k < m; ++k) acc = __fadd_rn(acc, q[4 * k]);
+                for (; k < m; ++k) acc = __fadd_rn(acc, q[4 * k]);
             }
         };
         // Software pipeline over groups: while group g is folded, the points of g+1 .. g+3 are in flight into the
