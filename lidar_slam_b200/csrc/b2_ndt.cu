@@ -887,10 +887,16 @@ struct SearchState {
     uint32_t pass_id = 0;      // passes produced so far
 };
 
+// Point of lane l in the round that starts at b: b + l * lstride.  lstride = 1 (batch kernel): a round is 32 consecutive
+// points (coalesced, neighbouring points share list lines in L1); lstride = number of search warps of the cluster
+// (single match): every warp takes a uniform sample of the scan -- the source is in voxel order, and rounds of
+// consecutive points differ several-fold in candidates (one 32-point round near the sensor held a whole cluster at the
+// pass barrier for 10 us, profiles/r2_single_match_trace.txt).
 __device__ __forceinline__ void search_pass(NdtSmem &S, const GridView &G, const float4 *__restrict__ src, uint32_t first,
-                                            uint32_t last, uint32_t b0, uint32_t stride, const float *T, int sw, int lane,
-                                            SearchState &st) {
+                                            uint32_t last, uint32_t b0, uint32_t stride, uint32_t lstride, const float *T, int sw,
+                                            int lane, SearchState &st) {
     (void)first;
+    const uint32_t loff = (uint32_t)lane * lstride;
     const uint32_t lt = (1u << lane) - 1u;
     float4 *ring = S.ring[sw];
     float4 *stage_all = S.stage[sw];
@@ -917,14 +923,14 @@ __device__ __forceinline__ void search_pass(NdtSmem &S, const GridView &G, const
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         // ld.global.cg (L2 only): the sources may still be streaming in from the host while the kernel runs, and a
         // 32-byte sector can hold points of two matches that arrive in different chunks
-        if (b < last && b + lane < last) v = __ldcg(&src[b + lane]);
+        if (b < last && b + loff < last) v = __ldcg(&src[b + loff]);
         return v;
     };
     {
             auto prepare = [&](uint32_t b, const float4 pt, int buf, uint32_t &off, uint32_t &cnt) {
                 off = 0u; cnt = 0u;
                 float tx = 0.f, ty = 0.f, tz = 0.f;
-                if (b < last && b + lane < last && G.ok) {
+                if (b < last && b + loff < last && G.ok) {
                     transform_f32(T, pt.x, pt.y, pt.z, tx, ty, tz);
                     if (finite3(tx, ty, tz)) {
                         // every cell that can hold a centroid within the radius (centroids may sit up to
@@ -1031,15 +1037,17 @@ __device__ __forceinline__ void search_pass(NdtSmem &S, const GridView &G, const
                         if (lane == 0) publish_tail(&S.tail[sw], my_tail);
                     }
                 }
-                // ---- irregular lanes: dense window walk over the cell grid, one row of <= 4 cells at a time
-                if (__any_sync(0xffffffffu, irregular)) {
-                    int ex0 = -1, ex1 = -1, ex2 = -1;
-                    size_t wbase = 0;
-                    const float4 pt = stage[lane];
-                    const float4 tq = stage[32 + lane];
+                // ---- irregular lanes (rare: a centre cell outside the grid -- e.g. returns above the map's height range --
+                // or a query within the margin of a cell face): the dense window of ONE such query at a time is searched
+                // by the whole warp, lane = window cell (<= 4 x 4 x 4), so a query costs one or two parallel load rounds
+                // instead of a serial walk over its rows (which held a single match's cluster at the pass barrier)
+                uint32_t irr_mask = __ballot_sync(0xffffffffu, irregular);
+                if (irr_mask) {
+                    int lo0 = 0, lo1 = 0, lo2 = 0, nx = 0, ny = 0, nz = 0;
                     if (irregular) {
+                        const float4 tq = stage[32 + lane];
                         const float q[3] = {tq.x, tq.y, tq.z};
-                        int lo[3], ex[3];
+                        int lo[3], nn[3];
                         bool empty = false;
 #pragma unroll
                         for (int a = 0; a < 3; ++a) {
@@ -1047,36 +1055,38 @@ __device__ __forceinline__ void search_pass(NdtSmem &S, const GridView &G, const
                             int l = (int)floorf((q[a] - G.res - mg) * G.inv_leaf) - G.min_b[a];
                             int h = (int)floorf((q[a] + G.res + mg) * G.inv_leaf) - G.min_b[a];
                             l = max(l, 0); h = min(h, G.div_b[a] - 1);
-                            lo[a] = l; ex[a] = min(h - l, 3);      // the window never exceeds 4 cells (margin << cell)
+                            lo[a] = l; nn[a] = min(h - l, 3) + 1;      // the window never exceeds 4 cells (margin << cell)
                             empty = empty || (h < l);
                         }
-                        if (!empty) {
-                            ex0 = ex[0]; ex1 = ex[1]; ex2 = ex[2];
-                            wbase = (size_t)lo[0] + (size_t)lo[1] * G.mul[1] + (size_t)lo[2] * G.mul[2];
-                        }
+                        if (!empty) { lo0 = lo[0]; lo1 = lo[1]; lo2 = lo[2]; nx = nn[0]; ny = nn[1]; nz = nn[2]; }
                     }
-                    const int nplanes = __reduce_max_sync(0xffffffffu, ex2 + 1);
-                    for (int plane = 0; plane < nplanes; ++plane) {
-                        const int nrows = __reduce_max_sync(0xffffffffu, (plane <= ex2) ? ex1 + 1 : 0);
-                        for (int row = 0; row < nrows; ++row) {
-                            ring_room(128u);
-                            const bool act = (plane <= ex2) && (row <= ex1);
-                            const float4 *wp = G.cells + wbase + (size_t)plane * G.mul[2] + (size_t)row * G.mul[1];
-                            uint32_t qn = my_tail;
-                            for (int dxi = 0; dxi < 4; ++dxi) {
-                                float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
-                                if (act && dxi <= ex0) c = __ldg(wp + dxi);
-                                const float ddx = __fsub_rn(tq.x, c.x), ddy = __fsub_rn(tq.y, c.y), ddz = __fsub_rn(tq.z, c.z);
-                                const float d2f = __fadd_rn(__fadd_rn(__fmul_rn(ddx, ddx), __fmul_rn(ddy, ddy)), __fmul_rn(ddz, ddz));
-                                const int code = __float_as_int(c.w);
-                                const bool hit = (code > 0) && (d2f < G.r2);
-                                const uint32_t b = __ballot_sync(0xffffffffu, hit);
-                                if (hit) ring[(qn + __popc(b & lt)) & (RING - 1u)] = make_float4(pt.x, pt.y, pt.z, __int_as_float(code - 1));
-                                qn += __popc(b);
+                    while (irr_mask) {
+                        const int srcl = __ffs(irr_mask) - 1;
+                        irr_mask &= irr_mask - 1u;
+                        const int wx = __shfl_sync(0xffffffffu, nx, srcl), wy = __shfl_sync(0xffffffffu, ny, srcl), wz = __shfl_sync(0xffffffffu, nz, srcl);
+                        const int b0x = __shfl_sync(0xffffffffu, lo0, srcl), b0y = __shfl_sync(0xffffffffu, lo1, srcl), b0z = __shfl_sync(0xffffffffu, lo2, srcl);
+                        const int total_c = wx * wy * wz;
+                        if (total_c == 0) continue;
+                        const float4 pt = stage[srcl];
+                        const float4 tq = stage[32 + srcl];
+                        const size_t wbase = (size_t)b0x + (size_t)b0y * G.mul[1] + (size_t)b0z * G.mul[2];
+                        for (int kb = 0; kb < total_c; kb += 32) {
+                            ring_room(32u);
+                            const int k = kb + lane;
+                            float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (k < total_c) {
+                                const int iz = k / (wx * wy), r = k - iz * wx * wy, iy = r / wx, ix = r - iy * wx;
+                                c = __ldg(G.cells + wbase + (size_t)ix + (size_t)iy * G.mul[1] + (size_t)iz * G.mul[2]);
                             }
-                            __syncwarp();
-                            if (qn != my_tail) {
-                                my_tail = qn;
+                            const float ddx = __fsub_rn(tq.x, c.x), ddy = __fsub_rn(tq.y, c.y), ddz = __fsub_rn(tq.z, c.z);
+                            const float d2f = __fadd_rn(__fadd_rn(__fmul_rn(ddx, ddx), __fmul_rn(ddy, ddy)), __fmul_rn(ddz, ddz));
+                            const int code = __float_as_int(c.w);
+                            const bool hit = (code > 0) && (d2f < G.r2);
+                            const uint32_t bm = __ballot_sync(0xffffffffu, hit);
+                            if (hit) ring[(my_tail + __popc(bm & lt)) & (RING - 1u)] = make_float4(pt.x, pt.y, pt.z, __int_as_float(code - 1));
+                            if (bm) {
+                                my_tail += __popc(bm);
+                                __syncwarp();
                                 if (lane == 0) publish_tail(&S.tail[sw], my_tail);
                             }
                         }
@@ -1280,8 +1290,14 @@ __global__ void __launch_bounds__(NDT_THREADS, NDT_MIN_CTAS) ndt_match_kernel(Gr
             // rounds are dealt out CTA-first (round = sw * C + crank): the source is in voxel order, so consecutive
             // rounds are spatial neighbours with similar hit counts and every CTA gets an even sample of the scan
             TRC(0);
-            search_pass(S, G, A.src, first, last, first + (sw * C + crank) * 32u, stride, SL.ctl.T, sw, lane, st);
+#ifdef NDT_TIMING
+            if (A.timing && match == 0 && trc_pass == 2 && lane == 0 && sw == 0) { unsigned long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); A.timing[128 + crank * 16 + 12] = g; }
+#endif
+            search_pass(S, G, A.src, first, last, first + (sw * C + crank), stride, C * NDT_NSW, SL.ctl.T, sw, lane, st);
             TRC(1);
+#ifdef NDT_TIMING
+            if (A.timing && match == 0 && trc_pass == 2 && lane == 0) { unsigned long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); A.timing[128 + crank * 16 + warp] = g; }
+#endif
 #ifdef NDT_TIMING
             ++trc_pass;
 #endif
@@ -1302,8 +1318,14 @@ __global__ void __launch_bounds__(NDT_THREADS, NDT_MIN_CTAS) ndt_match_kernel(Gr
         while (true) {
             (void)compute_drain(S, G, K, SL.ctl, warp, lane, ds, SL.warp_part[warp]);
             TRC(2);
+#ifdef NDT_TIMING
+            if (A.timing && match == 0 && trc_pass == 2 && lane == 0) { unsigned long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); A.timing[128 + crank * 16 + warp] = g; }
+#endif
             cta_barrier();                              // (1)
             TRC(3);
+#ifdef NDT_TIMING
+            if (A.timing && match == 0 && trc_pass == 1 && tid == 0) { unsigned long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); A.timing[96 + crank] = g; }
+#endif
             // ---------------- deterministic reduction: CTA -> cluster (fixed order) ----------------
             if (tid < NACC) {
                 double s = 0.0;
@@ -1314,6 +1336,9 @@ __global__ void __launch_bounds__(NDT_THREADS, NDT_MIN_CTAS) ndt_match_kernel(Gr
             if (C > 1) {
                 cluster.sync();
                 TRC(4);
+#ifdef NDT_TIMING
+                if (A.timing && match == 0 && trc_pass == 1 && tid == 0) { unsigned long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); A.timing[112 + crank] = g; }
+#endif
                 if (tid < NACC) {
                     // all remote (DSMEM) loads are issued before the first one is consumed; summed in rank order
                     double v[16];
@@ -1467,7 +1492,7 @@ __global__ void __launch_bounds__(NDT_THREADS, NDT_MIN_CTAS) ndt_batch_kernel(Gr
                 if (item) {
                     Slot &SL = S.slot[s];
                     const uint32_t first = ld_vol(&SL.first), last = ld_vol(&SL.last);
-                    search_pass(S, G, A.src, first, last, first + sw * 32u, NDT_NSW * 32u, SL.ctl.T, sw, lane, st);
+                    search_pass(S, G, A.src, first, last, first + sw * 32u, NDT_NSW * 32u, 1u, SL.ctl.T, sw, lane, st);
                     TMB_LAP(1);                                // [1] producing
                 } else {
                     search_dead_marker(S, sw, lane, st);
@@ -2198,8 +2223,8 @@ static int launch_match(b2ndt *h, const MatchArgs &A, size_t B, int C) {
     MatchArgs Ac = A;
 #ifdef NDT_TIMING
     static unsigned long long *d_tr = nullptr;
-    if (!d_tr) cudaMalloc(&d_tr, 96 * 8);
-    cudaMemsetAsync(d_tr, 0, 96 * 8, h->st);
+    if (!d_tr) cudaMalloc(&d_tr, 384 * 8);
+    cudaMemsetAsync(d_tr, 0, 384 * 8, h->st);
     Ac.timing = d_tr;
 #endif
     cudaError_t e = cudaLaunchKernelEx(&cfg, ndt_match_kernel, G, K, Ac);
@@ -2207,9 +2232,29 @@ static int launch_match(b2ndt *h, const MatchArgs &A, size_t B, int C) {
     if (e != cudaSuccess) { set_error("ndt_match_kernel launch failed: %s", cudaGetErrorString(e)); return B2_ERR_CUDA; }
 #ifdef NDT_TIMING
     if (B == 1 && !A.deriv_only) {
-        unsigned long long t[96];
+        unsigned long long t[384];
         cudaStreamSynchronize(h->st);
         cudaMemcpy(t, d_tr, sizeof(t), cudaMemcpyDeviceToHost);
+        {
+            // pass 1, every CTA of the cluster on the global timer: arrival at barrier 1 / release from the cluster barrier (ns after the first arrival)
+            unsigned long long t0 = ~0ull;
+            for (int r = 0; r < C; ++r) if (t[96 + r] && t[96 + r] < t0) t0 = t[96 + r];
+            fprintf(stderr, "[ndt cluster] C %d pass 1 b1(ns):", C);
+            for (int r = 0; r < C; ++r) fprintf(stderr, " %llu", t[96 + r] - t0);
+            fprintf(stderr, " | after cluster barrier:");
+            for (int r = 0; r < C; ++r) fprintf(stderr, " %llu", t[112 + r] - t0);
+            fprintf(stderr, "\n");
+            // pass 2, per CTA: search start (sw 0), then per warp: 4 x compute drained, 8 x search finished (ns after the earliest search start)
+            unsigned long long s0 = ~0ull;
+            for (int r = 0; r < C; ++r) if (t[128 + r * 16 + 12] && t[128 + r * 16 + 12] < s0) s0 = t[128 + r * 16 + 12];
+            for (int r = 0; r < C; ++r) {
+                fprintf(stderr, "[ndt warps] cta %2d start %5llu | drained", r, t[128 + r * 16 + 12] - s0);
+                for (int w = 0; w < NDT_NCW; ++w) fprintf(stderr, " %5llu", t[128 + r * 16 + w] - s0);
+                fprintf(stderr, " | search finished");
+                for (int w = NDT_NCW; w < NDT_WARPS; ++w) fprintf(stderr, " %5llu", t[128 + r * 16 + w] - s0);
+                fprintf(stderr, "\n");
+            }
+        }
         for (int p = 0; p < 3; ++p)
             fprintf(stderr, "[ndt trace] C %d pass %d | search: start %llu finish %llu | compute: drained %llu b1 %llu csync %llu totals(b2) %llu ctl(b3) %llu\n",
                     C, p, t[32 + p * 8 + 0], t[32 + p * 8 + 1], t[32 + p * 8 + 2], t[32 + p * 8 + 3], t[32 + p * 8 + 4], t[32 + p * 8 + 5], t[32 + p * 8 + 6]);

@@ -28,8 +28,8 @@ for r in rows[2:]:
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], stdout=subprocess.PIPE, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
 h = rows[1]
-data = [r for r in rows[2:] if len(r) == len(h)]
 si, ii = h.index("# Samples"), h.index("Instructions Executed")
+data = [r for r in rows[2:] if len(r) == len(h) and r[si].isdigit()]      # several kernels: their source pages follow one another
 tot = sum(int(r[si]) for r in data)
 print("total samples", tot, "sass instructions", len(data))
 stalls = [c for c in h if c.startswith("stall_") and "Not Issued" not in c]
