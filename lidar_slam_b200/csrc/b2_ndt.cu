@@ -20,6 +20,7 @@
 //                              header and one contiguous run instead of 27 scattered cells)
 // The path is a gather + reduction (no dense contraction): no tensor cores by design.
 #include <cooperative_groups.h>
+#include <cooperative_groups/scan.h>
 
 #include <algorithm>
 #include <cmath>
@@ -354,7 +355,7 @@ __device__ __forceinline__ void leaf_nbr_account(uint32_t j, const LayoutArg &LA
                                                  const float4 *__restrict__ centroid4, uint2 *__restrict__ nbr_head,
                                                  uint32_t *__restrict__ counters, uint32_t *__restrict__ active) {
     {
-        atomicAdd(&counters[0], 1u);
+        uint32_t first_mask = 0u;
         // how far the float centroid (PCL's kd-tree point) lies outside its own cell: bounds the search
         // window margin of the match kernel.  Cell k of an axis spans [k/inv, (k+1)/inv).
         const int idx = leaf_idx[j];
@@ -370,9 +371,25 @@ __device__ __forceinline__ void leaf_nbr_account(uint32_t j, const LayoutArg &LA
                     if (kx < 0 || ky < 0 || kz < 0 || kx >= LA.div_b[0] || ky >= LA.div_b[1] || kz >= LA.div_b[2]) continue;
                     if (!nbr_keep(c0.x, c0.y, c0.z, kx, ky, kz, LA)) continue;
                     const size_t cell = (size_t)kx + (size_t)ky * LA.div_b[0] + (size_t)kz * LA.div_b[0] * LA.div_b[1];
-                    // the first leaf to reach a cell puts it on the list of cells that own a neighbour list
-                    if (atomicAdd(&nbr_head[cell].y, 1u) == 0u) active[atomicAdd(&counters[3], 1u)] = (uint32_t)cell;
+                    // the first leaf to reach a cell puts it on the list of cells that own a neighbour list (below)
+                    if (atomicAdd(&nbr_head[cell].y, 1u) == 0u) first_mask |= 1u << ((dz + 1) * 9 + (dy + 1) * 3 + (dx + 1));
                 }
+        {
+            // one atomicAdd per warp for the listed-cell slots (a counter bumped once per cell serialises the kernel)
+            cg::coalesced_group g = cg::coalesced_threads();
+            const uint32_t mine = (uint32_t)__popc(first_mask);
+            const uint32_t incl = cg::inclusive_scan(g, mine);
+            uint32_t base = 0;
+            if (g.thread_rank() == g.size() - 1 && incl) base = atomicAdd(&counters[3], incl);
+            base = g.shfl(base, g.size() - 1);
+            uint32_t o = base + incl - mine;
+            for (uint32_t m = first_mask; m; m &= m - 1u) {
+                const int b = __ffs(m) - 1;
+                const int kz = iz + b / 9 - 1, ky = iy + (b % 9) / 3 - 1, kx = ix + b % 3 - 1;
+                active[o++] = (uint32_t)((size_t)kx + (size_t)ky * LA.div_b[0] + (size_t)kz * LA.div_b[0] * LA.div_b[1]);
+            }
+            if (g.thread_rank() == 0) atomicAdd(&counters[0], g.size());
+        }
         const float4 c = centroid4[j];
         const double cc[3] = {(double)c.x, (double)c.y, (double)c.z};
         const int ii[3] = {ix, iy, iz};
@@ -532,9 +549,6 @@ __global__ void __launch_bounds__(NBR_TPB) nbr_fill_kernel(uint2 *__restrict__ h
 #ifndef NDT_LPF
 #define NDT_LPF 1      // search warps pull the neighbour-list lines of the next round into L1
 #endif
-#ifndef NDT_PF
-#define NDT_PF 0       // compute warps prefetch the next chunk's voxel records into L1
-#endif
 constexpr int NACC = 35;                       // per-lane accumulators of a derivative pass (layout at ndt_pair)
 constexpr int NDT_WARPS = NDT_NCW + NDT_NSW;
 constexpr int NDT_THREADS = NDT_WARPS * 32;
@@ -545,9 +559,7 @@ constexpr int NDT_PPC = NDT_NSW / NDT_NCW;     // producers (search warps) per c
 #ifndef NDT_DRAIN_SLEEP
 #define NDT_DRAIN_SLEEP 32
 #endif
-#ifndef NDT_QUANTUM
-#define NDT_QUANTUM 32     // pairs a compute warp takes from a ring per turn: 32 (one per lane) or 64 (two per lane)
-#endif
+
 constexpr uint32_t RING = NDT_RING;            // ring entries per search warp (power of two, >= 128 + 32)
 static_assert(NDT_NCW % 4 == 0 && NDT_NSW % 4 == 0 && NDT_NSW % NDT_NCW == 0, "warp-group multiples");
 
@@ -1142,6 +1154,9 @@ __device__ __forceinline__ bool compute_drain(NdtSmem &S, const GridView &G, con
     for (int i = 0; i < NACC; ++i) acc[i] = 0.0;
     {
             uint32_t done_mask = 0;                         // bit k: producer k exhausted for this pass
+            uint32_t left[NDT_PPC];                         // pairs of producer k's last, partial chunk (folded together below)
+#pragma unroll
+            for (int kk = 0; kk < NDT_PPC; ++kk) left[kk] = 0u;
             int turn = 0;
             while (done_mask != (1u << NDT_PPC) - 1u) {
                 // fixed round-robin over this warp's producers (deterministic accumulation order)
@@ -1154,7 +1169,6 @@ __device__ __forceinline__ bool compute_drain(NdtSmem &S, const GridView &G, con
                 for (int kk = 0; kk < NDT_PPC; ++kk) if (kk == k) pos = ds.cpos[kk];
                 // wait for a full chunk of 32 pairs, or for the producer to finish the pass
                 uint32_t n = 0;
-                uint32_t avail_all = 0;
                 if (lane == 0) {
                     while (true) {
                         // tail first, finished second: when the pass is not finished yet, everything up to the
@@ -1167,8 +1181,7 @@ __device__ __forceinline__ bool compute_drain(NdtSmem &S, const GridView &G, con
                         __threadfence_block();
                         const uint32_t end = done ? ld_vol(&S.pass_end[sw][ds.pass_id & (PASS_RING - 1u)]) : tl;
                         const uint32_t avail = end - pos;
-                        avail_all = avail;
-                        if (avail >= (uint32_t)NDT_QUANTUM) { n = (uint32_t)NDT_QUANTUM; break; }
+                        if (avail >= 32u) { n = 32u; break; }
                         if (done) {     // final (possibly empty) chunk; bit 30: dead-slot marker
                             n = avail | 0x80000000u | (ld_vol(&S.pass_dead[sw][ds.pass_id & (PASS_RING - 1u)]) ? 0x40000000u : 0u);
                             break;
@@ -1182,46 +1195,53 @@ __device__ __forceinline__ bool compute_drain(NdtSmem &S, const GridView &G, con
                 n &= 0x3fffffffu;
                 __threadfence_block();
                 if (!have_desc) { hess = ctl.hess != 0; have_desc = true; }
-#if NDT_PF
-                {   // pull the records of this ring's NEXT chunk towards L1 while this chunk is computed
-                    avail_all = __shfl_sync(0xffffffffu, avail_all, 0);
-                    if (avail_all > 32u + (uint32_t)lane) {
-                        const float lw = S.ring[sw][(pos + 32u + lane) & (RING - 1u)].w;
-                        const char *gp = reinterpret_cast<const char *>(G.gauss + (size_t)__float_as_uint(lw) * GAUSS_STRIDE);
-                        asm volatile("prefetch.global.L1 [%0];" ::"l"(gp));
-                        asm volatile("prefetch.global.L1 [%0];" ::"l"(gp + 72));
-                    }
+                if (final_chunk) {
+                    // the last, partial chunk of a producer waits for those of the other producers: together they
+                    // fill fewer 32-pair steps (what is left is a property of the pass, not of the timing)
+#pragma unroll
+                    for (int kk = 0; kk < NDT_PPC; ++kk) if (kk == k) left[kk] = n;
+                    done_mask |= (1u << k);
+                    continue;
                 }
-#endif
-#if NDT_QUANTUM == 64
                 {
-                    // two pairs per lane: both record gathers are in flight before the first is used, and the two
-                    // (branch-free) arithmetic chains interleave
-                    const bool on_a = (uint32_t)lane < n, on_b = (uint32_t)lane + 32u < n;
-                    if (on_a) {
-                        float4 ea = S.ring[sw][(pos + lane) & (RING - 1u)];
-                        float4 eb = on_b ? S.ring[sw][(pos + 32u + lane) & (RING - 1u)] : ea;
-                        PairRec ra, rb;
-                        ndt_pair_load(G.gauss + (size_t)__float_as_uint(ea.w) * GAUSS_STRIDE, ra);
-                        ndt_pair_load(G.gauss + (size_t)__float_as_uint(eb.w) * GAUSS_STRIDE, rb);
-                        ndt_pair_math(true, ea.x, ea.y, ea.z, ra, T, ang, K.d1, K.d2, hess, acc);
-                        ndt_pair_math(on_b, eb.x, eb.y, eb.z, rb, T, ang, K.d1, K.d2, hess, acc);
-                    }
-                }
-#else
-                if ((uint32_t)lane < n) {
                     const float4 e = S.ring[sw][(pos + lane) & (RING - 1u)];
                     PairRec r;
                     ndt_pair_load(G.gauss + (size_t)__float_as_uint(e.w) * GAUSS_STRIDE, r);
                     ndt_pair_math(true, e.x, e.y, e.z, r, T, ang, K.d1, K.d2, hess, acc);
                 }
-#endif
-                pos += n;
+                pos += 32u;
 #pragma unroll
                 for (int kk = 0; kk < NDT_PPC; ++kk) if (kk == k) ds.cpos[kk] = pos;
                 __syncwarp();
-                if (lane == 0 && n) st_vol(&S.head[sw], pos);
-                if (final_chunk) done_mask |= (1u << k);
+                if (lane == 0) st_vol(&S.head[sw], pos);
+            }
+            // the partial chunks, concatenated in producer order, 32 pairs per step
+            uint32_t total_left = 0;
+#pragma unroll
+            for (int kk = 0; kk < NDT_PPC; ++kk) total_left += left[kk];
+            for (uint32_t g0 = 0; g0 < total_left; g0 += 32u) {
+                const uint32_t g = g0 + (uint32_t)lane;
+                if (g < total_left) {
+                    uint32_t base = 0, idx = 0;
+                    int sw = warp;
+#pragma unroll
+                    for (int kk = 0; kk < NDT_PPC; ++kk) {
+                        if (g >= base && g < base + left[kk]) { sw = warp + kk * NDT_NCW; idx = ds.cpos[kk] + (g - base); }
+                        base += left[kk];
+                    }
+                    const float4 e = S.ring[sw][idx & (RING - 1u)];
+                    PairRec r;
+                    ndt_pair_load(G.gauss + (size_t)__float_as_uint(e.w) * GAUSS_STRIDE, r);
+                    ndt_pair_math(true, e.x, e.y, e.z, r, T, ang, K.d1, K.d2, hess, acc);
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int kk = 0; kk < NDT_PPC; ++kk) {
+                if (left[kk]) {
+                    ds.cpos[kk] += left[kk];
+                    if (lane == 0) st_vol(&S.head[warp + kk * NDT_NCW], ds.cpos[kk]);
+                }
             }
     }
     // warp butterfly (fixed order) -> one partial per compute warp
