@@ -559,7 +559,6 @@ constexpr int NDT_PPC = NDT_NSW / NDT_NCW;     // producers (search warps) per c
 #ifndef NDT_DRAIN_SLEEP
 #define NDT_DRAIN_SLEEP 32
 #endif
-
 constexpr uint32_t RING = NDT_RING;            // ring entries per search warp (power of two, >= 128 + 32)
 static_assert(NDT_NCW % 4 == 0 && NDT_NSW % 4 == 0 && NDT_NSW % NDT_NCW == 0, "warp-group multiples");
 
@@ -844,17 +843,27 @@ __device__ __forceinline__ void finish_request_warp(Slot &S, int lane) {
 // One warp runs the controller of a slot on the reduced sums S.raw_total: contraction with the angle tables,
 // serial halves on lane 0, the 6x6 Newton solve on the whole warp, then the next pass request.  Returns 1
 // when another pass was requested (S.ctl.T / ang / hess describe it), 0 when the match is finished.
-__device__ __forceinline__ int controller_step(Slot &S, const NdtConst &K, int deriv_only, int lane) {
+#ifdef NDT_TIMING
+#define CTL_LAP(k) do { if (ctl_trace && lane == 0) ctl_trace[k] = (unsigned long long)clock64(); } while (0)
+#else
+#define CTL_LAP(k) do { } while (0)
+#endif
+__device__ __forceinline__ int controller_step(Slot &S, const NdtConst &K, int deriv_only, int lane, unsigned long long *ctl_trace = nullptr) {
+    (void)ctl_trace;
+    CTL_LAP(0);
     if (lane < ACC_N) S.total[lane] = acc_finish(S.raw_total, S.ctl.ang, lane);
     __syncwarp();
+    CTL_LAP(1);
     int code = CTL_DONE;
     if (!deriv_only) {
         if (lane == 0) code = ctl_pre(S.ctl, K, S.total);
         code = __shfl_sync(0xffffffffu, code, 0);
+        CTL_LAP(2);
         for (int guard = 0; guard < 8 && code == CTL_NEWTON; ++guard) {
             __syncwarp();
             double delta[6];
             const double rc = warp_lu_solve6(S.ctl.H, S.ctl.g, lane, delta);
+            CTL_LAP(3);
             if (lane == 0) {
                 bool fin = true;
 #pragma unroll
@@ -868,12 +877,14 @@ __device__ __forceinline__ int controller_step(Slot &S, const NdtConst &K, int d
                 code = ctl_post_newton(S.ctl, K, delta);
             }
             code = __shfl_sync(0xffffffffu, code, 0);
+            CTL_LAP(4);
         }
         if (code == CTL_NEWTON) { code = CTL_DONE; if (lane == 0) S.ctl.state = ST_DONE; }
     }
     const int go = (code == CTL_PASS) ? 1 : 0;
     __syncwarp();
     if (go) finish_request_warp(S, lane);
+    CTL_LAP(5);
     return go;
 }
 
@@ -1154,9 +1165,6 @@ __device__ __forceinline__ bool compute_drain(NdtSmem &S, const GridView &G, con
     for (int i = 0; i < NACC; ++i) acc[i] = 0.0;
     {
             uint32_t done_mask = 0;                         // bit k: producer k exhausted for this pass
-            uint32_t left[NDT_PPC];                         // pairs of producer k's last, partial chunk (folded together below)
-#pragma unroll
-            for (int kk = 0; kk < NDT_PPC; ++kk) left[kk] = 0u;
             int turn = 0;
             while (done_mask != (1u << NDT_PPC) - 1u) {
                 // fixed round-robin over this warp's producers (deterministic accumulation order)
@@ -1195,53 +1203,18 @@ __device__ __forceinline__ bool compute_drain(NdtSmem &S, const GridView &G, con
                 n &= 0x3fffffffu;
                 __threadfence_block();
                 if (!have_desc) { hess = ctl.hess != 0; have_desc = true; }
-                if (final_chunk) {
-                    // the last, partial chunk of a producer waits for those of the other producers: together they
-                    // fill fewer 32-pair steps (what is left is a property of the pass, not of the timing)
-#pragma unroll
-                    for (int kk = 0; kk < NDT_PPC; ++kk) if (kk == k) left[kk] = n;
-                    done_mask |= (1u << k);
-                    continue;
-                }
-                {
+                if ((uint32_t)lane < n) {
                     const float4 e = S.ring[sw][(pos + lane) & (RING - 1u)];
                     PairRec r;
                     ndt_pair_load(G.gauss + (size_t)__float_as_uint(e.w) * GAUSS_STRIDE, r);
                     ndt_pair_math(true, e.x, e.y, e.z, r, T, ang, K.d1, K.d2, hess, acc);
                 }
-                pos += 32u;
+                pos += n;
 #pragma unroll
                 for (int kk = 0; kk < NDT_PPC; ++kk) if (kk == k) ds.cpos[kk] = pos;
                 __syncwarp();
-                if (lane == 0) st_vol(&S.head[sw], pos);
-            }
-            // the partial chunks, concatenated in producer order, 32 pairs per step
-            uint32_t total_left = 0;
-#pragma unroll
-            for (int kk = 0; kk < NDT_PPC; ++kk) total_left += left[kk];
-            for (uint32_t g0 = 0; g0 < total_left; g0 += 32u) {
-                const uint32_t g = g0 + (uint32_t)lane;
-                if (g < total_left) {
-                    uint32_t base = 0, idx = 0;
-                    int sw = warp;
-#pragma unroll
-                    for (int kk = 0; kk < NDT_PPC; ++kk) {
-                        if (g >= base && g < base + left[kk]) { sw = warp + kk * NDT_NCW; idx = ds.cpos[kk] + (g - base); }
-                        base += left[kk];
-                    }
-                    const float4 e = S.ring[sw][idx & (RING - 1u)];
-                    PairRec r;
-                    ndt_pair_load(G.gauss + (size_t)__float_as_uint(e.w) * GAUSS_STRIDE, r);
-                    ndt_pair_math(true, e.x, e.y, e.z, r, T, ang, K.d1, K.d2, hess, acc);
-                }
-            }
-            __syncwarp();
-#pragma unroll
-            for (int kk = 0; kk < NDT_PPC; ++kk) {
-                if (left[kk]) {
-                    ds.cpos[kk] += left[kk];
-                    if (lane == 0) st_vol(&S.head[warp + kk * NDT_NCW], ds.cpos[kk]);
-                }
+                if (lane == 0 && n) st_vol(&S.head[sw], pos);
+                if (final_chunk) done_mask |= (1u << k);
             }
     }
     // warp butterfly (fixed order) -> one partial per compute warp
@@ -1376,7 +1349,11 @@ __global__ void __launch_bounds__(NDT_THREADS, NDT_MIN_CTAS) ndt_match_kernel(Gr
             TRC(5);
             // ---------------- controller: Newton step + More-Thuente state machine (warp 0) ----------------
             if (warp == 0) {
+#ifdef NDT_TIMING
+                const int go = controller_step(SL, K, A.deriv_only, lane, (A.timing && crank == 0 && match == 0 && trc_pass == 2) ? A.timing + 320 : nullptr);
+#else
                 const int go = controller_step(SL, K, A.deriv_only, lane);
+#endif
                 if (lane == 0) SL.go = go;
             }
             cta_barrier();                              // (3)
@@ -2267,6 +2244,8 @@ static int launch_match(b2ndt *h, const MatchArgs &A, size_t B, int C) {
             // pass 2, per CTA: search start (sw 0), then per warp: 4 x compute drained, 8 x search finished (ns after the earliest search start)
             unsigned long long s0 = ~0ull;
             for (int r = 0; r < C; ++r) if (t[128 + r * 16 + 12] && t[128 + r * 16 + 12] < s0) s0 = t[128 + r * 16 + 12];
+            fprintf(stderr, "[ndt controller] pass 2 cycles: contraction %llu, ctl_pre %llu, LU solve %llu, post-newton %llu, trig + tables %llu\n",
+                    t[321] - t[320], t[322] - t[321], t[323] - t[322], t[324] - t[323], t[325] - t[324]);
             for (int r = 0; r < C; ++r) {
                 fprintf(stderr, "[ndt warps] cta %2d start %5llu | drained", r, t[128 + r * 16 + 12] - s0);
                 for (int w = 0; w < NDT_NCW; ++w) fprintf(stderr, " %5llu", t[128 + r * 16 + w] - s0);
