@@ -96,8 +96,9 @@ void b2ndt_destroy(b2ndt *h);
 int  b2ndt_set_stream(b2ndt *h, void *cuda_stream);
 int  b2ndt_synchronize(b2ndt *h);
 /* thread-block cluster width per match.  single_match_ctas 1..16: upper bound for one ScanMatch (default 16; the
- * library picks by source size).  batch_ctas 0..16: 0 (default) = by batch size (1 = persistent batch kernel for
- * batches that fill the GPU, clusters of 2 / 4 / 8 CTAs per match for batches smaller than half a wave). */
+ * library picks by source size).  batch_ctas 0..16: 0 (default) = by batch size: 1 = the persistent batch kernel (two
+ * matches in flight per CTA) from ~800 matches on, clusters of 2 / 4 / 8 CTAs per match for smaller batches (a shard of
+ * config 4 / 5 on 8 GPUs), as wide as keeps the launch within about two waves of CTAs. */
 int  b2ndt_set_cluster(b2ndt *h, int single_match_ctas, int batch_ctas);
 
 int  b2ndt_set_target(b2ndt *h, const void *pts, size_t n, size_t stride, size_t ioff);

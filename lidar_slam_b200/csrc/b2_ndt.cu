@@ -737,14 +737,15 @@ __device__ __forceinline__ void ndt_pair_math(const bool on, const float px, con
 // [0] score, [1..6] gradient, [7..27] Hessian upper triangle row-major, [28] pairs.  Lane o (< ACC_N) of one
 // warp computes output o = t[base] + sum_k P[row_k] . table[vec_k]; AngTab is 23 consecutive 3-vectors
 // (j_ang_a..h then h_ang_a2..f3).
-__constant__ signed char ACCF_BASE[ACC_N] = {0, 1, 2, 3, -1, -1, -1,
+// (global memory, not __constant__: lane o reads entry o, and constant memory serialises a warp's distinct addresses)
+__device__ const signed char ACCF_BASE[ACC_N] = {0, 1, 2, 3, -1, -1, -1,
                                              13, 14, 15, 19, 20, 21, 16, 17, 22, 23, 24, 18, 25, 26, 27, 28, 29, 30, 31, 32, 33, 34};
-__constant__ signed char ACCF_ROW[ACC_N][3] = {
+__device__ const signed char ACCF_ROW[ACC_N][3] = {
     {-1, -1, -1}, {-1, -1, -1}, {-1, -1, -1}, {-1, -1, -1}, {1, 2, -1}, {0, 1, 2}, {0, 1, 2},
     {-1, -1, -1}, {-1, -1, -1}, {-1, -1, -1}, {-1, -1, -1}, {-1, -1, -1}, {-1, -1, -1}, {-1, -1, -1}, {-1, -1, -1},
     {-1, -1, -1}, {-1, -1, -1}, {-1, -1, -1}, {-1, -1, -1}, {-1, -1, -1}, {-1, -1, -1}, {-1, -1, -1},
     {1, 2, -1}, {1, 2, -1}, {1, 2, -1}, {0, 1, 2}, {0, 1, 2}, {0, 1, 2}, {-1, -1, -1}};
-__constant__ signed char ACCF_VEC[ACC_N][3] = {
+__device__ const signed char ACCF_VEC[ACC_N][3] = {
     {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 1, 0}, {2, 3, 4}, {5, 6, 7},
     {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0},
     {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0},
@@ -809,13 +810,16 @@ __device__ __noinline__ double warp_lu_solve6(const double *__restrict__ H, cons
             for (int c = k + 1; c < 7; ++c) a[c] -= f * pr[c];
         }
     }
+    // reciprocal of this lane's pivot: the six divisions run side by side (lu_solve6 multiplies by the same reciprocals)
+    const double diag = (r == 0) ? a[0] : (r == 1) ? a[1] : (r == 2) ? a[2] : (r == 3) ? a[3] : (r == 4) ? a[4] : a[5];
+    const double rinv = 1.0 / diag;
     double xs[6];
 #pragma unroll
     for (int rr = 5; rr >= 0; --rr) {
         double sacc = a[6];
 #pragma unroll
         for (int c = rr + 1; c < 6; ++c) sacc -= a[c] * xs[c];
-        xs[rr] = shfl_d(sacc / a[rr], rr);
+        xs[rr] = shfl_d(sacc * rinv, rr);
     }
 #pragma unroll
     for (int i = 0; i < 6; ++i) x[i] = xs[i];
@@ -835,7 +839,10 @@ __device__ __forceinline__ void finish_request_warp(Slot &S, int lane) {
             else S.trig_d[3 + k] = ang_cos(a);
         }
         __syncwarp();
-        if (lane == 0) ctl_finish_request(S.ctl, &S.trig_f[0], &S.trig_f[3], &S.trig_d[0], &S.trig_d[3]);
+        // pose matrix + angle tables: three lanes, a third of the tables each
+        if (lane < 3) ctl_finish_request(S.ctl, &S.trig_f[0], &S.trig_f[3], &S.trig_d[0], &S.trig_d[3], lane);
+        __syncwarp();
+        if (lane == 0) S.ctl.need_trig = 0;
     }
     __syncwarp();
 }
@@ -864,17 +871,27 @@ __device__ __forceinline__ int controller_step(Slot &S, const NdtConst &K, int d
             double delta[6];
             const double rc = warp_lu_solve6(S.ctl.H, S.ctl.g, lane, delta);
             CTL_LAP(3);
+            {
+                // the normalised direction delta / |delta| (ctl_post_newton): six divisions on six lanes.  Written before
+                // lane 0 decides whether the LU result stands; the SVD fallback recomputes it serially.
+                const double nrm = ctl_delta_norm(delta);
+                const double dl = (lane == 0) ? delta[0] : (lane == 1) ? delta[1] : (lane == 2) ? delta[2] : (lane == 3) ? delta[3] : (lane == 4) ? delta[4] : delta[5];
+                if (lane < 6) S.ctl.dir[lane] = dl / nrm;
+                __syncwarp();
+            }
             if (lane == 0) {
                 bool fin = true;
 #pragma unroll
                 for (int i = 0; i < 6; ++i) fin = fin && (delta[i] == delta[i]) && (fabs(delta[i]) <= DBL_MAX);
+                bool have_dir = true;
                 if (K.force_svd || !(rc > 1e-9 && fin)) {
                     // (near-)singular Hessian: Eigen's JacobiSVD solve with its rank truncation
                     double neg_g[6];
                     for (int i = 0; i < 6; ++i) neg_g[i] = -S.ctl.g[i];
                     svd_solve6(S.ctl.H, neg_g, delta);
+                    have_dir = false;
                 }
-                code = ctl_post_newton(S.ctl, K, delta);
+                code = ctl_post_newton(S.ctl, K, delta, have_dir);
             }
             code = __shfl_sync(0xffffffffu, code, 0);
             CTL_LAP(4);
@@ -2164,13 +2181,18 @@ static int launch_match(b2ndt *h, const MatchArgs &A, size_t B, int C) {
         h->batch_attrs_set = true;
     }
     if (C == 0) {
-        // CTAs per match chosen by batch size: a batch with fewer matches than half the resident CTAs (a shard of a
-        // relocalisation batch: 1024 hypotheses over 8 GPUs = 128 each) would leave SMs idle with one CTA per
-        // match, so each match gets a cluster of 2 / 4 / 8 CTAs (as many as keep the launch within one wave)
+        // CTAs per match chosen by batch size.  The persistent kernel keeps 2 matches per CTA in flight, i.e. it needs
+        // ~600 matches to fill the GPU and its time is then the latency of two interleaved single-CTA matches; smaller
+        // batches (a shard of config 4 or 5 on 8 GPUs: 500 frames / 128 hypotheses) finish sooner when every match is
+        // spread over a cluster of 2 / 4 / 8 CTAs, even if the launch then takes up to ~2 waves of CTAs (measured,
+        // tools/sweep_small_batches.sh: 500 matches 2.75 -> 2.18 ms with 2 CTAs, 128 matches 1.31 -> 1.10 ms with 4;
+        // from ~1000 matches on the persistent kernel wins).
         C = 1;
-        if (!A.deriv_only && B >= 1 && h->small_batch_clusters && B * 2 <= (size_t)h->batch_ctas) {
-            const size_t c = (size_t)h->batch_ctas / B;
-            C = c >= 8 ? 8 : c >= 4 ? 4 : 2;
+        if (!A.deriv_only && B >= 1 && h->small_batch_clusters) {
+            const size_t two_waves = 2u * (size_t)h->batch_ctas;
+            if (B * 8 <= two_waves) C = 8;
+            else if (B * 4 <= two_waves) C = 4;
+            else if (B <= 800) C = 2;
         }
     }
     if (C == 1 && !A.deriv_only && B >= 2 && h->use_batch_kernel) {

@@ -253,13 +253,16 @@ struct AngTab {
 // snapped trig of NDTM:527-549: |angle| < 10e-5 -> (cos, sin) = (1, 0)
 B2_HD double ang_sin(double a) { return (fabs(a) < 10e-5) ? 0.0 : b2_sin(a); }
 B2_HD double ang_cos(double a) { return (fabs(a) < 10e-5) ? 1.0 : b2_cos(a); }
-B2_HD_NOINLINE inline void angle_derivatives_sc(double sx, double cx, double sy, double cy, double sz, double cz, AngTab &A);
+// parts: bit 0 = j_ang_a..h, bit 1 = h_ang_a2..d2, bit 2 = h_ang_d3..f3 (every entry is an expression of its own, so
+// three lanes of the controller warp can each write a part)
+B2_HD_NOINLINE inline void angle_derivatives_sc(double sx, double cx, double sy, double cy, double sz, double cz, AngTab &A, int parts = 7);
 B2_HD_NOINLINE inline void angle_derivatives(const double p[6], AngTab &A) {
     angle_derivatives_sc(ang_sin(p[3]), ang_cos(p[3]), ang_sin(p[4]), ang_cos(p[4]), ang_sin(p[5]), ang_cos(p[5]), A);
 }
-B2_HD_NOINLINE inline void angle_derivatives_sc(double sx, double cx, double sy, double cy, double sz, double cz, AngTab &A) {
+B2_HD_NOINLINE inline void angle_derivatives_sc(double sx, double cx, double sy, double cy, double sz, double cz, AngTab &A, int parts) {
     double (*j)[3] = A.j;
     double (*h)[3] = A.h;
+    if (parts & 1) {
     j[0][0] = -sx * sz + cx * sy * cz; j[0][1] = -sx * cz - cx * sy * sz; j[0][2] = -cx * cy;
     j[1][0] = cx * sz + sx * sy * cz;  j[1][1] = cx * cz - sx * sy * sz;  j[1][2] = -sx * cy;
     j[2][0] = -sy * cz;                j[2][1] = sy * sz;                 j[2][2] = cy;
@@ -268,6 +271,8 @@ B2_HD_NOINLINE inline void angle_derivatives_sc(double sx, double cx, double sy,
     j[5][0] = -cy * sz;                j[5][1] = -cy * cz;                j[5][2] = 0;
     j[6][0] = cx * cz - sx * sy * sz;  j[6][1] = -cx * sz - sx * sy * cz; j[6][2] = 0;
     j[7][0] = sx * cz + cx * sy * sz;  j[7][1] = cx * sy * cz - sx * sz;  j[7][2] = 0;
+    }
+    if (parts & 2) {
     h[0][0] = -cx * sz - sx * sy * cz; h[0][1] = -cx * cz + sx * sy * sz; h[0][2] = sx * cy;
     h[1][0] = -sx * sz + cx * sy * cz; h[1][1] = -cx * sy * sz - sx * cz; h[1][2] = -cx * cy;
     h[2][0] = cx * cy * cz;            h[2][1] = -cx * cy * sz;           h[2][2] = cx * sy;
@@ -276,6 +281,8 @@ B2_HD_NOINLINE inline void angle_derivatives_sc(double sx, double cx, double sy,
     h[5][0] = cx * cz - sx * sy * sz;  h[5][1] = -sx * sy * cz - cx * sz; h[5][2] = 0;
     h[6][0] = -cy * cz;                h[6][1] = cy * sz;                 h[6][2] = sy;
     h[7][0] = -sx * sy * cz;           h[7][1] = sx * sy * sz;            h[7][2] = sx * cy;
+    }
+    if (parts & 4) {
     h[8][0] = cx * sy * cz;            h[8][1] = -cx * sy * sz;           h[8][2] = -cx * cy;
     h[9][0] = sy * sz;                 h[9][1] = sy * cz;                 h[9][2] = 0;
     h[10][0] = -sx * cy * sz;          h[10][1] = -sx * cy * cz;          h[10][2] = 0;
@@ -283,6 +290,7 @@ B2_HD_NOINLINE inline void angle_derivatives_sc(double sx, double cx, double sy,
     h[12][0] = -cy * cz;               h[12][1] = cy * sz;                h[12][2] = 0;
     h[13][0] = -cx * sz - sx * sy * cz;h[13][1] = -cx * cz + sx * sy * sz;h[13][2] = 0;
     h[14][0] = -sx * sz + cx * sy * cz;h[14][1] = -cx * sy * sz - sx * cz;h[14][2] = 0;
+    }
 }
 
 // ------------------------------------------------------------------ 3x3 double numerics -------
@@ -532,13 +540,18 @@ B2_HD_NOINLINE inline double lu_solve6(const double Hin[36], const double b[6], 
             for (int c = k + 1; c <= N; ++c) A[r][c] -= f * A[k][c];
         }
     }
+    // back substitution with the reciprocals of the pivots (the warp version computes the six of them side by side:
+    // one division latency instead of six in the dependent chain)
+    double rinv[N];
+#pragma unroll
+    for (int r = 0; r < N; ++r) rinv[r] = 1.0 / A[r][r];
     double xs[N];
 #pragma unroll
     for (int r = N - 1; r >= 0; --r) {
         double s = A[r][N];
 #pragma unroll
         for (int c = r + 1; c < N; ++c) s -= A[r][c] * xs[c];
-        xs[r] = s / A[r][r];
+        xs[r] = s * rinv[r];
     }
 #pragma unroll
     for (int r = 0; r < N; ++r) x[r] = xs[r];
@@ -667,13 +680,15 @@ B2_HD void ctl_trig_serial(const Ctl &c, float fs[3], float fc[3], double ds[3],
         ds[k] = ang_sin(c.x_req[3 + k]); dc[k] = ang_cos(c.x_req[3 + k]);
     }
 }
-B2_HD_NOINLINE inline void ctl_finish_request(Ctl &c, const float fs[3], const float fc[3], const double ds[3], const double dc[3]) {
-    if (c.need_trig == 1) {
+// who = -1: everything (serial); who = 0 / 1 / 2: the share of lane `who` of the controller warp (lane 0: pose matrix +
+// first part of the angle tables, lanes 1 and 2: the other two parts); the caller clears need_trig afterwards
+B2_HD_NOINLINE inline void ctl_finish_request(Ctl &c, const float fs[3], const float fc[3], const double ds[3], const double dc[3], int who = -1) {
+    if (c.need_trig == 1 && who <= 0) {
         pose_to_matrix_sc_f32(c.x_req, fs, fc, c.T);
         for (int i = 0; i < 16; ++i) c.finalT[i] = c.T[i];
     }
-    angle_derivatives_sc(ds[0], dc[0], ds[1], dc[1], ds[2], dc[2], c.ang);
-    c.need_trig = 0;
+    angle_derivatives_sc(ds[0], dc[0], ds[1], dc[1], ds[2], dc[2], c.ang, who < 0 ? 7 : (1 << who));
+    if (who < 0) c.need_trig = 0;
 }
 B2_HD void ctl_finish_request_serial(Ctl &c) {
     if (!c.need_trig) return;
@@ -793,18 +808,24 @@ B2_HD_NOINLINE inline int ctl_pre(Ctl &c, const NdtConst &k, const double *acc) 
 }
 
 // NDTM:353-365 after the solve, then the computeStepLengthMT prologue NDTM:656-698
-B2_HD_NOINLINE inline int ctl_post_newton(Ctl &c, const NdtConst &k, const double delta[6]) {
-    const double mu = 1.e-4;
+// |delta| as ctl_post_newton forms it (the controller warp evaluates it on every lane and divides on six of them)
+B2_HD double ctl_delta_norm(const double delta[6]) {
     double n2 = 0.0;
     for (int i = 0; i < 6; ++i) n2 += delta[i] * delta[i];
-    double nrm = sqrt(n2);
+    return sqrt(n2);
+}
+// have_dir: c.dir already holds delta / |delta| (written by six lanes of the controller warp)
+B2_HD_NOINLINE inline int ctl_post_newton(Ctl &c, const NdtConst &k, const double delta[6], bool have_dir = false) {
+    const double mu = 1.e-4;
+    double nrm = ctl_delta_norm(delta);
     if (nrm == 0 || nrm != nrm) {
         c.trans_probability = c.score / c.npoints;
         c.converged = (nrm == nrm) ? 1 : 0;
         c.state = ST_DONE;
         return CTL_DONE;
     }
-    for (int i = 0; i < 6; ++i) c.dir[i] = delta[i] / nrm;
+    if (!have_dir)
+        for (int i = 0; i < 6; ++i) c.dir[i] = delta[i] / nrm;
     c.phi_0 = -c.score;
     double d = 0.0;
     for (int i = 0; i < 6; ++i) d += c.g[i] * c.dir[i];
