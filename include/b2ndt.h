@@ -122,6 +122,12 @@ int  b2ndt_target_leaves(b2ndt *h, int32_t *idx, int32_t *n_raw, float *centroid
 
 int  b2ndt_align(b2ndt *h, const void *src, size_t n, size_t stride, size_t ioff, const float guess[16],
                  float pose_out[16], b2ndt_result *res);
+/* b2ndt_align + ScanMatch's result cloud (registration_interface.hpp:19-22; Registration::align(output)): the source
+ * transformed by the final pose with pcl::transformPointCloud's float arithmetic, computed on the device (the source is
+ * resident there) and written to result_cloud: n records of out_stride bytes, intensity at out_ioff (PointXYZI: 32 / 16,
+ * data[3] = 1).  result_cloud may be NULL (= b2ndt_align) or the source buffer. */
+int  b2ndt_align_ex(b2ndt *h, const void *src, size_t n, size_t stride, size_t ioff, const float guess[16],
+                    float pose_out[16], b2ndt_result *res, void *result_cloud, size_t out_stride, size_t out_ioff);
 /* B independent matches against the current target.  Sources are concatenated; offsets has B+1
  * entries (points).  offsets == NULL: one shared source of n_total points x B guesses. */
 int  b2ndt_align_batch(b2ndt *h, const void *src, size_t n_total, size_t stride, size_t ioff,

@@ -20,7 +20,7 @@ EXPORTS = [
     "b2ndt_params_default", "b2ndt_create", "b2ndt_destroy", "b2ndt_set_stream", "b2ndt_synchronize",
     "b2ndt_set_cluster", "b2ndt_set_target", "b2ndt_set_target_device", "b2ndt_target_info_get",
     "b2ndt_update_target", "b2ndt_update_target_device", "b2ndt_update_target_cloud",
-    "b2ndt_target_leaves", "b2ndt_align", "b2ndt_align_batch", "b2ndt_align_batch_device",
+    "b2ndt_target_leaves", "b2ndt_align", "b2ndt_align_ex", "b2ndt_align_batch", "b2ndt_align_batch_device",
     "b2ndt_derivatives", "b2ndt_fitness", "b2ndt_fitness_ex",
     "b2vf_create", "b2vf_destroy", "b2vf_set_stream", "b2vf_filter", "b2vf_filter_batch_device", "b2vf_filter_batch_append_device",
     "b2cloud_create", "b2cloud_destroy", "b2cloud_upload", "b2cloud_download", "b2cloud_size", "b2cloud_clear",
@@ -95,6 +95,7 @@ def lib():
     L.b2ndt_target_info_get.argtypes = [vp, C.POINTER(TargetInfo)]
     L.b2ndt_target_leaves.argtypes = [vp, i32p, i32p, fp, dp, dp]
     L.b2ndt_align.argtypes = [vp, vp, sz, sz, sz, fp, fp, C.POINTER(Result)]
+    L.b2ndt_align_ex.argtypes = [vp, vp, sz, sz, sz, fp, fp, C.POINTER(Result), vp, sz, sz]
     L.b2ndt_align_batch.argtypes = [vp, vp, sz, sz, sz, u32p, sz, fp, fp, vp]
     L.b2ndt_align_batch_device.argtypes = [vp, vp, sz, vp, sz, vp, vp, vp]
     L.b2ndt_derivatives.argtypes = [vp, vp, sz, sz, sz, dp, dp, dp, dp, C.POINTER(C.c_int64)]

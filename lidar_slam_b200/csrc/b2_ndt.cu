@@ -2445,6 +2445,47 @@ extern "C" int b2ndt_align(b2ndt *h, const void *src, size_t n, size_t stride, s
     return 0;
 }
 
+// pcl::transformPointCloud (float, left to right): the align(output) cloud of Registration::align
+__global__ void __launch_bounds__(256) transform_cloud_kernel(const float4 *__restrict__ src, uint32_t n, PoseArg P, float4 *__restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = __ldg(&src[i]);
+    float x, y, z;
+    transform_f32(P.T, p.x, p.y, p.z, x, y, z);
+    out[i] = make_float4(x, y, z, p.w);
+}
+
+// b2ndt_align + the result cloud of ScanMatch (registration_interface.hpp:19-22: result_cloud_ptr = the source moved by
+// the final pose) filled from the device: the source is already resident, so the transform costs a kernel and a D2H
+// instead of a host loop over the points (matters for unfiltered scans).  result_cloud: n records of out_stride bytes
+// (PointXYZI: 32 / intensity at 16; data[3] = 1, padding zeroed), may be the source buffer itself.
+extern "C" int b2ndt_align_ex(b2ndt *h, const void *src, size_t n, size_t stride, size_t ioff, const float guess[16], float pose_out[16],
+                              b2ndt_result *res, void *result_cloud, size_t out_stride, size_t out_ioff) {
+    int rc = b2ndt_align(h, src, n, stride, ioff, guess, pose_out, res);
+    if (rc || !result_cloud || n == 0) return rc;
+    if (out_stride < 16 || (out_stride & 3) || out_ioff + 4 > out_stride || (out_ioff & 3)) { set_error("b2ndt_align_ex: bad output stride / intensity offset"); return B2_ERR_INVALID; }
+    if ((rc = h->d_acc.reserve(n * 16 + 16))) return rc;
+    if ((rc = h->h_stage.reserve(n * 16 + 16))) return rc;
+    PoseArg P;
+    memcpy(P.T, pose_out, 64);
+    transform_cloud_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->st>>>(h->d_src.as<float4>(), (uint32_t)n, P, h->d_acc.as<float4>());
+    B2_LAUNCH_CHECK();
+    B2_CUDA(cudaMemcpyAsync(h->h_stage.p, h->d_acc.p, n * 16, cudaMemcpyDeviceToHost, h->st));
+    B2_CUDA(cudaStreamSynchronize(h->st));
+    const float *r = h->h_stage.as<float>();
+    char *o = (char *)result_cloud;
+    if (out_stride == 16 && out_ioff == 12) { memcpy(o, r, n * 16); return 0; }
+    for (size_t i = 0; i < n; ++i) {
+        float *q = (float *)(o + i * out_stride);
+        const float x = r[4 * i], y = r[4 * i + 1], z = r[4 * i + 2], w = r[4 * i + 3];
+        if (out_stride >= 32) memset(q, 0, out_stride);
+        q[0] = x; q[1] = y; q[2] = z;
+        if (out_stride >= 32 || out_ioff != 12) q[3] = 1.0f;
+        *(float *)(o + i * out_stride + out_ioff) = w;
+    }
+    return 0;
+}
+
 extern "C" int b2ndt_align_batch(b2ndt *h, const void *src, size_t n_total, size_t stride, size_t ioff, const uint32_t *offsets,
                                  size_t B, const float *guesses, float *poses_out, b2ndt_result *res) {
     if (!h || !guesses || !poses_out) { set_error("b2ndt_align_batch: NULL argument"); return B2_ERR_INVALID; }

@@ -68,8 +68,20 @@ bool NDTRegistration::ScanMatch(const CloudData::CLOUD_PTR& input_source, const 
     const std::size_t n = input_source->points.size();
     float pose[16];
     std::memcpy(pose, predict_pose.data(), sizeof(pose));
-    const bool ok = ndt_ && b2ndt_align(ndt_, input_source->points.data(), n, kStride, kIntensityOffset, predict_pose.data(), pose,
-                                        &last_) == B2_OK;
+    // a large (unfiltered) source: let the library fill the result cloud from the device copy of the source
+    const bool device_fill = result_cloud_ptr && n >= 16384;
+    if (device_fill && result_cloud_ptr.get() != input_source.get()) {
+        result_cloud_ptr->points.resize(n);
+        result_cloud_ptr->width = input_source->width; result_cloud_ptr->height = input_source->height; result_cloud_ptr->is_dense = input_source->is_dense;
+    }
+    const bool ok = ndt_ && (device_fill
+        ? b2ndt_align_ex(ndt_, input_source->points.data(), n, kStride, kIntensityOffset, predict_pose.data(), pose, &last_,
+                         result_cloud_ptr->points.data(), kStride, kIntensityOffset)
+        : b2ndt_align(ndt_, input_source->points.data(), n, kStride, kIntensityOffset, predict_pose.data(), pose, &last_)) == B2_OK;
+    if (ok && device_fill) {
+        std::memcpy(result_pose.data(), pose, sizeof(pose));
+        return true;
+    }
     if (!ok) {
         // engine failure: the outputs are still defined (pose = prediction, cloud = source moved by it) and the call
         // reports false -- the reference's `return true` (ndt_registration.cpp:60) holds for PCL, which cannot fail

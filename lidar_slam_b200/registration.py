@@ -179,12 +179,20 @@ class NDTRegistration(RegistrationInterface):
         g = capi.pose_to_colmajor(predict_pose)
         out = np.zeros(16, np.float32)
         res = capi.Result()
-        capi.check(capi.lib().b2ndt_align(self._h, ptr, n, stride, ioff, capi._fp(g), capi._fp(out), C.byref(res)))
+        cloud = None
+        if want_cloud == "device":
+            # result cloud filled by the library from the device-resident source (b2ndt_align_ex), packed x y z intensity
+            cloud = np.zeros((n, 4), np.float32)
+            capi.check(capi.lib().b2ndt_align_ex(self._h, ptr, n, stride, ioff, capi._fp(g), capi._fp(out), C.byref(res),
+                                                 cloud.ctypes.data_as(C.c_void_p), 16, 12))
+        else:
+            capi.check(capi.lib().b2ndt_align(self._h, ptr, n, stride, ioff, capi._fp(g), capi._fp(out), C.byref(res)))
         pose = capi.colmajor_to_pose(out)
         self.last_result = dict(iterations=res.iterations, converged=bool(res.converged), score=res.score,
                                 trans_probability=res.trans_probability, p=np.array(res.p[:]), passes=res.passes,
                                 mt_trials=res.mt_trials, pairs=res.pairs)
-        cloud = transform_cloud(a, pose) if want_cloud else None
+        if want_cloud is True:
+            cloud = transform_cloud(a, pose)
         return True, cloud, pose
 
     def GetFitnessScore(self, max_range=DBL_MAX):

@@ -2,13 +2,14 @@
 Tolerances (north_star): voxel assignment + counts bit-exact; pose <= 1e-3 m / 1e-4 rad; fitness <= 1e-4
 relative.  Tighter internal gates: per-pass score / gradient / Hessian <= 1e-9 relative at the same
 pose, identical iteration counts."""
+import ctypes as C
 import os
 import subprocess
 
 import numpy as np
 import pytest
 
-from lidar_slam_b200 import build, synth
+from lidar_slam_b200 import build, capi, synth
 from lidar_slam_b200.registration import NDTRegistration, VoxelFilter, to_xyzi8
 from tests.conftest import f32
 
@@ -232,6 +233,28 @@ def test_align_matches_oracle(oracle, setup, scans, small_map):
     ok, cloud, pose = reg.ScanMatch(to_xyzi8(src), ident)
     assert reg.last_result["iterations"] == ref["iterations"]
     _pose_close(reg.last_result["p"], pose, ref)
+
+
+def test_result_cloud_filled_on_device_equals_host_transform(setup, scans):
+    """b2ndt_align_ex: the result cloud written from the device copy of the source == the source moved by the final pose
+    with pcl::transformPointCloud's float arithmetic (what the host loop of the drop-in class computes)."""
+    reg, grid, prm, srcs = setup
+    guess = synth.pose6_to_matrix(scans[0][0] + np.array([0.1, 0.1, 0.0, 0.0, 0.0, 0.01])).astype(np.float32)
+    ok, c_host, pose_h = reg.ScanMatch(srcs[0], guess)
+    ok, c_dev, pose_d = reg.ScanMatch(srcs[0], guess, want_cloud="device")
+    assert np.array_equal(pose_h, pose_d)
+    assert c_dev.shape == (len(srcs[0]), 4) and np.array_equal(c_dev[:, 3], srcs[0][:, 3])
+    assert np.array_equal(c_dev[:, :3], c_host[:, :3])
+    # PointXYZI records (32 bytes, intensity at +16, data[3] = 1), written over the source buffer itself
+    src8 = to_xyzi8(srcs[0])
+    buf = src8.copy()
+    out = np.zeros(16, np.float32)
+    res = capi.Result()
+    g = capi.pose_to_colmajor(guess)
+    capi.check(capi.lib().b2ndt_align_ex(reg._h, buf.ctypes.data_as(C.c_void_p), len(buf), 32, 16, capi._fp(g), capi._fp(out), C.byref(res),
+                                         buf.ctypes.data_as(C.c_void_p), 32, 16))
+    assert np.array_equal(buf[:, :3], c_host[:, :3]) and np.all(buf[:, 3] == 1.0) and np.array_equal(buf[:, 4], srcs[0][:, 3])
+    assert np.all(buf[:, 5:] == 0.0)
 
 
 def test_cluster_widths_agree(oracle, setup, scans):
