@@ -130,6 +130,45 @@ def test_incremental_update_equals_full_build(oracle, small_map, scans):
     assert _leaves_equal(reg.TargetLeaves(), want)
 
 
+def test_incremental_update_many_small_updates_grow_the_tables(small_map):
+    """A small first target followed by many updates: the leaf tables and the point store are re-allocated several times
+    (contents must survive), most updates open new leaves, and the result is still the full build bit for bit.  Also the
+    raw-device-pointer entry point (b2ndt_update_target_device) and an update made of non-finite points only."""
+    import torch
+    ext = np.unique(np.concatenate([np.argmin(small_map[:, :3], 0), np.argmax(small_map[:, :3], 0)]))
+    cloud = np.concatenate([small_map[ext], np.delete(small_map, ext, 0)])[:120_000]
+    first = 2_000
+    reg = NDTRegistration(1.0, 0.1, 0.01, 30)
+    reg.SetInputTarget(cloud[:first])
+    cuts = np.linspace(first, len(cloud), 15).astype(int)
+    for k, (a, b) in enumerate(zip(cuts[:-1], cuts[1:])):
+        if k % 3 == 2:
+            t = torch.from_numpy(np.ascontiguousarray(cloud[a:b])).cuda()
+            capi.check(capi.lib().b2ndt_update_target_device(reg._h, C.c_void_p(t.data_ptr()), b - a))
+            reg.Synchronize()
+        else:
+            reg.UpdateInputTarget(cloud[a:b])
+    nan_only = np.full((100, 4), np.nan, np.float32)
+    reg.UpdateInputTarget(nan_only)
+    info = reg.TargetInfo()
+    assert info["updates_incremental"] == 15 and info["updates_rebuilt"] == 0
+    ref = NDTRegistration(1.0, 0.1, 0.01, 30)
+    ref.SetInputTarget(np.concatenate([cloud, nan_only]))
+    assert info["n_points"] == ref.TargetInfo()["n_points"] == len(cloud)
+    assert _leaves_equal(reg.TargetLeaves(), ref.TargetLeaves())
+    src = cloud[::40].copy()
+    guess = synth.pose6_to_matrix(np.array([0.15, -0.1, 0.05, 0.0, 0.0, 0.01])).astype(np.float32)
+    _, _, p1 = reg.ScanMatch(src, guess)
+    r1 = dict(reg.last_result)
+    _, _, p2 = ref.ScanMatch(src, guess)
+    assert np.array_equal(p1, p2) and r1["score"] == ref.last_result["score"] and r1["pairs"] == ref.last_result["pairs"]
+    assert reg.GetFitnessScore() == ref.GetFitnessScore()
+    # a fresh SetInputTarget after updates starts over (counters reset, no stale leaves)
+    reg.SetInputTarget(cloud[:first])
+    ref.SetInputTarget(cloud[:first])
+    assert reg.TargetInfo()["updates_incremental"] == 0 and _leaves_equal(reg.TargetLeaves(), ref.TargetLeaves())
+
+
 def test_golden_fixture(oracle):
     G = np.load(GOLD)
     reg = NDTRegistration(1.0, 0.1, 0.01, 30)
