@@ -193,6 +193,9 @@ int  b2cloud_clear(b2cloud *c);
 int  b2cloud_device_ptr(b2cloud *c, void **d_f4);
 /* dst += pcl::transformPointCloud(src, T) (T column-major float 4x4; intensity kept; order kept) */
 int  b2cloud_append_transformed(b2cloud *dst, b2cloud *src, const float T[16]);
+/* the whole local-map assembly of front_end.cpp:398-407 in one launch: dst = srcs[0] moved by poses[0] ++ srcs[1] moved
+ * by poses[1] ++ ... (K column-major float[16] poses); same points, same order as K calls of the function above */
+int  b2cloud_assemble(b2cloud *dst, b2cloud *const *srcs, const float *poses, size_t K);
 /* pcl::CropBox: dst = points of src with edge[0] <= x <= edge[1], edge[2] <= y <= edge[3],
  * edge[4] <= z <= edge[5] (BoxFilter::GetEdge order), input order kept, non-finite points dropped.
  * For this call, b2cloud_remove_nan and b2cloud_distortion_adjust dst may be src (the reference's in == out calls):

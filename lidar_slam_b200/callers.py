@@ -63,7 +63,7 @@ class FrontEnd:
 
 class FrontEndDevice(FrontEnd):
     """The same front end with every cloud resident in HBM: the raw frame is uploaded once,
-    key frames stay on the device, the local map is assembled (AppendTransformed), filtered (FilterCloud, in
+    key frames stay on the device, the local map is assembled (Assemble: one launch for the 20 key frames), filtered (FilterCloud, in
     place) and handed to SetInputTargetCloud without a host round trip."""
 
     def __init__(self, vf, lvf, reg, key_dist=2.0, local_frames=20, device=0):
@@ -79,9 +79,7 @@ class FrontEndDevice(FrontEnd):
         if len(self.keyframes) > self.local_frames:
             self.keyframes.pop(0)
         t0 = time.perf_counter()
-        self.local.Clear()
-        for T, c in self.keyframes:
-            self.local.AppendTransformed(c, T)
+        self.local.Assemble([c for _, c in self.keyframes], [T for T, _ in self.keyframes])
         self.t_assemble.append(1e3 * (time.perf_counter() - t0))
         t = time.perf_counter()
         if len(self.keyframes) >= 10:

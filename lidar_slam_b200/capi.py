@@ -24,7 +24,7 @@ EXPORTS = [
     "b2ndt_derivatives", "b2ndt_fitness", "b2ndt_fitness_ex",
     "b2vf_create", "b2vf_destroy", "b2vf_set_stream", "b2vf_filter", "b2vf_filter_batch_device", "b2vf_filter_batch_append_device",
     "b2cloud_create", "b2cloud_destroy", "b2cloud_upload", "b2cloud_download", "b2cloud_size", "b2cloud_clear",
-    "b2cloud_device_ptr", "b2cloud_append_transformed", "b2cloud_box_filter", "b2cloud_remove_nan", "b2cloud_distortion_adjust", "b2vf_filter_cloud", "b2vf_ingest_filter_cloud",
+    "b2cloud_device_ptr", "b2cloud_append_transformed", "b2cloud_assemble", "b2cloud_box_filter", "b2cloud_remove_nan", "b2cloud_distortion_adjust", "b2vf_filter_cloud", "b2vf_ingest_filter_cloud",
     "b2ndt_set_target_cloud", "b2ndt_align_cloud",
     "b2_pcd_read", "b2_pcd_free", "b2_pcd_write_binary", "b2cloud_load_pcd", "b2cloud_save_pcd",
     "b2hmap_create", "b2hmap_destroy", "b2hmap_build", "b2hmap_info", "b2hmap_cells", "b2hmap_yaw_search", "b2hmap_pose_search",
@@ -117,6 +117,7 @@ def lib():
     L.b2cloud_clear.argtypes = [vp]
     L.b2cloud_device_ptr.argtypes = [vp, C.POINTER(vp)]
     L.b2cloud_append_transformed.argtypes = [vp, vp, fp]
+    L.b2cloud_assemble.argtypes = [vp, C.POINTER(vp), fp, sz]
     L.b2cloud_box_filter.argtypes = [vp, fp, vp]
     L.b2cloud_remove_nan.argtypes = [vp, vp]
     L.b2cloud_distortion_adjust.argtypes = [vp, C.c_float, dp, dp, vp]

@@ -263,6 +263,59 @@ extern "C" int b2cloud_append_transformed(b2cloud *dst, b2cloud *src, const floa
     return 0;
 }
 
+// Local-map assembly of the front end (front_end.cpp:398-407: for every key frame  pcl::transformPointCloud + operator+=)
+// in ONE launch: blockIdx.y = key frame, each with its own pose; dst = the concatenation in key-frame order.
+struct AsmDesc { const float4 *src; uint32_t n, off; float T[16]; };
+__global__ void __launch_bounds__(256) assemble_kernel(const AsmDesc *__restrict__ descs, float4 *__restrict__ dst) {
+    __shared__ AsmDesc D;
+    if (threadIdx.x == 0) D = descs[blockIdx.y];
+    __syncthreads();
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < D.n; i += gridDim.x * blockDim.x) {
+        const float4 p = __ldg(&D.src[i]);
+        float4 o = p;
+        if (finite3(p.x, p.y, p.z)) transform_f32(D.T, p.x, p.y, p.z, o.x, o.y, o.z);
+        dst[D.off + i] = o;
+    }
+}
+
+extern "C" int b2cloud_assemble(b2cloud *dst, b2cloud *const *srcs, const float *poses, size_t K) {
+    int rc = cloud_check("b2cloud_assemble", dst);
+    if (rc) return rc;
+    if (K && (!srcs || !poses)) { set_error("b2cloud_assemble: NULL argument"); return B2_ERR_INVALID; }
+    if (K > 4096) { set_error("b2cloud_assemble: at most 4096 clouds per call"); return B2_ERR_INVALID; }
+    size_t total = 0, nmax = 0;
+    for (size_t k = 0; k < K; ++k) {
+        if ((rc = cloud_check("b2cloud_assemble", srcs[k]))) return rc;
+        if (srcs[k] == dst) { set_error("b2cloud_assemble: a source is the destination"); return B2_ERR_INVALID; }
+        if (srcs[k]->device != dst->device) { set_error("b2cloud_assemble: clouds live on different devices"); return B2_ERR_INVALID; }
+        total += srcs[k]->n;
+        if (srcs[k]->n > nmax) nmax = srcs[k]->n;
+    }
+    if (total >= 0xFFFFFFF0ull) { set_error("b2cloud_assemble: cloud too large"); return B2_ERR_INVALID; }
+    B2_CUDA(cudaSetDevice(dst->device));
+    dst->n = 0; dst->first_known = false;
+    if (total == 0) return 0;
+    if ((rc = dst->reserve(total))) return rc;
+    if ((rc = dst->h_small.reserve(K * sizeof(AsmDesc) + 256))) return rc;
+    if ((rc = dst->scratch.reserve(K * sizeof(AsmDesc) + 256))) return rc;
+    AsmDesc *hd = dst->h_small.as<AsmDesc>();
+    uint32_t off = 0;
+    for (size_t k = 0; k < K; ++k) {
+        hd[k].src = srcs[k]->d(); hd[k].n = (uint32_t)srcs[k]->n; hd[k].off = off;
+        memcpy(hd[k].T, poses + 16 * k, 64);
+        off += (uint32_t)srcs[k]->n;
+    }
+    B2_CUDA(cudaMemcpyAsync(dst->scratch.p, hd, K * sizeof(AsmDesc), cudaMemcpyHostToDevice, dst->st));
+    unsigned bx = (unsigned)((nmax + 255) / 256);
+    const unsigned cap = (unsigned)((148 * 16 + K - 1) / K);          // ~16 CTAs per SM over all key frames
+    if (bx > cap) bx = cap < 1 ? 1 : cap;
+    assemble_kernel<<<dim3(bx, (unsigned)K), 256, 0, dst->st>>>(dst->scratch.as<AsmDesc>(), dst->d());
+    B2_LAUNCH_CHECK();
+    B2_CUDA(cudaStreamSynchronize(dst->st));
+    dst->n = total;
+    return 0;
+}
+
 // order-preserving compaction of src into dst under Op (count per tile, scan, stable scatter)
 template <class Op>
 static int compact_cloud(const char *fn, b2cloud *src, b2cloud *dst, const Op &B) {

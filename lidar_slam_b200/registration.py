@@ -113,6 +113,16 @@ class DeviceCloud:
         return self
 
 
+    def Assemble(self, clouds, poses):
+        """*this = concat_k pcl::transformPointCloud(clouds[k], poses[k])  (the local-map loop of front_end.cpp:398-407)
+        in one launch; same points and order as Clear() + AppendTransformed per key frame."""
+        K = len(clouds)
+        hs = (C.c_void_p * max(K, 1))(*[c._h for c in clouds])
+        P = np.ascontiguousarray(np.concatenate([capi.pose_to_colmajor(p) for p in poses]) if K else np.zeros(16, np.float32), np.float32)
+        capi.check(capi.lib().b2cloud_assemble(self._h, hs, capi._fp(P), K))
+        return self
+
+
 class RegistrationInterface:
     def SetInputTarget(self, input_target):
         raise NotImplementedError

@@ -69,6 +69,19 @@ def test_local_map_assembly_filter_and_target(scene):
     ref_local = np.concatenate([O.transform_cloud(f, T) for f, T in zip(frames, rel)], axis=0)
     assert len(local) == len(ref_local)
     assert np.array_equal(local.Download(), ref_local)
+    # the same assembly in one launch (b2cloud_assemble), with an empty key frame in the middle and NaN points kept
+    fr2 = [f.copy() for f in frames]
+    fr2[2][::50, 0] = np.nan
+    fr2.insert(3, np.zeros((0, 4), np.float32))
+    rel2 = rel[:3] + [np.eye(4, dtype=np.float32)] + rel[3:]
+    one = DeviceCloud(np.ones((7, 4), np.float32))            # previous contents are replaced
+    one.Assemble([DeviceCloud(f) for f in fr2], rel2)
+    seq = DeviceCloud()
+    for f, T in zip(fr2, rel2):
+        seq.AppendTransformed(DeviceCloud(f), T)
+    assert len(one) == len(seq) and np.array_equal(one.Download(), seq.Download(), equal_nan=True)
+    one.Assemble([], [])
+    assert len(one) == 0
     vf = VoxelFilter(0.6, 0.6, 0.6)
     filt_dev = vf.FilterCloud(local)
     ok, filt_host = vf.Filter(ref_local)
