@@ -16,7 +16,7 @@
 //                              -(leaf+1) sparse, 0 empty
 //   nbr_head    uint2[ncells]  {first entry, count} of the cell's neighbour list
 //   nbr_list    float4[..]     per cell, the searchable leaves of its 3x3x3 window {centroid x,y,z, leaf} in
-//                              fixed (z,y,x) order, lists laid out in cell order (a radius query reads ONE
+//                              fixed (z,y,x) order, one contiguous run per cell (a radius query reads ONE
 //                              header and one contiguous run instead of 27 scattered cells)
 // The path is a gather + reduction (no dense contraction): no tensor cores by design.
 #include <cooperative_groups.h>

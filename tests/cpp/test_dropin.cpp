@@ -88,6 +88,45 @@ int main(int argc, char** argv) {
         std::printf("DEV %d %d\n", same ? 1 : 0, reg2.LastResult().iterations);
         b2cloud_destroy(d_map); b2cloud_destroy(d_scan); b2cloud_destroy(d_filt); b2cloud_destroy(d_res);
     }
+    // UpdateInputTarget (the in-tree NDT's updateVoxelGrid): target set from the first half of the map, second half added;
+    // the match must equal the one against the whole map.  The full raw scan as a source exercises the device-side fill
+    // of the result cloud (b2ndt_align_ex path of ScanMatch).
+    {
+        NDTRegistration reg3(1.0f, 0.1f, 0.01f, 30);
+        // the points that span the bounding box go into the first part (the update then stays inside the index box)
+        CloudData::CLOUD_PTR a(new CloudData::CLOUD()), b(new CloudData::CLOUD());
+        size_t ext[6] = {0, 0, 0, 0, 0, 0};
+        for (size_t i = 0; i < target->points.size(); ++i) {
+            const CloudData::POINT& p = target->points[i];
+            if (p.x < target->points[ext[0]].x) ext[0] = i; if (p.x > target->points[ext[1]].x) ext[1] = i;
+            if (p.y < target->points[ext[2]].y) ext[2] = i; if (p.y > target->points[ext[3]].y) ext[3] = i;
+            if (p.z < target->points[ext[4]].z) ext[4] = i; if (p.z > target->points[ext[5]].z) ext[5] = i;
+        }
+        for (size_t i = 0; i < target->points.size(); ++i) {
+            bool is_ext = false;
+            for (int k = 0; k < 6; ++k) is_ext = is_ext || ext[k] == i;
+            ((is_ext || i < target->points.size() / 2) ? a : b)->points.push_back(target->points[i]);
+        }
+        CloudData::CLOUD_PTR whole(new CloudData::CLOUD());
+        whole->points = a->points;
+        whole->points.insert(whole->points.end(), b->points.begin(), b->points.end());
+        bool ok = reg3.SetInputTarget(a) && reg3.UpdateInputTarget(b);
+        Eigen::Matrix4f p3 = Eigen::Matrix4f::Identity(), p4 = Eigen::Matrix4f::Identity();
+        CloudData::CLOUD_PTR r3(new CloudData::CLOUD()), r4(new CloudData::CLOUD());
+        ok = ok && reg3.ScanMatch(scan, guess, r3, p3);
+        NDTRegistration reg4(1.0f, 0.1f, 0.01f, 30);
+        ok = ok && reg4.SetInputTarget(whole) && reg4.ScanMatch(scan, guess, r4, p4);
+        bool same = ok && r3->points.size() == scan->points.size() && r4->points.size() == scan->points.size();
+        for (int i = 0; i < 16; ++i) same = same && p3.data()[i] == p4.data()[i];
+        // device-filled result cloud == the host formula on the first points
+        for (size_t i = 0; same && i < 64 && i < scan->points.size(); ++i) {
+            const CloudData::POINT& sp = scan->points[i];
+            const float* m = p3.data();
+            const float x = ((m[0] * sp.x + m[4] * sp.y) + m[8] * sp.z) + m[12];
+            same = same && r3->points[i].x == x && r3->points[i].intensity == sp.intensity && r3->points[i].data[3] == 1.0f;
+        }
+        std::printf("UPD %d %d %d\n", same ? 1 : 0, reg3.LastResult().iterations, reg4.LastResult().iterations);
+    }
     // result cloud = source under the final pose
     if (result->points.size() != filtered->points.size()) return 1;
     std::printf("R0 %.9g %.9g %.9g %.9g\n", result->points[0].x, result->points[0].y, result->points[0].z, result->points[0].intensity);

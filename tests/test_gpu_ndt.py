@@ -423,8 +423,9 @@ def test_cpp_dropin_classes(oracle, small_map, scans, tmp_path):
     np.ascontiguousarray(guess.flatten(order="F")).tofile(str(tmp_path / "g.bin"))
     out = subprocess.run([exe, str(tmp_path / "t.bin"), str(tmp_path / "s.bin"), str(tmp_path / "g.bin")],
                          stdout=subprocess.PIPE, text=True, check=True).stdout
-    kv = {l.split()[0]: l.split()[1:] for l in out.splitlines() if l and l.split()[0] in ("M", "POSE", "FIT", "ITER", "R0", "BOX", "DEV")}
+    kv = {l.split()[0]: l.split()[1:] for l in out.splitlines() if l and l.split()[0] in ("M", "POSE", "FIT", "ITER", "R0", "BOX", "DEV", "UPD")}
     assert kv["DEV"][0] == "1" and kv["DEV"][1] == kv["ITER"][0]          # device-resident C++ path == host-buffer path
+    assert kv["UPD"][0] == "1" and kv["UPD"][1] == kv["UPD"][2]           # UpdateInputTarget == SetInputTarget of the whole; device-filled result cloud
     assert kv["BOX"][0] == kv["BOX"][1] and int(kv["BOX"][0]) > 0 and kv["BOX"][2] == kv["BOX"][3]      # C++ BoxFilter == CropBox
     filt = oracle.voxel_filter(scan, 1.3, 1.3, 1.3)[0]
     grid = oracle.Grid(small_map, 1.0)
