@@ -464,6 +464,55 @@ def initial_yaw_angle(cells, scan, angle_size=270):
     return best, probs
 
 
+_REFMATCH = None
+
+
+def refmatch_lib():
+    """oracle/_ref/libmatching_ref.so: the reference's own matching.cpp (height grid + yaw scan) compiled against stub headers."""
+    global _REFMATCH
+    if _REFMATCH is not None:
+        return _REFMATCH
+    path = os.path.join(_HERE, "_ref", "libmatching_ref.so")
+    if not os.path.exists(path):
+        return None
+    R = C.CDLL(path)
+    fp, ip = C.POINTER(C.c_float), C.POINTER(C.c_int)
+    R.refmatch_new.argtypes = [C.c_double]; R.refmatch_new.restype = C.c_void_p
+    R.refmatch_free.argtypes = [C.c_void_p]
+    R.refmatch_build.argtypes = [C.c_void_p, fp, C.c_size_t, fp]
+    R.refmatch_info.argtypes = [C.c_void_p, ip, fp, fp]
+    R.refmatch_cells.argtypes = [C.c_void_p, fp, fp, ip]
+    R.refmatch_yaw.argtypes = [C.c_void_p, fp, C.c_size_t]; R.refmatch_yaw.restype = C.c_double
+    _REFMATCH = R
+    return R
+
+
+def gauss2d_map_cells_reference(local_map, origin, grid_resolution=0.8, scans=()):
+    """Run the reference's own Matching::generateGauss2DMapCells (+ getInitialYawAngle for every cloud in `scans`);
+    only where oracle/_ref was built.  -> (cells dict like gauss2d_map_cells, [yaw angle per scan])"""
+    R = refmatch_lib()
+    if R is None:
+        raise RuntimeError("oracle/_ref/libmatching_ref.so is not built (needs /root/reference)")
+    fp, ip = C.POINTER(C.c_float), C.POINTER(C.c_int)
+    m = np.ascontiguousarray(local_map, np.float32)
+    o = np.ascontiguousarray(origin, np.float32)
+    h = R.refmatch_new(float(grid_resolution))
+    try:
+        R.refmatch_build(h, m.ctypes.data_as(fp), len(m), o.ctypes.data_as(fp))
+        wh = np.zeros(2, np.int32); mn = np.zeros(3, np.float32); mx = np.zeros(3, np.float32)
+        R.refmatch_info(h, wh.ctypes.data_as(ip), mn.ctypes.data_as(fp), mx.ctypes.data_as(fp))
+        w, hh = int(wh[0]), int(wh[1])
+        mu = np.zeros((w, hh), np.float32); sg = np.zeros((w, hh), np.float32); cnt = np.zeros((w, hh), np.int32)
+        R.refmatch_cells(h, mu.ctypes.data_as(fp), sg.ctypes.data_as(fp), cnt.ctypes.data_as(ip))
+        yaws = []
+        for s in scans:
+            s = np.ascontiguousarray(s, np.float32)
+            yaws.append(R.refmatch_yaw(h, s.ctypes.data_as(fp), len(s)))
+    finally:
+        R.refmatch_free(h)
+    return dict(width=w, height=hh, min_xyz=mn, max_xyz=mx, mu=mu, sigma=sg, cnt=cnt, res=max(0.1, float(grid_resolution))), yaws
+
+
 # ------------------------------------------------------------------ scan de-skew (data_pretreat) -------------
 _DESKEW = None
 

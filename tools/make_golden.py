@@ -234,6 +234,30 @@ def intree_update():
     print("intree_update.npz: voxels", len(ijk), "vs the reference's full build: same voxel set", same, "max |dmean|", d_mean, "max rel dicov", d_icov)
 
 
+def intree_matching():
+    """Outputs of the reference's OWN position-only initialisation (matching.cpp: generateGauss2DMapCells :344-394,
+    getInitialYawAngle :267-308, compiled where it lies into oracle/_ref/libmatching_ref.so) on a seeded local map (with
+    a few non-finite points) and two scans: the Gaussian height grid (mu / sigma / count per cell) and the winning yaw."""
+    from lidar_slam_b200 import synth
+    O.build(ref=True)
+    scene = synth.Scene(leg=60.0)
+    m = scene.make_map(20000, 2.0)
+    m[::501, 0] = np.nan
+    origin = np.array([10.0, 2.0, 0.5], np.float32)
+    scans = []
+    for k, s in enumerate((20.0, 33.0)):
+        sc = scene.scan(5 + k, scene.path_pose(s))[::40].copy()
+        sc[::97, 1] = np.nan
+        # the scan as the matching node sees it: sensor frame rotated by an unknown heading about the local-map origin
+        scans.append(sc)
+    ref, yaws = O.gauss2d_map_cells_reference(m, origin, 0.8, scans)
+    np.savez_compressed(os.path.join(OUT, "intree_matching.npz"), local_map=m, origin=origin, grid_resolution=np.array(0.8),
+                        scan0=scans[0], scan1=scans[1], width=np.array(ref["width"]), height=np.array(ref["height"]),
+                        min_xyz=ref["min_xyz"], max_xyz=ref["max_xyz"], mu=ref["mu"], sigma=ref["sigma"], cnt=ref["cnt"],
+                        yaw=np.array(yaws))
+    print("intree_matching.npz: grid", ref["width"], "x", ref["height"], "occupied", int((ref["cnt"] > 0).sum()), "yaw", yaws)
+
+
 def deskew():
     """Outputs of the reference's OWN DistortionAdjust (oracle/_ref/libdeskew_ref.so = distortion_adjust.cpp compiled
     where it lies against oracle/ref_stubs + the vendored Eigen) on a seeded synthetic sweep."""
@@ -258,4 +282,5 @@ if __name__ == "__main__":
     ndt_small()
     intree_ndt()
     intree_update()
+    intree_matching()
     deskew()
