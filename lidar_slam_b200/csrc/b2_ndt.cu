@@ -553,6 +553,15 @@ constexpr int NACC = 35;                       // per-lane accumulators of a der
 constexpr int NDT_WARPS = NDT_NCW + NDT_NSW;
 constexpr int NDT_THREADS = NDT_WARPS * 32;
 constexpr int NDT_PPC = NDT_NSW / NDT_NCW;     // producers (search warps) per compute warp
+// A single match (and any launch whose CTAs fit the GPU one per SM) runs ndt_match_kernel with NDT_NCW_WIDE compute warps
+// per CTA, one per search warp: the drain of a pass -- the longest phase of a single match, ~113 pairs = 4 dependent
+// 32-pair chunks per compute warp -- takes half the steps.  Register file: 8 x 128 + 8 x 56 per lane = one CTA per SM.
+constexpr int NDT_NCW_WIDE = (NDT_NSW > NDT_NCW) ? NDT_NSW : NDT_NCW;
+#ifndef NDT_POLL_ALL
+#define NDT_POLL_ALL 1  // ring polls (consumer: next chunk, producer: ring room) run on every lane (same shared-memory words, broadcast)
+                        // instead of lane 0 only: the warp stays converged, so the shuffles that follow never take the
+                        // divergent-warp path (WARPSYNC.COLLECTIVE per shuffle: 350 of them in the reduction = 41 us)
+#endif
 #ifndef NDT_RING
 #define NDT_RING 512
 #endif
@@ -610,7 +619,7 @@ constexpr uint32_t PASS_RING = 8;               // pass markers kept per search 
 
 struct Slot {                      // one match in flight
     Ctl ctl;
-    double warp_part[NDT_NCW][NACC];
+    double warp_part[NDT_NCW_WIDE][NACC];
     double cta_part[2][NACC];      // cluster mode: double-buffered per-CTA partial, read by cluster peers over DSMEM
     double raw_total[NACC];        // reduced pair sums (NACC layout)
     double total[ACC_N];           // contracted with the angle tables: what the controller consumes
@@ -638,7 +647,8 @@ struct NdtSmem {
     float4 stage[NDT_NSW][192];    // per search warp, three slots: [lane] source point, [32 + lane] transformed point
 };
 
-__device__ __forceinline__ void cta_barrier() { asm volatile("bar.sync 0, %0;" ::"n"(NDT_THREADS) : "memory"); }
+template <int THREADS>
+__device__ __forceinline__ void cta_barrier() { asm volatile("bar.sync 0, %0;" ::"n"(THREADS) : "memory"); }
 __device__ __forceinline__ uint32_t ld_vol(const uint32_t *p) { return *reinterpret_cast<const volatile uint32_t *>(p); }
 __device__ __forceinline__ void st_vol(uint32_t *p, uint32_t v) { *reinterpret_cast<volatile uint32_t *>(p) = v; }
 #ifndef NDT_FENCE
@@ -946,9 +956,14 @@ __device__ __forceinline__ void search_pass(NdtSmem &S, const GridView &G, const
     auto ring_room = [&](uint32_t need) {
         if (my_tail - hd_seen > RING - need) {
             uint32_t hd = 0;
-            if (lane == 0) {
+            if (NDT_POLL_ALL || lane == 0) {
                 hd = ld_vol(&S.head[sw]);
-                while (my_tail - hd > RING - need) { __nanosleep(64); hd = ld_vol(&S.head[sw]); }
+                while (my_tail - hd > RING - need) {
+#if NDT_DRAIN_SLEEP > 0
+                    __nanosleep(64);
+#endif
+                    hd = ld_vol(&S.head[sw]);
+                }
             }
             hd_seen = __shfl_sync(0xffffffffu, hd, 0);
         }
@@ -1161,6 +1176,40 @@ __device__ __forceinline__ void search_dead_marker(NdtSmem &S, int sw, int lane,
     }
 }
 
+// Sum of every accumulator over the 32 lanes -> part[NACC].  Each sum is the XOR-butterfly tree (lane l adds the value of
+// lane l ^ 16, then ^ 8, 4, 2, 1): the order every earlier version used, so the bits of a match's sums do not change.  But
+// instead of 35 full butterflies (175 double shuffles, every lane ending up with every total) the lanes SPLIT the values at
+// each step -- the half of the warp with the step's lane bit clear keeps the lower half of the values and hands over the
+// upper half, and vice versa -- so a step moves half of what the previous one did: 18 + 9 + 5 + 3 + 2 = 37 double shuffles,
+// and each total ends in exactly one lane, which stores it.  (a + b is commutative bit for bit, so the keeper's
+// own + received is the value both partners of the full butterfly would compute.)
+template <int N, int H>
+__device__ __forceinline__ void halve_step(const double (&in)[N], double (&out)[H], const bool upper, const int xor_mask) {
+    static_assert(H == (N + 1) / 2, "halves");
+#pragma unroll
+    for (int i = 0; i < H; ++i) {
+        const double a = in[i];
+        const double b = (i + H < N) ? in[i + H] : 0.0;
+        const double keep = upper ? b : a, send = upper ? a : b;
+        out[i] = keep + __shfl_xor_sync(0xffffffffu, send, xor_mask);
+    }
+}
+__device__ __forceinline__ void warp_reduce_acc(const double (&acc)[NACC], const int lane, double *__restrict__ part) {
+    double r18[18], r9[9], r5[5], r3[3], r2[2];
+    halve_step<NACC, 18>(acc, r18, (lane & 16) != 0, 16);
+    halve_step<18, 9>(r18, r9, (lane & 8) != 0, 8);
+    halve_step<9, 5>(r9, r5, (lane & 4) != 0, 4);
+    halve_step<5, 3>(r5, r3, (lane & 2) != 0, 2);
+    halve_step<3, 2>(r3, r2, (lane & 1) != 0, 1);
+    // which accumulators this lane ended up with (an index beyond a level's size is that level's zero padding)
+    const int o5 = (lane & 1) ? 2 : 0, o4 = (lane & 2) ? 3 : 0, o3 = (lane & 4) ? 5 : 0, o2 = (lane & 8) ? 9 : 0, o1 = (lane & 16) ? 18 : 0;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int k5 = o5 + j, k4 = o4 + k5, k3 = o3 + k4, k1 = o1 + o2 + k3;
+        if (k5 < 3 && k4 < 5 && k3 < 9 && k1 < NACC) part[k1] = j ? r2[1] : r2[0];
+    }
+}
+
 // ---------------------------------------------------------------- compute warps (consumers) ----
 // Drain one pass from this compute warp's rings: lane = (point, voxel) pair, fixed round-robin over the
 // producers, 32 pairs at a time; the warp's partial sums (butterfly, fixed order) go to `part`.
@@ -1171,8 +1220,11 @@ struct DrainState {
 
 // Returns false when the "pass" was the marker of a dead slot (batch kernel).  The pass description (ctl.T, ctl.ang,
 // ctl.hess) is read only once the producers have delivered data or finished, i.e. after its request was published.
+template <int NCW>
 __device__ __forceinline__ bool compute_drain(NdtSmem &S, const GridView &G, const NdtConst &K, const Ctl &ctl, int warp, int lane,
                                               DrainState &ds, double *__restrict__ part) {
+    constexpr int PPC = NDT_NSW / NCW;             // producers per compute warp (<= NDT_PPC, the size of ds.cpos)
+    static_assert(NCW >= NDT_NCW && NDT_NSW % NCW == 0, "compute warps per CTA");
     ++ds.pass_id;
     const float *T = ctl.T;
     bool hess = false, have_desc = false, slot_dead = false;
@@ -1183,18 +1235,18 @@ __device__ __forceinline__ bool compute_drain(NdtSmem &S, const GridView &G, con
     {
             uint32_t done_mask = 0;                         // bit k: producer k exhausted for this pass
             int turn = 0;
-            while (done_mask != (1u << NDT_PPC) - 1u) {
+            while (done_mask != (1u << PPC) - 1u) {
                 // fixed round-robin over this warp's producers (deterministic accumulation order)
                 const int k = turn;
-                turn = (turn + 1 == NDT_PPC) ? 0 : turn + 1;
+                turn = (turn + 1 == PPC) ? 0 : turn + 1;
                 if (done_mask & (1u << k)) continue;
-                const int sw = warp + k * NDT_NCW;
+                const int sw = warp + k * NCW;
                 uint32_t pos = 0;
 #pragma unroll
-                for (int kk = 0; kk < NDT_PPC; ++kk) if (kk == k) pos = ds.cpos[kk];
+                for (int kk = 0; kk < PPC; ++kk) if (kk == k) pos = ds.cpos[kk];
                 // wait for a full chunk of 32 pairs, or for the producer to finish the pass
                 uint32_t n = 0;
-                if (lane == 0) {
+                if (NDT_POLL_ALL || lane == 0) {
                     while (true) {
                         // tail first, finished second: when the pass is not finished yet, everything up to the
                         // tail read before belongs to it; once finished, the pass ends at pass_end (the producer
@@ -1211,7 +1263,9 @@ __device__ __forceinline__ bool compute_drain(NdtSmem &S, const GridView &G, con
                             n = avail | 0x80000000u | (ld_vol(&S.pass_dead[sw][ds.pass_id & (PASS_RING - 1u)]) ? 0x40000000u : 0u);
                             break;
                         }
+#if NDT_DRAIN_SLEEP > 0
                         __nanosleep(NDT_DRAIN_SLEEP);
+#endif
                     }
                 }
                 n = __shfl_sync(0xffffffffu, n, 0);
@@ -1228,27 +1282,22 @@ __device__ __forceinline__ bool compute_drain(NdtSmem &S, const GridView &G, con
                 }
                 pos += n;
 #pragma unroll
-                for (int kk = 0; kk < NDT_PPC; ++kk) if (kk == k) ds.cpos[kk] = pos;
+                for (int kk = 0; kk < PPC; ++kk) if (kk == k) ds.cpos[kk] = pos;
                 __syncwarp();
                 if (lane == 0 && n) st_vol(&S.head[sw], pos);
                 if (final_chunk) done_mask |= (1u << k);
             }
     }
-    // warp butterfly (fixed order) -> one partial per compute warp
-#pragma unroll
-    for (int i = 0; i < NACC; ++i) {
-        double vsum = acc[i];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) vsum += __shfl_xor_sync(0xffffffffu, vsum, o);
-        if (lane == 0) part[i] = vsum;
-    }
+    warp_reduce_acc(acc, lane, part);
     return !slot_dead;
 }
 
 // ================================================================ kernel 1: one match per cluster ======
 // One thread-block cluster (1..16 CTAs) per match: lowest latency for a single ScanMatch, also the
 // derivatives-only entry point.  Passes are separated by CTA / cluster barriers.
-__global__ void __launch_bounds__(NDT_THREADS, NDT_MIN_CTAS) ndt_match_kernel(GridView G, NdtConst K, MatchArgs A) {
+template <int NCW>
+__global__ void __launch_bounds__((NCW + NDT_NSW) * 32, (NCW > NDT_NCW) ? 1 : NDT_MIN_CTAS) ndt_match_kernel(GridView G, NdtConst K, MatchArgs A) {
+    constexpr int THREADS = (NCW + NDT_NSW) * 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     NdtSmem &S = *reinterpret_cast<NdtSmem *>(smem_raw);
     Slot &SL = S.slot[0];
@@ -1257,7 +1306,7 @@ __global__ void __launch_bounds__(NDT_THREADS, NDT_MIN_CTAS) ndt_match_kernel(Gr
     const unsigned crank = cluster.block_rank();
     const unsigned match = blockIdx.x / C;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const bool is_compute = warp < NDT_NCW;
+    const bool is_compute = warp < NCW;
 
     uint32_t first = 0, last = A.n_shared;
     if (A.offsets) { first = A.offsets[match]; last = A.offsets[match + 1]; }
@@ -1286,7 +1335,7 @@ __global__ void __launch_bounds__(NDT_THREADS, NDT_MIN_CTAS) ndt_match_kernel(Gr
 #define TRC(slot_) do { if (A.timing && crank == 0 && match == 0 && trc_pass < 6 && (tid == trc_tid)) A.timing[32 + trc_pass * 8 + (slot_)] = (unsigned long long)(clock64() - trc_t0); } while (0)
     const long long trc_t0 = clock64();
     int trc_pass = 0;
-    const int trc_tid = is_compute ? 0 : NDT_NCW * 32;
+    const int trc_tid = is_compute ? 0 : NCW * 32;
 #else
 #define TRC(slot_) do { } while (0)
 #endif
@@ -1294,14 +1343,14 @@ __global__ void __launch_bounds__(NDT_THREADS, NDT_MIN_CTAS) ndt_match_kernel(Gr
     // budget); they meet at CTA-wide barriers issued from both branches.
     if (!is_compute) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(NDT_REG_SEARCH));
-        const int sw = warp - NDT_NCW;
+        const int sw = warp - NCW;
         SearchState st;
         while (true) {
             // rounds are dealt out CTA-first (round = sw * C + crank): the source is in voxel order, so consecutive
             // rounds are spatial neighbours with similar hit counts and every CTA gets an even sample of the scan
             TRC(0);
 #ifdef NDT_TIMING
-            if (A.timing && match == 0 && trc_pass == 2 && lane == 0 && sw == 0) { unsigned long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); A.timing[128 + crank * 16 + 12] = g; }
+            if (A.timing && match == 0 && trc_pass == 2 && lane == 0 && sw == 0) { unsigned long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); A.timing[352 + crank] = g; }
 #endif
             search_pass(S, G, A.src, first, last, first + (sw * C + crank), stride, C * NDT_NSW, SL.ctl.T, sw, lane, st);
             TRC(1);
@@ -1311,10 +1360,10 @@ __global__ void __launch_bounds__(NDT_THREADS, NDT_MIN_CTAS) ndt_match_kernel(Gr
 #ifdef NDT_TIMING
             ++trc_pass;
 #endif
-            cta_barrier();                          // (1) all pairs of the pass consumed, partials written
+            cta_barrier<THREADS>();                          // (1) all pairs of the pass consumed, partials written
             if (C > 1) cluster.sync();
-            cta_barrier();                          // (2) totals ready
-            cta_barrier();                          // (3) controller done
+            cta_barrier<THREADS>();                          // (2) totals ready
+            cta_barrier<THREADS>();                          // (3) controller done
             if (!ld_vol(reinterpret_cast<const uint32_t *>(&SL.go))) break;
         }
         if (C > 1) cluster.sync();
@@ -1326,12 +1375,12 @@ __global__ void __launch_bounds__(NDT_THREADS, NDT_MIN_CTAS) ndt_match_kernel(Gr
         for (int k = 0; k < NDT_PPC; ++k) ds.cpos[k] = 0;
         ds.pass_id = 0;
         while (true) {
-            (void)compute_drain(S, G, K, SL.ctl, warp, lane, ds, SL.warp_part[warp]);
+            (void)compute_drain<NCW>(S, G, K, SL.ctl, warp, lane, ds, SL.warp_part[warp]);
             TRC(2);
 #ifdef NDT_TIMING
             if (A.timing && match == 0 && trc_pass == 2 && lane == 0) { unsigned long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); A.timing[128 + crank * 16 + warp] = g; }
 #endif
-            cta_barrier();                              // (1)
+            cta_barrier<THREADS>();                              // (1)
             TRC(3);
 #ifdef NDT_TIMING
             if (A.timing && match == 0 && trc_pass == 1 && tid == 0) { unsigned long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); A.timing[96 + crank] = g; }
@@ -1340,7 +1389,7 @@ __global__ void __launch_bounds__(NDT_THREADS, NDT_MIN_CTAS) ndt_match_kernel(Gr
             if (tid < NACC) {
                 double s = 0.0;
 #pragma unroll
-                for (int w = 0; w < NDT_NCW; ++w) s += SL.warp_part[w][tid];
+                for (int w = 0; w < NCW; ++w) s += SL.warp_part[w][tid];
                 SL.cta_part[parity][tid] = s;
             }
             if (C > 1) {
@@ -1362,7 +1411,7 @@ __global__ void __launch_bounds__(NDT_THREADS, NDT_MIN_CTAS) ndt_match_kernel(Gr
             } else {
                 if (tid < NACC) SL.raw_total[tid] = SL.cta_part[parity][tid];
             }
-            cta_barrier();                              // (2)
+            cta_barrier<THREADS>();                              // (2)
             TRC(5);
             // ---------------- controller: Newton step + More-Thuente state machine (warp 0) ----------------
             if (warp == 0) {
@@ -1373,7 +1422,7 @@ __global__ void __launch_bounds__(NDT_THREADS, NDT_MIN_CTAS) ndt_match_kernel(Gr
 #endif
                 if (lane == 0) SL.go = go;
             }
-            cta_barrier();                              // (3)
+            cta_barrier<THREADS>();                              // (3)
             TRC(6);
 #ifdef NDT_TIMING
             ++trc_pass;
@@ -1536,7 +1585,7 @@ __global__ void __launch_bounds__(NDT_THREADS, NDT_MIN_CTAS) ndt_batch_kernel(Gr
                 cnt_pack = (cnt_pack & ~(0xFu << (4 * s))) | ((((cnt_pack >> (4 * s)) + 1u) & 0xFu) << (4 * s));
                 const uint32_t seen_s = (cnt_pack >> (4 * s)) & 0xFu;
                 Slot &SL = S.slot[s];
-                const bool live = compute_drain(S, G, K, SL.ctl, warp, lane, ds, SL.warp_part[warp]);
+                const bool live = compute_drain<NDT_NCW>(S, G, K, SL.ctl, warp, lane, ds, SL.warp_part[warp]);
                 if (!live) { dead_mask |= 1u << s; continue; }
                 TMB_LAP(1);                                    // [1] draining (incl. waiting for chunks)
                 // the controller role of a slot rotates over the compute warps pass by pass (every warp knows the
@@ -1717,6 +1766,7 @@ struct b2ndt {
     PinBuf h_ready;
     bool stream_batches = true;            // B2NDT_STREAM=0: copy everything, then launch
     bool small_batch_clusters = true;      // B2NDT_SMALL_BATCH=0: never widen the matches of a small batch to clusters
+    bool wide_single = true;               // B2NDT_WIDE_SINGLE=0: launches that fit one CTA per SM keep the 4 + 8 warp shape (A/B runs)
 };
 
 static void gauss_constants(double outlier_ratio, float resolution, double *d1, double *d2) {
@@ -1757,12 +1807,14 @@ extern "C" int b2ndt_create(const b2ndt_params *p, int device, b2ndt **out) {
         // load the two large match kernels now (CUDA loads kernels lazily, ~0.1-0.25 s each on first launch): the
         // cost belongs to construction, not to the first ScanMatch of a 10 Hz pipeline
         cudaFuncAttributes fa;
-        if (cudaFuncGetAttributes(&fa, ndt_match_kernel) != cudaSuccess) cudaGetLastError();
+        if (cudaFuncGetAttributes(&fa, ndt_match_kernel<NDT_NCW>) != cudaSuccess) cudaGetLastError();
+        if (cudaFuncGetAttributes(&fa, ndt_match_kernel<NDT_NCW_WIDE>) != cudaSuccess) cudaGetLastError();
         if (cudaFuncGetAttributes(&fa, ndt_batch_kernel) != cudaSuccess) cudaGetLastError();
     }
     if (const char *e = getenv("B2NDT_BATCH_KERNEL")) h->use_batch_kernel = atoi(e) != 0;
     if (const char *e = getenv("B2NDT_STREAM")) h->stream_batches = atoi(e) != 0;
     if (const char *e = getenv("B2NDT_SMALL_BATCH")) h->small_batch_clusters = atoi(e) != 0;
+    if (const char *e = getenv("B2NDT_WIDE_SINGLE")) h->wide_single = atoi(e) != 0;
     *out = h;
     return 0;
 }
@@ -2166,8 +2218,12 @@ static GridView make_grid_view(const b2ndt *h) {
 static int launch_match(b2ndt *h, const MatchArgs &A, size_t B, int C) {
     if (B == 0) return 0;
     if (!h->attrs_set) {
-        B2_CUDA(cudaFuncSetAttribute(ndt_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NdtSmem)));
-        B2_CUDA(cudaFuncSetAttribute(ndt_match_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        B2_CUDA(cudaFuncSetAttribute(ndt_match_kernel<NDT_NCW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NdtSmem)));
+        B2_CUDA(cudaFuncSetAttribute(ndt_match_kernel<NDT_NCW>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        if (NDT_NCW_WIDE != NDT_NCW) {
+            B2_CUDA(cudaFuncSetAttribute(ndt_match_kernel<NDT_NCW_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NdtSmem)));
+            B2_CUDA(cudaFuncSetAttribute(ndt_match_kernel<NDT_NCW_WIDE>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        }
         h->attrs_set = true;
     }
     GridView G = make_grid_view(h);
@@ -2231,7 +2287,10 @@ static int launch_match(b2ndt *h, const MatchArgs &A, size_t B, int C) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)(B * (size_t)C));
-    cfg.blockDim = dim3(NDT_THREADS);
+    // the wide shape (one compute warp per search warp) holds one CTA per SM: taken when every CTA of the launch gets an SM
+    // of its own anyway (a single match's cluster, a handful of matches); larger launches keep two CTAs per SM
+    const bool wide = (NDT_NCW_WIDE != NDT_NCW) && h->wide_single && (B * (size_t)C <= (size_t)(h->batch_ctas / NDT_MIN_CTAS));
+    cfg.blockDim = dim3(wide ? (NDT_NCW_WIDE + NDT_NSW) * 32 : NDT_THREADS);
     cfg.dynamicSmemBytes = sizeof(NdtSmem);
     cfg.stream = h->st;
     cudaLaunchAttribute at[1];
@@ -2246,7 +2305,8 @@ static int launch_match(b2ndt *h, const MatchArgs &A, size_t B, int C) {
     cudaMemsetAsync(d_tr, 0, 384 * 8, h->st);
     Ac.timing = d_tr;
 #endif
-    cudaError_t e = cudaLaunchKernelEx(&cfg, ndt_match_kernel, G, K, Ac);
+    cudaError_t e = wide ? cudaLaunchKernelEx(&cfg, ndt_match_kernel<NDT_NCW_WIDE>, G, K, Ac)
+                         : cudaLaunchKernelEx(&cfg, ndt_match_kernel<NDT_NCW>, G, K, Ac);
     b2::count_launch();
     if (e != cudaSuccess) { set_error("ndt_match_kernel launch failed: %s", cudaGetErrorString(e)); return B2_ERR_CUDA; }
 #ifdef NDT_TIMING
@@ -2265,14 +2325,15 @@ static int launch_match(b2ndt *h, const MatchArgs &A, size_t B, int C) {
             fprintf(stderr, "\n");
             // pass 2, per CTA: search start (sw 0), then per warp: 4 x compute drained, 8 x search finished (ns after the earliest search start)
             unsigned long long s0 = ~0ull;
-            for (int r = 0; r < C; ++r) if (t[128 + r * 16 + 12] && t[128 + r * 16 + 12] < s0) s0 = t[128 + r * 16 + 12];
+            for (int r = 0; r < C; ++r) if (t[352 + r] && t[352 + r] < s0) s0 = t[352 + r];
             fprintf(stderr, "[ndt controller] pass 2 cycles: contraction %llu, ctl_pre %llu, LU solve %llu, post-newton %llu, trig + tables %llu\n",
                     t[321] - t[320], t[322] - t[321], t[323] - t[322], t[324] - t[323], t[325] - t[324]);
             for (int r = 0; r < C; ++r) {
-                fprintf(stderr, "[ndt warps] cta %2d start %5llu | drained", r, t[128 + r * 16 + 12] - s0);
-                for (int w = 0; w < NDT_NCW; ++w) fprintf(stderr, " %5llu", t[128 + r * 16 + w] - s0);
+                fprintf(stderr, "[ndt warps] cta %2d start %5llu | drained", r, t[352 + r] - s0);
+                const int ncw = wide ? NDT_NCW_WIDE : NDT_NCW;
+                for (int w = 0; w < ncw; ++w) fprintf(stderr, " %5llu", t[128 + r * 16 + w] - s0);
                 fprintf(stderr, " | search finished");
-                for (int w = NDT_NCW; w < NDT_WARPS; ++w) fprintf(stderr, " %5llu", t[128 + r * 16 + w] - s0);
+                for (int w = ncw; w < ncw + NDT_NSW; ++w) fprintf(stderr, " %5llu", t[128 + r * 16 + w] - s0);
                 fprintf(stderr, "\n");
             }
         }
