@@ -645,6 +645,7 @@ struct NdtSmem {
     uint32_t pass_dead[NDT_NSW][PASS_RING];// batch kernel: "pass" p is only the marker that its slot has no more work
     float4 ring[NDT_NSW][RING];    // (source point x, y, z, leaf index): consumers never touch the source cloud
     float4 stage[NDT_NSW][192];    // per search warp, three slots: [lane] source point, [32 + lane] transformed point
+    uint32_t cur_slot[NDT_NCW_WIDE];   // per compute warp: the slot whose pass it is draining
 };
 
 template <int THREADS>
@@ -1221,14 +1222,12 @@ struct DrainState {
 // Returns false when the "pass" was the marker of a dead slot (batch kernel).  The pass description (ctl.T, ctl.ang,
 // ctl.hess) is read only once the producers have delivered data or finished, i.e. after its request was published.
 template <int NCW>
-__device__ __forceinline__ bool compute_drain(NdtSmem &S, const GridView &G, const NdtConst &K, const Ctl &ctl, int warp, int lane,
+__device__ __forceinline__ bool compute_drain(NdtSmem &S, const GridView &G, const NdtConst &K, int warp, int lane,
                                               DrainState &ds, double *__restrict__ part) {
     constexpr int PPC = NDT_NSW / NCW;             // producers per compute warp (<= NDT_PPC, the size of ds.cpos)
     static_assert(NCW >= NDT_NCW && NDT_NSW % NCW == 0, "compute warps per CTA");
     ++ds.pass_id;
-    const float *T = ctl.T;
     bool hess = false, have_desc = false, slot_dead = false;
-    const AngTab &ang = ctl.ang;
     double acc[NACC];
 #pragma unroll
     for (int i = 0; i < NACC; ++i) acc[i] = 0.0;
@@ -1273,6 +1272,12 @@ __device__ __forceinline__ bool compute_drain(NdtSmem &S, const GridView &G, con
                 if (n & 0x40000000u) slot_dead = true;
                 n &= 0x3fffffffu;
                 __threadfence_block();
+                // The slot whose pass this is comes from shared memory (cur_slot, set by the caller), chunk by chunk: kept in a
+                // register across this loop it was spilled, and the reload -- a local-memory load that misses the L1 the list
+                // and record streams run through -- stalled every chunk for an L2 round trip (9 % of the compute warps' time).
+                const Ctl &ctl = S.slot[ld_vol(&S.cur_slot[warp])].ctl;
+                const float *T = ctl.T;
+                const AngTab &ang = ctl.ang;
                 if (!have_desc) { hess = ctl.hess != 0; have_desc = true; }
                 if ((uint32_t)lane < n) {
                     const float4 e = S.ring[sw][(pos + lane) & (RING - 1u)];
@@ -1370,12 +1375,14 @@ __global__ void __launch_bounds__((NCW + NDT_NSW) * 32, (NCW > NDT_NCW) ? 1 : ND
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(NDT_REG_COMPUTE));
         int parity = 0;
+        if (lane == 0) st_vol(&S.cur_slot[warp], 0u);
+        __syncwarp();
         DrainState ds;
 #pragma unroll
         for (int k = 0; k < NDT_PPC; ++k) ds.cpos[k] = 0;
         ds.pass_id = 0;
         while (true) {
-            (void)compute_drain<NCW>(S, G, K, SL.ctl, warp, lane, ds, SL.warp_part[warp]);
+            (void)compute_drain<NCW>(S, G, K, warp, lane, ds, SL.warp_part[warp]);
             TRC(2);
 #ifdef NDT_TIMING
             if (A.timing && match == 0 && trc_pass == 2 && lane == 0) { unsigned long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); A.timing[128 + crank * 16 + warp] = g; }
@@ -1585,7 +1592,9 @@ __global__ void __launch_bounds__(NDT_THREADS, NDT_MIN_CTAS) ndt_batch_kernel(Gr
                 cnt_pack = (cnt_pack & ~(0xFu << (4 * s))) | ((((cnt_pack >> (4 * s)) + 1u) & 0xFu) << (4 * s));
                 const uint32_t seen_s = (cnt_pack >> (4 * s)) & 0xFu;
                 Slot &SL = S.slot[s];
-                const bool live = compute_drain<NDT_NCW>(S, G, K, SL.ctl, warp, lane, ds, SL.warp_part[warp]);
+                if (lane == 0) st_vol(&S.cur_slot[warp], (uint32_t)s);
+                __syncwarp();
+                const bool live = compute_drain<NDT_NCW>(S, G, K, warp, lane, ds, SL.warp_part[warp]);
                 if (!live) { dead_mask |= 1u << s; continue; }
                 TMB_LAP(1);                                    // [1] draining (incl. waiting for chunks)
                 // the controller role of a slot rotates over the compute warps pass by pass (every warp knows the
