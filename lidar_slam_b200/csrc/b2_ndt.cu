@@ -648,6 +648,7 @@ struct NdtSmem {
     uint32_t cur_slot[NDT_NCW_WIDE];   // per compute warp: the slot whose pass it is draining
 };
 
+static_assert(sizeof(NdtSmem) <= (233472 / NDT_MIN_CTAS) - 1024, "NDT_MIN_CTAS CTAs per SM no longer fit the 228 KB of shared memory");
 template <int THREADS>
 __device__ __forceinline__ void cta_barrier() { asm volatile("bar.sync 0, %0;" ::"n"(THREADS) : "memory"); }
 __device__ __forceinline__ uint32_t ld_vol(const uint32_t *p) { return *reinterpret_cast<const volatile uint32_t *>(p); }
