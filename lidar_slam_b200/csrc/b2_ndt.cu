@@ -566,7 +566,13 @@ constexpr int NDT_NCW_WIDE = (NDT_NSW > NDT_NCW) ? NDT_NSW : NDT_NCW;
 #define NDT_RING 512
 #endif
 #ifndef NDT_DRAIN_SLEEP
-#define NDT_DRAIN_SLEEP 32
+#define NDT_DRAIN_SLEEP 128     // ns between two looks of a compute warp at an empty ring
+#endif
+#ifndef NDT_ROOM_SLEEP
+#define NDT_ROOM_SLEEP 256     // ns between two looks at the consumer position while a search warp's ring is full
+#endif
+#ifndef NDT_MBAR_HINT
+#define NDT_MBAR_HINT 1000     // ns: suspend-time hint of the pass-request wait (0: the hardware's default time limit)
 #endif
 constexpr uint32_t RING = NDT_RING;            // ring entries per search warp (power of two, >= 128 + 32)
 static_assert(NDT_NCW % 4 == 0 && NDT_NSW % 4 == 0 && NDT_NSW % NDT_NCW == 0, "warp-group multiples");
@@ -961,8 +967,8 @@ __device__ __forceinline__ void search_pass(NdtSmem &S, const GridView &G, const
             if (NDT_POLL_ALL || lane == 0) {
                 hd = ld_vol(&S.head[sw]);
                 while (my_tail - hd > RING - need) {
-#if NDT_DRAIN_SLEEP > 0
-                    __nanosleep(64);
+#if NDT_ROOM_SLEEP > 0
+                    __nanosleep(NDT_ROOM_SLEEP);
 #endif
                     hd = ld_vol(&S.head[sw]);
                 }
@@ -1472,10 +1478,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     asm volatile(
         "{\n\t.reg .pred p;\n"
         "B2_MBAR_WAIT:\n\t"
+#if NDT_MBAR_HINT > 0
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+#else
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+#endif
         "@p bra B2_MBAR_DONE;\n\t"
         "bra B2_MBAR_WAIT;\n"
-        "B2_MBAR_DONE:\n\t}" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+        "B2_MBAR_DONE:\n\t}" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(parity), "r"((uint32_t)NDT_MBAR_HINT) : "memory");
 }
 
 __global__ void __launch_bounds__(NDT_THREADS, NDT_MIN_CTAS) ndt_batch_kernel(GridView G, NdtConst K, MatchArgs A, uint32_t B,
