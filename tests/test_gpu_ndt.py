@@ -296,7 +296,7 @@ def test_result_cloud_filled_on_device_equals_host_transform(setup, scans):
     assert np.all(buf[:, 5:] == 0.0)
 
 
-def test_cluster_widths_agree(oracle, setup, scans):
+def test_cluster_widths_agree(oracle, setup, scans, small_map):
     reg, grid, prm, srcs = setup
     truth, _ = scans[1]
     guess = synth.pose6_to_matrix(truth + np.array([0.3, -0.2, 0.1, 0.01, 0.01, -0.02])).astype(np.float32)
@@ -312,6 +312,19 @@ def test_cluster_widths_agree(oracle, setup, scans):
     ok, _, p1 = reg.ScanMatch(srcs[1], guess, want_cloud=False)
     ok, _, p2 = reg.ScanMatch(srcs[1], guess, want_cloud=False)
     assert np.array_equal(p1, p2)
+    # the two CTA shapes of ndt_match_kernel: a launch with at most one CTA per SM runs 8 compute + 8 search warps per CTA
+    # (<8>), B2NDT_WIDE_SINGLE=0 (read when a handle is created) keeps the 4 + 8 shape (<4>) that larger launches use
+    os.environ["B2NDT_WIDE_SINGLE"] = "0"
+    try:
+        narrow = NDTRegistration(1.0, 0.1, 0.01, 30)
+    finally:
+        del os.environ["B2NDT_WIDE_SINGLE"]
+    narrow.SetInputTarget(small_map)
+    for C_ in (1, 8, 11):
+        narrow.SetCluster(C_, 1)
+        ok, _, pose = narrow.ScanMatch(srcs[1], guess, want_cloud=False)
+        assert ok and narrow.last_result["iterations"] == res[0][1] and np.max(np.abs(pose - res[0][0])) <= 1e-6
+        assert narrow.last_result["pairs"] == reg.last_result["pairs"]
 
 
 def test_more_thuente_enabled_matches_oracle(oracle, small_map, scans):
