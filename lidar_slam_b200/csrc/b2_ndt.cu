@@ -2327,6 +2327,13 @@ static int launch_match(b2ndt *h, const MatchArgs &A, size_t B, int C) {
 #endif
     cudaError_t e = wide ? cudaLaunchKernelEx(&cfg, ndt_match_kernel<NDT_NCW_WIDE>, G, K, Ac)
                          : cudaLaunchKernelEx(&cfg, ndt_match_kernel<NDT_NCW>, G, K, Ac);
+    if (wide && e != cudaSuccess) {
+        // the wide shape needs a whole SM per CTA: when such a cluster cannot be placed (SMs held by other work), take the
+        // shape that shares an SM
+        cudaGetLastError();
+        cfg.blockDim = dim3(NDT_THREADS);
+        e = cudaLaunchKernelEx(&cfg, ndt_match_kernel<NDT_NCW>, G, K, Ac);
+    }
     b2::count_launch();
     if (e != cudaSuccess) { set_error("ndt_match_kernel launch failed: %s", cudaGetErrorString(e)); return B2_ERR_CUDA; }
 #ifdef NDT_TIMING
