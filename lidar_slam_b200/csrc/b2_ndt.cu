@@ -1786,6 +1786,7 @@ struct b2ndt {
     PinBuf h_ready;
     bool stream_batches = true;            // B2NDT_STREAM=0: copy everything, then launch
     bool small_batch_clusters = true;      // B2NDT_SMALL_BATCH=0: never widen the matches of a small batch to clusters
+    bool zero_copy_small = true;           // B2NDT_ZERO_COPY=0: guesses / results of small launches through copy operations (A/B runs)
     bool wide_single = true;               // B2NDT_WIDE_SINGLE=0: launches that fit one CTA per SM keep the 4 + 8 warp shape (A/B runs)
 };
 
@@ -1835,6 +1836,7 @@ extern "C" int b2ndt_create(const b2ndt_params *p, int device, b2ndt **out) {
     if (const char *e = getenv("B2NDT_STREAM")) h->stream_batches = atoi(e) != 0;
     if (const char *e = getenv("B2NDT_SMALL_BATCH")) h->small_batch_clusters = atoi(e) != 0;
     if (const char *e = getenv("B2NDT_WIDE_SINGLE")) h->wide_single = atoi(e) != 0;
+    if (const char *e = getenv("B2NDT_ZERO_COPY")) h->zero_copy_small = atoi(e) != 0;
     *out = h;
     return 0;
 }
@@ -2410,7 +2412,11 @@ static int align_host(b2ndt *h, const void *src, size_t n_total, size_t stride, 
     const size_t src_stage = direct ? 0 : n_total * 16;
     float *gst = (float *)(stage + src_stage);
     memcpy(gst, guesses, B * 64);
-    B2_CUDA(cudaMemcpyAsync(h->d_guess.p, gst, B * 64, cudaMemcpyHostToDevice, h->st));
+    // A handful of matches (a single ScanMatch above all): the kernel reads the guesses from, and writes poses + results
+    // to, PINNED HOST memory directly (unified addressing: 64 B read + ~170 B written per match over PCIe) instead of
+    // one H2D and two D2H copy operations around it, each of which costs more than the kernel-side access.
+    const bool zero_copy = (B <= 16) && h->zero_copy_small;
+    if (!zero_copy) B2_CUDA(cudaMemcpyAsync(h->d_guess.p, gst, B * 64, cudaMemcpyHostToDevice, h->st));
     const uint32_t *d_off = nullptr;
     if (offsets) {
         if ((rc = h->d_off.reserve((B + 1) * 4))) return rc;
@@ -2504,11 +2510,18 @@ static int align_host(b2ndt *h, const void *src, size_t n_total, size_t stride, 
         A.src = h->d_src.as<float4>(); A.offsets = d_off ? d_off + c0 : nullptr; A.n_shared = (uint32_t)n_total;
         A.guesses = h->d_guess.as<float>() + c0 * 16; A.poses_out = h->d_pose.as<float>() + c0 * 16;
         A.results = h->d_res.as<b2ndt_result>() + c0;
+        if (zero_copy) {
+            A.guesses = gst + c0 * 16;
+            A.poses_out = h->h_res.as<float>() + c0 * 16;
+            A.results = reinterpret_cast<b2ndt_result *>(h->h_res.as<char>() + B * 64) + c0;
+        }
         if ((rc = launch_match(h, A, c1 - c0, C))) return rc;
     }
     char *hres = h->h_res.as<char>();
-    B2_CUDA(cudaMemcpyAsync(hres, h->d_pose.p, B * 64, cudaMemcpyDeviceToHost, h->st));
-    B2_CUDA(cudaMemcpyAsync(hres + B * 64, h->d_res.p, B * sizeof(b2ndt_result), cudaMemcpyDeviceToHost, h->st));
+    if (!zero_copy) {
+        B2_CUDA(cudaMemcpyAsync(hres, h->d_pose.p, B * 64, cudaMemcpyDeviceToHost, h->st));
+        B2_CUDA(cudaMemcpyAsync(hres + B * 64, h->d_res.p, B * sizeof(b2ndt_result), cudaMemcpyDeviceToHost, h->st));
+    }
     B2_CUDA(cudaStreamSynchronize(h->st));
     memcpy(poses_out, hres, B * 64);
     if (res) memcpy(res, hres + B * 64, B * sizeof(b2ndt_result));
