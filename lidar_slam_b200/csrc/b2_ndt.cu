@@ -519,7 +519,9 @@ __global__ void __launch_bounds__(NBR_TPB) nbr_fill_kernel(uint2 *__restrict__ h
 // The whole Newton / More-Thuente loop of a match runs inside a kernel (no host round trip per iteration).  Two
 // kernels share the same building blocks (search_pass, compute_drain, controller_step, below):
 //   ndt_batch_kernel  batches: persistent CTAs, NDT_SLOTS matches in flight per CTA, work fetched from a counter;
-//   ndt_match_kernel  a single ScanMatch / the derivatives-only entry: one thread-block cluster (1..16 CTAs) per match.
+//   ndt_match_kernel  a single ScanMatch / the derivatives-only entry: one thread-block cluster (1..16 CTAs) per match,
+//                     in two CTA shapes (<NDT_NCW> = 4 compute + 8 search warps, two CTAs per SM; <NDT_NCW_WIDE> = 8 + 8,
+//                     one CTA per SM, for launches with at most one CTA per SM).
 // Every CTA is WARP-SPECIALISED (producer / consumer, registers re-balanced with setmaxnreg):
 //   search warps  (NDT_NSW, 56 registers): lane = source point.  Float transform, ONE 8-byte neighbour-list header
 //     per query, then the warp walks the concatenation of its 32 lists (coalesced 16-byte entries {centroid, leaf},
@@ -1220,7 +1222,7 @@ __device__ __forceinline__ void warp_reduce_acc(const double (&acc)[NACC], const
 
 // ---------------------------------------------------------------- compute warps (consumers) ----
 // Drain one pass from this compute warp's rings: lane = (point, voxel) pair, fixed round-robin over the
-// producers, 32 pairs at a time; the warp's partial sums (butterfly, fixed order) go to `part`.
+// producers, 32 pairs at a time; the warp's partial sums (warp_reduce_acc: the butterfly tree, fixed order) go to `part`.
 struct DrainState {
     uint32_t cpos[NDT_PPC];    // entries consumed per producer
     uint32_t pass_id;          // passes drained so far
