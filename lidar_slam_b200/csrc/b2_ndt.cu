@@ -1671,6 +1671,7 @@ struct PoseArg { float T[16]; };
 constexpr int FIT_THREADS = 128;
 constexpr int FIT_WARPS = FIT_THREADS / 32;
 constexpr int FIT_RMAX = 8;
+constexpr int FIT_U = 4;        // groups of 32 window cells whose loads are in flight together
 
 __device__ __forceinline__ float warp_min(float v) {
 #pragma unroll
@@ -1680,7 +1681,7 @@ __device__ __forceinline__ float warp_min(float v) {
 
 // One WARP per source point: the ring walk is warp-uniform (all lanes share the query), the points of every
 // bucket are split over the lanes, and the minimum is exact whatever the split (min is order independent).
-__global__ void __launch_bounds__(FIT_THREADS) fitness_kernel(FitView F, const float4 *__restrict__ src, uint32_t n, PoseArg P,
+__global__ void __launch_bounds__(FIT_THREADS, 8) fitness_kernel(FitView F, const float4 *__restrict__ src, uint32_t n, PoseArg P,
                                                               double max_range, double *__restrict__ part_sum,
                                                               unsigned long long *__restrict__ part_cnt) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1701,32 +1702,69 @@ __global__ void __launch_bounds__(FIT_THREADS) fitness_kernel(FitView F, const f
         // records and bucket descriptors are fetched in parallel; only occupied buckets are then scanned, their
         // points split over the lanes
         for (int r = 1; r <= FIT_RMAX && !done; ++r) {
-            const int side = 2 * r + 1, cube = side * side * side;
-            for (int c0 = 0; c0 < cube; c0 += 32) {
-                const int c = c0 + lane;
-                uint32_t bs = 0, bn = 0;
-                if (c < cube) {
-                    const int dx = c % side - r, dy = (c / side) % side - r, dz = c / (side * side) - r;
-                    const bool shell = (r == 1) || (abs(dx) == r) || (abs(dy) == r) || (abs(dz) == r);
-                    const int kx = cx + dx, ky = cy + dy, kz = cz + dz;
-                    if (shell && kx >= 0 && ky >= 0 && kz >= 0 && kx < F.div_b[0] && ky < F.div_b[1] && kz < F.div_b[2]) {
-                        const int32_t v = __float_as_int(__ldg(F.cells + (size_t)kx + (size_t)ky * F.mul[1] + (size_t)kz * F.mul[2]).w);
-                        if (v != 0) {
-                            const int j = (v > 0 ? v : -v) - 1;
-                            bs = __ldg(&F.leaf_start[j]);
-                            bn = (uint32_t)__ldg(&F.leaf_n[j]);
+            // The cells of shell r, enumerated without the interior the previous shells covered and without the layers
+            // above / below the grid (a street map is a few cells high: most of a large cube lies outside it): the
+            // (2r-1) interior layers contribute their perimeter ring of 8r cells each, the two face layers dz = -r, +r
+            // their whole (2r+1)^2 square.  r = 1 is the full 3x3x3 block.
+            const int side = 2 * r + 1, ring = 8 * r, sq = side * side;
+            int zlo = -(r - 1), zhi = r - 1;
+            if (zlo < -cz) zlo = -cz;
+            if (zhi > F.div_b[2] - 1 - cz) zhi = F.div_b[2] - 1 - cz;
+            const int nzi = (r == 1) ? 0 : ((zhi >= zlo) ? zhi - zlo + 1 : 0);
+            const bool f_lo = (r > 1) && (cz - r >= 0) && (cz - r < F.div_b[2]), f_hi = (r > 1) && (cz + r >= 0) && (cz + r < F.div_b[2]);
+            const int n_ring = nzi * ring;
+            const int total = (r == 1) ? 27 : n_ring + ((int)f_lo + (int)f_hi) * sq;
+            // FIT_U groups of 32 cells per step: their cell records, then their bucket descriptors, are independent loads in
+            // flight together (a query far from every target point walks all 8 shells, and the two dependent L2 round
+            // trips per group of 32 cells were what the slowest query, i.e. the kernel, took: ~110 us)
+            for (int c0 = 0; c0 < total; c0 += 32 * FIT_U) {
+                uint32_t bs[FIT_U], bn[FIT_U];
+                int32_t code[FIT_U];
+#pragma unroll
+                for (int u = 0; u < FIT_U; ++u) {
+                    const int c = c0 + u * 32 + lane;
+                    bs[u] = 0; bn[u] = 0; code[u] = 0;
+                    if (c < total) {
+                        int dx, dy, dz;
+                        if (r == 1) {
+                            dx = c % 3 - 1; dy = (c / 3) % 3 - 1; dz = c / 9 - 1;
+                        } else if (c < n_ring) {
+                            const int layer = c / ring, t = c - layer * ring;
+                            dz = zlo + layer;
+                            if (t < side) { dy = -r; dx = t - r; }
+                            else if (t < 2 * side) { dy = r; dx = t - side - r; }
+                            else if (t < 3 * side - 2) { dx = -r; dy = t - 2 * side - r + 1; }
+                            else { dx = r; dy = t - (3 * side - 2) - r + 1; }
+                        } else {
+                            const int o = c - n_ring, f = o / sq, q = o - f * sq;
+                            dz = (f == 0 && f_lo) ? -r : r;
+                            dx = q % side - r; dy = q / side - r;
                         }
+                        const int kx = cx + dx, ky = cy + dy, kz = cz + dz;
+                        if (kx >= 0 && ky >= 0 && kz >= 0 && kx < F.div_b[0] && ky < F.div_b[1] && kz < F.div_b[2])
+                            code[u] = __float_as_int(__ldg(F.cells + (size_t)kx + (size_t)ky * F.mul[1] + (size_t)kz * F.mul[2]).w);
                     }
                 }
-                uint32_t occ = __ballot_sync(0xffffffffu, bn != 0u);
-                while (occ) {
-                    const int src_lane = __ffs(occ) - 1;
-                    occ &= occ - 1u;
-                    const uint32_t s0 = __shfl_sync(0xffffffffu, bs, src_lane), n0 = __shfl_sync(0xffffffffu, bn, src_lane);
-                    for (uint32_t k = s0 + lane; k < s0 + n0; k += 32u) {
-                        const float4 p = __ldg(&F.pts_sorted[k]);
-                        const float dx = __fsub_rn(qx, p.x), dy = __fsub_rn(qy, p.y), dz = __fsub_rn(qz, p.z);
-                        best = fminf(best, __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+#pragma unroll
+                for (int u = 0; u < FIT_U; ++u) {
+                    if (code[u] != 0) {
+                        const int j = (code[u] > 0 ? code[u] : -code[u]) - 1;
+                        bs[u] = __ldg(&F.leaf_start[j]);
+                        bn[u] = (uint32_t)__ldg(&F.leaf_n[j]);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < FIT_U; ++u) {
+                    uint32_t occ = __ballot_sync(0xffffffffu, bn[u] != 0u);
+                    while (occ) {
+                        const int src_lane = __ffs(occ) - 1;
+                        occ &= occ - 1u;
+                        const uint32_t s0 = __shfl_sync(0xffffffffu, bs[u], src_lane), n0 = __shfl_sync(0xffffffffu, bn[u], src_lane);
+                        for (uint32_t k = s0 + lane; k < s0 + n0; k += 32u) {
+                            const float4 p = __ldg(&F.pts_sorted[k]);
+                            const float dx = __fsub_rn(qx, p.x), dy = __fsub_rn(qy, p.y), dz = __fsub_rn(qz, p.z);
+                            best = fminf(best, __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+                        }
                     }
                 }
             }
