@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -40,6 +41,31 @@ inline void count_launch(uint64_t n = 1) { g_launches.fetch_add(n, std::memory_o
             return B2_ERR_CUDA;                                                               \
         }                                                                                     \
     } while (0)
+
+// Programmatic dependent launch for chains of small dependent kernels (voxel pipeline, target build): a kernel launched
+// through launch_chain() may have its CTAs placed while the kernel before it in the stream is still draining; every such
+// kernel starts with chain_sync() -- griddepcontrol.wait returns once the previous kernel has completed and its memory is
+// visible -- BEFORE its first global-memory access, so only the launch latency overlaps, never the data.  (In a kernel
+// launched the ordinary way the two instructions do nothing.)  B2_PDL=0 in the environment launches the ordinary way.
+__device__ __forceinline__ void chain_sync() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+inline bool chain_enabled() {
+    static const bool on = [] { const char *e = getenv("B2_PDL"); return !(e && atoi(e) == 0); }();
+    return on;
+}
+template <typename... KArgs, typename... Args>
+inline void launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = chain_enabled() ? 1 : 0;
+    (void)cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);      // the error, if any, is picked up by B2_LAUNCH_CHECK
+}
 
 // growable device / pinned buffers (never shrink; reused across calls).  Device memory comes from the device's
 // stream-ordered pool (cudaMallocAsync) with an unlimited release threshold: a buffer that has to grow -- the local

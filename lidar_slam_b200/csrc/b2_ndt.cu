@@ -191,6 +191,7 @@ __global__ void __launch_bounds__(LCROWD_THREADS) leaf_crowded_kernel(const floa
                                                                       uint32_t n_finite, LeafOut O,
                                                                       const uint32_t *__restrict__ crowded,
                                                                       const uint32_t *__restrict__ n_crowded, LeafUpd U) {
+    chain_sync();
     const uint32_t n = *n_crowded;
     const uint32_t *__restrict__ keys = sv.keys();
     const uint32_t *__restrict__ vals = sv.vals();
@@ -322,6 +323,7 @@ __global__ void __launch_bounds__(128) leaf_finish_kernel(uint32_t V, int min_pt
                                                           uint32_t *__restrict__ active, const uint32_t *__restrict__ list) {
     // list != NULL (incremental update): V entries of `list` name the leaves to finish, and the neighbour-list
     // accounting is left to nbr_count_kernel (it has to be redone over ALL leaves)
+    chain_sync();
     uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= V) return;
     const bool account = (list == nullptr);
@@ -469,6 +471,7 @@ __global__ void __launch_bounds__(NBR_TPB) nbr_fill_kernel(uint2 *__restrict__ h
                                                            uint32_t *__restrict__ counters,
                                                            const uint32_t *__restrict__ active, LayoutArg LA,
                                                            float4 *__restrict__ list) {
+    chain_sync();
     const uint32_t n = counters[3];
     const int dx_n = LA.div_b[0], dy_n = LA.div_b[1], dz_n = LA.div_b[2];
     const int lane = threadIdx.x & 31;
@@ -1996,15 +1999,15 @@ static int build_target(b2ndt *h, const float4 *d_pts, size_t n, int nbits_hint)
         if (blocks > 148 * 16) blocks = 148 * 16;
         leaf_stats_kernel<false><<<blocks, 256, 0, h->st>>>(d_pts, h->pipe.view(), h->pipe.run_start(), V, t.L.n_finite, O, crowded, cnt + 5, U);
         B2_LAUNCH_CHECK();
-        leaf_crowded_kernel<false><<<148 * 8, LCROWD_THREADS, 0, h->st>>>(d_pts, h->pipe.view(), h->pipe.run_start(), V, t.L.n_finite, O, crowded, cnt + 5, U);
+        launch_chain(leaf_crowded_kernel<false>, 148 * 8, LCROWD_THREADS, 0, h->st, d_pts, h->pipe.view(), h->pipe.run_start(), V, t.L.n_finite, O, crowded, cnt + 5, U);
         B2_LAUNCH_CHECK();
-        leaf_finish_kernel<<<(V + 127) / 128, 128, 0, h->st>>>(V, h->prm.min_pts, h->prm.eig_mult, LA, t.leaf_idx.as<int32_t>(),
-                                                              t.leaf_n.as<int32_t>(), t.centroid4.as<float4>(), t.sums.as<double>(),
-                                                              t.gauss.as<double>(), t.icov9.as<double>(), t.cells.as<float4>(),
-                                                              t.nbr_head.as<uint2>(), cnt, active, nullptr);
+        launch_chain(leaf_finish_kernel, (V + 127) / 128, 128, 0, h->st, V, h->prm.min_pts, h->prm.eig_mult, LA, t.leaf_idx.as<int32_t>(),
+                     t.leaf_n.as<int32_t>(), t.centroid4.as<float4>(), t.sums.as<double>(),
+                     t.gauss.as<double>(), t.icov9.as<double>(), t.cells.as<float4>(),
+                     t.nbr_head.as<uint2>(), cnt, active, (const uint32_t *)nullptr);
         B2_LAUNCH_CHECK();
         // neighbour lists of the listed cells
-        nbr_fill_kernel<<<148 * 8, NBR_TPB, 0, h->st>>>(t.nbr_head.as<uint2>(), t.cells.as<float4>(), cnt, active, LA, t.nbr_list.as<float4>());
+        launch_chain(nbr_fill_kernel, 148 * 8, NBR_TPB, 0, h->st, t.nbr_head.as<uint2>(), t.cells.as<float4>(), cnt, active, LA, t.nbr_list.as<float4>());
         B2_LAUNCH_CHECK();
     }
     B2_CUDA(cudaMemcpyAsync(misc, t.counters.p, 32, cudaMemcpyDeviceToHost, h->st));

@@ -271,6 +271,7 @@ __global__ void __launch_bounds__(SORT_THREADS) key_hist_kernel(const float4 *__
                                                                 const VoxLayout *__restrict__ layouts, uint32_t *__restrict__ keys,
                                                                 uint32_t *__restrict__ hist, uint32_t *__restrict__ state,
                                                                 const uint32_t *__restrict__ scalars) {
+    chain_sync();
     const TileDesc t = get_tile(P, blockIdx.x);
     __shared__ VoxLayout L;
     __shared__ uint32_t h[4][RADIX];
@@ -318,6 +319,7 @@ template <int ITEMS>
 __global__ void __launch_bounds__(SORT_THREADS, (ITEMS > 8 ? 3 : 4)) onesweep_kernel(SortView sv, PlanView P, const uint32_t *__restrict__ hist,
                                                                 uint32_t *__restrict__ state, uint32_t *__restrict__ ticket,
                                                                 int pass) {
+    chain_sync();
     const int shift = pass * RADIX_BITS;
     if ((uint32_t)shift >= __ldg(&sv.scalars[0])) return;
     const bool odd = (pass & 1) != 0;
@@ -454,6 +456,7 @@ __global__ void __launch_bounds__(SORT_THREADS) runs_kernel(SortView sv, PlanVie
                                                             uint32_t *__restrict__ state, uint32_t *__restrict__ ticket,
                                                             uint32_t *__restrict__ run_start, uint32_t *__restrict__ run_seg,
                                                             uint32_t *__restrict__ run_seg_off, uint32_t *__restrict__ scalars) {
+    chain_sync();
     const uint32_t *__restrict__ keys = sv.keys();
     __shared__ uint32_t s_tile, s_ok, s_inv, s_excl;
     __shared__ uint32_t wsum[SORT_THREADS / 32 + 1];
@@ -627,17 +630,17 @@ int VoxPipeline::sort_and_runs(int npass_launch, cudaStream_t st) {
     const bool large = tile_elems == SORT_THREADS * SORT_ITEMS_LARGE;
     for (int p = 0; p < npass_launch; ++p) {
         uint32_t *stp = state + (size_t)p * nt * RADIX;
-        if (large) onesweep_kernel<SORT_ITEMS_LARGE><<<nt, SORT_THREADS, 0, st>>>(sv, P, d_hist.as<uint32_t>(), stp, sc + 4 + p, p);
-        else onesweep_kernel<SORT_ITEMS_SMALL><<<nt, SORT_THREADS, 0, st>>>(sv, P, d_hist.as<uint32_t>(), stp, sc + 4 + p, p);
+        if (large) launch_chain(onesweep_kernel<SORT_ITEMS_LARGE>, nt, SORT_THREADS, 0, st, sv, P, d_hist.as<uint32_t>(), stp, sc + 4 + p, p);
+        else launch_chain(onesweep_kernel<SORT_ITEMS_SMALL>, nt, SORT_THREADS, 0, st, sv, P, d_hist.as<uint32_t>(), stp, sc + 4 + p, p);
         B2_LAUNCH_CHECK();
     }
     uint32_t *str = state + (size_t)4 * nt * RADIX;
     if (large)
-        runs_kernel<SORT_ITEMS_LARGE><<<nt, SORT_THREADS, 0, st>>>(sv, P, layouts(), str, sc + 8, d_run_start.as<uint32_t>(),
-                                                                   d_run_seg.as<uint32_t>(), d_run_seg_off.as<uint32_t>(), sc);
+        launch_chain(runs_kernel<SORT_ITEMS_LARGE>, nt, SORT_THREADS, 0, st, sv, P, layouts(), str, sc + 8, d_run_start.as<uint32_t>(),
+                     d_run_seg.as<uint32_t>(), d_run_seg_off.as<uint32_t>(), sc);
     else
-        runs_kernel<SORT_ITEMS_SMALL><<<nt, SORT_THREADS, 0, st>>>(sv, P, layouts(), str, sc + 8, d_run_start.as<uint32_t>(),
-                                                                   d_run_seg.as<uint32_t>(), d_run_seg_off.as<uint32_t>(), sc);
+        launch_chain(runs_kernel<SORT_ITEMS_SMALL>, nt, SORT_THREADS, 0, st, sv, P, layouts(), str, sc + 8, d_run_start.as<uint32_t>(),
+                     d_run_seg.as<uint32_t>(), d_run_seg_off.as<uint32_t>(), sc);
     B2_LAUNCH_CHECK();
     return 0;
 }
@@ -657,8 +660,8 @@ static int run_pipeline(VoxPipeline &pp, const float4 *d_pts, float4 *d_pts_out,
     bbox_layout_kernel<Op><<<nt, SORT_THREADS, 0, st>>>(d_pts, d_pts_out, op, P, lx, ly, lz, pp.d_bbox_part.as<float>(), lay, sc,
                                                        pp.d_hist.as<uint32_t>(), nB * 4 * RADIX);
     B2_LAUNCH_CHECK();
-    key_hist_kernel<true><<<nt, SORT_THREADS, 0, st>>>(d_pts_out ? d_pts_out : d_pts, P, lay, pp.d_keys[0].as<uint32_t>(),
-                                                      pp.d_hist.as<uint32_t>(), pp.d_state.as<uint32_t>(), sc);
+    launch_chain(key_hist_kernel<true>, nt, SORT_THREADS, 0, st, (const float4 *)(d_pts_out ? d_pts_out : d_pts), P, lay, pp.d_keys[0].as<uint32_t>(),
+                 pp.d_hist.as<uint32_t>(), pp.d_state.as<uint32_t>(), sc);
     B2_LAUNCH_CHECK();
     int passes = 32 / RADIX_BITS;
     if (nbits_hint > 0) passes = (nbits_hint + RADIX_BITS - 1) / RADIX_BITS;
@@ -686,8 +689,8 @@ int VoxPipeline::run_prepared(uint32_t invalid_key, int nbits, cudaStream_t st) 
     prepared_layout_kernel<<<(nB * 4 * RADIX + 255) / 256 < 64 ? (nB * 4 * RADIX + 255) / 256 : 64, 256, 0, st>>>(
         lay, sc, d_hist.as<uint32_t>(), nB * 4 * RADIX, nB, invalid_key, nbits);
     B2_LAUNCH_CHECK();
-    key_hist_kernel<false><<<nt, SORT_THREADS, 0, st>>>(nullptr, P, lay, d_keys[0].as<uint32_t>(), d_hist.as<uint32_t>(),
-                                                       d_state.as<uint32_t>(), sc);
+    launch_chain(key_hist_kernel<false>, nt, SORT_THREADS, 0, st, (const float4 *)nullptr, P, lay, d_keys[0].as<uint32_t>(), d_hist.as<uint32_t>(),
+                 d_state.as<uint32_t>(), sc);
     B2_LAUNCH_CHECK();
     return sort_and_runs((nbits + RADIX_BITS - 1) / RADIX_BITS, st);
 }
@@ -790,6 +793,7 @@ __global__ void __launch_bounds__(CROWD_THREADS) vf_crowded_kernel(const float4 
                                                                    const uint32_t *__restrict__ out_base, uint32_t out_capacity,
                                                                    float4 *__restrict__ out, int32_t *__restrict__ out_idx,
                                                                    int32_t *__restrict__ out_cnt) {
+    chain_sync();
     const uint32_t n = *n_crowded;
     const uint32_t ob = out_base ? *out_base : 0u;
     if ((size_t)ob + sv.scalars[1] > (size_t)out_capacity) return;
@@ -967,9 +971,9 @@ static int vf_launch_centroids(b2vf *h, const float4 *d_in, float4 *d_out, int32
                                                  h->pipe.plan_view(), h->pipe.layouts(), h->d_crowded.as<uint32_t>(), ncr, d_out_base,
                                                  out_capacity, d_out, d_idx, d_cnt);
     B2_LAUNCH_CHECK();
-    vf_crowded_kernel<<<148 * 8, CROWD_THREADS, 0, h->st>>>(d_in, h->pipe.view(), h->pipe.run_start(), h->pipe.run_seg(), h->pipe.run_seg_off(),
-                                                 h->pipe.plan_view(), h->pipe.layouts(), h->d_crowded.as<uint32_t>(), ncr, d_out_base,
-                                                 out_capacity, d_out, d_idx, d_cnt);
+    launch_chain(vf_crowded_kernel, 148 * 8, CROWD_THREADS, 0, h->st, d_in, h->pipe.view(), h->pipe.run_start(), h->pipe.run_seg(), h->pipe.run_seg_off(),
+                 h->pipe.plan_view(), h->pipe.layouts(), h->d_crowded.as<uint32_t>(), ncr, d_out_base,
+                 out_capacity, d_out, d_idx, d_cnt);
     B2_LAUNCH_CHECK();
     return 0;
 }
