@@ -67,6 +67,7 @@ __global__ void __launch_bounds__(CROP_THREADS) crop_count_kernel(const float4 *
 
 // pass 2 (single CTA): exclusive scan of the tile counts in place; total -> tile_cnt[ntiles]
 __global__ void __launch_bounds__(1024) crop_scan_kernel(uint32_t *__restrict__ tile_cnt, uint32_t ntiles) {
+    chain_sync();
     __shared__ uint32_t wt[33];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     uint32_t base = 0;
@@ -98,6 +99,7 @@ __global__ void __launch_bounds__(1024) crop_scan_kernel(uint32_t *__restrict__ 
 template <class Op>
 __global__ void __launch_bounds__(CROP_THREADS) crop_scatter_kernel(const float4 *__restrict__ src, uint32_t n, Op B,
                                                                     const uint32_t *__restrict__ tile_off, float4 *__restrict__ dst) {
+    chain_sync();
     __shared__ uint32_t wcnt[CROP_THREADS / 32];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     uint32_t base = tile_off[blockIdx.x];
@@ -339,9 +341,9 @@ static int compact_cloud(const char *fn, b2cloud *src, b2cloud *dst, const Op &B
     float4 *out = in_place ? dst->alt.as<float4>() : dst->d();
     crop_count_kernel<<<ntiles, CROP_THREADS, 0, dst->st>>>(src->d(), (uint32_t)n, B, tiles);
     B2_LAUNCH_CHECK();
-    crop_scan_kernel<<<1, 1024, 0, dst->st>>>(tiles, ntiles);
+    launch_chain(crop_scan_kernel, 1, 1024, 0, dst->st, tiles, ntiles);
     B2_LAUNCH_CHECK();
-    crop_scatter_kernel<<<ntiles, CROP_THREADS, 0, dst->st>>>(src->d(), (uint32_t)n, B, tiles, out);
+    launch_chain(crop_scatter_kernel<Op>, ntiles, CROP_THREADS, 0, dst->st, (const float4 *)src->d(), (uint32_t)n, B, (const uint32_t *)tiles, out);
     B2_LAUNCH_CHECK();
     B2_CUDA(cudaMemcpyAsync(dst->h_small.p, tiles + ntiles, 4, cudaMemcpyDeviceToHost, dst->st));
     B2_CUDA(cudaStreamSynchronize(dst->st));

@@ -179,6 +179,7 @@ __global__ void __launch_bounds__(SORT_THREADS) bbox_layout_kernel(const float4 
                                                                    float lz, float *__restrict__ part,
                                                                    VoxLayout *__restrict__ layouts, uint32_t *__restrict__ scalars,
                                                                    uint32_t *__restrict__ hist, uint32_t hist_words) {
+    chain_sync();
     const TileDesc t = get_tile(P, blockIdx.x);
     float mn0 = FLT_MAX, mn1 = FLT_MAX, mn2 = FLT_MAX, mx0 = -FLT_MAX, mx1 = -FLT_MAX, mx2 = -FLT_MAX;
     uint32_t cnt = 0;
@@ -657,8 +658,8 @@ static int run_pipeline(VoxPipeline &pp, const float4 *d_pts, float4 *d_pts_out,
         return 0;
     }
     const PlanView P = pp.plan_view();
-    bbox_layout_kernel<Op><<<nt, SORT_THREADS, 0, st>>>(d_pts, d_pts_out, op, P, lx, ly, lz, pp.d_bbox_part.as<float>(), lay, sc,
-                                                       pp.d_hist.as<uint32_t>(), nB * 4 * RADIX);
+    launch_chain(bbox_layout_kernel<Op>, nt, SORT_THREADS, 0, st, d_pts, d_pts_out, op, P, lx, ly, lz, pp.d_bbox_part.as<float>(), lay, sc,
+                 pp.d_hist.as<uint32_t>(), nB * 4 * RADIX);
     B2_LAUNCH_CHECK();
     launch_chain(key_hist_kernel<true>, nt, SORT_THREADS, 0, st, (const float4 *)(d_pts_out ? d_pts_out : d_pts), P, lay, pp.d_keys[0].as<uint32_t>(),
                  pp.d_hist.as<uint32_t>(), pp.d_state.as<uint32_t>(), sc);
@@ -730,6 +731,7 @@ __global__ void __launch_bounds__(256) vf_centroid_kernel(const float4 *__restri
                                                           uint32_t out_capacity,
                                                           float4 *__restrict__ out, int32_t *__restrict__ out_idx,
                                                           int32_t *__restrict__ out_cnt) {
+    chain_sync();
     const uint32_t total = sv.scalars[1];
     // append mode (batched ingest): the output starts at the cursor another call left on the device; a batch that
     // would not fit is dropped as a whole (vf_append_kernel raises the overflow flag)
@@ -967,9 +969,9 @@ static int vf_launch_centroids(b2vf *h, const float4 *d_in, float4 *d_out, int32
     if (blocks < 148) blocks = 148;
     if (blocks > 148 * 16) blocks = 148 * 16;
     uint32_t *ncr = const_cast<uint32_t *>(h->pipe.scalars()) + 10;
-    vf_centroid_kernel<<<blocks, 256, 0, h->st>>>(d_in, h->pipe.view(), h->pipe.run_start(), h->pipe.run_seg(), h->pipe.run_seg_off(),
-                                                 h->pipe.plan_view(), h->pipe.layouts(), h->d_crowded.as<uint32_t>(), ncr, d_out_base,
-                                                 out_capacity, d_out, d_idx, d_cnt);
+    launch_chain(vf_centroid_kernel, blocks, 256, 0, h->st, d_in, h->pipe.view(), h->pipe.run_start(), h->pipe.run_seg(), h->pipe.run_seg_off(),
+                 h->pipe.plan_view(), h->pipe.layouts(), h->d_crowded.as<uint32_t>(), ncr, d_out_base,
+                 out_capacity, d_out, d_idx, d_cnt);
     B2_LAUNCH_CHECK();
     launch_chain(vf_crowded_kernel, 148 * 8, CROWD_THREADS, 0, h->st, d_in, h->pipe.view(), h->pipe.run_start(), h->pipe.run_seg(), h->pipe.run_seg_off(),
                  h->pipe.plan_view(), h->pipe.layouts(), h->d_crowded.as<uint32_t>(), ncr, d_out_base,
