@@ -1032,6 +1032,16 @@ __device__ __forceinline__ void search_pass(NdtSmem &S, const GridView &G, const
             prepare(b0, load_pt(b0), 0, off, cnt);
             prepare(b0 + stride, load_pt(b0 + stride), 1, off_1, cnt_1);
             float4 pt_3 = load_pt(b0 + 2u * stride);
+#if NDT_LPF
+            // the FIRST round of the pass has no predecessor that pulls its list lines in: pull them all now, so that the walk
+            // pays one L2 round trip for the round instead of one per 64-entry step (a single match gives every search warp
+            // exactly one round: 7 steps, i.e. most of its search time)
+            if (cnt != IRREGULAR) {
+                const float4 *lp = G.nbr_list + off;
+                for (uint32_t k = 0; k < cnt; k += 8u) asm volatile("prefetch.global.L1 [%0];" ::"l"(lp + k));
+                if (cnt) asm volatile("prefetch.global.L1 [%0];" ::"l"(lp + cnt - 1u));
+            }
+#endif
             int slot = 0;
             for (uint32_t base = b0; base < last; base += stride, slot = (slot == 2) ? 0 : slot + 1) {
                 __syncwarp();
