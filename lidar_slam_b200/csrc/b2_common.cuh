@@ -64,7 +64,13 @@ inline void launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = chain_enabled() ? 1 : 0;
-    (void)cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);      // the error, if any, is picked up by B2_LAUNCH_CHECK
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+    if (e != cudaSuccess && cfg.numAttrs) {        // an attribute the driver refuses: launch the ordinary way
+        cudaGetLastError();
+        cfg.numAttrs = 0;
+        e = cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+    }
+    (void)e;                                       // an error left standing is picked up by B2_LAUNCH_CHECK (cudaGetLastError)
 }
 
 // growable device / pinned buffers (never shrink; reused across calls).  Device memory comes from the device's
